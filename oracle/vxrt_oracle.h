@@ -1,0 +1,89 @@
+/*
+ * vxrt_oracle.h — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A CPU restatement of the reference's GLSL hot path (swr06/VoxelTracing, Core/Shaders/*).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (voxeltracing_b200/libvxrt_cuda.so) never links or calls it.
+ *
+ * Parity pinning: the reference has no tests and no golden vectors.  The
+ * oracle is pinned against the reference's own shader sources compiled for the CPU through a
+ * GLSL-as-C++ shim (oracle/_ref, built by oracle/build_ref.py when /root/reference is mounted)
+ * and against golden fixtures generated from that build (tests/golden/).
+ *
+ * Pinned implementation-defined behaviour (GL leaves these to the driver; documented in DESIGN.md):
+ *   - unorm8 -> float is k/255.0f; float -> unorm8 is round-half-even(clamp(f,0,1)*255)
+ *   - float -> R16F is round-to-nearest-even
+ *   - no FMA contraction anywhere; dot(a,b) = (ax*bx + ay*by) + az*bz; normalize(v) = v * (1/sqrt(dot(v,v)))
+ *   - mat4*vec4 uses glm's association  (m0*x + m1*y) + (m2*z + m3*w)
+ *   - float -> int conversions saturate and map NaN to 0
+ *   - min/max follow GLSL/glm: max(a,b) = (a<b)?b:a, min(a,b) = (b<a)?b:a
+ */
+#ifndef VXRT_ORACLE_H
+#define VXRT_ORACLE_H
+
+#include "../include/vxrt_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vxo_world {
+    const uint8_t* blocks; /* x-fastest block ids */
+    const uint8_t* df;     /* distance field, same layout */
+    int32_t nx, ny, nz;
+} vxo_world;
+
+/* ManhattanDistance{X,Y,Z}.comp in dispatch order of World.cpp:75-110 */
+void vxo_distance_field(const uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, uint8_t* df);
+/* literal float-carrying version (imageLoad/imageStore through val/255, floor(r*255)); slow,
+ * used on small grids to prove the integer version is an exact restatement                  */
+void vxo_distance_field_literal(const uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, uint8_t* df);
+/* brute-force min(254, L1 distance to nearest solid) — self-check */
+void vxo_distance_field_brute(const uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, uint8_t* df);
+/* 256-entry step table E[k] computed exactly as the shader does (float path) */
+void vxo_step_table(int32_t* out256);
+
+typedef struct vxo_hit {
+    float t;          /* return value of VoxelTraversalDF */
+    float normal[3];  /* valid when intersection != 0 */
+    float end[3];     /* final ray position */
+    int32_t block;    /* block id at the end position (0..255), 0 if none */
+    int32_t intersection;
+    int32_t min_idx;
+    int32_t iterations;
+    int32_t dda_steps;
+} vxo_hit;
+
+/* VoxelTraversalDF (InitialRayTraceFrag.glsl:307-374) */
+float vxo_traverse(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_iter,
+                   vxo_hit* hit);
+/* plain Amanatides-Woo DDA returning the first solid voxel (self-check).
+ * returns 1 and fills voxel[3] on hit, 0 on leaving the volume / max_steps.                 */
+int32_t vxo_plain_dda(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_steps,
+                      int32_t voxel[3]);
+
+/* InitialRayTraceFrag.glsl main() — outputs as the attachments of Pipeline.cpp:1142 hold them.
+ * t32 (optional) receives the float value written to the R16F target before rounding.
+ * stats (optional) accumulates.                                                              */
+void vxo_initial_trace(const vxo_world* w, const vxrt_primary_params* p, uint16_t* t_half,
+                       uint8_t* normal_u8, uint8_t* block_u8, float* inv_t, float* t32,
+                       vxrt_trace_stats* stats);
+
+/* ShadowRayTraceFrag.glsl main(); gbuffer = attachments of the primary pass at gw x gh. */
+void vxo_shadow_trace(const vxo_world* w, const vxrt_shadow_params* p, const uint16_t* g_t_half,
+                      const uint8_t* g_normal_u8, int32_t gw, int32_t gh, const uint8_t* blue_rgba,
+                      int32_t bw, int32_t bh, uint8_t* shadow_u8, uint16_t* transversal_half,
+                      vxrt_trace_stats* stats);
+
+/* format helpers */
+uint16_t vxo_float_to_half(float f);
+float vxo_half_to_float(uint16_t h);
+uint8_t vxo_float_to_unorm8(float f);
+
+void vxo_set_threads(int32_t n); /* 0 = all cores */
+int32_t vxo_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

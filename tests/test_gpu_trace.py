@@ -1,0 +1,169 @@
+"""CUDA primary + shadow passes vs the oracle through the C ABI (BASELINE configs 1 and 3)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from voxeltracing_b200 import abi, engine, host_api
+
+pytestmark = pytest.mark.gpu
+
+POSES = [(yaw, -20.0) for yaw in range(0, 360, 45)] + [(90.0, 0.0)]
+
+
+@pytest.fixture(scope="module")
+def scene(plains0, plains0_oracle):
+    c = engine.Context(0)
+    c.upload_world(plains0)
+    c.generate_distance_field()
+    rng = np.random.default_rng(11)
+    blue = rng.integers(0, 256, (256, 256, 4), dtype=np.uint8)
+    c.set_blue_noise_texture(blue)
+    yield c, plains0_oracle, blue
+    c.close()
+
+
+def _compare_primary(c, ow, cam, w, h, jitter=None, rd=350, tile=(0, 0)):
+    p = c.initial_trace(cam, w, h, rd, jitter, tile)
+    want = ow.initial_trace(p)
+    got = {
+        "t": c.read_attachment(abi.ATT_INITIAL_T), "normal": c.read_attachment(abi.ATT_INITIAL_NORMAL),
+        "block": c.read_attachment(abi.ATT_INITIAL_BLOCK), "inv_t": c.read_attachment(abi.ATT_INITIAL_INVT),
+    }
+    return got, want
+
+
+@pytest.mark.parametrize("yaw,pitch", POSES)
+def test_config1_primary_640x360(scene, yaw, pitch):
+    c, ow, _ = scene
+    cam = host_api.camera([192, 75, 192], float(yaw), float(pitch), 640 / 360)
+    got, want = _compare_primary(c, ow, cam, 640, 360)
+    same = (got["block"] == want["block"]) & (got["normal"] == want["normal"])
+    assert same.mean() >= 0.999, same.mean()          # north_star: voxel + face exact on >= 99.9 %
+    assert (want["block"] > 0).mean() > 0.05            # the pose actually sees terrain
+    hit = same & (want["block"] > 0)
+    rel = np.abs(1.0 / got["inv_t"][hit] - 1.0 / want["inv_t"][hit]) * np.abs(want["inv_t"][hit])
+    assert rel.max() <= 1e-4                            # north_star: t within 1e-4 relative
+    # the R16F attachment is RNE(t)
+    assert np.array_equal(got["t"].view(np.uint16)[same], want["t"].view(np.uint16)[same])
+    # with --fmad=false the CUDA path rounds like the oracle: in practice everything is bit-exact
+    assert same.all() and np.array_equal(got["inv_t"].view(np.uint32), want["inv_t"].view(np.uint32))
+
+
+def test_primary_jitter_odd_size_and_outside_camera(scene):
+    c, ow, _ = scene
+    cam = host_api.camera([192, 75, 192], 30.0, -35.0, 333 / 177)
+    got, want = _compare_primary(c, ow, cam, 333, 177, jitter=host_api.taa_jitter(5))
+    for k in ("block", "normal"):
+        assert np.array_equal(got[k], want[k])
+    assert np.array_equal(got["inv_t"].view(np.uint32), want["inv_t"].view(np.uint32))
+    # camera outside the volume: rays are clipped to the box first (InitialRayTraceFrag.glsl:448-452)
+    cam = host_api.camera([-60, 150, -40], 45.0, -30.0, 16 / 9)
+    got, want = _compare_primary(c, ow, cam, 320, 180)
+    assert (want["block"] > 0).mean() > 0.2
+    for k in ("block", "normal"):
+        assert np.array_equal(got[k], want[k])
+    assert np.array_equal(got["t"].view(np.uint16), want["t"].view(np.uint16))
+    # tiny iteration cap: rays that run out of iterations miss
+    cam = host_api.camera([192, 75, 192], 90.0, -20.0, 16 / 9)
+    got, want = _compare_primary(c, ow, cam, 320, 180, rd=12)
+    assert np.array_equal(got["block"], want["block"]) and (want["block"] == 0).mean() > 0.5
+
+
+def test_primary_inside_solid_and_empty_world():
+    dims = (32, 16, 48)
+    c = engine.Context(0, dims)
+    w = np.zeros((48, 16, 32), np.uint8)
+    c.upload_world(w)
+    c.generate_distance_field()
+    cam = host_api.camera([16, 8, 24], 10.0, 5.0, 1.0)
+    c.initial_trace(cam, 64, 64)
+    assert (c.read_attachment(abi.ATT_INITIAL_BLOCK) == 0).all()
+    assert (c.read_attachment(abi.ATT_INITIAL_NORMAL) == 255).all()
+    assert (c.read_attachment(abi.ATT_INITIAL_T).astype(np.float32) == -1.0).all()
+    w[:] = 3  # camera buried in solid: every ray starts in a solid voxel and misses
+    c.upload_world(w)
+    c.generate_distance_field()
+    p = c.initial_trace(cam, 64, 64)
+    assert (c.read_attachment(abi.ATT_INITIAL_BLOCK) == 0).all()
+    want = ob.OracleWorld(w).initial_trace(p)
+    assert np.array_equal(want["block"], c.read_attachment(abi.ATT_INITIAL_BLOCK))
+    c.close()
+
+
+def test_tile_sharded_primary_equals_full_frame(scene):
+    c, ow, _ = scene
+    cam = host_api.camera([192, 75, 192], 135.0, -20.0, 16 / 9)
+    c.initial_trace(cam, 640, 360)
+    full = {a: c.read_attachment(a).copy() for a in (abi.ATT_INITIAL_T, abi.ATT_INITIAL_NORMAL, abi.ATT_INITIAL_BLOCK, abi.ATT_INITIAL_INVT)}
+    c2 = engine.Context(0)
+    c2.upload_world(ow.blocks)
+    c2.generate_distance_field()
+    for row0, rows in [(0, 100), (100, 57), (157, 203)]:
+        c2.initial_trace(cam, 640, 360, tile=(row0, rows))
+    for a, img in full.items():
+        assert np.array_equal(c2.read_attachment(a), img)
+    c2.close()
+
+
+def _shadow_case(c, ow, blue, cam, w, h, sw, sh, soft, frame, halton=(0.0, 0.0), light=None):
+    c.initial_trace(cam, w, h)
+    g_t = c.read_attachment(abi.ATT_INITIAL_T)
+    g_n = c.read_attachment(abi.ATT_INITIAL_NORMAL)
+    if light is None:
+        light = host_api.sun_direction(50.0)[2]
+    p = c.shadow_trace(cam, sw, sh, light, frame=frame, halton=halton, soft=soft)
+    want = ow.shadow_trace(p, g_t, g_n, blue, want_stats=True)
+    got_s = c.read_attachment(abi.ATT_SHADOW)
+    got_t = c.read_attachment(abi.ATT_SHADOW_TRANSVERSAL)
+    return got_s, got_t, want
+
+
+def test_hard_shadows_are_bit_exact(scene):
+    c, ow, blue = scene
+    cam = host_api.camera([192, 75, 192], 200.0, -25.0, 16 / 9)
+    got_s, got_t, want = _shadow_case(c, ow, blue, cam, 640, 360, 640, 360, soft=False, frame=0)
+    assert np.array_equal(got_s, want["shadow"])
+    assert np.array_equal(got_t.view(np.uint16), want["transversal"].view(np.uint16))
+    assert 0.02 < (want["shadow"] == 255).mean() < 0.98 and want["stats"]["rays"] > 10000
+
+
+@pytest.mark.parametrize("frame,res", [(0, (640, 360)), (7, (640, 360)), (3, (320, 180))])
+def test_soft_shadows_config3_style(scene, frame, res):
+    """soft=true, blue-noise cone jitter.  sinf/cosf differ from libm by an ulp, so the jittered
+    direction may differ in the last bit: occlusion must agree on >= 99.9 % of pixels and the
+    transversal (T/100) within 1e-3 relative where both agree."""
+    c, ow, blue = scene
+    cam = host_api.camera([192, 75, 192], 60.0, -20.0, 16 / 9)
+    halton = (0.0, 0.0) if res == (640, 360) else tuple(host_api.taa_jitter(frame) )
+    got_s, got_t, want = _shadow_case(c, ow, blue, cam, 640, 360, res[0], res[1], soft=True, frame=frame, halton=halton)
+    same = got_s == want["shadow"]
+    assert same.mean() >= 0.999, same.mean()
+    a, b = got_t.astype(np.float32)[same], want["transversal"].astype(np.float32)[same]
+    close = np.abs(a - b) <= 1e-3 * np.abs(b) + 1e-6
+    assert close.mean() >= 0.999
+
+
+def test_shadow_needs_gbuffer_and_blue_noise(plains0):
+    c = engine.Context(0)
+    c.upload_world(plains0)
+    c.generate_distance_field()
+    cam = host_api.camera([192, 75, 192], 60.0, -20.0, 16 / 9)
+    with pytest.raises(engine.VxrtError):
+        c.shadow_trace(cam, 64, 64, [0, 1, 0], soft=False)
+    c.initial_trace(cam, 64, 64)
+    with pytest.raises(engine.VxrtError):
+        c.shadow_trace(cam, 64, 64, [0, 1, 0], soft=True)  # no blue-noise texture bound
+    c.shadow_trace(cam, 64, 64, [0, 1, 0], soft=False)
+    c.close()
+
+
+def test_stats_counters_match_oracle(scene):
+    c, ow, _ = scene
+    cam = host_api.camera([192, 75, 192], 270.0, -20.0, 16 / 9)
+    c.stats_enable(True)
+    c.stats_read(reset=True)
+    p = c.initial_trace(cam, 640, 360)
+    got = c.stats_read(reset=True)
+    c.stats_enable(False)
+    want = ow.initial_trace(p, want_stats=True)["stats"]
+    assert got == want

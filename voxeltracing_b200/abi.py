@@ -1,0 +1,149 @@
+"""ctypes view of include/vxrt_cuda.h (the C ABI) and voxeltracing_b200/host/vxrt_host.h.
+
+This is the reference-side binding stub a maintainer would write; it contains no
+compute.  Loading fails loudly if the CUDA library has not been built: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+CUDA_LIB_PATH = _PKG / "libvxrt_cuda.so"
+HOST_LIB_PATH = _PKG / "libvxrt_host.so"
+
+VXRT_OK = 0
+
+# vxrt_attachment
+ATT_INITIAL_T, ATT_INITIAL_NORMAL, ATT_INITIAL_BLOCK, ATT_INITIAL_INVT = 0, 1, 2, 3
+ATT_SHADOW, ATT_SHADOW_TRANSVERSAL = 4, 5
+ATT_GBUF_ALBEDO, ATT_GBUF_NORMAL, ATT_GBUF_PBR, ATT_GBUF_TEXAO, ATT_DIRECT = 6, 7, 8, 9, 10
+ATT_GI_SH, ATT_GI_COCG, ATT_GI_UTILITY, ATT_GI_AOSKY = 11, 12, 13, 14
+ATT_REFL_COLOR, ATT_REFL_HITDIST, ATT_REFL_EMISSIVE = 15, 16, 17
+
+TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
+
+
+class Tile(C.Structure):
+    _fields_ = [("row0", C.c_int32), ("rows", C.c_int32)]
+
+
+class PrimaryParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16),
+        ("inv_projection", C.c_float * 16),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("jitter", C.c_float * 2),
+        ("jitter_on", C.c_int32),
+        ("render_distance", C.c_int32),
+        ("alpha_test", C.c_int32),
+        ("tile", Tile),
+    ]
+
+
+class ShadowParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16),
+        ("inv_projection", C.c_float * 16),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("light_direction", C.c_float * 3),
+        ("current_frame", C.c_int32),
+        ("halton", C.c_float * 2),
+        ("soft_shadows", C.c_int32),
+        ("alpha_test", C.c_int32),
+        ("max_iterations", C.c_int32),
+        ("tile", Tile),
+    ]
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("iterations", C.c_uint64), ("dda_steps", C.c_uint64), ("hits", C.c_uint64)]
+
+
+def declared_symbols(header: Path) -> list[str]:
+    """Names of every function a C header declares (used by the export-coverage test)."""
+    import re
+
+    text = header.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:vxrt_cuda|vxh|vxo)_[a-z0-9_]+)\s*\(", text)))
+
+
+_cuda = None
+_host = None
+
+
+def load_cuda() -> C.CDLL:
+    """dlopen the product library.  Raises if it was not built (no fallback path exists)."""
+    global _cuda
+    if _cuda is not None:
+        return _cuda
+    if not CUDA_LIB_PATH.exists():
+        raise RuntimeError(
+            f"{CUDA_LIB_PATH} is missing: build it with `python -m voxeltracing_b200.build` "
+            "(the hot path is CUDA-only; there is no CPU fallback)"
+        )
+    lib = C.CDLL(str(CUDA_LIB_PATH))
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    P = C.POINTER
+    sig = {
+        "vxrt_cuda_create": (C.c_int, [P(vp), C.c_int, P(i32)]),
+        "vxrt_cuda_destroy": (C.c_int, [vp]),
+        "vxrt_cuda_last_error": (C.c_char_p, []),
+        "vxrt_cuda_set_stream": (C.c_int, [vp, vp]),
+        "vxrt_cuda_synchronize": (C.c_int, [vp]),
+        "vxrt_cuda_launch_count": (i64, [vp]),
+        "vxrt_cuda_upload_world": (C.c_int, [vp, vp]),
+        "vxrt_cuda_download_world": (C.c_int, [vp, vp]),
+        "vxrt_cuda_edit_blocks": (C.c_int, [vp, vp, i32]),
+        "vxrt_cuda_generate_distance_field": (C.c_int, [vp]),
+        "vxrt_cuda_download_distance_field": (C.c_int, [vp, vp]),
+        "vxrt_cuda_upload_distance_field": (C.c_int, [vp, vp]),
+        "vxrt_cuda_set_block_data": (C.c_int, [vp, vp]),
+        "vxrt_cuda_set_blue_noise": (C.c_int, [vp, vp, i32]),
+        "vxrt_cuda_set_blue_noise_texture": (C.c_int, [vp, vp, i32, i32]),
+        "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
+        "vxrt_cuda_attachment_device": (C.c_int, [vp, i32, P(vp), P(i32), P(i32), P(i32)]),
+        "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),
+        "vxrt_cuda_shadow_trace": (C.c_int, [vp, P(ShadowParams)]),
+        "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
+        "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _cuda = lib
+    return lib
+
+
+def load_host() -> C.CDLL:
+    global _host
+    if _host is not None:
+        return _host
+    if not HOST_LIB_PATH.exists():
+        raise RuntimeError(f"{HOST_LIB_PATH} is missing: build it with `python -m voxeltracing_b200.build`")
+    lib = C.CDLL(str(HOST_LIB_PATH))
+    vp, i32, u32, f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
+    sig = {
+        "vxh_perspective": (None, [f, f, f, f, vp]),
+        "vxh_look_at": (None, [vp, vp, vp, vp]),
+        "vxh_inverse": (None, [vp, vp]),
+        "vxh_camera": (None, [vp, f, f, f, f, vp, vp, vp, vp]),
+        "vxh_taa_jitter": (None, [i32, vp]),
+        "vxh_sun_direction": (None, [f, vp, vp, vp]),
+        "vxh_gen_plains": (None, [u32, i32, i32, i32, i32, vp]),
+        "vxh_gen_rooms": (None, [u32, i32, i32, i32, vp]),
+        "vxh_gen_town": (None, [u32, i32, i32, i32, vp]),
+        "vxh_random_edits": (None, [u32, i32, i32, i32, i32, vp, vp]),
+        "vxh_world_save": (i32, [C.c_char_p, vp, C.c_int64]),
+        "vxh_world_load": (i32, [C.c_char_p, vp, C.c_int64]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _host = lib
+    return lib

@@ -1,0 +1,294 @@
+// api.cu — the extern "C" vxrt_cuda_* layer (include/vxrt_cuda.h).  Never throws, never aborts;
+// every entry point validates its arguments and returns a vxrt_status.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include <unordered_map>
+
+#include "ctx.h"
+
+static thread_local char g_err[512] = "";
+
+int vxrt_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int vxrt_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return VXRT_OK;
+    return vxrt_fail(VXRT_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+#define REQUIRE_CTX(c) \
+    if (!(c)) return vxrt_fail(VXRT_E_INVALID, "%s: ctx is NULL", __func__)
+#define REQUIRE_PTR(p) \
+    if (!(p)) return vxrt_fail(VXRT_E_INVALID, "%s: %s is NULL", __func__, #p)
+
+int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "bad attachment size %dx%d", w, h);
+    Attachment& a = c->att[id];
+    size_t need = (size_t)w * h * bpp;
+    if (need > a.capacity) {
+        if (a.ptr) VX_CUDA(cudaFree(a.ptr));
+        a.ptr = nullptr;
+        a.capacity = 0;
+        VX_CUDA(cudaMalloc(&a.ptr, need));
+        a.capacity = need;
+    }
+    if (a.width != w || a.height != h || a.bpp != bpp) {
+        // a tile-sharded pass only writes its rows: keep the rest defined
+        VX_CUDA(cudaMemsetAsync(a.ptr, 0, need, c->stream));
+    }
+    a.width = w; a.height = h; a.bpp = bpp;
+    return VXRT_OK;
+}
+
+extern "C" {
+
+const char* vxrt_cuda_last_error(void) { return g_err; }
+
+int vxrt_cuda_create(vxrt_ctx** out, int device, const int32_t* dims) {
+    REQUIRE_PTR(out);
+    *out = nullptr;
+    int nx = VXRT_WORLD_SIZE_X, ny = VXRT_WORLD_SIZE_Y, nz = VXRT_WORLD_SIZE_Z;
+    if (dims) { nx = dims[0]; ny = dims[1]; nz = dims[2]; }
+    if (nx < 16 || ny < 16 || nz < 16 || nx > 1024 || ny > 1024 || nz > 1024 || (nx % 16) != 0 ||
+        (size_t)nx * ny > 65536)
+        return vxrt_fail(VXRT_E_INVALID, "unsupported grid dims %dx%dx%d", nx, ny, nz);
+    int ndev = 0;
+    VX_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return vxrt_fail(VXRT_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    VX_CUDA(cudaSetDevice(device));
+    vxrt_ctx* c = new (std::nothrow) vxrt_ctx();
+    if (!c) return vxrt_fail(VXRT_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->nx = nx; c->ny = ny; c->nz = nz;
+    c->nvox = (size_t)nx * ny * nz;
+    cudaDeviceProp prop;
+    int rc = vxrt_check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (rc == VXRT_OK && prop.major < 10) rc = vxrt_fail(VXRT_E_UNSUPPORTED, "sm_%d%d device; this library is built for sm_100a only", prop.major, prop.minor);
+    if (rc == VXRT_OK) { c->sm_count = prop.multiProcessorCount; rc = vxrt_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate"); }
+    if (rc == VXRT_OK) { c->stream = c->own_stream; rc = vxrt_check_cuda(cudaMalloc(&c->d_blocks, c->nvox), "cudaMalloc(blocks)"); }
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_df, c->nvox), "cudaMalloc(df)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_block_data, 6 * 128 * sizeof(int32_t)), "cudaMalloc(block_data)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_stats, sizeof(TraceStatsDev)), "cudaMalloc(stats)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMemset(c->d_stats, 0, sizeof(TraceStatsDev)), "cudaMemset(stats)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMemset(c->d_block_data, 0xff, 6 * 128 * sizeof(int32_t)), "cudaMemset(block_data)");
+    if (rc != VXRT_OK) { vxrt_cuda_destroy(c); return rc; }
+    *out = c;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_destroy(vxrt_ctx* c) {
+    if (!c) return VXRT_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
+    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats);
+    for (int i = 0; i < VXRT_ATT_COUNT; ++i) cudaFree(c->att[i].ptr);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_set_stream(vxrt_ctx* c, void* s) {
+    REQUIRE_CTX(c);
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return VXRT_OK;
+}
+int vxrt_cuda_synchronize(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+int64_t vxrt_cuda_launch_count(vxrt_ctx* c) { return c ? c->launches : -1; }
+
+int vxrt_cuda_upload_world(vxrt_ctx* c, const uint8_t* blocks) {
+    REQUIRE_CTX(c); REQUIRE_PTR(blocks);
+    VX_CUDA(cudaMemcpyAsync(c->d_blocks, blocks, c->nvox, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // host buffer is only borrowed for the call
+    c->world_uploaded = true;
+    c->df_valid = false;
+    return VXRT_OK;
+}
+int vxrt_cuda_download_world(vxrt_ctx* c, uint8_t* out) {
+    REQUIRE_CTX(c); REQUIRE_PTR(out);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "download_world before upload_world");
+    VX_CUDA(cudaMemcpyAsync(out, c->d_blocks, c->nvox, cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+int vxrt_cuda_edit_blocks(vxrt_ctx* c, const int32_t* e, int32_t n) {
+    REQUIRE_CTX(c);
+    if (n < 0) return vxrt_fail(VXRT_E_INVALID, "edit_blocks: n < 0");
+    if (n == 0) return VXRT_OK;
+    REQUIRE_PTR(e);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "edit_blocks before upload_world");
+    for (int i = 0; i < n; ++i) {
+        int x = e[4 * i], y = e[4 * i + 1], z = e[4 * i + 2], id = e[4 * i + 3];
+        if (x < 0 || y < 0 || z < 0 || x >= c->nx || y >= c->ny || z >= c->nz || id < 0 || id > 255)
+            return vxrt_fail(VXRT_E_INVALID, "edit %d out of range: (%d,%d,%d) id %d", i, x, y, z, id);
+    }
+    // the reference applies edits one by one: a later edit of the same voxel wins.  Keep only the
+    // last edit per voxel so the parallel scatter is deterministic.
+    std::vector<int32_t> last;
+    const int32_t* src = e;
+    int m = n;
+    {
+        std::unordered_map<int64_t, int> seen;
+        seen.reserve((size_t)n * 2);
+        bool dup = false;
+        for (int i = 0; i < n; ++i) {
+            int64_t key = (int64_t)e[4 * i] + (int64_t)c->nx * (e[4 * i + 1] + (int64_t)c->ny * e[4 * i + 2]);
+            auto it = seen.find(key);
+            if (it != seen.end()) { dup = true; it->second = i; } else seen.emplace(key, i);
+        }
+        if (dup) {
+            last.reserve(seen.size() * 4);
+            for (int i = 0; i < n; ++i) {
+                int64_t key = (int64_t)e[4 * i] + (int64_t)c->nx * (e[4 * i + 1] + (int64_t)c->ny * e[4 * i + 2]);
+                if (seen[key] == i) last.insert(last.end(), e + 4 * i, e + 4 * i + 4);
+            }
+            src = last.data();
+            m = (int)(last.size() / 4);
+        }
+    }
+    size_t bytes = (size_t)m * 4 * sizeof(int32_t);
+    if (bytes > c->edit_cap) {
+        if (c->d_edit_buf) VX_CUDA(cudaFree(c->d_edit_buf));
+        c->d_edit_buf = nullptr; c->edit_cap = 0;
+        VX_CUDA(cudaMalloc(&c->d_edit_buf, bytes));
+        c->edit_cap = bytes;
+    }
+    VX_CUDA(cudaMemcpyAsync(c->d_edit_buf, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = vxrt_launch_edit_blocks(c, c->d_edit_buf, m);
+    if (rc) return rc;
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // src may be a temporary / borrowed buffer
+    c->df_valid = false;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_generate_distance_field(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "generate_distance_field before upload_world");
+    int rc = vxrt_launch_distance_field(c);
+    if (rc) return rc;
+    c->df_valid = true;
+    return VXRT_OK;
+}
+int vxrt_cuda_download_distance_field(vxrt_ctx* c, uint8_t* out) {
+    REQUIRE_CTX(c); REQUIRE_PTR(out);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "distance field has not been generated");
+    VX_CUDA(cudaMemcpyAsync(out, c->d_df, c->nvox, cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+int vxrt_cuda_upload_distance_field(vxrt_ctx* c, const uint8_t* df) {
+    REQUIRE_CTX(c); REQUIRE_PTR(df);
+    VX_CUDA(cudaMemcpyAsync(c->d_df, df, c->nvox, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->df_valid = true;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_set_block_data(vxrt_ctx* c, const int32_t* table) {
+    REQUIRE_CTX(c); REQUIRE_PTR(table);
+    VX_CUDA(cudaMemcpyAsync(c->d_block_data, table, 6 * 128 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+int vxrt_cuda_set_blue_noise(vxrt_ctx* c, const int32_t* data, int32_t count) {
+    REQUIRE_CTX(c); REQUIRE_PTR(data);
+    if (count != 256 * 256 + 2 * 128 * 128 * 8) return vxrt_fail(VXRT_E_INVALID, "blue noise table must hold 327680 ints, got %d", count);
+    if (!c->d_blue_noise) VX_CUDA(cudaMalloc(&c->d_blue_noise, (size_t)count * sizeof(int32_t)));
+    VX_CUDA(cudaMemcpyAsync(c->d_blue_noise, data, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->blue_noise_count = count;
+    return VXRT_OK;
+}
+int vxrt_cuda_set_blue_noise_texture(vxrt_ctx* c, const uint8_t* rgba, int32_t w, int32_t h) {
+    REQUIRE_CTX(c); REQUIRE_PTR(rgba);
+    if (w <= 0 || h <= 0 || w > 4096 || h > 4096) return vxrt_fail(VXRT_E_INVALID, "bad blue-noise texture size %dx%d", w, h);
+    if (c->d_blue_tex) { VX_CUDA(cudaFree(c->d_blue_tex)); c->d_blue_tex = nullptr; }
+    VX_CUDA(cudaMalloc(&c->d_blue_tex, (size_t)w * h * 4));
+    VX_CUDA(cudaMemcpyAsync(c->d_blue_tex, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->blue_w = w; c->blue_h = h;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_read_attachment(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    const Attachment& a = c->att[id];
+    if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
+    size_t have = (size_t)a.width * a.height * a.bpp;
+    if (bytes != have) return vxrt_fail(VXRT_E_INVALID, "attachment %d holds %zu bytes, caller asked for %zu", id, have, bytes);
+    VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+int vxrt_cuda_attachment_device(vxrt_ctx* c, int32_t id, void** p, int32_t* w, int32_t* h, int32_t* bpp) {
+    REQUIRE_CTX(c);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    const Attachment& a = c->att[id];
+    if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
+    if (p) *p = a.ptr;
+    if (w) *w = a.width;
+    if (h) *h = a.height;
+    if (bpp) *bpp = a.bpp;
+    return VXRT_OK;
+}
+
+static int check_frame(const char* fn, int w, int h, const vxrt_tile& t) {
+    if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "%s: bad dimensions %dx%d", fn, w, h);
+    if (t.rows < 0 || t.row0 < 0 || (t.rows > 0 && t.row0 >= h)) return vxrt_fail(VXRT_E_INVALID, "%s: bad tile rows [%d,+%d) of %d", fn, t.row0, t.rows, h);
+    return VXRT_OK;
+}
+
+int vxrt_cuda_initial_trace(vxrt_ctx* c, const vxrt_primary_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "initial_trace needs a world and a distance field");
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if (p->alpha_test) return vxrt_fail(VXRT_E_UNSUPPORTED, "alpha-tested traversal (InitialRayTraceFrag.glsl:189-305) is off by default in the reference and not implemented");
+    if (p->render_distance < 0) return vxrt_fail(VXRT_E_INVALID, "render_distance < 0");
+    return vxrt_launch_initial_trace(c, *p);
+}
+
+int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "shadow_trace needs a world and a distance field");
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if (p->alpha_test) return vxrt_fail(VXRT_E_UNSUPPORTED, "alpha-tested traversal is not implemented");
+    if (!c->att[VXRT_ATT_INITIAL_T].ptr || !c->att[VXRT_ATT_INITIAL_NORMAL].ptr)
+        return vxrt_fail(VXRT_E_STATE, "shadow_trace consumes the primary G-buffer: run initial_trace first");
+    if (p->soft_shadows && !c->d_blue_tex) return vxrt_fail(VXRT_E_STATE, "soft shadows need set_blue_noise_texture");
+    if (p->max_iterations < 0) return vxrt_fail(VXRT_E_INVALID, "max_iterations < 0");
+    return vxrt_launch_shadow_trace(c, *p);
+}
+
+int vxrt_cuda_stats_enable(vxrt_ctx* c, int32_t on) {
+    REQUIRE_CTX(c);
+    c->stats_on = on != 0;
+    return VXRT_OK;
+}
+int vxrt_cuda_stats_read(vxrt_ctx* c, vxrt_trace_stats* out, int32_t reset) {
+    REQUIRE_CTX(c); REQUIRE_PTR(out);
+    TraceStatsDev h;
+    VX_CUDA(cudaMemcpyAsync(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    out->rays = h.rays; out->iterations = h.iterations; out->dda_steps = h.dda_steps; out->hits = h.hits;
+    if (reset) VX_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(TraceStatsDev), c->stream));
+    return VXRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// ctx.h — context object behind the vxrt_cuda_* C ABI (include/vxrt_cuda.h).
+// Owns every device allocation: the block-id grid, the distance field, the material / blue-noise
+// tables and the pass attachments (the reference keeps these as GL textures, SSBOs and FBO
+// attachments: Core/World.h:167-171, Core/BlockDataSSBO.cpp, Core/Pipeline.cpp:1142-1202).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/vxrt_cuda.h"
+
+struct GridView {
+    const uint8_t* __restrict__ df;   // distance field, x-fastest
+    const uint8_t* __restrict__ blk;  // block ids, x-fastest
+    int nx, ny, nz;
+    int sy;  // nx
+    int sz;  // nx*ny
+};
+
+struct Attachment {
+    void* ptr = nullptr;
+    size_t capacity = 0;  // bytes allocated
+    int width = 0, height = 0, bpp = 0;
+};
+
+struct TraceStatsDev {
+    unsigned long long rays, iterations, dda_steps, hits;
+};
+
+struct vxrt_ctx {
+    int device = 0;
+    int nx = 0, ny = 0, nz = 0;
+    size_t nvox = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int sm_count = 0;
+    int64_t launches = 0;
+
+    uint8_t* d_blocks = nullptr;
+    uint8_t* d_df = nullptr;
+    bool world_uploaded = false;
+    bool df_valid = false;
+
+    int32_t* d_block_data = nullptr;      // 6*128
+    int32_t* d_blue_noise = nullptr;      // sobol ++ scramble ++ ranking
+    int32_t blue_noise_count = 0;
+    uint8_t* d_blue_tex = nullptr;        // rgba8
+    int blue_w = 0, blue_h = 0;
+
+    int32_t* d_edit_buf = nullptr;
+    size_t edit_cap = 0;
+
+    Attachment att[VXRT_ATT_COUNT];
+
+    TraceStatsDev* d_stats = nullptr;
+    bool stats_on = false;
+
+    GridView grid() const {
+        GridView g;
+        g.df = d_df; g.blk = d_blocks; g.nx = nx; g.ny = ny; g.nz = nz; g.sy = nx; g.sz = nx * ny;
+        return g;
+    }
+};
+
+// error plumbing (api.cu)
+int vxrt_fail(int code, const char* fmt, ...);
+int vxrt_check_cuda(cudaError_t e, const char* what);
+#define VX_CUDA(call)                                              \
+    do {                                                           \
+        int _rc = vxrt_check_cuda((call), #call);                  \
+        if (_rc != VXRT_OK) return _rc;                            \
+    } while (0)
+
+// kernel launchers (one per .cu)
+int vxrt_launch_distance_field(vxrt_ctx* c);
+int vxrt_launch_edit_blocks(vxrt_ctx* c, const int32_t* d_edits, int n);
+int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
+int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
+int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);

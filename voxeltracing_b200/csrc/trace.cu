@@ -1,0 +1,284 @@
+// trace.cu — primary G-buffer pass and sun-shadow pass (sm_100a, compiled with --fmad=false).
+//
+// primary: InitialRayTraceFrag.glsl:398-496 (GetRayStuff, IntersectBox, main), dispatched from
+//          Core/Pipeline.cpp:2051-2094; attachments Core/Pipeline.cpp:1142.
+// shadow:  ShadowRayTraceFrag.glsl:303-331,388-398,414-513, dispatched from Pipeline.cpp:2888-2945;
+//          attachments Core/Pipeline.cpp:1200.
+// One ray per thread; a warp covers an 8x4 pixel tile so the rays of a warp walk neighbouring
+// voxels (coherent 32-byte sectors of the x-fastest grids, which are L2/L1 resident).
+#include "ctx.h"
+#include "traverse.cuh"
+
+namespace {
+
+struct PrimaryArgs {
+    float inv_view[16];
+    float inv_proj[16];
+    int width, height;
+    float jitter_x, jitter_y;
+    int jitter_on;
+    int max_iter;
+    int row0, row1;
+    uint16_t* t_half;
+    uint8_t* normal;
+    uint8_t* block;
+    float* inv_t;
+};
+
+struct ShadowArgs {
+    float inv_view[16];
+    float inv_proj[16];
+    int width, height;
+    float light[3];
+    int frame;
+    float halton_x, halton_y;
+    int soft;
+    int max_iter;
+    int row0, row1;
+    const uint16_t* g_t;
+    const uint8_t* g_normal;
+    int gw, gh;
+    const uint8_t* blue;
+    int bw, bh;
+    uint8_t* shadow;
+    uint16_t* transversal;
+};
+
+// GetRayStuff (InitialRayTraceFrag.glsl:398-416) / GetRayDirectionAt (ShadowRayTraceFrag.glsl:303-308)
+VXD f3 ray_direction_at(const float* inv_view, const float* inv_proj, f2 ss) {
+    f4 clip = F4(ss.x * 2.0f - 1.0f, ss.y * 2.0f - 1.0f, -1.0f, 1.0f);
+    f4 e = mat4_mul(inv_proj, clip);
+    f4 r = mat4_mul(inv_view, F4(e.x, e.y, -1.0f, 0.0f));
+    return F3(r.x, r.y, r.z);
+}
+
+// IntersectBox (InitialRayTraceFrag.glsl:418-432)
+VXD f2 intersect_box(f3 ro, f3 invrd, f3 rad) {
+    f3 n = invrd * ro;
+    f3 k = F3(fabsf(invrd.x), fabsf(invrd.y), fabsf(invrd.z)) * rad;
+    f3 t1 = -n - k;
+    f3 t2 = -n + k;
+    float tN = gmax(gmax(t1.x, t1.y), t1.z);
+    float tF = gmin(gmin(t2.x, t2.y), t2.z);
+    if (tN > tF || tF < 0.0f) return F2(-1.0f, -1.0f);
+    return F2(tN, tF);
+}
+
+// GetNormalID (InitialRayTraceFrag.glsl:140-185)
+VXD float normal_id(f3 n) {
+    if (n.x == 0.0f && n.y == 0.0f && n.z == 1.0f) return 0.0f / 10.0f;
+    if (n.x == 0.0f && n.y == 0.0f && n.z == -1.0f) return 1.0f / 10.0f;
+    if (n.x == 0.0f && n.y == 1.0f && n.z == 0.0f) return 2.0f / 10.0f;
+    if (n.x == 0.0f && n.y == -1.0f && n.z == 0.0f) return 3.0f / 10.0f;
+    if (n.x == -1.0f && n.y == 0.0f && n.z == 0.0f) return 4.0f / 10.0f;
+    if (n.x == 1.0f && n.y == 0.0f && n.z == 0.0f) return 5.0f / 10.0f;
+    return 0.0f;
+}
+
+// pixel of this thread: CTA = 32x8 pixels, warp = 8x4 tile
+VXD void pixel_of_thread(int& px, int& py, int row0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    py = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) initial_trace_kernel(GridView g, const __grid_constant__ PrimaryArgs a,
+                                                            TraceStatsDev* stats) {
+    int px, py;
+    pixel_of_thread(px, py, a.row0);
+    const bool active = px < a.width && py < a.row1;
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    if (active) {
+        const float W = (float)a.width, H = (float)a.height;
+        f2 ss = F2(((float)px + 0.5f) / W, ((float)py + 0.5f) / H);
+        if (a.jitter_on) {
+            ss.x -= a.jitter_x * (1.0f / W);
+            ss.y -= a.jitter_y * (1.0f / H);
+        }
+        f3 dir = normalize(ray_direction_at(a.inv_view, a.inv_proj, ss));
+        f3 ro = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+        const f3 half = F3((float)g.nx / 2.0f, (float)g.ny / 2.0f, (float)g.nz / 2.0f);
+        float AddT = 0.0f;
+        f2 box = intersect_box(ro - half, F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z), half);
+        if (box.x > 0.0f) {
+            AddT = box.x + 0.5f;
+            ro = ro + dir * AddT;
+        }
+        TraceResult r = traverse_df<STATS>(g, ro, dir, a.max_iter, &ls);
+        const bool intersect = r.t > 0.0f && r.block > 0;
+        float t = r.t + AddT * (intersect ? 1.0f : 0.0f);
+        const size_t i = (size_t)py * a.width + px;
+        a.t_half[i] = float_to_half_bits(t);
+        a.inv_t[i] = 1.0f / t;
+        a.normal[i] = float_to_unorm8(intersect ? normal_id(r.normal) : 1.0f);
+        a.block[i] = intersect ? (uint8_t)r.block : (uint8_t)0;
+    }
+    if (STATS) flush_stats(stats, ls);
+}
+
+// texture(R16F, uv): LINEAR + REPEAT (Core/GLClasses/Framebuffer.cpp:64-68), weights in full float
+VXD float sample_r16f_bilinear(const uint16_t* __restrict__ img, int w, int h, f2 uv) {
+    float u = uv.x * (float)w - 0.5f, v = uv.y * (float)h - 0.5f;
+    float fu = floorf(u), fv = floorf(v);
+    float a = u - fu, b = v - fv;
+    int i0 = wrap_repeat(cvt_floor(fu), w), j0 = wrap_repeat(cvt_floor(fv), h);
+    int i1 = wrap_repeat(i0 + 1, w), j1 = wrap_repeat(j0 + 1, h);
+    float t00 = half_bits_to_float(__ldg(img + (size_t)j0 * w + i0)), t10 = half_bits_to_float(__ldg(img + (size_t)j0 * w + i1));
+    float t01 = half_bits_to_float(__ldg(img + (size_t)j1 * w + i0)), t11 = half_bits_to_float(__ldg(img + (size_t)j1 * w + i1));
+    float top = t00 * (1.0f - a) + t10 * a;
+    float bot = t01 * (1.0f - a) + t11 * a;
+    return top * (1.0f - b) + bot * b;
+}
+VXD float sample_r8_nearest(const uint8_t* __restrict__ img, int w, int h, f2 uv) {
+    int i = wrap_repeat(cvt_floor(uv.x * (float)w), w), j = wrap_repeat(cvt_floor(uv.y * (float)h), h);
+    return unorm8_to_float(__ldg(img + (size_t)j * w + i));
+}
+
+// GetNormalFromID (ShadowRayTraceFrag.glsl:317-328)
+VXD f3 normal_from_id(float n) {
+    int i = cvt_round(n * 10.0f);
+    switch (i) {
+        case 0: return F3(0.0f, 0.0f, 1.0f);
+        case 1: return F3(0.0f, 0.0f, -1.0f);
+        case 2: return F3(0.0f, 1.0f, 0.0f);
+        case 3: return F3(0.0f, -1.0f, 0.0f);
+        case 4: return F3(-1.0f, 0.0f, 0.0f);
+        case 5: return F3(1.0f, 0.0f, 0.0f);
+        default: return F3(1.0f, 1.0f, 1.0f);
+    }
+}
+
+// SampleCone (ShadowRayTraceFrag.glsl:388-398)
+VXD f3 sample_cone(f2 Xi, float CosThetaMax) {
+    const float PI = 3.14159265359f;
+    float CosTheta = (1.0f - Xi.x) + Xi.x * CosThetaMax;
+    float SinTheta = sqrtf(1.0f - CosTheta * CosTheta);
+    float phi = Xi.y * PI * 2.0f;
+    return F3(SinTheta * cosf(phi), SinTheta * sinf(phi), CosTheta);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __grid_constant__ ShadowArgs a,
+                                                           TraceStatsDev* stats) {
+    int px, py;
+    pixel_of_thread(px, py, a.row0);
+    const bool active = px < a.width && py < a.row1;
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    if (active) {
+        const size_t i = (size_t)py * a.width + px;
+        const float W = (float)a.width, H = (float)a.height;
+        f2 tc = F2(((float)px + 0.5f) / W, ((float)py + 0.5f) / H);
+        tc = tc + F2(a.halton_x, a.halton_y) * F2(1.0f / W, 1.0f / H);
+        const float Dist = sample_r16f_bilinear(a.g_t, a.gw, a.gh, tc);
+        uint8_t o_shadow;
+        float o_trans;
+        if (Dist < 0.0f) {
+            o_shadow = 0;
+            o_trans = 64.0f;
+        } else {
+            const f3 cam = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+            const f3 P = cam + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * Dist;
+            const f3 L = F3(a.light[0], a.light[1], a.light[2]);
+            f3 rd = L;
+            if (a.soft) {
+                int n = a.frame % 1024;
+                float qx = (float)(int)((unsigned)n * 12664745u), qy = (float)(int)((unsigned)n * 9560333u);
+                float offx = gfract(qx / 16777216.0f) * 1024.0f, offy = gfract(qy / 16777216.0f) * 1024.0f;
+                int sx = cvt_trunc(((float)px + 0.5f) + (float)cvt_trunc(floorf(offx))) % a.bw;
+                int sy = cvt_trunc(((float)py + 0.5f) + (float)cvt_trunc(floorf(offy))) % a.bh;
+                const uchar4 tx = __ldg(reinterpret_cast<const uchar4*>(a.blue) + ((size_t)sy * a.bw + sx));
+                f2 Xi = F2(unorm8_to_float(tx.x), unorm8_to_float(tx.y));
+                f3 T = normalize(cross(L, F3(0.0f, 1.0f, 1.0f)));
+                f3 B = cross(T, L);
+                rd = mat3_mul(T, B, L, sample_cone(Xi, 0.9999505604617f));
+            }
+            const f3 N = normal_from_id(sample_r8_nearest(a.g_normal, a.gw, a.gh, tc));
+            const float NDotL = dot(N, rd);
+            if (NDotL <= 0.01f) {
+                o_shadow = 255;
+                o_trans = 1.0f / 100.0f;
+            } else {
+                const f3 o = P + N * F3(0.1f);
+                const int block_at = get_voxel(g, cvt_floor(o.x), cvt_floor(o.y), cvt_floor(o.z));
+                float T = -1.0f;
+                if (Dist > 0.0f) {
+                    TraceResult r = traverse_df<STATS>(g, o, rd, a.max_iter, &ls);
+                    T = r.t;
+                }
+                o_shadow = (T > 0.0f || block_at > 0) ? 255 : 0;
+                o_trans = gclamp(T / 100.0f, 0.00001f, 196.0f);
+                if (T < 0.0f) o_trans = 4.25f / 100.0f;
+            }
+        }
+        a.shadow[i] = o_shadow;
+        a.transversal[i] = float_to_half_bits(o_trans);
+    }
+    if (STATS) flush_stats(stats, ls);
+}
+
+inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+}
+
+}  // namespace
+
+int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p) {
+    int rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_INITIAL_T, p.width, p.height, 2))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_INITIAL_NORMAL, p.width, p.height, 1))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_INITIAL_BLOCK, p.width, p.height, 1))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_INITIAL_INVT, p.width, p.height, 4))) return rc;
+    PrimaryArgs a;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    a.width = p.width; a.height = p.height;
+    a.jitter_x = p.jitter[0]; a.jitter_y = p.jitter[1];
+    a.jitter_on = p.jitter_on;
+    a.max_iter = p.render_distance;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    a.t_half = (uint16_t*)c->att[VXRT_ATT_INITIAL_T].ptr;
+    a.normal = (uint8_t*)c->att[VXRT_ATT_INITIAL_NORMAL].ptr;
+    a.block = (uint8_t*)c->att[VXRT_ATT_INITIAL_BLOCK].ptr;
+    a.inv_t = (float*)c->att[VXRT_ATT_INITIAL_INVT].ptr;
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (c->stats_on)
+        initial_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    else
+        initial_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p) {
+    int rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_SHADOW, p.width, p.height, 1))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_SHADOW_TRANSVERSAL, p.width, p.height, 2))) return rc;
+    ShadowArgs a;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    a.width = p.width; a.height = p.height;
+    for (int i = 0; i < 3; ++i) a.light[i] = p.light_direction[i];
+    a.frame = p.current_frame;
+    a.halton_x = p.halton[0]; a.halton_y = p.halton[1];
+    a.soft = p.soft_shadows;
+    a.max_iter = p.max_iterations;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    const Attachment& gt = c->att[VXRT_ATT_INITIAL_T];
+    const Attachment& gn = c->att[VXRT_ATT_INITIAL_NORMAL];
+    a.g_t = (const uint16_t*)gt.ptr; a.g_normal = (const uint8_t*)gn.ptr;
+    a.gw = gt.width; a.gh = gt.height;
+    a.blue = c->d_blue_tex; a.bw = c->blue_w; a.bh = c->blue_h;
+    a.shadow = (uint8_t*)c->att[VXRT_ATT_SHADOW].ptr;
+    a.transversal = (uint16_t*)c->att[VXRT_ATT_SHADOW_TRANSVERSAL].ptr;
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (c->stats_on)
+        shadow_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    else
+        shadow_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}

@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's pass interface over the vxrt_cuda_* C ABI.
+
+Names follow the reference: World::Buffer / GenerateDistanceField (Core/World.h, Core/World.cpp:69-113),
+the InitialTrace / ShadowTrace / DiffuseTrace / ReflectionTrace / GenerateGBuffer / ColorPass dispatches
+of Core/Pipeline.cpp.  Everything here marshals arguments; all arithmetic happens in libvxrt_cuda.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class VxrtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vxrt_cuda error {code}: {msg}")
+        self.code = code
+
+
+_ATT_DTYPES = {
+    abi.ATT_INITIAL_T: (np.float16, 1),
+    abi.ATT_INITIAL_NORMAL: (np.uint8, 1),
+    abi.ATT_INITIAL_BLOCK: (np.uint8, 1),
+    abi.ATT_INITIAL_INVT: (np.float32, 1),
+    abi.ATT_SHADOW: (np.uint8, 1),
+    abi.ATT_SHADOW_TRANSVERSAL: (np.float16, 1),
+    abi.ATT_GBUF_ALBEDO: (np.float16, 3),
+    abi.ATT_GBUF_NORMAL: (np.float16, 3),
+    abi.ATT_GBUF_PBR: (np.uint8, 4),
+    abi.ATT_GBUF_TEXAO: (np.uint8, 1),
+    abi.ATT_DIRECT: (np.float16, 3),
+    abi.ATT_GI_SH: (np.float16, 4),
+    abi.ATT_GI_COCG: (np.float16, 2),
+    abi.ATT_GI_UTILITY: (np.float16, 1),
+    abi.ATT_GI_AOSKY: (np.uint8, 2),
+    abi.ATT_REFL_COLOR: (np.float16, 4),
+    abi.ATT_REFL_HITDIST: (np.float16, 1),
+    abi.ATT_REFL_EMISSIVE: (np.uint8, 1),
+}
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fill(dst, src):
+    src = np.asarray(src, dtype=np.float32).ravel()
+    for i, v in enumerate(src):
+        dst[i] = float(v)
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch.as_tensor() can alias an attachment."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None,
+        }
+
+
+class Context:
+    """One GPU's resources: grids, tables and attachments (the reference's GL context)."""
+
+    def __init__(self, device: int = 0, dims=None):
+        self._lib = abi.load_cuda()
+        self._h = C.c_void_p()
+        d = None
+        if dims is not None:
+            d = (C.c_int32 * 3)(*dims)
+        self.dims = tuple(dims) if dims is not None else (384, 128, 384)
+        self._check(self._lib.vxrt_cuda_create(C.byref(self._h), device, d))
+
+    # -- plumbing --
+    def _check(self, rc: int):
+        if rc != abi.VXRT_OK:
+            raise VxrtError(rc, self._lib.vxrt_cuda_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._lib.vxrt_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.vxrt_cuda_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.vxrt_cuda_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vxrt_cuda_launch_count(self._h))
+
+    @property
+    def nvox(self) -> int:
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+    # -- world (Core/World.h) --
+    def upload_world(self, blocks: np.ndarray):
+        b = np.ascontiguousarray(blocks, dtype=np.uint8)
+        if b.size != self.nvox:
+            raise ValueError(f"world has {b.size} voxels, context expects {self.nvox}")
+        self._check(self._lib.vxrt_cuda_upload_world(self._h, _p(b)))
+
+    def download_world(self) -> np.ndarray:
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx), dtype=np.uint8)
+        self._check(self._lib.vxrt_cuda_download_world(self._h, _p(out)))
+        return out
+
+    def edit_blocks(self, xyz_id: np.ndarray):
+        e = np.ascontiguousarray(xyz_id, dtype=np.int32).reshape(-1, 4)
+        self._check(self._lib.vxrt_cuda_edit_blocks(self._h, _p(e), e.shape[0]))
+
+    def generate_distance_field(self):
+        self._check(self._lib.vxrt_cuda_generate_distance_field(self._h))
+
+    def download_distance_field(self) -> np.ndarray:
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx), dtype=np.uint8)
+        self._check(self._lib.vxrt_cuda_download_distance_field(self._h, _p(out)))
+        return out
+
+    def upload_distance_field(self, df: np.ndarray):
+        d = np.ascontiguousarray(df, dtype=np.uint8)
+        if d.size != self.nvox:
+            raise ValueError("distance field size mismatch")
+        self._check(self._lib.vxrt_cuda_upload_distance_field(self._h, _p(d)))
+
+    # -- tables --
+    def set_block_data(self, table: np.ndarray):
+        t = np.ascontiguousarray(table, dtype=np.int32)
+        if t.size != 6 * 128:
+            raise ValueError("block data table must be 6 x 128 int32")
+        self._check(self._lib.vxrt_cuda_set_block_data(self._h, _p(t)))
+
+    def set_blue_noise(self, data: np.ndarray):
+        d = np.ascontiguousarray(data, dtype=np.int32)
+        self._check(self._lib.vxrt_cuda_set_blue_noise(self._h, _p(d), d.size))
+
+    def set_blue_noise_texture(self, rgba: np.ndarray):
+        t = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = t.shape[0], t.shape[1]
+        self._check(self._lib.vxrt_cuda_set_blue_noise_texture(self._h, _p(t), w, h))
+
+    # -- passes --
+    def initial_trace(self, cam, width: int, height: int, render_distance: int = 350, jitter=None, tile=(0, 0)):
+        p = abi.PrimaryParams()
+        _fill(p.inv_view, cam.inv_view)
+        _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = width, height
+        if jitter is not None:
+            p.jitter[0], p.jitter[1] = float(jitter[0]), float(jitter[1])
+            p.jitter_on = 1
+        p.render_distance = render_distance
+        p.alpha_test = 0
+        p.tile.row0, p.tile.rows = tile
+        self._check(self._lib.vxrt_cuda_initial_trace(self._h, C.byref(p)))
+        return p
+
+    def shadow_trace(self, cam, width: int, height: int, light_direction, frame: int = 0, halton=(0.0, 0.0),
+                     soft: bool = True, max_iterations: int = 350, tile=(0, 0)):
+        p = abi.ShadowParams()
+        _fill(p.inv_view, cam.inv_view)
+        _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = width, height
+        _fill(p.light_direction, light_direction)
+        p.current_frame = frame
+        p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
+        p.soft_shadows = int(soft)
+        p.alpha_test = 0
+        p.max_iterations = max_iterations
+        p.tile.row0, p.tile.rows = tile
+        self._check(self._lib.vxrt_cuda_shadow_trace(self._h, C.byref(p)))
+        return p
+
+    # -- attachments --
+    def attachment_info(self, att: int):
+        ptr, w, h, bpp = C.c_void_p(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.vxrt_cuda_attachment_device(self._h, att, C.byref(ptr), C.byref(w), C.byref(h), C.byref(bpp)))
+        return ptr.value, w.value, h.value, bpp.value
+
+    def read_attachment(self, att: int, out: np.ndarray | None = None) -> np.ndarray:
+        _, w, h, bpp = self.attachment_info(att)
+        dt, ch = _ATT_DTYPES[att]
+        shape = (h, w) if ch == 1 else (h, w, ch)
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        assert out.nbytes == w * h * bpp
+        self._check(self._lib.vxrt_cuda_read_attachment(self._h, att, _p(out), out.nbytes))
+        return out
+
+    def attachment_as_device_array(self, att: int):
+        """Zero-copy view for torch.as_tensor(..., device='cuda') (NCCL tile gathers)."""
+        ptr, w, h, bpp = self.attachment_info(att)
+        dt, ch = _ATT_DTYPES[att]
+        shape = (h, w) if ch == 1 else (h, w, ch)
+        return _DeviceArray(ptr, shape, np.dtype(dt).str)
+
+    # -- statistics --
+    def stats_enable(self, on: bool):
+        self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))
+
+    def stats_read(self, reset: bool = True) -> dict:
+        s = abi.TraceStats()
+        self._check(self._lib.vxrt_cuda_stats_read(self._h, C.byref(s), int(reset)))
+        return {"rays": s.rays, "iterations": s.iterations, "dda_steps": s.dda_steps, "hits": s.hits}

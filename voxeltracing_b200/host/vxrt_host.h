@@ -1,0 +1,48 @@
+/*
+ * vxrt_host.h — host-side mirror of the reference's C++ producers of the hot path's inputs:
+ * camera matrices (Core/FpsCamera.cpp, glm), TAA jitter (Core/TAAJitter.cpp), sun/moon direction
+ * (Core/Pipeline.cpp:1731-1749), world container + raw save format (Core/World.h,
+ * Core/WorldFileHandler.cpp), deterministic stand-in world generators and the
+ * block database (Core/BlockDatabaseParser.cpp, Core/BlockDataSSBO.cpp).
+ * Plain C ABI so the parity tests and bench (Python, ctypes) and a C++ engine can both use it.
+ */
+#ifndef VXRT_HOST_H
+#define VXRT_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* glm::perspective(radians(fov_deg), aspect, near, far) — column-major out[16] */
+void vxh_perspective(float fov_deg, float aspect, float z_near, float z_far, float* out16);
+/* glm::lookAt(eye, center, up) */
+void vxh_look_at(const float* eye, const float* center, const float* up, float* out16);
+/* glm::inverse(mat4) */
+void vxh_inverse(const float* m16, float* out16);
+/* FPSCamera: front from yaw/pitch (FpsCamera.cpp:66-70), view = lookAt(pos, pos+front, (0,1,0)),
+ * proj = perspective(fov, aspect, 0.1, 1000) (Player.cpp:10); outputs may be NULL.               */
+void vxh_camera(const float* pos, float yaw_deg, float pitch_deg, float fov_deg, float aspect,
+                float* view16, float* proj16, float* inv_view16, float* inv_proj16);
+/* Halton(2,3) jitter of GenerateJitterStuff / GetTAAJitter (TAAJitter.cpp:6-41) */
+void vxh_taa_jitter(int32_t frame, float* out2);
+/* Pipeline.cpp:1731-1749: sun = normalize(Rz(2*sun_tick deg) * (1,1,1)), moon = (-x,-y,z),
+ * stronger = (-sun.y < 0.01) ? sun : moon                                                        */
+void vxh_sun_direction(float sun_tick, float* sun3, float* moon3, float* stronger3);
+
+/* deterministic stand-in worlds; blocks is nx*ny*nz bytes, x fastest */
+void vxh_gen_plains(uint32_t seed, int32_t structures, int32_t nx, int32_t ny, int32_t nz, uint8_t* blocks);
+void vxh_gen_rooms(uint32_t seed, int32_t nx, int32_t ny, int32_t nz, uint8_t* blocks);
+void vxh_gen_town(uint32_t seed, int32_t nx, int32_t ny, int32_t nz, uint8_t* blocks);
+/* config-2 edit list: n random toggles (solid -> 0, air -> id 3) applied to `blocks` in order;
+ * xyz_id receives n x {x,y,z,id}.  PRNG: mt19937(seed).                                          */
+void vxh_random_edits(uint32_t seed, int32_t n, int32_t nx, int32_t ny, int32_t nz, uint8_t* blocks,
+                      int32_t* xyz_id);
+
+/* raw headerless world dump (WorldFileHandler.cpp:10-83); 0 on success */
+int32_t vxh_world_save(const char* path, const uint8_t* blocks, int64_t nbytes);
+int32_t vxh_world_load(const char* path, uint8_t* blocks, int64_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
