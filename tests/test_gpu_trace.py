@@ -59,7 +59,7 @@ def test_primary_jitter_odd_size_and_outside_camera(scene):
     # camera outside the volume: rays are clipped to the box first (InitialRayTraceFrag.glsl:448-452)
     cam = host_api.camera([-60, 150, -40], 45.0, -30.0, 16 / 9)
     got, want = _compare_primary(c, ow, cam, 320, 180)
-    assert (want["block"] > 0).mean() > 0.2
+    assert (want["block"] > 0).mean() > 0.05
     for k in ("block", "normal"):
         assert np.array_equal(got[k], want[k])
     assert np.array_equal(got["t"].view(np.uint16), want["t"].view(np.uint16))
