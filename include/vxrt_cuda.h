@@ -79,6 +79,21 @@ int vxrt_cuda_set_blue_noise(vxrt_ctx* ctx, const int32_t* data, int32_t count /
 /* BluenoiseTexture (Core/Pipeline.cpp:1532): RGBA8, w x h (256 x 256), file row 0 first. */
 int vxrt_cuda_set_blue_noise_texture(vxrt_ctx* ctx, const uint8_t* rgba8, int32_t w, int32_t h);
 
+typedef enum vxrt_texture_kind {
+    VXRT_TEX_ALBEDO = 0,  /* GL_SRGB_ALPHA: decoded to linear before filtering */
+    VXRT_TEX_NORMAL = 1,
+    VXRT_TEX_PBR = 2,
+    VXRT_TEX_EMISSIVE = 3
+} vxrt_texture_kind;
+/* TextureArray::CreateArray (Core/GLClasses/TextureArray.cpp:10-69): level-0 texels
+ * layers*h*w*4 bytes, file row 0 first; the mip chain is built inside (2x2 box filter,
+ * albedo averaged in linear light).  w == h, power of two.                                   */
+int vxrt_cuda_set_texture_array(vxrt_ctx* ctx, int32_t kind, int32_t layers, int32_t w, int32_t h,
+                                const uint8_t* rgba8);
+/* Sky cubemap consumed by GI / reflections (Core/Pipeline.cpp:1468-1470, 2339, 3207):
+ * 6 faces (+X,-X,+Y,-Y,+Z,-Z) of res*res RGB float32, rows as uploaded with glTexImage2D.    */
+int vxrt_cuda_set_skymap(vxrt_ctx* ctx, int32_t res, const float* rgb_faces);
+
 /* ---- attachments (the FBO colour attachments of Core/Pipeline.cpp:1142-1202) ---- */
 typedef enum vxrt_attachment {
     VXRT_ATT_INITIAL_T = 0,        /* R16F  hit distance, -1 = miss   InitialTraceFBO[0] */
@@ -144,6 +159,103 @@ typedef struct vxrt_shadow_params {
     vxrt_tile tile;
 } vxrt_shadow_params;
 int vxrt_cuda_shadow_trace(vxrt_ctx* ctx, const vxrt_shadow_params* p);
+
+/* ---- hit-material fetch: GenerateGBuffer.glsl, Core/Pipeline.cpp:2147-2229 ----
+ * consumes INITIAL_INVT (R32F, bilinear), INITIAL_NORMAL, INITIAL_BLOCK; writes GBUF_*.
+ * Parallax mapping (u_POM) is off by default and not implemented; lava's animated 3-D textures are
+ * not modelled (a lava block is shaded from its ordinary array layers).                            */
+typedef struct vxrt_gbuffer_params {
+    float inv_view[16];
+    float inv_projection[16];
+    int32_t width, height;
+    int32_t grass_props[10];   /* u_GrassBlockProps  (Pipeline.cpp:2177-2186) */
+    int32_t cactus_props[10];  /* u_CactusBlockProps (Pipeline.cpp:2166-2175) */
+    vxrt_tile tile;
+} vxrt_gbuffer_params;
+int vxrt_cuda_generate_gbuffer(vxrt_ctx* ctx, const vxrt_gbuffer_params* p);
+
+/* ---- Cook-Torrance direct term of the colour pass: ColorPassFrag.glsl:394-451, 776, 812-816,
+ * 886-899, 1201-1210, dispatched at Core/Pipeline.cpp:3702-3918 ----
+ * consumes INITIAL_INVT, GBUF_* and SHADOW (raw trace; the shadow denoiser is out of scope);
+ * writes DIRECT = max(mix(SunDirect, MoonDirect, SunVisibility) * !(emissive > 0.05), 1e-6).        */
+typedef struct vxrt_direct_params {
+    float inv_view[16];
+    float inv_projection[16];
+    int32_t width, height;
+    float viewer_position[3];  /* u_ViewerPosition */
+    float sun_direction[3];    /* u_SunDirection */
+    float moon_direction[3];   /* u_MoonDirection */
+    float sun_color[3];        /* SampleSunColor()  — caller supplied, the sky model is out of scope */
+    float moon_color[3];       /* SampleMoonColor() */
+    float texture_desat_amount; /* u_TextureDesatAmount (0.1, Pipeline.cpp:245) */
+    int32_t amplify_normal_map; /* u_AmplifyNormalMap (false, Pipeline.cpp:276) */
+    vxrt_tile tile;
+} vxrt_direct_params;
+int vxrt_cuda_shade_direct(vxrt_ctx* ctx, const vxrt_direct_params* p);
+
+/* ---- diffuse GI: DiffuseRayTraceFrag.glsl, Core/Pipeline.cpp:2267-2374 ----
+ * consumes INITIAL_T (bilinear) + INITIAL_NORMAL, grids, BlockData, blue-noise tables, albedo / PBR /
+ * emissive arrays, sky cube map; writes GI_*.  Direct light sampling / MIS (off by default,
+ * Pipeline.cpp:80) and the hash RNG (u_UseBlueNoise = false) are not implemented.                  */
+typedef struct vxrt_gi_params {
+    float inv_view[16];
+    float inv_projection[16];
+    int32_t width, height;           /* u_Dimensions of the GI target */
+    int32_t spp;                     /* u_SPP (3) */
+    int32_t checker_spp;             /* u_CheckerSPP = (spp + spp%2)/2 */
+    int32_t checkerboard;            /* CHECKERBOARD_SPP */
+    int32_t trace_length;            /* u_DiffuseTraceLength (48) */
+    int32_t shadow_trace_length;     /* GetShadowAt loop cap (128, DiffuseRayTraceFrag.glsl:1306) */
+    int32_t current_frame;           /* u_CurrentFrame */
+    int32_t current_frame_mod128;    /* u_CurrentFrameMod128 */
+    int32_t use_blue_noise;          /* u_UseBlueNoise (must be 1) */
+    int32_t supersample;             /* u_Supersample */
+    float halton[2];                 /* u_Halton */
+    float sun_direction[3];          /* u_SunDirection */
+    float moon_direction[3];         /* u_MoonDirection */
+    float sun_visibility;            /* u_SunVisibility */
+    float gi_sun_strength;           /* u_GISunStrength (1.0) */
+    float gi_sky_strength;           /* u_GISkyStrength (1.125) */
+    float diffuse_light_intensity;   /* u_DiffuseLightIntensity (1.25) */
+    float viewer_position[3];        /* u_ViewerPosition */
+    int32_t apply_player_shadow;     /* u_APPLY_PLAYER_SHADOW (false) */
+    vxrt_tile tile;
+} vxrt_gi_params;
+int vxrt_cuda_diffuse_trace(vxrt_ctx* ctx, const vxrt_gi_params* p);
+
+/* ---- reflections: ReflectionTraceFrag.glsl, Core/Pipeline.cpp:3096-3257 ----
+ * consumes INITIAL_T/NORMAL, GBUF_NORMAL/PBR, GI_SH/COCG/AOSKY, SHADOW; writes REFL_*.
+ * LPV ambient (u_LPVGI), projected clouds (u_CloudReflections), player reflection and lava UV
+ * distortion depend on out-of-scope subsystems and must be off.                                    */
+typedef struct vxrt_reflection_params {
+    float inv_view[16];
+    float inv_projection[16];
+    float view[16];                  /* u_View */
+    float projection[16];            /* u_Projection */
+    int32_t width, height;
+    int32_t spp;                     /* u_SPP (2) */
+    int32_t checkerboard;            /* CHECKERBOARD_SPEC_SPP */
+    int32_t trace_length;            /* u_ReflectionTraceLength (64) */
+    int32_t shadow_trace_length;     /* 150 (ReflectionTraceFrag.glsl:1098) */
+    int32_t current_frame;
+    int32_t current_frame_mod128;
+    int32_t use_blue_noise;          /* must be 1 */
+    int32_t rough_reflections;       /* u_RoughReflections */
+    int32_t roughness_bias;          /* u_RoughnessBias */
+    int32_t temporal;                /* TEMPORAL_SPEC / u_TemporalFilterReflections */
+    int32_t reproject_to_screen_space; /* u_ReprojectToScreenSpace */
+    int32_t derive_from_diffuse_sh;  /* u_DeriveFromDiffuseSH */
+    float halton[2];
+    float sun_direction[3];
+    float moon_direction[3];
+    float stronger_light_direction[3];
+    float viewer_position[3];
+    float sun_strength_modifier;     /* u_SunStrengthModifier (0.85) */
+    float moon_strength_modifier;    /* u_MoonStrengthModifier */
+    int32_t grass_props[10];
+    vxrt_tile tile;
+} vxrt_reflection_params;
+int vxrt_cuda_reflection_trace(vxrt_ctx* ctx, const vxrt_reflection_params* p);
 
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {

@@ -145,3 +145,123 @@ class OracleWorld:
         if want_stats:
             out["stats"] = {"rays": st.rays, "iterations": st.iterations, "dda_steps": st.dda_steps, "hits": st.hits}
         return out
+
+
+# ---- scene (tables, texture arrays, sky map) + material / direct / GI / reflection passes ----------
+
+class ReflectionInputs(C.Structure):
+    _fields_ = [
+        ("g_t_half", C.c_void_p), ("g_normal", C.c_void_p), ("gw", C.c_int32), ("gh", C.c_int32),
+        ("gb_normal_h3", C.c_void_p), ("gb_pbr_u8x4", C.c_void_p), ("mw", C.c_int32), ("mh", C.c_int32),
+        ("gi_sh_h4", C.c_void_p), ("gi_cocg_h2", C.c_void_p), ("gi_aosky_u8x2", C.c_void_p), ("iw", C.c_int32), ("ih", C.c_int32),
+        ("shadow_u8", C.c_void_p), ("sw", C.c_int32), ("sh", C.c_int32),
+    ]
+
+
+def _scene_sigs(L):
+    if getattr(L, "_scene_sigs_done", False):
+        return
+    vp, i32, P = C.c_void_p, C.c_int32, C.POINTER
+    L.vxo_scene_create.restype = vp
+    L.vxo_scene_create.argtypes = [P(World)]
+    L.vxo_scene_destroy.argtypes = [vp]
+    L.vxo_scene_set_block_data.argtypes = [vp, vp]
+    L.vxo_scene_set_blue_noise.argtypes = [vp, vp, i32]
+    L.vxo_scene_set_texture_array.argtypes = [vp, i32, i32, i32, i32, vp]
+    L.vxo_scene_set_skymap.argtypes = [vp, i32, vp]
+    L.vxo_scene_texture_level.argtypes = [vp, i32, i32, vp, C.c_int64]
+    L.vxo_scene_texture_level.restype = i32
+    L.vxo_generate_gbuffer.argtypes = [vp, P(abi.GBufferParams), vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.vxo_shade_direct.argtypes = [P(abi.DirectParams), vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp]
+    L.vxo_diffuse_trace.argtypes = [vp, P(abi.GIParams), vp, vp, i32, i32, vp, vp, vp, vp, P(abi.TraceStats)]
+    if hasattr(L, "vxo_reflection_trace"):
+        L.vxo_reflection_trace.argtypes = [vp, P(abi.ReflectionParams), P(ReflectionInputs), vp, vp, vp, P(abi.TraceStats)]
+    L._scene_sigs_done = True
+
+
+def _stats(st):
+    return {"rays": st.rays, "iterations": st.iterations, "dda_steps": st.dda_steps, "hits": st.hits}
+
+
+class OracleScene:
+    """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
+
+    def __init__(self, world: OracleWorld):
+        self.world = world
+        self.L = lib()
+        _scene_sigs(self.L)
+        self.h = self.L.vxo_scene_create(C.byref(world.c))
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.L.vxo_scene_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_block_data(self, table):
+        t = np.ascontiguousarray(table, dtype=np.int32)
+        self.L.vxo_scene_set_block_data(self.h, _p(t))
+
+    def set_blue_noise(self, data):
+        d = np.ascontiguousarray(data, dtype=np.int32)
+        self.L.vxo_scene_set_blue_noise(self.h, _p(d), d.size)
+
+    def set_texture_array(self, kind, rgba):
+        t = np.ascontiguousarray(rgba, dtype=np.uint8)
+        self.L.vxo_scene_set_texture_array(self.h, kind, t.shape[0], t.shape[2], t.shape[1], _p(t))
+
+    def set_skymap(self, faces):
+        f = np.ascontiguousarray(faces, dtype=np.float32)
+        self.L.vxo_scene_set_skymap(self.h, f.shape[1], _p(f))
+
+    def texture_level(self, kind, level, layers, size):
+        s = max(size >> level, 1)
+        out = np.zeros((layers, s, s, 4), dtype=np.uint8)
+        rc = self.L.vxo_scene_texture_level(self.h, kind, level, _p(out), out.nbytes)
+        assert rc == 0, rc
+        return out
+
+    def generate_gbuffer(self, p: abi.GBufferParams, g_inv_t, g_normal, g_block):
+        gh, gw = g_inv_t.shape
+        w, h = p.width, p.height
+        out = {"albedo": np.zeros((h, w, 3), np.float16), "normal": np.zeros((h, w, 3), np.float16),
+               "pbr": np.zeros((h, w, 4), np.uint8), "texao": np.zeros((h, w), np.uint8)}
+        self.L.vxo_generate_gbuffer(self.h, C.byref(p), _p(np.ascontiguousarray(g_inv_t, np.float32)), _p(np.ascontiguousarray(g_normal, np.uint8)),
+                                    _p(np.ascontiguousarray(g_block, np.uint8)), gw, gh, _p(out["albedo"]), _p(out["normal"]), _p(out["pbr"]), _p(out["texao"]))
+        return out
+
+    def shade_direct(self, p: abi.DirectParams, g_inv_t, gb, shadow):
+        gh, gw = g_inv_t.shape
+        mh, mw = gb["texao"].shape
+        sh, sw = shadow.shape
+        out = np.zeros((p.height, p.width, 3), np.float16)
+        self.L.vxo_shade_direct(C.byref(p), _p(np.ascontiguousarray(g_inv_t, np.float32)), gw, gh, _p(gb["albedo"]), _p(gb["normal"]), _p(gb["pbr"]),
+                                _p(gb["texao"]), mw, mh, _p(np.ascontiguousarray(shadow, np.uint8)), sw, sh, _p(out))
+        return out
+
+    def diffuse_trace(self, p: abi.GIParams, g_t, g_normal):
+        gh, gw = g_t.shape
+        w, h = p.width, p.height
+        out = {"sh": np.zeros((h, w, 4), np.float16), "cocg": np.zeros((h, w, 2), np.float16), "utility": np.zeros((h, w), np.float16),
+               "aosky": np.zeros((h, w, 2), np.uint8)}
+        st = abi.TraceStats()
+        self.L.vxo_diffuse_trace(self.h, C.byref(p), _p(np.ascontiguousarray(g_t, np.float16)), _p(np.ascontiguousarray(g_normal, np.uint8)), gw, gh,
+                                 _p(out["sh"]), _p(out["cocg"]), _p(out["utility"]), _p(out["aosky"]), C.byref(st))
+        out["stats"] = _stats(st)
+        return out
+
+    def reflection_trace(self, p: abi.ReflectionParams, g_t, g_normal, gb, gi, shadow):
+        gh, gw = g_t.shape
+        mh, mw = gb["texao"].shape
+        ih, iw = gi["utility"].shape
+        sh, sw = shadow.shape
+        keep = [np.ascontiguousarray(g_t, np.float16), np.ascontiguousarray(g_normal, np.uint8), np.ascontiguousarray(shadow, np.uint8)]
+        ri = ReflectionInputs(keep[0].ctypes.data, keep[1].ctypes.data, gw, gh, gb["normal"].ctypes.data, gb["pbr"].ctypes.data, mw, mh,
+                              gi["sh"].ctypes.data, gi["cocg"].ctypes.data, gi["aosky"].ctypes.data, iw, ih, keep[2].ctypes.data, sw, sh)
+        w, h = p.width, p.height
+        out = {"color": np.zeros((h, w, 4), np.float16), "hitdist": np.zeros((h, w), np.float16), "emissive": np.zeros((h, w), np.uint8)}
+        st = abi.TraceStats()
+        self.L.vxo_reflection_trace(self.h, C.byref(p), C.byref(ri), _p(out["color"]), _p(out["hitdist"]), _p(out["emissive"]), C.byref(st))
+        out["stats"] = _stats(st)
+        return out

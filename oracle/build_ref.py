@@ -36,11 +36,42 @@ SHADERS = {
     "DiffuseRayTraceFrag": ("DiffuseRayTraceFrag.glsl", "fragment"),
     "ReflectionTraceFrag": ("ReflectionTraceFrag.glsl", "fragment"),
     "GenerateGBuffer": ("GenerateGBuffer.glsl", "fragment"),
-    "ColorPassFrag": ("ColorPassFrag.glsl", "fragment"),
+    # the colour pass composites sky / clouds / denoised GI (out of scope); only its Cook-Torrance
+    # functions are compiled: they are cut out of the file by name, unmodified
+    "ColorPassDirect": ("ColorPassFrag.glsl", "extract"),
+}
+EXTRACT = {
+    "ColorPassDirect": {
+        "prelude": "#define PI 3.14159265359\nuniform vec3 u_ViewerPosition;\n"
+                   "vec3 FresnelSchlickRoughness(vec3 Eye, vec3 norm, vec3 F0, float roughness);\n",
+        "functions": ["ndfGGX", "gaSchlickG1", "gaSchlickGGX", "CalculateDirectionalLight", "FresnelSchlickRoughness", "BasicSaturation"],
+    }
 }
 
+
+def extract_functions(text: str, names) -> str:
+    """Cut whole function definitions (all overloads) out of a GLSL file, in file order."""
+    text = strip_comments(text)
+    out = []
+    pat = re.compile(r"^[ \t]*(?:float|vec[234]|void|int|bool)\s+(\w+)\s*\([^;{]*\)\s*\{", re.M)
+    for m in pat.finditer(text):
+        if m.group(1) not in names:
+            continue
+        depth, j = 0, m.end() - 1
+        while j < len(text):
+            if text[j] == "{":
+                depth += 1
+            elif text[j] == "}":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        out.append(text[m.start():j + 1])
+    return "\n\n".join(out)
+
+
 TYPES = (r"(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|bvec[234]|mat[34](?:x[34])?|"
-         r"sampler2D|sampler3D|sampler2DArray|samplerCube|image3D|Ray|[A-Z]\w*)")
+         r"sampler2D|sampler3D|usampler3D|sampler2DArray|samplerCube|image3D|Ray|[A-Z]\w*)")
 
 
 def strip_comments(src: str) -> str:
@@ -83,8 +114,47 @@ def fix_array_constructors(src: str) -> str:
         open_i = m.end() - 1
         close_i = match_paren(src, open_i)
         src = src[:m.start()] + "{" + src[open_i + 1:close_i] + "}" + src[close_i + 1:]
+    # functions returning arrays: `float[6] f(` -> `arr<float, 6> f(`;  `float x[6] = f(...)` -> `auto x = f(...)`
+    src = re.sub(r"\b(float|int|vec[234])\s*\[\s*(\d+)\s*\]\s+(\w+)\s*\(", r"arr<\1, \2> \3(", src)
+    src = re.sub(r"\b(?:float|int|vec[234])\s+(\w+)\s*\[\s*\d+\s*\]\s*=\s*(?![\s{])", r"auto \1 = ", src)
     # `const vec2[4] name = {` -> `const vec2 name[4] = {`
     src = re.sub(r"\b(" + TYPES + r")\s*\[\s*(\w+)\s*\]\s+(\w+)\s*=", r"\1 \3[\2] =", src)
+    return src
+
+
+def wrap_call_swizzles(src: str) -> str:
+    """`f(args).xy` -> `vec2(f(args).xy)`: a swizzle of a temporary must be materialised before the
+    temporary dies or is copied (e.g. as an operand of ?:)."""
+    pat = re.compile(r"\)\s*\.([xyzw]{2,4}|[rgba]{2,4}|[stpq]{2,4})\b(?!\s*\()")
+    pos = 0
+    while True:
+        m = pat.search(src, pos)
+        if not m:
+            break
+        close_i = m.start()
+        depth, j = 0, close_i
+        while j >= 0:
+            if src[j] == ")":
+                depth += 1
+            elif src[j] == "(":
+                depth -= 1
+                if depth == 0:
+                    break
+            j -= 1
+        k = j
+        while k > 0 and (src[k - 1].isalnum() or src[k - 1] == "_"):
+            k -= 1
+        name = src[k:j]
+        n = len(m.group(1))
+        if not name or name in ("if", "while", "for", "return", "switch"):
+            pos = m.end()
+            continue
+        # integer-valued built-ins keep their integer type
+        ctor = ("ivec%d" if name in ("textureSize", "ivec2", "ivec3", "ivec4") else "vec%d") % n
+        if name in ("uvec2", "uvec3", "uvec4"):
+            ctor = "uvec%d" % n
+        src = src[:k] + ctor + "(" + src[k:m.end()] + ")" + src[m.end():]
+        pos = m.end() + len(ctor) + 2
     return src
 
 
@@ -175,6 +245,7 @@ def transform(name: str, text: str, kind: str) -> str:
     resets: list = []
     src = fix_globals(src, kind, resets)
     src = fix_param_qualifiers(src)
+    src = wrap_call_swizzles(src)
     src = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", src)
     src = re.sub(r"\bdiscard\s*;", "{ shader_discarded = true; return; }", src)
     # mat3(mat4) constructor
@@ -232,7 +303,10 @@ def main():
         if n not in want:
             continue
         cpp = GEN / f"{n}.cpp"
-        cpp.write_text(transform(n, (sdir / SHADERS[n][0]).read_text(errors="replace"), SHADERS[n][1]))
+        text = (sdir / SHADERS[n][0]).read_text(errors="replace")
+        if SHADERS[n][1] == "extract":
+            text = EXTRACT[n]["prelude"] + extract_functions(text, EXTRACT[n]["functions"])
+        cpp.write_text(transform(n, text, SHADERS[n][1]))
         obj = GEN / f"{n}.o"
         cmd = ["g++", "-std=gnu++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fopenmp", "-w", "-fpermissive",
                "-c", str(cpp), "-o", str(obj)]

@@ -30,11 +30,16 @@ template <class T, int N> struct vecn;
 /* swizzle proxy: lives inside the union of its parent vector, addresses the parent's storage */
 template <class T, int N, int A, int B, int C = -1, int D = -1>
 struct swz {
+    swz() = default;
+    swz(const swz&) = delete; /* a copied proxy would lose its parent vector: build_ref.py wraps such uses */
     T* p() { return reinterpret_cast<T*>(this); }
     const T* p() const { return reinterpret_cast<const T*>(this); }
     operator vecn<T, N>() const;
-    template <class U, class = std::enable_if_t<!std::is_same<U, T>::value>>
+    template <class U, class = std::enable_if_t<!std::is_same<U, T>::value && !(std::is_same<U, float>::value && std::is_integral<T>::value && !std::is_same<T, bool>::value)>>
     explicit operator vecn<U, N>() const { return vecn<U, N>((vecn<T, N>)(*this)); }
+    /* GLSL converts integer vectors to float vectors implicitly (e.g. vec2 r = textureSize(s, 0).xy) */
+    template <class U = T, class = std::enable_if_t<std::is_integral<U>::value && !std::is_same<U, bool>::value>>
+    operator vecn<float, N>() const { return vecn<float, N>((vecn<T, N>)(*this)); }
     swz& operator=(const vecn<T, N>& v);
     swz& operator=(const swz& o) { return *this = (vecn<T, N>)o; }
     template <int A2, int B2, int C2, int D2> swz& operator=(const swz<T, N, A2, B2, C2, D2>& o) { return *this = (vecn<T, N>)o; }
@@ -249,6 +254,7 @@ inline float length(float a) { return ::fabsf(a); }
 inline float length(const vec2& a) { return ::sqrtf(dot(a, a)); }
 inline float length(const vec3& a) { return ::sqrtf(dot(a, a)); }
 inline float length(const vec4& a) { return ::sqrtf(dot(a, a)); }
+inline float distance(float a, float b) { return ::fabsf(b - a); }
 inline float distance(const vec2& a, const vec2& b) { return length(b - a); }
 inline float distance(const vec3& a, const vec3& b) { return length(b - a); }
 inline vec2 normalize(const vec2& a) { return a * (1.0f / ::sqrtf(dot(a, a))); }
@@ -318,11 +324,22 @@ inline mat3 inverse(const mat3& m) {
     return transpose(mat3(r0 * inv, r1 * inv, r2 * inv));
 }
 
+/* fixed-size arrays as function results (GLSL `float[6] f()`) */
+template <class T, int N> struct arr {
+    T v[N];
+    arr() {}
+    arr(const T (&a)[N]) { for (int i = 0; i < N; ++i) v[i] = a[i]; }
+    template <class... A, class = std::enable_if_t<sizeof...(A) == N>> arr(A... a) : v{T(a)...} {}
+    T& operator[](int i) { return v[i]; }
+    const T& operator[](int i) const { return v[i]; }
+};
+
 /* ---- resources ---- */
 struct sampler3D { const uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };     /* R8 unorm, NEAREST (Texture3D.cpp:20-27) */
 struct image3D { uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };             /* r8 image */
+struct usampler3D { const uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };    /* LPV block ids: never bound (LPV is off for parity) */
 typedef vxo::Tex2D sampler2D;
-typedef vxo::TexArray sampler2DArray;
+struct sampler2DArray { const vxo::TexArray* t = nullptr; };
 typedef vxo::TexCube samplerCube;
 
 inline vec4 texelFetch(const sampler3D& s, const ivec3& p, int) {
@@ -334,15 +351,20 @@ inline vec4 imageLoad(const image3D& s, const ivec3& p) {
 inline void imageStore(image3D& s, const ivec3& p, const vec4& v) {
     s.data[p.x + (size_t)p.y * s.w + (size_t)p.z * s.w * s.h] = vxo::float_to_unorm8(v.x);
 }
+/* filtered reads of 3-D textures only occur on the lava / LPV paths, which are disabled for parity */
+inline vec4 texture(const sampler3D&, const vec3&) { return vec4(0.0f); }
+inline uvec4 texture(const usampler3D&, const vec3&) { return uvec4(0u); }
+inline uvec4 texelFetch(const usampler3D&, const ivec3&, int) { return uvec4(0u); }
 inline vec4 to4(const vxo::v4& v) { return vec4(v.x, v.y, v.z, v.w); }
 inline vec4 texture(const sampler2D& s, const vec2& uv) { return to4(vxo::tex2d_sample(s, uv.x, uv.y)); }
 inline vec4 textureLod(const sampler2D& s, const vec2& uv, float) { return to4(vxo::tex2d_sample(s, uv.x, uv.y)); }
 inline vec4 texelFetch(const sampler2D& s, const ivec2& p, int) { return to4(vxo::tex2d_fetch(s, p.x, p.y)); }
 inline ivec2 textureSize(const sampler2D& s, int) { return ivec2(s.w, s.h); }
-inline vec4 textureLod(const sampler2DArray& s, const vec3& c, float lod) { return to4(vxo::texarray_sample(s, c.x, c.y, c.z, lod)); }
-inline vec4 texture(const sampler2DArray& s, const vec3& c) { return to4(vxo::texarray_sample(s, c.x, c.y, c.z, 0.0f)); } /* implicit LOD pinned to 0 */
-inline vec4 textureGrad(const sampler2DArray& s, const vec3& c, const vec2&, const vec2&) { return to4(vxo::texarray_sample(s, c.x, c.y, c.z, 0.0f)); }
-inline ivec3 textureSize(const sampler2DArray& s, int) { return ivec3(s.w, s.h, s.layers); }
+inline vec4 textureLod(const sampler2DArray& s, const vec3& c, float lod) { return to4(vxo::texarray_sample(*s.t, c.x, c.y, c.z, lod)); }
+inline vec4 texture(const sampler2DArray& s, const vec3& c) { return to4(vxo::texarray_sample(*s.t, c.x, c.y, c.z, 0.0f)); } /* implicit LOD pinned to 0 */
+inline vec4 texture(const sampler2DArray& s, const vec3& c, float bias) { return to4(vxo::texarray_sample(*s.t, c.x, c.y, c.z, bias)); }
+inline vec4 textureGrad(const sampler2DArray& s, const vec3& c, const vec2&, const vec2&) { return to4(vxo::texarray_sample(*s.t, c.x, c.y, c.z, 0.0f)); }
+inline ivec3 textureSize(const sampler2DArray& s, int) { return ivec3(s.t->w, s.t->h, s.t->layers); }
 inline vec4 texture(const samplerCube& s, const vec3& d) { return to4(vxo::texcube_sample(s, d.x, d.y, d.z)); }
 inline vec4 textureLod(const samplerCube& s, const vec3& d, float) { return to4(vxo::texcube_sample(s, d.x, d.y, d.z)); }
 

@@ -66,3 +66,70 @@ def shadow_trace(blocks, df, params: abi.ShadowParams, g_t, g_normal, blue_rgba)
     lib().vxref_shadow_trace(_p(blocks), _p(df), C.byref(params), _p(g_t), _p(g_normal), gw, gh, _p(blue_rgba),
                              blue_rgba.shape[1], blue_rgba.shape[0], _p(out["shadow"]), _p(out["transversal"]))
     return out
+
+
+# ---- scene resources + material / GI / reflection shaders -------------------------------------------
+_keep = {}
+
+
+def set_scene(blocks, df, table, blue_noise, textures, skymap):
+    """textures: {kind: uint8[layers, size, size, 4]}"""
+    L = lib()
+    _keep["blocks"] = np.ascontiguousarray(blocks, np.uint8)
+    _keep["df"] = np.ascontiguousarray(df, np.uint8)
+    L.vxref_set_world(_p(_keep["blocks"]), _p(_keep["df"]))
+    t = np.ascontiguousarray(table, np.int32)
+    L.vxref_set_block_data(_p(t))
+    b = np.ascontiguousarray(blue_noise, np.int32)
+    L.vxref_set_blue_noise(_p(b), b.size)
+    for kind, tex in textures.items():
+        tex = np.ascontiguousarray(tex, np.uint8)
+        L.vxref_set_texture_array(kind, tex.shape[0], tex.shape[2], tex.shape[1], _p(tex))
+    f = np.ascontiguousarray(skymap, np.float32)
+    L.vxref_set_skymap(f.shape[1], _p(f))
+
+
+def generate_gbuffer(p: abi.GBufferParams, g_inv_t, g_normal, g_block):
+    gh, gw = g_inv_t.shape
+    w, h = p.width, p.height
+    out = {"albedo": np.zeros((h, w, 3), np.float16), "normal": np.zeros((h, w, 3), np.float16),
+           "pbr": np.zeros((h, w, 4), np.uint8), "texao": np.zeros((h, w), np.uint8)}
+    lib().vxref_generate_gbuffer(C.byref(p), _p(np.ascontiguousarray(g_inv_t, np.float32)), _p(np.ascontiguousarray(g_normal, np.uint8)),
+                                 _p(np.ascontiguousarray(g_block, np.uint8)), gw, gh, _p(out["albedo"]), _p(out["normal"]), _p(out["pbr"]), _p(out["texao"]))
+    return out
+
+
+def diffuse_trace(p: abi.GIParams, g_t, g_normal):
+    gh, gw = g_t.shape
+    w, h = p.width, p.height
+    out = {"sh": np.zeros((h, w, 4), np.float16), "cocg": np.zeros((h, w, 2), np.float16), "utility": np.zeros((h, w), np.float16),
+           "aosky": np.zeros((h, w, 2), np.uint8)}
+    lib().vxref_diffuse_trace(C.byref(p), _p(np.ascontiguousarray(g_t, np.float16)), _p(np.ascontiguousarray(g_normal, np.uint8)), gw, gh,
+                              _p(out["sh"]), _p(out["cocg"]), _p(out["utility"]), _p(out["aosky"]))
+    return out
+
+
+def shade_direct(p: abi.DirectParams, g_inv_t, gb, shadow):
+    gh, gw = g_inv_t.shape
+    mh, mw = gb["texao"].shape
+    sh, sw = shadow.shape
+    out = np.zeros((p.height, p.width, 3), np.float16)
+    lib().vxref_shade_direct(C.byref(p), _p(np.ascontiguousarray(g_inv_t, np.float32)), gw, gh, _p(gb["albedo"]), _p(gb["normal"]), _p(gb["pbr"]),
+                             _p(gb["texao"]), mw, mh, _p(np.ascontiguousarray(shadow, np.uint8)), sw, sh, _p(out))
+    return out
+
+
+def reflection_trace(p: abi.ReflectionParams, g_t, g_normal, gb, gi, shadow):
+    from oracle.binding import ReflectionInputs
+
+    gh, gw = g_t.shape
+    mh, mw = gb["texao"].shape
+    ih, iw = gi["utility"].shape
+    sh, sw = shadow.shape
+    keep = [np.ascontiguousarray(g_t, np.float16), np.ascontiguousarray(g_normal, np.uint8), np.ascontiguousarray(shadow, np.uint8)]
+    ri = ReflectionInputs(keep[0].ctypes.data, keep[1].ctypes.data, gw, gh, gb["normal"].ctypes.data, gb["pbr"].ctypes.data, mw, mh,
+                          gi["sh"].ctypes.data, gi["cocg"].ctypes.data, gi["aosky"].ctypes.data, iw, ih, keep[2].ctypes.data, sw, sh)
+    w, h = p.width, p.height
+    out = {"color": np.zeros((h, w, 4), np.float16), "hitdist": np.zeros((h, w), np.float16), "emissive": np.zeros((h, w), np.uint8)}
+    lib().vxref_reflection_trace(C.byref(p), C.byref(ri), _p(out["color"]), _p(out["hitdist"]), _p(out["emissive"]))
+    return out

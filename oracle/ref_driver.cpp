@@ -29,6 +29,19 @@ thread_local uvec3 gl_GlobalInvocationID;
 #include "ShadowRayTraceFrag.cpp"
 #endif
 
+#ifdef VXREF_HAVE_GenerateGBuffer
+#include "GenerateGBuffer.cpp"
+#endif
+#ifdef VXREF_HAVE_DiffuseRayTraceFrag
+#include "DiffuseRayTraceFrag.cpp"
+#endif
+#ifdef VXREF_HAVE_ReflectionTraceFrag
+#include "ReflectionTraceFrag.cpp"
+#endif
+#ifdef VXREF_HAVE_ColorPassDirect
+#include "ColorPassDirect.cpp"
+#endif
+
 #include "../include/vxrt_cuda.h"
 #include <omp.h>
 
@@ -53,6 +66,18 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_ShadowRayTraceFrag
     m |= 16;
+#endif
+#ifdef VXREF_HAVE_GenerateGBuffer
+    m |= 32;
+#endif
+#ifdef VXREF_HAVE_DiffuseRayTraceFrag
+    m |= 64;
+#endif
+#ifdef VXREF_HAVE_ReflectionTraceFrag
+    m |= 128;
+#endif
+#ifdef VXREF_HAVE_ColorPassDirect
+    m |= 256;
 #endif
     return m;
 }
@@ -168,6 +193,249 @@ void vxref_shadow_trace(const uint8_t* blocks, const uint8_t* df, const vxrt_sha
             size_t i = (size_t)py * W + px;
             shadow_u8[i] = vxo::float_to_unorm8(S::o_Shadow);
             transversal_half[i] = vxo::float_to_half(S::o_IntersectionTransversal);
+        }
+}
+#endif
+
+
+/* ---- scene resources shared by the material / GI / reflection shaders ---- */
+static struct RefScene {
+    const uint8_t* blocks = nullptr; const uint8_t* df = nullptr;
+    int32_t block_data[6 * 128];
+    std::vector<int32_t> blue;
+    vxo::TexArray tex[4];
+    std::vector<float> sky; vxo::TexCube cube;
+} g_scene;
+
+void vxref_set_world(const uint8_t* blocks, const uint8_t* df) { g_scene.blocks = blocks; g_scene.df = df; }
+void vxref_set_block_data(const int32_t* t) { memcpy(g_scene.block_data, t, sizeof(g_scene.block_data)); }
+void vxref_set_blue_noise(const int32_t* d, int32_t n) { g_scene.blue.assign(d, d + n); }
+void vxref_set_texture_array(int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba) {
+    vxo::texarray_build(g_scene.tex[kind], rgba, layers, w, h, kind == 0);
+}
+void vxref_set_skymap(int32_t res, const float* f) {
+    g_scene.sky.assign(f, f + (size_t)6 * res * res * 3);
+    g_scene.cube.data = g_scene.sky.data(); g_scene.cube.res = res;
+}
+
+static inline void bind3d(sampler3D& s, const uint8_t* d) { s.data = d; s.w = 384; s.h = 128; s.d = 384; }
+static inline void bind2d(sampler2D& s, const float* d, int w, int h, int ch, bool linear) { s.data = d; s.w = w; s.h = h; s.ch = ch; s.linear = linear; }
+static std::vector<float> h2f(const uint16_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = vxo::half_to_float(h[i]); return o; }
+static std::vector<float> u2f(const uint8_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = vxo::unorm8_to_float(h[i]); return o; }
+#define BIND_BLOCK_SSBO(S)                                                                                    \
+    S::BlockAlbedoData.data = g_scene.block_data; S::BlockNormalData.data = g_scene.block_data + 128;           \
+    S::BlockPBRData.data = g_scene.block_data + 256; S::BlockEmissiveData.data = g_scene.block_data + 384;      \
+    S::BlockTransparentData.data = g_scene.block_data + 512;
+#define BIND_BLUE_SSBO(S)                                                                                     \
+    S::sobol_256spp_256d.data = g_scene.blue.data(); S::scramblingTile.data = g_scene.blue.data() + 65536;      \
+    S::rankingTile.data = g_scene.blue.data() + 65536 + 131072;
+
+#ifdef VXREF_HAVE_GenerateGBuffer
+/* Pipeline.cpp:2147-2229 */
+void vxref_generate_gbuffer(const vxrt_gbuffer_params* p, const float* g_inv_t, const uint8_t* g_normal, const uint8_t* g_block,
+                            int32_t gw, int32_t gh, uint16_t* albedo_h3, uint16_t* normal_h3, uint8_t* pbr_u8x4, uint8_t* texao_u8) {
+    namespace S = shader_GenerateGBuffer;
+    std::vector<float> nf = u2f(g_normal, (size_t)gw * gh), bf = u2f(g_block, (size_t)gw * gh);
+    bind2d(S::u_NonLinearDepth, g_inv_t, gw, gh, 1, true);
+    bind2d(S::u_Normals, nf.data(), gw, gh, 1, false);
+    bind2d(S::u_BlockIDs, bf.data(), gw, gh, 1, false);
+    S::u_BlockAlbedos.t = &g_scene.tex[0]; S::u_BlockNormals.t = &g_scene.tex[1]; S::u_BlockPBR.t = &g_scene.tex[2]; S::u_BlockEmissive.t = &g_scene.tex[3];
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    for (int i = 0; i < 10; ++i) { S::u_GrassBlockProps[i] = p->grass_props[i]; S::u_CactusBlockProps[i] = p->cactus_props[i]; }
+    S::u_LavaBlockID = -1;  /* lava's animated 3-D textures are out of scope */
+    S::u_Time = 0.0f; S::uTime = 0.0f; S::u_UpdateGBufferThisFrame = true; S::u_Frame = 0;
+    S::u_POM = false; S::u_HighQualityPOM = false; S::u_DitherPOM = false; S::u_POMHeight = 1.0f; S::u_POMExp = 1.0f;
+    BIND_BLOCK_SSBO(S)
+    const int W = p->width, H = p->height;
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::shader_reset(); S::shader_main();
+            size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 3; ++c) { albedo_h3[3 * i + c] = vxo::float_to_half(S::o_Albedo[c]); normal_h3[3 * i + c] = vxo::float_to_half(S::o_Normal[c]); }
+            for (int c = 0; c < 4; ++c) pbr_u8x4[4 * i + c] = vxo::float_to_unorm8(S::o_PBR[c]);
+            texao_u8[i] = vxo::float_to_unorm8(S::o_TextureAO);
+        }
+}
+#endif
+
+#ifdef VXREF_HAVE_DiffuseRayTraceFrag
+/* Pipeline.cpp:2267-2374 + FBOVert.glsl */
+void vxref_diffuse_trace(const vxrt_gi_params* p, const uint16_t* g_t_half, const uint8_t* g_normal, int32_t gw, int32_t gh,
+                         uint16_t* sh_h4, uint16_t* cocg_h2, uint16_t* utility_h, uint8_t* aosky_u8x2) {
+    namespace S = shader_DiffuseRayTraceFrag;
+    std::vector<float> tf = h2f(g_t_half, (size_t)gw * gh), nf = u2f(g_normal, (size_t)gw * gh);
+    bind3d(S::u_VoxelData, g_scene.blocks); bind3d(S::u_DistanceFieldTexture, g_scene.df);
+    bind2d(S::u_PositionTexture, tf.data(), gw, gh, 1, true);
+    bind2d(S::u_NormalTexture, nf.data(), gw, gh, 1, false);
+    S::u_Skymap = g_scene.cube;
+    S::u_BlockNormalTextures.t = &g_scene.tex[1]; S::u_BlockAlbedoTextures.t = &g_scene.tex[0];
+    S::u_BlockPBRTextures.t = &g_scene.tex[2]; S::u_BlockEmissiveTextures.t = &g_scene.tex[3];
+    S::CHECKERBOARD_SPP = p->checkerboard != 0;
+    S::u_Dimensions = vec2((float)p->width, (float)p->height);
+    S::u_Halton = vec2(p->halton[0], p->halton[1]);
+    S::u_Time = 0.0f; S::u_Supersample = p->supersample != 0;
+    S::u_APPLY_PLAYER_SHADOW = p->apply_player_shadow != 0;
+    S::u_UseDirectSampling = false;
+    S::u_SPP = p->spp; S::u_DiffuseTraceLength = p->trace_length; S::u_CheckerSPP = p->checker_spp;
+    S::u_CurrentFrame = p->current_frame; S::u_CurrentFrameMod512 = p->current_frame % 512; S::u_CurrentFrameMod128 = p->current_frame_mod128;
+    S::u_UseBlueNoise = p->use_blue_noise != 0;
+    S::u_GISunStrength = p->gi_sun_strength; S::u_GISkyStrength = p->gi_sky_strength; S::u_SunVisibility = p->sun_visibility;
+    S::u_ViewerPosition = vec3(p->viewer_position[0], p->viewer_position[1], p->viewer_position[2]);
+    S::u_SunDirection = vec3(p->sun_direction[0], p->sun_direction[1], p->sun_direction[2]);
+    S::u_MoonDirection = vec3(p->moon_direction[0], p->moon_direction[1], p->moon_direction[2]);
+    S::u_DiffuseLightIntensity = p->diffuse_light_intensity;
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    BIND_BLOCK_SSBO(S)
+    BIND_BLUE_SSBO(S)
+    const int W = p->width, H = p->height;
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam;
+            S::v_RayDirection = S::GetRayDirectionAt(S::v_TexCoords);  /* FBOVert.glsl:15-20, interpolated */
+            S::shader_reset(); S::shader_main();
+            size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) sh_h4[4 * i + c] = vxo::float_to_half(S::o_SH[c]);
+            cocg_h2[2 * i] = vxo::float_to_half(S::o_CoCg.x); cocg_h2[2 * i + 1] = vxo::float_to_half(S::o_CoCg.y);
+            utility_h[i] = vxo::float_to_half(S::o_Utility);
+            aosky_u8x2[2 * i] = vxo::float_to_unorm8(S::o_AOAndSkyLighting.x); aosky_u8x2[2 * i + 1] = vxo::float_to_unorm8(S::o_AOAndSkyLighting.y);
+        }
+}
+#endif
+
+
+#ifdef VXREF_HAVE_ColorPassDirect
+/* The direct-lighting term of ColorPassFrag.glsl main(): the BRDF functions are the reference's own
+ * (cut out of the file by name); the call site below restates :776, :802-816, :886-899.             */
+void vxref_shade_direct(const vxrt_direct_params* p, const float* g_inv_t, int32_t gw, int32_t gh, const uint16_t* albedo_h3,
+                        const uint16_t* normal_h3, const uint8_t* pbr_u8x4, const uint8_t* texao_u8, int32_t mw, int32_t mh,
+                        const uint8_t* shadow_u8, int32_t sw, int32_t sh, uint16_t* direct_h3) {
+    namespace S = shader_ColorPassDirect;
+    std::vector<float> af = h2f(albedo_h3, (size_t)mw * mh * 3), nf = h2f(normal_h3, (size_t)mw * mh * 3);
+    std::vector<float> pf = u2f(pbr_u8x4, (size_t)mw * mh * 4), sf = u2f(shadow_u8, (size_t)sw * sh);
+    sampler2D tInvT, tA, tN, tP, tS;
+    bind2d(tInvT, g_inv_t, gw, gh, 1, true);
+    bind2d(tA, af.data(), mw, mh, 3, true); bind2d(tN, nf.data(), mw, mh, 3, true);
+    bind2d(tP, pf.data(), mw, mh, 4, false); bind2d(tS, sf.data(), sw, sh, 1, true);
+    S::u_ViewerPosition = vec3(p->viewer_position[0], p->viewer_position[1], p->viewer_position[2]);
+    mat4 inv_view, inv_proj;
+    inv_view.load(p->inv_view); inv_proj.load(p->inv_projection);
+    const vec3 u_SunDirection(p->sun_direction[0], p->sun_direction[1], p->sun_direction[2]);
+    const vec3 u_MoonDirection(p->moon_direction[0], p->moon_direction[1], p->moon_direction[2]);
+    const vec3 SunColor(p->sun_color[0], p->sun_color[1], p->sun_color[2]), MoonColor(p->moon_color[0], p->moon_color[1], p->moon_color[2]);
+    float SunVisibility = clamp(dot(u_SunDirection, vec3(0.0f, 1.0f, 0.0f)) + 0.05f, 0.0f, 0.1f) * 12.0f; SunVisibility = 1.0f - SunVisibility;
+    const int W = p->width, H = p->height;
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            vec2 g_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            vec4 clip = vec4(g_TexCoords * 2.0f - 1.0f, -1.0f, 1.0f);
+            vec4 eye = vec4(vec2(inv_proj * clip), -1.0f, 0.0f);
+            vec3 rd = vec3(inv_view * eye);
+            float Dist = 1.0f / texture(tInvT, g_TexCoords).r;
+            vec4 WorldPosition = vec4(vec3(inv_view[3]) + normalize(rd) * Dist, Dist);
+            vec3 o_Direct = vec3(0.0f);
+            if (WorldPosition.w > 0.0f) {
+                vec3 AlbedoColor = vec3(texture(tA, g_TexCoords));
+                vec3 NormalMapped = vec3(texture(tN, g_TexCoords));
+                vec4 PBRMap = texture(tP, g_TexCoords);
+                float Emissivity = PBRMap.w;
+                AlbedoColor = S::BasicSaturation(AlbedoColor, 1.0f - p->texture_desat_amount);
+                if (PBRMap.y >= 0.1f - 0.01f) AlbedoColor = S::BasicSaturation(AlbedoColor, 0.9f);
+                if (p->amplify_normal_map) {
+                    NormalMapped.x *= 1.64f; NormalMapped.z *= 1.85f; NormalMapped += 1e-4f; NormalMapped = normalize(NormalMapped);
+                }
+                float RayTracedShadow = clamp(texture(tS, g_TexCoords).r, 0.0f, 1.0f);
+                vec3 SunDirectLighting = S::CalculateDirectionalLight(vec3(WorldPosition), u_SunDirection, SunColor, SunColor, AlbedoColor, NormalMapped, vec3(PBRMap), RayTracedShadow);
+                vec3 MoonDirectLighting = S::CalculateDirectionalLight(vec3(WorldPosition), u_MoonDirection, MoonColor, MoonColor, AlbedoColor, NormalMapped, vec3(PBRMap), RayTracedShadow);
+                vec3 DirectLighting = mix(SunDirectLighting, MoonDirectLighting, SunVisibility * vec3(1.0f));
+                DirectLighting = (float(!(Emissivity > 0.05f)) * DirectLighting);
+                DirectLighting = max(DirectLighting, 0.000001f);
+                o_Direct = DirectLighting;
+            }
+            size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 3; ++c) direct_h3[3 * i + c] = vxo::float_to_half(o_Direct[c]);
+        }
+}
+#endif
+
+
+#ifdef VXREF_HAVE_ReflectionTraceFrag
+/* Pipeline.cpp:3096-3257 + FBOVert.glsl.  LPV, projected clouds, player reflection and lava are off. */
+struct vxref_reflection_inputs {
+    const uint16_t* g_t_half; const uint8_t* g_normal; int32_t gw, gh;
+    const uint16_t* gb_normal_h3; const uint8_t* gb_pbr_u8x4; int32_t mw, mh;
+    const uint16_t* gi_sh_h4; const uint16_t* gi_cocg_h2; const uint8_t* gi_aosky_u8x2; int32_t iw, ih;
+    const uint8_t* shadow_u8; int32_t sw, sh;
+};
+void vxref_reflection_trace(const vxrt_reflection_params* p, const vxref_reflection_inputs* in, uint16_t* color_h4, uint16_t* hitdist_h,
+                            uint8_t* emissive_u8) {
+    namespace S = shader_ReflectionTraceFrag;
+    std::vector<float> tf = h2f(in->g_t_half, (size_t)in->gw * in->gh), nf = u2f(in->g_normal, (size_t)in->gw * in->gh);
+    std::vector<float> gnf = h2f(in->gb_normal_h3, (size_t)in->mw * in->mh * 3), gpf = u2f(in->gb_pbr_u8x4, (size_t)in->mw * in->mh * 4);
+    std::vector<float> shf = h2f(in->gi_sh_h4, (size_t)in->iw * in->ih * 4), ccf = h2f(in->gi_cocg_h2, (size_t)in->iw * in->ih * 2);
+    std::vector<float> aof = u2f(in->gi_aosky_u8x2, (size_t)in->iw * in->ih * 2), sf = u2f(in->shadow_u8, (size_t)in->sw * in->sh);
+    bind3d(S::u_VoxelData, g_scene.blocks); bind3d(S::u_DistanceFieldTexture, g_scene.df);
+    bind2d(S::u_PositionTexture, tf.data(), in->gw, in->gh, 1, true);
+    bind2d(S::u_InitialTraceNormalTexture, nf.data(), in->gw, in->gh, 1, false);
+    bind2d(S::u_GBufferNormals, gnf.data(), in->mw, in->mh, 3, true);
+    bind2d(S::u_GBufferPBR, gpf.data(), in->mw, in->mh, 4, false);
+    bind2d(S::u_DiffuseSH, shf.data(), in->iw, in->ih, 4, true);
+    bind2d(S::u_DiffuseCoCg, ccf.data(), in->iw, in->ih, 2, true);
+    bind2d(S::u_IndirectAO, aof.data(), in->iw, in->ih, 2, true);
+    bind2d(S::u_ShadowTrace, sf.data(), in->sw, in->sh, 1, true);
+    S::u_Skymap = g_scene.cube;
+    S::u_BlockNormalTextures.t = &g_scene.tex[1]; S::u_BlockAlbedoTextures.t = &g_scene.tex[0];
+    S::u_BlockPBRTextures.t = &g_scene.tex[2]; S::u_BlockEmissiveTextures.t = &g_scene.tex[3];
+    S::u_SunStrengthModifier = p->sun_strength_modifier; S::u_MoonStrengthModifier = p->moon_strength_modifier;
+    S::u_CloudReflections = false; S::u_TemporalFilterReflections = p->temporal != 0; S::TEMPORAL_SPEC = p->temporal != 0;
+    S::u_RoughReflections = p->rough_reflections != 0; S::CHECKERBOARD_SPEC_SPP = p->checkerboard != 0;
+    S::u_ScreenSpaceSkylightingValid = false; S::u_ReflectionTraceRes = 1.0f;
+    S::u_Dimensions = vec2((float)p->width, (float)p->height);
+    S::u_SunDirection = vec3(p->sun_direction[0], p->sun_direction[1], p->sun_direction[2]);
+    S::u_MoonDirection = vec3(p->moon_direction[0], p->moon_direction[1], p->moon_direction[2]);
+    S::u_StrongerLightDirection = vec3(p->stronger_light_direction[0], p->stronger_light_direction[1], p->stronger_light_direction[2]);
+    S::u_Time = 0.0f;
+    for (int i = 0; i < 10; ++i) S::u_GrassBlockProps[i] = p->grass_props[i];
+    S::u_ViewerPosition = vec3(p->viewer_position[0], p->viewer_position[1], p->viewer_position[2]);
+    S::u_SPP = p->spp; S::u_LavaBlockID = -1; S::u_ReflectionTraceLength = p->trace_length;
+    S::u_CurrentFrame = p->current_frame; S::u_CurrentFrameMod128 = p->current_frame_mod128;
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_View.load(p->view); S::u_Projection.load(p->projection);
+    S::u_ReprojectToScreenSpace = p->reproject_to_screen_space != 0; S::u_UseBlueNoise = p->use_blue_noise != 0;
+    S::u_ReflectPlayer = false; S::u_DeriveFromDiffuseSH = p->derive_from_diffuse_sh != 0;
+    S::u_LPVGI = false; S::u_QualityLPVGI = false; S::u_Halton = vec2(p->halton[0], p->halton[1]);
+    S::u_RoughnessBias = p->roughness_bias != 0; S::u_UseDecoupledGI = false;
+    BIND_BLOCK_SSBO(S)
+    BIND_BLUE_SSBO(S)
+    const int W = p->width, H = p->height;
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam;
+            S::v_RayDirection = S::GetRayDirectionAt(S::v_TexCoords);
+            S::shader_reset(); S::shader_main();
+            size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) color_h4[4 * i + c] = vxo::float_to_half(S::o_Color[c]);
+            hitdist_h[i] = vxo::float_to_half(S::o_HitDistance);
+            emissive_u8[i] = vxo::float_to_unorm8(S::o_EmissivityHitMask);
         }
 }
 #endif

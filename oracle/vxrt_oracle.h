@@ -75,6 +75,40 @@ void vxo_shadow_trace(const vxo_world* w, const vxrt_shadow_params* p, const uin
                       int32_t bw, int32_t bh, uint8_t* shadow_u8, uint16_t* transversal_half,
                       vxrt_trace_stats* stats);
 
+/* ---- scene: tables, texture arrays, sky map (the GL resources the material / GI / reflection
+ * shaders bind) ---- */
+typedef struct vxo_scene vxo_scene;
+vxo_scene* vxo_scene_create(const vxo_world* w);
+void vxo_scene_destroy(vxo_scene* s);
+void vxo_scene_set_block_data(vxo_scene* s, const int32_t* table6x128);
+void vxo_scene_set_blue_noise(vxo_scene* s, const int32_t* data, int32_t count);
+void vxo_scene_set_texture_array(vxo_scene* s, int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba);
+void vxo_scene_set_skymap(vxo_scene* s, int32_t res, const float* rgb_faces);
+/* mip level `level` of array `kind` as built by the pinned glGenerateMipmap model (for tests) */
+int32_t vxo_scene_texture_level(const vxo_scene* s, int32_t kind, int32_t level, uint8_t* out, int64_t out_bytes);
+
+/* GenerateGBuffer.glsl main(); inputs = primary attachments (1/t R32F, face R8, block R8) at gw x gh */
+void vxo_generate_gbuffer(const vxo_scene* s, const vxrt_gbuffer_params* p, const float* g_inv_t, const uint8_t* g_normal,
+                          const uint8_t* g_block, int32_t gw, int32_t gh, uint16_t* albedo_h3, uint16_t* normal_h3,
+                          uint8_t* pbr_u8x4, uint8_t* texao_u8);
+/* Cook-Torrance direct term (ColorPassFrag.glsl:419-451, 776, 812-816, 886-899) */
+void vxo_shade_direct(const vxrt_direct_params* p, const float* g_inv_t, int32_t gw, int32_t gh, const uint16_t* albedo_h3,
+                      const uint16_t* normal_h3, const uint8_t* pbr_u8x4, const uint8_t* texao_u8, int32_t mw, int32_t mh,
+                      const uint8_t* shadow_u8, int32_t sw, int32_t sh, uint16_t* direct_h3);
+/* DiffuseRayTraceFrag.glsl main() */
+void vxo_diffuse_trace(const vxo_scene* s, const vxrt_gi_params* p, const uint16_t* g_t_half, const uint8_t* g_normal,
+                       int32_t gw, int32_t gh, uint16_t* sh_h4, uint16_t* cocg_h2, uint16_t* utility_h, uint8_t* aosky_u8x2,
+                       vxrt_trace_stats* stats);
+/* ReflectionTraceFrag.glsl main() */
+typedef struct vxo_reflection_inputs {
+    const uint16_t* g_t_half; const uint8_t* g_normal; int32_t gw, gh;          /* primary G-buffer */
+    const uint16_t* gb_normal_h3; const uint8_t* gb_pbr_u8x4; int32_t mw, mh;   /* generated G-buffer */
+    const uint16_t* gi_sh_h4; const uint16_t* gi_cocg_h2; const uint8_t* gi_aosky_u8x2; int32_t iw, ih; /* GI outputs */
+    const uint8_t* shadow_u8; int32_t sw, sh;                                   /* shadow trace */
+} vxo_reflection_inputs;
+void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_params* p, const vxo_reflection_inputs* in,
+                          uint16_t* color_h4, uint16_t* hitdist_h, uint8_t* emissive_u8, vxrt_trace_stats* stats);
+
 /* format helpers */
 uint16_t vxo_float_to_half(float f);
 float vxo_half_to_float(uint16_t h);

@@ -58,6 +58,47 @@ class ShadowParams(C.Structure):
     ]
 
 
+class GBufferParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+        ("grass_props", C.c_int32 * 10), ("cactus_props", C.c_int32 * 10), ("tile", Tile),
+    ]
+
+
+class DirectParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+        ("viewer_position", C.c_float * 3), ("sun_direction", C.c_float * 3), ("moon_direction", C.c_float * 3),
+        ("sun_color", C.c_float * 3), ("moon_color", C.c_float * 3), ("texture_desat_amount", C.c_float),
+        ("amplify_normal_map", C.c_int32), ("tile", Tile),
+    ]
+
+
+class GIParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+        ("spp", C.c_int32), ("checker_spp", C.c_int32), ("checkerboard", C.c_int32), ("trace_length", C.c_int32),
+        ("shadow_trace_length", C.c_int32), ("current_frame", C.c_int32), ("current_frame_mod128", C.c_int32),
+        ("use_blue_noise", C.c_int32), ("supersample", C.c_int32), ("halton", C.c_float * 2),
+        ("sun_direction", C.c_float * 3), ("moon_direction", C.c_float * 3), ("sun_visibility", C.c_float),
+        ("gi_sun_strength", C.c_float), ("gi_sky_strength", C.c_float), ("diffuse_light_intensity", C.c_float),
+        ("viewer_position", C.c_float * 3), ("apply_player_shadow", C.c_int32), ("tile", Tile),
+    ]
+
+
+class ReflectionParams(C.Structure):
+    _fields_ = [
+        ("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("view", C.c_float * 16), ("projection", C.c_float * 16),
+        ("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("checkerboard", C.c_int32), ("trace_length", C.c_int32),
+        ("shadow_trace_length", C.c_int32), ("current_frame", C.c_int32), ("current_frame_mod128", C.c_int32),
+        ("use_blue_noise", C.c_int32), ("rough_reflections", C.c_int32), ("roughness_bias", C.c_int32), ("temporal", C.c_int32),
+        ("reproject_to_screen_space", C.c_int32), ("derive_from_diffuse_sh", C.c_int32), ("halton", C.c_float * 2),
+        ("sun_direction", C.c_float * 3), ("moon_direction", C.c_float * 3), ("stronger_light_direction", C.c_float * 3),
+        ("viewer_position", C.c_float * 3), ("sun_strength_modifier", C.c_float), ("moon_strength_modifier", C.c_float),
+        ("grass_props", C.c_int32 * 10), ("tile", Tile),
+    ]
+
+
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("iterations", C.c_uint64), ("dda_steps", C.c_uint64), ("hits", C.c_uint64)]
 
@@ -104,6 +145,12 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_set_block_data": (C.c_int, [vp, vp]),
         "vxrt_cuda_set_blue_noise": (C.c_int, [vp, vp, i32]),
         "vxrt_cuda_set_blue_noise_texture": (C.c_int, [vp, vp, i32, i32]),
+        "vxrt_cuda_set_texture_array": (C.c_int, [vp, i32, i32, i32, i32, vp]),
+        "vxrt_cuda_set_skymap": (C.c_int, [vp, i32, vp]),
+        "vxrt_cuda_generate_gbuffer": (C.c_int, [vp, P(GBufferParams)]),
+        "vxrt_cuda_shade_direct": (C.c_int, [vp, P(DirectParams)]),
+        "vxrt_cuda_diffuse_trace": (C.c_int, [vp, P(GIParams)]),
+        "vxrt_cuda_reflection_trace": (C.c_int, [vp, P(ReflectionParams)]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_attachment_device": (C.c_int, [vp, i32, P(vp), P(i32), P(i32), P(i32)]),
         "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),
@@ -140,6 +187,18 @@ def load_host() -> C.CDLL:
         "vxh_random_edits": (None, [u32, i32, i32, i32, i32, vp, vp]),
         "vxh_world_save": (i32, [C.c_char_p, vp, C.c_int64]),
         "vxh_world_load": (i32, [C.c_char_p, vp, C.c_int64]),
+        "vxh_blockdb_parse": (vp, [C.c_char_p]),
+        "vxh_blockdb_free": (None, [vp]),
+        "vxh_blockdb_block_count": (i32, [vp]),
+        "vxh_blockdb_block_id": (i32, [vp, C.c_char_p]),
+        "vxh_blockdb_block_name": (C.c_char_p, [vp, i32]),
+        "vxh_blockdb_layer_count": (i32, [vp, i32]),
+        "vxh_blockdb_layer_path": (C.c_char_p, [vp, i32, i32]),
+        "vxh_blockdb_texture": (i32, [vp, i32, i32, i32]),
+        "vxh_blockdb_table": (None, [vp, vp]),
+        "vxh_blockdb_face_props": (None, [vp, C.c_char_p, vp]),
+        "vxh_blockdb_minecraft_lut": (None, [vp, vp]),
+        "vxh_gen_texture_array": (None, [u32, i32, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -316,3 +316,197 @@ int32_t vxh_world_load(const char* path, uint8_t* blocks, int64_t nbytes) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Block database: same record grammar and precedence as the engine's parser
+// (Core/BlockDatabaseParser.cpp:44-417): records are `{` ... `}` line blocks of `Key : value` fields;
+// face-specific keys assign, the generic key fills whatever is still empty; ids count records from 1.
+// ---------------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+
+namespace {
+struct FaceSet { std::string f[6]; };  // front, back, top, bottom, left, right
+struct BlockRec {
+    std::string name, emissive;
+    FaceSet maps[3];  // albedo, normal, pbr
+    bool transparent = false, sss = false;
+    std::vector<int> mc_ids;
+    int id = 0;
+};
+std::string field_value(const std::string& field) {
+    size_t loc = field.find(':');
+    std::string s = loc == std::string::npos ? field : field.substr(loc + 1);
+    s.erase(std::remove_if(s.begin(), s.end(), [](unsigned char c) { return isspace(c); }), s.end());
+    return s;
+}
+bool has(const std::string& f, const char* k) { return f.find(k) != std::string::npos; }
+}  // namespace
+
+struct vxh_blockdb {
+    std::vector<BlockRec> blocks;                  // index = id - 1
+    std::map<std::string, int> by_name;
+    std::vector<std::string> layers[4];            // sorted unique paths per kind
+    int layer_of(int kind, const std::string& p) const {
+        auto it = std::lower_bound(layers[kind].begin(), layers[kind].end(), p);
+        return (it != layers[kind].end() && *it == p) ? (int)(it - layers[kind].begin()) : -1;
+    }
+};
+
+extern "C" {
+
+vxh_blockdb* vxh_blockdb_parse(const char* path) {
+    std::ifstream in(path);
+    if (!in.good()) return nullptr;
+    vxh_blockdb* db = new vxh_blockdb();
+    static const char* kind_key[3] = {"Albedo", "Normal", "PBR"};
+    static const char* face_key[6] = {"_front", "_back", "_top", "_bottom", "_left", "_right"};
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line != "{") continue;
+        BlockRec r;
+        std::vector<std::string> fields;
+        std::string f;
+        while (std::getline(in, f)) {
+            if (!f.empty() && f.back() == '\r') f.pop_back();
+            if (f == "}") break;
+            fields.push_back(f);
+        }
+        for (const std::string& field : fields) {
+            if (has(field, "Name")) { r.name = field_value(field); continue; }
+            bool done = false;
+            for (int k = 0; k < 3 && !done; ++k) {
+                for (int face = 0; face < 6 && !done; ++face)
+                    if (has(field, (std::string(kind_key[k]) + face_key[face]).c_str())) { r.maps[k].f[face] = field_value(field); done = true; }
+                if (!done && has(field, kind_key[k])) {  // "<Kind>_default" or plain "<Kind>": fill the empty faces
+                    std::string v = field_value(field);
+                    for (int face = 0; face < 6; ++face) if (r.maps[k].f[face].empty()) r.maps[k].f[face] = v;
+                    done = true;
+                }
+            }
+            if (done) continue;
+            if (has(field, "Transparent")) r.transparent = true;
+            else if (has(field, "sss") || has(field, "SSS") || has(field, "SUBSURFACE")) r.sss = true;
+            else if (has(field, "Emissive")) r.emissive = field_value(field);
+            else if (has(field, "SND_STEP") || has(field, "SND_MODIFY")) {}
+            else if (has(field, "MC_ID") || has(field, "MCID") || has(field, "mc_id") || has(field, "mcid")) {
+                size_t loc = field.find(':');
+                std::stringstream ss(loc == std::string::npos ? "" : field.substr(loc + 1));
+                std::string tok;
+                while (std::getline(ss, tok, ',')) { try { r.mc_ids.push_back(std::stoi(tok)); } catch (...) {} }
+            }
+        }
+        if (db->blocks.size() >= 127) break;  // GenerateBlockID throws at 128 (BlockDatabaseParser.cpp:31-42)
+        r.id = (int)db->blocks.size() + 1;
+        auto it = db->by_name.find(r.name);
+        if (it != db->by_name.end()) {  // a repeated name overwrites the map entry but still burns an id
+            db->blocks.push_back(r);
+            it->second = r.id;
+        } else {
+            db->by_name[r.name] = r.id;
+            db->blocks.push_back(r);
+        }
+    }
+    for (const BlockRec& b : db->blocks) {
+        if (db->by_name[b.name] != b.id) continue;
+        for (int k = 0; k < 3; ++k) for (int face = 0; face < 6; ++face) db->layers[k].push_back(b.maps[k].f[face]);
+        if (!b.emissive.empty()) db->layers[3].push_back(b.emissive);
+    }
+    for (int k = 0; k < 4; ++k) {
+        std::sort(db->layers[k].begin(), db->layers[k].end());
+        db->layers[k].erase(std::unique(db->layers[k].begin(), db->layers[k].end()), db->layers[k].end());
+    }
+    return db;
+}
+void vxh_blockdb_free(vxh_blockdb* db) { delete db; }
+int32_t vxh_blockdb_block_count(const vxh_blockdb* db) { return (int32_t)db->by_name.size(); }
+int32_t vxh_blockdb_block_id(const vxh_blockdb* db, const char* name) {
+    auto it = db->by_name.find(name);
+    return it == db->by_name.end() ? 0 : it->second;
+}
+static const BlockRec* rec_by_id(const vxh_blockdb* db, int id) {
+    if (id < 1 || id > (int)db->blocks.size()) return nullptr;
+    const BlockRec& b = db->blocks[id - 1];
+    auto it = db->by_name.find(b.name);
+    return (it != db->by_name.end() && it->second == id) ? &b : nullptr;
+}
+const char* vxh_blockdb_block_name(const vxh_blockdb* db, int32_t id) {
+    const BlockRec* b = rec_by_id(db, id);
+    return b ? b->name.c_str() : "???";
+}
+int32_t vxh_blockdb_layer_count(const vxh_blockdb* db, int32_t kind) { return (kind < 0 || kind > 3) ? 0 : (int32_t)db->layers[kind].size(); }
+const char* vxh_blockdb_layer_path(const vxh_blockdb* db, int32_t kind, int32_t layer) {
+    if (kind < 0 || kind > 3 || layer < 0 || layer >= (int)db->layers[kind].size()) return "";
+    return db->layers[kind][layer].c_str();
+}
+int32_t vxh_blockdb_texture(const vxh_blockdb* db, int32_t kind, int32_t id, int32_t face) {
+    const BlockRec* b = rec_by_id(db, id);
+    if (!b) return kind == 2 ? 0 : -1;  // unknown id: PBR lookup returns 0 (BlockDatabase.cpp:398-401), others -1
+    if (kind == 3) return b->emissive.empty() ? -1 : db->layer_of(3, b->emissive);
+    if (kind < 0 || kind > 2 || face < 0 || face > 5) return -1;
+    return db->layer_of(kind, b->maps[kind].f[face]);
+}
+void vxh_blockdb_table(const vxh_blockdb* db, int32_t* t) {
+    for (int i = 0; i < 128; ++i) {
+        t[0 * 128 + i] = vxh_blockdb_texture(db, 0, i, 0);
+        t[1 * 128 + i] = vxh_blockdb_texture(db, 1, i, 0);
+        t[2 * 128 + i] = vxh_blockdb_texture(db, 2, i, 0);
+        t[3 * 128 + i] = vxh_blockdb_texture(db, 3, i, 0);
+        const BlockRec* b = rec_by_id(db, i);
+        t[4 * 128 + i] = (b && b->transparent) ? 1 : 0;
+        t[5 * 128 + i] = (b && b->sss) ? 1 : 0;
+    }
+}
+void vxh_blockdb_face_props(const vxh_blockdb* db, const char* name, int32_t* o) {
+    int id = vxh_blockdb_block_id(db, name);
+    o[0] = id;
+    const int faces[3] = {2, 0, 3};  // top, front, bottom
+    for (int g = 0; g < 3; ++g)
+        for (int k = 0; k < 3; ++k) o[1 + g * 3 + k] = id ? vxh_blockdb_texture(db, k, id, faces[g]) : -1;
+}
+void vxh_blockdb_minecraft_lut(const vxh_blockdb* db, uint8_t* out256) {
+    memset(out256, 0, 256);
+    for (const BlockRec& b : db->blocks) {
+        if (!rec_by_id(db, b.id)) continue;
+        for (int mc : b.mc_ids) out256[(uint8_t)mc] = (uint8_t)b.id;
+    }
+}
+
+void vxh_gen_texture_array(uint32_t seed, int32_t kind, int32_t layers, int32_t size, uint8_t* rgba) {
+    for (int L = 0; L < layers; ++L) {
+        uint32_t ls = seed * 977u + (uint32_t)L * 131u + (uint32_t)kind * 7u;
+        float base[3] = {0.25f + 0.7f * (float)(hash3(ls, 1, 1) & 255) / 255.0f, 0.25f + 0.7f * (float)(hash3(ls, 2, 1) & 255) / 255.0f,
+                         0.25f + 0.7f * (float)(hash3(ls, 3, 1) & 255) / 255.0f};
+        bool metal = (hash3(ls, 4, 1) % 5) == 0;
+        float rough0 = 0.1f + 0.85f * (float)(hash3(ls, 5, 1) & 255) / 255.0f;
+        for (int y = 0; y < size; ++y)
+            for (int x = 0; x < size; ++x) {
+                float u = (float)x / (float)size, v = (float)y / (float)size;
+                float n = fbm(u * 8.0f, v * 8.0f, 4, ls), m = value_noise(u * 32.0f, v * 32.0f, ls + 9u);
+                uint8_t* p = rgba + (((size_t)L * size + y) * size + x) * 4;
+                auto q = [](float f) { f = f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f); return (uint8_t)(f * 255.0f + 0.5f); };
+                if (kind == 0) {
+                    float s = 0.75f + 0.25f * n + 0.08f * m;
+                    bool brick = ((x / 64 + y / 32) & 1) != 0;
+                    p[0] = q(base[0] * s * (brick ? 0.9f : 1.0f)); p[1] = q(base[1] * s); p[2] = q(base[2] * s * (brick ? 1.0f : 0.92f));
+                    p[3] = (L % 7 == 6 && m > 0.3f) ? 0 : 255;  // a few cut-out (leaf-like) layers
+                } else if (kind == 1) {
+                    float dx = value_noise(u * 16.0f + 0.37f, v * 16.0f, ls) * 0.35f, dy = value_noise(u * 16.0f, v * 16.0f + 0.61f, ls + 3u) * 0.35f;
+                    float nz = sqrtf(fmaxf(0.05f, 1.0f - dx * dx - dy * dy));
+                    p[0] = q(0.5f + 0.5f * dx); p[1] = q(0.5f + 0.5f * dy); p[2] = q(0.5f + 0.5f * nz); p[3] = 255;
+                } else if (kind == 2) {
+                    p[0] = q(rough0 + 0.15f * n); p[1] = metal ? q(0.85f + 0.15f * m) : q(0.02f * (m + 1.0f));
+                    p[2] = q(0.5f + 0.5f * n); p[3] = q(0.8f + 0.2f * m);
+                } else {
+                    float e = (fabsf(u - 0.5f) < 0.3f && fabsf(v - 0.5f) < 0.3f) ? 0.7f + 0.3f * n : 0.05f;
+                    p[0] = q(e); p[1] = q(e * 0.8f); p[2] = q(e * 0.5f); p[3] = 255;
+                }
+            }
+    }
+}
+
+}  // extern "C"

@@ -42,6 +42,32 @@ void vxh_random_edits(uint32_t seed, int32_t n, int32_t nx, int32_t ny, int32_t 
 int32_t vxh_world_save(const char* path, const uint8_t* blocks, int64_t nbytes);
 int32_t vxh_world_load(const char* path, uint8_t* blocks, int64_t nbytes);
 
+/* ---- block database (Core/BlockDatabaseParser.cpp:44-417, Core/BlockDatabase.cpp:13-104, 111-468) ----
+ * kinds: 0 albedo, 1 normal, 2 pbr, 3 emissive.  faces: 0 front, 1 back, 2 top, 3 bottom, 4 left, 5 right.
+ * Block ids are the 1-based order of the records; a texture's layer is its index in the sorted list of
+ * unique paths of its kind (Core/GLClasses/TextureArray.cpp:12-13,56).                              */
+typedef struct vxh_blockdb vxh_blockdb;
+vxh_blockdb* vxh_blockdb_parse(const char* path); /* NULL if the file cannot be opened */
+void vxh_blockdb_free(vxh_blockdb* db);
+int32_t vxh_blockdb_block_count(const vxh_blockdb* db);
+int32_t vxh_blockdb_block_id(const vxh_blockdb* db, const char* name);       /* 0 if unknown */
+const char* vxh_blockdb_block_name(const vxh_blockdb* db, int32_t id);       /* "???" if unknown */
+int32_t vxh_blockdb_layer_count(const vxh_blockdb* db, int32_t kind);
+const char* vxh_blockdb_layer_path(const vxh_blockdb* db, int32_t kind, int32_t layer);
+/* GetBlockTexture / GetBlockNormalTexture / GetBlockPBRTexture / GetBlockEmissiveTexture by id */
+int32_t vxh_blockdb_texture(const vxh_blockdb* db, int32_t kind, int32_t block_id, int32_t face);
+/* BlockDataSSBO::CreateBuffers (Core/BlockDataSSBO.cpp:17-35): int[6][128] */
+void vxh_blockdb_table(const vxh_blockdb* db, int32_t* out6x128);
+/* u_GrassBlockProps / u_CactusBlockProps layout (Core/Pipeline.cpp:2166-2186): {id, top a/n/p, front a/n/p, bottom a/n/p} */
+void vxh_blockdb_face_props(const vxh_blockdb* db, const char* name, int32_t* out10);
+/* MC_ID lookup table (Core/BlockDatabase.cpp:93-103): out256[mc_id] = block id or 0 */
+void vxh_blockdb_minecraft_lut(const vxh_blockdb* db, uint8_t* out256);
+
+/* deterministic synthetic 'block textures' (the reference's PNGs do not travel to the GPU box):
+ * layers*size*size RGBA8, kind-appropriate content (albedo colours, tangent-space normals,
+ * roughness/metal/displacement/AO, emissive masks).                                                 */
+void vxh_gen_texture_array(uint32_t seed, int32_t kind, int32_t layers, int32_t size, uint8_t* rgba);
+
 #ifdef __cplusplus
 }
 #endif

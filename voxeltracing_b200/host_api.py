@@ -96,3 +96,89 @@ def save_world(path: str, blocks: np.ndarray) -> None:
     rc = abi.load_host().vxh_world_save(str(path).encode(), _p(np.ascontiguousarray(blocks)), blocks.size)
     if rc != 0:
         raise OSError(f"could not write {path}")
+
+
+class BlockDatabase:
+    """blockdb.txt -> block ids, texture-array layers and the BlockData table
+    (Core/BlockDatabaseParser.cpp, Core/BlockDatabase.cpp, Core/BlockDataSSBO.cpp)."""
+
+    KINDS = ("albedo", "normal", "pbr", "emissive")
+
+    def __init__(self, path):
+        self._lib = abi.load_host()
+        self._h = self._lib.vxh_blockdb_parse(str(path).encode())
+        if not self._h:
+            raise OSError(f"could not open block database {path}")
+
+    def close(self):
+        if self._h:
+            self._lib.vxh_blockdb_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def block_count(self) -> int:
+        return self._lib.vxh_blockdb_block_count(self._h)
+
+    def block_id(self, name: str) -> int:
+        return self._lib.vxh_blockdb_block_id(self._h, name.encode())
+
+    def block_name(self, block_id: int) -> str:
+        return self._lib.vxh_blockdb_block_name(self._h, block_id).decode()
+
+    def layer_paths(self, kind: int) -> list[str]:
+        n = self._lib.vxh_blockdb_layer_count(self._h, kind)
+        return [self._lib.vxh_blockdb_layer_path(self._h, kind, i).decode() for i in range(n)]
+
+    def texture(self, kind: int, block_id: int, face: int = 0) -> int:
+        return self._lib.vxh_blockdb_texture(self._h, kind, block_id, face)
+
+    def table(self) -> np.ndarray:
+        t = np.zeros((6, 128), dtype=np.int32)
+        self._lib.vxh_blockdb_table(self._h, _p(t))
+        return t
+
+    def face_props(self, name: str) -> np.ndarray:
+        o = np.zeros(10, dtype=np.int32)
+        self._lib.vxh_blockdb_face_props(self._h, name.encode(), _p(o))
+        return o
+
+    def minecraft_lut(self) -> np.ndarray:
+        o = np.zeros(256, dtype=np.uint8)
+        self._lib.vxh_blockdb_minecraft_lut(self._h, _p(o))
+        return o
+
+
+def gen_texture_array(kind: int, layers: int, size: int = 512, seed: int = 7) -> np.ndarray:
+    """Deterministic synthetic block textures [layers, size, size, 4] uint8 (the reference's PNGs do not
+    travel to the GPU box; with the reference mounted, load the PNGs named by BlockDatabase.layer_paths)."""
+    out = np.zeros((layers, size, size, 4), dtype=np.uint8)
+    abi.load_host().vxh_gen_texture_array(seed, kind, layers, size, _p(out))
+    return out
+
+
+def constant_skymap(res: int = 16, rgb=(0.5, 0.7, 1.0)) -> np.ndarray:
+    """Config-4 sky: constant-colour cube faces so the atmosphere model stays out of the loop."""
+    sky = np.empty((6, res, res, 3), dtype=np.float32)
+    sky[...] = np.asarray(rgb, dtype=np.float32)
+    return sky
+
+
+def gradient_skymap(res: int = 16) -> np.ndarray:
+    """A simple analytic sky (horizon-to-zenith gradient + warm +X side) to exercise the cube-map lookup."""
+    sky = np.empty((6, res, res, 3), dtype=np.float32)
+    for f in range(6):
+        for j in range(res):
+            for i in range(res):
+                s, t = (i + 0.5) / res * 2 - 1, (j + 0.5) / res * 2 - 1
+                d = [(1, -t, -s), (-1, -t, s), (s, 1, t), (s, -1, -t), (s, -t, 1), (-s, -t, -1)][f]
+                d = np.asarray(d, dtype=np.float64)
+                d /= np.linalg.norm(d)
+                up = max(d[1], 0.0)
+                sky[f, j, i] = (0.55 - 0.3 * up + 0.25 * max(d[0], 0) ** 4, 0.7 - 0.15 * up, 0.95 + 0.3 * up)
+    return sky
