@@ -89,7 +89,8 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
-    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats);
+    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky);
+    for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i) cudaFree(c->att[i].ptr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -274,6 +275,79 @@ int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
     if (p->soft_shadows && !c->d_blue_tex) return vxrt_fail(VXRT_E_STATE, "soft shadows need set_blue_noise_texture");
     if (p->max_iterations < 0) return vxrt_fail(VXRT_E_INVALID, "max_iterations < 0");
     return vxrt_launch_shadow_trace(c, *p);
+}
+
+int vxrt_cuda_set_texture_array(vxrt_ctx* c, int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba8) {
+    REQUIRE_CTX(c); REQUIRE_PTR(rgba8);
+    if (kind < 0 || kind > 3) return vxrt_fail(VXRT_E_INVALID, "set_texture_array: bad kind %d", kind);
+    if (layers < 1 || layers > 255) return vxrt_fail(VXRT_E_INVALID, "set_texture_array: %d layers (1..255, TextureArray.cpp:17-23)", layers);
+    if (w < 1 || h < 1 || w > 4096 || h > 4096 || (w & (w - 1)) || (h & (h - 1)) || w != h)
+        return vxrt_fail(VXRT_E_INVALID, "set_texture_array: size %dx%d must be a square power of two", w, h);
+    return vxrt_set_texture_array(c, kind, layers, w, h, rgba8);
+}
+int vxrt_cuda_set_skymap(vxrt_ctx* c, int32_t res, const float* rgb_faces) {
+    REQUIRE_CTX(c); REQUIRE_PTR(rgb_faces);
+    if (res < 1 || res > 2048) return vxrt_fail(VXRT_E_INVALID, "set_skymap: bad resolution %d", res);
+    return vxrt_set_skymap(c, res, rgb_faces);
+}
+
+static int require_att(vxrt_ctx* c, const char* fn, int id, const char* producer) {
+    if (!c->att[id].ptr) return vxrt_fail(VXRT_E_STATE, "%s consumes attachment %d: run %s first", fn, id, producer);
+    return VXRT_OK;
+}
+static int require_textures(vxrt_ctx* c, const char* fn, bool need_normal) {
+    for (int k = 0; k < 4; ++k) {
+        if (k == VXRT_TEX_NORMAL && !need_normal) continue;
+        if (!c->tex_set[k]) return vxrt_fail(VXRT_E_STATE, "%s needs texture array %d (vxrt_cuda_set_texture_array)", fn, k);
+    }
+    return VXRT_OK;
+}
+
+int vxrt_cuda_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_INVT, "vxrt_cuda_initial_trace"))) return rc;
+    if ((rc = require_textures(c, __func__, true))) return rc;
+    return vxrt_launch_generate_gbuffer(c, *p);
+}
+int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_INVT, "vxrt_cuda_initial_trace"))) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_ALBEDO, "vxrt_cuda_generate_gbuffer"))) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_SHADOW, "vxrt_cuda_shadow_trace"))) return rc;
+    return vxrt_launch_shade_direct(c, *p);
+}
+int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs a world and a distance field");
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_T, "vxrt_cuda_initial_trace"))) return rc;
+    if ((rc = require_textures(c, __func__, false))) return rc;
+    if (!c->d_blue_noise) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs vxrt_cuda_set_blue_noise");
+    if (!c->sky.data) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs vxrt_cuda_set_skymap");
+    if (!p->use_blue_noise) return vxrt_fail(VXRT_E_UNSUPPORTED, "the fract(sin()) hash RNG (u_UseBlueNoise = false) is not portable and not implemented");
+    if (p->spp < 1 || p->trace_length < 0 || p->shadow_trace_length < 0) return vxrt_fail(VXRT_E_INVALID, "diffuse_trace: bad spp / trace length");
+    return vxrt_launch_diffuse_trace(c, *p);
+}
+int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs a world and a distance field");
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_T, "vxrt_cuda_initial_trace"))) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_NORMAL, "vxrt_cuda_generate_gbuffer"))) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_GI_SH, "vxrt_cuda_diffuse_trace"))) return rc;
+    if ((rc = require_att(c, __func__, VXRT_ATT_SHADOW, "vxrt_cuda_shadow_trace"))) return rc;
+    if ((rc = require_textures(c, __func__, true))) return rc;
+    if (!c->d_blue_noise) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs vxrt_cuda_set_blue_noise");
+    if (!c->sky.data) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs vxrt_cuda_set_skymap");
+    if (!p->use_blue_noise) return vxrt_fail(VXRT_E_UNSUPPORTED, "the fract(sin()) hash RNG is not implemented");
+    if (p->spp < 1 || p->trace_length < 0 || p->shadow_trace_length < 0) return vxrt_fail(VXRT_E_INVALID, "reflection_trace: bad spp / trace length");
+    return vxrt_launch_reflection_trace(c, *p);
 }
 
 int vxrt_cuda_stats_enable(vxrt_ctx* c, int32_t on) {

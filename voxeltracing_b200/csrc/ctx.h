@@ -9,6 +9,7 @@
 #include <stddef.h>
 
 #include "../../include/vxrt_cuda.h"
+#include <vector>
 
 struct GridView {
     const uint8_t* __restrict__ df;   // distance field, x-fastest
@@ -22,6 +23,18 @@ struct Attachment {
     void* ptr = nullptr;
     size_t capacity = 0;  // bytes allocated
     int width = 0, height = 0, bpp = 0;
+};
+
+// device view of one block texture array (see texture.cuh)
+struct TexArrayDev {
+    const uint8_t* data;      // all mip levels; level l starts at data + level_offset[l]; RGBA8, layer-major
+    const float* decode;      // 256-entry code -> float table for RGB (sRGB decode for albedo, k/255 otherwise)
+    unsigned level_offset[12];
+    int w, h, layers, levels;
+};
+struct TexCubeDev {
+    const float* data;  // 6 faces (+X,-X,+Y,-Y,+Z,-Z) x res x res x RGB float
+    int res;
 };
 
 struct TraceStatsDev {
@@ -47,6 +60,15 @@ struct vxrt_ctx {
     int32_t blue_noise_count = 0;
     uint8_t* d_blue_tex = nullptr;        // rgba8
     int blue_w = 0, blue_h = 0;
+
+    // block texture arrays (Core/GLClasses/TextureArray.cpp) and the sky cube map
+    uint8_t* d_tex_data[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* d_tex_decode[4] = {nullptr, nullptr, nullptr, nullptr};
+    TexArrayDev tex[4] = {};
+    bool tex_set[4] = {false, false, false, false};
+    float* d_sky = nullptr;
+    TexCubeDev sky = {nullptr, 0};
+    std::vector<float> h_sky;  // host copy: per-frame sun / moon colours are evaluated on the host
 
     int32_t* d_edit_buf = nullptr;
     size_t edit_cap = 0;
@@ -78,3 +100,14 @@ int vxrt_launch_edit_blocks(vxrt_ctx* c, const int32_t* d_edits, int n);
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
 int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);
+int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, const uint8_t* rgba8);
+int vxrt_set_skymap(vxrt_ctx* c, int res, const float* rgb_faces);
+int vxrt_launch_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params& p);
+int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p);
+int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p);
+int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p);
+// host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)
+void vxrt_host_sky_sample(const vxrt_ctx* c, const float dir[3], float rgb[3]);
+// SampleSunColor() / SampleMoonColor() of the GI / reflection shaders, evaluated once per pass on the host
+void vxrt_host_sun_color(const vxrt_ctx* c, const float sun_dir[3], float strength, float rgb[3]);
+void vxrt_host_moon_color(const vxrt_ctx* c, const float moon_dir[3], float strength, float rgb[3]);

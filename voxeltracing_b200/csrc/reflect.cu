@@ -1,0 +1,414 @@
+// reflect.cu — reflection pass: ReflectionTraceFrag.glsl (main :717-1038), dispatched at
+// Core/Pipeline.cpp:3096-3257; attachments Core/Pipeline.cpp:1189.
+// One thread per pixel: GGX-importance-sampled (best of 3) reflection ray per sample, Cook-Torrance hit
+// shading with the specular lobe zeroed exactly as the reference does, optional screen-space reuse of
+// the diffuse SH / shadow attachments, <= 150-iteration shadow ray for the first max(SPP/4,1) hits.
+// Not modelled (out-of-scope subsystems, must be off): LPV ambient, projected clouds, player
+// reflection, lava UV distortion.
+#include "shading.cuh"
+
+namespace {
+
+struct ReflArgs {
+    float inv_view[16], inv_proj[16], proj_view[16];
+    int width, height, row0, row1;
+    int spp, checkerboard, trace_length, shadow_trace_length, frame, frame_mod128;
+    int rough, roughness_bias, temporal, reproject, derive_sh;
+    float halton[2];
+    float sun[3], moon[3], strong[3], viewer[3];
+    float color_mixed[3];
+    int grass[10];
+    const uint16_t* g_t; const uint8_t* g_normal; int gw, gh;
+    const uint16_t* gb_normal; const uint8_t* gb_pbr; int mw, mh;
+    const uint16_t* gi_sh; const uint16_t* gi_cocg; const uint8_t* gi_aosky; int iw, ih;
+    const uint8_t* shadow; int sw, sh;
+    TexArrayDev tex[4];
+    TexCubeDev sky;
+    const int32_t* block_data;
+    const int32_t* blue;
+    uint16_t* color; uint16_t* hitdist; uint8_t* emissive;
+};
+
+struct RfState { int px, py, CurrentBLSample; };
+
+// SampleBlueNoise2D (:606-614)
+VXD f2 rf_blue_noise_2d(const ReflArgs& a, RfState& st, int Index) {
+    f2 n;
+    n.x = blue_noise_1d(a.blue, st.px, st.py, Index, 1 + st.CurrentBLSample);
+    n.y = blue_noise_1d(a.blue, st.px, st.py, Index, 2 + st.CurrentBLSample);
+    st.CurrentBLSample += 2;
+    st.CurrentBLSample = st.CurrentBLSample % 128;
+    return n;
+}
+// ImportanceSampleGGX (:345-365)
+VXD f3 importance_sample_ggx(f3 N, float roughness, f2 Xi) {
+    float alpha = roughness * roughness;
+    float alpha2 = alpha * alpha;
+    float phi = 2.0f * VX_PI * Xi.x;
+    float cosTheta = sqrtf((1.0f - Xi.y) / (1.0f + (alpha2 - 1.0f) * Xi.y));
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    f3 H = F3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta);
+    f3 up = fabsf(N.z) < 0.999f ? F3(0.0f, 0.0f, 1.0f) : F3(1.0f, 0.0f, 0.0f);
+    f3 tangent = normalize(cross(up, N));
+    f3 bitangent = cross(N, tangent);
+    f3 sampleVec = tangent * H.x + bitangent * H.y + N * H.z;
+    return normalize(sampleVec);
+}
+// GetReflectionDirection (:621-644)
+VXD f3 get_reflection_direction(const ReflArgs& a, RfState& st, f3 N, float R) {
+    R = gmax(R, 0.05f);
+    float NearestDot = -100.0f;
+    f3 Best = F3(0.0f);
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        f2 Xi = rf_blue_noise_2d(a, st, a.temporal ? a.frame_mod128 : 100);
+        Xi = Xi * F2(0.9f, 0.65f);
+        f3 H = importance_sample_ggx(N, R, Xi);
+        float d = dot(H, N);
+        if (d > NearestDot) { Best = H; NearestDot = d; }
+    }
+    return Best;
+}
+// SHToIrradianceA (:452-462), SHToIrridiance (:437-449)
+VXD f3 sh_to_irradiance_a(f4 shY, f2 CoCg) {
+    float Y = gmax(0.0f, 3.544905f * shY.w);
+    CoCg = CoCg * (Y * 0.282095f / (shY.w + 1e-6f));
+    float T = Y - CoCg.y * 0.5f;
+    float G = CoCg.y + T;
+    float B = T - CoCg.x * 0.5f;
+    float R = B + CoCg.x;
+    return F3(gmax(R, 0.0f), gmax(G, 0.0f), gmax(B, 0.0f));
+}
+VXD f3 sh_to_irradiance(f4 shY, f2 CoCg, f3 v) {
+    float x = dot(F3(shY.x, shY.y, shY.z), v);
+    float Y = 2.0f * (1.023326f * x + 0.886226f * shY.w);
+    Y = gmax(Y, 0.0f);
+    CoCg = CoCg * (Y * 0.282095f / (shY.w + 1e-6f));
+    float T = Y - CoCg.y * 0.5f;
+    float G = CoCg.y + T;
+    float B = T - CoCg.x * 0.5f;
+    float R = B + CoCg.x;
+    return F3(gmax(R, 0.0f), gmax(G, 0.0f), gmax(B, 0.0f));
+}
+VXD float sq(float x) { return x * x; }
+// G_Smith_over_NdotV, SpecularGGX (:410-435), DeriveSpecularFromDiffuseSH (:521-546)
+VXD float g_smith_over_ndotv(float roughness, float NdotV, float NdotL) {
+    float alpha = sq(roughness);
+    float g1 = NdotV * sqrtf(sq(alpha) + (1.0f - sq(alpha)) * sq(NdotL));
+    float g2 = NdotL * sqrtf(sq(alpha) + (1.0f - sq(alpha)) * sq(NdotV));
+    return 2.0f * NdotL / (g1 + g2);
+}
+VXD float specular_ggx(f3 V, f3 L, f3 N, float roughness, float NoH_offset) {
+    f3 H = normalize(L - V);
+    float NoL = gmax(0.0f, dot(N, L));
+    float NoV = gmax(0.0f, -dot(N, V));
+    float NoH = gclamp(dot(N, H) + NoH_offset, 0.0f, 1.0f);
+    if (NoL > 0.0f) {
+        float G = g_smith_over_ndotv(roughness, NoV, NoL);
+        float alpha = sq(gmax(roughness, 0.02f));
+        float D = sq(alpha) / (VX_PI * sq(sq(NoH) * sq(alpha) + (1.0f - sq(NoH))));
+        return D * G / 4.0f;
+    }
+    return 0.0f;
+}
+VXD f3 derive_specular_from_diffuse_sh(f4 SHy, f3 IndirectDiffuse, f3 Eye, f3 Normal) {
+    float Roughness = 0.4f;
+    f3 IncomingDir = F3(SHy.x, SHy.y, SHy.z) / SHy.w * (0.282095f / 0.488603f);
+    f3 RawSpecularDir = reflect(Eye, Normal);
+    float IncomingLen = length(IncomingDir);
+    float Directionality = IncomingLen;
+    float Scale = 1.0f;
+    if (Directionality >= 1.0f) {
+        IncomingDir = IncomingDir / IncomingLen;
+    } else {
+        f3 q = IncomingDir / (IncomingLen + 0.00001f);
+        IncomingDir = F3(gmix(RawSpecularDir.x, q.x, Directionality), gmix(RawSpecularDir.y, q.y, Directionality), gmix(RawSpecularDir.z, q.z, Directionality));
+        Scale = powf(Roughness + 1.0f, 3.0f);
+    }
+    float Sp = specular_ggx(Eye, IncomingDir, Normal, gmax(Roughness, 0.39f), 0.0f);
+    f3 Integrated = powf(Sp, 1.2f) * IndirectDiffuse * 18.0f * Scale;
+    if (Integrated.x != Integrated.x || isinf(Integrated.x) || Integrated.y != Integrated.y || isinf(Integrated.y) || Integrated.z != Integrated.z || isinf(Integrated.z))
+        Integrated = F3(0.0f);
+    return gmax(Integrated, 0.00001f);
+}
+// capIntersect (:1264-1291), GetPlayerIntersect (:1301-1307)
+VXD float cap_intersect(f3 ro, f3 rd, f3 pa, f3 pb, float r) {
+    f3 ba = pb - pa, oa = ro - pa;
+    float baba = dot(ba, ba), bard = dot(ba, rd), baoa = dot(ba, oa), rdoa = dot(rd, oa), oaoa = dot(oa, oa);
+    float a = baba - bard * bard;
+    float b = baba * rdoa - baoa * bard;
+    float cc = baba * oaoa - baoa * baoa - r * r * baba;
+    float h = b * b - a * cc;
+    if (h >= 0.0f) {
+        float t = (-b - sqrtf(h)) / a;
+        float y = baoa + t * bard;
+        if (y > 0.0f && y < baba) return t;
+        f3 oc = (y <= 0.0f) ? oa : ro - pb;
+        b = dot(rd, oc);
+        cc = dot(oc, oc) - r * r;
+        h = b * b - cc;
+        if (h > 0.0f) return -b - sqrtf(h);
+    }
+    return -1.0f;
+}
+VXD bool get_player_intersect(f3 viewer, f3 WorldPos, f3 d) {
+    float x = 0.4f;
+    f3 VP = viewer + F3(-x, -x, +x);
+    return cap_intersect(WorldPos, d, VP, VP + F3(0.0f, 1.0f, 0.0f), 0.5f) > 0.0f;
+}
+// the reflection pass' own CalculateDirectionalLight (:313-336)
+VXD f3 rf_directional_light(f3 viewer, f3 world_pos, f3 light_dir, f3 radiance, f3 albedo, f3 normal, f3 pbr, float shadow) {
+    const float Epsilon = 0.00001f;
+    float Shadow = gmin(shadow, 1.0f);
+    f3 Lo = normalize(viewer - world_pos);
+    f3 N = normal;
+    float cosLo = gmax(0.0f, dot(N, Lo));
+    f3 F0 = gmix(F3(0.04f), albedo, pbr.y);
+    f3 Li = light_dir;
+    f3 Lh = normalize(Li + Lo);
+    float cosLi = gmax(0.0f, dot(N, Li));
+    float cosLh = gmax(0.0f, dot(N, Lh));
+    float fc = powf(1.0f - gmax(0.0f, dot(Lh, Lo)), 5.0f);
+    f3 F = F0 + (F3(1.0f) - F0) * fc;
+    float D = ndf_ggx(cosLh, pbr.x);
+    float G = ga_schlick_ggx(cosLi, cosLo, pbr.x);
+    f3 kd = gmix(F3(1.0f) - F, F3(0.0f), pbr.y);
+    f3 diffuseBRDF = kd * albedo;
+    f3 specularBRDF = (F * D * G) / gmax(Epsilon, 4.0f * cosLi * cosLo);
+    f3 radiance_s = radiance * 0.05f * 0.0f;
+    f3 Result = (diffuseBRDF * radiance * cosLi) + (specularBRDF * radiance_s * cosLi);
+    return gmax(Result, 0.0f) * gclamp(1.0f - Shadow, 0.0f, 1.0f);
+}
+VXD bool in_thresholded_screen_space(f2 v) {
+    float b = 0.032593f;
+    return v.x > b && v.x < 1.0f - b && v.y > b && v.y < 1.0f - b;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) reflection_trace_kernel(GridView g, const __grid_constant__ ReflArgs a, TraceStatsDev* stats) {
+    int px, py;
+    tile_pixel(px, py, a.row0);
+    const bool active = px < a.width && py < a.row1;
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    if (active) {
+        const size_t i = (size_t)py * a.width + px;
+        RfState st;
+        st.px = px; st.py = py; st.CurrentBLSample = 0;
+        const f2 vtc = pixel_uv(px, py, a.width, a.height);
+        const bool CheckerStep = cvt_trunc(((float)px + 0.5f) + ((float)py + 0.5f)) % 2 == (a.frame % 2);
+        int SPP = iclamp(a.spp, 1, 16);
+        if (a.checkerboard) SPP = cvt_trunc(gmix((float)a.spp, (float)((a.spp + a.spp % 2) / 2), CheckerStep ? 1.0f : 0.0f));
+        SPP = iclamp(SPP, 1, 16);
+        const f2 Jitter = F2(gclamp(a.halton[0] * 1.0f, -2.0f, 2.0f), gclamp(a.halton[1] * 1.0f, -2.0f, 2.0f));
+        const float tf = a.temporal ? 1.0f : 0.0f;
+        const f2 tc = F2(vtc.x + (Jitter.x / (float)a.width) * tf, vtc.y + (Jitter.y / (float)a.height) * tf);
+        const float Dist = att_r16f_bilinear(a.g_t, a.gw, a.gh, tc);
+        const f3 cam = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+        const f3 viewer = F3(a.viewer[0], a.viewer[1], a.viewer[2]);
+        const f3 strong = F3(a.strong[0], a.strong[1], a.strong[2]);
+        f3 P = cam + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * Dist;
+        f4 oColor = F4(0.0f, 0.0f, 0.0f, 0.0f);
+        float oHit = -1.0f, oMask = 0.0f;
+        if (!(Dist < 0.0f)) {
+            const f3 N0 = normal_from_id(att_r8_nearest(a.g_normal, a.gw, a.gh, tc), F3(1.0f));
+            const int mi = wrap_repeat(cvt_floor(vtc.x * (float)a.mw), a.mw), mj = wrap_repeat(cvt_floor(vtc.y * (float)a.mh), a.mh);
+            const uchar4 pb = __ldg(reinterpret_cast<const uchar4*>(a.gb_pbr) + ((size_t)mj * a.mw + mi));
+            const f4 PBRMap = F4(unorm8_to_float(pb.x), unorm8_to_float(pb.y), unorm8_to_float(pb.z), unorm8_to_float(pb.w));
+            const f3 I = normalize(P - viewer);
+            P = P + N0 * 0.035f;
+            float nv[3], shv[4], ccv[2];
+            att_half_bilinear<3>(a.gb_normal, a.mw, a.mh, vtc, nv);
+            att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, shv);
+            att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, ccv);
+            const f3 NormalMappedInitial = F3(nv[0], nv[1], nv[2]);
+            const f4 DiffuseSH = F4(shv[0], shv[1], shv[2], shv[3]);
+            const f2 DiffuseCoCg = F2(ccv[0], ccv[1]);
+            const f3 BaseIndirectDiffuse = sh_to_irradiance_a(DiffuseSH, DiffuseCoCg);
+            if (PBRMap.x >= 0.865f && a.derive_sh) {
+                f3 r = derive_specular_from_diffuse_sh(DiffuseSH, sh_to_irradiance(DiffuseSH, DiffuseCoCg, NormalMappedInitial), I, NormalMappedInitial);
+                oColor = F4(r.x, r.y, r.z, 0.0f); oHit = 0.5f; oMask = 0.0f;
+            } else {
+                const float RoughnessAt = PBRMap.x;
+                const float RoughnessBias = gmix(1.0f, 0.85f, a.roughness_bias ? 1.0f : 0.0f);
+                float ComputedShadow = 0.0f;
+                int ShadowItr = 0;
+                float AveragedHitDistance = 0.001f, TotalMeaningfulHits = 0.0f, EmissivityMask = 0.0f;
+                int total_hits = 0;
+                f4 TotalColor = F4(0.0f, 0.0f, 0.0f, 0.0f);
+                const f3 MIXED = F3(a.color_mixed[0], a.color_mixed[1], a.color_mixed[2]);
+#pragma unroll 1
+                for (int s = 0; s < SPP; ++s) {
+                    const f3 ReflectionNormal = a.rough ? get_reflection_direction(a, st, NormalMappedInitial, gclamp(RoughnessAt * RoughnessBias, 0.01f, 1.0f)) : NormalMappedInitial;
+                    const f3 R = reflect(I, ReflectionNormal);
+                    TraceResult h = traverse_df<STATS>(g, P, R, a.trace_length, &ls);
+                    const float T = h.t;
+                    const f3 Normal = h.normal;
+                    const f3 HitPosition = P + (R * T);
+                    if (T > 0.0f) {
+                        f2 UV = F2(0.0f, 0.0f);
+                        f3 Tangent = F3(0.0f), Bitangent = F3(0.0f);
+                        calculate_vectors(HitPosition, Normal, Tangent, Bitangent, UV);
+                        UV.y = 1.0f - UV.y;
+                        const int reference_id = iclamp(h.block, 0, 127);
+                        bool ReprojectionSuccessful = false;
+                        f2 SS = F2(-1.0f, -1.0f);
+                        f3 Ambient = BaseIndirectDiffuse;
+                        if (a.reproject) {
+                            // ReprojectReflectionToScreenSpace (:574-586)
+                            f4 pp = mat4_mul(a.proj_view, F4(HitPosition.x, HitPosition.y, HitPosition.z, 1.0f));
+                            f3 q = F3(pp.x / pp.w, pp.y / pp.w, pp.z / pp.w);
+                            SS = F2(q.x * 0.5f + 0.5f, q.y * 0.5f + 0.5f);
+                            const float d2 = att_r16f_bilinear(a.g_t, a.gw, a.gh, SS);
+                            const f3 PosAt = cam + normalize(ray_direction_at(a.inv_view, a.inv_proj, SS)) * d2;
+                            const f3 NormalAt = normal_from_id(att_r8_nearest(a.g_normal, a.gw, a.gh, SS), F3(1.0f));
+                            const f3 df = PosAt - HitPosition;
+                            const f3 diff = F3(fabsf(df.x), fabsf(df.y), fabsf(df.z));
+                            const float Error = dot(diff, diff);
+                            ReprojectionSuccessful = Error < 0.095f && eq3(NormalAt, Normal) && in_thresholded_screen_space(SS);
+                            if (ReprojectionSuccessful) {
+                                float rs[4], rc[2], ra[2];
+                                att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, SS, rs);
+                                att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, SS, rc);
+                                Ambient = sh_to_irradiance_a(F4(rs[0], rs[1], rs[2], rs[3]), F2(rc[0], rc[1]));
+                                att_unorm8_bilinear<2>(a.gi_aosky, a.iw, a.ih, SS, ra);
+                                const float ReprojectedVXAO = powf(ra[0], 0.75f);
+                                if (d2 > 0.0f) {
+                                    if (distance(PosAt, cam) < 40.0f) Ambient = Ambient * ReprojectedVXAO;
+                                }
+                            }
+                        }
+                        f4 ids = F4((float)__ldg(a.block_data + reference_id), (float)__ldg(a.block_data + 128 + reference_id),
+                                    (float)__ldg(a.block_data + 256 + reference_id), (float)__ldg(a.block_data + 384 + reference_id));
+                        if (reference_id == a.grass[0]) {
+                            if (eq3(Normal, face_normal(4)) || eq3(Normal, face_normal(5)) || eq3(Normal, face_normal(0)) || eq3(Normal, face_normal(1))) { ids.x = (float)a.grass[4]; ids.y = (float)a.grass[5]; ids.z = (float)a.grass[6]; }
+                            else if (eq3(Normal, face_normal(2))) { ids.x = (float)a.grass[1]; ids.y = (float)a.grass[2]; ids.z = (float)a.grass[3]; }
+                            else if (eq3(Normal, face_normal(3))) { ids.x = (float)a.grass[7]; ids.y = (float)a.grass[8]; ids.z = (float)a.grass[9]; }
+                        }
+                        const f3 Albedo = xyz(texarray_sample(a.tex[VXRT_TEX_ALBEDO], UV.x, UV.y, ids.x, 0.0f));
+                        const f3 Radiance = MIXED * 0.6f;
+                        const f4 SampledPBR = texarray_sample(a.tex[VXRT_TEX_PBR], UV.x, UV.y, ids.z, 0.0f);
+                        const float AO = powf(SampledPBR.w, 2.0f);
+                        const bool PlayerInShadow = get_player_intersect(viewer, HitPosition + Normal * 0.035f, strong);
+                        if (ShadowItr < (SPP / 4 > 1 ? SPP / 4 : 1)) {
+                            if (!PlayerInShadow) {
+                                if (ReprojectionSuccessful && a.reproject && in_thresholded_screen_space(SS)) {
+                                    float sv[1];
+                                    att_unorm8_bilinear<1>(a.shadow, a.sw, a.sh, SS, sv);
+                                    ComputedShadow = sv[0];
+                                } else {
+                                    // GetShadowAt (:1327-1346)
+                                    const f3 spos = HitPosition + Normal * 0.055f;
+                                    if (get_player_intersect(viewer, spos, strong)) ComputedShadow = 1.0f;
+                                    else {
+                                        TraceResult sh = traverse_df<STATS>(g, spos, strong, a.shadow_trace_length, &ls);
+                                        ComputedShadow = sh.t > 0.0f ? 1.0f : 0.0f;
+                                    }
+                                }
+                            } else {
+                                ComputedShadow = 1.0f;
+                            }
+                            ShadowItr = ShadowItr + 1;
+                        }
+                        Ambient = (Ambient * 1.0f * gclamp(AO, 0.1f, 1.0f)) * Albedo;
+                        const f3 nm = xyz(texarray_sample(a.tex[VXRT_TEX_NORMAL], UV.x, UV.y, ids.y, 3.0f)) * 2.0f - F3(1.0f);
+                        const f3 NormalMapped = mat3_mul(Tangent, Bitangent, Normal, nm);
+                        f3 DirectLighting = Ambient + rf_directional_light(viewer, HitPosition, strong, Radiance, Albedo, NormalMapped,
+                                                                           F3(SampledPBR.x, SampledPBR.y, SampledPBR.z), ComputedShadow);
+                        if (ids.w > -0.5f) {
+                            float Emissivity = texarray_sample(a.tex[VXRT_TEX_EMISSIVE], UV.x, UV.y, ids.w, 2.0f).x;
+                            if (Emissivity > 0.1f) {
+                                const float m = 19.0f, lbiasx = 0.02501f, lbiasy = 0.03001f;
+                                Emissivity *= (UV.x > lbiasx && UV.x < 1.0f - lbiasx && UV.y > lbiasy && UV.y < 1.0f - lbiasy) ? 1.0f : 0.0f;
+                                const float Flicker = 1.0f;
+                                DirectLighting = Albedo * gmax(Emissivity * m * Flicker, 2.0f);
+                                EmissivityMask = 1.0f;
+                            }
+                        }
+                        TotalColor = F4(TotalColor.x + DirectLighting.x, TotalColor.y + DirectLighting.y, TotalColor.z + DirectLighting.z, TotalColor.w + 1.0f);
+                        AveragedHitDistance += T;
+                        TotalMeaningfulHits += 1.0f;
+                    } else {
+                        const f3 Atmos = texcube_sample(a.sky, normalize(R));
+                        const f3 am = Atmos * gmix(1.0f, 1.175f, (PBRMap.y > 0.05f) ? 1.0f : 0.0f);
+                        TotalColor = F4(TotalColor.x + am.x, TotalColor.y + am.y, TotalColor.z + am.z, TotalColor.w + 1.0f);
+                    }
+                    total_hits++;
+                }
+                AveragedHitDistance /= gmax(TotalMeaningfulHits, 0.01f);
+                const float th = (float)total_hits;
+                TotalColor = F4(TotalColor.x / th, TotalColor.y / th, TotalColor.z / th, TotalColor.w / th);
+                oColor = F4(gclamp(TotalColor.x, 0.0000001f, 100.0f), gclamp(TotalColor.y, 0.0000001f, 100.0f), gclamp(TotalColor.z, 0.0000001f, 100.0f),
+                            gclamp(TotalColor.w, 0.0000001f, 100.0f));
+                oHit = gclamp(TotalMeaningfulHits > 0.01f ? AveragedHitDistance : -1.0f, -10.0f, 200.0f);
+                oMask = gclamp(EmissivityMask, 0.0f, 1.0f);
+            }
+        }
+        reinterpret_cast<ushort4*>(a.color)[i] = make_ushort4(float_to_half_bits(oColor.x), float_to_half_bits(oColor.y), float_to_half_bits(oColor.z), float_to_half_bits(oColor.w));
+        a.hitdist[i] = float_to_half_bits(oHit);
+        a.emissive[i] = float_to_unorm8(oMask);
+    }
+    if (STATS) flush_stats(stats, ls);
+}
+
+inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+}
+
+}  // namespace
+
+int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
+    int rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_REFL_COLOR, p.width, p.height, 8))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_REFL_HITDIST, p.width, p.height, 2))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_REFL_EMISSIVE, p.width, p.height, 1))) return rc;
+    ReflArgs a;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    // u_Projection * u_View: mat4 * mat4 evaluated column by column with the pinned mat4*vec4 association
+    for (int col = 0; col < 4; ++col)
+        for (int r = 0; r < 4; ++r) {
+            const float* v = p.view + 4 * col;
+            a.proj_view[4 * col + r] = (p.projection[r] * v[0] + p.projection[4 + r] * v[1]) + (p.projection[8 + r] * v[2] + p.projection[12 + r] * v[3]);
+        }
+    a.width = p.width; a.height = p.height;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    a.spp = p.spp; a.checkerboard = p.checkerboard; a.trace_length = p.trace_length; a.shadow_trace_length = p.shadow_trace_length;
+    a.frame = p.current_frame; a.frame_mod128 = p.current_frame_mod128;
+    a.rough = p.rough_reflections; a.roughness_bias = p.roughness_bias; a.temporal = p.temporal; a.reproject = p.reproject_to_screen_space;
+    a.derive_sh = p.derive_from_diffuse_sh;
+    a.halton[0] = p.halton[0]; a.halton[1] = p.halton[1];
+    for (int i = 0; i < 3; ++i) { a.sun[i] = p.sun_direction[i]; a.moon[i] = p.moon_direction[i]; a.strong[i] = p.stronger_light_direction[i]; a.viewer[i] = p.viewer_position[i]; }
+    // main() prologue (:722-727): SAMPLED_COLOR_MIXED = mix(SampleSunColor(), SampleMoonColor(), SunVisibility)
+    float sc[3], mc[3];
+    vxrt_host_sun_color(c, p.sun_direction, p.sun_strength_modifier, sc);
+    vxrt_host_moon_color(c, p.moon_direction, p.moon_strength_modifier, mc);
+    float sdot = (p.sun_direction[0] * 0.0f + p.sun_direction[1] * 1.0f) + p.sun_direction[2] * 0.0f;
+    float sv = sdot + 0.05f;
+    sv = sv < 0.0f ? 0.0f : sv; sv = (0.1f < sv) ? 0.1f : sv;
+    sv = sv * 12.0f;
+    sv = 1.0f - sv;
+    for (int i = 0; i < 3; ++i) a.color_mixed[i] = sc[i] * (1.0f - sv) + mc[i] * sv;
+    for (int i = 0; i < 10; ++i) a.grass[i] = p.grass_props[i];
+    const Attachment& gt = c->att[VXRT_ATT_INITIAL_T];
+    a.g_t = (const uint16_t*)gt.ptr; a.g_normal = (const uint8_t*)c->att[VXRT_ATT_INITIAL_NORMAL].ptr; a.gw = gt.width; a.gh = gt.height;
+    const Attachment& gn = c->att[VXRT_ATT_GBUF_NORMAL];
+    a.gb_normal = (const uint16_t*)gn.ptr; a.gb_pbr = (const uint8_t*)c->att[VXRT_ATT_GBUF_PBR].ptr; a.mw = gn.width; a.mh = gn.height;
+    const Attachment& gs = c->att[VXRT_ATT_GI_SH];
+    a.gi_sh = (const uint16_t*)gs.ptr; a.gi_cocg = (const uint16_t*)c->att[VXRT_ATT_GI_COCG].ptr; a.gi_aosky = (const uint8_t*)c->att[VXRT_ATT_GI_AOSKY].ptr;
+    a.iw = gs.width; a.ih = gs.height;
+    const Attachment& sh = c->att[VXRT_ATT_SHADOW];
+    a.shadow = (const uint8_t*)sh.ptr; a.sw = sh.width; a.sh = sh.height;
+    for (int k = 0; k < 4; ++k) a.tex[k] = c->tex[k];
+    a.sky = c->sky;
+    a.block_data = c->d_block_data;
+    a.blue = c->d_blue_noise;
+    a.color = (uint16_t*)c->att[VXRT_ATT_REFL_COLOR].ptr; a.hitdist = (uint16_t*)c->att[VXRT_ATT_REFL_HITDIST].ptr;
+    a.emissive = (uint8_t*)c->att[VXRT_ATT_REFL_EMISSIVE].ptr;
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (c->stats_on) reflection_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    else reflection_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}

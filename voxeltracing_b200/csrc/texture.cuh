@@ -6,17 +6,7 @@
 #pragma once
 #include "vmath.cuh"
 
-struct TexArrayDev {
-    const uint8_t* data;      // all levels, level l at data + level_offset[l]; RGBA8, layer-major
-    const float* decode;      // 256-entry code -> float table for RGB (sRGB or /255)
-    unsigned level_offset[12];
-    int w, h, layers, levels;
-};
-
-struct TexCubeDev {
-    const float* data;  // 6 faces (+X,-X,+Y,-Y,+Z,-Z) x res x res x RGB float
-    int res;
-};
+#include "ctx.h"
 
 VXD f4 texarray_texel(const TexArrayDev& t, int level, int layer, int x, int y) {
     int lw = max(t.w >> level, 1), lh = max(t.h >> level, 1);

@@ -150,6 +150,17 @@ class Context:
         h, w = t.shape[0], t.shape[1]
         self._check(self._lib.vxrt_cuda_set_blue_noise_texture(self._h, _p(t), w, h))
 
+    def set_texture_array(self, kind: int, rgba: np.ndarray):
+        """rgba: uint8[layers, size, size, 4], file row 0 first (TextureArray::CreateArray)."""
+        t = np.ascontiguousarray(rgba, dtype=np.uint8)
+        layers, h, w = t.shape[0], t.shape[1], t.shape[2]
+        self._check(self._lib.vxrt_cuda_set_texture_array(self._h, kind, layers, w, h, _p(t)))
+
+    def set_skymap(self, faces: np.ndarray):
+        """faces: float32[6, res, res, 3] in +X,-X,+Y,-Y,+Z,-Z order."""
+        f = np.ascontiguousarray(faces, dtype=np.float32)
+        self._check(self._lib.vxrt_cuda_set_skymap(self._h, f.shape[1], _p(f)))
+
     # -- passes --
     def initial_trace(self, cam, width: int, height: int, render_distance: int = 350, jitter=None, tile=(0, 0)):
         p = abi.PrimaryParams()
@@ -180,6 +191,18 @@ class Context:
         p.tile.row0, p.tile.rows = tile
         self._check(self._lib.vxrt_cuda_shadow_trace(self._h, C.byref(p)))
         return p
+
+    def generate_gbuffer(self, params: "abi.GBufferParams"):
+        self._check(self._lib.vxrt_cuda_generate_gbuffer(self._h, C.byref(params)))
+
+    def shade_direct(self, params: "abi.DirectParams"):
+        self._check(self._lib.vxrt_cuda_shade_direct(self._h, C.byref(params)))
+
+    def diffuse_trace(self, params: "abi.GIParams"):
+        self._check(self._lib.vxrt_cuda_diffuse_trace(self._h, C.byref(params)))
+
+    def reflection_trace(self, params: "abi.ReflectionParams"):
+        self._check(self._lib.vxrt_cuda_reflection_trace(self._h, C.byref(params)))
 
     # -- attachments --
     def attachment_info(self, att: int):
