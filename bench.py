@@ -1,16 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — Mrays/s of DF-DDA traversal (BASELINE.json metric) on the frame workload.
+"""bench.py — Mrays/s of DF-DDA traversal (BASELINE.json metric) on a frame workload.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One step = one frame of the workload (every VoxelTraversalDF invocation counts as one ray).  With
-N > 1 (torchrun, one rank per GPU) every rank renders its own frame of the camera-path batch per step
-(grids replicated, weak scaling) and the frames' output attachments are gathered to rank 0 over NCCL.
-Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every field.
+One step = one frame of the workload: every VoxelTraversalDF invocation (primary, sun-shadow, GI bounce,
+GI shadow, reflection, reflection shadow) counts as one ray.  With N > 1 (torchrun, one rank per GPU)
+every rank renders its own frame of the camera-path batch per step (grids and tables replicated, weak
+scaling) and the frames' output attachments are gathered to rank 0 over NCCL inside the timed region.
+Prints ONE JSON line on rank 0.  DESIGN.md §6 defines every field.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -23,24 +25,34 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
-    # BASELINE.json configs[2]: 1080p primary + sun-shadow rays (+ direct shading) on generated plains
-    "config3_1080p_primary_shadow": dict(width=1920, height=1080, world=("plains_structures", "plains", 1),
-                                         passes=("primary", "shadow")),
+    # BASELINE.json configs[2]: 1080p primary + sun-shadow rays + Cook-Torrance direct shading, generated plains
+    "config3_1080p_direct": dict(width=1920, height=1080, world=("plains_structures", "plains", 1), camera="orbit",
+                                 passes=("primary", "gbuffer", "shadow", "direct")),
+    # BASELINE.json configs[3]: 1080p 1-spp 2-bounce path-traced diffuse GI + rough reflections ('Test Worlds/gi')
+    "config4_1080p_gi": dict(width=1920, height=1080, world=("gi", "rooms", 2), camera="rooms",
+                             passes=("primary", "gbuffer", "gi", "shadow", "reflection", "direct")),
+    # BASELINE.json configs[4]: 4K 4-spp GI camera-path batch on the Medival import (stand-in: town)
+    "config5_4k_gi4": dict(width=3840, height=2160, world=("Medival", "town", 3), camera="orbit", gi_spp=4,
+                           passes=("primary", "gbuffer", "gi", "shadow", "reflection", "direct")),
 }
-DEFAULT_WORKLOAD = "config3_1080p_primary_shadow"
+DEFAULT_WORKLOAD = "config4_1080p_gi"
+TRACE_PASSES = ("primary", "shadow", "gi", "reflection")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="only warm-up + steps of the plain step (for ncu)")
+    ap.add_argument("--tex-size", type=int, default=512)
     return ap.parse_args()
 
 
@@ -61,9 +73,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
-        self.gpu = gpu_index
+        self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
         try:
@@ -108,83 +118,135 @@ def build_world(spec, dims=(384, 128, 384)):
     from voxeltracing_b200 import host_api
 
     name, kind, seed = spec
-    blocks, desc = host_api.load_named_world(name, kind, seed, dims)
-    return blocks, desc
+    return host_api.load_named_world(name, kind, seed, dims)
+
+
+def camera_for(wl, frame):
+    from voxeltracing_b200.pipeline import orbit_camera, rooms_camera
+
+    aspect = wl["width"] / wl["height"]
+    return rooms_camera(frame, aspect) if wl["camera"] == "rooms" else orbit_camera(frame, aspect)
+
+
+def frame_config(wl):
+    from voxeltracing_b200.pipeline import FrameConfig
+
+    return FrameConfig(width=wl["width"], height=wl["height"], passes=wl["passes"], gi_spp=wl.get("gi_spp", 1))
+
+
+BLUE_TEX = np.random.default_rng(11).integers(0, 256, (256, 256, 4), dtype=np.uint8)
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm: the CPU implementation of the path on the host cores (oracle/_ref if it was built
-# from the reference's shaders, else the oracle port)
+# CPU implementation of the path on the host cores: oracle/_ref (the reference's own shaders compiled
+# for the CPU) when that build is present, else the oracle port
 # --------------------------------------------------------------------------------------------------
 
-def cpu_frame_runner(blocks, wl):
-    """Returns (run(frame_index) -> rays, kind, description). Prefers oracle/_ref (the reference's own
-    shader sources compiled for the CPU)."""
-    from oracle import binding as ob
-    from voxeltracing_b200 import abi, host_api
-    from voxeltracing_b200.pipeline import orbit_camera
+class CpuFrame:
+    def __init__(self, blocks, wl, inputs, prefer_ref=True):
+        from oracle import binding as ob
+        from oracle import ref_binding as rb
+        from voxeltracing_b200.pipeline import FrameRenderer
 
-    kind = "port"
-    ow = ob.OracleWorld(blocks)
-    W, H = wl["width"], wl["height"]
-    light = host_api.sun_direction(50.0)[2]
-    rng = np.random.default_rng(11)
-    blue = rng.integers(0, 256, (256, 256, 4), dtype=np.uint8)
+        self.ob, self.rb, self.wl = ob, rb, wl
+        self.ow = ob.OracleWorld(blocks)
+        self.scene = ob.OracleScene(self.ow)
+        inputs.apply_to_oracle(self.scene)
+        need = {"primary": "initial", "shadow": "shadow", "gbuffer": "gbuffer", "gi": "diffuse", "reflection": "reflection", "direct": "color"}
+        self.use_ref = (prefer_ref and blocks.shape == (384, 128, 384) and rb.available("df")
+                        and all(rb.available(need[p]) for p in wl["passes"]))
+        if self.use_ref:
+            rb.set_scene(blocks, self.ow.df, inputs.table, inputs.blue, inputs.textures, inputs.sky)
+        self.kind = "reference" if self.use_ref else "port"
+        self.cores = ob.get_threads()
+        # parameter marshalling is shared with the GPU arm (params_for needs no Context)
+        self.fr = FrameRenderer(None, frame_config(wl), inputs.grass, inputs.cactus)
 
-    def fill(dst, src):
-        for i, v in enumerate(np.asarray(src, np.float32).ravel()):
-            dst[i] = float(v)
-
-    def run(frame: int, rows=None) -> int:
-        cam = orbit_camera(frame, W / H)
+    def run(self, frame: int, rows=None) -> int:
+        """Renders (a band of rows of) one frame on the CPU; returns the number of rays traced.  Every pass is
+        restricted to the band: with equal resolutions and screen-space reprojection off (the bench
+        configurations) a pass only reads its own pixel of the earlier attachments."""
+        rb, ow, sc, wl = self.rb, self.ow, self.scene, self.wl
+        cam = camera_for(wl, frame)
+        tile = rows if rows else (0, 0)
         rays = 0
-        p = abi.PrimaryParams()
-        fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
-        p.width, p.height, p.render_distance = W, H, 350
-        if rows:
-            p.tile.row0, p.tile.rows = rows
-        g = ow.initial_trace(p, want_stats=True)
-        rays += g["stats"]["rays"]
-        if "shadow" in wl["passes"]:
-            s = abi.ShadowParams()
-            fill(s.inv_view, cam.inv_view); fill(s.inv_projection, cam.inv_projection)
-            s.width, s.height = W, H
-            fill(s.light_direction, light)
-            s.current_frame, s.soft_shadows, s.max_iterations = frame, 1, 350
-            if rows:
-                s.tile.row0, s.tile.rows = rows
-            o = ow.shadow_trace(s, g["t"], g["normal"], blue, want_stats=True)
-            rays += o["stats"]["rays"]
+        out = {}
+        for name in wl["passes"]:
+            p = self.fr.params_for(name, cam, frame, tile)
+            if name == "primary":
+                if self.use_ref:
+                    g = rb.initial_trace(ow.blocks, ow.df, p)
+                    rays += (rows[1] if rows else wl["height"]) * wl["width"]  # one VoxelTraversalDF call per pixel
+                else:
+                    g = ow.initial_trace(p, want_stats=True)
+                    rays += g["stats"]["rays"]
+                out["g"] = g
+            elif name == "gbuffer":
+                g = out["g"]
+                out["gb"] = (rb.generate_gbuffer if self.use_ref else sc.generate_gbuffer)(p, g["inv_t"], g["normal"], g["block"])
+            elif name == "shadow":
+                g = out["g"]
+                if self.use_ref:
+                    s = rb.shadow_trace(ow.blocks, ow.df, p, g["t"], g["normal"], BLUE_TEX)
+                    # a shadow ray is cast unless the pixel is sky (transversal 64) or faces away (0.01)
+                    r0, nr = rows if rows else (0, wl["height"])
+                    tr = s["transversal"][r0:r0 + nr].astype(np.float32)
+                    rays += int(((tr != 64.0) & (tr != np.float32(np.float16(0.01)))).sum())
+                else:
+                    s = ow.shadow_trace(p, g["t"], g["normal"], BLUE_TEX, want_stats=True)
+                    rays += s["stats"]["rays"]
+                out["sh"] = s
+            elif name == "gi":
+                g = out["g"]
+                out["gi"] = sc.diffuse_trace(p, g["t"], g["normal"])
+                rays += out["gi"]["stats"]["rays"]
+            elif name == "reflection":
+                g = out["g"]
+                rays += sc.reflection_trace(p, g["t"], g["normal"], out["gb"], out["gi"], out["sh"]["shadow"])["stats"]["rays"]
+            elif name == "direct":
+                g = out["g"]
+                (rb.shade_direct if self.use_ref else sc.shade_direct)(p, g["inv_t"], out["gb"], out["sh"]["shadow"])
         return rays
 
-    return run, kind, ob.get_threads()
+
+def cpu_sample(cpu: CpuFrame, wl, first_frame: int, max_steps: int, seconds: float, frame_budget_s: float):
+    """Times a bounded sample: a band of rows of each frame, sized so one frame is ~frame_budget_s of CPU work."""
+    H = wl["height"]
+    probe_rows = 64
+    t0 = time.perf_counter(); cpu.run(first_frame, rows=(H // 2 - probe_rows // 2, probe_rows)); dt = time.perf_counter() - t0
+    rows = int(min(H, max(8, probe_rows * frame_budget_s / max(dt, 1e-4))))
+    band = ((H - rows) // 2, rows)
+    n, rays, t0 = 0, 0, time.perf_counter()
+    while n < max_steps and (time.perf_counter() - t0 < seconds or n < 2):
+        rays += cpu.run(first_frame + n, rows=band); n += 1
+    dt = time.perf_counter() - t0
+    return rays / dt / 1e6, dt / n * 1e3, n, band
 
 
-def run_reference_arm(args, wl, rank, world_size):
+def cpu_arm(blocks, wl, inputs):
+    """oracle/_ref runs the reference's own shaders; its GI / reflection drivers do not count rays, so the
+    frames that contain those passes are timed on the port (bit-identical to oracle/_ref: tests/test_oracle_golden.py)."""
+    return CpuFrame(blocks, wl, inputs, prefer_ref=not any(p in wl["passes"] for p in ("gi", "reflection")))
+
+
+def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
+    import scene_util as su
+
     blocks, world_desc = build_world(wl["world"])
-    run, kind, cores = cpu_frame_runner(blocks, wl)
-    H = wl["height"]
-    # bounded sample: a band of rows of each frame, sized so a step is ~0.25 s of CPU work
-    t0 = time.perf_counter(); probe_rays = run(0, rows=(H // 2 - 8, 16)); dt = time.perf_counter() - t0
-    rows = int(min(H, max(16, 16 * 0.25 / max(dt, 1e-4))))
-    band = ((H - rows) // 2, rows)
-    for i in range(args.warmup):
-        run(i, rows=band)
-    rays = 0
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        rays += run(i, rows=band)
-    dt = time.perf_counter() - t0
-    mrays = rays / dt / 1e6
+    inputs = su.SceneInputs(args.tex_size, sky="constant" if wl["camera"] == "rooms" else "gradient")
+    cpu = cpu_arm(blocks, wl, inputs)
+    for i in range(min(args.warmup, 2)):
+        cpu.run(i, rows=(wl["height"] // 2 - 32, 64))
+    mrays, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, 120.0, 0.5)
     line = {
         "impl": "reference", "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": n, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "world": world_desc, "width": wl["width"], "height": wl["height"]},
-        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind,
-                         "sample": f"rows [{band[0]},{band[0] + band[1]}) of each {wl['width']}x{wl['height']} frame, {args.steps} frames"},
+        "config": {"workload": args.workload, "world": world_desc, "width": wl["width"], "height": wl["height"], "passes": list(wl["passes"])},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind,
+                         "sample": f"rows [{band[0]},{band[0] + band[1]}) of each {wl['width']}x{wl['height']} frame (every pass restricted to the band), {n} frames"},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -202,14 +264,15 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference_arm(args, wl, rank, world_size)
+        run_reference_arm(args, wl, rank)
         return
 
     import torch
     import torch.distributed as dist
 
-    from voxeltracing_b200 import abi, engine
-    from voxeltracing_b200.pipeline import FrameConfig, FrameRenderer, orbit_camera
+    import scene_util as su
+    from voxeltracing_b200 import engine
+    from voxeltracing_b200.pipeline import PASS_KERNEL, PASS_OUTPUT_BYTES, FrameRenderer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -219,6 +282,7 @@ def main():
 
     W, H = wl["width"], wl["height"]
     blocks, world_desc = build_world(wl["world"])
+    inputs = su.SceneInputs(args.tex_size, sky="constant" if wl["camera"] == "rooms" else "gradient")
     ctx = engine.Context(local_rank)
     # all work of this rank (our kernels, NCCL gathers, timing events) goes on one explicit torch stream
     stream = torch.cuda.Stream(device=local_rank)
@@ -226,51 +290,58 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     ctx.upload_world(blocks)
     ctx.generate_distance_field()
-    rng = np.random.default_rng(11)
-    ctx.set_blue_noise_texture(rng.integers(0, 256, (256, 256, 4), dtype=np.uint8))
-    cfg = FrameConfig(width=W, height=H, passes=wl["passes"])
-    fr = FrameRenderer(ctx, cfg)
+    ctx.set_blue_noise_texture(BLUE_TEX)
+    inputs.apply_to_context(ctx)
+    cfg = frame_config(wl)
+    fr = FrameRenderer(ctx, cfg, inputs.grass, inputs.cactus)
 
-    # every rank renders its own frame of the camera path per step (weak scaling)
-    def frame_of(step):
+    def frame_of(step):  # every rank renders its own frame of the camera path per step (weak scaling)
         return step * world_size + rank
 
-    cams = [orbit_camera(frame_of(s), W / H) for s in range(args.warmup + args.steps + 1)]
+    n_total = args.warmup + args.steps
+    prepared = [fr.prepare(camera_for(wl, frame_of(s)), frame_of(s)) for s in range(n_total)]
 
-    # rays per step are deterministic: count them once with the stats variant, outside the timed region
+    if args.profile:
+        for s in range(n_total):
+            fr.submit(prepared[s])
+        torch.cuda.synchronize()
+        ctx.close()
+        return
+
+    # rays per step are deterministic: count them once per pass with the stats variant of the kernels,
+    # outside the timed region
+    trace_passes = [p for p in cfg.passes if p in TRACE_PASSES]
+    pass_stats = {p: {"rays": 0, "iterations": 0} for p in trace_passes}
+    rays_per_step = []
     ctx.stats_enable(True)
     ctx.stats_read(reset=True)
-    rays_per_step = []
-    iters_total = 0
-    for s in range(args.warmup, args.warmup + args.steps):
-        fr.render(cams[s], frame=frame_of(s))
-        st = ctx.stats_read(reset=True)
-        rays_per_step.append(st["rays"])
-        iters_total += st["iterations"]
+    for s in range(args.warmup, n_total):
+        acc = [0]
+
+        def stat_hook(name, where, acc=acc):
+            if where == "end" and name in pass_stats:
+                st = ctx.stats_read(reset=True)
+                pass_stats[name]["rays"] += st["rays"]
+                pass_stats[name]["iterations"] += st["iterations"]
+                acc[0] += st["rays"]
+
+        fr.submit(prepared[s], hook=stat_hook)
+        rays_per_step.append(acc[0])
     ctx.stats_enable(False)
     total_rays = int(sum(rays_per_step))
-    mean_iters = iters_total / max(total_rays, 1)
-    # primary-only statistics for the roofline of the dominant kernel
-    ctx.stats_enable(True); ctx.stats_read(reset=True)
-    prim = FrameRenderer(ctx, FrameConfig(width=W, height=H, passes=("primary",)))
-    for s in range(args.warmup, args.warmup + args.steps):
-        prim.render(cams[s], frame=frame_of(s))
-    pst = ctx.stats_read(reset=True)
-    ctx.stats_enable(False)
-    fr.render(cams[0])  # restore full attachments
+    total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
 
-    # gather buffers (N > 1): output attachments of every rank land on rank 0
-    outs = [torch.as_tensor(ctx.attachment_as_device_array(a), device=f"cuda:{local_rank}") for a in cfg.outputs]
+    outs = [torch.as_tensor(ctx.attachment_as_device_array(a), device=f"cuda:{local_rank}") for a in fr.outputs]
     gather_bufs = None
     if world_size > 1:
         gather_bufs = [[torch.empty_like(o) for _ in range(world_size)] if rank == 0 else None for o in outs]
 
-    # the inputs (37.7 MB of grids) are smaller than L2, so L2 is flushed between timed steps by
-    # overwriting a 256 MiB buffer; the flush is outside the per-step event pairs.
+    # the inputs (37.7 MB of grids + the touched texture mips) are smaller than L2, so L2 is flushed between
+    # timed steps by overwriting a 256 MiB buffer; the flush is outside the per-step event pairs
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
     def step(s, hook=None):
-        fr.render(cams[s], frame=frame_of(s), hook=hook)
+        fr.submit(prepared[s], hook=hook)
         if world_size > 1:
             for o, gb in zip(outs, gather_bufs):
                 dist.gather(o, gb, dst=0)
@@ -280,13 +351,15 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident ----
-    dom = "primary"
-    dom_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    pass_ev = [{p: (ev(), ev()) for p in cfg.passes} for _ in range(args.steps)]
+    step_ev = [(ev(), ev()) for _ in range(args.steps)]
 
     def make_hook(i):
         def hook(name, where):
-            if name == dom:
-                dom_ev[i][0 if where == "begin" else 1].record(stream)
+            pass_ev[i][name][0 if where == "begin" else 1].record(stream)
         return hook
 
     sampler = ClockSampler(local_rank)
@@ -295,7 +368,6 @@ def main():
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches_before = ctx.launch_count
     for i in range(args.steps):
         flush_buf.zero_()
@@ -308,10 +380,10 @@ def main():
     ms = float(sum(a.elapsed_time(b) for a, b in step_ev))  # exactly K steps, flushes excluded
     launches = ctx.launch_count - launches_before
     clocks = sampler.stop() if rank == 0 else None
-    dom_ms = float(np.mean([a.elapsed_time(b) for a, b in dom_ev]))
+    pass_ms = {p: float(np.mean([pe[p][0].elapsed_time(pe[p][1]) for pe in pass_ev])) for p in cfg.passes}
 
     # ---- distance-field regeneration (BASELINE config 2), L2 flushed before every regeneration ----
-    df_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+    df_ev = [(ev(), ev()) for _ in range(30)]
     for a, b in df_ev:
         flush_buf.zero_()
         a.record(stream)
@@ -320,15 +392,17 @@ def main():
     torch.cuda.synchronize()
     df_us = float(np.median([a.elapsed_time(b) for a, b in df_ev])) * 1e3
 
-    # ---- end to end through the C ABI with host buffers (params in, attachments out) ----
+    # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera,
+    # every output attachment read back to pinned host memory, inside the timed region ----
     host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
     host_np = [h.numpy() for h in host_out]
     d2h = sum(h.nbytes for h in host_np)
-    h2d = 2 * (16 * 4 * 2 + 64)  # the per-pass parameter blocks (matrices + scalars) are the only per-step inputs
+    h2d = sum(ctypes.sizeof(p) for _, _, p in prepared[0])
 
     def e2e_step(s):
-        fr.render(cams[s], frame=frame_of(s))
-        for att, buf in zip(cfg.outputs, host_np):
+        prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s))
+        fr.submit(prep)
+        for att, buf in zip(fr.outputs, host_np):
             ctx.read_attachment(att, buf)
 
     for s in range(min(3, args.warmup)):
@@ -336,7 +410,7 @@ def main():
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
-    e2e_steps = max(3, min(args.steps, 50))
+    e2e_steps = max(3, min(args.steps, 30))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(args.warmup + i)
@@ -349,51 +423,54 @@ def main():
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        r = torch.tensor([total_rays, e2e_rays, launches], device="cuda", dtype=torch.int64)
+        r = torch.tensor([total_rays, e2e_rays, launches, total_iters], device="cuda", dtype=torch.int64)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        total_rays, e2e_rays, launches = int(r[0]), int(r[1]), int(r[2])
+        total_rays, e2e_rays, launches, total_iters = int(r[0]), int(r[1]), int(r[2]), int(r[3])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         mrays = total_rays / (ms * 1e-3) / 1e6
-        # roofline of the dominant kernel (primary trace): algorithmic bytes per ray = S + 1 + W
-        S = pst["iterations"] / max(pst["rays"], 1)
-        rays_per_launch = pst["rays"] / args.steps
-        alg_bytes = rays_per_launch * (S + 1 + 8)
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        sector_bytes = rays_per_launch * (32 * (S + 1) + 8)
+        # roofline of the dominant kernel: algorithmic bytes per launch = rays*(S+1) + output bytes
+        dom = max(trace_passes, key=lambda p: pass_ms[p])
+        st = pass_stats[dom]
+        S = st["iterations"] / max(st["rays"], 1)
+        rays_per_launch = st["rays"] / args.steps
+        out_bytes = PASS_OUTPUT_BYTES[dom] * W * H
+        alg_bytes = rays_per_launch * (S + 1) + out_bytes
+        achieved = alg_bytes / (pass_ms[dom] * 1e-3) / 1e9
+        sector_bytes = rays_per_launch * 32 * (S + 1) + out_bytes
         line = {
             "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "world": world_desc, "width": W, "height": H, "passes": list(cfg.passes),
-                       "rays_per_step_per_gpu": total_rays / args.steps / world_size, "mean_iterations_per_ray": mean_iters,
-                       "sharding": "one frame of the camera path per rank per step; outputs gathered to rank 0 (NCCL)" if world_size > 1 else "single GPU",
+                       "gi_spp": cfg.gi_spp, "reflection_spp": cfg.refl_spp, "texture_size": args.tex_size,
+                       "rays_per_step_per_gpu": total_rays / args.steps / world_size,
+                       "mean_iterations_per_ray": total_iters / max(total_rays, 1),
+                       "sharding": ("one frame of the camera path per rank per step; output attachments gathered to rank 0 (NCCL)"
+                                    if world_size > 1 else "single GPU"),
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); camera pose changes every step"},
             "clocks": clocks,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
             "gpu_launches": launches,
-            "roofline": {"kernel": "initial_trace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "pass_ms": pass_ms,
+            "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},
+            "roofline": {"kernel": PASS_KERNEL[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "mean_iterations_per_ray": S, "rays_per_launch": rays_per_launch, "avg_launch_ms": dom_ms,
-                         "algorithmic_bytes_per_ray": S + 1 + 8, "l2_sector_gbs": sector_bytes / (dom_ms * 1e-3) / 1e9,
-                         "kernel_mrays": rays_per_launch / (dom_ms * 1e-3) / 1e6},
+                         "mean_iterations_per_ray": S, "rays_per_launch": rays_per_launch, "avg_launch_ms": pass_ms[dom],
+                         "algorithmic_bytes_per_launch": alg_bytes, "l2_sector_gbs": sector_bytes / (pass_ms[dom] * 1e-3) / 1e9,
+                         "kernel_mrays": rays_per_launch / (pass_ms[dom] * 1e-3) / 1e6,
+                         "note": "grids are L2 resident: the operative roof is L2/L1 gather latency and issue slots, see DESIGN.md §3"},
         }
         nvox = blocks.size
         line["df_regen"] = {"us_per_regeneration": df_us, "algorithmic_bytes": 2 * nvox,
                             "achieved_gbs": 2 * nvox / (df_us * 1e-6) / 1e9, "frac_of_hbm_peak": 2 * nvox / (df_us * 1e-6) / 1e9 / peak,
                             "l2": "flushed before each regeneration", "launches_per_regeneration": 2}
         if not args.no_cpu_baseline and world_size == 1:
-            run, kind, cores = cpu_frame_runner(blocks, wl)
-            t0 = time.perf_counter(); run(0, rows=(H // 2 - 8, 16)); dt = time.perf_counter() - t0
-            rows = int(min(H, max(16, 16 * 1.0 / max(dt, 1e-4))))
-            band = ((H - rows) // 2, rows)
-            n, rays, t0 = 0, 0, time.perf_counter()
-            while time.perf_counter() - t0 < args.cpu_seconds and n < args.steps:
-                rays += run(args.warmup + n, rows=band); n += 1
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            cpu = cpu_arm(blocks, wl, inputs)
+            v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": f"rows [{band[0]},{band[0] + band[1]}) of {n} frames of the same camera path"}
         else:
             line["cpu_baseline"] = None

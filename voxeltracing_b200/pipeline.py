@@ -23,10 +23,25 @@ class FrameConfig:
     shadow_iterations: int = 350         # ShadowRayTraceFrag.glsl:233
     soft_shadows: bool = True
     sun_tick: float = 50.0               # Pipeline.cpp:67
+    gi_spp: int = 1                      # BASELINE config 4 (engine default 3, Pipeline.cpp:76)
+    gi_checkerboard: bool = False
+    refl_spp: int = 1                    # BASELINE config 4 (engine default 2, Pipeline.cpp:108)
+    refl_reproject: bool = False
     passes: tuple = ("primary", "shadow")
-    # attachments read back by the end-to-end path / gathered to rank 0
-    outputs: tuple = (abi.ATT_INITIAL_T, abi.ATT_INITIAL_NORMAL, abi.ATT_INITIAL_BLOCK, abi.ATT_INITIAL_INVT,
-                      abi.ATT_SHADOW, abi.ATT_SHADOW_TRANSVERSAL)
+
+
+PASS_OUTPUTS = {
+    "primary": (abi.ATT_INITIAL_T, abi.ATT_INITIAL_NORMAL, abi.ATT_INITIAL_BLOCK, abi.ATT_INITIAL_INVT),
+    "gbuffer": (abi.ATT_GBUF_ALBEDO, abi.ATT_GBUF_NORMAL, abi.ATT_GBUF_PBR, abi.ATT_GBUF_TEXAO),
+    "gi": (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY),
+    "shadow": (abi.ATT_SHADOW, abi.ATT_SHADOW_TRANSVERSAL),
+    "reflection": (abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE),
+    "direct": (abi.ATT_DIRECT,),
+}
+# output bytes per ray-tracing pixel: the W of the algorithmic-bytes formula
+PASS_OUTPUT_BYTES = {"primary": 8, "shadow": 3, "gi": 16, "reflection": 11}
+PASS_KERNEL = {"primary": "initial_trace_kernel", "shadow": "shadow_trace_kernel", "gi": "diffuse_trace_kernel",
+               "reflection": "reflection_trace_kernel", "gbuffer": "generate_gbuffer_kernel", "direct": "shade_direct_kernel"}
 
 
 def orbit_camera(frame: int, aspect: float, n_frames: int = 64, radius: float = 120.0, height: float = 90.0,
@@ -40,34 +55,152 @@ def orbit_camera(frame: int, aspect: float, n_frames: int = 64, radius: float = 
     return host_api.camera(pos, yaw, pitch, aspect)
 
 
-class FrameRenderer:
-    """Issues the passes of one frame on a Context.  `tile` = (row0, rows) restricts every pass to a
-    band of rows (screen-tile sharding); (0, 0) renders the whole frame."""
+def rooms_camera(frame: int, aspect: float, dims=(384, 128, 384)) -> host_api.Camera:
+    """Config-4 camera path for the `rooms` stand-in: visits the 6x6 rooms of the building (vxh_gen_rooms:
+    24-voxel cells around the grid centre, floor at ny/2-12), standing at head height in the cell centre and
+    turning 37 degrees per frame."""
+    nx, ny, nz = dims
+    room, floor_y = 24, ny // 2 - 12
+    cell = (frame * 7) % 36
+    rx, rz = cell % 6, cell // 6
+    pos = np.array([nx / 2 - 3 * room + rx * room + 12.5, floor_y + 6.5, nz / 2 - 3 * room + rz * room + 12.5], dtype=np.float32)
+    return host_api.camera(pos, float((frame * 37) % 360), -10.0, aspect)
 
-    def __init__(self, ctx: Context, cfg: FrameConfig):
+
+def _fill(dst, src):
+    for i, v in enumerate(np.asarray(src).ravel()):
+        dst[i] = v.item()
+
+
+class FrameRenderer:
+    """Issues the passes of one frame on a Context in the order of Core/Pipeline.cpp.  `tile` = (row0, rows)
+    restricts every pass to a band of rows (screen-tile sharding); (0, 0) renders the whole frame.
+    `scene` supplies the block-database-derived uniforms (grass / cactus face props)."""
+
+    def __init__(self, ctx: Context, cfg: FrameConfig, grass_props=None, cactus_props=None):
         self.ctx = ctx
         self.cfg = cfg
-        self.light = host_api.sun_direction(cfg.sun_tick)[2]
+        self.sun, self.moon, self.light = host_api.sun_direction(cfg.sun_tick)
+        self.grass = np.zeros(10, np.int32) if grass_props is None else np.asarray(grass_props, np.int32)
+        self.cactus = np.zeros(10, np.int32) if cactus_props is None else np.asarray(cactus_props, np.int32)
+        # Pipeline.cpp:1906
+        self.sun_visibility = float(np.clip(np.float32(self.sun[1]) + np.float32(0.05), 0.0, 0.1) * np.float32(12.0))
 
-    def render(self, cam: host_api.Camera, frame: int = 0, tile=(0, 0), hook=None):
+    @property
+    def outputs(self):
+        out = []
+        for name in self.cfg.passes:
+            out.extend(PASS_OUTPUTS[name])
+        return tuple(out)
+
+    def _gbuffer_params(self, cam, tile):
+        p = abi.GBufferParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = self.cfg.width, self.cfg.height
+        _fill(p.grass_props, self.grass); _fill(p.cactus_props, self.cactus)
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def _direct_params(self, cam, tile):
+        p = abi.DirectParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = self.cfg.width, self.cfg.height
+        _fill(p.viewer_position, cam.position); _fill(p.sun_direction, self.sun); _fill(p.moon_direction, self.moon)
+        c = np.float32(np.pi) * np.float32(2.2) * np.float32(0.85)  # SURVEY §8d config 3: constant sun radiance
+        _fill(p.sun_color, np.array([c, c, c], np.float32)); _fill(p.moon_color, np.array([0.12, 0.14, 0.25], np.float32))
+        p.texture_desat_amount, p.amplify_normal_map = 0.1, 0
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def _gi_params(self, cam, frame, tile):
+        cfg = self.cfg
+        p = abi.GIParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = cfg.width, cfg.height
+        p.spp, p.checker_spp, p.checkerboard = cfg.gi_spp, (cfg.gi_spp + cfg.gi_spp % 2) // 2, int(cfg.gi_checkerboard)
+        p.trace_length, p.shadow_trace_length = 48, 128           # Pipeline.cpp:78, DiffuseRayTraceFrag.glsl:1306
+        p.current_frame, p.current_frame_mod128 = frame, frame % 128
+        p.use_blue_noise, p.supersample = 1, 0
+        _fill(p.sun_direction, self.sun); _fill(p.moon_direction, self.moon)
+        p.sun_visibility, p.gi_sun_strength, p.gi_sky_strength, p.diffuse_light_intensity = self.sun_visibility, 1.0, 1.125, 1.25
+        _fill(p.viewer_position, cam.position)
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def _reflection_params(self, cam, frame, tile):
+        cfg = self.cfg
+        p = abi.ReflectionParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        _fill(p.view, cam.view); _fill(p.projection, cam.projection)
+        p.width, p.height = cfg.width, cfg.height
+        p.spp, p.checkerboard, p.trace_length, p.shadow_trace_length = cfg.refl_spp, 0, 64, 150   # Pipeline.cpp:105
+        p.current_frame, p.current_frame_mod128 = frame, frame % 128
+        p.use_blue_noise, p.rough_reflections, p.roughness_bias, p.temporal = 1, 1, 0, 0
+        p.reproject_to_screen_space, p.derive_from_diffuse_sh = int(cfg.refl_reproject), 0
+        _fill(p.sun_direction, self.sun); _fill(p.moon_direction, self.moon); _fill(p.stronger_light_direction, self.light)
+        _fill(p.viewer_position, cam.position)
+        p.sun_strength_modifier, p.moon_strength_modifier = 0.85, 1.0
+        _fill(p.grass_props, self.grass)
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def _primary_params(self, cam, tile):
+        p = abi.PrimaryParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height, p.render_distance = self.cfg.width, self.cfg.height, self.cfg.render_distance
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def _shadow_params(self, cam, frame, tile):
+        p = abi.ShadowParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height = self.cfg.width, self.cfg.height
+        _fill(p.light_direction, self.light)
+        p.current_frame, p.soft_shadows, p.max_iterations = frame, int(self.cfg.soft_shadows), self.cfg.shadow_iterations
+        p.tile.row0, p.tile.rows = tile
+        return p
+
+    def params_for(self, name: str, cam, frame: int = 0, tile=(0, 0)):
+        """The parameter block of pass `name` (the uniform set the reference uploads before the draw)."""
+        if name == "primary":
+            return self._primary_params(cam, tile)
+        if name == "gbuffer":
+            return self._gbuffer_params(cam, tile)
+        if name == "gi":
+            return self._gi_params(cam, frame, tile)
+        if name == "shadow":
+            return self._shadow_params(cam, frame, tile)
+        if name == "reflection":
+            return self._reflection_params(cam, frame, tile)
+        if name == "direct":
+            return self._direct_params(cam, tile)
+        raise ValueError(f"unknown pass {name!r}")
+
+    def prepare(self, cam: host_api.Camera, frame: int = 0, tile=(0, 0)):
+        """Marshal the parameter blocks of a frame once; `submit` then only makes the C-ABI calls."""
+        lib, h = self.ctx._lib, self.ctx._h
+        fns = {"primary": lib.vxrt_cuda_initial_trace, "gbuffer": lib.vxrt_cuda_generate_gbuffer, "gi": lib.vxrt_cuda_diffuse_trace,
+               "shadow": lib.vxrt_cuda_shadow_trace, "reflection": lib.vxrt_cuda_reflection_trace, "direct": lib.vxrt_cuda_shade_direct}
+        return [(name, fns[name], self.params_for(name, cam, frame, tile)) for name in self.cfg.passes]
+
+    def submit(self, prepared, hook=None):
         """hook(name, 'begin'|'end') lets the bench bracket individual passes with CUDA events."""
-        c, cfg = self.ctx, self.cfg
-        for name in cfg.passes:
+        import ctypes as C
+
+        h = self.ctx._h
+        for name, fn, params in prepared:
             if hook:
                 hook(name, "begin")
-            if name == "primary":
-                c.initial_trace(cam, cfg.width, cfg.height, cfg.render_distance, tile=tile)
-            elif name == "shadow":
-                c.shadow_trace(cam, cfg.width, cfg.height, self.light, frame=frame, soft=cfg.soft_shadows,
-                               max_iterations=cfg.shadow_iterations, tile=tile)
-            else:
-                raise ValueError(f"unknown pass {name!r}")
+            self.ctx._check(fn(h, C.byref(params)))
             if hook:
                 hook(name, "end")
 
+    def render(self, cam: host_api.Camera, frame: int = 0, tile=(0, 0), hook=None):
+        self.submit(self.prepare(cam, frame, tile), hook)
+
     def output_bytes(self) -> int:
         total = 0
-        for att in self.cfg.outputs:
+        for att in self.outputs:
             _, w, h, bpp = self.ctx.attachment_info(att)
             total += w * h * bpp
         return total
