@@ -69,6 +69,25 @@ int vxrt_cuda_download_distance_field(vxrt_ctx* ctx, uint8_t* df_out);
 /* test hook: overwrite the distance field (lets tests feed an oracle-made field to the tracers). */
 int vxrt_cuda_upload_distance_field(vxrt_ctx* ctx, const uint8_t* df);
 
+/* ---- multi-GPU z-slab distance field (new, the reference is single-GPU) ----
+ * The grid is replicated; rank s owns planes [slab_z0[s], slab_z0[s+1]).
+ *   phase A: X and Y sweeps plus slab-local Z sweeps on the rank's planes.
+ *   exchange (caller, NCCL): all-gather every rank's first and last plane (nx*ny bytes each), obtained
+ *            with vxrt_cuda_df_plane_device().
+ *   phase B: apply the carries of the other slabs from the gathered planes (device pointers to nslabs
+ *            consecutive planes each).
+ *   the caller then all-gathers the slabs through vxrt_cuda_grid_device() and calls vxrt_cuda_df_commit().
+ * nslabs <= 64.                                                                                     */
+int vxrt_cuda_df_slab_phase_a(vxrt_ctx* ctx, int32_t slab, int32_t nslabs, const int32_t* slab_z0 /*nslabs+1*/);
+int vxrt_cuda_df_slab_phase_b(vxrt_ctx* ctx, int32_t slab, int32_t nslabs, const int32_t* slab_z0,
+                              const void* dev_first_planes, const void* dev_last_planes);
+/* device pointer to plane z of the distance field (nx*ny bytes) */
+int vxrt_cuda_df_plane_device(vxrt_ctx* ctx, int32_t z, void** dev_ptr);
+/* device pointers to the block grid and the distance field (nx*ny*nz bytes each) */
+int vxrt_cuda_grid_device(vxrt_ctx* ctx, void** dev_blocks, void** dev_df);
+/* declare the distance field valid after it was completed through device pointers (slab all-gather) */
+int vxrt_cuda_df_commit(vxrt_ctx* ctx);
+
 /* ---- tables ---- */
 /* BlockDataSSBO::CreateBuffers (Core/BlockDataSSBO.cpp:5-40): 6 x int[128] =
  * albedo, normal, pbr, emissive layer ids, transparent flag, sss flag.                      */

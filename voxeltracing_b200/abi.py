@@ -142,6 +142,11 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_generate_distance_field": (C.c_int, [vp]),
         "vxrt_cuda_download_distance_field": (C.c_int, [vp, vp]),
         "vxrt_cuda_upload_distance_field": (C.c_int, [vp, vp]),
+        "vxrt_cuda_df_slab_phase_a": (C.c_int, [vp, i32, i32, P(i32)]),
+        "vxrt_cuda_df_slab_phase_b": (C.c_int, [vp, i32, i32, P(i32), vp, vp]),
+        "vxrt_cuda_df_plane_device": (C.c_int, [vp, i32, P(vp)]),
+        "vxrt_cuda_grid_device": (C.c_int, [vp, P(vp), P(vp)]),
+        "vxrt_cuda_df_commit": (C.c_int, [vp]),
         "vxrt_cuda_set_block_data": (C.c_int, [vp, vp]),
         "vxrt_cuda_set_blue_noise": (C.c_int, [vp, vp, i32]),
         "vxrt_cuda_set_blue_noise_texture": (C.c_int, [vp, vp, i32, i32]),

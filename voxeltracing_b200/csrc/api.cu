@@ -89,7 +89,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
-    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky);
+    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i) cudaFree(c->att[i].ptr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -195,6 +195,52 @@ int vxrt_cuda_upload_distance_field(vxrt_ctx* c, const uint8_t* df) {
     REQUIRE_CTX(c); REQUIRE_PTR(df);
     VX_CUDA(cudaMemcpyAsync(c->d_df, df, c->nvox, cudaMemcpyHostToDevice, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->df_valid = true;
+    return VXRT_OK;
+}
+
+static int check_slabs(vxrt_ctx* c, const char* fn, int32_t slab, int32_t nslabs, const int32_t* z0) {
+    if (!z0) return vxrt_fail(VXRT_E_INVALID, "%s: slab_z0 is NULL", fn);
+    if (nslabs < 1 || nslabs > 64 || slab < 0 || slab >= nslabs) return vxrt_fail(VXRT_E_INVALID, "%s: bad slab %d of %d", fn, slab, nslabs);
+    if (z0[0] != 0 || z0[nslabs] != c->nz) return vxrt_fail(VXRT_E_INVALID, "%s: slabs must cover [0, %d)", fn, c->nz);
+    for (int i = 0; i < nslabs; ++i)
+        if (z0[i + 1] <= z0[i]) return vxrt_fail(VXRT_E_INVALID, "%s: slab %d is empty", fn, i);
+    return VXRT_OK;
+}
+int vxrt_cuda_df_slab_phase_a(vxrt_ctx* c, int32_t slab, int32_t nslabs, const int32_t* z0) {
+    REQUIRE_CTX(c);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "df_slab_phase_a before upload_world");
+    int rc = check_slabs(c, __func__, slab, nslabs, z0);
+    if (rc) return rc;
+    c->df_valid = false;
+    return vxrt_launch_df_slab_phase_a(c, z0[slab], z0[slab + 1]);
+}
+int vxrt_cuda_df_slab_phase_b(vxrt_ctx* c, int32_t slab, int32_t nslabs, const int32_t* z0, const void* first_planes, const void* last_planes) {
+    REQUIRE_CTX(c); REQUIRE_PTR(first_planes); REQUIRE_PTR(last_planes);
+    int rc = check_slabs(c, __func__, slab, nslabs, z0);
+    if (rc) return rc;
+    if (!c->d_slab_z0) VX_CUDA(cudaMalloc(&c->d_slab_z0, 65 * sizeof(int32_t)));
+    VX_CUDA(cudaMemcpyAsync(c->d_slab_z0, z0, (size_t)(nslabs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    rc = vxrt_launch_df_slab_phase_b(c, slab, nslabs, c->d_slab_z0, z0[slab], z0[slab + 1], first_planes, last_planes);
+    if (rc) return rc;
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // slab_z0 is borrowed
+    return VXRT_OK;
+}
+int vxrt_cuda_df_plane_device(vxrt_ctx* c, int32_t z, void** p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    if (z < 0 || z >= c->nz) return vxrt_fail(VXRT_E_INVALID, "df_plane_device: plane %d out of range", z);
+    *p = c->d_df + (size_t)z * c->nx * c->ny;
+    return VXRT_OK;
+}
+int vxrt_cuda_grid_device(vxrt_ctx* c, void** blocks, void** df) {
+    REQUIRE_CTX(c);
+    if (blocks) *blocks = c->d_blocks;
+    if (df) *df = c->d_df;
+    return VXRT_OK;
+}
+int vxrt_cuda_df_commit(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "df_commit before upload_world");
     c->df_valid = true;
     return VXRT_OK;
 }

@@ -70,6 +70,8 @@ struct vxrt_ctx {
     TexCubeDev sky = {nullptr, 0};
     std::vector<float> h_sky;  // host copy: per-frame sun / moon colours are evaluated on the host
 
+    int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)
+
     int32_t* d_edit_buf = nullptr;
     size_t edit_cap = 0;
 
@@ -97,6 +99,9 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
 // kernel launchers (one per .cu)
 int vxrt_launch_distance_field(vxrt_ctx* c);
 int vxrt_launch_edit_blocks(vxrt_ctx* c, const int32_t* d_edits, int n);
+int vxrt_launch_df_slab_phase_a(vxrt_ctx* c, int z0, int z1);
+int vxrt_launch_df_slab_phase_b(vxrt_ctx* c, int slab, int nslabs, const int* d_slab_z0, int z0, int z1, const void* first_planes,
+                                const void* last_planes);
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
 int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);

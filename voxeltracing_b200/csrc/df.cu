@@ -166,6 +166,35 @@ __global__ void __launch_bounds__(128) df_z_columns_kernel(uint8_t* __restrict__
     }
 }
 
+// ---- z-slab sharding (multi-GPU regeneration) -------------------------------------
+// After the slab-local sweeps every rank holds L[z] = min over its own planes z' of xy[z'] + |z - z'|.
+// With B_t = L on the last plane of slab t and F_t = L on the first plane of slab t (all-gathered, one
+// nx*ny plane each), the global transform on slab s is
+//   D[z] = min( L[z],  min_{t<s} B_t + (z - (z1_t - 1)),  min_{t>s} F_t + (z0_t - z) ),  clamped to 254.
+__global__ void __launch_bounds__(256) df_slab_apply_kernel(uint8_t* __restrict__ df, int words_per_plane, int slab, int nslabs,
+                                                            const int* __restrict__ slab_z0, const uint8_t* __restrict__ first_planes,
+                                                            const uint8_t* __restrict__ last_planes) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z0 = slab_z0[slab], z1 = slab_z0[slab + 1];
+    const int z = z0 + blockIdx.y;
+    if (col >= words_per_plane || z >= z1) return;
+    const unsigned* F = reinterpret_cast<const unsigned*>(first_planes);
+    const unsigned* B = reinterpret_cast<const unsigned*>(last_planes);
+    unsigned* p = reinterpret_cast<unsigned*>(df) + (size_t)z * words_per_plane + col;
+    const unsigned w = *p;
+    unsigned e = even_lanes(w), o = odd_lanes(w);
+    for (int t = 0; t < nslabs; ++t) {
+        if (t == slab) continue;
+        unsigned add, src;
+        if (t < slab) { src = B[(size_t)t * words_per_plane + col]; add = (unsigned)(z - (slab_z0[t + 1] - 1)); }
+        else { src = F[(size_t)t * words_per_plane + col]; add = (unsigned)(slab_z0[t] - z); }
+        const unsigned add2 = add | (add << 16);  // add <= 1023, lanes hold <= 254: no carry between the u16 lanes
+        e = __viaddmin_u16x2(even_lanes(src), add2, e);
+        o = __viaddmin_u16x2(odd_lanes(src), add2, o);
+    }
+    *p = pack_lanes(e, o);  // e, o <= their previous value <= 254
+}
+
 // glTexSubImage3D single-voxel edits (Core/World.cpp:372-373, 458-459)
 __global__ void edit_blocks_kernel(uint8_t* __restrict__ blocks, const int32_t* __restrict__ e, int n, int nx,
                                    int ny) {
@@ -177,22 +206,57 @@ __global__ void edit_blocks_kernel(uint8_t* __restrict__ blocks, const int32_t* 
 
 }  // namespace
 
-int vxrt_launch_distance_field(vxrt_ctx* c) {
-    const int nx = c->nx, ny = c->ny, nz = c->nz;
-    const unsigned maxd = (unsigned)((nx + ny + nz) < 254 ? (nx + ny + nz) : 254);
-    const int stride = (nx >> 2) | 1;
-    const size_t smem = (size_t)ny * stride * sizeof(unsigned);
+static int set_xy_smem_attr() {
     static bool attr_set = false;
     if (!attr_set) {
         VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
+    return VXRT_OK;
+}
+
+int vxrt_launch_distance_field(vxrt_ctx* c) {
+    const int nx = c->nx, ny = c->ny, nz = c->nz;
+    const unsigned maxd = (unsigned)((nx + ny + nz) < 254 ? (nx + ny + nz) : 254);
+    const int stride = (nx >> 2) | 1;
+    const size_t smem = (size_t)ny * stride * sizeof(unsigned);
+    int rc = set_xy_smem_attr();
+    if (rc) return rc;
     df_xy_slice_kernel<<<nz, 128, smem, c->stream>>>(c->d_blocks, c->d_df, nx, ny, 0, maxd);
     VX_CUDA(cudaGetLastError());
     const int wpp = (nx * ny) >> 2;
     df_z_columns_kernel<<<(wpp + 127) / 128, 128, 0, c->stream>>>(c->d_df, wpp, 0, nz);
     VX_CUDA(cudaGetLastError());
     c->launches += 2;
+    return VXRT_OK;
+}
+
+// phase A of the sharded regeneration: X, Y and slab-local Z sweeps on planes [z0, z1)
+int vxrt_launch_df_slab_phase_a(vxrt_ctx* c, int z0, int z1) {
+    const int nx = c->nx, ny = c->ny, nz = c->nz;
+    const unsigned maxd = (unsigned)((nx + ny + nz) < 254 ? (nx + ny + nz) : 254);
+    const int stride = (nx >> 2) | 1;
+    const size_t smem = (size_t)ny * stride * sizeof(unsigned);
+    int rc = set_xy_smem_attr();
+    if (rc) return rc;
+    df_xy_slice_kernel<<<z1 - z0, 128, smem, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd);
+    VX_CUDA(cudaGetLastError());
+    const int wpp = (nx * ny) >> 2;
+    df_z_columns_kernel<<<(wpp + 127) / 128, 128, 0, c->stream>>>(c->d_df, wpp, z0, z1);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 2;
+    return VXRT_OK;
+}
+
+// phase B: apply the carries of the other slabs (boundary planes are device pointers, nslabs planes each)
+int vxrt_launch_df_slab_phase_b(vxrt_ctx* c, int slab, int nslabs, const int* d_slab_z0, int z0, int z1, const void* first_planes,
+                                const void* last_planes) {
+    const int wpp = (c->nx * c->ny) >> 2;
+    dim3 grid((wpp + 255) / 256, z1 - z0);
+    df_slab_apply_kernel<<<grid, 256, 0, c->stream>>>(c->d_df, wpp, slab, nslabs, d_slab_z0, (const uint8_t*)first_planes,
+                                                      (const uint8_t*)last_planes);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
     return VXRT_OK;
 }
 

@@ -134,6 +134,26 @@ class Context:
             raise ValueError("distance field size mismatch")
         self._check(self._lib.vxrt_cuda_upload_distance_field(self._h, _p(d)))
 
+    # -- z-slab sharded regeneration (multi-GPU; see voxeltracing_b200/sharding.py) --
+    def df_slab_phase_a(self, slab: int, slab_z0):
+        z = (C.c_int32 * len(slab_z0))(*[int(v) for v in slab_z0])
+        self._check(self._lib.vxrt_cuda_df_slab_phase_a(self._h, slab, len(slab_z0) - 1, z))
+
+    def df_slab_phase_b(self, slab: int, slab_z0, first_planes_ptr: int, last_planes_ptr: int):
+        z = (C.c_int32 * len(slab_z0))(*[int(v) for v in slab_z0])
+        self._check(self._lib.vxrt_cuda_df_slab_phase_b(self._h, slab, len(slab_z0) - 1, z, C.c_void_p(first_planes_ptr),
+                                                        C.c_void_p(last_planes_ptr)))
+
+    def df_commit(self):
+        self._check(self._lib.vxrt_cuda_df_commit(self._h))
+
+    def df_device_array(self):
+        """Zero-copy [nz, ny, nx] uint8 view of the distance field for torch.as_tensor (NCCL all-gather of slabs)."""
+        blocks, df = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.vxrt_cuda_grid_device(self._h, C.byref(blocks), C.byref(df)))
+        nx, ny, nz = self.dims
+        return _DeviceArray(df.value, (nz, ny, nx), "|u1")
+
     # -- tables --
     def set_block_data(self, table: np.ndarray):
         t = np.ascontiguousarray(table, dtype=np.int32)
