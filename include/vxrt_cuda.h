@@ -143,6 +143,13 @@ int vxrt_cuda_read_attachment(vxrt_ctx* ctx, int32_t attachment, void* host_dst,
 int vxrt_cuda_attachment_device(vxrt_ctx* ctx, int32_t attachment, void** dev_ptr, int32_t* width,
                                 int32_t* height, int32_t* bytes_per_pixel);
 
+/* Bind caller-owned device memory as the storage of an attachment — the analogue of attaching a texture
+ * to an FBO; lets a caller ping-pong output sets like InitialTraceFBO_1 / _2 (Core/Pipeline.cpp:2046-2048)
+ * or render straight into a communication buffer.  `capacity` bytes must cover width*height*bpp of the
+ * pass that writes it.  dev_ptr == NULL restores context-owned storage.  Rebinding keeps the geometry, so
+ * later passes of the frame can consume a set rendered earlier.                                        */
+int vxrt_cuda_bind_attachment(vxrt_ctx* ctx, int32_t attachment, void* dev_ptr, size_t capacity);
+
 /* Screen-tile sharding: a pass only shades rows [row0, row0+rows) of the frame;
  * rows == 0 means the whole frame.  Attachments always have full-frame geometry.             */
 typedef struct vxrt_tile {

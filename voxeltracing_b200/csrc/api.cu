@@ -33,6 +33,8 @@ int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
     if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "bad attachment size %dx%d", w, h);
     Attachment& a = c->att[id];
     size_t need = (size_t)w * h * bpp;
+    if (need > a.capacity && a.external)
+        return vxrt_fail(VXRT_E_INVALID, "attachment %d: bound storage holds %zu bytes, the pass needs %zu", id, a.capacity, need);
     if (need > a.capacity) {
         if (a.ptr) VX_CUDA(cudaFree(a.ptr));
         a.ptr = nullptr;
@@ -91,7 +93,8 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
-    for (int i = 0; i < VXRT_ATT_COUNT; ++i) cudaFree(c->att[i].ptr);
+    for (int i = 0; i < VXRT_ATT_COUNT; ++i)
+        if (!c->att[i].external) cudaFree(c->att[i].ptr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return VXRT_OK;
@@ -280,6 +283,19 @@ int vxrt_cuda_read_attachment(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) 
     if (bytes != have) return vxrt_fail(VXRT_E_INVALID, "attachment %d holds %zu bytes, caller asked for %zu", id, have, bytes);
     VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+int vxrt_cuda_bind_attachment(vxrt_ctx* c, int32_t id, void* dev_ptr, size_t capacity) {
+    REQUIRE_CTX(c);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    Attachment& a = c->att[id];
+    if (a.ptr && !a.external) VX_CUDA(cudaFree(a.ptr));
+    if (dev_ptr) {
+        if (capacity == 0) return vxrt_fail(VXRT_E_INVALID, "bind_attachment: capacity is 0");
+        a.ptr = dev_ptr; a.capacity = capacity; a.external = true;
+    } else {
+        a.ptr = nullptr; a.capacity = 0; a.external = false; a.width = a.height = a.bpp = 0;
+    }
     return VXRT_OK;
 }
 int vxrt_cuda_attachment_device(vxrt_ctx* c, int32_t id, void** p, int32_t* w, int32_t* h, int32_t* bpp) {

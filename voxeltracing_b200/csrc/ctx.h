@@ -23,6 +23,7 @@ struct Attachment {
     void* ptr = nullptr;
     size_t capacity = 0;  // bytes allocated
     int width = 0, height = 0, bpp = 0;
+    bool external = false;  // storage bound by the caller (vxrt_cuda_bind_attachment), never freed here
 };
 
 // device view of one block texture array (see texture.cuh)

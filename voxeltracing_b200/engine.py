@@ -230,6 +230,10 @@ class Context:
         self._check(self._lib.vxrt_cuda_attachment_device(self._h, att, C.byref(ptr), C.byref(w), C.byref(h), C.byref(bpp)))
         return ptr.value, w.value, h.value, bpp.value
 
+    def bind_attachment(self, att: int, dev_ptr: int | None, capacity: int = 0):
+        """Use caller-owned device memory for an attachment (None restores context-owned storage)."""
+        self._check(self._lib.vxrt_cuda_bind_attachment(self._h, att, C.c_void_p(dev_ptr or 0), capacity))
+
     def read_attachment(self, att: int, out: np.ndarray | None = None) -> np.ndarray:
         _, w, h, bpp = self.attachment_info(att)
         dt, ch = _ATT_DTYPES[att]

@@ -28,6 +28,9 @@ def gather_bands(full: torch.Tensor, height: int, rank: int, world: int, dst: in
     After the call rank `dst` holds every band (rows are contiguous in memory, so the receives land in place)."""
     if world == 1:
         return full
+    result = full
+    if full.dtype not in (torch.uint8, torch.float32, torch.float16, torch.int32):
+        full = full.view(torch.uint8)  # NCCL moves bytes; not every dtype (e.g. int16) is accepted
     ops = []
     if rank == dst:
         for r in range(world):
@@ -43,7 +46,7 @@ def gather_bands(full: torch.Tensor, height: int, rank: int, world: int, dst: in
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-    return full
+    return result
 
 
 class CudaSlabBackend:
