@@ -53,6 +53,10 @@ const char* vxrt_cuda_last_error(void);
 /* run all subsequent work of this ctx on an existing cudaStream_t (NULL = ctx-owned stream). */
 int vxrt_cuda_set_stream(vxrt_ctx* ctx, void* cuda_stream);
 int vxrt_cuda_synchronize(vxrt_ctx* ctx);
+/* implementation options (no reference counterpart).  "wavefront" = 1 (default; env VXRT_WAVEFRONT) runs
+ * the GI / reflection passes as wavefront pipelines (compacted ray queues, one kernel per phase); 0 runs
+ * the one-thread-per-pixel kernels.  Both produce bit-identical attachments.                          */
+int vxrt_cuda_set_option(vxrt_ctx* ctx, const char* name, int32_t value);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches"). */
 int64_t vxrt_cuda_launch_count(vxrt_ctx* ctx);
 

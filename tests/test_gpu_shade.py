@@ -183,3 +183,25 @@ def test_pass_order_errors(inputs):
     c.generate_gbuffer(su.gbuffer_params(cam, W, H, inputs))
     c.diffuse_trace(su.gi_params(cam, W, H))
     c.close()
+
+
+@pytest.mark.parametrize("world,pos,frame,spp,checker", [("rooms", [200, 58, 200], 4, 3, True), ("plains", [192, 80, 192], 1, 2, False)])
+def test_wavefront_gi_is_bit_identical_to_the_per_pixel_kernel(request, inputs, world, pos, frame, spp, checker):
+    c, ow, sc = request.getfixturevalue(world)
+    cam = host_api.camera(pos, 75.0, -12.0, W / H)
+    c.initial_trace(cam, W, H)
+    ip = su.gi_params(cam, W, H, frame=frame, spp=spp, checkerboard=checker)
+    atts = (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY)
+    res = {}
+    for mode in (0, 1):
+        c.set_option("wavefront", mode)
+        c.stats_enable(True); c.stats_read(True)
+        c.diffuse_trace(ip)
+        res[mode] = ([c.read_attachment(a).copy() for a in atts], c.stats_read(True))
+        c.stats_enable(False)
+    c.set_option("wavefront", 1)
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert res[0][1] == res[1][1]   # same rays, iterations, DDA steps, hits
+    with pytest.raises(engine.VxrtError):
+        c.set_option("no-such-option", 1)

@@ -135,6 +135,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_last_error": (C.c_char_p, []),
         "vxrt_cuda_set_stream": (C.c_int, [vp, vp]),
         "vxrt_cuda_synchronize": (C.c_int, [vp]),
+        "vxrt_cuda_set_option": (C.c_int, [vp, C.c_char_p, i32]),
         "vxrt_cuda_launch_count": (i64, [vp]),
         "vxrt_cuda_upload_world": (C.c_int, [vp, vp]),
         "vxrt_cuda_download_world": (C.c_int, [vp, vp]),

@@ -2,6 +2,7 @@
 // every entry point validates its arguments and returns a vxrt_status.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -69,6 +70,7 @@ int vxrt_cuda_create(vxrt_ctx** out, int device, const int32_t* dims) {
     vxrt_ctx* c = new (std::nothrow) vxrt_ctx();
     if (!c) return vxrt_fail(VXRT_E_NOMEM, "out of host memory");
     c->device = device;
+    if (const char* e = getenv("VXRT_WAVEFRONT")) c->wavefront = atoi(e) != 0;
     c->nx = nx; c->ny = ny; c->nz = nz;
     c->nvox = (size_t)nx * ny * nz;
     cudaDeviceProp prop;
@@ -91,7 +93,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
-    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0);
+    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
@@ -110,6 +112,11 @@ int vxrt_cuda_synchronize(vxrt_ctx* c) {
     REQUIRE_CTX(c);
     VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
+}
+int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
+    REQUIRE_CTX(c); REQUIRE_PTR(name);
+    if (!strcmp(name, "wavefront")) { c->wavefront = value != 0; return VXRT_OK; }
+    return vxrt_fail(VXRT_E_INVALID, "unknown option '%s'", name);
 }
 int64_t vxrt_cuda_launch_count(vxrt_ctx* c) { return c ? c->launches : -1; }
 

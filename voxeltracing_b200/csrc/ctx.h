@@ -71,6 +71,11 @@ struct vxrt_ctx {
     TexCubeDev sky = {nullptr, 0};
     std::vector<float> h_sky;  // host copy: per-frame sun / moon colours are evaluated on the host
 
+    // wavefront path-state arena (gi_wavefront.cu, reflect_wavefront.cu) and pipeline selection
+    void* d_wf = nullptr;
+    size_t wf_cap = 0;
+    bool wavefront = true;  // VXRT_WAVEFRONT=0 selects the one-thread-per-pixel GI / reflection kernels
+
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)
 
     int32_t* d_edit_buf = nullptr;
@@ -112,6 +117,7 @@ int vxrt_launch_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params& p);
 int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p);
 int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p);
 int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p);
+int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 // host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)
 void vxrt_host_sky_sample(const vxrt_ctx* c, const float dir[3], float rgb[3]);
 // SampleSunColor() / SampleMoonColor() of the GI / reflection shaders, evaluated once per pass on the host

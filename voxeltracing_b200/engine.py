@@ -91,6 +91,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.vxrt_cuda_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.vxrt_cuda_set_option(self._h, name.encode(), int(value)))
+
     def synchronize(self):
         self._check(self._lib.vxrt_cuda_synchronize(self._h))
 
