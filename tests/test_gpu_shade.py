@@ -205,3 +205,30 @@ def test_wavefront_gi_is_bit_identical_to_the_per_pixel_kernel(request, inputs, 
     assert res[0][1] == res[1][1]   # same rays, iterations, DDA steps, hits
     with pytest.raises(engine.VxrtError):
         c.set_option("no-such-option", 1)
+
+
+@pytest.mark.parametrize("world,pos,kw", [("rooms", [200, 58, 200], dict(frame=9, spp=5, reproject=True, temporal=True)),
+                                         ("plains", [192, 80, 192], dict(frame=2, spp=2)), ("rooms", [150.5, 60.2, 221.3], dict(frame=0, spp=1))])
+def test_wavefront_reflections_are_bit_identical_to_the_per_pixel_kernel(request, inputs, world, pos, kw):
+    c, ow, sc = request.getfixturevalue(world)
+    cam = host_api.camera(pos, 110.0, -8.0, W / H)
+    c.initial_trace(cam, W, H)
+    c.shadow_trace(cam, W, H, host_api.sun_direction(50.0)[2], soft=False)
+    c.generate_gbuffer(su.gbuffer_params(cam, W, H, inputs))
+    c.diffuse_trace(su.gi_params(cam, W, H, frame=kw["frame"], spp=1))
+    rp = su.reflection_params(cam, W, H, inputs=inputs, **kw)
+    if kw["spp"] == 5:
+        rp.checkerboard = 1
+        rp.derive_from_diffuse_sh = 1
+    atts = (abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE)
+    res = {}
+    for mode in (0, 1):
+        c.set_option("wavefront", mode)
+        c.stats_enable(True); c.stats_read(True)
+        c.reflection_trace(rp)
+        res[mode] = ([c.read_attachment(a).copy() for a in atts], c.stats_read(True))
+        c.stats_enable(False)
+    c.set_option("wavefront", 1)
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert res[0][1] == res[1][1]

@@ -118,6 +118,7 @@ int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p);
 int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p);
 int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
+int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);
 // host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)
 void vxrt_host_sky_sample(const vxrt_ctx* c, const float dir[3], float rgb[3]);
 // SampleSunColor() / SampleMoonColor() of the GI / reflection shaders, evaluated once per pass on the host

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) gi_wf_gen_kernel(const __grid_constant__ 
             reinterpret_cast<uchar2*>(a.aosky)[pi] = make_uchar2(float_to_unorm8(1.0f), float_to_unorm8(0.0f));
             w.bl[i] = -1;
             w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            w.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // no path: the arena may hold a stale flag
             return;
         }
         int SPP = iclamp(a.spp, 1, 32);
