@@ -287,6 +287,24 @@ typedef struct vxrt_reflection_params {
 } vxrt_reflection_params;
 int vxrt_cuda_reflection_trace(vxrt_ctx* ctx, const vxrt_reflection_params* p);
 
+/* ---- VoxelTraversalDF as a function: a batch of arbitrary rays --------------------------------------------
+ * Replaces a direct call of VoxelTraversalDF(origin, direction, normal, block, iterations)
+ * (InitialRayTraceFrag.glsl:307-374 and its clones ShadowRayTraceFrag.glsl:222-289,
+ * DiffuseRayTraceFrag.glsl:1129-1196, ReflectionTraceFrag.glsl:1088-1155, PostProcessingVert.glsl:103-170) for
+ * callers that hold their own rays (picking, probes, the lens-flare visibility ray).  origins / directions:
+ * 3*n floats each, HOST memory, borrowed for the call; hits: n records, HOST memory.  Directions are used
+ * as given (the shaders pass unit vectors). */
+typedef struct vxrt_ray_hit {
+    float t;              /* return value: distance(end, origin) or -1 */
+    float normal[3];      /* face normal, valid when intersection != 0 */
+    float end[3];         /* final ray position */
+    int32_t block;        /* block id at the end position, 0 if none */
+    int32_t intersection; /* the sticky Intersection flag */
+    int32_t iterations;   /* loop iterations executed (distance-field fetches) */
+} vxrt_ray_hit;
+int vxrt_cuda_trace_rays(vxrt_ctx* ctx, const float* origins, const float* directions, int32_t n, int32_t max_iterations,
+                         vxrt_ray_hit* hits);
+
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {
     uint64_t rays;        /* VoxelTraversalDF invocations */

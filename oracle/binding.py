@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
     L.vxo_step_table.argtypes = [vp]
     L.vxo_traverse.argtypes = [P(World), vp, vp, i32, P(Hit)]
     L.vxo_traverse.restype = C.c_float
+    L.vxo_traverse_batch.argtypes = [P(World), vp, vp, i32, i32, vp]
+    L.vxo_traverse_batch.restype = None
     L.vxo_plain_dda.argtypes = [P(World), vp, vp, i32, vp]
     L.vxo_plain_dda.restype = i32
     L.vxo_initial_trace.argtypes = [P(World), P(abi.PrimaryParams), vp, vp, vp, vp, vp, P(abi.TraceStats)]
@@ -105,6 +107,18 @@ class OracleWorld:
         h = Hit()
         lib().vxo_traverse(C.byref(self.c), _p(o), _p(d), max_iter, C.byref(h))
         return h
+
+    HIT_DTYPE = np.dtype([("t", "<f4"), ("normal", "<f4", 3), ("end", "<f4", 3), ("block", "<i4"), ("intersection", "<i4"),
+                          ("min_idx", "<i4"), ("iterations", "<i4"), ("dda_steps", "<i4")])
+
+    def traverse_batch(self, origins, directions, max_iter: int = 350) -> np.ndarray:
+        """vxo_traverse over (n,3) float32 origins / directions; returns a structured array (HIT_DTYPE)."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        assert o.shape == d.shape and self.HIT_DTYPE.itemsize == C.sizeof(Hit)
+        hits = np.zeros(len(o), dtype=self.HIT_DTYPE)
+        lib().vxo_traverse_batch(C.byref(self.c), _p(o), _p(d), len(o), max_iter, _p(hits))
+        return hits
 
     def plain_dda(self, origin, direction, max_steps: int = 2000):
         o = np.asarray(origin, dtype=np.float32)

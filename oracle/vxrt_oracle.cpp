@@ -228,6 +228,13 @@ extern "C" float vxo_traverse(const vxo_world* w, const float origin0[3], const 
     return t;
 }
 
+/* vxo_traverse over n rays (origins / dirs: 3*n floats), scanline-parallel like the passes */
+extern "C" void vxo_traverse_batch(const vxo_world* w, const float* origins, const float* dirs, int32_t n, int32_t max_iter,
+                                   vxo_hit* hits) {
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int32_t i = 0; i < n; ++i) vxo_traverse(w, origins + 3 * (size_t)i, dirs + 3 * (size_t)i, max_iter, hits + i);
+}
+
 /* Plain Amanatides–Woo grid walk (the style of Shaders/Implementations/DDA/DDA.glsl:134-253),
  * double precision, used only as an independent cross-check of vxo_traverse.                  */
 extern "C" int32_t vxo_plain_dda(const vxo_world* w, const float o[3], const float d[3], int32_t max_steps,

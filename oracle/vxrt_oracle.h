@@ -57,6 +57,7 @@ typedef struct vxo_hit {
 /* VoxelTraversalDF (InitialRayTraceFrag.glsl:307-374) */
 float vxo_traverse(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_iter,
                    vxo_hit* hit);
+void vxo_traverse_batch(const vxo_world* w, const float* origins, const float* dirs, int32_t n, int32_t max_iter, vxo_hit* hits);
 /* plain Amanatides-Woo DDA returning the first solid voxel (self-check).
  * returns 1 and fills voxel[3] on hit, 0 on leaving the volume / max_steps.                 */
 int32_t vxo_plain_dda(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_steps,

@@ -167,3 +167,60 @@ def test_stats_counters_match_oracle(scene):
     c.stats_enable(False)
     want = ow.initial_trace(p, want_stats=True)["stats"]
     assert got == want
+
+
+def _ray_batch(n, seed, dims=(384, 128, 384)):
+    """Random rays plus the degenerate families the loop treats specially: axis-aligned directions (zero components
+    give inf / NaN in 1/dir), origins on voxel boundaries, origins outside the volume, far-away and non-finite origins."""
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = dims
+    o = np.stack([rng.uniform(-20, nx + 20, n), rng.uniform(-10, ny + 30, n), rng.uniform(-20, nz + 20, n)], 1).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float32)
+    k = n // 8
+    d[:k] = axes[rng.integers(0, 6, k)]                                  # axis aligned
+    d[k:2 * k, rng.integers(0, 3)] = 0.0                                 # one zero component (not renormalised: used as given)
+    o[2 * k:3 * k] = np.floor(o[2 * k:3 * k])                            # exactly on voxel corners
+    o[3 * k:4 * k, 1] = np.floor(o[3 * k:4 * k, 1])                      # on a horizontal voxel face
+    d[3 * k:3 * k + k // 2] = axes[rng.integers(0, 6, k // 2)]           # ... walking along it
+    o[4 * k:4 * k + 8] = np.array([[1e9, 60, 100], [-1e9, 60, 100], [100, 3e38, 100], [np.inf, 60, 60], [100, -np.inf, 100],
+                                   [np.nan, 60, 60], [4194304.0, 60, 60], [-4194305.0, 60, 60]], dtype=np.float32)
+    d[4 * k + 8:4 * k + 12] = np.array([[-0.0, -1, 0], [0, -1, -0.0], [-0.0, -0.0, 1], [0, 0, 0]], dtype=np.float32)
+    return o, d
+
+
+@pytest.mark.parametrize("max_iter", [350, 48, 1, 0])
+def test_trace_rays_batch_bit_exact(scene, max_iter):
+    """vxrt_cuda_trace_rays == the oracle's VoxelTraversalDF for every ray, bit for bit: t, end position, normal, block id,
+    Intersection flag and iteration count (the conversion-free CUDA loop against the literal one).  The batch contains
+    rays whose positions become inf / NaN (an unguarded zero direction component, InitialRayTraceFrag.glsl:343-347)."""
+    ctx, ow, _ = scene
+    o, d = _ray_batch(400_000, 5 + max_iter)
+    got = ctx.trace_rays(o, d, max_iter)
+    want = ow.traverse_batch(o, d, max_iter)
+    def bits(a):  # bit patterns with every NaN canonicalised (x86 and the GPU produce different payloads for inf * 0)
+        a = np.ascontiguousarray(a)
+        b = a.view(np.uint32).copy()
+        b[np.isnan(a)] = 0x7FC00000
+        return b
+
+    assert np.array_equal(bits(got["t"]), bits(want["t"]))
+    assert np.array_equal(bits(got["end"]), bits(want["end"]))
+    assert np.array_equal(bits(got["normal"]), bits(want["normal"]))
+    assert np.array_equal(got["block"], want["block"]) and np.array_equal(got["intersection"], want["intersection"])
+    assert np.array_equal(got["iterations"], want["iterations"])
+    if max_iter == 350:
+        assert (got["t"] > 0).mean() > 0.2 and got["iterations"].max() > 100
+
+
+def test_trace_rays_argument_checks(scene):
+    ctx = scene[0]
+    assert len(ctx.trace_rays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))) == 0
+    with pytest.raises(engine.VxrtError):
+        ctx.trace_rays(np.zeros((4, 3), np.float32), np.ones((4, 3), np.float32), -1)
+    fresh = engine.Context(0)
+    with pytest.raises(engine.VxrtError):
+        fresh.trace_rays(np.zeros((4, 3), np.float32), np.ones((4, 3), np.float32))
+    fresh.close()

@@ -43,6 +43,29 @@ def test_df_dda_hits_same_voxel_as_plain_dda(plains0, plains0_oracle):
     assert same / total > 0.999
 
 
+def test_step_table():
+    """The CUDA loop replaces floor(float(k) * 0.57735026918f) by (k * 9459) >> 14 (csrc/traverse.cuh): both must be the
+    oracle's table for every byte, with k == 1 -> 1 (InitialRayTraceFrag.glsl:89-92,331-333)."""
+    t = ob.step_table()
+    k = np.arange(256)
+    want = np.floor(k.astype(np.float32) * np.float32(0.57735026918)).astype(np.int64)
+    want[1] = 1
+    assert np.array_equal(t, want)
+    fast = (k * 9459) >> 14
+    fast[1] = 1
+    assert np.array_equal(t, fast)
+    assert set(np.nonzero(t == 1)[0]) == {1, 2, 3} and t[0] == 0 and t[4] == 2 and t[254] == 146
+
+
+def test_batch_traverse_equals_single_ray_calls(plains0_oracle):
+    o, d = _rays(300, 11, (384, 128, 384))
+    hits = plains0_oracle.traverse_batch(o, d, 350)
+    for i in range(len(o)):
+        h = plains0_oracle.traverse(o[i], d[i], 350)
+        assert hits["t"][i].tobytes() == np.float32(h.t).tobytes() and hits["block"][i] == h.block
+        assert hits["iterations"][i] == h.iterations and list(hits["end"][i]) == list(h.end[:])
+
+
 def test_iteration_cap_and_leaving_volume_miss(plains0_oracle):
     ow = plains0_oracle
     h = ow.traverse([192.0, 120.0, 192.0], [0.0, 1.0, 0.0], 350)  # straight up and out

@@ -99,6 +99,11 @@ class ReflectionParams(C.Structure):
     ]
 
 
+class RayHit(C.Structure):
+    _fields_ = [("t", C.c_float), ("normal", C.c_float * 3), ("end", C.c_float * 3), ("block", C.c_int32),
+                ("intersection", C.c_int32), ("iterations", C.c_int32)]
+
+
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("iterations", C.c_uint64), ("dda_steps", C.c_uint64), ("hits", C.c_uint64)]
 
@@ -162,6 +167,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_attachment_device": (C.c_int, [vp, i32, P(vp), P(i32), P(i32), P(i32)]),
         "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),
         "vxrt_cuda_shadow_trace": (C.c_int, [vp, P(ShadowParams)]),
+        "vxrt_cuda_trace_rays": (C.c_int, [vp, vp, vp, i32, i32, vp]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
         "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
     }

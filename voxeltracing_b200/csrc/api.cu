@@ -93,7 +93,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blocks); cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
-    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf);
+    cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
@@ -331,6 +331,32 @@ int vxrt_cuda_initial_trace(vxrt_ctx* c, const vxrt_primary_params* p) {
     if (p->alpha_test) return vxrt_fail(VXRT_E_UNSUPPORTED, "alpha-tested traversal (InitialRayTraceFrag.glsl:189-305) is off by default in the reference and not implemented");
     if (p->render_distance < 0) return vxrt_fail(VXRT_E_INVALID, "render_distance < 0");
     return vxrt_launch_initial_trace(c, *p);
+}
+
+int vxrt_cuda_trace_rays(vxrt_ctx* c, const float* origins, const float* directions, int32_t n, int32_t max_iterations, vxrt_ray_hit* hits) {
+    REQUIRE_CTX(c);
+    if (n < 0 || max_iterations < 0) return vxrt_fail(VXRT_E_INVALID, "trace_rays: n < 0 or max_iterations < 0");
+    if (n == 0) return VXRT_OK;
+    REQUIRE_PTR(origins); REQUIRE_PTR(directions); REQUIRE_PTR(hits);
+    if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "trace_rays needs a world and a distance field");
+    const size_t vec_bytes = ((size_t)n * 3 * sizeof(float) + 255) / 256 * 256, need = 2 * vec_bytes + (size_t)n * sizeof(vxrt_ray_hit);
+    if (need > c->ray_cap) {
+        if (c->d_ray_buf) VX_CUDA(cudaFree(c->d_ray_buf));
+        c->d_ray_buf = nullptr; c->ray_cap = 0;
+        VX_CUDA(cudaMalloc(&c->d_ray_buf, need));
+        c->ray_cap = need;
+    }
+    char* base = (char*)c->d_ray_buf;
+    float* d_o = (float*)base;
+    float* d_d = (float*)(base + vec_bytes);
+    vxrt_ray_hit* d_h = (vxrt_ray_hit*)(base + 2 * vec_bytes);
+    VX_CUDA(cudaMemcpyAsync(d_o, origins, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(d_d, directions, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int rc = vxrt_launch_trace_rays(c, d_o, d_d, n, max_iterations, d_h);
+    if (rc) return rc;
+    VX_CUDA(cudaMemcpyAsync(hits, d_h, (size_t)n * sizeof(vxrt_ray_hit), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // host buffers are only borrowed for the call
+    return VXRT_OK;
 }
 
 int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {

@@ -81,6 +81,9 @@ struct vxrt_ctx {
     int32_t* d_edit_buf = nullptr;
     size_t edit_cap = 0;
 
+    void* d_ray_buf = nullptr;  // staging of vxrt_cuda_trace_rays: origins | directions | hits
+    size_t ray_cap = 0;
+
     Attachment att[VXRT_ATT_COUNT];
 
     TraceStatsDev* d_stats = nullptr;
@@ -110,6 +113,7 @@ int vxrt_launch_df_slab_phase_b(vxrt_ctx* c, int slab, int nslabs, const int* d_
                                 const void* last_planes);
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
 int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
+int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int n, int max_iter, vxrt_ray_hit* d_hits);
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);
 int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, const uint8_t* rgba8);
 int vxrt_set_skymap(vxrt_ctx* c, int res, const float* rgb_faces);

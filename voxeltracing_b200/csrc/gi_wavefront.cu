@@ -19,6 +19,7 @@
 // The lean trace kernels run at the occupancy of the primary pass, the shading kernels run converged.
 // Path state lives in HBM as SoA float4 arrays (~150 B per pixel); results are bit-identical to gi.cu.
 #include "gi_common.cuh"
+#include "trace_queue.cuh"
 
 namespace {
 
@@ -60,37 +61,53 @@ VXD f3 unpack_normal(unsigned info) {
 }
 VXD f3 ld3(const float4* p) { float4 v = *p; return F3(v.x, v.y, v.z); }
 
-// ---- trace kernels ---------------------------------------------------------------------------------
-// closest hit for the path rays; `list` == nullptr walks all paths whose contrib.w flag is set
+// ---- trace kernels (trace_queue.cuh) -----------------------------------------------------------------
+// closest hit for the path rays; `list` == nullptr walks all paths whose ray is flagged active
+struct PathRays {
+    GiWf w;
+    const int* list;
+    VXD bool fetch(int idx, f3& o, f3& d) const {
+        const int i = list ? list[idx] : idx;
+        const float4 d4 = w.rayD[i];
+        if (!list && d4.w == 0.0f) return false;
+        const float4 o4 = w.rayO[i];
+        o = F3(o4.x, o4.y, o4.z); d = F3(d4.x, d4.y, d4.z);
+        return true;
+    }
+    VXD void store(int idx, const TraceResult& r) const {
+        const int i = list ? list[idx] : idx;
+        w.hitT[i] = r.t;
+        w.hitInfo[i] = pack_hit(r);
+    }
+};
 template <bool STATS>
-__global__ void __launch_bounds__(256) wf_trace_paths_kernel(GridView g, GiWf w, const int* __restrict__ list, const int* __restrict__ count_ptr,
+__global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_paths_kernel(GridView g, GiWf w, const int* __restrict__ list, const int* __restrict__ count_ptr,
                                                              int n, int max_iter, TraceStatsDev* stats) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = list ? *count_ptr : n;
     LaneStats ls = {0u, 0u, 0u, 0u};
-    if (gi < count) {
-        const int i = list ? list[gi] : gi;
-        const float4 d4 = w.rayD[i];
-        if (list || d4.w != 0.0f) {
-            const float4 o4 = w.rayO[i];
-            TraceResult r = traverse_df<STATS>(g, F3(o4.x, o4.y, o4.z), F3(d4.x, d4.y, d4.z), max_iter, &ls);
-            w.hitT[i] = r.t;
-            w.hitInfo[i] = pack_hit(r);
-        }
-    }
+    PathRays pol = {w, list};
+    trace_queue<STATS>(g, pol, count, max_iter, &ls);
     if (STATS) flush_stats(stats, ls);
 }
 // any hit along the (single) light direction for the compacted shadow queue
+struct ShadowRays {
+    GiWf w;
+    f3 light;
+    VXD bool fetch(int idx, f3& o, f3& d) const {
+        const float4 o4 = w.qShadowO[idx];
+        o = F3(o4.x, o4.y, o4.z); d = light;
+        return true;
+    }
+    VXD void store(int idx, const TraceResult& r) const {
+        w.shadowRes[__float_as_int(w.qShadowO[idx].w)] = r.t > 0.0f ? 1.0f : 0.0f;
+    }
+};
 template <bool STATS>
-__global__ void __launch_bounds__(256) wf_trace_shadow_kernel(GridView g, GiWf w, f3 light, int max_iter, TraceStatsDev* stats) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_shadow_kernel(GridView g, GiWf w, f3 light, int max_iter, TraceStatsDev* stats) {
     const int count = w.counters[0];
     LaneStats ls = {0u, 0u, 0u, 0u};
-    if (gi < count) {
-        const float4 o4 = w.qShadowO[gi];
-        TraceResult r = traverse_df<STATS>(g, F3(o4.x, o4.y, o4.z), light, max_iter, &ls);
-        w.shadowRes[__float_as_int(o4.w)] = r.t > 0.0f ? 1.0f : 0.0f;
-    }
+    ShadowRays pol = {w, light};
+    trace_queue<STATS>(g, pol, count, max_iter, &ls);
     if (STATS) flush_stats(stats, ls);
 }
 
@@ -361,7 +378,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     w.counters = carve<int>(p, 16);
 
     const dim3 pgrid((a.width + 31) / 32, (rows + 7) / 8);
-    const int lgrid = (int)((n + 255) / 256);
+    const int lgrid = trace_queue_grid(n);
     const GridView g = c->grid();
     f3 light;
     light.x = a.sun_stronger ? a.sun[0] : a.moon[0]; light.y = a.sun_stronger ? a.sun[1] : a.moon[1]; light.z = a.sun_stronger ? a.sun[2] : a.moon[2];
@@ -372,13 +389,13 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     cudaStream_t s = c->stream;
 #define TRACE_PATHS(list, cnt, iters)                                                                                     \
     do {                                                                                                                  \
-        if (st) wf_trace_paths_kernel<true><<<lgrid, 256, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);            \
-        else wf_trace_paths_kernel<false><<<lgrid, 256, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);              \
+        if (st) wf_trace_paths_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);            \
+        else wf_trace_paths_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);              \
     } while (0)
 #define TRACE_SHADOW()                                                                                                    \
     do {                                                                                                                  \
-        if (st) wf_trace_shadow_kernel<true><<<lgrid, 256, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);       \
-        else wf_trace_shadow_kernel<false><<<lgrid, 256, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);         \
+        if (st) wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);       \
+        else wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);         \
     } while (0)
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), s));

@@ -11,6 +11,7 @@
 //   shadeB   combine with the shadow term, accumulate colour / hit distance
 //   resolve  averages, clamps, attachment formats
 #include "reflect_common.cuh"
+#include "trace_queue.cuh"
 
 namespace {
 
@@ -46,31 +47,45 @@ VXD f3 unpack_normal(unsigned info) {
     return face == 7u ? F3(0.0f) : face_normal((int)face);
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(256) rf_wf_trace_kernel(GridView g, RfWf w, int n, int max_iter, TraceStatsDev* stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    LaneStats ls = {0u, 0u, 0u, 0u};
-    if (i < n) {
-        const float4 d4 = w.rayD[i];
-        if (d4.w != 0.0f) {
-            const float4 o4 = w.P[i];
-            TraceResult r = traverse_df<STATS>(g, F3(o4.x, o4.y, o4.z), F3(d4.x, d4.y, d4.z), max_iter, &ls);
-            w.hitT[i] = r.t;
-            w.hitInfo[i] = pack_hit(r);
-        }
+struct ReflRays {
+    RfWf w;
+    VXD bool fetch(int idx, f3& o, f3& d) const {
+        const float4 d4 = w.rayD[idx];
+        if (d4.w == 0.0f) return false;
+        const float4 o4 = w.P[idx];
+        o = F3(o4.x, o4.y, o4.z); d = F3(d4.x, d4.y, d4.z);
+        return true;
     }
+    VXD void store(int idx, const TraceResult& r) const {
+        w.hitT[idx] = r.t;
+        w.hitInfo[idx] = pack_hit(r);
+    }
+};
+template <bool STATS>
+__global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_kernel(GridView g, RfWf w, int n, int max_iter, TraceStatsDev* stats) {
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    ReflRays pol = {w};
+    trace_queue<STATS>(g, pol, n, max_iter, &ls);
     if (STATS) flush_stats(stats, ls);
 }
+struct ReflShadowRays {
+    RfWf w;
+    f3 light;
+    VXD bool fetch(int idx, f3& o, f3& d) const {
+        const float4 o4 = w.qShadowO[idx];
+        o = F3(o4.x, o4.y, o4.z); d = light;
+        return true;
+    }
+    VXD void store(int idx, const TraceResult& r) const {
+        w.shadowRes[__float_as_int(w.qShadowO[idx].w)] = r.t > 0.0f ? 1.0f : 0.0f;
+    }
+};
 template <bool STATS>
-__global__ void __launch_bounds__(256) rf_wf_trace_shadow_kernel(GridView g, RfWf w, f3 light, int max_iter, TraceStatsDev* stats) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_shadow_kernel(GridView g, RfWf w, f3 light, int max_iter, TraceStatsDev* stats) {
     const int count = w.counters[0];
     LaneStats ls = {0u, 0u, 0u, 0u};
-    if (gi < count) {
-        const float4 o4 = w.qShadowO[gi];
-        TraceResult r = traverse_df<STATS>(g, F3(o4.x, o4.y, o4.z), light, max_iter, &ls);
-        w.shadowRes[__float_as_int(o4.w)] = r.t > 0.0f ? 1.0f : 0.0f;
-    }
+    ReflShadowRays pol = {w, light};
+    trace_queue<STATS>(g, pol, count, max_iter, &ls);
     if (STATS) flush_stats(stats, ls);
 }
 
@@ -350,7 +365,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     w.counters = carve<int>(p, 16);
 
     const dim3 pgrid((a.width + 31) / 32, (rows + 7) / 8);
-    const int lgrid = (int)((n + 255) / 256);
+    const int lgrid = trace_queue_grid(n);
     const GridView g = c->grid();
     f3 strong;
     strong.x = a.strong[0]; strong.y = a.strong[1]; strong.z = a.strong[2];
@@ -360,11 +375,11 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         rf_wf_gen_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);
-        if (st) rf_wf_trace_kernel<true><<<lgrid, 256, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
-        else rf_wf_trace_kernel<false><<<lgrid, 256, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
+        if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
+        else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         rf_wf_shade_a_kernel<<<pgrid, 256, 0, s>>>(a, w);
-        if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, 256, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
-        else rf_wf_trace_shadow_kernel<false><<<lgrid, 256, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
+        if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
+        else rf_wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w);
         c->launches += 5;
     }

@@ -282,3 +282,27 @@ int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p) {
     c->launches += 1;
     return VXRT_OK;
 }
+
+// ---- VoxelTraversalDF for caller-supplied rays (vxrt_cuda_trace_rays) -----------------------------------
+namespace {
+__global__ void __launch_bounds__(128) trace_rays_kernel(GridView g, const float* __restrict__ o, const float* __restrict__ d, int n, int max_iter,
+                                                         vxrt_ray_hit* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    const TraceResult r = traverse_df<true>(g, F3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), F3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), max_iter, &ls);
+    vxrt_ray_hit h;
+    h.t = r.t;
+    h.normal[0] = r.normal.x; h.normal[1] = r.normal.y; h.normal[2] = r.normal.z;
+    h.end[0] = r.end.x; h.end[1] = r.end.y; h.end[2] = r.end.z;
+    h.block = r.block; h.intersection = r.intersection ? 1 : 0; h.iterations = (int)ls.iterations;
+    out[i] = h;
+}
+}  // namespace
+
+int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int n, int max_iter, vxrt_ray_hit* d_hits) {
+    trace_rays_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->grid(), d_o, d_d, n, max_iter, d_hits);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}

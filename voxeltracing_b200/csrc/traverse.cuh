@@ -37,27 +37,76 @@ VXD int euclidean_step(int k) {
     return __float2int_rd(ce);
 }
 
+// ---- conversion-free iteration -------------------------------------------------------------------------
+// ncu on the first version of this loop (profiles/r1_b_*): the XU pipe (F2I / I2F, 16 lanes/clk/SM) was the
+// busiest pipe of the primary and shadow kernels (54 %), ahead of the ALU.  The loop below produces the same
+// bits without a single conversion instruction:
+//   floor(x)            FADD.RM x + 1.5*2^23: for x in [-2^22, 2^22) the sum lies in [2^23, 2^24) where floats
+//                       are the integers, so rounding down gives floor(x) + 1.5*2^23 exactly; the integer is
+//                       the mantissa (bits - 0x4B400000), the float floor is F - 1.5*2^23 (exact).
+//                       Anything else (|x| >= 2^22, inf, NaN) lands outside the in-volume window of bit
+//                       patterns, and only then the saturating conversion decides (NaN -> 0 as pinned in
+//                       DESIGN.md §4); a ray with a NaN coordinate that is still "inside" continues in
+//                       traverse_df_tail, the literal loop.
+//   ivec3(origin)       == floor(origin) inside the volume (every component >= 0).
+//   E(k)                floor(float(k) * 0.57735026918f) == (k * 9459) >> 14 for every byte k
+//                       (tests/test_oracle_traverse.py::test_step_table); k == 1 -> 1.  So k == 0 stops,
+//                       k in 1..3 is a DDA step, k >= 4 skips E - 1 voxels.
+//   float(E - 1)        (2^23 + n) - 2^23 built from the bit pattern 0x4B000000 + n.
+//   float(G + s)        floor_float + float(s), exact on integers.
+#define VX_FLOOR_MAGIC 12582912.0f
+#define VX_FLOOR_MAGIC_BITS 0x4B400000
+
+struct RaySetup {
+    f3 d, inv;
+    f3 fs;      // float(RaySign)
+    f3 fp;      // float((1 + RaySign) >> 1)
+    f3 omp;     // float(1 - ((1 + RaySign) >> 1))
+    f3 nudge;   // float(RaySign) * 0.0001f
+    int sx, sy, sz;
+};
+VXD RaySetup ray_setup(f3 direction) {
+    RaySetup r;
+    r.d = direction;
+    r.sx = gsign(direction.x); r.sy = gsign(direction.y); r.sz = gsign(direction.z);
+    const int px = (1 + r.sx) >> 1, py = (1 + r.sy) >> 1, pz = (1 + r.sz) >> 1;
+    r.inv = F3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    r.fs = F3((float)r.sx, (float)r.sy, (float)r.sz);
+    r.fp = F3((float)px, (float)py, (float)pz);
+    r.omp = F3((float)(1 - px), (float)(1 - py), (float)(1 - pz));
+    r.nudge = F3(r.fs.x * 0.0001f, r.fs.y * 0.0001f, r.fs.z * 0.0001f);
+    return r;
+}
+
+// the literal loop (one F2I per floor, I2F per ivec -> vec), continuing a ray from iteration `itr`
+struct TailState {
+    f3 origin;
+    int MinIdx;
+    bool Intersection;
+    unsigned iterations, dda;  // stats deltas
+};
 template <bool STATS>
-VXD TraceResult traverse_df(const GridView& g, f3 origin, f3 direction, int max_iter, LaneStats* st) {
-    const f3 initial_origin = origin;
+__device__ __noinline__ TailState traverse_df_tail(const uint8_t* __restrict__ df, int nx, int ny, int nz, f3 origin, f3 direction, int itr,
+                                                   int max_iter, bool Intersection, int MinIdx) {
+    GridView g;
+    g.df = df; g.blk = nullptr; g.nx = nx; g.ny = ny; g.nz = nz; g.sy = nx; g.sz = nx * ny;
+    TailState ts;
+    ts.iterations = 0u; ts.dda = 0u;
     const int sx = gsign(direction.x), sy = gsign(direction.y), sz = gsign(direction.z);
     const int px = (1 + sx) >> 1, py = (1 + sy) >> 1, pz = (1 + sz) >> 1;
     const f3 inv = F3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    bool Intersection = false;
-    int MinIdx = 0;
-
-    for (int itr = 0; itr < max_iter; ++itr) {
+    for (; itr < max_iter; ++itr) {
         int lx = cvt_floor(origin.x), ly = cvt_floor(origin.y), lz = cvt_floor(origin.z);
         if (!in_volume(g, lx, ly, lz)) {
             Intersection = false;
             break;
         }
         int k = __ldg(g.df + (lx + ly * g.sy + lz * g.sz));
-        if (STATS) st->iterations++;
+        if (STATS) ts.iterations++;
         int E = euclidean_step(k);
         if (E == 0) break;
         if (E == 1) {
-            if (STATS) st->dda++;
+            if (STATS) ts.dda++;
             int gx = cvt_trunc(origin.x), gy = cvt_trunc(origin.y), gz = cvt_trunc(origin.z);
             f3 W = origin - F3((float)gx, (float)gy, (float)gz);
             f3 DF = (F3((float)px, (float)py, (float)pz) - W) * inv;
@@ -77,7 +126,62 @@ VXD TraceResult traverse_df(const GridView& g, f3 origin, f3 direction, int max_
             origin = origin + (float)(E - 1) * direction;
         }
     }
+    ts.origin = origin; ts.MinIdx = MinIdx; ts.Intersection = Intersection;
+    return ts;
+}
+// continues a ray in the literal loop and folds the result back into the caller's state
+template <bool STATS>
+VXD void run_tail(const GridView& g, f3& origin, f3 direction, int itr, int max_iter, bool& Intersection, int& MinIdx, LaneStats* st) {
+    const TailState ts = traverse_df_tail<STATS>(g.df, g.nx, g.ny, g.nz, origin, direction, itr, max_iter, Intersection, MinIdx);
+    origin = ts.origin; MinIdx = ts.MinIdx; Intersection = ts.Intersection;
+    if (STATS) { st->iterations += ts.iterations; st->dda += ts.dda; }
+}
 
+enum { VX_ITER_CONTINUE = 0, VX_ITER_STOP = 1, VX_ITER_TAIL = 2 };
+
+// one iteration of VoxelTraversalDF (InitialRayTraceFrag.glsl:320-371)
+template <bool STATS>
+VXD int df_iteration(const GridView& g, const RaySetup& r, f3& origin, bool& Intersection, int& MinIdx, LaneStats* st) {
+    const float Fx = __fadd_rd(origin.x, VX_FLOOR_MAGIC), Fy = __fadd_rd(origin.y, VX_FLOOR_MAGIC), Fz = __fadd_rd(origin.z, VX_FLOOR_MAGIC);
+    const unsigned bx = __float_as_uint(Fx), by = __float_as_uint(Fy), bz = __float_as_uint(Fz);  // 0x4B400000 + floor
+    if (!(((bx - VX_FLOOR_MAGIC_BITS) < (unsigned)g.nx) & ((by - VX_FLOOR_MAGIC_BITS) < (unsigned)g.ny) & ((bz - VX_FLOOR_MAGIC_BITS) < (unsigned)g.nz))) {
+        if (!in_volume(g, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z))) {
+            Intersection = false;
+            return VX_ITER_STOP;
+        }
+        return VX_ITER_TAIL;  // NaN coordinate converted to 0: leave the fast path
+    }
+    // linear index from the biased integers: the bias of every term is removed by one constant (mod 2^32)
+    const unsigned idx = bx + by * (unsigned)g.sy + bz * (unsigned)g.sz - VX_FLOOR_MAGIC_BITS * (1u + (unsigned)g.sy + (unsigned)g.sz);
+    const int k = __ldg(g.df + idx);
+    if (STATS) st->iterations++;
+    if (k < 4) {
+        if (k == 0) return VX_ITER_STOP;
+        if (STATS) st->dda++;
+        const f3 fl = F3(Fx - VX_FLOOR_MAGIC, Fy - VX_FLOOR_MAGIC, Fz - VX_FLOOR_MAGIC);  // vec3(ivec3(origin))
+        f3 W = origin - fl;
+        const f3 DF = (r.fp - W) * r.inv;
+        // MinIdx (:345-347) as predicate logic: x iff (DF.x < DF.y && sx != 0) && (DF.x < DF.z || sz == 0), ...
+        const bool first = (DF.x < DF.y) & (r.sx != 0), z_off = r.sz == 0;
+        const bool ax = first & ((DF.x < DF.z) | z_off), ay = !first & ((DF.y < DF.z) | z_off), az = !(ax | ay);
+        MinIdx = ax ? 0 : (ay ? 1 : 2);
+        W = W + r.d * (ax ? DF.x : (ay ? DF.y : DF.z));
+        const float gx = ax ? fl.x + r.fs.x : fl.x, gy = ay ? fl.y + r.fs.y : fl.y, gz = az ? fl.z + r.fs.z : fl.z;
+        W.x = ax ? r.omp.x : W.x; W.y = ay ? r.omp.y : W.y; W.z = az ? r.omp.z : W.z;
+        origin = F3(gx, gy, gz) + W;
+        origin.x = ax ? origin.x + r.nudge.x : origin.x;
+        origin.y = ay ? origin.y + r.nudge.y : origin.y;
+        origin.z = az ? origin.z + r.nudge.z : origin.z;
+        Intersection = true;
+    } else {
+        const float skip = __int_as_float(0x4B000000 + ((k * 9459) >> 14) - 1) - 8388608.0f;  // float(E - 1)
+        origin = origin + skip * r.d;
+    }
+    return VX_ITER_CONTINUE;
+}
+
+template <bool STATS>
+VXD TraceResult trace_result(const GridView& g, const RaySetup& rs, f3 origin, f3 initial_origin, bool Intersection, int MinIdx, LaneStats* st) {
     TraceResult r;
     r.t = -1.0f;
     r.block = 0;
@@ -85,13 +189,28 @@ VXD TraceResult traverse_df(const GridView& g, f3 origin, f3 direction, int max_
     r.intersection = Intersection;
     r.end = origin;
     if (Intersection) {
-        int s = MinIdx == 0 ? sx : (MinIdx == 1 ? sy : sz);
+        int s = MinIdx == 0 ? rs.sx : (MinIdx == 1 ? rs.sy : rs.sz);
         set_comp(r.normal, MinIdx, (float)(-s));
         r.block = get_voxel(g, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z));
         r.t = r.block > 0 ? distance(origin, initial_origin) : -1.0f;
     }
     if (STATS) { st->rays++; st->hits += (r.t > 0.0f) ? 1u : 0u; }
     return r;
+}
+
+template <bool STATS>
+VXD TraceResult traverse_df(const GridView& g, f3 origin, f3 direction, int max_iter, LaneStats* st) {
+    const f3 initial_origin = origin;
+    const RaySetup rs = ray_setup(direction);
+    bool Intersection = false;
+    int MinIdx = 0;
+    for (int itr = 0; itr < max_iter; ++itr) {
+        const int c = df_iteration<STATS>(g, rs, origin, Intersection, MinIdx, st);
+        if (c == VX_ITER_CONTINUE) continue;
+        if (c == VX_ITER_TAIL) run_tail<STATS>(g, origin, direction, itr, max_iter, Intersection, MinIdx, st);
+        break;
+    }
+    return trace_result<STATS>(g, rs, origin, initial_origin, Intersection, MinIdx, st);
 }
 
 // warp-aggregated flush of per-lane counters

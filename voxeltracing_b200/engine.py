@@ -254,6 +254,19 @@ class Context:
         shape = (h, w) if ch == 1 else (h, w, ch)
         return _DeviceArray(ptr, shape, np.dtype(dt).str)
 
+    RAY_HIT_DTYPE = np.dtype([("t", "<f4"), ("normal", "<f4", 3), ("end", "<f4", 3), ("block", "<i4"), ("intersection", "<i4"),
+                              ("iterations", "<i4")])
+
+    def trace_rays(self, origins, directions, max_iterations: int = 350) -> np.ndarray:
+        """VoxelTraversalDF over a batch of caller-supplied rays ((n,3) float32 each); structured array of hits."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        if o.shape != d.shape:
+            raise ValueError("origins and directions must have the same shape")
+        hits = np.zeros(len(o), dtype=self.RAY_HIT_DTYPE)
+        self._check(self._lib.vxrt_cuda_trace_rays(self._h, _p(o), _p(d), len(o), int(max_iterations), _p(hits)))
+        return hits
+
     # -- statistics --
     def stats_enable(self, on: bool):
         self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))
