@@ -432,19 +432,22 @@ def main():
         for att, off, n in layout:
             ctx.bind_attachment(att, None)      # back to context-owned attachments for the end-to-end leg
         fr.submit(prepared[0])
-    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-    host_np = [h.numpy() for h in host_out]
-    d2h = sum(h.nbytes for h in host_np)
+    # two sets of page-locked host buffers: frame k is copied out (vxrt_cuda_read_attachment_async, the PBO + fence
+    # pattern) while frame k+1 renders; a pass that overwrites an attachment waits on the device for its copy
+    host_out = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs] for _ in range(2)]
+    host_np = [[h.numpy() for h in hs] for hs in host_out]
+    d2h = sum(h.nbytes for h in host_np[0])
     h2d = sum(ctypes.sizeof(p) for _, _, p in prepared[0])
 
     def e2e_step(s):
         prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s))
         fr.submit(prep)
-        for att, buf in zip(fr.outputs, host_np):
-            ctx.read_attachment(att, buf)
+        for att, buf in zip(fr.outputs, host_np[s & 1]):
+            ctx.read_attachment_async(att, buf)
 
     for s in range(min(3, args.warmup)):
         e2e_step(s)
+    ctx.wait_reads()
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
@@ -452,6 +455,7 @@ def main():
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(args.warmup + i)
+    ctx.wait_reads()                      # every frame's attachments are in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_rays = int(sum(rays_per_step[:e2e_steps]))

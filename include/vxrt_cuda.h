@@ -142,6 +142,13 @@ typedef enum vxrt_attachment {
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
 int vxrt_cuda_read_attachment(vxrt_ctx* ctx, int32_t attachment, void* host_dst, size_t bytes);
+/* Asynchronous read-back, the glGetTexImage-into-a-pixel-pack-buffer + fence pattern: the copy is queued on the
+ * context's copy stream behind everything issued so far and the call returns at once; the next pass that writes
+ * the attachment waits for the copy on the device, later passes that only read it do not.  dst should be
+ * page-locked host memory (with pageable memory the copy degrades to a synchronous one); it is owned by the
+ * library until vxrt_cuda_wait_reads returns. */
+int vxrt_cuda_read_attachment_async(vxrt_ctx* ctx, int32_t id, void* dst, size_t bytes);
+int vxrt_cuda_wait_reads(vxrt_ctx* ctx);
 /* device pointer + geometry of an attachment (valid until the pass that owns it is re-run at a
  * different size).  Used by the host side for NCCL tile gathers.                              */
 int vxrt_cuda_attachment_device(vxrt_ctx* ctx, int32_t attachment, void** dev_ptr, int32_t* width,

@@ -163,6 +163,8 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_diffuse_trace": (C.c_int, [vp, P(GIParams)]),
         "vxrt_cuda_reflection_trace": (C.c_int, [vp, P(ReflectionParams)]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
+        "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),
+        "vxrt_cuda_wait_reads": (C.c_int, [vp]),
         "vxrt_cuda_bind_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_attachment_device": (C.c_int, [vp, i32, P(vp), P(i32), P(i32), P(i32)]),
         "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),

@@ -34,9 +34,14 @@ int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
     if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "bad attachment size %dx%d", w, h);
     Attachment& a = c->att[id];
     size_t need = (size_t)w * h * bpp;
+    if (c->att_read_pending[id]) {  // the pass about to write this attachment must not overtake a read-back in flight
+        VX_CUDA(cudaStreamWaitEvent(c->stream, c->att_read_done[id], 0));
+        c->att_read_pending[id] = false;
+    }
     if (need > a.capacity && a.external)
         return vxrt_fail(VXRT_E_INVALID, "attachment %d: bound storage holds %zu bytes, the pass needs %zu", id, a.capacity, need);
     if (need > a.capacity) {
+        if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
         if (a.ptr) VX_CUDA(cudaFree(a.ptr));
         a.ptr = nullptr;
         a.capacity = 0;
@@ -97,6 +102,11 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < VXRT_ATT_COUNT; ++i) {
+        if (c->att_ready[i]) cudaEventDestroy(c->att_ready[i]);
+        if (c->att_read_done[i]) cudaEventDestroy(c->att_read_done[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return VXRT_OK;
@@ -292,9 +302,35 @@ int vxrt_cuda_read_attachment(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) 
     VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
+int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    const Attachment& a = c->att[id];
+    if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
+    size_t have = (size_t)a.width * a.height * a.bpp;
+    if (bytes != have) return vxrt_fail(VXRT_E_INVALID, "attachment %d holds %zu bytes, caller asked for %zu", id, have, bytes);
+    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->att_ready[id]) {
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
+    }
+    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));               // everything issued so far has produced the attachment
+    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
+    VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, c->copy_stream));
+    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
+    c->att_read_pending[id] = true;
+    return VXRT_OK;
+}
+int vxrt_cuda_wait_reads(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return VXRT_OK;
+}
 int vxrt_cuda_bind_attachment(vxrt_ctx* c, int32_t id, void* dev_ptr, size_t capacity) {
     REQUIRE_CTX(c);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->att_read_pending[id] = false;
     Attachment& a = c->att[id];
     if (a.ptr && !a.external) VX_CUDA(cudaFree(a.ptr));
     if (dev_ptr) {

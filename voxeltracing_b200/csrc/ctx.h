@@ -85,6 +85,12 @@ struct vxrt_ctx {
     size_t ray_cap = 0;
 
     Attachment att[VXRT_ATT_COUNT];
+    // asynchronous read-back (vxrt_cuda_read_attachment_async): copies run on their own stream, ordered against
+    // the passes by one event pair per attachment
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t att_ready[VXRT_ATT_COUNT] = {};      // recorded on `stream` when a read is requested
+    cudaEvent_t att_read_done[VXRT_ATT_COUNT] = {};  // recorded on `copy_stream` after the copy
+    bool att_read_pending[VXRT_ATT_COUNT] = {};
 
     TraceStatsDev* d_stats = nullptr;
     bool stats_on = false;

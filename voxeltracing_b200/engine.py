@@ -247,6 +247,16 @@ class Context:
         self._check(self._lib.vxrt_cuda_read_attachment(self._h, att, _p(out), out.nbytes))
         return out
 
+    def read_attachment_async(self, att: int, out: np.ndarray):
+        """Queues the read-back behind the passes issued so far and returns; `out` (page-locked for a truly asynchronous
+        copy) is valid after wait_reads()."""
+        _, w, h, bpp = self.attachment_info(att)
+        assert out.nbytes == w * h * bpp and out.flags["C_CONTIGUOUS"]
+        self._check(self._lib.vxrt_cuda_read_attachment_async(self._h, att, _p(out), out.nbytes))
+
+    def wait_reads(self):
+        self._check(self._lib.vxrt_cuda_wait_reads(self._h))
+
     def attachment_as_device_array(self, att: int):
         """Zero-copy view for torch.as_tensor(..., device='cuda') (NCCL tile gathers)."""
         ptr, w, h, bpp = self.attachment_info(att)
