@@ -439,11 +439,18 @@ def main():
     d2h = sum(h.nbytes for h in host_np[0])
     h2d = sum(ctypes.sizeof(p) for _, _, p in prepared[0])
 
+    from voxeltracing_b200.pipeline import PASS_OUTPUTS
+    host_of = [dict(zip(fr.outputs, bufs)) for bufs in host_np]
+
     def e2e_step(s):
         prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s))
-        fr.submit(prep)
-        for att, buf in zip(fr.outputs, host_np[s & 1]):
-            ctx.read_attachment_async(att, buf)
+
+        def read_pass_outputs(name, where):   # a pass's attachments start their way to the host as soon as it is queued
+            if where == "end":
+                for att in PASS_OUTPUTS[name]:
+                    ctx.read_attachment_async(att, host_of[s & 1][att])
+
+        fr.submit(prep, hook=read_pass_outputs)
 
     for s in range(min(3, args.warmup)):
         e2e_step(s)
