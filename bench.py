@@ -313,8 +313,10 @@ def main():
     trace_passes = [p for p in cfg.passes if p in TRACE_PASSES]
     pass_stats = {p: {"rays": 0, "iterations": 0} for p in trace_passes}
     rays_per_step = []
+    ctx.set_option("probe", 1)          # event pairs around every launch of the GI path-ray trace kernel
     ctx.stats_enable(True)
     ctx.stats_read(reset=True)
+    ctx.probe_read(reset=True)
     for s in range(args.warmup, n_total):
         acc = [0]
 
@@ -327,6 +329,7 @@ def main():
 
         fr.submit(prepared[s], hook=stat_hook)
         rays_per_step.append(acc[0])
+    probe_stats = ctx.probe_read(reset=True)   # rays / iterations of the probed kernel's launches alone
     ctx.stats_enable(False)
     total_rays = int(sum(rays_per_step))
     total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
@@ -395,6 +398,7 @@ def main():
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    ctx.probe_read(reset=True)
     launches_before = ctx.launch_count
     for i in range(args.steps):
         flush_buf.zero_()
@@ -412,6 +416,8 @@ def main():
         torch.cuda.synchronize()
         ms += max(0.0, step_ev[-1][1].elapsed_time(tail))
     launches = ctx.launch_count - launches_before
+    probe_time = ctx.probe_read(reset=True)    # summed CUDA-event time of the probed kernel inside the timed region
+    ctx.set_option("probe", 0)
     clocks = sampler.stop() if rank == 0 else None
     pass_ms = {p: float(np.mean([pe[p][0].elapsed_time(pe[p][1]) for pe in pass_ev])) for p in cfg.passes}
 
@@ -479,15 +485,28 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         mrays = total_rays / (ms * 1e-3) / 1e6
-        # roofline of the dominant kernel: algorithmic bytes per launch = rays*(S+1) + output bytes
+        # roofline of the dominant kernel.  Algorithmic bytes per launch = rays*(S+1) (one distance-field byte per
+        # iteration + the block byte) + the bytes the kernel must read / write per ray.
         dom = max(trace_passes, key=lambda p: pass_ms[p])
-        st = pass_stats[dom]
-        S = st["iterations"] / max(st["rays"], 1)
-        rays_per_launch = st["rays"] / args.steps
-        out_bytes = PASS_OUTPUT_BYTES[dom] * W * H
-        alg_bytes = rays_per_launch * (S + 1) + out_bytes
-        achieved = alg_bytes / (pass_ms[dom] * 1e-3) / 1e9
-        sector_bytes = rays_per_launch * 32 * (S + 1) + out_bytes
+        if dom == "gi" and probe_time["launches"] > 0:
+            # GI is a wavefront pipeline: its dominant kernel is the path-ray trace kernel, timed by the probe
+            kname = "wf_trace_paths_kernel"
+            n_launch = probe_time["launches"]
+            k_ms = probe_time["ms"] / n_launch
+            k_rays = probe_stats["rays"] / max(probe_stats["launches"], 1)
+            S = probe_stats["iterations"] / max(probe_stats["rays"], 1)
+            io_bytes = 40.0 * k_rays   # per ray: origin + direction (2 x float4) in, t + packed hit (8 B) out
+        else:
+            kname = PASS_KERNEL[dom]
+            st = pass_stats[dom]
+            S = st["iterations"] / max(st["rays"], 1)
+            k_rays = st["rays"] / args.steps
+            k_ms = pass_ms[dom]
+            io_bytes = PASS_OUTPUT_BYTES[dom] * W * H
+        alg_bytes = k_rays * (S + 1) + io_bytes
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        sector_bytes = k_rays * 32 * (S + 1) + io_bytes
+        gather_peak_gbs = ctx.gather_peak(256) * 32 / 1e9
         line = {
             "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -506,12 +525,15 @@ def main():
             "gpu_launches": launches,
             "pass_ms": pass_ms,
             "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},
-            "roofline": {"kernel": PASS_KERNEL[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "mean_iterations_per_ray": S, "rays_per_launch": rays_per_launch, "avg_launch_ms": pass_ms[dom],
-                         "algorithmic_bytes_per_launch": alg_bytes, "l2_sector_gbs": sector_bytes / (pass_ms[dom] * 1e-3) / 1e9,
-                         "kernel_mrays": rays_per_launch / (pass_ms[dom] * 1e-3) / 1e6,
-                         "note": "grids are L2 resident: the operative roof is L2/L1 gather latency and issue slots, see DESIGN.md §3"},
+                         "mean_iterations_per_ray": S, "rays_per_launch": k_rays, "avg_launch_ms": k_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_mrays": k_rays / (k_ms * 1e-3) / 1e6,
+                         "l2_gather": {"achieved": sector_bytes / (k_ms * 1e-3) / 1e9, "peak": gather_peak_gbs, "unit": "GB/s",
+                                       "frac": sector_bytes / (k_ms * 1e-3) / 1e9 / gather_peak_gbs,
+                                       "peak_source": "vxrt_cuda_gather_peak: independent random 1-byte loads of the L2-resident distance field, 32 B per sector, measured in this run"},
+                         "note": "grids are L2 resident (dram throughput < 1 % in profiles/): HBM is the contract's roof, the operative one is issue slots, then the L2/L1 gather rate (l2_gather); see DESIGN.md §3"},
         }
         nvox = blocks.size
         line["df_regen"] = {"us_per_regeneration": df_us, "algorithmic_bytes": 2 * nvox,

@@ -322,6 +322,15 @@ typedef struct vxrt_trace_stats {
 /* enable/disable (re)counting; when enabled every trace pass accumulates into the counters. */
 int vxrt_cuda_stats_enable(vxrt_ctx* ctx, int32_t on);
 int vxrt_cuda_stats_read(vxrt_ctx* ctx, vxrt_trace_stats* out, int32_t reset);
+/* Kernel probe (measurement only): after vxrt_cuda_set_option(ctx, "probe", 1) every launch of the GI path-ray
+ * trace kernel (the dominant kernel of a GI frame) is bracketed by a CUDA-event pair on the context's stream.
+ * probe_read synchronises and returns the summed duration, the number of launches and, when statistics are
+ * enabled, the traversal statistics of those launches alone. */
+int vxrt_cuda_probe_read(vxrt_ctx* ctx, double* total_ms, int64_t* launches, vxrt_trace_stats* stats, int32_t reset);
+/* Measurement only: the rate (32-byte sectors per second) at which this GPU serves independent 1-byte loads at
+ * random addresses of the L2-resident distance field, all SMs loaded: the gather roof the traversal is compared
+ * with.  Each thread issues rounds * 8 loads. */
+int vxrt_cuda_gather_peak(vxrt_ctx* ctx, int32_t rounds, double* sectors_per_second);
 
 #ifdef __cplusplus
 }

@@ -172,6 +172,8 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_trace_rays": (C.c_int, [vp, vp, vp, i32, i32, vp]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
         "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
+        "vxrt_cuda_gather_peak": (C.c_int, [vp, i32, P(C.c_double)]),
+        "vxrt_cuda_probe_read": (C.c_int, [vp, P(C.c_double), P(i64), P(TraceStats), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -56,6 +56,16 @@ int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
     return VXRT_OK;
 }
 
+cudaEvent_t vxrt_probe_event(vxrt_ctx* c) {
+    if (!c->probe_on) return nullptr;
+    if (c->probe_used == c->probe_ev.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->probe_ev.push_back(e);
+    }
+    return c->probe_ev[c->probe_used++];
+}
+
 extern "C" {
 
 const char* vxrt_cuda_last_error(void) { return g_err; }
@@ -85,8 +95,8 @@ int vxrt_cuda_create(vxrt_ctx** out, int device, const int32_t* dims) {
     if (rc == VXRT_OK) { c->stream = c->own_stream; rc = vxrt_check_cuda(cudaMalloc(&c->d_blocks, c->nvox), "cudaMalloc(blocks)"); }
     if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_df, c->nvox), "cudaMalloc(df)");
     if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_block_data, 6 * 128 * sizeof(int32_t)), "cudaMalloc(block_data)");
-    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_stats, sizeof(TraceStatsDev)), "cudaMalloc(stats)");
-    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMemset(c->d_stats, 0, sizeof(TraceStatsDev)), "cudaMemset(stats)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMalloc(&c->d_stats, 2 * sizeof(TraceStatsDev)), "cudaMalloc(stats)");
+    if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMemset(c->d_stats, 0, 2 * sizeof(TraceStatsDev)), "cudaMemset(stats)");
     if (rc == VXRT_OK) rc = vxrt_check_cuda(cudaMemset(c->d_block_data, 0xff, 6 * 128 * sizeof(int32_t)), "cudaMemset(block_data)");
     if (rc != VXRT_OK) { vxrt_cuda_destroy(c); return rc; }
     *out = c;
@@ -102,6 +112,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
+    for (cudaEvent_t e : c->probe_ev) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i) {
         if (c->att_ready[i]) cudaEventDestroy(c->att_ready[i]);
@@ -126,6 +137,7 @@ int vxrt_cuda_synchronize(vxrt_ctx* c) {
 int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     REQUIRE_CTX(c); REQUIRE_PTR(name);
     if (!strcmp(name, "wavefront")) { c->wavefront = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
     return vxrt_fail(VXRT_E_INVALID, "unknown option '%s'", name);
 }
 int64_t vxrt_cuda_launch_count(vxrt_ctx* c) { return c ? c->launches : -1; }
@@ -488,11 +500,45 @@ int vxrt_cuda_stats_enable(vxrt_ctx* c, int32_t on) {
 }
 int vxrt_cuda_stats_read(vxrt_ctx* c, vxrt_trace_stats* out, int32_t reset) {
     REQUIRE_CTX(c); REQUIRE_PTR(out);
-    TraceStatsDev h;
-    VX_CUDA(cudaMemcpyAsync(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    TraceStatsDev h[2];
+    VX_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
-    out->rays = h.rays; out->iterations = h.iterations; out->dda_steps = h.dda_steps; out->hits = h.hits;
-    if (reset) VX_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(TraceStatsDev), c->stream));
+    out->rays = h[0].rays + h[1].rays; out->iterations = h[0].iterations + h[1].iterations;
+    out->dda_steps = h[0].dda_steps + h[1].dda_steps; out->hits = h[0].hits + h[1].hits;
+    if (reset) {
+        c->probe_acc.rays += h[1].rays; c->probe_acc.iterations += h[1].iterations;
+        c->probe_acc.dda_steps += h[1].dda_steps; c->probe_acc.hits += h[1].hits;
+        VX_CUDA(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(TraceStatsDev), c->stream));
+    }
+    return VXRT_OK;
+}
+int vxrt_cuda_gather_peak(vxrt_ctx* c, int32_t rounds, double* sectors_per_second) {
+    REQUIRE_CTX(c); REQUIRE_PTR(sectors_per_second);
+    if (rounds < 1 || rounds > (1 << 16)) return vxrt_fail(VXRT_E_INVALID, "gather_peak: rounds out of range");
+    return vxrt_launch_gather_peak(c, rounds, sectors_per_second);
+}
+int vxrt_cuda_probe_read(vxrt_ctx* c, double* total_ms, int64_t* launches, vxrt_trace_stats* stats, int32_t reset) {
+    REQUIRE_CTX(c);
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < c->probe_used; i += 2) {
+        float t = 0.0f;
+        VX_CUDA(cudaEventElapsedTime(&t, c->probe_ev[i], c->probe_ev[i + 1]));
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)(c->probe_used / 2);
+    if (stats) {
+        TraceStatsDev h;
+        VX_CUDA(cudaMemcpy(&h, c->d_stats + 1, sizeof(h), cudaMemcpyDeviceToHost));
+        stats->rays = h.rays + c->probe_acc.rays; stats->iterations = h.iterations + c->probe_acc.iterations;
+        stats->dda_steps = h.dda_steps + c->probe_acc.dda_steps; stats->hits = h.hits + c->probe_acc.hits;
+    }
+    if (reset) {
+        c->probe_used = 0;
+        c->probe_acc = TraceStatsDev{0, 0, 0, 0};
+        VX_CUDA(cudaMemsetAsync(c->d_stats + 1, 0, sizeof(TraceStatsDev), c->stream));
+    }
     return VXRT_OK;
 }
 

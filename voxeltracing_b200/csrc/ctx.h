@@ -92,8 +92,15 @@ struct vxrt_ctx {
     cudaEvent_t att_read_done[VXRT_ATT_COUNT] = {};  // recorded on `copy_stream` after the copy
     bool att_read_pending[VXRT_ATT_COUNT] = {};
 
-    TraceStatsDev* d_stats = nullptr;
+    TraceStatsDev* d_stats = nullptr;  // [0] every trace kernel except the probed one, [1] the probed kernel
     bool stats_on = false;
+
+    // kernel probe (vxrt_cuda_set_option "probe", vxrt_cuda_probe_read): CUDA-event pairs around every launch of the
+    // GI path-ray trace kernel, so bench.py can report the dominant kernel's own duration, live, outside a profiler
+    bool probe_on = false;
+    std::vector<cudaEvent_t> probe_ev;  // pairs
+    size_t probe_used = 0;              // events consumed since the last read
+    TraceStatsDev probe_acc = {0, 0, 0, 0};  // statistics of the probed kernel folded in by stats_read(reset) since the last probe_read
 
     GridView grid() const {
         GridView g;
@@ -111,6 +118,8 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
         if (_rc != VXRT_OK) return _rc;                            \
     } while (0)
 
+cudaEvent_t vxrt_probe_event(vxrt_ctx* c);  // next pooled event (nullptr when the probe is off or on error)
+
 // kernel launchers (one per .cu)
 int vxrt_launch_distance_field(vxrt_ctx* c);
 int vxrt_launch_edit_blocks(vxrt_ctx* c, const int32_t* d_edits, int n);
@@ -119,6 +128,7 @@ int vxrt_launch_df_slab_phase_b(vxrt_ctx* c, int slab, int nslabs, const int* d_
                                 const void* last_planes);
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
 int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
+int vxrt_launch_gather_peak(vxrt_ctx* c, int rounds, double* sectors_per_second);
 int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int n, int max_iter, vxrt_ray_hit* d_hits);
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);
 int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, const uint8_t* rgba8);

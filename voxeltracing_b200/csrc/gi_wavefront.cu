@@ -387,10 +387,14 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     if (!a.sun_stronger) max_spp *= 2;
     const bool st = c->stats_on;
     cudaStream_t s = c->stream;
+    // the path-ray kernel is the probed kernel: its own stats slot, event pairs around each launch when the probe is on
 #define TRACE_PATHS(list, cnt, iters)                                                                                     \
     do {                                                                                                                  \
-        if (st) wf_trace_paths_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);            \
-        else wf_trace_paths_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats);              \
+        cudaEvent_t e0 = vxrt_probe_event(c), e1 = vxrt_probe_event(c);                                                   \
+        if (e0 && e1) cudaEventRecord(e0, s);                                                                             \
+        if (st) wf_trace_paths_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1); \
+        else wf_trace_paths_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1);   \
+        if (e0 && e1) cudaEventRecord(e1, s);                                                                             \
     } while (0)
 #define TRACE_SHADOW()                                                                                                    \
     do {                                                                                                                  \

@@ -306,3 +306,50 @@ int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int 
     c->launches += 1;
     return VXRT_OK;
 }
+
+// ---- gather roof (vxrt_cuda_gather_peak) -----------------------------------------------------------------
+// The operative roof of the traversal is the rate at which the memory system serves independent 1-byte loads
+// from an L2-resident grid (each moves one 32-byte sector).  This kernel measures it on the distance field
+// itself: every thread issues batches of 8 independent loads at hashed addresses (no reuse: L1 cannot help).
+namespace {
+__global__ void __launch_bounds__(256) gather_peak_kernel(const uint8_t* __restrict__ buf, unsigned n, int rounds, unsigned* __restrict__ sink) {
+    unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    unsigned acc = 0;
+    for (int r = 0; r < rounds; ++r) {
+        unsigned v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x = x * 1664525u + 1013904223u;
+            v[i] = __ldg(buf + __umulhi(x, n));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += v[i];
+    }
+    if (acc == 0xffffffffu) *sink = acc;  // keeps the loads alive
+}
+}  // namespace
+
+int vxrt_launch_gather_peak(vxrt_ctx* c, int rounds, double* sectors_per_second) {
+    cudaEvent_t e0, e1;
+    VX_CUDA(cudaEventCreate(&e0));
+    VX_CUDA(cudaEventCreate(&e1));
+    const int grid = c->sm_count * 8;
+    unsigned* sink = reinterpret_cast<unsigned*>(c->d_stats);  // never written: the guard value cannot occur
+    gather_peak_kernel<<<grid, 256, 0, c->stream>>>(c->d_df, (unsigned)c->nvox, 4, sink);  // warm-up: pull the grid into L2
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        VX_CUDA(cudaEventRecord(e0, c->stream));
+        gather_peak_kernel<<<grid, 256, 0, c->stream>>>(c->d_df, (unsigned)c->nvox, rounds, sink);
+        VX_CUDA(cudaEventRecord(e1, c->stream));
+        VX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        VX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)grid * 256.0 * rounds * 8.0 / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *sectors_per_second = best;
+    c->launches += 4;
+    return VXRT_OK;
+}

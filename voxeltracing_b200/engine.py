@@ -281,6 +281,18 @@ class Context:
     def stats_enable(self, on: bool):
         self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))
 
+    def gather_peak(self, rounds: int = 256) -> float:
+        """Measured 32-byte sectors / s for independent random 1-byte loads of the L2-resident distance field."""
+        r = C.c_double(0.0)
+        self._check(self._lib.vxrt_cuda_gather_peak(self._h, int(rounds), C.byref(r)))
+        return r.value
+
+    def probe_read(self, reset: bool = True) -> dict:
+        """Summed CUDA-event duration / launch count / traversal statistics of the probed kernel (set_option('probe', 1))."""
+        ms, n, s = C.c_double(0.0), C.c_int64(0), abi.TraceStats()
+        self._check(self._lib.vxrt_cuda_probe_read(self._h, C.byref(ms), C.byref(n), C.byref(s), int(reset)))
+        return {"ms": ms.value, "launches": n.value, "rays": s.rays, "iterations": s.iterations}
+
     def stats_read(self, reset: bool = True) -> dict:
         s = abi.TraceStats()
         self._check(self._lib.vxrt_cuda_stats_read(self._h, C.byref(s), int(reset)))
