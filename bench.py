@@ -249,15 +249,32 @@ def run_reference_arm(args, wl, rank):
                          "sample": f"rows [{band[0]},{band[0] + band[1]}) of each {wl['width']}x{wl['height']} frame (every pass restricted to the band), {n} frames"},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
 
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, which prints its version
+    banner to stdout) writes to fd 1 has been redirected to stderr by quiet_stdout()."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -546,7 +563,7 @@ def main():
                                     "sample": f"rows [{band[0]},{band[0] + band[1]}) of {n} frames of the same camera path"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
 
     ctx.close()
     if world_size > 1:
