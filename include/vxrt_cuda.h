@@ -176,8 +176,10 @@ typedef struct vxrt_primary_params {
     float jitter[2];           /* u_CurrentTAAJitter */
     int32_t jitter_on;         /* u_JitterSceneForTAA */
     int32_t render_distance;   /* u_RenderDistance (iteration cap, 350) */
-    int32_t alpha_test;        /* u_ShouldAlphaTest (must be 0: off by default, Pipeline.cpp:146) */
+    int32_t alpha_test;        /* u_ShouldAlphaTest: VoxelTraversalDF_AlphaTest (InitialRayTraceFrag.glsl:189-305); off by
+                                  default (Pipeline.cpp:146); needs set_block_data and the albedo texture array */
     vxrt_tile tile;
+    float fov;                 /* u_FOV in degrees (Pipeline.cpp:2073); only read when alpha_test != 0 */
 } vxrt_primary_params;
 int vxrt_cuda_initial_trace(vxrt_ctx* ctx, const vxrt_primary_params* p);
 
@@ -191,9 +193,10 @@ typedef struct vxrt_shadow_params {
     int32_t current_frame;     /* u_CurrentFrame */
     float halton[2];           /* u_Halton */
     int32_t soft_shadows;      /* u_ContactHardeningShadows */
-    int32_t alpha_test;        /* u_ShouldAlphaTest (must be 0) */
+    int32_t alpha_test;        /* u_ShouldAlphaTest (ShadowRayTraceFrag.glsl:105-220, Pipeline.cpp:2913); off by default */
     int32_t max_iterations;    /* loop cap; the shader uses u_RenderDistance-less constant 350 */
     vxrt_tile tile;
+    float fov;                 /* u_FOV in degrees (Pipeline.cpp:2914); only read when alpha_test != 0 */
 } vxrt_shadow_params;
 int vxrt_cuda_shadow_trace(vxrt_ctx* ctx, const vxrt_shadow_params* p);
 

@@ -179,6 +179,7 @@ def _scene_sigs(L):
     L.vxo_scene_create.restype = vp
     L.vxo_scene_create.argtypes = [P(World)]
     L.vxo_scene_destroy.argtypes = [vp]
+    L.vxo_bind_alpha_scene.argtypes = [vp]
     L.vxo_scene_set_block_data.argtypes = [vp, vp]
     L.vxo_scene_set_blue_noise.argtypes = [vp, vp, i32]
     L.vxo_scene_set_texture_array.argtypes = [vp, i32, i32, i32, i32, vp]
@@ -216,6 +217,22 @@ class OracleScene:
     def set_block_data(self, table):
         t = np.ascontiguousarray(table, dtype=np.int32)
         self.L.vxo_scene_set_block_data(self.h, _p(t))
+
+    # primary / shadow passes with this scene's block table and albedo array bound for the alpha-tested traversal
+    # (params.alpha_test != 0; VoxelTraversalDF_AlphaTest)
+    def initial_trace(self, params, want_stats: bool = False):
+        self.L.vxo_bind_alpha_scene(self.h)
+        try:
+            return self.world.initial_trace(params, want_stats)
+        finally:
+            self.L.vxo_bind_alpha_scene(None)
+
+    def shadow_trace(self, params, g_t, g_normal, blue_rgba, want_stats: bool = False):
+        self.L.vxo_bind_alpha_scene(self.h)
+        try:
+            return self.world.shadow_trace(params, g_t, g_normal, blue_rgba, want_stats)
+        finally:
+            self.L.vxo_bind_alpha_scene(None)
 
     def set_blue_noise(self, data):
         d = np.ascontiguousarray(data, dtype=np.int32)

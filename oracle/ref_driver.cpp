@@ -112,6 +112,26 @@ void vxref_distance_field(const uint8_t* blocks, uint8_t* df) {
 }
 #endif
 
+/* ---- scene resources shared by the alpha-tested traversal and the material / GI / reflection shaders ---- */
+static struct RefScene {
+    const uint8_t* blocks = nullptr; const uint8_t* df = nullptr;
+    int32_t block_data[6 * 128];
+    std::vector<int32_t> blue;
+    vxo::TexArray tex[4];
+    std::vector<float> sky; vxo::TexCube cube;
+} g_scene;
+
+void vxref_set_world(const uint8_t* blocks, const uint8_t* df) { g_scene.blocks = blocks; g_scene.df = df; }
+void vxref_set_block_data(const int32_t* t) { memcpy(g_scene.block_data, t, sizeof(g_scene.block_data)); }
+void vxref_set_blue_noise(const int32_t* d, int32_t n) { g_scene.blue.assign(d, d + n); }
+void vxref_set_texture_array(int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba) {
+    vxo::texarray_build(g_scene.tex[kind], rgba, layers, w, h, kind == 0);
+}
+void vxref_set_skymap(int32_t res, const float* f) {
+    g_scene.sky.assign(f, f + (size_t)6 * res * res * 3);
+    g_scene.cube.data = g_scene.sky.data(); g_scene.cube.res = res;
+}
+
 static inline void rows_of(const vxrt_tile& t, int H, int* r0, int* r1) {
     if (t.rows <= 0) { *r0 = 0; *r1 = H; } else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > H) *r1 = H; }
 }
@@ -127,11 +147,15 @@ void vxref_initial_trace(const uint8_t* blocks, const uint8_t* df, const vxrt_pr
     S::u_InverseView.load(p->inv_view);
     S::u_InverseProjection.load(p->inv_projection);
     S::u_Dimensions = vec2((float)p->width, (float)p->height);
-    S::u_ShouldAlphaTest = false;
+    S::u_ShouldAlphaTest = p->alpha_test != 0;   /* Pipeline.cpp:2076 */
+    if (p->alpha_test) {
+        S::u_AlbedoTextures.t = &g_scene.tex[0];
+        S::BlockAlbedoData.data = g_scene.block_data; S::BlockTransparentData.data = g_scene.block_data + 512;
+    }
     S::u_RenderDistance = p->render_distance;
     S::u_JitterSceneForTAA = p->jitter_on != 0;
     S::u_CurrentTAAJitter = vec2(p->jitter[0], p->jitter[1]);
-    S::u_FOV = 90.0f;
+    S::u_FOV = p->alpha_test ? p->fov : 90.0f;   /* Pipeline.cpp:2073; only the alpha test reads it */
     S::u_Time = 0.0f;
     S::u_CurrentFrame = 0;
     const int W = p->width, H = p->height;
@@ -173,11 +197,15 @@ void vxref_shadow_trace(const uint8_t* blocks, const uint8_t* df, const vxrt_sha
     S::u_InverseProjection.load(p->inv_projection);
     S::u_CurrentFrame = p->current_frame;
     S::u_ContactHardeningShadows = p->soft_shadows != 0;
-    S::u_ShouldAlphaTest = false;
+    S::u_ShouldAlphaTest = p->alpha_test != 0;   /* Pipeline.cpp:2913 */
+    if (p->alpha_test) {
+        S::u_AlbedoTextures.t = &g_scene.tex[0];
+        S::BlockAlbedoData.data = g_scene.block_data; S::BlockTransparentData.data = g_scene.block_data + 512;
+    }
     S::u_Dimensions = vec2((float)p->width, (float)p->height);
     S::u_Halton = vec2(p->halton[0], p->halton[1]);
     S::u_Time = 0.0f;
-    S::u_FOV = 90.0f;
+    S::u_FOV = p->alpha_test ? p->fov : 90.0f;   /* Pipeline.cpp:2914 */
     S::u_DoFullTrace = true;
     const int W = p->width, H = p->height;
     int r0, r1;
@@ -197,26 +225,6 @@ void vxref_shadow_trace(const uint8_t* blocks, const uint8_t* df, const vxrt_sha
 }
 #endif
 
-
-/* ---- scene resources shared by the material / GI / reflection shaders ---- */
-static struct RefScene {
-    const uint8_t* blocks = nullptr; const uint8_t* df = nullptr;
-    int32_t block_data[6 * 128];
-    std::vector<int32_t> blue;
-    vxo::TexArray tex[4];
-    std::vector<float> sky; vxo::TexCube cube;
-} g_scene;
-
-void vxref_set_world(const uint8_t* blocks, const uint8_t* df) { g_scene.blocks = blocks; g_scene.df = df; }
-void vxref_set_block_data(const int32_t* t) { memcpy(g_scene.block_data, t, sizeof(g_scene.block_data)); }
-void vxref_set_blue_noise(const int32_t* d, int32_t n) { g_scene.blue.assign(d, d + n); }
-void vxref_set_texture_array(int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba) {
-    vxo::texarray_build(g_scene.tex[kind], rgba, layers, w, h, kind == 0);
-}
-void vxref_set_skymap(int32_t res, const float* f) {
-    g_scene.sky.assign(f, f + (size_t)6 * res * res * 3);
-    g_scene.cube.data = g_scene.sky.data(); g_scene.cube.res = res;
-}
 
 static inline void bind3d(sampler3D& s, const uint8_t* d) { s.data = d; s.w = 384; s.h = 128; s.d = 384; }
 static inline void bind2d(sampler2D& s, const float* d, int w, int h, int ch, bool linear) { s.data = d; s.w = w; s.h = h; s.ch = ch; s.linear = linear; }

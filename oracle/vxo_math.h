@@ -41,6 +41,7 @@ static inline v2 operator/(v2 a, v2 b) { return V2(a.x / b.x, a.y / b.y); }
 static inline float& idx(v3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 static inline float idx(const v3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 static inline int& idx(i3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+static inline int idx(const i3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
 /* GLSL/glm min/max/clamp/mix */
 static inline float gmin(float a, float b) { return (b < a) ? b : a; }

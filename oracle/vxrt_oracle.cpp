@@ -141,25 +141,7 @@ extern "C" void vxo_distance_field_brute(const uint8_t* blocks, int32_t nx, int3
  * Traversal
  * ---------------------------------------------------------------------------------------- */
 
-/* IsInVolume (InitialRayTraceFrag.glsl:68-77), applied to an ivec3 converted to vec3 */
-static inline bool in_volume(const vxo_world* w, int x, int y, int z) {
-    float px = (float)x, py = (float)y, pz = (float)z;
-    if (px < 0.0f || py < 0.0f || pz < 0.0f || px > (float)(w->nx - 1) || py > (float)(w->ny - 1) ||
-        pz > (float)(w->nz - 1))
-        return false;
-    return true;
-}
-/* GetVoxel (:79-87) — returns the raw texel code (id), the shader's value is id/255 */
-static inline int get_voxel(const vxo_world* w, int x, int y, int z) {
-    if (in_volume(w, x, y, z)) return w->blocks[x + (size_t)y * w->nx + (size_t)z * w->nx * w->ny];
-    return 0;
-}
-/* GetDistance (:94-102) * 255, ToConservativeEuclidean (:89-92), int(floor()) (:331-333) */
-static inline int euclidean_step(int k) {
-    float Dist = unorm8_to_float(k) * 255.0f;
-    float ce = (Dist == 1.0f) ? 1.0f : Dist * 0.57735026918f;
-    return (int)floorf(ce);
-}
+#include "vxo_grid.h"
 extern "C" void vxo_step_table(int32_t* out256) {
     for (int k = 0; k < 256; ++k) out256[k] = euclidean_step(k);
 }
@@ -311,6 +293,14 @@ static inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
     else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
 }
 
+static const vxo_scene* g_alpha_scene = nullptr;
+extern "C" void vxo_bind_alpha_scene(const vxo_scene* s) { g_alpha_scene = s; }
+extern "C" float vxo_alpha_g_k(float fov_degrees, int32_t width) {
+    /* radians(x) = x * pi/180 as a float constant; tanf from libm (the CUDA library computes g_K on the host with
+     * the same expression, so the device never evaluates tan) */
+    return 1.0f / (tanf((fov_degrees * 0.01745329251994329577f) / (2.0f * (float)width)) * 2.0f);
+}
+
 /* main() (InitialRayTraceFrag.glsl:434-496); attachment formats Pipeline.cpp:1142 */
 extern "C" void vxo_initial_trace(const vxo_world* w, const vxrt_primary_params* p, uint16_t* t_half,
                                   uint8_t* normal_u8, uint8_t* block_u8, float* inv_t, float* t32,
@@ -341,7 +331,13 @@ extern "C" void vxo_initial_trace(const vxo_world* w, const vxrt_primary_params*
             }
             vxo_hit h;
             float o[3] = {ro.x, ro.y, ro.z}, d[3] = {dir.x, dir.y, dir.z};
-            float t = vxo_traverse(w, o, d, p->render_distance, &h);
+            float t;
+            if (p->alpha_test && g_alpha_scene) {
+                const float viewer[3] = {p->inv_view[12], p->inv_view[13], p->inv_view[14]};
+                t = vxo_traverse_alpha(g_alpha_scene, o, d, p->render_distance, viewer, vxo_alpha_g_k(p->fov, W), 0, &h);
+            } else {
+                t = vxo_traverse(w, o, d, p->render_distance, &h);
+            }
             /* id is the texel value block/255; `id > 0` <=> block > 0.  On a miss id/normal are
              * uninitialised in the shader but t = -1 makes `intersect` false regardless.        */
             bool intersect = t > 0.0f && h.block > 0;
@@ -457,7 +453,12 @@ extern "C" void vxo_shadow_trace(const vxo_world* w, const vxrt_shadow_params* p
             if (Dist > 0.0f) {
                 vxo_hit h;
                 float oo[3] = {o.x, o.y, o.z}, dd[3] = {RayDirection.x, RayDirection.y, RayDirection.z};
-                T = vxo_traverse(w, oo, dd, p->max_iterations, &h);
+                if (p->alpha_test && g_alpha_scene) {
+                    const float viewer[3] = {p->inv_view[12], p->inv_view[13], p->inv_view[14]};
+                    T = vxo_traverse_alpha(g_alpha_scene, oo, dd, p->max_iterations, viewer, vxo_alpha_g_k(p->fov, W), 1, &h);
+                } else {
+                    T = vxo_traverse(w, oo, dd, p->max_iterations, &h);
+                }
                 s_rays += 1; s_it += h.iterations; s_dda += h.dda_steps; s_hits += (T > 0.0f) ? 1 : 0;
             }
             shadow_u8[i] = float_to_unorm8((T > 0.0f || block_at > 0) ? 1.0f : 0.0f);

@@ -58,6 +58,17 @@ typedef struct vxo_hit {
 float vxo_traverse(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_iter,
                    vxo_hit* hit);
 void vxo_traverse_batch(const vxo_world* w, const float* origins, const float* dirs, int32_t n, int32_t max_iter, vxo_hit* hits);
+/* VoxelTraversalDF_AlphaTest + StopRay + CalculateUV (InitialRayTraceFrag.glsl:189-305,498-540 with shadow_variant == 0,
+ * ShadowRayTraceFrag.glsl:105-220 with shadow_variant == 1).  viewer = u_InverseView[3].xyz, g_K as main() computes it.
+ * Needs the scene's block table and albedo array.                                             */
+struct vxo_scene;
+float vxo_traverse_alpha(const struct vxo_scene* s, const float origin[3], const float dir[3], int32_t max_iter,
+                         const float viewer[3], float g_K, int32_t shadow_variant, vxo_hit* hit);
+/* the scene the primary / shadow passes take their alpha-test resources from while params->alpha_test != 0
+ * (process-wide; the reference binds them as GL state the same way) */
+void vxo_bind_alpha_scene(const struct vxo_scene* s);
+/* g_K = 1 / (tan(radians(fov) / (2 * width)) * 2)  (InitialRayTraceFrag.glsl:438, ShadowRayTraceFrag.glsl:419) */
+float vxo_alpha_g_k(float fov_degrees, int32_t width);
 /* plain Amanatides-Woo DDA returning the first solid voxel (self-check).
  * returns 1 and fills voxel[3] on hit, 0 on leaving the volume / max_steps.                 */
 int32_t vxo_plain_dda(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_steps,

@@ -7,6 +7,7 @@
 #include "vxrt_oracle.h"
 #include "vxo_math.h"
 #include "vxo_texture.h"
+#include "vxo_grid.h"
 
 #include <vector>
 #ifdef _OPENMP
@@ -110,6 +111,118 @@ static inline void calculate_uv(v3 p, v3 n, v2* uv) {
     else if (cmp3(n, V3(1, 0, 0)) || cmp3(n, V3(-1, 0, 0))) *uv = fract2(p.z, p.y);
     else if (cmp3(n, V3(0, 0, 1)) || cmp3(n, V3(0, 0, -1))) *uv = fract2(p.x, p.y);
 }
+/* ------------------------------------------------------------------------------------------------
+ * Alpha-tested traversal (off by default in the engine, Pipeline.cpp:146-147)
+ * ---------------------------------------------------------------------------------------------- */
+/* StopRay (InitialRayTraceFrag.glsl:189-203; ShadowRayTraceFrag.glsl:105-118 flips only v and biases the LOD by -2).
+ * `block` is the raw texel byte; GetBlockID clamps it to 0..127.  An N that matches no axis (RaySign == 0 on MinIdx)
+ * leaves uv undefined in the shader: pinned to (0, 0).                                                       */
+static inline bool stop_ray(const vxo_scene* s, v3 P, v3 N, int block, v3 viewer, float g_K, bool shadow_variant) {
+    const int id = iclamp(block, 0, 127);
+    if (s->block_data[4 * 128 + id] == 0) return true;
+    v2 uv = V2(0.0f, 0.0f);
+    calculate_uv(P, N, &uv);
+    uv.y = 1.0f - uv.y;
+    if (!shadow_variant) uv.x = 1.0f - uv.x;
+    float D = distance(P, viewer);
+    int LOD = cvt_trunc(log2f(512.0f / (1.0f / D * g_K)));
+    float lod = shadow_variant ? gclamp((float)LOD - 2.0f, 0.0f, 8.0f) : gclamp((float)LOD, 0.0f, 8.0f);
+    float Alpha = texarray_sample(s->tex[VXRT_TEX_ALBEDO], uv.x, uv.y, (float)s->block_data[0 * 128 + id], lod).w;
+    return Alpha > 0.975f;
+}
+
+/* one DDA step (InitialRayTraceFrag.glsl:233-243 == :268-282) */
+static inline void alpha_dda_step(v3& origin, v3 direction, i3 RaySign, i3 Step01, int& MinIdx) {
+    i3 G = {cvt_trunc(origin.x), cvt_trunc(origin.y), cvt_trunc(origin.z)};
+    v3 W = origin - V3((float)G.x, (float)G.y, (float)G.z);
+    v3 inv = V3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    v3 DF = (V3((float)Step01.x, (float)Step01.y, (float)Step01.z) - W) * inv;
+    MinIdx = (DF.x < DF.y && RaySign.x != 0) ? ((DF.x < DF.z || RaySign.z == 0) ? 0 : 2) : ((DF.y < DF.z || RaySign.z == 0) ? 1 : 2);
+    idx(G, MinIdx) += idx(RaySign, MinIdx);
+    W = W + direction * idx(DF, MinIdx);
+    idx(W, MinIdx) = (float)(1 - idx(Step01, MinIdx));
+    origin = V3((float)G.x, (float)G.y, (float)G.z) + W;
+    idx(origin, MinIdx) += (float)idx(RaySign, MinIdx) * 0.0001f;
+}
+
+extern "C" float vxo_traverse_alpha(const vxo_scene* s, const float origin0[3], const float dir[3], int32_t max_iter,
+                                    const float viewer3[3], float g_K, int32_t shadow_variant, vxo_hit* hit) {
+    const vxo_world* w = &s->world;
+    const v3 viewer = V3(viewer3[0], viewer3[1], viewer3[2]);
+    const v3 initial_origin = V3(origin0[0], origin0[1], origin0[2]);
+    v3 origin = initial_origin;
+    const v3 direction = V3(dir[0], dir[1], dir[2]);
+    bool Intersection = false;
+    int MinIdx = 0;
+    const i3 RaySign = {gsign(direction.x), gsign(direction.y), gsign(direction.z)};
+    const i3 Step01 = {(1 + RaySign.x) >> 1, (1 + RaySign.y) >> 1, (1 + RaySign.z) >> 1};
+    int iters = 0, dda = 0;
+    float t = -1.0f;
+    int block = 0;
+    v3 normal = V3(0.0f);
+    bool returned = false;
+
+    for (int itr = 0; itr < max_iter && !returned; ++itr) {
+        int lx = cvt_floor(origin.x), ly = cvt_floor(origin.y), lz = cvt_floor(origin.z);
+        if (!in_volume(w, lx, ly, lz)) {
+            Intersection = false;
+            break;
+        }
+        iters++;
+        int k = w->df[lx + (size_t)ly * w->nx + (size_t)lz * w->nx * w->ny];
+        int Euclidean = euclidean_step(k);
+        if (Euclidean == 0) {
+            v3 tn = V3(0.0f);
+            idx(tn, MinIdx) = (float)(-idx(RaySign, MinIdx));
+            int bt = get_voxel(w, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z));
+            if (stop_ray(s, origin, tn, bt, viewer, g_K, shadow_variant != 0)) break;
+            for (int i = 0; i < 4; ++i) {
+                alpha_dda_step(origin, direction, RaySign, Step01, MinIdx);
+                dda++;
+                int b2 = get_voxel(w, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z));
+                if (b2 > 0) {
+                    v3 tn2 = V3(0.0f);
+                    idx(tn2, MinIdx) = (float)(-idx(RaySign, MinIdx));
+                    if (stop_ray(s, origin, tn2, b2, viewer, g_K, shadow_variant != 0)) {
+                        normal = V3(0.0f);
+                        idx(normal, MinIdx) = (float)(-idx(RaySign, MinIdx));
+                        block = b2;
+                        t = block > 0 ? distance(origin, initial_origin) : -1.0f;
+                        returned = true;  /* `return` inside the loop (:251-256) */
+                        break;
+                    }
+                }
+            }
+            if (returned) break;
+        }
+        if (Euclidean == 1) {
+            alpha_dda_step(origin, direction, RaySign, Step01, MinIdx);
+            dda++;
+            Intersection = true;
+        } else {
+            /* also taken after an unresolved Euclidean == 0 block: int(0 - 1) * direction steps one unit BACK (:285-288) */
+            origin = origin + (float)(Euclidean - 1) * direction;
+        }
+    }
+    if (!returned && Intersection) {
+        normal = V3(0.0f);
+        idx(normal, MinIdx) = (float)(-idx(RaySign, MinIdx));
+        block = get_voxel(w, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z));
+        t = block > 0 ? distance(origin, initial_origin) : -1.0f;
+    }
+    if (hit) {
+        hit->t = t;
+        hit->normal[0] = normal.x; hit->normal[1] = normal.y; hit->normal[2] = normal.z;
+        hit->end[0] = origin.x; hit->end[1] = origin.y; hit->end[2] = origin.z;
+        hit->block = block;
+        hit->intersection = (returned || Intersection) ? 1 : 0;
+        hit->min_idx = MinIdx;
+        hit->iterations = iters;
+        hit->dda_steps = dda;
+    }
+    return t;
+}
+
 /* BasicSaturation (ColorPassFrag.glsl:1228-1233) */
 static inline v3 basic_saturation(v3 c, float adj) {
     float l = dot(c, V3(0.2125f, 0.7154f, 0.0721f));

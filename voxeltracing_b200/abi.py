@@ -39,6 +39,7 @@ class PrimaryParams(C.Structure):
         ("render_distance", C.c_int32),
         ("alpha_test", C.c_int32),
         ("tile", Tile),
+        ("fov", C.c_float),
     ]
 
 
@@ -55,6 +56,7 @@ class ShadowParams(C.Structure):
         ("alpha_test", C.c_int32),
         ("max_iterations", C.c_int32),
         ("tile", Tile),
+        ("fov", C.c_float),
     ]
 
 

@@ -376,7 +376,9 @@ int vxrt_cuda_initial_trace(vxrt_ctx* c, const vxrt_primary_params* p) {
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "initial_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
-    if (p->alpha_test) return vxrt_fail(VXRT_E_UNSUPPORTED, "alpha-tested traversal (InitialRayTraceFrag.glsl:189-305) is off by default in the reference and not implemented");
+    if (p->alpha_test && !c->tex_set[VXRT_TEX_ALBEDO])
+        return vxrt_fail(VXRT_E_STATE, "alpha-tested traversal needs the albedo texture array (vxrt_cuda_set_texture_array) and the block table");
+    if (p->alpha_test && !(p->fov > 0.0f && p->fov < 180.0f)) return vxrt_fail(VXRT_E_INVALID, "alpha test: fov must be in (0, 180) degrees");
     if (p->render_distance < 0) return vxrt_fail(VXRT_E_INVALID, "render_distance < 0");
     return vxrt_launch_initial_trace(c, *p);
 }
@@ -412,7 +414,9 @@ int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "shadow_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
-    if (p->alpha_test) return vxrt_fail(VXRT_E_UNSUPPORTED, "alpha-tested traversal is not implemented");
+    if (p->alpha_test && !c->tex_set[VXRT_TEX_ALBEDO])
+        return vxrt_fail(VXRT_E_STATE, "alpha-tested traversal needs the albedo texture array (vxrt_cuda_set_texture_array) and the block table");
+    if (p->alpha_test && !(p->fov > 0.0f && p->fov < 180.0f)) return vxrt_fail(VXRT_E_INVALID, "alpha test: fov must be in (0, 180) degrees");
     if (!c->att[VXRT_ATT_INITIAL_T].ptr || !c->att[VXRT_ATT_INITIAL_NORMAL].ptr)
         return vxrt_fail(VXRT_E_STATE, "shadow_trace consumes the primary G-buffer: run initial_trace first");
     if (p->soft_shadows && !c->d_blue_tex) return vxrt_fail(VXRT_E_STATE, "soft shadows need set_blue_noise_texture");

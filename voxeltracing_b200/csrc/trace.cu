@@ -8,6 +8,7 @@
 // voxels (coherent 32-byte sectors of the x-fastest grids, which are L2/L1 resident).
 #include "ctx.h"
 #include "traverse.cuh"
+#include "traverse_alpha.cuh"
 
 namespace {
 
@@ -44,13 +45,7 @@ struct ShadowArgs {
     uint16_t* transversal;
 };
 
-// GetRayStuff (InitialRayTraceFrag.glsl:398-416) / GetRayDirectionAt (ShadowRayTraceFrag.glsl:303-308)
-VXD f3 ray_direction_at(const float* inv_view, const float* inv_proj, f2 ss) {
-    f4 clip = F4(ss.x * 2.0f - 1.0f, ss.y * 2.0f - 1.0f, -1.0f, 1.0f);
-    f4 e = mat4_mul(inv_proj, clip);
-    f4 r = mat4_mul(inv_view, F4(e.x, e.y, -1.0f, 0.0f));
-    return F3(r.x, r.y, r.z);
-}
+// GetRayStuff (InitialRayTraceFrag.glsl:398-416) / GetRayDirectionAt (ShadowRayTraceFrag.glsl:303-308): ray_direction_at of shading.cuh
 
 // IntersectBox (InitialRayTraceFrag.glsl:418-432)
 VXD f2 intersect_box(f3 ro, f3 invrd, f3 rad) {
@@ -82,9 +77,9 @@ VXD void pixel_of_thread(int& px, int& py, int row0) {
     py = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
 }
 
-template <bool STATS>
+template <bool STATS, bool ALPHA>
 __global__ void __launch_bounds__(256) initial_trace_kernel(GridView g, const __grid_constant__ PrimaryArgs a,
-                                                            TraceStatsDev* stats) {
+                                                            TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
     pixel_of_thread(px, py, a.row0);
     const bool active = px < a.width && py < a.row1;
@@ -105,7 +100,9 @@ __global__ void __launch_bounds__(256) initial_trace_kernel(GridView g, const __
             AddT = box.x + 0.5f;
             ro = ro + dir * AddT;
         }
-        TraceResult r = traverse_df<STATS>(g, ro, dir, a.max_iter, &ls);
+        TraceResult r;
+        if (ALPHA) r = traverse_df_alpha<STATS>(g, alpha, ro, dir, a.max_iter, &ls);
+        else r = traverse_df<STATS>(g, ro, dir, a.max_iter, &ls);
         const bool intersect = r.t > 0.0f && r.block > 0;
         float t = r.t + AddT * (intersect ? 1.0f : 0.0f);
         const size_t i = (size_t)py * a.width + px;
@@ -158,9 +155,9 @@ VXD f3 sample_cone(f2 Xi, float CosThetaMax) {
     return F3(SinTheta * cosf(phi), SinTheta * sinf(phi), CosTheta);
 }
 
-template <bool STATS>
+template <bool STATS, bool ALPHA>
 __global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __grid_constant__ ShadowArgs a,
-                                                           TraceStatsDev* stats) {
+                                                           TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
     pixel_of_thread(px, py, a.row0);
     const bool active = px < a.width && py < a.row1;
@@ -203,7 +200,9 @@ __global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __g
                 const int block_at = get_voxel(g, cvt_floor(o.x), cvt_floor(o.y), cvt_floor(o.z));
                 float T = -1.0f;
                 if (Dist > 0.0f) {
-                    TraceResult r = traverse_df<STATS>(g, o, rd, a.max_iter, &ls);
+                    TraceResult r;
+                    if (ALPHA) r = traverse_df_alpha<STATS>(g, alpha, o, rd, a.max_iter, &ls);
+                    else r = traverse_df<STATS>(g, o, rd, a.max_iter, &ls);
                     T = r.t;
                 }
                 o_shadow = (T > 0.0f || block_at > 0) ? 255 : 0;
@@ -224,6 +223,18 @@ inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
 
 }  // namespace
 
+// u_AlbedoTextures / SSBO 0 / u_FOV of the alpha-tested traversal.  g_K (InitialRayTraceFrag.glsl:438,
+// ShadowRayTraceFrag.glsl:419) is evaluated here on the host: radians(x) = x * pi/180 as a float constant, libm tanf.
+static AlphaCtx make_alpha_ctx(const vxrt_ctx* c, const float* inv_view, float fov, int width, int shadow_variant) {
+    AlphaCtx x;
+    x.albedo = c->tex[VXRT_TEX_ALBEDO];
+    x.block_data = c->d_block_data;
+    x.viewer.x = inv_view[12]; x.viewer.y = inv_view[13]; x.viewer.z = inv_view[14];
+    x.g_K = 1.0f / (tanf((fov * 0.01745329251994329577f) / (2.0f * (float)width)) * 2.0f);
+    x.shadow_variant = shadow_variant;
+    return x;
+}
+
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p) {
     int rc;
     if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_INITIAL_T, p.width, p.height, 2))) return rc;
@@ -243,10 +254,14 @@ int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p) {
     a.inv_t = (float*)c->att[VXRT_ATT_INITIAL_INVT].ptr;
     if (a.row1 <= a.row0) return VXRT_OK;
     dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
-    if (c->stats_on)
-        initial_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
-    else
-        initial_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    const AlphaCtx ax = make_alpha_ctx(c, p.inv_view, p.fov, p.width, 0);
+    if (p.alpha_test) {
+        if (c->stats_on) initial_trace_kernel<true, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+        else initial_trace_kernel<false, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+    } else {
+        if (c->stats_on) initial_trace_kernel<true, false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+        else initial_trace_kernel<false, false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+    }
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;
@@ -274,10 +289,14 @@ int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p) {
     a.transversal = (uint16_t*)c->att[VXRT_ATT_SHADOW_TRANSVERSAL].ptr;
     if (a.row1 <= a.row0) return VXRT_OK;
     dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
-    if (c->stats_on)
-        shadow_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
-    else
-        shadow_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
+    const AlphaCtx ax = make_alpha_ctx(c, p.inv_view, p.fov, p.width, 1);
+    if (p.alpha_test) {
+        if (c->stats_on) shadow_trace_kernel<true, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+        else shadow_trace_kernel<false, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+    } else {
+        if (c->stats_on) shadow_trace_kernel<true, false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+        else shadow_trace_kernel<false, false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
+    }
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;

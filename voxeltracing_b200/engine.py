@@ -185,7 +185,8 @@ class Context:
         self._check(self._lib.vxrt_cuda_set_skymap(self._h, f.shape[1], _p(f)))
 
     # -- passes --
-    def initial_trace(self, cam, width: int, height: int, render_distance: int = 350, jitter=None, tile=(0, 0)):
+    def initial_trace(self, cam, width: int, height: int, render_distance: int = 350, jitter=None, tile=(0, 0),
+                      alpha_test: bool = False, fov: float = 90.0):
         p = abi.PrimaryParams()
         _fill(p.inv_view, cam.inv_view)
         _fill(p.inv_projection, cam.inv_projection)
@@ -194,13 +195,14 @@ class Context:
             p.jitter[0], p.jitter[1] = float(jitter[0]), float(jitter[1])
             p.jitter_on = 1
         p.render_distance = render_distance
-        p.alpha_test = 0
+        p.alpha_test = int(alpha_test)
+        p.fov = float(fov)
         p.tile.row0, p.tile.rows = tile
         self._check(self._lib.vxrt_cuda_initial_trace(self._h, C.byref(p)))
         return p
 
     def shadow_trace(self, cam, width: int, height: int, light_direction, frame: int = 0, halton=(0.0, 0.0),
-                     soft: bool = True, max_iterations: int = 350, tile=(0, 0)):
+                     soft: bool = True, max_iterations: int = 350, tile=(0, 0), alpha_test: bool = False, fov: float = 90.0):
         p = abi.ShadowParams()
         _fill(p.inv_view, cam.inv_view)
         _fill(p.inv_projection, cam.inv_projection)
@@ -209,7 +211,8 @@ class Context:
         p.current_frame = frame
         p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
         p.soft_shadows = int(soft)
-        p.alpha_test = 0
+        p.alpha_test = int(alpha_test)
+        p.fov = float(fov)
         p.max_iterations = max_iterations
         p.tile.row0, p.tile.rows = tile
         self._check(self._lib.vxrt_cuda_shadow_trace(self._h, C.byref(p)))
