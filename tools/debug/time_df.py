@@ -13,7 +13,8 @@ ctx.upload_world(blocks); ctx.generate_distance_field()
 ok = np.array_equal(ctx.download_distance_field(), ob.distance_field(blocks))
 print("bit-exact vs oracle:", ok)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for do_flush in (True, False):
+for stage, do_flush, sx, sy in ((0, True, 0, 0), (1, True, 0, 0), (2, True, 0, 0), (1, True, 1, 1), (1, True, 3, 1), (1, True, 1, 4), (1, True, 3, 2), (0, True, 1, 1)):
+    ctx.set_option("df_stage", stage); ctx.set_option("df_sx", sx); ctx.set_option("df_sy", sy)
     ts = []
     for _ in range(40):
         if do_flush: flush.zero_()
@@ -21,5 +22,8 @@ for do_flush in (True, False):
         a.record(stream); ctx.generate_distance_field(); b.record(stream); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     ts = np.array(ts[5:])
-    print(f"flush={do_flush}: median {np.median(ts):.1f} us  min {ts.min():.1f} us  -> {2*blocks.size/np.median(ts)/1e3:.0f} GB/s algorithmic")
+    print(f"stage={stage} sx={sx} sy={sy} flush={do_flush}: median {np.median(ts):.1f} us  min {ts.min():.1f} us  -> {2*blocks.size/np.median(ts)/1e3:.0f} GB/s algorithmic")
+ctx.set_option("df_stage", 0); ctx.set_option("df_sx", 0); ctx.set_option("df_sy", 0)
+ctx.generate_distance_field()
+print("bit-exact again:", np.array_equal(ctx.download_distance_field(), ob.distance_field(blocks)))
 ctx.close()

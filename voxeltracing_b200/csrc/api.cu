@@ -138,6 +138,9 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     REQUIRE_CTX(c); REQUIRE_PTR(name);
     if (!strcmp(name, "wavefront")) { c->wavefront = value != 0; return VXRT_OK; }
     if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
+    if (!strcmp(name, "df_sx")) { c->df_sx = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
+    if (!strcmp(name, "df_sy")) { c->df_sy = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
     return vxrt_fail(VXRT_E_INVALID, "unknown option '%s'", name);
 }
 int64_t vxrt_cuda_launch_count(vxrt_ctx* c) { return c ? c->launches : -1; }

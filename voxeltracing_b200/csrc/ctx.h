@@ -55,6 +55,8 @@ struct vxrt_ctx {
     uint8_t* d_df = nullptr;
     bool world_uploaded = false;
     bool df_valid = false;
+    int df_sx = 0, df_sy = 0;  // measurement aid: override the segment counts of the XY kernel (0 = automatic)
+    int df_stage = 0;  // measurement aid (set_option "df_stage"): 1 = XY kernel only, 2 = Z kernel only, 0 = both
 
     int32_t* d_block_data = nullptr;      // 6*128
     int32_t* d_blue_noise = nullptr;      // sobol ++ scramble ++ ranking

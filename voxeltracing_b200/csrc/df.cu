@@ -25,7 +25,13 @@ namespace {
 
 __device__ __forceinline__ unsigned even_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4240); }  // (b0, b2)
 __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4341); }   // (b1, b3)
-__device__ __forceinline__ unsigned pack_lanes(unsigned e, unsigned o) { return __byte_perm(e, o, 0x6240); }
+// lanes hold values < 256, so the pack is e + 256 * o: one IMAD on the FMA pipe.  Both kernels are bound by the
+// half-rate integer (ALU) pipe that VIADDMNMX / PRMT / LOP3 share (ncu: pipe_alu 62 %, math-pipe throttle the top
+// stall), so everything that can be a multiply-add is one.
+__device__ __forceinline__ unsigned pack_lanes(unsigned e, unsigned o) { return o * 256u + e; }
+__device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {
+    return (b3 * 256u + b2) * 65536u + (b1 * 256u + b0);
+}
 
 // solid ? 0 : maxd for the four bytes of w
 __device__ __forceinline__ unsigned seed_word(unsigned w, unsigned maxd4) {
@@ -36,30 +42,44 @@ __device__ __forceinline__ unsigned seed_word(unsigned w, unsigned maxd4) {
 
 // forward min-plus step through the four bytes of w (low byte first); c = running value
 __device__ __forceinline__ unsigned sweep_word_up(unsigned w, unsigned& c) {
-    const unsigned b0 = __viaddmin_u32(c, 1u, w & 0xffu);
-    const unsigned b1 = __viaddmin_u32(b0, 1u, (w >> 8) & 0xffu);
-    const unsigned b2 = __viaddmin_u32(b1, 1u, (w >> 16) & 0xffu);
-    const unsigned b3 = __viaddmin_u32(b2, 1u, w >> 24);
+    const unsigned b0 = __viaddmin_u32(c, 1u, __byte_perm(w, 0u, 0x4440));
+    const unsigned b1 = __viaddmin_u32(b0, 1u, __byte_perm(w, 0u, 0x4441));
+    const unsigned b2 = __viaddmin_u32(b1, 1u, __byte_perm(w, 0u, 0x4442));
+    const unsigned b3 = __viaddmin_u32(b2, 1u, __byte_perm(w, 0u, 0x4443));
     c = b3;
-    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    return pack_bytes(b0, b1, b2, b3);
 }
 __device__ __forceinline__ unsigned sweep_word_down(unsigned w, unsigned& c) {
-    const unsigned b3 = __viaddmin_u32(c, 1u, w >> 24);
-    const unsigned b2 = __viaddmin_u32(b3, 1u, (w >> 16) & 0xffu);
-    const unsigned b1 = __viaddmin_u32(b2, 1u, (w >> 8) & 0xffu);
-    const unsigned b0 = __viaddmin_u32(b1, 1u, w & 0xffu);
+    const unsigned b3 = __viaddmin_u32(c, 1u, __byte_perm(w, 0u, 0x4443));
+    const unsigned b2 = __viaddmin_u32(b3, 1u, __byte_perm(w, 0u, 0x4442));
+    const unsigned b1 = __viaddmin_u32(b2, 1u, __byte_perm(w, 0u, 0x4441));
+    const unsigned b0 = __viaddmin_u32(b1, 1u, __byte_perm(w, 0u, 0x4440));
     c = b0;
-    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    return pack_bytes(b0, b1, b2, b3);
 }
 
 // ---- kernel 1: X and Y sweeps of one z-slice in shared memory ---------------------------------
 // ManhattanDistanceX.comp:53-68 and ManhattanDistanceY.comp:35-49.
-constexpr int XY_THREADS = 256;
-constexpr int XY_BATCH = 6;  // 16-byte loads in flight per thread
+// All slices are resident at once (one wave), so the kernel lasts as long as one CTA's chain of phases: every phase
+// has to keep all 12 warps busy.  Rows are cut into sx segments and columns into sy segments (3 x 128 voxels and
+// 4 x 32 rows for the 384 x 128 slice) so both sweeps have 384 independent chains; the segments are joined exactly by
+// carries, like the Z kernels: after the local two-sided sweeps a segment's boundary value + distance is what any
+// other segment can see of it.  The X carries are folded into the first touch of the Y sweep, the Y carries into
+// the write-out, so no extra pass over the slice is needed.
+//   stage   16-byte loads (8 per thread, all in flight), seeds -> shared memory rows (odd stride in quads)
+//   X       local forward + backward sweep per (row, x-segment)
+//   xcarry  per (row, x-segment): value arriving from the left / right segments
+//   Y       local forward (X carries applied on the fly) + backward sweep per (word column, y-segment)
+//   ycarry  per (word column, y-segment): values arriving from above / below
+//   store   Y carries applied, 16-byte stores
+constexpr int XY_THREADS = 384;
+constexpr int XY_BATCH = 8;   // 16-byte loads in flight per thread
+constexpr int XY_MAX_SEG = 8;
+constexpr unsigned NO_CARRY = 0x03ffu;  // above every distance, small enough to add offsets in a u16 lane
 
-__global__ void __launch_bounds__(XY_THREADS) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
-                                                                 uint8_t* __restrict__ df, int nx, int ny,
-                                                                 int z_begin, unsigned maxd) {
+__global__ void __launch_bounds__(XY_THREADS, 3) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
+                                                                    uint8_t* __restrict__ df, int nx, int ny,
+                                                                    int z_begin, unsigned maxd, int sx, int sy) {
     extern __shared__ uint4 smem4[];
     unsigned* smem = reinterpret_cast<unsigned*>(smem4);
     const int qpr = nx >> 4;       // 16-byte quads per row
@@ -67,12 +87,19 @@ __global__ void __launch_bounds__(XY_THREADS) df_xy_slice_kernel(const uint8_t* 
     const int sw = sq << 2;        // row stride in words
     const int nxw = nx >> 2;       // words per row
     const int nq = qpr * ny;       // quads in the slice (<= 4096)
+    const int qps = qpr / sx;      // quads per x-segment
+    const int segvox = qps << 4;   // voxels per x-segment
+    const int rps = ny / sy;       // rows per y-segment
+    unsigned* xcar = smem + ny * sw;                                   // [ny][sx]: fwd | bwd << 16
+    uint4* ycar = reinterpret_cast<uint4*>(xcar + ((ny * sx + 3) & ~3));  // [sy][4][qpr]: (fwd.e, fwd.o, bwd.e, bwd.o)
     const unsigned rdiv = ((1u << 20) + qpr - 1) / qpr;  // q / qpr == (q * rdiv) >> 20 for q < 4096, qpr <= 64
+    const unsigned ydiv = ((1u << 20) + rps - 1) / rps;  // row / rps likewise (row < 4096)
     const int z = z_begin + blockIdx.x;
     const size_t slice_off = (size_t)z * nx * ny;
     const uint4* src = reinterpret_cast<const uint4*>(blocks + slice_off);
     const unsigned maxd4 = maxd * 0x01010101u;
 
+    // ---- stage ----
     for (int base = 0; base < nq; base += XY_THREADS * XY_BATCH) {
         uint4 v[XY_BATCH];
 #pragma unroll
@@ -92,19 +119,20 @@ __global__ void __launch_bounds__(XY_THREADS) df_xy_slice_kernel(const uint8_t* 
     }
     __syncthreads();
 
-    // X sweep: d[x] = min(seed[x], d[x-1]+1) forward, then d[x] = min(d[x], d[x+1]+1) backward.
-    for (int row = threadIdx.x; row < ny; row += XY_THREADS) {
-        uint4* r = smem4 + row * sq;
+    // ---- X: local sweeps per (row, x-segment); consecutive threads take consecutive rows (conflict-free LDS.128) ----
+    for (int item = threadIdx.x; item < ny * sx; item += XY_THREADS) {
+        const int seg = item / ny, row = item - seg * ny;
+        uint4* r = smem4 + row * sq + seg * qps;
         unsigned c = 255u;  // min(seed, 256) == seed for the first voxel
 #pragma unroll 2
-        for (int j = 0; j < qpr; ++j) {
+        for (int j = 0; j < qps; ++j) {
             uint4 w = r[j];
             w.x = sweep_word_up(w.x, c); w.y = sweep_word_up(w.y, c); w.z = sweep_word_up(w.z, c); w.w = sweep_word_up(w.w, c);
             r[j] = w;
         }
         c = 255u;
 #pragma unroll 2
-        for (int j = qpr - 1; j >= 0; --j) {
+        for (int j = qps - 1; j >= 0; --j) {
             uint4 w = r[j];
             w.w = sweep_word_down(w.w, c); w.z = sweep_word_down(w.z, c); w.y = sweep_word_down(w.y, c); w.x = sweep_word_down(w.x, c);
             r[j] = w;
@@ -112,21 +140,45 @@ __global__ void __launch_bounds__(XY_THREADS) df_xy_slice_kernel(const uint8_t* 
     }
     __syncthreads();
 
-    // Y sweep on 4-voxel word columns, two u16x2 lane pairs per word.
-    for (int col = threadIdx.x; col < nxw; col += XY_THREADS) {
+    // ---- xcarry: what reaches the first / last voxel of (row, seg) from the other segments of the row ----
+    for (int item = threadIdx.x; item < ny * sx; item += XY_THREADS) {
+        const int seg = item / ny, row = item - seg * ny;
+        const unsigned* r = smem + row * sw;
+        unsigned cf = NO_CARRY, cb = NO_CARRY;
+        for (int t = 0; t < sx; ++t) {
+            if (t < seg) cf = min(cf, (r[(t + 1) * (qps << 2) - 1] >> 24) + (unsigned)((seg - t - 1) * segvox + 1));       // last voxel of t
+            else if (t > seg) cb = min(cb, (r[t * (qps << 2)] & 0xffu) + (unsigned)((t - seg - 1) * segvox + 1));        // first voxel of t
+        }
+        xcar[row * sx + seg] = cf | (cb << 16);
+    }
+    __syncthreads();
+
+    // ---- Y: local sweeps per (word column, y-segment), two u16x2 lane pairs per word ----
+    for (int item = threadIdx.x; item < nxw * sy; item += XY_THREADS) {
+        const int ys = item / nxw, col = item - ys * nxw;
+        const int xseg = col / (qps << 2);
+        const unsigned d0 = (unsigned)(col * 4 - xseg * segvox);              // distance of byte 0 from the segment's first voxel
+        const unsigned b0 = (unsigned)(segvox - 1) - d0;                      // ... from its last voxel (>= 3)
+        const unsigned offFe = d0 | ((d0 + 2) << 16), offFo = (d0 + 1) | ((d0 + 3) << 16);
+        const unsigned offBe = b0 | ((b0 - 2) << 16), offBo = (b0 - 1) | ((b0 - 3) << 16);
         unsigned* cptr = smem + col;
-        unsigned w = cptr[0];
-        unsigned e = even_lanes(w), o = odd_lanes(w);
-#pragma unroll 8
-        for (int y = 1; y < ny; ++y) {
-            w = cptr[y * sw];
-            e = __viaddmin_u16x2(e, 0x00010001u, even_lanes(w));
-            o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
+        const unsigned* xc = xcar + xseg;
+        const int y0 = ys * rps, y1 = y0 + rps;
+        unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first row
+#pragma unroll 4
+        for (int y = y0; y < y1; ++y) {
+            const unsigned w = cptr[y * sw], c = xc[y * sx];
+            const unsigned cf2 = __byte_perm(c, 0u, 0x1010), cb2 = __byte_perm(c, 0u, 0x3232);
+            unsigned ve = even_lanes(w), vo = odd_lanes(w);
+            ve = __viaddmin_u16x2(cf2, offFe, ve); vo = __viaddmin_u16x2(cf2, offFo, vo);   // the row's X transform, completed
+            ve = __viaddmin_u16x2(cb2, offBe, ve); vo = __viaddmin_u16x2(cb2, offBo, vo);
+            e = __viaddmin_u16x2(e, 0x00010001u, ve);
+            o = __viaddmin_u16x2(o, 0x00010001u, vo);
             cptr[y * sw] = pack_lanes(e, o);
         }
-#pragma unroll 8
-        for (int y = ny - 2; y >= 0; --y) {
-            w = cptr[y * sw];
+#pragma unroll 4
+        for (int y = y1 - 2; y >= y0; --y) {
+            const unsigned w = cptr[y * sw];
             e = __viaddmin_u16x2(e, 0x00010001u, even_lanes(w));
             o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
             cptr[y * sw] = pack_lanes(e, o);
@@ -134,10 +186,41 @@ __global__ void __launch_bounds__(XY_THREADS) df_xy_slice_kernel(const uint8_t* 
     }
     __syncthreads();
 
+    // ---- ycarry: what reaches the first / last row of (column, ys) from the other y-segments ----
+    for (int item = threadIdx.x; item < nxw * sy; item += XY_THREADS) {
+        const int ys = item / nxw, col = item - ys * nxw;
+        unsigned fe = NO_CARRY * 0x00010001u, fo = fe, be = fe, bo = fe;
+        for (int t = 0; t < sy; ++t) {
+            if (t < ys) {
+                const unsigned w = smem[((t + 1) * rps - 1) * sw + col], d = (unsigned)((ys - t - 1) * rps + 1), d2 = d | (d << 16);
+                fe = __viaddmin_u16x2(even_lanes(w), d2, fe); fo = __viaddmin_u16x2(odd_lanes(w), d2, fo);
+            } else if (t > ys) {
+                const unsigned w = smem[(t * rps) * sw + col], d = (unsigned)((t - ys - 1) * rps + 1), d2 = d | (d << 16);
+                be = __viaddmin_u16x2(even_lanes(w), d2, be); bo = __viaddmin_u16x2(odd_lanes(w), d2, bo);
+            }
+        }
+        ycar[(ys * 4 + (col & 3)) * qpr + (col >> 2)] = make_uint4(fe, fo, be, bo);
+    }
+    __syncthreads();
+
+    // ---- store: Y carries applied on the way out ----
     uint4* dst = reinterpret_cast<uint4*>(df + slice_off);
     for (int q = threadIdx.x; q < nq; q += XY_THREADS) {
-        const int row = (int)(((unsigned)q * rdiv) >> 20), col = q - row * qpr;
-        dst[q] = smem4[row * sq + col];
+        const int row = (int)(((unsigned)q * rdiv) >> 20), colq = q - row * qpr;
+        const int ys = (int)(((unsigned)row * ydiv) >> 20);
+        const unsigned df_ = (unsigned)(row - ys * rps), db_ = (unsigned)(rps - 1) - df_;
+        const unsigned df2 = df_ | (df_ << 16), db2 = db_ | (db_ << 16);
+        uint4 v = smem4[row * sq + colq];
+        unsigned* vw = reinterpret_cast<unsigned*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 c = ycar[(ys * 4 + k) * qpr + colq];
+            unsigned e = even_lanes(vw[k]), o = odd_lanes(vw[k]);
+            e = __viaddmin_u16x2(c.x, df2, e); o = __viaddmin_u16x2(c.y, df2, o);
+            e = __viaddmin_u16x2(c.z, db2, e); o = __viaddmin_u16x2(c.w, db2, o);
+            vw[k] = pack_lanes(e, o);
+        }
+        dst[q] = v;
     }
 }
 
@@ -251,6 +334,84 @@ __global__ void __launch_bounds__(Z_THREADS) df_z_tile_kernel(uint8_t* __restric
     }
 }
 
+// ---- kernel 2, register-resident variant (plane ranges of exactly ZR_WARPS * SEG planes) ------------------------
+// Same decomposition as df_z_tile_kernel, but a lane keeps the SEG words of its column segment in registers: all of
+// a lane's loads are in flight at once, the two local sweeps and the carry fold run on registers, and shared memory
+// only carries the boundary planes of the 16 segments (8 KB).  Every warp-level load / store moves one 128-byte row
+// of a plane.  SEG is a compile-time constant (24 for the 384-plane world, 12 / 6 / 3 for its 2 / 4 / 8 z-slabs), so
+// the loops are straight-line code; at <= 42 registers three 512-thread CTAs fit an SM and the 384 tiles of the
+// default grid are resident in one wave.
+constexpr int ZR_WARPS = 16;
+constexpr int ZR_THREADS = ZR_WARPS * 32;
+
+template <int SEG>
+__global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __restrict__ df, int words_per_plane, int z0) {
+    __shared__ uint4 bnd[ZR_WARPS][32];  // per segment and column: first-plane (e, o), last-plane (e, o) after the local sweeps
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 32 + lane;
+    const bool col_ok = col < words_per_plane;
+    unsigned* base = reinterpret_cast<unsigned*>(df) + (size_t)(z0 + s * SEG) * words_per_plane + (col_ok ? col : 0);
+    const size_t ps = (size_t)words_per_plane;
+
+    unsigned w[SEG];
+    {
+        const unsigned* p = base;  // running pointer: one live address instead of SEG of them
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+            w[i] = *p;  // a column past the end re-reads column 0 of the tile and is never stored
+            p += ps;
+        }
+    }
+    // local forward sweep, then backward (the last plane is final after the forward sweep)
+    unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first plane
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+        e = __viaddmin_u16x2(e, 0x00010001u, even_lanes(w[i]));
+        o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w[i]));
+        w[i] = pack_lanes(e, o);
+    }
+    const unsigned last_e = e, last_o = o;
+#pragma unroll
+    for (int i = SEG - 2; i >= 0; --i) {
+        e = __viaddmin_u16x2(e, 0x00010001u, even_lanes(w[i]));
+        o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w[i]));
+        w[i] = pack_lanes(e, o);
+    }
+    bnd[s][lane] = make_uint4(e, o, last_e, last_o);
+    __syncthreads();
+
+    // carries of the other segments (see df_z_tile_kernel): fwd arrives at this segment's first plane from the last
+    // plane of segment t < s, (s - t - 1) * SEG + 1 planes away; bwd arrives at its last plane likewise
+    unsigned fe = 0x03ff03ffu, fo = 0x03ff03ffu, be = 0x03ff03ffu, bo = 0x03ff03ffu;
+#pragma unroll
+    for (int t = 0; t < ZR_WARPS; ++t) {
+        const uint4 v = bnd[t][lane];
+        if (t < s) {
+            const unsigned d = (unsigned)((s - t - 1) * SEG + 1), d2 = d | (d << 16);
+            fe = __viaddmin_u16x2(v.z, d2, fe);
+            fo = __viaddmin_u16x2(v.w, d2, fo);
+        } else if (t > s) {
+            const unsigned d = (unsigned)((t - s - 1) * SEG + 1), d2 = d | (d << 16);
+            be = __viaddmin_u16x2(v.x, d2, be);
+            bo = __viaddmin_u16x2(v.y, d2, bo);
+        }
+    }
+    // fold: plane i of the segment sees fwd + i and bwd + (SEG - 1 - i); lanes stay below 2^16.
+    // The store addresses are re-derived from an opaque copy of the base pointer: left to itself the compiler keeps
+    // the SEG load addresses alive across the whole kernel and spills them (ncu: STL/LDL on the critical path).
+    asm volatile("" : "+l"(base));
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+        unsigned ve = even_lanes(w[i]), vo = odd_lanes(w[i]);
+        ve = __viaddmin_u16x2(fe, (unsigned)i * 0x00010001u, ve);
+        vo = __viaddmin_u16x2(fo, (unsigned)i * 0x00010001u, vo);
+        ve = __viaddmin_u16x2(be, (unsigned)(SEG - 1 - i) * 0x00010001u, ve);
+        vo = __viaddmin_u16x2(bo, (unsigned)(SEG - 1 - i) * 0x00010001u, vo);
+        if (col_ok) *base = pack_lanes(ve, vo);
+        base += ps;
+    }
+}
+
 // ---- z-slab sharding (multi-GPU regeneration) -------------------------------------
 // After the slab-local sweeps every rank holds L[z] = min over its own planes z' of xy[z'] + |z - z'|.
 // With B_t = L on the last plane of slab t and F_t = L on the first plane of slab t (all-gathered, one
@@ -305,15 +466,34 @@ static int set_smem_attrs() {
 static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     const int nx = c->nx, ny = c->ny, nz = c->nz;
     const unsigned maxd = (unsigned)((nx + ny + nz) < 254 ? (nx + ny + nz) : 254);
-    const size_t smem_xy = (size_t)ny * ((nx >> 4) | 1) * sizeof(uint4);
+    // segments per row / per column: as many as keep XY_THREADS chains busy, dividing the row / column evenly
+    const int qpr = nx >> 4, nxw = nx >> 2;
+    int sx = XY_THREADS / ny, sy = XY_THREADS / nxw;
+    sx = sx < 1 ? 1 : (sx > XY_MAX_SEG ? XY_MAX_SEG : sx);
+    sy = sy < 1 ? 1 : (sy > XY_MAX_SEG ? XY_MAX_SEG : sy);
+    if (c->df_sx > 0) sx = c->df_sx;
+    if (c->df_sy > 0) sy = c->df_sy;
+    while (qpr % sx) --sx;
+    while (ny % sy) --sy;
+    const size_t smem_xy = (size_t)ny * (qpr | 1) * sizeof(uint4) + (((size_t)ny * sx + 3) & ~(size_t)3) * sizeof(unsigned) +
+                           (size_t)sy * 4 * qpr * sizeof(uint4);
     int rc = set_smem_attrs();
     if (rc) return rc;
-    df_xy_slice_kernel<<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd);
+    if (c->df_stage != 2)
+        df_xy_slice_kernel<<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
     VX_CUDA(cudaGetLastError());
+    if (c->df_stage == 1) return VXRT_OK;
     const int wpp = (nx * ny) >> 2, nzr = z1 - z0;
-    const int seg = (nzr + Z_SEGS - 1) / Z_SEGS;
-    const size_t smem_z = ((size_t)nzr * Z_TILE_QUADS + (size_t)Z_SEGS * Z_TILE_WORDS) * sizeof(uint4);
-    df_z_tile_kernel<<<(wpp + Z_TILE_WORDS - 1) / Z_TILE_WORDS, Z_THREADS, smem_z, c->stream>>>(c->d_df, wpp, z0, z1, seg);
+    const int ztiles = (wpp + 31) / 32;
+    if (nzr == ZR_WARPS * 24) df_z_reg_kernel<24><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 12) df_z_reg_kernel<12><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 6) df_z_reg_kernel<6><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 3) df_z_reg_kernel<3><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else {
+        const int seg = (nzr + Z_SEGS - 1) / Z_SEGS;
+        const size_t smem_z = ((size_t)nzr * Z_TILE_QUADS + (size_t)Z_SEGS * Z_TILE_WORDS) * sizeof(uint4);
+        df_z_tile_kernel<<<(wpp + Z_TILE_WORDS - 1) / Z_TILE_WORDS, Z_THREADS, smem_z, c->stream>>>(c->d_df, wpp, z0, z1, seg);
+    }
     VX_CUDA(cudaGetLastError());
     c->launches += 2;
     return VXRT_OK;
