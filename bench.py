@@ -549,7 +549,8 @@ def main():
                          "kernel_mrays": k_rays / (k_ms * 1e-3) / 1e6,
                          "l2_gather": {"achieved": sector_bytes / (k_ms * 1e-3) / 1e9, "peak": gather_peak_gbs, "unit": "GB/s",
                                        "frac": sector_bytes / (k_ms * 1e-3) / 1e9 / gather_peak_gbs,
-                                       "peak_source": "vxrt_cuda_gather_peak: independent random 1-byte loads of the L2-resident distance field, 32 B per sector, measured in this run"},
+                                       "peak_source": "vxrt_cuda_gather_peak: independent random 1-byte loads of the L2-resident distance field, 32 B per sector, measured in this run",
+                                       "note": "the model charges one 32-byte sector per iteration; coherent rays (primary, sun shadow) get 85-95 % of them from L1, so frac can exceed 1 there"},
                          "note": "grids are L2 resident (dram throughput < 1 % in profiles/): HBM is the contract's roof, the operative one is issue slots, then the L2/L1 gather rate (l2_gather); see DESIGN.md §3"},
         }
         nvox = blocks.size
