@@ -53,28 +53,31 @@ VXD int euclidean_step(int k) {
 //                       (tests/test_oracle_traverse.py::test_step_table); k == 1 -> 1.  So k == 0 stops,
 //                       k in 1..3 is a DDA step, k >= 4 skips E - 1 voxels.
 //   float(E - 1)        (2^23 + n) - 2^23 built from the bit pattern 0x4B000000 + n.
-//   float(G + s)        floor_float + float(s), exact on integers.
+//   float(G + s) + (1 - p)   on the stepped axis: floor_float + float(s + 1 - p), exact on integers, then the nudge is
+//                       added with one rounding exactly like the shader's `origin[MinIdx] += RaySign[MinIdx] * 0.0001f`;
+//                       the other two axes are floor_float + (W + dir * DistanceFactor[MinIdx]).
+//   Intersection / MinIdx    one register: `state` = MinIdx | 4 once a DDA step has been taken.
 #define VX_FLOOR_MAGIC 12582912.0f
 #define VX_FLOOR_MAGIC_BITS 0x4B400000
 
 struct RaySetup {
     f3 d, inv;
-    f3 fs;      // float(RaySign)
     f3 fp;      // float((1 + RaySign) >> 1)
-    f3 omp;     // float(1 - ((1 + RaySign) >> 1))
+    f3 c;       // float(RaySign) + float(1 - ((1 + RaySign) >> 1)): what a DDA step adds to the floor on its axis (exact)
     f3 nudge;   // float(RaySign) * 0.0001f
     int sx, sy, sz;
+    unsigned nx, ny, nz, nxy;  // grid size kept in registers: the loop otherwise reloads it from the constant bank
 };
-VXD RaySetup ray_setup(f3 direction) {
+VXD RaySetup ray_setup(const GridView& g, f3 direction) {
     RaySetup r;
+    r.nx = (unsigned)g.nx; r.ny = (unsigned)g.ny; r.nz = (unsigned)g.nz; r.nxy = (unsigned)g.sz;
     r.d = direction;
     r.sx = gsign(direction.x); r.sy = gsign(direction.y); r.sz = gsign(direction.z);
     const int px = (1 + r.sx) >> 1, py = (1 + r.sy) >> 1, pz = (1 + r.sz) >> 1;
     r.inv = F3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    r.fs = F3((float)r.sx, (float)r.sy, (float)r.sz);
     r.fp = F3((float)px, (float)py, (float)pz);
-    r.omp = F3((float)(1 - px), (float)(1 - py), (float)(1 - pz));
-    r.nudge = F3(r.fs.x * 0.0001f, r.fs.y * 0.0001f, r.fs.z * 0.0001f);
+    r.c = F3((float)(r.sx + 1 - px), (float)(r.sy + 1 - py), (float)(r.sz + 1 - pz));
+    r.nudge = F3((float)r.sx * 0.0001f, (float)r.sy * 0.0001f, (float)r.sz * 0.0001f);
     return r;
 }
 
@@ -141,19 +144,19 @@ enum { VX_ITER_CONTINUE = 0, VX_ITER_STOP = 1, VX_ITER_TAIL = 2 };
 
 // one iteration of VoxelTraversalDF (InitialRayTraceFrag.glsl:320-371)
 template <bool STATS>
-VXD int df_iteration(const GridView& g, const RaySetup& r, f3& origin, bool& Intersection, int& MinIdx, LaneStats* st) {
+VXD int df_iteration(const GridView& g, const RaySetup& r, f3& origin, int& state, LaneStats* st) {
     const float Fx = __fadd_rd(origin.x, VX_FLOOR_MAGIC), Fy = __fadd_rd(origin.y, VX_FLOOR_MAGIC), Fz = __fadd_rd(origin.z, VX_FLOOR_MAGIC);
-    const unsigned bx = __float_as_uint(Fx), by = __float_as_uint(Fy), bz = __float_as_uint(Fz);  // 0x4B400000 + floor
-    if (!(((bx - VX_FLOOR_MAGIC_BITS) < (unsigned)g.nx) & ((by - VX_FLOOR_MAGIC_BITS) < (unsigned)g.ny) & ((bz - VX_FLOOR_MAGIC_BITS) < (unsigned)g.nz))) {
+    // floor as unsigned: bits - 0x4B400000; a negative or non-finite coordinate wraps far above any grid size
+    const unsigned lx = __float_as_uint(Fx) - VX_FLOOR_MAGIC_BITS, ly = __float_as_uint(Fy) - VX_FLOOR_MAGIC_BITS,
+                   lz = __float_as_uint(Fz) - VX_FLOOR_MAGIC_BITS;
+    if (!((lx < r.nx) & (ly < r.ny) & (lz < r.nz))) {
         if (!in_volume(g, cvt_floor(origin.x), cvt_floor(origin.y), cvt_floor(origin.z))) {
-            Intersection = false;
+            state &= 3;  // Intersection = false
             return VX_ITER_STOP;
         }
         return VX_ITER_TAIL;  // NaN coordinate converted to 0: leave the fast path
     }
-    // linear index from the biased integers: the bias of every term is removed by one constant (mod 2^32)
-    const unsigned idx = bx + by * (unsigned)g.sy + bz * (unsigned)g.sz - VX_FLOOR_MAGIC_BITS * (1u + (unsigned)g.sy + (unsigned)g.sz);
-    const int k = __ldg(g.df + idx);
+    const int k = __ldg(g.df + (lx + ly * r.nx + lz * r.nxy));
     if (STATS) st->iterations++;
     if (k < 4) {
         if (k == 0) return VX_ITER_STOP;
@@ -164,15 +167,11 @@ VXD int df_iteration(const GridView& g, const RaySetup& r, f3& origin, bool& Int
         // MinIdx (:345-347) as predicate logic: x iff (DF.x < DF.y && sx != 0) && (DF.x < DF.z || sz == 0), ...
         const bool first = (DF.x < DF.y) & (r.sx != 0), z_off = r.sz == 0;
         const bool ax = first & ((DF.x < DF.z) | z_off), ay = !first & ((DF.y < DF.z) | z_off), az = !(ax | ay);
-        MinIdx = ax ? 0 : (ay ? 1 : 2);
+        state = ax ? 4 : (ay ? 5 : 6);  // Intersection = true, MinIdx
         W = W + r.d * (ax ? DF.x : (ay ? DF.y : DF.z));
-        const float gx = ax ? fl.x + r.fs.x : fl.x, gy = ay ? fl.y + r.fs.y : fl.y, gz = az ? fl.z + r.fs.z : fl.z;
-        W.x = ax ? r.omp.x : W.x; W.y = ay ? r.omp.y : W.y; W.z = az ? r.omp.z : W.z;
-        origin = F3(gx, gy, gz) + W;
-        origin.x = ax ? origin.x + r.nudge.x : origin.x;
-        origin.y = ay ? origin.y + r.nudge.y : origin.y;
-        origin.z = az ? origin.z + r.nudge.z : origin.z;
-        Intersection = true;
+        origin.x = ax ? (fl.x + r.c.x) + r.nudge.x : fl.x + W.x;
+        origin.y = ay ? (fl.y + r.c.y) + r.nudge.y : fl.y + W.y;
+        origin.z = az ? (fl.z + r.c.z) + r.nudge.z : fl.z + W.z;
     } else {
         const float skip = __int_as_float(0x4B000000 + ((k * 9459) >> 14) - 1) - 8388608.0f;  // float(E - 1)
         origin = origin + skip * r.d;
@@ -181,7 +180,9 @@ VXD int df_iteration(const GridView& g, const RaySetup& r, f3& origin, bool& Int
 }
 
 template <bool STATS>
-VXD TraceResult trace_result(const GridView& g, const RaySetup& rs, f3 origin, f3 initial_origin, bool Intersection, int MinIdx, LaneStats* st) {
+VXD TraceResult trace_result(const GridView& g, const RaySetup& rs, f3 origin, f3 initial_origin, int state, LaneStats* st) {
+    const bool Intersection = (state & 4) != 0;
+    const int MinIdx = state & 3;
     TraceResult r;
     r.t = -1.0f;
     r.block = 0;
@@ -201,16 +202,20 @@ VXD TraceResult trace_result(const GridView& g, const RaySetup& rs, f3 origin, f
 template <bool STATS>
 VXD TraceResult traverse_df(const GridView& g, f3 origin, f3 direction, int max_iter, LaneStats* st) {
     const f3 initial_origin = origin;
-    const RaySetup rs = ray_setup(direction);
-    bool Intersection = false;
-    int MinIdx = 0;
+    const RaySetup rs = ray_setup(g, direction);
+    int state = 0;  // MinIdx = 0, Intersection = false
     for (int itr = 0; itr < max_iter; ++itr) {
-        const int c = df_iteration<STATS>(g, rs, origin, Intersection, MinIdx, st);
+        const int c = df_iteration<STATS>(g, rs, origin, state, st);
         if (c == VX_ITER_CONTINUE) continue;
-        if (c == VX_ITER_TAIL) run_tail<STATS>(g, origin, direction, itr, max_iter, Intersection, MinIdx, st);
+        if (c == VX_ITER_TAIL) {
+            bool Intersection = (state & 4) != 0;
+            int MinIdx = state & 3;
+            run_tail<STATS>(g, origin, direction, itr, max_iter, Intersection, MinIdx, st);
+            state = MinIdx | (Intersection ? 4 : 0);
+        }
         break;
     }
-    return trace_result<STATS>(g, rs, origin, initial_origin, Intersection, MinIdx, st);
+    return trace_result<STATS>(g, rs, origin, initial_origin, state, st);
 }
 
 // warp-aggregated flush of per-lane counters
