@@ -6,7 +6,10 @@
 // measured on config 4 and lost: GI 1.33 -> 1.52 ms, reflections 0.76 -> 0.84 ms at the best geometry
 // (chunk 128, refill 8; larger chunks were worse).  The queues are latency bound, not lane bound: the
 // refill rounds expose the queue loads once per round instead of once per warp and the resumable ray state
-// costs 20 more registers (profiles/r1_e_wavefront_sweep.txt).
+// costs 20 more registers (profiles/r1_e_wavefront_sweep.txt).  So did in-CTA compaction (live rays packed into the
+// lowest threads through shared memory every 4..16 iterations, emptied warps exiting): GI 1.12 -> 1.32..1.56 ms
+// although a replay of the oracle's iteration counts predicted 40 % fewer warp-iterations — 60 registers instead of
+// 40 and one block barrier per round, at which seven warps wait for the slowest (profiles/r1_p_cta_compaction_sweep.txt).
 #pragma once
 #include "traverse.cuh"
 
