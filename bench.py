@@ -114,6 +114,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank (and first-touch its pinned host buffers) on the CPU socket its GPU hangs off: with 8 ranks reading
+    126 MB per frame back over 8 PCIe links, remote-socket host memory is the bottleneck otherwise.  Best effort."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def build_world(spec, dims=(384, 128, 384)):
     from voxeltracing_b200 import host_api
 
@@ -294,6 +319,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -538,7 +564,7 @@ def main():
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); camera pose changes every step"},
             "clocks": clocks,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "rank0_numa_node": numa_node},
             "gpu_launches": launches,
             "pass_ms": pass_ms,
             "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},

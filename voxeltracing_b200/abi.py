@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-CUDA_LIB_PATH = _PKG / "libvxrt_cuda.so"
+# VXRT_CUDA_LIB selects another build of the same library (A/B experiments, tools/debug); never a fallback
+CUDA_LIB_PATH = Path(os.environ["VXRT_CUDA_LIB"]) if os.environ.get("VXRT_CUDA_LIB") else _PKG / "libvxrt_cuda.so"
 HOST_LIB_PATH = _PKG / "libvxrt_host.so"
 
 VXRT_OK = 0

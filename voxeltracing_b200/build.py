@@ -59,6 +59,16 @@ def _run(cmd, **kw):
     return r.stdout
 
 
+def build_cuda_variant(name: str, defines, verbose: bool = False) -> Path:
+    """Experimental build with extra -D flags into voxeltracing_b200/libvxrt_cuda_<name>.so (select it with VXRT_CUDA_LIB)."""
+    out = CUDA_LIB.with_name(f"libvxrt_cuda_{name}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(out)] + [str(s) for s in sorted(CSRC.glob("*.cu"))]
+    o = _run(cmd)
+    if verbose:
+        print(o)
+    return out
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = sorted(CSRC.glob("*.cu"))
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "vxrt_cuda.h"]

@@ -21,6 +21,10 @@
 #include "gi_common.cuh"
 #include "trace_queue.cuh"
 
+#ifndef VX_SHADE_OCC
+#define VX_SHADE_OCC 1  // minimum CTAs per SM asked of the shading kernels (register cap)
+#endif
+
 namespace {
 
 struct GiWf {
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_shadow_kernel(GridView 
 }
 
 // ---- gen: main() prologue per pixel (:910-969) + first direction of sample `sample` ------------------
-__global__ void __launch_bounds__(256) gi_wf_gen_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
     int px, py;
     tile_pixel(px, py, a.row0);
     if (px >= a.width || py >= a.row1) return;
@@ -196,7 +200,7 @@ VXD void finish_sample(const GiWf& w, int i, f3 contrib, float skyhit) {
 // ---- shade<BOUNCE>: the body of the bounce loop of CalculateDiffuse (:547-655) ----------------------
 // BOUNCE 0/1: consume the closest-hit result of that bounce; BOUNCE 2: only apply the pending bounce-1 terms.
 template <int BOUNCE>
-__global__ void __launch_bounds__(256) gi_wf_shade_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
     int px, py;
     tile_pixel(px, py, a.row0);
     const bool inside = px < a.width && py < a.row1;

@@ -13,6 +13,10 @@
 #include "reflect_common.cuh"
 #include "trace_queue.cuh"
 
+#ifndef VX_SHADE_OCC
+#define VX_SHADE_OCC 1  // minimum CTAs per SM asked of the shading kernels (register cap)
+#endif
+
 namespace {
 
 struct RfWf {
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_shadow_kernel(GridVi
     if (STATS) flush_stats(stats, ls);
 }
 
-__global__ void __launch_bounds__(256) rf_wf_gen_kernel(const __grid_constant__ ReflArgs a, RfWf w, int sample) {
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __grid_constant__ ReflArgs a, RfWf w, int sample) {
     int px, py;
     tile_pixel(px, py, a.row0);
     if (px >= a.width || py >= a.row1) return;
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256) rf_wf_gen_kernel(const __grid_constant__ 
     w.rayD[i] = make_float4(R.x, R.y, R.z, 1.0f);
 }
 
-__global__ void __launch_bounds__(256) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
     int px, py;
     tile_pixel(px, py, a.row0);
     const bool inside = px < a.width && py < a.row1;
