@@ -51,8 +51,10 @@ struct vxrt_ctx {
     int sm_count = 0;
     int64_t launches = 0;
 
+    uint8_t* d_df = nullptr;      // one allocation: distance field, then block ids
     uint8_t* d_blocks = nullptr;
-    uint8_t* d_df = nullptr;
+    bool l2_persist = false;      // L2 access-policy window over the grids (set_option "l2_persist", VXRT_L2_PERSIST); see api.cu
+    size_t l2_persist_max = 0;
     bool world_uploaded = false;
     bool df_valid = false;
     int df_sx = 0, df_sy = 0;  // measurement aid: override the segment counts of the XY kernel (0 = automatic)
@@ -120,7 +122,8 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
         if (_rc != VXRT_OK) return _rc;                            \
     } while (0)
 
-cudaEvent_t vxrt_probe_event(vxrt_ctx* c);  // next pooled event (nullptr when the probe is off or on error)
+cudaEvent_t vxrt_probe_event(vxrt_ctx* c);
+int vxrt_apply_l2_policy(vxrt_ctx* c);  // next pooled event (nullptr when the probe is off or on error)
 
 // kernel launchers (one per .cu)
 int vxrt_launch_distance_field(vxrt_ctx* c);
