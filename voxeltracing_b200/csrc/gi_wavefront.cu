@@ -144,8 +144,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __gr
             a.utility[pi] = float_to_half_bits(0.0f);
             reinterpret_cast<uchar2*>(a.aosky)[pi] = make_uchar2(float_to_unorm8(1.0f), float_to_unorm8(0.0f));
             w.bl[i] = -1;
-            w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            w.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // no path: the arena may hold a stale flag
+            w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // no path (shade<0> marks it dead for the later stages)
             return;
         }
         int SPP = iclamp(a.spp, 1, 32);
@@ -158,14 +157,11 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __gr
         w.pixP[i] = make_float4(P.x, P.y, P.z, (float)cvt_round(nid * 10.0f));
         w.bl[i] = 0;
         w.spp[i] = SPP;
-        w.accSH[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        w.accRadAO[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        w.accCoCgSky[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // the accumulators are not cleared here: the first sample's finish_sample writes 0 + x instead of reading them
     }
     const int bl = w.bl[i];
     if (bl < 0 || sample >= w.spp[i]) {
         w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        w.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         return;
     }
     const float4 p4 = w.pixP[i];
@@ -179,21 +175,21 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __gr
     w.rayO[i] = make_float4(o.x, o.y, o.z, 0.0f);
     w.rayD[i] = make_float4(d.x, d.y, d.z, 1.0f);
     w.odirAo[i] = make_float4(d.x, d.y, d.z, 1.0f);
-    w.contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-    w.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    // RayContribution = 0, RayThroughput = 1, no sky hit: shade<0> starts from these constants instead of loading them
 }
 
 // sample epilogue of main() (:985-1000): clamp, SH encode, accumulate
-VXD void finish_sample(const GiWf& w, int i, f3 contrib, float skyhit) {
+VXD void finish_sample(const GiWf& w, int i, f3 contrib, float skyhit, bool first) {
     const float4 oa = w.odirAo[i];
     const f3 xc = gclamp(contrib, 0.0f, 8.0f);
     float SH[6];
     irradiance_to_sh(xc, F3(oa.x, oa.y, oa.z), SH);
-    float4 s = w.accSH[i];
+    const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // 0 + x, not x: keeps -0 -> +0 like the shader's running sum
+    const float4 s = first ? zero : w.accSH[i];
     w.accSH[i] = make_float4(s.x + SH[0], s.y + SH[1], s.z + SH[2], s.w + SH[3]);
-    float4 r = w.accRadAO[i];
+    const float4 r = first ? zero : w.accRadAO[i];
     w.accRadAO[i] = make_float4(r.x + xc.x, r.y + xc.y, r.z + xc.z, r.w + oa.w);
-    float4 c = w.accCoCgSky[i];
+    const float4 c = first ? zero : w.accCoCgSky[i];
     w.accCoCgSky[i] = make_float4(c.x + SH[4], c.y + SH[5], c.z + skyhit, 0.0f);
 }
 
@@ -207,11 +203,21 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
     const int i = inside ? (py - a.row0) * a.width + px : 0;
     bool push_shadow = false, push_bounce = false;
     f3 shadow_o = F3(0.0f);
-    float4 c4 = inside ? w.contrib[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const bool alive = inside && c4.w != 0.0f;
+    // a path is alive at bounce 0 iff gen gave it a ray (rayD.w), later iff the previous stage left contrib.w set
+    float4 c4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t4 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    bool alive = false;
+    if (inside) {
+        if (BOUNCE == 0) {
+            alive = w.rayD[i].w != 0.0f;
+            if (!alive) w.contrib[i] = c4;  // dead for shade<1>, shade<2> (the arena may hold a stale flag)
+        } else {
+            c4 = w.contrib[i];
+            alive = c4.w != 0.0f;
+            if (alive) t4 = w.thr[i];
+        }
+    }
     if (alive) {
         f3 contrib = F3(c4.x, c4.y, c4.z);
-        float4 t4 = w.thr[i];
         f3 thr = F3(t4.x, t4.y, t4.z);
         float skyhit = t4.w;
         bool still_alive = false;
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
             w.contrib[i] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
             w.thr[i] = make_float4(thr.x, thr.y, thr.z, skyhit);
         } else {
-            finish_sample(w, i, contrib, skyhit);
+            finish_sample(w, i, contrib, skyhit, sample == 0);
             w.contrib[i] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
         }
     }
