@@ -550,6 +550,10 @@ def main():
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         sector_bytes = k_rays * 32 * (S + 1) + io_bytes
         gather_peak_gbs = ctx.gather_peak(256) * 32 / 1e9
+        try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/traffic.json)
+            traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(args.workload, {}).get(kname)
+        except Exception:
+            traffic = None
         line = {
             "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -569,7 +573,7 @@ def main():
             "pass_ms": pass_ms,
             "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},
             "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "mean_iterations_per_ray": S, "rays_per_launch": k_rays, "avg_launch_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_mrays": k_rays / (k_ms * 1e-3) / 1e6,
