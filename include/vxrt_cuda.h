@@ -315,6 +315,15 @@ typedef struct vxrt_ray_hit {
 int vxrt_cuda_trace_rays(vxrt_ctx* ctx, const float* origins, const float* directions, int32_t n, int32_t max_iterations,
                          vxrt_ray_hit* hits);
 
+/* ---- picking ray: World::RaycastDetect (Core/World.cpp:496-546; call site Core/Pipeline.cpp:2044) and the march of
+ * World::Raycast (Core/World.cpp:214-262), which places / removes a block next to / at the hit ----
+ * positions / directions: 3*n floats each, HOST memory; out: 8 int32 per ray = hit voxel x, y, z, block id, face normal
+ * x, y, z (as World::Raycast derives it: -1 / +1 on every axis whose slab plane the last step crossed), found (1 / 0).
+ * The march is 48 steps of the block-id grid itself (no distance field); voxel index 0 counts as outside, like the
+ * reference's `<= 0` test.  Nothing hit within reach: found = 0 and x = y = z = block = -1 (the reference function has
+ * no return statement on that path).  The engine follows a hit with vxrt_cuda_edit_blocks + generate_distance_field. */
+int vxrt_cuda_raycast_detect(vxrt_ctx* ctx, const float* positions, const float* directions, int32_t n, int32_t* out);
+
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {
     uint64_t rays;        /* VoxelTraversalDF invocations */

@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
     L.vxo_traverse.restype = C.c_float
     L.vxo_traverse_batch.argtypes = [P(World), vp, vp, i32, i32, vp]
     L.vxo_traverse_batch.restype = None
+    L.vxo_raycast_detect_batch.argtypes = [P(World), vp, vp, i32, vp]
+    L.vxo_raycast_detect_batch.restype = None
     L.vxo_plain_dda.argtypes = [P(World), vp, vp, i32, vp]
     L.vxo_plain_dda.restype = i32
     L.vxo_initial_trace.argtypes = [P(World), P(abi.PrimaryParams), vp, vp, vp, vp, vp, P(abi.TraceStats)]
@@ -119,6 +121,14 @@ class OracleWorld:
         hits = np.zeros(len(o), dtype=self.HIT_DTYPE)
         lib().vxo_traverse_batch(C.byref(self.c), _p(o), _p(d), len(o), max_iter, _p(hits))
         return hits
+
+    def raycast_detect(self, positions, directions) -> np.ndarray:
+        """World::RaycastDetect over (n,3) rays; int32 (n,8): x, y, z, block, normal xyz, found."""
+        o = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((len(o), 8), dtype=np.int32)
+        lib().vxo_raycast_detect_batch(C.byref(self.c), _p(o), _p(d), len(o), _p(out))
+        return out
 
     def plain_dda(self, origin, direction, max_steps: int = 2000):
         o = np.asarray(origin, dtype=np.float32)

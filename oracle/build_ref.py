@@ -258,6 +258,58 @@ def transform(name: str, text: str, kind: str) -> str:
     return hdr + src + reset_fn + "\n} }\n"
 
 
+def gen_raycast_detect() -> bool:
+    """World::RaycastDetect is host C++ (Core/World.cpp): its text is lifted in place into a generated translation unit
+    with a minimal World (the real class drags in OpenGL), compiled against the reference's own glm.  The function has
+    no return statement after its loop (undefined behaviour when nothing is hit): the generated copy returns
+    ivec4(-2) there so that the no-hit case can be observed."""
+    src = (REF / "Core" / "World.cpp").read_text(errors="replace")
+    m = re.search(r"glm::ivec4\s+VoxelRT::World::RaycastDetect\s*\(", src)
+    glm_dir = REF / "Dependencies" / "glm"
+    if not m or not (glm_dir / "glm" / "glm.hpp").exists():
+        return False
+    i = src.index("{", m.end())
+    depth, j = 0, i
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[j], 0)
+        if depth == 0:
+            break
+        j += 1
+    body = src[m.start():j] + "\n\treturn glm::ivec4(-2); // added: the reference falls off the end here\n}"
+    macros = (REF / "Core" / "Macros.h").read_text(errors="replace")
+    sizes = "\n".join(l for l in macros.splitlines() if re.match(r"\s*#define\s+WORLD_SIZE_[XYZ]\b", l))
+    (GEN / "RaycastDetect.cpp").write_text(f"""// GENERATED from Core/World.cpp by oracle/build_ref.py -- do not commit
+#include <stdint.h>
+#include <math.h>
+#include <algorithm>
+#include <glm/glm.hpp>
+{sizes}
+namespace VoxelRT {{
+struct Block {{ uint8_t block; }};
+struct World {{
+    const Block* m_WorldData;
+    const Block& GetBlock(uint16_t x, uint16_t y, uint16_t z) {{ return m_WorldData[x + y * WORLD_SIZE_X + z * WORLD_SIZE_X * WORLD_SIZE_Y]; }}
+    glm::ivec4 RaycastDetect(const glm::vec3& pos, const glm::vec3& dir);
+}};
+}}
+{body}
+extern "C" void vxref_raycast_detect(const uint8_t* blocks, const float* pos, const float* dir, int32_t n, int32_t* out4) {{
+    VoxelRT::World w; w.m_WorldData = reinterpret_cast<const VoxelRT::Block*>(blocks);
+    for (int32_t i = 0; i < n; ++i) {{
+        glm::ivec4 r = w.RaycastDetect(glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), glm::vec3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+        out4[4 * i] = r.x; out4[4 * i + 1] = r.y; out4[4 * i + 2] = r.z; out4[4 * i + 3] = r.w;
+    }}
+}}
+""")
+    cmd = ["g++", "-std=gnu++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", f"-I{glm_dir}", "-c", str(GEN / "RaycastDetect.cpp"),
+           "-o", str(GEN / "RaycastDetect.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        print("[build_ref] RaycastDetect: does not compile, skipped\n" + "\n".join(r.stderr.split("\n")[:30]))
+        return False
+    return True
+
+
 def gen_swizzles():
     GEN.mkdir(parents=True, exist_ok=True)
     sets = ["xyzw", "rgba", "stpq"]
@@ -286,6 +338,8 @@ def main():
     h = hashlib.sha256()
     for d in deps:
         h.update(d.read_bytes())
+    if (REF / "Core" / "World.cpp").exists():
+        h.update((REF / "Core" / "World.cpp").read_bytes())
     names = [n for n in SHADERS if (not only or n in only)]
     enabled = []
     for n in names:
@@ -315,8 +369,12 @@ def main():
             print(f"[build_ref] {n}: does not compile through the shim, skipped\n" + "\n".join(r.stderr.split("\n")[:40]))
             continue
         defs.append(f"-DVXREF_HAVE_{n}=1")
+    extra = []
+    if gen_raycast_detect():
+        extra.append(str(GEN / "RaycastDetect.o"))
+        defs.append("-DVXREF_HAVE_RaycastDetect=1")
     cmd = ["g++", "-std=gnu++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fopenmp", "-w", "-shared",
-           f"-I{GEN}", "-o", str(LIB), str(driver)] + defs
+           f"-I{GEN}", "-o", str(LIB), str(driver)] + extra + defs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         print(r.stderr[:6000])

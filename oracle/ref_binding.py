@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 from voxeltracing_b200 import abi  # noqa: E402  (struct layouts only)
 
 LIB_PATH = ROOT / "oracle" / "_ref" / "libvxrt_ref.so"
-HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256}
+HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256, "raycast": 512}
 _lib = None
 
 
@@ -51,6 +51,17 @@ def initial_trace(blocks, df, params: abi.PrimaryParams):
            "inv_t": np.zeros((h, w), np.float32), "t32": np.zeros((h, w), np.float32)}
     lib().vxref_initial_trace(_p(blocks), _p(df), C.byref(params), _p(out["t"]), _p(out["normal"]), _p(out["block"]),
                               _p(out["inv_t"]), _p(out["t32"]))
+    return out
+
+
+def raycast_detect(blocks, positions, directions) -> np.ndarray:
+    """World::RaycastDetect (the reference's own C++, lifted in place): int32 (n,4) = x, y, z, block; -2s when nothing is hit."""
+    b = np.ascontiguousarray(blocks, np.uint8)
+    assert b.shape == (384, 128, 384)
+    o = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+    out = np.zeros((len(o), 4), np.int32)
+    lib().vxref_raycast_detect(_p(b), _p(o), _p(d), len(o), _p(out))
     return out
 
 

@@ -79,6 +79,9 @@ int32_t vxref_available(void) {
 #ifdef VXREF_HAVE_ColorPassDirect
     m |= 256;
 #endif
+#ifdef VXREF_HAVE_RaycastDetect
+    m |= 512;   /* World::RaycastDetect, host C++ lifted from Core/World.cpp (vxref_raycast_detect, generated unit) */
+#endif
     return m;
 }
 

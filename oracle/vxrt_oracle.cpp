@@ -5,6 +5,7 @@
  * root, Core/Shaders/<name> unless noted).  Build: g++ -O2 -ffp-contract=off -fopenmp.
  */
 #include "vxrt_oracle.h"
+#include <algorithm>
 #include "vxo_math.h"
 
 #include <stdlib.h>
@@ -215,6 +216,42 @@ extern "C" void vxo_traverse_batch(const vxo_world* w, const float* origins, con
                                    vxo_hit* hits) {
 #pragma omp parallel for schedule(dynamic, 1024)
     for (int32_t i = 0; i < n; ++i) vxo_traverse(w, origins + 3 * (size_t)i, dirs + 3 * (size_t)i, max_iter, hits + i);
+}
+
+/* World::RaycastDetect (Core/World.cpp:496-546).  The bounds test excludes index 0 as well as the far faces
+ * (`<= 0`, :512-513); GetBlock takes uint16_t coordinates (World.h:46-49) but is only reached inside the bounds. */
+extern "C" void vxo_raycast_detect(const vxo_world* w, const float pos[3], const float dir[3], int32_t out8[8]) {
+    v3 position = V3(pos[0], pos[1], pos[2]);
+    const v3 direction = V3(dir[0], dir[1], dir[2]);
+    const v3 sign = V3(direction.x > 0.0f ? 1.0f : 0.0f, direction.y > 0.0f ? 1.0f : 0.0f, direction.z > 0.0f ? 1.0f : 0.0f);
+    for (int k = 0; k < 8; ++k) out8[k] = k < 4 ? -1 : 0;
+    for (int i = 0; i < 48; ++i) {  /* block reach */
+        v3 tvec = (V3(floorf(position.x + sign.x), floorf(position.y + sign.y), floorf(position.z + sign.z)) - position) / direction;
+        float t = std::min(tvec.x, std::min(tvec.y, tvec.z));
+        position = position + direction * (t + 0.001f);
+        int fx = (int)floorf(position.x), fy = (int)floorf(position.y), fz = (int)floorf(position.z);
+        if (!(fx >= w->nx || fy >= w->ny || fz >= w->nz || fx <= 0 || fy <= 0 || fz <= 0)) {
+            int b = w->blocks[(int)position.x + (size_t)(int)position.y * w->nx + (size_t)(int)position.z * w->nx * w->ny];
+            if (b != 0) {
+                float n[3];
+                for (int j = 0; j < 3; ++j) {
+                    n[j] = (t == idx(tvec, j)) ? 1.0f : 0.0f;
+                    if (idx(sign, j) != 0.0f) n[j] = -n[j];
+                }
+                position = V3(floorf(position.x), floorf(position.y), floorf(position.z));
+                /* the second bounds test (:533-537) repeats the first on the floored position: never fails here */
+                out8[0] = (int)position.x; out8[1] = (int)position.y; out8[2] = (int)position.z;
+                out8[3] = w->blocks[out8[0] + (size_t)out8[1] * w->nx + (size_t)out8[2] * w->nx * w->ny];
+                out8[4] = (int)n[0]; out8[5] = (int)n[1]; out8[6] = (int)n[2];
+                out8[7] = 1;
+                return;
+            }
+        }
+    }
+}
+extern "C" void vxo_raycast_detect_batch(const vxo_world* w, const float* pos, const float* dir, int32_t n, int32_t* out8) {
+#pragma omp parallel for schedule(static, 256)
+    for (int32_t i = 0; i < n; ++i) vxo_raycast_detect(w, pos + 3 * (size_t)i, dir + 3 * (size_t)i, out8 + 8 * (size_t)i);
 }
 
 /* Plain Amanatides–Woo grid walk (the style of Shaders/Implementations/DDA/DDA.glsl:134-253),

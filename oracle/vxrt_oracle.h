@@ -69,6 +69,13 @@ float vxo_traverse_alpha(const struct vxo_scene* s, const float origin[3], const
 void vxo_bind_alpha_scene(const struct vxo_scene* s);
 /* g_K = 1 / (tan(radians(fov) / (2 * width)) * 2)  (InitialRayTraceFrag.glsl:438, ShadowRayTraceFrag.glsl:419) */
 float vxo_alpha_g_k(float fov_degrees, int32_t width);
+/* World::RaycastDetect (Core/World.cpp:496-546), the CPU picking ray behind block placement / removal
+ * (World::Raycast, Core/World.cpp:214-262, uses the same march and adds the face normal).  out8 = hit voxel x, y, z,
+ * block id, face normal x, y, z (what World::Raycast derives: -/+1 on every axis whose slab was hit), found (1 / 0).
+ * No hit within the 48-step reach: the reference falls off the end of the function (undefined); here found = 0 and
+ * x = y = z = block = -1.                                                                                    */
+void vxo_raycast_detect(const vxo_world* w, const float pos[3], const float dir[3], int32_t out8[8]);
+void vxo_raycast_detect_batch(const vxo_world* w, const float* pos, const float* dir, int32_t n, int32_t* out8);
 /* plain Amanatides-Woo DDA returning the first solid voxel (self-check).
  * returns 1 and fills voxel[3] on hit, 0 on leaving the volume / max_steps.                 */
 int32_t vxo_plain_dda(const vxo_world* w, const float origin[3], const float dir[3], int32_t max_steps,

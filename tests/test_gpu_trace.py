@@ -250,3 +250,21 @@ def test_async_readback_is_ordered_against_the_next_pass(scene):
     with pytest.raises(engine.VxrtError):
         c.read_attachment_async(abi.ATT_INITIAL_T, np.empty((h, w + 1), np.float16)) if False else c._check(
             c._lib.vxrt_cuda_read_attachment_async(c._h, abi.ATT_INITIAL_T, bufs[0][0].numpy().ctypes.data, 12))
+
+
+def test_picking_ray_matches_oracle_and_reference_golden(scene):
+    """vxrt_cuda_raycast_detect == World::RaycastDetect: every field against the oracle on 200k rays, hit voxels against
+    the committed output of the reference's own function."""
+    import pick_util as pu
+    from pathlib import Path
+
+    c, ow, _ = scene
+    o, d = pu.pick_rays(200_000, 3)
+    got, want = c.raycast_detect(o, d), ow.raycast_detect(o, d)
+    assert np.array_equal(got, want)
+    assert 0.1 < (got[:, 7] == 1).mean() < 0.9
+    g = np.load(Path(__file__).resolve().parent / "golden" / "pick_ref.npz")
+    r = c.raycast_detect(g["positions"], g["directions"])
+    found = r[:, 7] == 1
+    assert np.array_equal(r[found, :4], g["hits"][found]) and (g["hits"][~found] == -2).all()
+    assert len(c.raycast_detect(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))) == 0

@@ -175,6 +175,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),
         "vxrt_cuda_shadow_trace": (C.c_int, [vp, P(ShadowParams)]),
         "vxrt_cuda_trace_rays": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+        "vxrt_cuda_raycast_detect": (C.c_int, [vp, vp, vp, i32, vp]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
         "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
         "vxrt_cuda_gather_peak": (C.c_int, [vp, i32, P(C.c_double)]),

@@ -444,6 +444,32 @@ int vxrt_cuda_trace_rays(vxrt_ctx* c, const float* origins, const float* directi
     return VXRT_OK;
 }
 
+int vxrt_cuda_raycast_detect(vxrt_ctx* c, const float* positions, const float* directions, int32_t n, int32_t* out) {
+    REQUIRE_CTX(c);
+    if (n < 0) return vxrt_fail(VXRT_E_INVALID, "raycast_detect: n < 0");
+    if (n == 0) return VXRT_OK;
+    REQUIRE_PTR(positions); REQUIRE_PTR(directions); REQUIRE_PTR(out);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "raycast_detect before upload_world");
+    const size_t vec_bytes = ((size_t)n * 3 * sizeof(float) + 255) / 256 * 256, need = 2 * vec_bytes + (size_t)n * 8 * sizeof(int32_t);
+    if (need > c->ray_cap) {
+        if (c->d_ray_buf) VX_CUDA(cudaFree(c->d_ray_buf));
+        c->d_ray_buf = nullptr; c->ray_cap = 0;
+        VX_CUDA(cudaMalloc(&c->d_ray_buf, need));
+        c->ray_cap = need;
+    }
+    char* base = (char*)c->d_ray_buf;
+    float* d_o = (float*)base;
+    float* d_d = (float*)(base + vec_bytes);
+    int32_t* d_r = (int32_t*)(base + 2 * vec_bytes);
+    VX_CUDA(cudaMemcpyAsync(d_o, positions, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(d_d, directions, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int rc = vxrt_launch_raycast_detect(c, d_o, d_d, n, d_r);
+    if (rc) return rc;
+    VX_CUDA(cudaMemcpyAsync(out, d_r, (size_t)n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
 int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "shadow_trace needs a world and a distance field");

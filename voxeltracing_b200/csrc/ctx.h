@@ -133,6 +133,7 @@ int vxrt_launch_df_slab_phase_b(vxrt_ctx* c, int slab, int nslabs, const int* d_
                                 const void* last_planes);
 int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p);
 int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p);
+int vxrt_launch_raycast_detect(vxrt_ctx* c, const float* d_pos, const float* d_dir, int n, int32_t* d_out);
 int vxrt_launch_gather_peak(vxrt_ctx* c, int rounds, double* sectors_per_second);
 int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int n, int max_iter, vxrt_ray_hit* d_hits);
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp);

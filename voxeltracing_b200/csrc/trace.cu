@@ -326,6 +326,50 @@ int vxrt_launch_trace_rays(vxrt_ctx* c, const float* d_o, const float* d_d, int 
     return VXRT_OK;
 }
 
+// ---- picking ray (vxrt_cuda_raycast_detect): World::RaycastDetect, Core/World.cpp:496-546 ----------------------------
+namespace {
+__global__ void __launch_bounds__(128) raycast_detect_kernel(const uint8_t* __restrict__ blocks, int nx, int ny, int nz, const float* __restrict__ pos,
+                                                            const float* __restrict__ dir, int n, int32_t* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    f3 position = F3(pos[3 * r], pos[3 * r + 1], pos[3 * r + 2]);
+    const f3 direction = F3(dir[3 * r], dir[3 * r + 1], dir[3 * r + 2]);
+    const f3 sign = F3(direction.x > 0.0f ? 1.0f : 0.0f, direction.y > 0.0f ? 1.0f : 0.0f, direction.z > 0.0f ? 1.0f : 0.0f);
+    int32_t res[8] = {-1, -1, -1, -1, 0, 0, 0, 0};
+    for (int i = 0; i < 48; ++i) {  // block reach
+        const f3 tvec = (F3(floorf(position.x + sign.x), floorf(position.y + sign.y), floorf(position.z + sign.z)) - position) / direction;
+        const float t = fminf(tvec.x, fminf(tvec.y, tvec.z));  // std::min chain: NaN handling differs only when a component is NaN
+        position = position + direction * (t + 0.001f);
+        const int fx = cvt_floor(position.x), fy = cvt_floor(position.y), fz = cvt_floor(position.z);
+        if (!(fx >= nx || fy >= ny || fz >= nz || fx <= 0 || fy <= 0 || fz <= 0)) {
+            const size_t at = (size_t)fx + (size_t)fy * nx + (size_t)fz * nx * ny;  // (int)position == floor inside the bounds
+            const int b = __ldg(blocks + at);
+            if (b != 0) {
+                res[0] = fx; res[1] = fy; res[2] = fz; res[3] = b;
+                const float tv[3] = {tvec.x, tvec.y, tvec.z}, sg[3] = {sign.x, sign.y, sign.z};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int nj = (t == tv[j]) ? 1 : 0;
+                    if (sg[j] != 0.0f) nj = -nj;
+                    res[4 + j] = nj;
+                }
+                res[7] = 1;
+                break;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[8 * (size_t)r + k] = res[k];
+}
+}  // namespace
+
+int vxrt_launch_raycast_detect(vxrt_ctx* c, const float* d_pos, const float* d_dir, int n, int32_t* d_out) {
+    raycast_detect_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_blocks, c->nx, c->ny, c->nz, d_pos, d_dir, n, d_out);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
 // ---- gather roof (vxrt_cuda_gather_peak) -----------------------------------------------------------------
 // The operative roof of the traversal is the rate at which the memory system serves independent 1-byte loads
 // from an L2-resident grid (each moves one 32-byte sector).  This kernel measures it on the distance field

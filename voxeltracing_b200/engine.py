@@ -280,6 +280,16 @@ class Context:
         self._check(self._lib.vxrt_cuda_trace_rays(self._h, _p(o), _p(d), len(o), int(max_iterations), _p(hits)))
         return hits
 
+    def raycast_detect(self, positions, directions) -> np.ndarray:
+        """World::RaycastDetect over (n,3) rays; int32 (n,8): hit voxel x, y, z, block, face normal xyz, found."""
+        o = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        if o.shape != d.shape:
+            raise ValueError("positions and directions must have the same shape")
+        out = np.zeros((len(o), 8), dtype=np.int32)
+        self._check(self._lib.vxrt_cuda_raycast_detect(self._h, _p(o), _p(d), len(o), _p(out)))
+        return out
+
     # -- statistics --
     def stats_enable(self, on: bool):
         self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))
