@@ -72,12 +72,18 @@ __device__ __forceinline__ unsigned sweep_word_down(unsigned w, unsigned& c) {
 //   Y       local forward (X carries applied on the fly) + backward sweep per (word column, y-segment)
 //   ycarry  per (word column, y-segment): values arriving from above / below
 //   store   Y carries applied, 16-byte stores
-constexpr int XY_THREADS = 384;
+#ifndef VX_XY_THREADS
+#define VX_XY_THREADS 384
+#endif
+#ifndef VX_XY_OCC
+#define VX_XY_OCC 3
+#endif
+constexpr int XY_THREADS = VX_XY_THREADS;
 constexpr int XY_BATCH = 8;   // 16-byte loads in flight per thread
 constexpr int XY_MAX_SEG = 8;
 constexpr unsigned NO_CARRY = 0x03ffu;  // above every distance, small enough to add offsets in a u16 lane
 
-__global__ void __launch_bounds__(XY_THREADS, 3) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
+__global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
                                                                     uint8_t* __restrict__ df, int nx, int ny,
                                                                     int z_begin, unsigned maxd, int sx, int sy) {
     extern __shared__ uint4 smem4[];
