@@ -137,7 +137,18 @@ typedef enum vxrt_attachment {
     VXRT_ATT_REFL_COLOR = 15,      /* RGBA16F                      ReflectionTraceFBO[0] */
     VXRT_ATT_REFL_HITDIST = 16,    /* R16F                                            [1] */
     VXRT_ATT_REFL_EMISSIVE = 17,   /* R8                                              [2] */
-    VXRT_ATT_COUNT = 18
+    /* SVGF chain of the diffuse GI (Core/Pipeline.cpp:1151-1156): an image set is four consecutive ids
+     * (SH RGBA16F, CoCg RG16F, X, AO/sky RG8); X is the utility triple RGB16F (accumulated frames, second
+     * moment, luminance) of the temporal sets and the variance R16F of the others */
+    VXRT_ATT_SVGF_TEMPORAL_A = 18, /* DiffuseTemporalFBO1: +0 SH, +1 CoCg, +2 utility RGB16F, +3 AO/sky */
+    VXRT_ATT_SVGF_TEMPORAL_B = 22, /* DiffuseTemporalFBO2 */
+    VXRT_ATT_SVGF_VARIANCE = 26,   /* VarianceFBO: +0 SH, +1 CoCg, +2 variance R16F (+3 unused) */
+    VXRT_ATT_SVGF_DENOISE_A = 30,  /* DiffuseDenoiseFBO: +0 SH, +1 CoCg, +2 variance R16F, +3 AO/sky */
+    VXRT_ATT_SVGF_DENOISE_B = 34,  /* DiffuseDenoisedFBO2 */
+    VXRT_ATT_PREV_INITIAL_T = 38,      /* previous frame's primary G-buffer (the engine ping-pongs InitialTraceFBO_1/_2, */
+    VXRT_ATT_PREV_INITIAL_NORMAL = 39, /*   Core/Pipeline.cpp:2046-2048); filled by vxrt_cuda_svgf_end_frame */
+    VXRT_ATT_PREV_INITIAL_BLOCK = 40,
+    VXRT_ATT_COUNT = 41
 } vxrt_attachment;
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
@@ -323,6 +334,55 @@ int vxrt_cuda_trace_rays(vxrt_ctx* ctx, const float* origins, const float* direc
  * reference's `<= 0` test.  Nothing hit within reach: found = 0 and x = y = z = block = -1 (the reference function has
  * no return statement on that path).  The engine follows a hit with vxrt_cuda_edit_blocks + generate_distance_field. */
 int vxrt_cuda_raycast_detect(vxrt_ctx* ctx, const float* positions, const float* directions, int32_t n, int32_t* out);
+
+/* ---- SVGF denoiser chain of the diffuse GI: Core/Shaders/SVGF/{TemporalFilter,VarianceEstimate,
+ * SpatialFilter}.glsl, orchestrated by Core/Pipeline.cpp:2377-2710 ----
+ * Every pass reads and writes image sets named by their first attachment id (VXRT_ATT_GI_SH for the raw trace output,
+ * VXRT_ATT_SVGF_*); the caller sequences them like the engine: temporal (current raw set + previous temporal set ->
+ * current temporal set, ping-ponged by frame parity), variance, five spatial iterations with steps 16, 8, 4, 2, 1
+ * ping-ponging DENOISE_A / DENOISE_B, then vxrt_cuda_svgf_end_frame.  The optional 3x3 pre-pass
+ * (Spatial3x3Initial.glsl, PreTemporalSpatialPass) is not covered: the temporal pass takes the raw trace output. */
+typedef struct vxrt_svgf_temporal_params {   /* Pipeline.cpp:2428-2528 */
+    float inv_view[16], inv_projection[16];  /* u_InverseView, u_InverseProjection (v_RayOrigin = u_InverseView[3]) */
+    float prev_view[16], prev_projection[16];/* u_PrevView, u_PrevProjection */
+    int32_t width, height;                   /* size of the GI / temporal images */
+    int32_t in_set;                          /* VXRT_ATT_GI_SH */
+    int32_t history_set;                     /* previous frame's temporal set */
+    int32_t out_set;                         /* this frame's temporal set */
+    int32_t be_useful;                       /* u_BeUseful (DO_SVGF_TEMPORAL) */
+    vxrt_tile tile;
+} vxrt_svgf_temporal_params;
+int vxrt_cuda_svgf_temporal(vxrt_ctx* ctx, const vxrt_svgf_temporal_params* p);
+
+typedef struct vxrt_svgf_variance_params {   /* Pipeline.cpp:2532-2567 */
+    float inv_view[16], inv_projection[16];
+    int32_t width, height;
+    int32_t in_set;                          /* this frame's temporal set */
+    int32_t do_spatial;                      /* DO_SPATIAL (DO_VARIANCE_SPATIAL, true) */
+    int32_t aggressive_disocclusion;         /* AGGRESSIVE_DISOCCLUSION_HANDLING (true) */
+    vxrt_tile tile;
+} vxrt_svgf_variance_params;                 /* writes VXRT_ATT_SVGF_VARIANCE */
+int vxrt_cuda_svgf_variance(vxrt_ctx* ctx, const vxrt_svgf_variance_params* p);
+
+typedef struct vxrt_svgf_spatial_params {    /* Pipeline.cpp:2592-2700 */
+    float inv_view[16], inv_projection[16];
+    int32_t width, height;
+    int32_t in_set;                          /* SH, CoCg, variance and AO/sky of the previous iteration (VARIANCE set first) */
+    int32_t ao_set;                          /* set whose +3 image is u_AO: the temporal set for iteration 0, else in_set */
+    int32_t temporal_set;                    /* this frame's temporal set: u_Utility (+3!, Pipeline.cpp:2693) and u_TemporalMoment (+2) */
+    int32_t out_set;
+    int32_t step;                            /* u_Step */
+    int32_t large_kernel;                    /* u_LargeKernel (false) */
+    int32_t do_spatial;                      /* DO_SPATIAL (true) */
+    int32_t aggressive_disocclusion;         /* AGGRESSIVE_DISOCCLUSION_HANDLING (true) */
+    float color_phi_bias;                    /* u_ColorPhiBias (2.8) */
+    float time;                              /* u_Time (glfwGetTime) */
+    float resolution_scale;                  /* u_ResolutionScale (DiffuseIndirectSuperSampleRes, 0.25) */
+    vxrt_tile tile;
+} vxrt_svgf_spatial_params;
+int vxrt_cuda_svgf_spatial(vxrt_ctx* ctx, const vxrt_svgf_spatial_params* p);
+/* end of frame: this frame's primary G-buffer (INITIAL_T / NORMAL / BLOCK) becomes VXRT_ATT_PREV_INITIAL_* */
+int vxrt_cuda_svgf_end_frame(vxrt_ctx* ctx);
 
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {

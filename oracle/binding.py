@@ -208,6 +208,30 @@ def _stats(st):
     return {"rays": st.rays, "iterations": st.iterations, "dda_steps": st.dda_steps, "hits": st.hits}
 
 
+class SvgfSet(C.Structure):
+    _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("x", C.c_void_p), ("aosky", C.c_void_p)]
+
+
+def svgf_set(d: dict) -> SvgfSet:
+    """d: {"sh": f16 (h,w,4), "cocg": f16 (h,w,2), "x": f16 (h,w[,3]), "aosky": u8 (h,w,2)} (arrays must stay alive)."""
+    return SvgfSet(d["sh"].ctypes.data, d["cocg"].ctypes.data, d["x"].ctypes.data, d["aosky"].ctypes.data)
+
+
+def svgf_alloc(h: int, w: int, x_channels: int) -> dict:
+    return {"sh": np.zeros((h, w, 4), np.float16), "cocg": np.zeros((h, w, 2), np.float16),
+            "x": np.zeros((h, w, x_channels) if x_channels > 1 else (h, w), np.float16), "aosky": np.zeros((h, w, 2), np.uint8)}
+
+
+def svgf_temporal(p: "abi.SvgfTemporalParams", cur: dict, hist: dict, g: dict, prev_g: dict, fn=None) -> dict:
+    """TemporalFilter.glsl.  cur: raw GI set (x = luminance R16F), hist: previous temporal set (x = utility RGB16F),
+    g / prev_g: {"t": f16, "normal": u8, "block": u8}.  fn: the entry point (oracle by default, oracle/_ref for pinning)."""
+    out = svgf_alloc(p.height, p.width, 3)
+    a, b, o = svgf_set(cur), svgf_set(hist), svgf_set(out)
+    (fn or lib().vxo_svgf_temporal)(C.byref(p), C.byref(a), C.byref(b), _p(g["t"]), _p(g["normal"]), _p(g["block"]), _p(prev_g["t"]),
+                                   _p(prev_g["normal"]), _p(prev_g["block"]), C.byref(o))
+    return out
+
+
 class OracleScene:
     """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
 

@@ -36,6 +36,10 @@ SHADERS = {
     "DiffuseRayTraceFrag": ("DiffuseRayTraceFrag.glsl", "fragment"),
     "ReflectionTraceFrag": ("ReflectionTraceFrag.glsl", "fragment"),
     "GenerateGBuffer": ("GenerateGBuffer.glsl", "fragment"),
+    # SVGF chain of the diffuse GI: temporal accumulation, variance estimate, a-trous spatial filter
+    "SVGFTemporal": ("SVGF/TemporalFilter.glsl", "fragment"),
+    "SVGFVariance": ("SVGF/VarianceEstimate.glsl", "fragment"),
+    "SVGFSpatial": ("SVGF/SpatialFilter.glsl", "fragment"),
     # the colour pass composites sky / clouds / denoised GI (out of scope); only its Cook-Torrance
     # functions are compiled: they are cut out of the file by name, unmodified
     "ColorPassDirect": ("ColorPassFrag.glsl", "extract"),

@@ -165,6 +165,16 @@ typedef vecn<bool, 2> bvec2; typedef vecn<bool, 3> bvec3; typedef vecn<bool, 4> 
 GLSL_ARITH(vec2, float) GLSL_ARITH(vec3, float) GLSL_ARITH(vec4, float)
 GLSL_ARITH(ivec2, int) GLSL_ARITH(ivec3, int) GLSL_ARITH(ivec4, int)
 GLSL_ARITH(uvec2, uint) GLSL_ARITH(uvec3, uint) GLSL_ARITH(uvec4, uint)
+/* mixed float / integer-vector arithmetic: GLSL converts the integer operand implicitly (ivecN -> vecN), e.g.
+ * `vec2 TexelSize = 1.0f / textureSize(u_SH, 0)` (SVGF/TemporalFilter.glsl:146); without these overloads C++ would
+ * convert the float to int instead */
+#define GLSL_MIXOP(VF, VI, op)                                                                                          \
+    inline VF operator op(float a, const VI& b) { VF r; for (int i = 0; i < (int)(sizeof(VI) / sizeof(int)); ++i) r[i] = a op (float)b[i]; return r; }       \
+    inline VF operator op(const VI& a, float b) { VF r; for (int i = 0; i < (int)(sizeof(VI) / sizeof(int)); ++i) r[i] = (float)a[i] op b; return r; }       \
+    inline VF operator op(const VF& a, const VI& b) { VF r; for (int i = 0; i < (int)(sizeof(VI) / sizeof(int)); ++i) r[i] = a[i] op (float)b[i]; return r; } \
+    inline VF operator op(const VI& a, const VF& b) { VF r; for (int i = 0; i < (int)(sizeof(VI) / sizeof(int)); ++i) r[i] = (float)a[i] op b[i]; return r; }
+#define GLSL_MIX(VF, VI) GLSL_MIXOP(VF, VI, +) GLSL_MIXOP(VF, VI, -) GLSL_MIXOP(VF, VI, *) GLSL_MIXOP(VF, VI, /)
+GLSL_MIX(vec2, ivec2) GLSL_MIX(vec3, ivec3) GLSL_MIX(vec4, ivec4)
 #define GLSL_INTOPS(V, T) GLSL_BINOP(V, T, %) GLSL_BINOP(V, T, >>) GLSL_BINOP(V, T, <<) GLSL_BINOP(V, T, &) GLSL_BINOP(V, T, |) GLSL_BINOP(V, T, ^)
 GLSL_INTOPS(ivec2, int) GLSL_INTOPS(ivec3, int) GLSL_INTOPS(ivec4, int)
 GLSL_INTOPS(uvec2, uint) GLSL_INTOPS(uvec3, uint) GLSL_INTOPS(uvec4, uint)

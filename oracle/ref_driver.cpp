@@ -38,6 +38,16 @@ thread_local uvec3 gl_GlobalInvocationID;
 #ifdef VXREF_HAVE_ReflectionTraceFrag
 #include "ReflectionTraceFrag.cpp"
 #endif
+#ifdef VXREF_HAVE_SVGFTemporal
+#include "SVGFTemporal.cpp"
+#endif
+#ifdef VXREF_HAVE_SVGFVariance
+#include "SVGFVariance.cpp"
+#endif
+#ifdef VXREF_HAVE_SVGFSpatial
+#undef sqr   /* a function in SpatialFilter.glsl, a macro in ReflectionTraceFrag.glsl (one translation unit here) */
+#include "SVGFSpatial.cpp"
+#endif
 #ifdef VXREF_HAVE_ColorPassDirect
 #include "ColorPassDirect.cpp"
 #endif
@@ -78,6 +88,15 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_ColorPassDirect
     m |= 256;
+#endif
+#ifdef VXREF_HAVE_SVGFTemporal
+    m |= 1024;
+#endif
+#ifdef VXREF_HAVE_SVGFVariance
+    m |= 2048;
+#endif
+#ifdef VXREF_HAVE_SVGFSpatial
+    m |= 4096;
 #endif
 #ifdef VXREF_HAVE_RaycastDetect
     m |= 512;   /* World::RaycastDetect, host C++ lifted from Core/World.cpp (vxref_raycast_detect, generated unit) */
@@ -452,3 +471,53 @@ void vxref_reflection_trace(const vxrt_reflection_params* p, const vxref_reflect
 #endif
 
 }  // extern "C"
+
+
+/* ---- SVGF chain of the diffuse GI (Core/Pipeline.cpp:2428-2700) ---- */
+struct vxref_svgf_set { const uint16_t* sh; const uint16_t* cocg; const uint16_t* x; const uint8_t* aosky; };
+struct vxref_svgf_out { uint16_t* sh; uint16_t* cocg; uint16_t* x; uint8_t* aosky; };
+static std::vector<float> svgf_half(const uint16_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = vxo::half_to_float(h[i]); return o; }
+static std::vector<float> svgf_u8(const uint8_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = vxo::unorm8_to_float(h[i]); return o; }
+
+#ifdef VXREF_HAVE_SVGFTemporal
+extern "C" void vxref_svgf_temporal(const vxrt_svgf_temporal_params* p, const vxref_svgf_set* cur, const vxref_svgf_set* hist,
+                                    const uint16_t* g_t, const uint8_t* g_normal, const uint8_t* g_block, const uint16_t* prev_t,
+                                    const uint8_t* prev_normal, const uint8_t* prev_block, const vxref_svgf_out* out) {
+    namespace S = shader_SVGFTemporal;
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = svgf_half(cur->sh, 4 * n), fcc = svgf_half(cur->cocg, 2 * n), flum = svgf_half(cur->x, n), fao = svgf_u8(cur->aosky, 2 * n);
+    auto hsh = svgf_half(hist->sh, 4 * n), hcc = svgf_half(hist->cocg, 2 * n), hut = svgf_half(hist->x, 3 * n), hao = svgf_u8(hist->aosky, 2 * n);
+    auto ft = svgf_half(g_t, n), fn = svgf_u8(g_normal, n), fb = svgf_u8(g_block, n);
+    auto pt = svgf_half(prev_t, n), pn = svgf_u8(prev_normal, n), pb = svgf_u8(prev_block, n);
+    bind2d(S::u_CurrentSH, fsh.data(), W, H, 4, true); bind2d(S::u_CurrentCoCg, fcc.data(), W, H, 2, true);
+    bind2d(S::u_NoisyLuminosity, flum.data(), W, H, 1, true); bind2d(S::u_CurrentAO, fao.data(), W, H, 2, true);
+    bind2d(S::u_PreviousSH, hsh.data(), W, H, 4, true); bind2d(S::u_PrevCoCg, hcc.data(), W, H, 2, true);
+    bind2d(S::u_PreviousUtility, hut.data(), W, H, 3, true); bind2d(S::u_PreviousAO, hao.data(), W, H, 2, true);
+    bind2d(S::u_CurrentPositionTexture, ft.data(), W, H, 1, true); bind2d(S::u_CurrentNormalTexture, fn.data(), W, H, 1, false);
+    bind2d(S::u_CurrentBlockIDTexture, fb.data(), W, H, 1, false);
+    bind2d(S::u_PreviousPositionTexture, pt.data(), W, H, 1, true); bind2d(S::u_PreviousNormalTexture, pn.data(), W, H, 1, false);
+    bind2d(S::u_PrevBlockIDTexture, pb.data(), W, H, 1, false);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_PrevView.load(p->prev_view); S::u_PrevProjection.load(p->prev_projection);
+    S::u_MinimumMix = 0.0f; S::u_MaximumMix = 0.96f;   /* Pipeline.cpp:2464-2465 (unused by the shader body) */
+    S::u_BeUseful = p->be_useful != 0;
+    S::u_Time = 0.0f; S::u_DeltaTime = 0.0f;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam;
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out->sh[4 * i + c] = vxo::float_to_half(S::o_SH[c]);
+            for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
+            for (int c = 0; c < 3; ++c) out->x[3 * i + c] = vxo::float_to_half(S::o_Utility[c]);
+            for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOAndSkyLighting[c]);
+        }
+}
+#endif

@@ -1,0 +1,185 @@
+/*
+ * vxrt_oracle_svgf.cpp — CPU ORACLE (TEST INFRASTRUCTURE ONLY, see vxrt_oracle.h).
+ * SVGF denoiser chain of the diffuse GI: Core/Shaders/SVGF/TemporalFilter.glsl, VarianceEstimate.glsl,
+ * SpatialFilter.glsl (dispatch and bindings: Core/Pipeline.cpp:2428-2700).  Citations are file:line of the reference.
+ * FBO attachments are LINEAR + REPEAT for the float formats and RG8, NEAREST for the R8 G-buffer planes
+ * (Core/Pipeline.cpp:1142-1156, Core/GLClasses/Framebuffer.h:16-18).
+ */
+#include "vxrt_oracle.h"
+#include "vxo_math.h"
+#include "vxo_texture.h"
+
+#include <vector>
+
+using namespace vxo;
+
+namespace {
+
+inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+}
+inline v3 ray_direction_at(const float* inv_view, const float* inv_proj, v2 ss) {
+    v4 clip = V4(ss.x * 2.0f - 1.0f, ss.y * 2.0f - 1.0f, -1.0f, 1.0f);
+    v4 e = mat4_mul(inv_proj, clip);
+    v4 r = mat4_mul(inv_view, V4(e.x, e.y, -1.0f, 0.0f));
+    return V3(r.x, r.y, r.z);
+}
+/* GetNormalFromID (TemporalFilter.glsl:111-123): idx > 5 -> (1,1,1) */
+inline v3 normal_from_id(float n) {
+    static const v3 N[6] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}};
+    int i = cvt_round(n * 10.0f);
+    if (i > 5) return V3(1.0f, 1.0f, 1.0f);
+    return N[i];
+}
+inline Tex2D view(const std::vector<float>& d, int w, int h, int ch, bool linear) { Tex2D t; t.data = d.data(); t.w = w; t.h = h; t.ch = ch; t.linear = linear; return t; }
+std::vector<float> from_half(const uint16_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = half_to_float(h[i]); return o; }
+std::vector<float> from_u8(const uint8_t* h, size_t n) { std::vector<float> o(n); for (size_t i = 0; i < n; ++i) o[i] = unorm8_to_float(h[i]); return o; }
+inline float gclampf(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+inline bool in_screen_space(v2 v) { return v.x < 1.0f && v.x > 0.0f && v.y < 1.0f && v.y > 0.0f; }
+/* SHToY (VarianceEstimate.glsl:43-46) */
+inline float sh_to_y(v4 sh) { return gmax(0.0f, 3.544905f * sh.w); }
+
+struct GBuf {
+    Tex2D t, n, b;
+    const float* inv_view; const float* inv_proj;
+    v3 origin;
+    /* GetPositionAt (TemporalFilter.glsl:80-84): current inverse matrices and ray origin for BOTH frames' depth */
+    v4 position_at(const Tex2D& pos, v2 txc) const {
+        float Dist = tex2d_sample(pos, txc.x, txc.y).x;
+        v3 p = origin + normalize(ray_direction_at(inv_view, inv_proj, txc)) * Dist;
+        return V4(p.x, p.y, p.z, Dist);
+    }
+};
+
+}  // namespace
+
+/* one image set as the attachments hold it */
+struct vxo_svgf_set {
+    const uint16_t* sh;    /* RGBA16F */
+    const uint16_t* cocg;  /* RG16F */
+    const uint16_t* x;     /* RGB16F utility or R16F variance / luminance */
+    const uint8_t* aosky;  /* RG8 */
+};
+struct vxo_svgf_out {
+    uint16_t* sh; uint16_t* cocg; uint16_t* x; uint8_t* aosky;
+};
+
+/* TemporalFilter.glsl main() (:133-344).  cur.x = u_NoisyLuminosity (R16F); hist.x = u_PreviousUtility (RGB16F).
+ * Jitter = ivec2((GradientNoise() - 0.5) * 1.0) is (0, 0) for every pixel: the noise is in [0, 1) and int() truncates. */
+extern "C" void vxo_svgf_temporal(const vxrt_svgf_temporal_params* p, const vxo_svgf_set* cur, const vxo_svgf_set* hist,
+                                  const uint16_t* g_t, const uint8_t* g_normal, const uint8_t* g_block,
+                                  const uint16_t* prev_t, const uint8_t* prev_normal, const uint8_t* prev_block, const vxo_svgf_out* out) {
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = from_half(cur->sh, 4 * n), fcc = from_half(cur->cocg, 2 * n), flum = from_half(cur->x, n), fao = from_u8(cur->aosky, 2 * n);
+    auto hsh = from_half(hist->sh, 4 * n), hcc = from_half(hist->cocg, 2 * n), hut = from_half(hist->x, 3 * n), hao = from_u8(hist->aosky, 2 * n);
+    auto ft = from_half(g_t, n), fn = from_u8(g_normal, n), fb = from_u8(g_block, n);
+    auto pt = from_half(prev_t, n), pn = from_u8(prev_normal, n), pb = from_u8(prev_block, n);
+    const Tex2D tSH = view(fsh, W, H, 4, true), tCC = view(fcc, W, H, 2, true), tLum = view(flum, W, H, 1, true), tAO = view(fao, W, H, 2, true);
+    const Tex2D pSH = view(hsh, W, H, 4, true), pCC = view(hcc, W, H, 2, true), pUt = view(hut, W, H, 3, true), pAO = view(hao, W, H, 2, true);
+    const Tex2D tT = view(ft, W, H, 1, true), tN = view(fn, W, H, 1, false), tB = view(fb, W, H, 1, false);
+    const Tex2D qT = view(pt, W, H, 1, true), qN = view(pn, W, H, 1, false), qB = view(pb, W, H, 1, false);
+    GBuf g; g.inv_view = p->inv_view; g.inv_proj = p->inv_projection; g.origin = V3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    /* u_PrevProjection * u_PrevView (left to right: the matrix product first), columns = M * column */
+    float PV[16];
+    for (int j = 0; j < 4; ++j) {
+        v4 c = mat4_mul(p->prev_projection, V4(p->prev_view[4 * j], p->prev_view[4 * j + 1], p->prev_view[4 * j + 2], p->prev_view[4 * j + 3]));
+        PV[4 * j] = c.x; PV[4 * j + 1] = c.y; PV[4 * j + 2] = c.z; PV[4 * j + 3] = c.w;
+    }
+    const float Weights[5] = {3.0f / 32.0f, 3.0f / 32.0f, 9.0f / 64.0f, 3.0f / 32.0f, 3.0f / 32.0f};
+    const v2 Offsets[5] = {{1, 0}, {0, 1}, {0, 0}, {-1, 0}, {0, -1}};
+    const v2 TexelSize = V2(1.0f / (float)W, 1.0f / (float)H);
+    int r0, r1;
+    tile_rows(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const v2 tc = V2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            const v4 BasePosition = g.position_at(tT, tc);
+            const v3 BaseNormal = normal_from_id(tex2d_sample(tN, tc.x, tc.y).x);
+            const v4 BaseSH = tex2d_sample(tSH, tc.x, tc.y);
+            const v4 cc = tex2d_sample(tCC, tc.x, tc.y);
+            const v2 BaseCoCg = V2(cc.x, cc.y);
+            const v4 ao = tex2d_sample(tAO, tc.x, tc.y);
+            const v2 BaseAOSky = V2(ao.x, ao.y);
+            float TotalWeight = 0.0f, SumLuminosity = 0.0f, SumSPP = 0.0f, SumMoment = 0.0f;
+            v4 SumSH = V4(0.0f, 0.0f, 0.0f, 0.0f);
+            v2 SumCoCg = V2(0.0f, 0.0f), SumAOSky = V2(0.0f, 0.0f);
+            v4 Proj = mat4_mul(PV, V4(BasePosition.x, BasePosition.y, BasePosition.z, 1.0f));
+            const v2 ReprojectedCoord = V2((Proj.x / Proj.w) * 0.5f + 0.5f, (Proj.y / Proj.w) * 0.5f + 0.5f);
+            const float BaseLuminosity = tex2d_sample(tLum, tc.x, tc.y).x;
+            const int BaseBlock = iclamp(cvt_trunc(floorf(tex2d_sample(tB, tc.x, tc.y).x * 255.0f)), 0, 127);
+            int SuccessfulSamples = 0;
+            bool DoBlockWeight = true, DoNormalWeight = true;
+            float Tol = 0.75f;
+            const float DistanceToPlayer = distance(V3(BasePosition.x, BasePosition.y, BasePosition.z), g.origin);
+            if (DistanceToPlayer < 4.0f) Tol = 0.3f;
+            else if (DistanceToPlayer < 6.0f) Tol = 0.65f;
+            else if (DistanceToPlayer < 8.0f) Tol = 0.85f;
+            else if (DistanceToPlayer < 16.0f) Tol = 1.414f;
+            else if (DistanceToPlayer < 32.0f) Tol = 2.4f;
+            else if (DistanceToPlayer < 48.0f) { Tol = 3.5f; DoBlockWeight = false; }
+            else if (DistanceToPlayer < 64.0f) { Tol = 4.2f; DoBlockWeight = false; }
+            else if (DistanceToPlayer < 96.0f) { Tol = 6.25f; DoBlockWeight = false; DoNormalWeight = false; }
+            else if (DistanceToPlayer < 128.0f) { Tol = 9.0f; DoBlockWeight = false; DoNormalWeight = false; }
+            else if (DistanceToPlayer < 200.0f) { Tol = 14.0f; DoBlockWeight = false; DoNormalWeight = false; }
+            for (int i = 0; i < 5; ++i) {
+                const v2 sc = V2(ReprojectedCoord.x + (Offsets[i].x + 0.0f) * TexelSize.x, ReprojectedCoord.y + (Offsets[i].y + 0.0f) * TexelSize.y);
+                const float b = 0.0035f;  /* InThresholdedScreenSpace (:101-105) */
+                if (!(sc.x < 1.0f - b && sc.x > b && sc.y < 1.0f - b && sc.y > b)) continue;
+                const v4 Prev = g.position_at(qT, sc);
+                const v3 PrevNormal = normal_from_id(tex2d_sample(qN, sc.x, sc.y).x);
+                const v3 d = V3(fabsf(BasePosition.x - Prev.x), fabsf(BasePosition.y - Prev.y), fabsf(BasePosition.z - Prev.z));
+                const float PositionError = dot(d, d);
+                const float CurrentWeight = Weights[i];
+                const int SampleBlock = iclamp(cvt_trunc(floorf(tex2d_sample(qB, sc.x, sc.y).x * 255.0f)), 0, 127);
+                bool SampleValid = false;
+                if (PositionError < Tol && ((Prev.w < 0.0f) == (BasePosition.w < 0.0f))) {
+                    SampleValid = true;
+                    if (DoNormalWeight && (PrevNormal.x != BaseNormal.x || PrevNormal.y != BaseNormal.y || PrevNormal.z != BaseNormal.z)) SampleValid = false;
+                    if (DoBlockWeight && BaseBlock != SampleBlock) SampleValid = false;
+                }
+                if (SampleValid) {
+                    const v4 u = tex2d_sample(pUt, sc.x, sc.y), s = tex2d_sample(pSH, sc.x, sc.y), c2 = tex2d_sample(pCC, sc.x, sc.y), a2 = tex2d_sample(pAO, sc.x, sc.y);
+                    SumSH = V4(SumSH.x + s.x * CurrentWeight, SumSH.y + s.y * CurrentWeight, SumSH.z + s.z * CurrentWeight, SumSH.w + s.w * CurrentWeight);
+                    SumCoCg = V2(SumCoCg.x + c2.x * CurrentWeight, SumCoCg.y + c2.y * CurrentWeight);
+                    SumSPP += u.x * CurrentWeight;
+                    SumMoment += u.y * CurrentWeight;
+                    SumLuminosity += u.z * CurrentWeight;
+                    SumAOSky = V2(SumAOSky.x + a2.x * CurrentWeight, SumAOSky.y + a2.y * CurrentWeight);
+                    TotalWeight += CurrentWeight;
+                    SuccessfulSamples++;
+                }
+            }
+            if (TotalWeight > 0.001f) {
+                SumSH = V4(SumSH.x / TotalWeight, SumSH.y / TotalWeight, SumSH.z / TotalWeight, SumSH.w / TotalWeight);
+                SumCoCg = V2(SumCoCg.x / TotalWeight, SumCoCg.y / TotalWeight);
+                SumMoment /= TotalWeight; SumSPP /= TotalWeight; SumLuminosity /= TotalWeight;
+                SumAOSky = V2(SumAOSky.x / TotalWeight, SumAOSky.y / TotalWeight);
+            } else {
+                SuccessfulSamples = 0;
+            }
+            const float Increment = p->be_useful ? 1.0f : 0.0f;
+            float SumSPPAndIncrement = SumSPP + Increment;
+            if (SuccessfulSamples <= 0) SumSPPAndIncrement = 0.01f;
+            float BlendFactor = gmax(1.0f / SumSPPAndIncrement, 0.05f);
+            const float MomentFactor = gmax(1.0f / SumSPPAndIncrement, 0.05f);
+            if (!p->be_useful) BlendFactor = 0.99f;
+            float UtilitySPP = SumSPPAndIncrement;
+            if (SuccessfulSamples <= 0) UtilitySPP = 0.0f;
+            const float UtilityMoment = (1.0f - MomentFactor) * SumMoment + MomentFactor * (BaseLuminosity * BaseLuminosity);
+            const float StoreLuma = gmix(SumLuminosity, BaseLuminosity, BlendFactor);
+            v4 oSH = V4(gmix(SumSH.x, BaseSH.x, BlendFactor), gmix(SumSH.y, BaseSH.y, BlendFactor), gmix(SumSH.z, BaseSH.z, BlendFactor), gmix(SumSH.w, BaseSH.w, BlendFactor));
+            v2 oCC = V2(gmix(SumCoCg.x, BaseCoCg.x, BlendFactor), gmix(SumCoCg.y, BaseCoCg.y, BlendFactor));
+            v2 oAO = V2(gmix(SumAOSky.x, BaseAOSky.x, BlendFactor), gmix(SumAOSky.y, BaseAOSky.y, BlendFactor));
+            if (SuccessfulSamples <= 0) { oSH = BaseSH; oCC = BaseCoCg; oAO = BaseAOSky; }
+            const size_t i = (size_t)py * W + px;
+            out->sh[4 * i] = float_to_half(gclampf(oSH.x, -100.0f, 100.0f)); out->sh[4 * i + 1] = float_to_half(gclampf(oSH.y, -100.0f, 100.0f));
+            out->sh[4 * i + 2] = float_to_half(gclampf(oSH.z, -100.0f, 100.0f)); out->sh[4 * i + 3] = float_to_half(gclampf(oSH.w, -100.0f, 100.0f));
+            out->cocg[2 * i] = float_to_half(gclampf(oCC.x, -10.0f, 100.0f)); out->cocg[2 * i + 1] = float_to_half(gclampf(oCC.y, -10.0f, 100.0f));
+            out->x[3 * i] = float_to_half(gclampf(UtilitySPP, -150.0f, 150.0f)); out->x[3 * i + 1] = float_to_half(gclampf(UtilityMoment, -150.0f, 150.0f));
+            out->x[3 * i + 2] = float_to_half(gclampf(StoreLuma, -150.0f, 150.0f));
+            out->aosky[2 * i] = float_to_unorm8(gclampf(oAO.x, 0.0f, 1.0f)); out->aosky[2 * i + 1] = float_to_unorm8(gclampf(oAO.y, 0.0f, 1.0f));
+        }
+}

@@ -1,0 +1,48 @@
+"""Two-frame inputs for the SVGF tests: G-buffers and raw GI outputs of two nearby camera poses in the rooms world,
+produced by the oracle (CPU) so the same arrays feed the oracle, oracle/_ref and the CUDA passes."""
+import numpy as np
+
+import scene_util as su
+from oracle import binding as ob
+from voxeltracing_b200 import abi, host_api
+
+W, H = 192, 108
+POSES = [([192.0, 62.0, 192.0], 30.0, -15.0), ([192.4, 62.0, 191.7], 33.0, -14.0), ([192.7, 62.1, 191.5], 35.0, -14.0)]   # small camera motion
+
+
+def fill(dst, src):
+    for i, v in enumerate(np.asarray(src, np.float32).ravel()):
+        dst[i] = float(v)
+
+
+def frames(world_blocks, inputs=None):
+    """Returns [{"cam", "g": {t, normal, block}, "raw": {sh, cocg, x (luminance), aosky}} per frame]."""
+    inputs = inputs or su.SceneInputs(64)
+    ow = ob.OracleWorld(world_blocks)
+    sc = ob.OracleScene(ow)
+    inputs.apply_to_oracle(sc)
+    out = []
+    for f, (pos, yaw, pitch) in enumerate(POSES):
+        cam = host_api.camera(pos, yaw, pitch, W / H)
+        p = abi.PrimaryParams()
+        fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
+        p.width, p.height, p.render_distance = W, H, 350
+        g = ow.initial_trace(p)
+        gi = sc.diffuse_trace(su.gi_params(cam, W, H, frame=f, spp=1), g["t"], g["normal"])
+        raw = {"sh": np.ascontiguousarray(gi["sh"]), "cocg": np.ascontiguousarray(gi["cocg"]), "x": np.ascontiguousarray(gi["utility"]),
+               "aosky": np.ascontiguousarray(gi["aosky"])}
+        out.append({"cam": cam, "g": {k: np.ascontiguousarray(g[k]) for k in ("t", "normal", "block")}, "raw": raw})
+    return out
+
+
+def temporal_params(cam, prev_cam, in_set, history_set, out_set, be_useful=True) -> abi.SvgfTemporalParams:
+    p = abi.SvgfTemporalParams()
+    fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
+    fill(p.prev_view, prev_cam.view); fill(p.prev_projection, prev_cam.projection)
+    p.width, p.height = W, H
+    p.in_set, p.history_set, p.out_set, p.be_useful = in_set, history_set, out_set, int(be_useful)
+    return p
+
+
+def zero_gbuf():
+    return {"t": np.zeros((H, W), np.float16), "normal": np.zeros((H, W), np.uint8), "block": np.zeros((H, W), np.uint8)}

@@ -23,6 +23,9 @@ ATT_SHADOW, ATT_SHADOW_TRANSVERSAL = 4, 5
 ATT_GBUF_ALBEDO, ATT_GBUF_NORMAL, ATT_GBUF_PBR, ATT_GBUF_TEXAO, ATT_DIRECT = 6, 7, 8, 9, 10
 ATT_GI_SH, ATT_GI_COCG, ATT_GI_UTILITY, ATT_GI_AOSKY = 11, 12, 13, 14
 ATT_REFL_COLOR, ATT_REFL_HITDIST, ATT_REFL_EMISSIVE = 15, 16, 17
+# SVGF image sets: +0 SH, +1 CoCg, +2 utility (temporal) / variance, +3 AO/sky
+ATT_SVGF_TEMPORAL_A, ATT_SVGF_TEMPORAL_B, ATT_SVGF_VARIANCE, ATT_SVGF_DENOISE_A, ATT_SVGF_DENOISE_B = 18, 22, 26, 30, 34
+ATT_PREV_INITIAL_T, ATT_PREV_INITIAL_NORMAL, ATT_PREV_INITIAL_BLOCK = 38, 39, 40
 
 TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
@@ -102,6 +105,24 @@ class ReflectionParams(C.Structure):
         ("viewer_position", C.c_float * 3), ("sun_strength_modifier", C.c_float), ("moon_strength_modifier", C.c_float),
         ("grass_props", C.c_int32 * 10), ("tile", Tile),
     ]
+
+
+class SvgfTemporalParams(C.Structure):
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("prev_view", C.c_float * 16),
+                ("prev_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32), ("in_set", C.c_int32),
+                ("history_set", C.c_int32), ("out_set", C.c_int32), ("be_useful", C.c_int32), ("tile", Tile)]
+
+
+class SvgfVarianceParams(C.Structure):
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+                ("in_set", C.c_int32), ("do_spatial", C.c_int32), ("aggressive_disocclusion", C.c_int32), ("tile", Tile)]
+
+
+class SvgfSpatialParams(C.Structure):
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+                ("in_set", C.c_int32), ("ao_set", C.c_int32), ("temporal_set", C.c_int32), ("out_set", C.c_int32), ("step", C.c_int32),
+                ("large_kernel", C.c_int32), ("do_spatial", C.c_int32), ("aggressive_disocclusion", C.c_int32),
+                ("color_phi_bias", C.c_float), ("time", C.c_float), ("resolution_scale", C.c_float), ("tile", Tile)]
 
 
 class RayHit(C.Structure):
