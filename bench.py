@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="only warm-up + steps of the plain step (for ncu)")
     ap.add_argument("--tex-size", type=int, default=512)
+    ap.add_argument("--no-svgf", action="store_true", help="skip the SVGF denoiser-chain measurement")
     return ap.parse_args()
 
 
@@ -474,6 +475,46 @@ def main():
     torch.cuda.synchronize()
     df_us = float(np.median([a.elapsed_time(b) for a, b in df_ev])) * 1e3
 
+    # ---- SVGF denoiser chain of the GI output: temporal, variance, 5 a-trous iterations, per-stage CUDA
+    # events, L2 flushed before each chain; runs on consecutive frames of the camera path so the history is live ----
+    svgf = None
+    if world_size == 1 and "gi" in cfg.passes and not args.no_svgf:
+        from voxeltracing_b200.pipeline import SvgfChain
+        chain = SvgfChain(ctx, W, H)
+        n_chain = 8
+        stage_ev = []
+        launches0 = ctx.launch_count
+        for k in range(n_chain):
+            cam = camera_for(wl, 1000 + k) if wl["camera"] != "rooms" else camera_for(wl, 0)   # rooms: hold one pose so frames accumulate
+            fr.render(cam, 1000 + k)
+            prep = chain.prepare(cam, k)
+            evs = {}
+
+            def hook(name, where, evs=evs):
+                e = ev(); e.record(stream)
+                evs.setdefault(name, []).append(e)
+            flush_buf.zero_()
+            launches1 = ctx.launch_count
+            chain.submit(prep, hook=hook)
+            stage_ev.append(evs)
+        torch.cuda.synchronize()
+        per = {}
+        for evs in stage_ev[2:]:            # the first two chains run against an empty history
+            for name, (a, b) in evs.items():
+                key = "spatial" if name.startswith("spatial") else name
+                per.setdefault(key, []).append(a.elapsed_time(b))
+        n_px = W * H
+        stages = {}
+        for key, v in per.items():
+            calls = 5 if key == "spatial" else 1
+            ms_stage = float(np.mean(v))
+            by = SvgfChain.STAGE_BYTES[key] * n_px
+            stages[key] = {"ms_per_launch": ms_stage, "launches_per_chain": calls, "algorithmic_bytes_per_launch": by,
+                           "achieved_gbs": by / (ms_stage * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms_stage * 1e-3) / 1e9 / measured_peaks()[0]}
+        chain_ms = sum(st["ms_per_launch"] * st["launches_per_chain"] for st in stages.values())
+        svgf = {"ms_per_chain": chain_ms, "launches_per_chain": ctx.launch_count - launches1, "resolution": [W, H], "stages": stages,
+                "bytes_per_pixel": SvgfChain.STAGE_BYTES, "l2": "flushed before each chain"}
+
     # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera,
     # every output attachment read back to pinned host memory, inside the timed region ----
     if world_size > 1:
@@ -587,6 +628,8 @@ def main():
         line["df_regen"] = {"us_per_regeneration": df_us, "algorithmic_bytes": 2 * nvox,
                             "achieved_gbs": 2 * nvox / (df_us * 1e-6) / 1e9, "frac_of_hbm_peak": 2 * nvox / (df_us * 1e-6) / 1e9 / peak,
                             "l2": "flushed before each regeneration", "launches_per_regeneration": 2}
+        if svgf:
+            line["svgf"] = svgf
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_arm(blocks, wl, inputs)
             v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)

@@ -153,6 +153,11 @@ typedef enum vxrt_attachment {
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
 int vxrt_cuda_read_attachment(vxrt_ctx* ctx, int32_t attachment, void* host_dst, size_t bytes);
+/* glTexImage2D equivalent: (re)defines the attachment as width x height pixels of bytes_per_pixel and fills it from
+ * HOST memory (borrowed for the call).  Lets a caller seed history images (the SVGF sets, the previous G-buffer) or
+ * feed a pass with inputs produced elsewhere; formats are the ones listed above.                     */
+int vxrt_cuda_write_attachment(vxrt_ctx* ctx, int32_t attachment, int32_t width, int32_t height, int32_t bytes_per_pixel,
+                               const void* host_src);
 /* Asynchronous read-back, the glGetTexImage-into-a-pixel-pack-buffer + fence pattern: the copy is queued on the
  * context's copy stream behind everything issued so far and the call returns at once; the next pass that writes
  * the attachment waits for the copy on the device, later passes that only read it do not.  dst should be

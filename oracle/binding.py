@@ -232,6 +232,26 @@ def svgf_temporal(p: "abi.SvgfTemporalParams", cur: dict, hist: dict, g: dict, p
     return out
 
 
+def svgf_variance(p: "abi.SvgfVarianceParams", temporal: dict, g: dict, fn=None) -> dict:
+    """VarianceEstimate.glsl.  temporal: this frame's temporal set (x = utility RGB16F).  Returns sh, cocg, x = variance R16F
+    (aosky stays zero: VarianceFBO has no fourth attachment)."""
+    out = svgf_alloc(p.height, p.width, 1)
+    a, o = svgf_set(temporal), svgf_set(out)
+    (fn or lib().vxo_svgf_variance)(C.byref(p), C.byref(a), _p(g["t"]), _p(g["normal"]), C.byref(o))
+    return out
+
+
+def svgf_spatial(p: "abi.SvgfSpatialParams", prev: dict, ao: np.ndarray, temporal_utility: np.ndarray, g: dict, fn=None) -> dict:
+    """SpatialFilter.glsl, one a-trous iteration.  prev: sh / cocg / x = variance of the previous iteration (the variance
+    pass's output first); ao: the RG8 image bound as u_AO; temporal_utility: RGB16F u_TemporalMoment."""
+    out = svgf_alloc(p.height, p.width, 1)
+    ao = np.ascontiguousarray(ao)
+    a = SvgfSet(prev["sh"].ctypes.data, prev["cocg"].ctypes.data, prev["x"].ctypes.data, ao.ctypes.data)
+    o = svgf_set(out)
+    (fn or lib().vxo_svgf_spatial)(C.byref(p), C.byref(a), _p(temporal_utility), _p(g["t"]), _p(g["normal"]), C.byref(o))
+    return out
+
+
 class OracleScene:
     """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
 

@@ -521,3 +521,71 @@ extern "C" void vxref_svgf_temporal(const vxrt_svgf_temporal_params* p, const vx
         }
 }
 #endif
+
+#ifdef VXREF_HAVE_SVGFVariance
+extern "C" void vxref_svgf_variance(const vxrt_svgf_variance_params* p, const vxref_svgf_set* in, const uint16_t* g_t, const uint8_t* g_normal,
+                                    const vxref_svgf_out* out) {
+    namespace S = shader_SVGFVariance;
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = svgf_half(in->sh, 4 * n), fcc = svgf_half(in->cocg, 2 * n), fut = svgf_half(in->x, 3 * n);
+    auto ft = svgf_half(g_t, n), fn = svgf_u8(g_normal, n);
+    bind2d(S::u_PositionTexture, ft.data(), W, H, 1, true); bind2d(S::u_NormalTexture, fn.data(), W, H, 1, false);
+    bind2d(S::u_SH, fsh.data(), W, H, 4, true); bind2d(S::u_CoCg, fcc.data(), W, H, 2, true); bind2d(S::u_Utility, fut.data(), W, H, 3, true);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::DO_SPATIAL = p->do_spatial != 0; S::AGGRESSIVE_DISOCCLUSION_HANDLING = p->aggressive_disocclusion != 0;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam;
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out->sh[4 * i + c] = vxo::float_to_half(S::o_SH[c]);
+            for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
+            out->x[i] = vxo::float_to_half(S::o_Variance);
+        }
+}
+#endif
+
+#ifdef VXREF_HAVE_SVGFSpatial
+extern "C" void vxref_svgf_spatial(const vxrt_svgf_spatial_params* p, const vxref_svgf_set* in, const uint16_t* temporal_utility, const uint16_t* g_t,
+                                   const uint8_t* g_normal, const vxref_svgf_out* out) {
+    namespace S = shader_SVGFSpatial;
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = svgf_half(in->sh, 4 * n), fcc = svgf_half(in->cocg, 2 * n), fvar = svgf_half(in->x, n), fao = svgf_u8(in->aosky, 2 * n);
+    auto fut = svgf_half(temporal_utility, 3 * n), ft = svgf_half(g_t, n), fn = svgf_u8(g_normal, n);
+    bind2d(S::u_SH, fsh.data(), W, H, 4, true); bind2d(S::u_CoCg, fcc.data(), W, H, 2, true);
+    bind2d(S::u_VarianceTexture, fvar.data(), W, H, 1, true); bind2d(S::u_AO, fao.data(), W, H, 2, true);
+    bind2d(S::u_Utility, fao.data(), W, H, 2, true);   /* Pipeline.cpp:2693 binds the temporal set's AO image here; never used */
+    bind2d(S::u_TemporalMoment, fut.data(), W, H, 3, true);
+    bind2d(S::u_PositionTexture, ft.data(), W, H, 1, true); bind2d(S::u_NormalTexture, fn.data(), W, H, 1, false);
+    bind2d(S::u_BlockIDTexture, fn.data(), W, H, 1, false);   /* declared, never sampled by main() */
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_Dimensions = vec2((float)W, (float)H);
+    S::u_Step = p->step; S::u_ShouldDetailWeight = true; S::DO_SPATIAL = p->do_spatial != 0; S::u_LargeKernel = p->large_kernel != 0;
+    S::AGGRESSIVE_DISOCCLUSION_HANDLING = p->aggressive_disocclusion != 0;
+    S::u_ColorPhiBias = p->color_phi_bias; S::u_DeltaTime = 0.0f; S::u_Time = p->time; S::u_ResolutionScale = p->resolution_scale;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam; S::v_RayDirection = vec3(0.0f, 0.0f, 1.0f);
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out->sh[4 * i + c] = vxo::float_to_half(S::o_SH[c]);
+            for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
+            out->x[i] = vxo::float_to_half(S::o_Variance);
+            for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOAndSkylighting[c]);
+        }
+}
+#endif

@@ -183,3 +183,222 @@ extern "C" void vxo_svgf_temporal(const vxrt_svgf_temporal_params* p, const vxo_
             out->aosky[2 * i] = float_to_unorm8(gclampf(oAO.x, 0.0f, 1.0f)); out->aosky[2 * i + 1] = float_to_unorm8(gclampf(oAO.y, 0.0f, 1.0f));
         }
 }
+
+/* VarianceEstimate.glsl main() (:75-184).  in->x = u_Utility (RGB16F: accumulated frames, second moment, luminance);
+ * out->x = o_Variance (R16F); out->aosky is not written (VarianceFBO has three attachments, Pipeline.cpp:1153).
+ * GetPositionAt(SampleCoord) is only consumed through .w, the sampled distance. */
+extern "C" void vxo_svgf_variance(const vxrt_svgf_variance_params* p, const vxo_svgf_set* in, const uint16_t* g_t, const uint8_t* g_normal,
+                                  const vxo_svgf_out* out) {
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = from_half(in->sh, 4 * n), fcc = from_half(in->cocg, 2 * n), fut = from_half(in->x, 3 * n);
+    auto ft = from_half(g_t, n), fn = from_u8(g_normal, n);
+    const Tex2D tSH = view(fsh, W, H, 4, true), tCC = view(fcc, W, H, 2, true), tUt = view(fut, W, H, 3, true);
+    const Tex2D tT = view(ft, W, H, 1, true), tN = view(fn, W, H, 1, false);
+    const v2 TexelSize = V2(1.0f / (float)W, 1.0f / (float)H);
+    const bool aggressive = p->aggressive_disocclusion != 0;
+    int r0, r1;
+    tile_rows(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const v2 tc = V2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            const float BaseDist = tex2d_sample(tT, tc.x, tc.y).x;
+            const v3 BaseNormal = normal_from_id(tex2d_sample(tN, tc.x, tc.y).x);
+            const v4 BaseUtility = tex2d_sample(tUt, tc.x, tc.y);
+            const v4 BaseSH = tex2d_sample(tSH, tc.x, tc.y);
+            const v4 bcc = tex2d_sample(tCC, tc.x, tc.y);
+            const float BaseLuminosity = sh_to_y(BaseSH);
+            const float ACCUMULATED_FRAMES = BaseUtility.x, BaseMoment = BaseUtility.y;
+            v4 oSH = BaseSH;
+            v2 oCC = V2(bcc.x, bcc.y);
+            float Variance = BaseMoment - BaseLuminosity * BaseLuminosity;
+            if (p->do_spatial) {
+                const float THRESH = aggressive ? 4.0f + 4.0f + 4.0f : 4.0f + 4.0f;
+                if (ACCUMULATED_FRAMES < THRESH) {
+                    const float ColorPhi = aggressive ? 5.0f : 5.0f * 2.0f;
+                    const int K = aggressive ? 4 : 1;
+                    float TotalWeight = 0.0f, TotalMoment = 0.0f, TotalLuminosity = 0.0f, TotalWeight2 = 0.0f;
+                    v4 TotalSH = V4(0.0f, 0.0f, 0.0f, 0.0f);
+                    v2 TotalCoCg = V2(0.0f, 0.0f);
+                    for (int x = -K; x <= K; ++x)
+                        for (int y = -K; y <= K; ++y) {
+                            const v2 sc = V2(tc.x + (float)x * TexelSize.x, tc.y + (float)y * TexelSize.y);
+                            if (!in_screen_space(sc)) continue;
+                            const float SampleDist = tex2d_sample(tT, sc.x, sc.y).x;
+                            const v3 SampleNormal = normal_from_id(tex2d_sample(tN, sc.x, sc.y).x);
+                            const float SampleMoment = tex2d_sample(tUt, sc.x, sc.y).y;
+                            const v4 SampleSH = tex2d_sample(tSH, sc.x, sc.y);
+                            const v4 scc = tex2d_sample(tCC, sc.x, sc.y);
+                            const float SampleLuminosity = sh_to_y(SampleSH);
+                            const float NormalWeight = powf(gmax(dot(BaseNormal, SampleNormal), 0.0f), 16.0f);
+                            const float DepthWeight = powf(expf(-fabsf(SampleDist - BaseDist)), 2.0f);
+                            const float LuminosityWeight = fabsf(SampleLuminosity - BaseLuminosity) / ColorPhi;
+                            float Weight = expf(-LuminosityWeight) * NormalWeight * DepthWeight;
+                            float Weight_2 = Weight;
+                            Weight = gmax(Weight, 0.000000015f);
+                            Weight_2 = gmax(Weight_2, 0.0000000015f);
+                            TotalWeight += Weight;
+                            TotalMoment += SampleMoment * Weight_2;
+                            TotalSH = V4(TotalSH.x + SampleSH.x * Weight, TotalSH.y + SampleSH.y * Weight, TotalSH.z + SampleSH.z * Weight, TotalSH.w + SampleSH.w * Weight);
+                            TotalCoCg = V2(TotalCoCg.x + scc.x * Weight, TotalCoCg.y + scc.y * Weight);
+                            TotalLuminosity += SampleLuminosity * Weight_2;
+                            TotalWeight2 += Weight_2;
+                        }
+                    if (TotalWeight > 0.0f) {
+                        TotalMoment /= TotalWeight2;
+                        TotalLuminosity /= TotalWeight2;
+                        TotalCoCg = V2(TotalCoCg.x / TotalWeight, TotalCoCg.y / TotalWeight);
+                        TotalSH = V4(TotalSH.x / TotalWeight, TotalSH.y / TotalWeight, TotalSH.z / TotalWeight, TotalSH.w / TotalWeight);
+                    }
+                    oSH = TotalSH; oCC = TotalCoCg;
+                    Variance = TotalMoment - TotalLuminosity * TotalLuminosity;
+                    Variance *= 3.0f;
+                }
+                Variance *= THRESH / ACCUMULATED_FRAMES;
+            }
+            const size_t i = (size_t)py * W + px;
+            if (p->do_spatial) {   /* the !DO_SPATIAL path returns before the clamps (:96-101) */
+                oSH = V4(gclampf(oSH.x, -100.0f, 100.0f), gclampf(oSH.y, -100.0f, 100.0f), gclampf(oSH.z, -100.0f, 100.0f), gclampf(oSH.w, -100.0f, 100.0f));
+                oCC = V2(gclampf(oCC.x, -10.0f, 100.0f), gclampf(oCC.y, -10.0f, 100.0f));
+                Variance = gclampf(Variance, -1.0f, 50.0f);
+            }
+            out->sh[4 * i] = float_to_half(oSH.x); out->sh[4 * i + 1] = float_to_half(oSH.y);
+            out->sh[4 * i + 2] = float_to_half(oSH.z); out->sh[4 * i + 3] = float_to_half(oSH.w);
+            out->cocg[2 * i] = float_to_half(oCC.x); out->cocg[2 * i + 1] = float_to_half(oCC.y);
+            out->x[i] = float_to_half(Variance);
+        }
+}
+
+/* TweakVariance (SpatialFilter.glsl:170-176) */
+static inline float tweak_variance(float V, float E) {
+    float F = gclampf(V, 0.0f, 1.0f);
+    const float T = 1.0f - F;
+    return F * powf(T, E + 6.0f);
+}
+
+/* SpatialFilter.glsl main() (:178-364), one a-trous iteration.  in->x = u_VarianceTexture (R16F), in->aosky = u_AO (the
+ * temporal set's for iteration 0, Pipeline.cpp:2620-2636); temporal_utility = u_TemporalMoment (RGB16F, .x = accumulated
+ * frames).  u_Utility, u_BlockIDTexture and BaseUtility are bound / sampled by the reference but never used.
+ * `BaseDepth < 0.0f == DepthDiff < 0.0f` parses as (BaseDepth < 0) == (DepthDiff < 0); DepthDiff is an abs(). */
+extern "C" void vxo_svgf_spatial(const vxrt_svgf_spatial_params* p, const vxo_svgf_set* in, const uint16_t* temporal_utility, const uint16_t* g_t,
+                                 const uint8_t* g_normal, const vxo_svgf_out* out) {
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = from_half(in->sh, 4 * n), fcc = from_half(in->cocg, 2 * n), fvar = from_half(in->x, n), fao = from_u8(in->aosky, 2 * n);
+    auto fut = from_half(temporal_utility, 3 * n), ft = from_half(g_t, n), fn = from_u8(g_normal, n);
+    const Tex2D tSH = view(fsh, W, H, 4, true), tCC = view(fcc, W, H, 2, true), tVar = view(fvar, W, H, 1, true), tAO = view(fao, W, H, 2, true);
+    const Tex2D tUt = view(fut, W, H, 3, true), tT = view(ft, W, H, 1, true), tN = view(fn, W, H, 1, false);
+    const float AtrousWeights[3] = {1.0f, 2.0f / 3.0f, 1.0f / 6.0f};
+    const float Gaussian[2] = {0.60283f, 0.198585f};
+    const v2 TexelSize = V2(1.0f / (float)W, 1.0f / (float)H);       /* 1 / u_Dimensions */
+    const v2 TexelSizeSH = V2(1.0f / (float)W, 1.0f / (float)H);     /* 1 / textureSize(u_SH, 0) */
+    const bool FilterAO = p->step <= 4;
+    const bool FilterSky = p->step <= 6 || FilterAO;
+    const int K = p->large_kernel ? 2 : 1;
+    const float AdditionalScale = gmix(1.0f, 2.4f, p->resolution_scale);
+    const float tmod = p->time * 100.493850275f;
+    const float toff = tmod - 500.0f * floorf(tmod / 500.0f);        /* mod(u_Time * 100.49.., 500) */
+    int r0, r1;
+    tile_rows(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const v2 tc = V2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            /* GradientNoise (:163-168) */
+            const float cx = ((float)px + 0.5f) + toff, cy = ((float)py + 0.5f) + toff;
+            const float noise = gfract(52.9829189f * gfract(0.06711056f * cx + 0.00583715f * cy));
+            const float js = (noise - 0.5f) * ((float)p->step * 0.8f);
+            const int Jx = cvt_trunc(js), Jy = Jx;
+            const float BaseDepth = tex2d_sample(tT, tc.x, tc.y).x;
+            const v3 BaseNormal = normal_from_id(tex2d_sample(tN, tc.x, tc.y).x);
+            const v4 BaseSH = tex2d_sample(tSH, tc.x, tc.y);
+            const v4 bcc = tex2d_sample(tCC, tc.x, tc.y);
+            const v2 BaseCoCg = V2(bcc.x, bcc.y);
+            const float BaseLuminance = sh_to_y(BaseSH);
+            /* GaussianVariance (:98-133) */
+            float BaseVariance = 0.0f, VarianceSum = 0.0f, TotalKernel = 0.0f;
+            for (int x = -1; x <= 1; ++x)
+                for (int y = -1; y <= 1; ++y) {
+                    const v2 sc = V2(tc.x + (float)x * TexelSizeSH.x, tc.y + (float)y * TexelSizeSH.y);
+                    if (!in_screen_space(sc)) continue;
+                    const float KernelValue = Gaussian[x < 0 ? -x : x] * Gaussian[y < 0 ? -y : y];
+                    const float V = tex2d_sample(tVar, sc.x, sc.y).x;
+                    if (x == 0 && y == 0) BaseVariance = V;
+                    VarianceSum += V * KernelValue;
+                    TotalKernel += KernelValue;
+                }
+            const float VarianceEstimate = VarianceSum / gmax(TotalKernel, 0.01f);
+            const v4 bao = tex2d_sample(tAO, tc.x, tc.y);
+            const v2 BaseAOSky = V2(bao.x, bao.y);
+            v4 oSH = BaseSH; v2 oCC = BaseCoCg; float oVar = BaseVariance; v2 oAO = BaseAOSky;
+            if (p->do_spatial) {
+                v4 TotalSH = BaseSH; v2 TotalCoCg = BaseCoCg; float TotalWeight = 1.0f, TotalVariance = BaseVariance;
+                v2 TotalAOSky = BaseAOSky; float TotalAOWeight = 1.0f;
+                const float AccumulatedFrames = tex2d_sample(tUt, tc.x, tc.y).x;
+                const bool DoStrongSpatial = AccumulatedFrames <= 8.0f && p->aggressive_disocclusion && p->step <= 8;
+                float CurveExponent = 0.0f;
+                if (VarianceEstimate < 0.01f) CurveExponent = 128.0f;
+                else if (VarianceEstimate < 0.025f) CurveExponent = 112.0f;
+                else if (VarianceEstimate < 0.05f) CurveExponent = 96.0f;
+                else if (VarianceEstimate < 0.075f) CurveExponent = 84.0f;
+                else if (VarianceEstimate < 0.1f) CurveExponent = 70.0f;
+                const float TweakedVariance = VarianceEstimate < 0.1f ? tweak_variance(VarianceEstimate, CurveExponent) : VarianceEstimate;
+                float PhiColor = sqrtf(gmax(0.0f, 0.000001f + TweakedVariance));
+                PhiColor /= gmax(p->color_phi_bias, 0.1f);
+                for (int x = -K; x <= K; ++x)
+                    for (int y = -K; y <= K; ++y) {
+                        if (x == 0 && y == 0) continue;
+                        const v2 sc = V2(tc.x + (((float)x * (float)p->step) * AdditionalScale + (float)Jx * 0.5f) * TexelSize.x,
+                                         tc.y + (((float)y * (float)p->step) * AdditionalScale + (float)Jy * 0.5f) * TexelSize.y);
+                        if (!in_screen_space(sc)) continue;
+                        const float SampleDepth = tex2d_sample(tT, sc.x, sc.y).x;
+                        const float DepthDiff = fabsf(SampleDepth - BaseDepth);
+                        const v3 SampleNormal = normal_from_id(tex2d_sample(tN, sc.x, sc.y).x);
+                        if ((BaseDepth < 0.0f) == (DepthDiff < 0.0f)) {
+                            const v4 SampleSH = tex2d_sample(tSH, sc.x, sc.y);
+                            const v4 scc = tex2d_sample(tCC, sc.x, sc.y);
+                            const float SampleLuma = sh_to_y(SampleSH);
+                            const float SampleVariance = tex2d_sample(tVar, sc.x, sc.y).x;
+                            float NormalWeight = powf(gmax(dot(BaseNormal, SampleNormal), 0.0f), 32.0f);
+                            NormalWeight = gclampf(NormalWeight, 0.001f, 1.0f);
+                            const float LuminosityWeight = fabsf(SampleLuma - BaseLuminance) / PhiColor;
+                            const float DepthWeight = gclampf(powf(expf(-gmax(DepthDiff, 0.00001f)), 2.0f), 0.0001f, 1.0f);
+                            float Weight = DoStrongSpatial ? (NormalWeight * DepthWeight) : (expf(-LuminosityWeight) * NormalWeight * DepthWeight);
+                            Weight = gclampf(Weight, 0.001f, 1.0f);
+                            const float XWeight = AtrousWeights[x < 0 ? -x : x], YWeight = AtrousWeights[y < 0 ? -y : y];
+                            Weight = (XWeight * YWeight) * Weight;
+                            Weight = gmax(Weight, 0.00000001f);
+                            TotalSH = V4(TotalSH.x + SampleSH.x * Weight, TotalSH.y + SampleSH.y * Weight, TotalSH.z + SampleSH.z * Weight, TotalSH.w + SampleSH.w * Weight);
+                            TotalCoCg = V2(TotalCoCg.x + scc.x * Weight, TotalCoCg.y + scc.y * Weight);
+                            TotalVariance += (Weight * Weight) * SampleVariance;
+                            TotalWeight += Weight;
+                            if (FilterSky || FilterAO) {
+                                const float CurrAOWeight = gclampf((XWeight * YWeight) * NormalWeight * DepthWeight, 0.000001f, 1.0f);
+                                const v4 a = tex2d_sample(tAO, sc.x, sc.y);
+                                TotalAOSky.x += a.x * CurrAOWeight;
+                                TotalAOSky.y += a.y * CurrAOWeight;
+                                TotalAOWeight += CurrAOWeight;
+                            }
+                        }
+                    }
+                oSH = V4(TotalSH.x / TotalWeight, TotalSH.y / TotalWeight, TotalSH.z / TotalWeight, TotalSH.w / TotalWeight);
+                oCC = V2(TotalCoCg.x / TotalWeight, TotalCoCg.y / TotalWeight);
+                oVar = TotalVariance / (TotalWeight * TotalWeight);
+                oAO = V2(TotalAOSky.x / TotalAOWeight, TotalAOSky.y / TotalAOWeight);
+                if (!FilterAO) oAO.x = BaseAOSky.x;
+            }
+            const size_t i = (size_t)py * W + px;
+            if (p->do_spatial) {   /* the !DO_SPATIAL path returns before the clamps (:205-211) */
+                oSH = V4(gclampf(oSH.x, -100.0f, 100.0f), gclampf(oSH.y, -100.0f, 100.0f), gclampf(oSH.z, -100.0f, 100.0f), gclampf(oSH.w, -100.0f, 100.0f));
+                oCC = V2(gclampf(oCC.x, -10.0f, 100.0f), gclampf(oCC.y, -10.0f, 100.0f));
+                oVar = gclampf(oVar, -1.0f, 50.0f);
+                oAO = V2(gclampf(oAO.x, 0.0f, 1.0f), gclampf(oAO.y, 0.0f, 1.0f));
+            }
+            out->sh[4 * i] = float_to_half(oSH.x); out->sh[4 * i + 1] = float_to_half(oSH.y);
+            out->sh[4 * i + 2] = float_to_half(oSH.z); out->sh[4 * i + 3] = float_to_half(oSH.w);
+            out->cocg[2 * i] = float_to_half(oCC.x); out->cocg[2 * i + 1] = float_to_half(oCC.y);
+            out->x[i] = float_to_half(oVar);
+            out->aosky[2 * i] = float_to_unorm8(oAO.x); out->aosky[2 * i + 1] = float_to_unorm8(oAO.y);
+        }
+}

@@ -46,3 +46,51 @@ def temporal_params(cam, prev_cam, in_set, history_set, out_set, be_useful=True)
 
 def zero_gbuf():
     return {"t": np.zeros((H, W), np.float16), "normal": np.zeros((H, W), np.uint8), "block": np.zeros((H, W), np.uint8)}
+
+
+def variance_params(cam, in_set, do_spatial=True, aggressive=True) -> abi.SvgfVarianceParams:
+    p = abi.SvgfVarianceParams()
+    fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
+    p.width, p.height, p.in_set, p.do_spatial, p.aggressive_disocclusion = W, H, in_set, int(do_spatial), int(aggressive)
+    return p
+
+
+def spatial_params(cam, in_set, ao_set, temporal_set, out_set, step, time=0.0, large=False, do_spatial=True, aggressive=True,
+                   phi_bias=2.8, res_scale=0.25) -> abi.SvgfSpatialParams:
+    p = abi.SvgfSpatialParams()
+    fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
+    p.width, p.height = W, H
+    p.in_set, p.ao_set, p.temporal_set, p.out_set, p.step = in_set, ao_set, temporal_set, out_set, step
+    p.large_kernel, p.do_spatial, p.aggressive_disocclusion = int(large), int(do_spatial), int(aggressive)
+    p.color_phi_bias, p.time, p.resolution_scale = phi_bias, time, res_scale
+    return p
+
+
+STEPS = (16, 8, 4, 2, 1)   # Pipeline.cpp:2583-2589 (WiderSVGF off)
+
+
+def spatial_chain(cam, temporal, variance, g, spatial_fn, time=1.25, **kw):
+    """The five a-trous iterations of Pipeline.cpp:2592-2700: VARIANCE -> DENOISE_A -> DENOISE_B -> A -> B -> A.
+    spatial_fn(params, prev_set, ao_image, temporal_utility, g) -> set.  Returns the list of the five outputs."""
+    outs, prev, ao = [], variance, temporal["aosky"]
+    for i, step in enumerate(STEPS):
+        cur_id = abi.ATT_SVGF_DENOISE_A if i % 2 == 0 else abi.ATT_SVGF_DENOISE_B
+        prev_id = abi.ATT_SVGF_VARIANCE if i == 0 else (abi.ATT_SVGF_DENOISE_B if i % 2 == 0 else abi.ATT_SVGF_DENOISE_A)
+        p = spatial_params(cam, prev_id, abi.ATT_SVGF_TEMPORAL_A if i == 0 else prev_id, abi.ATT_SVGF_TEMPORAL_A, cur_id, step, time=time, **kw)
+        out = spatial_fn(p, prev, ao, temporal["x"], g)
+        outs.append(out)
+        prev, ao = out, out["aosky"]
+    return outs
+
+
+def same_bits(a, b, keys=("sh", "cocg", "x", "aosky")):
+    """bit equality with NaNs canonicalised (x86 and the GPU produce different quiet NaNs)"""
+    for k in keys:
+        x, y = a[k], b[k]
+        if x.dtype == np.float16:
+            nx, ny = np.isnan(x), np.isnan(y)
+            if not (np.array_equal(nx, ny) and np.array_equal(x.view(np.uint16)[~nx], y.view(np.uint16)[~ny])):
+                return False
+        elif not np.array_equal(x, y):
+            return False
+    return True

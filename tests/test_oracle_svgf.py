@@ -64,3 +64,77 @@ def test_oracle_temporal_equals_compiled_reference_shader(seq, be_useful):
         hist, prev_g = a[0], seq[0]["g"]
         p = sv.temporal_params(seq[1]["cam"], seq[0]["cam"], abi.ATT_GI_SH, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_TEMPORAL_A, be_useful=False)
         assert _same(ob.svgf_temporal(p, seq[1]["raw"], hist, seq[1]["g"], prev_g), ob.svgf_temporal(p, seq[1]["raw"], hist, seq[1]["g"], prev_g, L.vxref_svgf_temporal))
+
+
+@pytest.fixture(scope="module")
+def temporal(seq):
+    return _temporal_frames(seq)
+
+
+def test_variance_and_spatial_self_checks(seq, temporal):
+    f, t = seq[2], temporal[2]
+    v = ob.svgf_variance(sv.variance_params(f["cam"], abi.ATT_SVGF_TEMPORAL_A), t, f["g"])
+    # do_spatial off: the inputs pass through and variance = moment - luminance^2
+    v0 = ob.svgf_variance(sv.variance_params(f["cam"], abi.ATT_SVGF_TEMPORAL_A, do_spatial=False), t, f["g"])
+    # (bilinear weights at a pixel centre are not exactly 0 / 1 in float, so "pass through" is to within a half ulp or so)
+    assert np.allclose(v0["cocg"].astype(np.float32), t["cocg"].astype(np.float32), atol=2e-3, rtol=2e-3)
+    lum = np.maximum(0, 3.544905 * t["sh"][..., 3].astype(np.float32))
+    assert np.allclose(v0["x"].astype(np.float32), t["x"][..., 1].astype(np.float32) - lum * lum, atol=5e-2, rtol=1e-2)
+    acc = t["x"][..., 0].astype(np.float32)
+    # pixels without history: THRESH / 0 makes the variance inf (clamped to 50) or NaN (0 * inf)
+    fresh = acc == 0
+    vx = v["x"].astype(np.float32)
+    assert fresh.any() and (np.isnan(vx[fresh]) | (vx[fresh] == 50) | (vx[fresh] == -1)).all()
+    assert np.isfinite(vx[~fresh]).all() and (vx[~fresh] >= -1).all() and (vx[~fresh] <= 50).all()
+    # the 9x9 bilateral pre-filter smooths the SH luminance band
+    lum_in, lum_out = t["sh"][..., 3].astype(np.float32), v["sh"][..., 3].astype(np.float32)
+    assert np.abs(np.diff(lum_out, axis=1)).mean() < 0.7 * np.abs(np.diff(lum_in, axis=1)).mean()
+    outs = sv.spatial_chain(f["cam"], t, v, f["g"], ob.svgf_spatial)
+    assert len(outs) == 5
+    last = outs[-1]
+    assert np.isfinite(last["sh"].astype(np.float32)).all()
+    # AO is only filtered by the iterations with step <= 4 (the first two pass it through)
+    assert np.array_equal(outs[0]["aosky"][..., 0], t["aosky"][..., 0]) and np.array_equal(outs[1]["aosky"][..., 0], t["aosky"][..., 0])
+    assert not np.array_equal(outs[2]["aosky"][..., 0], outs[1]["aosky"][..., 0])
+    # do_spatial off: identity on sh / cocg / variance / ao
+    ident = ob.svgf_spatial(sv.spatial_params(f["cam"], abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_DENOISE_A, 16, do_spatial=False),
+                            v, t["aosky"], t["x"], f["g"])
+    ok = ~np.isnan(v["x"])
+    assert np.allclose(ident["sh"].astype(np.float32), v["sh"].astype(np.float32), atol=2e-3, rtol=2e-3)
+    assert np.allclose(ident["x"].astype(np.float32)[ok], v["x"].astype(np.float32)[ok], atol=2e-3, rtol=2e-3)
+    assert np.abs(ident["aosky"].astype(np.int32) - t["aosky"].astype(np.int32)).max() <= 1
+
+
+@pytest.mark.skipif(not rb.available("svgf_variance"), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("do_spatial,aggressive", [(True, True), (True, False), (False, True)])
+def test_oracle_variance_equals_compiled_reference_shader(seq, temporal, do_spatial, aggressive):
+    L = rb.lib()
+    for k in (0, 2):
+        p = sv.variance_params(seq[k]["cam"], abi.ATT_SVGF_TEMPORAL_A, do_spatial, aggressive)
+        a = ob.svgf_variance(p, temporal[k], seq[k]["g"])
+        b = ob.svgf_variance(p, temporal[k], seq[k]["g"], L.vxref_svgf_variance)
+        assert sv.same_bits(a, b, ("sh", "cocg", "x"))
+
+
+@pytest.mark.skipif(not rb.available("svgf_spatial"), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("kw", [dict(), dict(large=True, time=7.3), dict(aggressive=False, phi_bias=0.05, res_scale=1.0), dict(do_spatial=False)])
+def test_oracle_spatial_chain_equals_compiled_reference_shader(seq, temporal, kw):
+    L = rb.lib()
+    f, t = seq[2], temporal[2]
+    v = ob.svgf_variance(sv.variance_params(f["cam"], abi.ATT_SVGF_TEMPORAL_A), t, f["g"])
+    a = sv.spatial_chain(f["cam"], t, v, f["g"], ob.svgf_spatial, **kw)
+    b = sv.spatial_chain(f["cam"], t, v, f["g"], lambda *args: ob.svgf_spatial(*args, fn=L.vxref_svgf_spatial), **kw)
+    assert all(sv.same_bits(x, y) for x, y in zip(a, b))
+
+
+def test_oracle_chain_equals_golden_fixture(seq):
+    """tests/golden/svgf_ref.npz was produced by the reference's own shaders (tests/golden/make_golden_svgf.py)."""
+    import sys
+    sys.path.insert(0, str(sv.__file__).rsplit("/", 1)[0] + "/golden")
+    import make_golden_svgf as mg
+
+    z = np.load(mg.OUT / "svgf_ref.npz")
+    assert str(z["input_sha256"]) == mg.input_hash(seq), "the oracle no longer regenerates the fixture's inputs"
+    got = mg.run_chain(seq, ob.svgf_temporal, ob.svgf_variance, ob.svgf_spatial)
+    for name, a in got.items():
+        assert sv.same_bits({"v": a}, {"v": z[name]}, ("v",)), name

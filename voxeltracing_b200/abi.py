@@ -188,6 +188,11 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_shade_direct": (C.c_int, [vp, P(DirectParams)]),
         "vxrt_cuda_diffuse_trace": (C.c_int, [vp, P(GIParams)]),
         "vxrt_cuda_reflection_trace": (C.c_int, [vp, P(ReflectionParams)]),
+        "vxrt_cuda_svgf_temporal": (C.c_int, [vp, P(SvgfTemporalParams)]),
+        "vxrt_cuda_svgf_variance": (C.c_int, [vp, P(SvgfVarianceParams)]),
+        "vxrt_cuda_svgf_spatial": (C.c_int, [vp, P(SvgfSpatialParams)]),
+        "vxrt_cuda_svgf_end_frame": (C.c_int, [vp]),
+        "vxrt_cuda_write_attachment": (C.c_int, [vp, i32, i32, i32, i32, vp]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_wait_reads": (C.c_int, [vp]),

@@ -100,8 +100,9 @@ def build_host(force: bool = False) -> Path:
 
 def build_oracle(force: bool = False) -> Path:
     odir = ROOT / "oracle"
-    srcs = sorted(odir.glob("*.cpp"))
-    deps = srcs + sorted(odir.glob("*.h")) + [ROOT / "include" / "vxrt_cuda.h"]
+    # ref_driver.cpp belongs to oracle/_ref (it needs files build_ref.py generates), not to the restatement
+    srcs = sorted(p for p in odir.glob("*.cpp") if p.name != "ref_driver.cpp")
+    deps = srcs + sorted(p for p in odir.glob("*.h") if p.name != "glsl_shim.h") + [ROOT / "include" / "vxrt_cuda.h"]
     stamp = _digest(deps, " ".join(GXX_ORACLE_FLAGS))
     if not force and _up_to_date(ORACLE_LIB, stamp):
         return ORACLE_LIB

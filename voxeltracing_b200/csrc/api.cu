@@ -349,6 +349,16 @@ int vxrt_cuda_read_attachment(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) 
     VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
+int vxrt_cuda_write_attachment(vxrt_ctx* c, int32_t id, int32_t width, int32_t height, int32_t bytes_per_pixel, const void* src) {
+    REQUIRE_CTX(c); REQUIRE_PTR(src);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    if (bytes_per_pixel < 1 || bytes_per_pixel > 16) return vxrt_fail(VXRT_E_INVALID, "write_attachment: %d bytes per pixel", bytes_per_pixel);
+    int rc = vxrt_ensure_attachment(c, id, width, height, bytes_per_pixel);
+    if (rc) return rc;
+    VX_CUDA(cudaMemcpyAsync(c->att[id].ptr, src, (size_t)width * height * bytes_per_pixel, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // src is only borrowed for the call
+    return VXRT_OK;
+}
 int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
     REQUIRE_CTX(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
@@ -540,6 +550,28 @@ int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
     if (!p->use_blue_noise) return vxrt_fail(VXRT_E_UNSUPPORTED, "the fract(sin()) hash RNG (u_UseBlueNoise = false) is not portable and not implemented");
     if (p->spp < 1 || p->trace_length < 0 || p->shadow_trace_length < 0) return vxrt_fail(VXRT_E_INVALID, "diffuse_trace: bad spp / trace length");
     return vxrt_launch_diffuse_trace(c, *p);
+}
+int vxrt_cuda_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_svgf_temporal(c, *p);
+}
+int vxrt_cuda_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_svgf_variance(c, *p);
+}
+int vxrt_cuda_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_svgf_spatial(c, *p);
+}
+int vxrt_cuda_svgf_end_frame(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    return vxrt_launch_svgf_end_frame(c);
 }
 int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);

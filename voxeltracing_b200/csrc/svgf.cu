@@ -1,0 +1,560 @@
+// svgf.cu — SVGF denoiser chain of the diffuse GI: temporal accumulation, variance estimate and the
+// a-trous spatial filter of Core/Shaders/SVGF/{TemporalFilter,VarianceEstimate,SpatialFilter}.glsl, dispatched by
+// Core/Pipeline.cpp:2428-2700.  One thread per pixel, a warp covers an 8x4 pixel tile (taps of neighbouring pixels
+// share sectors), attachments are read with the sampler model of texture.cuh (LINEAR + REPEAT for the float and RG8
+// images, NEAREST for the R8 G-buffer planes) and written in their final formats.
+//
+// The temporal pass has no transcendental on its path and is bit-identical to the oracle; the variance and spatial
+// passes go through expf / powf (CUDA vs libm: <= 2 ulp), tolerance in tests/test_gpu_svgf.py.
+#include "ctx.h"
+#include "texture.cuh"
+
+namespace {
+
+struct SetIn {
+    const uint16_t* __restrict__ sh;    // RGBA16F
+    const uint16_t* __restrict__ cocg;  // RG16F
+    const uint16_t* __restrict__ x;     // RGB16F utility | R16F variance / luminance
+    const uint8_t* __restrict__ aosky;  // RG8
+    int w, h;
+};
+struct SetOut {
+    uint16_t* __restrict__ sh;
+    uint16_t* __restrict__ cocg;
+    uint16_t* __restrict__ x;
+    uint8_t* __restrict__ aosky;
+};
+struct GBufIn {
+    const uint16_t* __restrict__ t;  // R16F, LINEAR
+    const uint8_t* __restrict__ n;   // R8, NEAREST
+    const uint8_t* __restrict__ b;   // R8, NEAREST
+    int w, h;
+};
+
+VXD f3 ray_direction_at(const float* __restrict__ inv_view, const float* __restrict__ inv_proj, f2 ss) {
+    f4 clip = F4(ss.x * 2.0f - 1.0f, ss.y * 2.0f - 1.0f, -1.0f, 1.0f);
+    f4 e = mat4_mul(inv_proj, clip);
+    f4 r = mat4_mul(inv_view, F4(e.x, e.y, -1.0f, 0.0f));
+    return F3(r.x, r.y, r.z);
+}
+// GetNormalFromID (TemporalFilter.glsl:111-123) as an index: 0..5 = the face normals, 6 = (1, 1, 1)
+VXD int normal_index(float n) {
+    int i = cvt_round(n * 10.0f);
+    return i > 5 ? 6 : (i < 0 ? 0 : i);
+}
+VXD bool in_screen_space(f2 v) { return v.x < 1.0f && v.x > 0.0f && v.y < 1.0f && v.y > 0.0f; }
+VXD float sh_to_y(float w) { return gmax(0.0f, 3.544905f * w); }
+VXD int block_at(const GBufIn& g, f2 uv) { return iclamp(cvt_trunc(floorf(att_r8_nearest(g.b, g.w, g.h, uv) * 255.0f)), 0, 127); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// TemporalFilter.glsl main() (:133-344)
+struct TemporalArgs {
+    float inv_view[16], inv_proj[16], prev_pv[16];
+    int width, height, row0, row1, be_useful;
+    SetIn cur, hist;
+    GBufIn g, pg;
+    SetOut out;
+};
+
+__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ TemporalArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    const f3 origin = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+    const float BaseDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
+    const f3 BasePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * BaseDist;
+    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
+    float BaseSH[4], BaseCoCg[2], BaseAO[2], lum[1];
+    att_half_bilinear<4>(a.cur.sh, a.cur.w, a.cur.h, tc, BaseSH);
+    att_half_bilinear<2>(a.cur.cocg, a.cur.w, a.cur.h, tc, BaseCoCg);
+    att_unorm8_bilinear<2>(a.cur.aosky, a.cur.w, a.cur.h, tc, BaseAO);
+    att_half_bilinear<1>(a.cur.x, a.cur.w, a.cur.h, tc, lum);
+    const float BaseLuminosity = lum[0];
+    const int BaseBlock = block_at(a.g, tc);
+    const f4 Proj = mat4_mul(a.prev_pv, F4(BasePos.x, BasePos.y, BasePos.z, 1.0f));
+    const f2 Reproj = F2((Proj.x / Proj.w) * 0.5f + 0.5f, (Proj.y / Proj.w) * 0.5f + 0.5f);
+
+    bool DoBlockWeight = true, DoNormalWeight = true;
+    float Tol = 0.75f;
+    const float d = distance(BasePos, origin);
+    if (d < 4.0f) Tol = 0.3f;
+    else if (d < 6.0f) Tol = 0.65f;
+    else if (d < 8.0f) Tol = 0.85f;
+    else if (d < 16.0f) Tol = 1.414f;
+    else if (d < 32.0f) Tol = 2.4f;
+    else if (d < 48.0f) { Tol = 3.5f; DoBlockWeight = false; }
+    else if (d < 64.0f) { Tol = 4.2f; DoBlockWeight = false; }
+    else if (d < 96.0f) { Tol = 6.25f; DoBlockWeight = false; DoNormalWeight = false; }
+    else if (d < 128.0f) { Tol = 9.0f; DoBlockWeight = false; DoNormalWeight = false; }
+    else if (d < 200.0f) { Tol = 14.0f; DoBlockWeight = false; DoNormalWeight = false; }
+
+    float TotalWeight = 0.0f, SumLuminosity = 0.0f, SumSPP = 0.0f, SumMoment = 0.0f;
+    float SumSH[4] = {0.0f, 0.0f, 0.0f, 0.0f}, SumCoCg[2] = {0.0f, 0.0f}, SumAO[2] = {0.0f, 0.0f};
+    int Successful = 0;
+    const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);
+#pragma unroll 1
+    for (int i = 0; i < 5; ++i) {
+        // Offsets (1,0) (0,1) (0,0) (-1,0) (0,-1), Weights 3/32 3/32 9/64 3/32 3/32 (:150-156)
+        const float ox = i == 0 ? 1.0f : (i == 3 ? -1.0f : 0.0f), oy = i == 1 ? 1.0f : (i == 4 ? -1.0f : 0.0f);
+        const float w = i == 2 ? 9.0f / 64.0f : 3.0f / 32.0f;
+        const f2 sc = F2(Reproj.x + (ox + 0.0f) * Texel.x, Reproj.y + (oy + 0.0f) * Texel.y);
+        const float b = 0.0035f;
+        if (!(sc.x < 1.0f - b && sc.x > b && sc.y < 1.0f - b && sc.y > b)) continue;
+        const float PrevDist = att_r16f_bilinear(a.pg.t, a.pg.w, a.pg.h, sc);
+        const f3 PrevPos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, sc)) * PrevDist;
+        const f3 e = F3(fabsf(BasePos.x - PrevPos.x), fabsf(BasePos.y - PrevPos.y), fabsf(BasePos.z - PrevPos.z));
+        const float PositionError = dot(e, e);
+        if (!(PositionError < Tol && ((PrevDist < 0.0f) == (BaseDist < 0.0f)))) continue;
+        if (DoNormalWeight && normal_index(att_r8_nearest(a.pg.n, a.pg.w, a.pg.h, sc)) != BaseNormal) continue;
+        if (DoBlockWeight && block_at(a.pg, sc) != BaseBlock) continue;
+        float u[3], s[4], c2[2], a2[2];
+        att_half_bilinear<3>(a.hist.x, a.hist.w, a.hist.h, sc, u);
+        att_half_bilinear<4>(a.hist.sh, a.hist.w, a.hist.h, sc, s);
+        att_half_bilinear<2>(a.hist.cocg, a.hist.w, a.hist.h, sc, c2);
+        att_unorm8_bilinear<2>(a.hist.aosky, a.hist.w, a.hist.h, sc, a2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) SumSH[k] += s[k] * w;
+        SumCoCg[0] += c2[0] * w; SumCoCg[1] += c2[1] * w;
+        SumSPP += u[0] * w; SumMoment += u[1] * w; SumLuminosity += u[2] * w;
+        SumAO[0] += a2[0] * w; SumAO[1] += a2[1] * w;
+        TotalWeight += w;
+        Successful++;
+    }
+    if (TotalWeight > 0.001f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) SumSH[k] /= TotalWeight;
+        SumCoCg[0] /= TotalWeight; SumCoCg[1] /= TotalWeight;
+        SumMoment /= TotalWeight; SumSPP /= TotalWeight; SumLuminosity /= TotalWeight;
+        SumAO[0] /= TotalWeight; SumAO[1] /= TotalWeight;
+    } else {
+        Successful = 0;
+    }
+    float SppInc = SumSPP + (a.be_useful ? 1.0f : 0.0f);
+    if (Successful <= 0) SppInc = 0.01f;
+    float Blend = gmax(1.0f / SppInc, 0.05f);
+    const float MomentFactor = Blend;
+    if (!a.be_useful) Blend = 0.99f;
+    const float UtilitySPP = Successful <= 0 ? 0.0f : SppInc;
+    const float UtilityMoment = (1.0f - MomentFactor) * SumMoment + MomentFactor * (BaseLuminosity * BaseLuminosity);
+    const float StoreLuma = gmix(SumLuminosity, BaseLuminosity, Blend);
+    float oSH[4], oCC[2], oAO[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oSH[k] = Successful <= 0 ? BaseSH[k] : gmix(SumSH[k], BaseSH[k], Blend);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        oCC[k] = Successful <= 0 ? BaseCoCg[k] : gmix(SumCoCg[k], BaseCoCg[k], Blend);
+        oAO[k] = Successful <= 0 ? BaseAO[k] : gmix(SumAO[k], BaseAO[k], Blend);
+    }
+    const size_t i = (size_t)py * a.width + px;
+    ushort4 o4;
+    o4.x = float_to_half_bits(gclamp(oSH[0], -100.0f, 100.0f)); o4.y = float_to_half_bits(gclamp(oSH[1], -100.0f, 100.0f));
+    o4.z = float_to_half_bits(gclamp(oSH[2], -100.0f, 100.0f)); o4.w = float_to_half_bits(gclamp(oSH[3], -100.0f, 100.0f));
+    reinterpret_cast<ushort4*>(a.out.sh)[i] = o4;
+    ushort2 o2;
+    o2.x = float_to_half_bits(gclamp(oCC[0], -10.0f, 100.0f)); o2.y = float_to_half_bits(gclamp(oCC[1], -10.0f, 100.0f));
+    reinterpret_cast<ushort2*>(a.out.cocg)[i] = o2;
+    a.out.x[3 * i] = float_to_half_bits(gclamp(UtilitySPP, -150.0f, 150.0f));
+    a.out.x[3 * i + 1] = float_to_half_bits(gclamp(UtilityMoment, -150.0f, 150.0f));
+    a.out.x[3 * i + 2] = float_to_half_bits(gclamp(StoreLuma, -150.0f, 150.0f));
+    uchar2 ao;
+    ao.x = float_to_unorm8(gclamp(oAO[0], 0.0f, 1.0f)); ao.y = float_to_unorm8(gclamp(oAO[1], 0.0f, 1.0f));
+    reinterpret_cast<uchar2*>(a.out.aosky)[i] = ao;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VarianceEstimate.glsl main() (:75-184).  GetPositionAt(SampleCoord) is only consumed through .w (the sampled distance).
+struct VarianceArgs {
+    int width, height, row0, row1, do_spatial, aggressive;
+    SetIn in;  // temporal set: x = utility RGB16F
+    GBufIn g;
+    SetOut out;  // x = variance R16F; aosky not written
+};
+
+// pow(max(dot(n0, n1), 0), 16) over the values a pair of GetNormalFromID normals can produce (0, 1, 3): exact like powf
+VXD float normal_weight16(int n0, int n1) {
+    if (n0 == 6 && n1 == 6) return 43046720.0f;                      // powf(3, 16)
+    if (n0 == 6) return (n1 == 0 || n1 == 2 || n1 == 5) ? 1.0f : 0.0f;  // (1,1,1) . axis = sign of the axis
+    if (n1 == 6) return (n0 == 0 || n0 == 2 || n0 == 5) ? 1.0f : 0.0f;
+    return n0 == n1 ? 1.0f : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constant__ VarianceArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    const float BaseDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
+    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
+    float BaseUt[3], BaseSH[4], BaseCC[2];
+    att_half_bilinear<3>(a.in.x, a.in.w, a.in.h, tc, BaseUt);
+    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, tc, BaseSH);
+    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, tc, BaseCC);
+    const float BaseLum = sh_to_y(BaseSH[3]);
+    const float Frames = BaseUt[0], BaseMoment = BaseUt[1];
+    float oSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, oCC[2] = {BaseCC[0], BaseCC[1]};
+    float Variance = BaseMoment - BaseLum * BaseLum;
+    if (a.do_spatial) {
+        const float THRESH = a.aggressive ? 4.0f + 4.0f + 4.0f : 4.0f + 4.0f;
+        if (Frames < THRESH) {
+            const float ColorPhi = a.aggressive ? 5.0f : 5.0f * 2.0f;
+            const int K = a.aggressive ? 4 : 1;
+            const f2 Texel = F2(1.0f / (float)a.in.w, 1.0f / (float)a.in.h);
+            float TotalWeight = 0.0f, TotalMoment = 0.0f, TotalLum = 0.0f, TotalWeight2 = 0.0f;
+            float TotalSH[4] = {0.0f, 0.0f, 0.0f, 0.0f}, TotalCC[2] = {0.0f, 0.0f};
+#pragma unroll 1
+            for (int x = -K; x <= K; ++x)
+#pragma unroll 1
+                for (int y = -K; y <= K; ++y) {
+                    const f2 sc = F2(tc.x + (float)x * Texel.x, tc.y + (float)y * Texel.y);
+                    if (!in_screen_space(sc)) continue;
+                    const float SampleDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, sc);
+                    const int SampleNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, sc));
+                    float ut[3], sh[4], cc[2];
+                    att_half_bilinear<3>(a.in.x, a.in.w, a.in.h, sc, ut);
+                    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, sc, sh);
+                    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, sc, cc);
+                    const float SampleLum = sh_to_y(sh[3]);
+                    const float NormalWeight = normal_weight16(BaseNormal, SampleNormal);
+                    const float ed = expf(-fabsf(SampleDist - BaseDist));
+                    const float DepthWeight = ed * ed;
+                    const float LumWeight = fabsf(SampleLum - BaseLum) / ColorPhi;
+                    float Weight = expf(-LumWeight) * NormalWeight * DepthWeight;
+                    const float Weight_2 = gmax(Weight, 0.0000000015f);
+                    Weight = gmax(Weight, 0.000000015f);
+                    TotalWeight += Weight;
+                    TotalMoment += ut[1] * Weight_2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) TotalSH[k] += sh[k] * Weight;
+                    TotalCC[0] += cc[0] * Weight; TotalCC[1] += cc[1] * Weight;
+                    TotalLum += SampleLum * Weight_2;
+                    TotalWeight2 += Weight_2;
+                }
+            if (TotalWeight > 0.0f) {
+                TotalMoment /= TotalWeight2;
+                TotalLum /= TotalWeight2;
+                TotalCC[0] /= TotalWeight; TotalCC[1] /= TotalWeight;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) TotalSH[k] /= TotalWeight;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oSH[k] = TotalSH[k];
+            oCC[0] = TotalCC[0]; oCC[1] = TotalCC[1];
+            Variance = TotalMoment - TotalLum * TotalLum;
+            Variance *= 3.0f;
+        }
+        Variance *= THRESH / Frames;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oSH[k] = gclamp(oSH[k], -100.0f, 100.0f);
+        oCC[0] = gclamp(oCC[0], -10.0f, 100.0f); oCC[1] = gclamp(oCC[1], -10.0f, 100.0f);
+        Variance = gclamp(Variance, -1.0f, 50.0f);
+    }
+    const size_t i = (size_t)py * a.width + px;
+    ushort4 o4;
+    o4.x = float_to_half_bits(oSH[0]); o4.y = float_to_half_bits(oSH[1]); o4.z = float_to_half_bits(oSH[2]); o4.w = float_to_half_bits(oSH[3]);
+    reinterpret_cast<ushort4*>(a.out.sh)[i] = o4;
+    ushort2 o2;
+    o2.x = float_to_half_bits(oCC[0]); o2.y = float_to_half_bits(oCC[1]);
+    reinterpret_cast<ushort2*>(a.out.cocg)[i] = o2;
+    a.out.x[i] = float_to_half_bits(Variance);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SpatialFilter.glsl main() (:178-364), one a-trous iteration
+struct SpatialArgs {
+    int width, height, row0, row1;
+    int step, large_kernel, do_spatial, aggressive;
+    float phi_bias, time_offset, additional_scale;
+    SetIn in;                           // sh, cocg, x = u_VarianceTexture (R16F), aosky = u_AO
+    const uint16_t* __restrict__ temporal_utility;  // u_TemporalMoment RGB16F
+    int tw, th;
+    GBufIn g;
+    SetOut out;
+};
+
+__global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant__ SpatialArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    // GradientNoise (:163-168); Jitter = ivec2(float) has both components equal
+    const float cx = ((float)px + 0.5f) + a.time_offset, cy = ((float)py + 0.5f) + a.time_offset;
+    const float noise = gfract(52.9829189f * gfract(0.06711056f * cx + 0.00583715f * cy));
+    const float jf = (float)cvt_trunc((noise - 0.5f) * ((float)a.step * 0.8f)) * 0.5f;
+    const float BaseDepth = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
+    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
+    float BaseSH[4], BaseCC[2], BaseAO[2];
+    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, tc, BaseSH);
+    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, tc, BaseCC);
+    const float BaseLum = sh_to_y(BaseSH[3]);
+    // GaussianVariance (:98-133)
+    float BaseVariance = 0.0f, VarianceSum = 0.0f, TotalKernel = 0.0f;
+    {
+        const f2 TexelSH = F2(1.0f / (float)a.in.w, 1.0f / (float)a.in.h);
+#pragma unroll
+        for (int x = -1; x <= 1; ++x)
+#pragma unroll
+            for (int y = -1; y <= 1; ++y) {
+                const f2 sc = F2(tc.x + (float)x * TexelSH.x, tc.y + (float)y * TexelSH.y);
+                if (!in_screen_space(sc)) continue;
+                const float kx = x == 0 ? 0.60283f : 0.198585f, ky = y == 0 ? 0.60283f : 0.198585f;
+                const float KernelValue = kx * ky;
+                const float V = att_r16f_bilinear(a.in.x, a.in.w, a.in.h, sc);
+                if (x == 0 && y == 0) BaseVariance = V;
+                VarianceSum += V * KernelValue;
+                TotalKernel += KernelValue;
+            }
+    }
+    const float VarianceEstimate = VarianceSum / gmax(TotalKernel, 0.01f);
+    att_unorm8_bilinear<2>(a.in.aosky, a.in.w, a.in.h, tc, BaseAO);
+    float oSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, oCC[2] = {BaseCC[0], BaseCC[1]}, oVar = BaseVariance, oAO[2] = {BaseAO[0], BaseAO[1]};
+    if (a.do_spatial) {
+        const bool FilterAO = a.step <= 4;
+        float TotalSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, TotalCC[2] = {BaseCC[0], BaseCC[1]};
+        float TotalWeight = 1.0f, TotalVariance = BaseVariance, TotalAO[2] = {BaseAO[0], BaseAO[1]}, TotalAOWeight = 1.0f;
+        float tu[3];
+        att_half_bilinear<3>(a.temporal_utility, a.tw, a.th, tc, tu);
+        const bool Strong = tu[0] <= 8.0f && a.aggressive && a.step <= 8;
+        float CurveExponent = 0.0f;
+        if (VarianceEstimate < 0.01f) CurveExponent = 128.0f;
+        else if (VarianceEstimate < 0.025f) CurveExponent = 112.0f;
+        else if (VarianceEstimate < 0.05f) CurveExponent = 96.0f;
+        else if (VarianceEstimate < 0.075f) CurveExponent = 84.0f;
+        else if (VarianceEstimate < 0.1f) CurveExponent = 70.0f;
+        float Tweaked = VarianceEstimate;
+        if (VarianceEstimate < 0.1f) {  // TweakVariance (:170-176)
+            const float F = gclamp(VarianceEstimate, 0.0f, 1.0f);
+            Tweaked = F * powf(1.0f - F, CurveExponent + 6.0f);
+        }
+        float PhiColor = sqrtf(gmax(0.0f, 0.000001f + Tweaked));
+        PhiColor /= gmax(a.phi_bias, 0.1f);
+        const int K = a.large_kernel ? 2 : 1;
+        const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);
+        const float fstep = (float)a.step;
+#pragma unroll 1
+        for (int x = -K; x <= K; ++x)
+#pragma unroll 1
+            for (int y = -K; y <= K; ++y) {
+                if (x == 0 && y == 0) continue;
+                const f2 sc = F2(tc.x + (((float)x * fstep) * a.additional_scale + jf) * Texel.x,
+                                 tc.y + (((float)y * fstep) * a.additional_scale + jf) * Texel.y);
+                if (!in_screen_space(sc)) continue;
+                const float SampleDepth = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, sc);
+                const float DepthDiff = fabsf(SampleDepth - BaseDepth);
+                // `BaseDepth < 0.0f == DepthDiff < 0.0f` parses as (BaseDepth < 0) == (DepthDiff < 0)
+                if ((BaseDepth < 0.0f) != (DepthDiff < 0.0f)) continue;
+                const int SampleNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, sc));
+                float sh[4], cc[2];
+                att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, sc, sh);
+                att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, sc, cc);
+                const float SampleLum = sh_to_y(sh[3]);
+                const float SampleVariance = att_r16f_bilinear(a.in.x, a.in.w, a.in.h, sc);
+                // pow(max(dot, 0), 32) in {0, 1, 3^32}, clamped to [0.001, 1]
+                const float NormalWeight = normal_weight16(BaseNormal, SampleNormal) > 0.0f ? 1.0f : 0.001f;
+                const float LumWeight = fabsf(SampleLum - BaseLum) / PhiColor;
+                const float ed = expf(-gmax(DepthDiff, 0.00001f));
+                const float DepthWeight = gclamp(ed * ed, 0.0001f, 1.0f);
+                float Weight = Strong ? (NormalWeight * DepthWeight) : (expf(-LumWeight) * NormalWeight * DepthWeight);
+                Weight = gclamp(Weight, 0.001f, 1.0f);
+                const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
+                const float XW = ax == 0 ? 1.0f : (ax == 1 ? 2.0f / 3.0f : 1.0f / 6.0f), YW = ay == 0 ? 1.0f : (ay == 1 ? 2.0f / 3.0f : 1.0f / 6.0f);
+                Weight = (XW * YW) * Weight;
+                Weight = gmax(Weight, 0.00000001f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) TotalSH[k] += sh[k] * Weight;
+                TotalCC[0] += cc[0] * Weight; TotalCC[1] += cc[1] * Weight;
+                TotalVariance += (Weight * Weight) * SampleVariance;
+                TotalWeight += Weight;
+                if (a.step <= 6) {  // FilterSky || FilterAO
+                    const float AOW = gclamp((XW * YW) * NormalWeight * DepthWeight, 0.000001f, 1.0f);
+                    float ao[2];
+                    att_unorm8_bilinear<2>(a.in.aosky, a.in.w, a.in.h, sc, ao);
+                    TotalAO[0] += ao[0] * AOW; TotalAO[1] += ao[1] * AOW;
+                    TotalAOWeight += AOW;
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oSH[k] = gclamp(TotalSH[k] / TotalWeight, -100.0f, 100.0f);
+        oCC[0] = gclamp(TotalCC[0] / TotalWeight, -10.0f, 100.0f); oCC[1] = gclamp(TotalCC[1] / TotalWeight, -10.0f, 100.0f);
+        oVar = gclamp(TotalVariance / (TotalWeight * TotalWeight), -1.0f, 50.0f);
+        oAO[0] = FilterAO ? TotalAO[0] / TotalAOWeight : BaseAO[0];
+        oAO[1] = TotalAO[1] / TotalAOWeight;
+        oAO[0] = gclamp(oAO[0], 0.0f, 1.0f); oAO[1] = gclamp(oAO[1], 0.0f, 1.0f);
+    }
+    const size_t i = (size_t)py * a.width + px;
+    ushort4 o4;
+    o4.x = float_to_half_bits(oSH[0]); o4.y = float_to_half_bits(oSH[1]); o4.z = float_to_half_bits(oSH[2]); o4.w = float_to_half_bits(oSH[3]);
+    reinterpret_cast<ushort4*>(a.out.sh)[i] = o4;
+    ushort2 o2;
+    o2.x = float_to_half_bits(oCC[0]); o2.y = float_to_half_bits(oCC[1]);
+    reinterpret_cast<ushort2*>(a.out.cocg)[i] = o2;
+    a.out.x[i] = float_to_half_bits(oVar);
+    uchar2 ao;
+    ao.x = float_to_unorm8(oAO[0]); ao.y = float_to_unorm8(oAO[1]);
+    reinterpret_cast<uchar2*>(a.out.aosky)[i] = ao;
+}
+
+inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+}
+
+// bytes per pixel of image k (0..3) of a set: temporal sets carry the RGB16F utility, the others an R16F plane
+inline int set_bpp(int k, bool temporal) { return k == 0 ? 8 : (k == 1 ? 4 : (k == 2 ? (temporal ? 6 : 2) : 2)); }
+inline bool is_temporal_set(int id) { return id == VXRT_ATT_SVGF_TEMPORAL_A || id == VXRT_ATT_SVGF_TEMPORAL_B; }
+inline bool is_svgf_set(int id) {
+    return id == VXRT_ATT_SVGF_TEMPORAL_A || id == VXRT_ATT_SVGF_TEMPORAL_B || id == VXRT_ATT_SVGF_VARIANCE || id == VXRT_ATT_SVGF_DENOISE_A ||
+           id == VXRT_ATT_SVGF_DENOISE_B;
+}
+
+int set_in(vxrt_ctx* c, const char* fn, int id, int x_bpp, bool need_ao, SetIn* s) {
+    if (!(is_svgf_set(id) || id == VXRT_ATT_GI_SH)) return vxrt_fail(VXRT_E_INVALID, "%s: %d does not name an image set", fn, id);
+    const Attachment& a0 = c->att[id];
+    if (!a0.ptr || a0.width <= 0) return vxrt_fail(VXRT_E_STATE, "%s: image set %d has not been written", fn, id);
+    for (int k = 0; k < 4; ++k) {
+        if (k == 3 && !need_ao) continue;
+        const Attachment& a = c->att[id + k];
+        const int want = k == 2 ? x_bpp : set_bpp(k, false);
+        if (!a.ptr || a.width != a0.width || a.height != a0.height || a.bpp != want)
+            return vxrt_fail(VXRT_E_STATE, "%s: image %d of set %d is missing or has the wrong format (%d bytes per pixel, expected %d)", fn, k, id, a.bpp, want);
+    }
+    s->sh = (const uint16_t*)c->att[id].ptr; s->cocg = (const uint16_t*)c->att[id + 1].ptr; s->x = (const uint16_t*)c->att[id + 2].ptr;
+    s->aosky = need_ao ? (const uint8_t*)c->att[id + 3].ptr : nullptr;
+    s->w = a0.width; s->h = a0.height;
+    return VXRT_OK;
+}
+
+int set_out(vxrt_ctx* c, const char* fn, int id, int w, int h, bool with_ao, SetOut* s) {
+    if (!is_svgf_set(id)) return vxrt_fail(VXRT_E_INVALID, "%s: %d does not name an SVGF image set", fn, id);
+    int rc;
+    for (int k = 0; k < (with_ao ? 4 : 3); ++k)
+        if ((rc = vxrt_ensure_attachment(c, id + k, w, h, set_bpp(k, is_temporal_set(id))))) return rc;
+    s->sh = (uint16_t*)c->att[id].ptr; s->cocg = (uint16_t*)c->att[id + 1].ptr; s->x = (uint16_t*)c->att[id + 2].ptr;
+    s->aosky = with_ao ? (uint8_t*)c->att[id + 3].ptr : nullptr;
+    return VXRT_OK;
+}
+
+int gbuf_in(vxrt_ctx* c, const char* fn, int t_id, int n_id, int b_id, GBufIn* g) {
+    const Attachment& t = c->att[t_id];
+    if (!t.ptr || t.width <= 0) return vxrt_fail(VXRT_E_STATE, "%s: G-buffer attachment %d has not been written", fn, t_id);
+    const Attachment& n = c->att[n_id];
+    const Attachment& b = c->att[b_id];
+    if (!n.ptr || !b.ptr || n.width != t.width || n.height != t.height || b.width != t.width || b.height != t.height)
+        return vxrt_fail(VXRT_E_STATE, "%s: G-buffer attachments %d / %d / %d do not form one frame", fn, t_id, n_id, b_id);
+    g->t = (const uint16_t*)t.ptr; g->n = (const uint8_t*)n.ptr; g->b = (const uint8_t*)b.ptr; g->w = t.width; g->h = t.height;
+    return VXRT_OK;
+}
+
+}  // namespace
+
+int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
+    static const char* fn = "vxrt_cuda_svgf_temporal";
+    if (p.out_set == p.history_set || p.out_set == p.in_set) return vxrt_fail(VXRT_E_INVALID, "%s: out_set aliases an input set", fn);
+    if (!is_temporal_set(p.out_set) || !is_temporal_set(p.history_set)) return vxrt_fail(VXRT_E_INVALID, "%s: history_set / out_set must be VXRT_ATT_SVGF_TEMPORAL_A / _B", fn);
+    TemporalArgs a;
+    int rc;
+    if ((rc = set_in(c, fn, p.in_set, 2, true, &a.cur))) return rc;
+    if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
+    // first frame: no history yet.  The engine's FBOs start out zero-filled, so do these.
+    if (!c->att[p.history_set].ptr || c->att[p.history_set].width != p.width || c->att[p.history_set].height != p.height) {
+        SetOut z;
+        if ((rc = set_out(c, fn, p.history_set, p.width, p.height, true, &z))) return rc;
+        for (int k = 0; k < 4; ++k) VX_CUDA(cudaMemsetAsync(c->att[p.history_set + k].ptr, 0, (size_t)p.width * p.height * c->att[p.history_set + k].bpp, c->stream));
+    }
+    if (!c->att[VXRT_ATT_PREV_INITIAL_T].ptr || c->att[VXRT_ATT_PREV_INITIAL_T].width != a.g.w || c->att[VXRT_ATT_PREV_INITIAL_T].height != a.g.h) {
+        const int ids[3] = {VXRT_ATT_PREV_INITIAL_T, VXRT_ATT_PREV_INITIAL_NORMAL, VXRT_ATT_PREV_INITIAL_BLOCK}, bpp[3] = {2, 1, 1};
+        for (int k = 0; k < 3; ++k) {
+            if ((rc = vxrt_ensure_attachment(c, ids[k], a.g.w, a.g.h, bpp[k]))) return rc;
+            VX_CUDA(cudaMemsetAsync(c->att[ids[k]].ptr, 0, (size_t)a.g.w * a.g.h * bpp[k], c->stream));
+        }
+    }
+    if ((rc = set_in(c, fn, p.history_set, 6, true, &a.hist))) return rc;
+    if ((rc = gbuf_in(c, fn, VXRT_ATT_PREV_INITIAL_T, VXRT_ATT_PREV_INITIAL_NORMAL, VXRT_ATT_PREV_INITIAL_BLOCK, &a.pg))) return rc;
+    if ((rc = set_out(c, fn, p.out_set, p.width, p.height, true, &a.out))) return rc;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    // u_PrevProjection * u_PrevView: column j = P * (column j of V), with the mat4 * vec4 association of vmath.cuh
+    for (int j = 0; j < 4; ++j) {
+        const float* v = p.prev_view + 4 * j;
+        const float* m = p.prev_projection;
+        for (int r = 0; r < 4; ++r) a.prev_pv[4 * j + r] = (m[r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]);
+    }
+    a.width = p.width; a.height = p.height; a.be_useful = p.be_useful;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    svgf_temporal_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p) {
+    static const char* fn = "vxrt_cuda_svgf_variance";
+    VarianceArgs a;
+    int rc;
+    if (!is_temporal_set(p.in_set)) return vxrt_fail(VXRT_E_INVALID, "%s: in_set must be a temporal set", fn);
+    if ((rc = set_in(c, fn, p.in_set, 6, false, &a.in))) return rc;
+    if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
+    if ((rc = set_out(c, fn, VXRT_ATT_SVGF_VARIANCE, p.width, p.height, false, &a.out))) return rc;
+    a.width = p.width; a.height = p.height; a.do_spatial = p.do_spatial; a.aggressive = p.aggressive_disocclusion;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    svgf_variance_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p) {
+    static const char* fn = "vxrt_cuda_svgf_spatial";
+    if (p.out_set == p.in_set || p.out_set == p.ao_set || p.out_set == p.temporal_set) return vxrt_fail(VXRT_E_INVALID, "%s: out_set aliases an input set", fn);
+    if (p.out_set != VXRT_ATT_SVGF_DENOISE_A && p.out_set != VXRT_ATT_SVGF_DENOISE_B) return vxrt_fail(VXRT_E_INVALID, "%s: out_set must be VXRT_ATT_SVGF_DENOISE_A / _B", fn);
+    if (!is_temporal_set(p.temporal_set)) return vxrt_fail(VXRT_E_INVALID, "%s: temporal_set must be a temporal set", fn);
+    if (p.step < 1) return vxrt_fail(VXRT_E_INVALID, "%s: step %d", fn, p.step);
+    SpatialArgs a;
+    SetIn ao, tmp;
+    int rc;
+    if ((rc = set_in(c, fn, p.in_set, 2, false, &a.in))) return rc;
+    if ((rc = set_in(c, fn, p.ao_set, is_temporal_set(p.ao_set) ? 6 : 2, true, &ao))) return rc;
+    if ((rc = set_in(c, fn, p.temporal_set, 6, false, &tmp))) return rc;
+    if (ao.w != a.in.w || ao.h != a.in.h) return vxrt_fail(VXRT_E_STATE, "%s: ao_set and in_set differ in size", fn);
+    a.in.aosky = ao.aosky;
+    a.temporal_utility = tmp.x; a.tw = tmp.w; a.th = tmp.h;
+    if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
+    if ((rc = set_out(c, fn, p.out_set, p.width, p.height, true, &a.out))) return rc;
+    a.width = p.width; a.height = p.height;
+    a.step = p.step; a.large_kernel = p.large_kernel; a.do_spatial = p.do_spatial; a.aggressive = p.aggressive_disocclusion;
+    a.phi_bias = p.color_phi_bias;
+    const float tm = p.time * 100.493850275f;
+    a.time_offset = tm - 500.0f * floorf(tm / 500.0f);  // mod(u_Time * 100.493850275, 500)
+    a.additional_scale = 1.0f * (1.0f - p.resolution_scale) + 2.4f * p.resolution_scale;  // mix(1, 2.4, u_ResolutionScale)
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    svgf_spatial_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+// end of frame: this frame's primary G-buffer becomes the previous one (the engine swaps InitialTraceFBO_1 / _2,
+// Core/Pipeline.cpp:2046-2048).  4 bytes per pixel are copied on the stream (pointers handed out by
+// vxrt_cuda_attachment_device stay valid, which a swap would break).
+int vxrt_launch_svgf_end_frame(vxrt_ctx* c) {
+    const int cur[3] = {VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK};
+    const int prev[3] = {VXRT_ATT_PREV_INITIAL_T, VXRT_ATT_PREV_INITIAL_NORMAL, VXRT_ATT_PREV_INITIAL_BLOCK};
+    for (int k = 0; k < 3; ++k)
+        if (!c->att[cur[k]].ptr || c->att[cur[k]].width <= 0) return vxrt_fail(VXRT_E_STATE, "vxrt_cuda_svgf_end_frame: no primary G-buffer (vxrt_cuda_initial_trace)");
+    for (int k = 0; k < 3; ++k) {
+        Attachment& a = c->att[cur[k]];
+        Attachment& b = c->att[prev[k]];
+        int rc;
+        if ((rc = vxrt_ensure_attachment(c, prev[k], a.width, a.height, a.bpp))) return rc;
+        VX_CUDA(cudaMemcpyAsync(b.ptr, a.ptr, (size_t)a.width * a.height * a.bpp, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return VXRT_OK;
+}

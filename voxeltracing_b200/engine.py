@@ -38,7 +38,14 @@ _ATT_DTYPES = {
     abi.ATT_REFL_COLOR: (np.float16, 4),
     abi.ATT_REFL_HITDIST: (np.float16, 1),
     abi.ATT_REFL_EMISSIVE: (np.uint8, 1),
+    abi.ATT_PREV_INITIAL_T: (np.float16, 1),
+    abi.ATT_PREV_INITIAL_NORMAL: (np.uint8, 1),
+    abi.ATT_PREV_INITIAL_BLOCK: (np.uint8, 1),
 }
+# SVGF image sets (four consecutive ids): SH, CoCg, utility RGB16F (temporal sets) / variance R16F, AO + sky
+for _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_B):
+    _ATT_DTYPES.update({_s: (np.float16, 4), _s + 1: (np.float16, 2),
+                        _s + 2: (np.float16, 3 if _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B) else 1), _s + 3: (np.uint8, 2)})
 
 
 def _p(a: np.ndarray):
@@ -230,7 +237,39 @@ class Context:
     def reflection_trace(self, params: "abi.ReflectionParams"):
         self._check(self._lib.vxrt_cuda_reflection_trace(self._h, C.byref(params)))
 
+    # -- SVGF chain of the diffuse GI (Core/Pipeline.cpp:2428-2700) --
+    def svgf_temporal(self, params: "abi.SvgfTemporalParams"):
+        self._check(self._lib.vxrt_cuda_svgf_temporal(self._h, C.byref(params)))
+
+    def svgf_variance(self, params: "abi.SvgfVarianceParams"):
+        self._check(self._lib.vxrt_cuda_svgf_variance(self._h, C.byref(params)))
+
+    def svgf_spatial(self, params: "abi.SvgfSpatialParams"):
+        self._check(self._lib.vxrt_cuda_svgf_spatial(self._h, C.byref(params)))
+
+    def svgf_end_frame(self):
+        self._check(self._lib.vxrt_cuda_svgf_end_frame(self._h))
+
+    def read_set(self, first: int, with_ao: bool = True) -> dict:
+        d = {"sh": self.read_attachment(first), "cocg": self.read_attachment(first + 1), "x": self.read_attachment(first + 2)}
+        if with_ao:
+            d["aosky"] = self.read_attachment(first + 3)
+        return d
+
+    def write_set(self, first: int, d: dict):
+        for k, name in enumerate(("sh", "cocg", "x", "aosky")):
+            if name in d:
+                self.write_attachment(first + k, d[name])
+
     # -- attachments --
+    def write_attachment(self, att: int, data: np.ndarray):
+        """glTexImage2D: (h, w[, channels]) array in the attachment's format."""
+        dt, ch = _ATT_DTYPES[att]
+        a = np.ascontiguousarray(data, dtype=dt)
+        h, w = a.shape[:2]
+        assert a.size == h * w * ch, (a.shape, ch)
+        self._check(self._lib.vxrt_cuda_write_attachment(self._h, att, w, h, a.itemsize * ch, _p(a)))
+
     def attachment_info(self, att: int):
         ptr, w, h, bpp = C.c_void_p(), C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self._lib.vxrt_cuda_attachment_device(self._h, att, C.byref(ptr), C.byref(w), C.byref(h), C.byref(bpp)))

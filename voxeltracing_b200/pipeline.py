@@ -216,3 +216,69 @@ def band_rows(height: int, rank: int, world: int, band: int = 8):
     row0 = b0 * band
     rows = min(height, (b0 + nb) * band) - row0
     return row0, max(rows, 0)
+
+
+class SvgfChain:
+    """The SVGF denoiser chain of the diffuse GI in the order of Core/Pipeline.cpp:2428-2700: temporal accumulation
+    (temporal sets ping-ponged by frame parity, :2420-2426), variance estimate, five a-trous iterations with steps
+    16, 8, 4, 2, 1 ping-ponging the two denoise sets (:2592-2700), then the G-buffer hand-over to the next frame.
+    Consumes the attachments of `primary` and `gi` of the same frame; the denoised result is `final_set`."""
+
+    STEPS = (16, 8, 4, 2, 1)                    # Pipeline.cpp:2583-2589 (WiderSVGF off)
+    # bytes every stage reads + writes per pixel when each image is touched once (DESIGN.md §3.4)
+    STAGE_BYTES = {"temporal": 64, "variance": 35, "spatial": 41}
+    final_set = abi.ATT_SVGF_DENOISE_A          # iteration 4 writes DiffuseDenoiseFBO
+
+    def __init__(self, ctx: Context, width: int, height: int, color_phi_bias: float = 2.8, resolution_scale: float = 0.25,
+                 large_kernel: bool = False, aggressive: bool = True):
+        self.ctx, self.width, self.height = ctx, width, height
+        self.color_phi_bias, self.resolution_scale = color_phi_bias, resolution_scale     # Pipeline.cpp:86, 112
+        self.large_kernel, self.aggressive = large_kernel, aggressive
+        self.prev_cam = None
+
+    def prepare(self, cam: host_api.Camera, frame: int, time: float | None = None, tile=(0, 0)):
+        lib = self.ctx._lib
+        prev = self.prev_cam or cam
+        self.prev_cam = cam
+        cur_t, hist_t = (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B) if frame % 2 == 0 else (abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_TEMPORAL_A)
+        out = []
+        tp = abi.SvgfTemporalParams()
+        _fill(tp.inv_view, cam.inv_view); _fill(tp.inv_projection, cam.inv_projection)
+        _fill(tp.prev_view, prev.view); _fill(tp.prev_projection, prev.projection)
+        tp.width, tp.height, tp.in_set, tp.history_set, tp.out_set, tp.be_useful = self.width, self.height, abi.ATT_GI_SH, hist_t, cur_t, 1
+        tp.tile.row0, tp.tile.rows = tile
+        out.append(("temporal", lib.vxrt_cuda_svgf_temporal, tp))
+        vp = abi.SvgfVarianceParams()
+        _fill(vp.inv_view, cam.inv_view); _fill(vp.inv_projection, cam.inv_projection)
+        vp.width, vp.height, vp.in_set, vp.do_spatial, vp.aggressive_disocclusion = self.width, self.height, cur_t, 1, int(self.aggressive)
+        vp.tile.row0, vp.tile.rows = tile
+        out.append(("variance", lib.vxrt_cuda_svgf_variance, vp))
+        for i, step in enumerate(self.STEPS):
+            cur = abi.ATT_SVGF_DENOISE_A if i % 2 == 0 else abi.ATT_SVGF_DENOISE_B
+            prv = abi.ATT_SVGF_VARIANCE if i == 0 else (abi.ATT_SVGF_DENOISE_B if i % 2 == 0 else abi.ATT_SVGF_DENOISE_A)
+            sp = abi.SvgfSpatialParams()
+            _fill(sp.inv_view, cam.inv_view); _fill(sp.inv_projection, cam.inv_projection)
+            sp.width, sp.height = self.width, self.height
+            sp.in_set, sp.ao_set, sp.temporal_set, sp.out_set, sp.step = prv, (cur_t if i == 0 else prv), cur_t, cur, step
+            sp.large_kernel, sp.do_spatial, sp.aggressive_disocclusion = int(self.large_kernel), 1, int(self.aggressive)
+            sp.color_phi_bias, sp.resolution_scale = self.color_phi_bias, self.resolution_scale
+            sp.time = frame / 60.0 if time is None else time
+            sp.tile.row0, sp.tile.rows = tile
+            out.append((f"spatial{i}", lib.vxrt_cuda_svgf_spatial, sp))
+        return out
+
+    def submit(self, prepared, hook=None, end_frame: bool = True):
+        import ctypes as C
+
+        h = self.ctx._h
+        for name, fn, params in prepared:
+            if hook:
+                hook(name, "begin")
+            self.ctx._check(fn(h, C.byref(params)))
+            if hook:
+                hook(name, "end")
+        if end_frame:
+            self.ctx.svgf_end_frame()
+
+    def run(self, cam: host_api.Camera, frame: int, time: float | None = None, tile=(0, 0), hook=None):
+        self.submit(self.prepare(cam, frame, time, tile), hook)
