@@ -37,42 +37,129 @@ VXD f3 ray_direction_at(const float* __restrict__ inv_view, const float* __restr
     f4 r = mat4_mul(inv_view, F4(e.x, e.y, -1.0f, 0.0f));
     return F3(r.x, r.y, r.z);
 }
+VXD bool in_screen_space(f2 v) { return v.x < 1.0f && v.x > 0.0f && v.y < 1.0f && v.y > 0.0f; }
+VXD float sh_to_y(float w) { return gmax(0.0f, 3.544905f * w); }
+
+// ---- samplers (the model of texture.cuh: REPEAT, texel centres at +0.5, bilinear weights in full float), with the
+// coordinate set-up done once per tap and shared by every image of the same geometry, and texels loaded whole ----
+struct Tap {
+    int o00, o10, o01, o11;  // pixel offsets of the four texels
+    float a, b, ia, ib;      // weights and their complements
+};
+// REPEAT wrap; every tap of these passes lies in [-1, n] (screen-space tests), anything else takes the general path
+VXD int wrap_near(int i, int n) {
+    if ((unsigned)(i + 1) <= (unsigned)(n + 1)) return i < 0 ? i + n : (i >= n ? i - n : i);
+    return wrap_repeat(i, n);
+}
+// one axis of a tap: the two texel indices and the weight pair
+struct Axis {
+    int i0, i1;
+    float a, ia;
+};
+VXD Axis make_axis(int n, float s) {
+    Axis x;
+    const float u = s * (float)n - 0.5f, fu = floorf(u);
+    x.a = u - fu; x.ia = 1.0f - x.a;
+    x.i0 = wrap_near(cvt_floor(fu), n);
+    x.i1 = x.i0 + 1 == n ? 0 : x.i0 + 1;
+    return x;
+}
+VXD Tap join_axes(const Axis& x, const Axis& y, int w) {
+    Tap t;
+    t.a = x.a; t.ia = x.ia; t.b = y.a; t.ib = y.ia;
+    t.o00 = y.i0 * w + x.i0; t.o10 = y.i0 * w + x.i1; t.o01 = y.i1 * w + x.i0; t.o11 = y.i1 * w + x.i1;
+    return t;
+}
+VXD Tap make_tap(int w, int h, f2 uv) { return join_axes(make_axis(w, uv.x), make_axis(h, uv.y), w); }
+VXD int nearest_offset(int w, int h, f2 uv) {
+    return wrap_near(cvt_floor(uv.y * (float)h), h) * w + wrap_near(cvt_floor(uv.x * (float)w), w);
+}
+VXD float bl(const Tap& t, float t00, float t10, float t01, float t11) {
+    const float top = t00 * t.ia + t10 * t.a;
+    const float bot = t01 * t.ia + t11 * t.a;
+    return top * t.ib + bot * t.b;
+}
+VXD float2 h2f(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+VXD float hf(uint16_t v) { return __half2float(__ushort_as_half(v)); }
+
+VXD void sample_rgba16(const uint16_t* __restrict__ img, const Tap& t, float* o) {
+    const uint2* p = reinterpret_cast<const uint2*>(img);
+    const uint2 q00 = __ldg(p + t.o00), q10 = __ldg(p + t.o10), q01 = __ldg(p + t.o01), q11 = __ldg(p + t.o11);
+    const float2 a00 = h2f(q00.x), a10 = h2f(q10.x), a01 = h2f(q01.x), a11 = h2f(q11.x);
+    const float2 b00 = h2f(q00.y), b10 = h2f(q10.y), b01 = h2f(q01.y), b11 = h2f(q11.y);
+    o[0] = bl(t, a00.x, a10.x, a01.x, a11.x); o[1] = bl(t, a00.y, a10.y, a01.y, a11.y);
+    o[2] = bl(t, b00.x, b10.x, b01.x, b11.x); o[3] = bl(t, b00.y, b10.y, b01.y, b11.y);
+}
+VXD void sample_rg16(const uint16_t* __restrict__ img, const Tap& t, float* o) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(img);
+    const float2 a00 = h2f(__ldg(p + t.o00)), a10 = h2f(__ldg(p + t.o10)), a01 = h2f(__ldg(p + t.o01)), a11 = h2f(__ldg(p + t.o11));
+    o[0] = bl(t, a00.x, a10.x, a01.x, a11.x); o[1] = bl(t, a00.y, a10.y, a01.y, a11.y);
+}
+VXD float sample_r16(const uint16_t* __restrict__ img, const Tap& t) {
+    return bl(t, hf(__ldg(img + t.o00)), hf(__ldg(img + t.o10)), hf(__ldg(img + t.o01)), hf(__ldg(img + t.o11)));
+}
+// one channel of an RGB16F image
+VXD float sample_rgb16_ch(const uint16_t* __restrict__ img, const Tap& t, int ch) {
+    return bl(t, hf(__ldg(img + 3 * t.o00 + ch)), hf(__ldg(img + 3 * t.o10 + ch)), hf(__ldg(img + 3 * t.o01 + ch)), hf(__ldg(img + 3 * t.o11 + ch)));
+}
+// RG8 through the k / 255 table in shared memory (a float division per texel channel otherwise)
+VXD void sample_rg8(const uint8_t* __restrict__ img, const Tap& t, const float* __restrict__ lut, float* o) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(img);
+    const uint32_t q00 = __ldg(p + t.o00), q10 = __ldg(p + t.o10), q01 = __ldg(p + t.o01), q11 = __ldg(p + t.o11);
+    o[0] = bl(t, lut[q00 & 255], lut[q10 & 255], lut[q01 & 255], lut[q11 & 255]);
+    o[1] = bl(t, lut[q00 >> 8], lut[q10 >> 8], lut[q01 >> 8], lut[q11 >> 8]);
+}
 // GetNormalFromID (TemporalFilter.glsl:111-123) as an index: 0..5 = the face normals, 6 = (1, 1, 1)
 VXD int normal_index(float n) {
     int i = cvt_round(n * 10.0f);
     return i > 5 ? 6 : (i < 0 ? 0 : i);
 }
-VXD bool in_screen_space(f2 v) { return v.x < 1.0f && v.x > 0.0f && v.y < 1.0f && v.y > 0.0f; }
-VXD float sh_to_y(float w) { return gmax(0.0f, 3.544905f * w); }
-VXD int block_at(const GBufIn& g, f2 uv) { return iclamp(cvt_trunc(floorf(att_r8_nearest(g.b, g.w, g.h, uv) * 255.0f)), 0, 127); }
+VXD int normal_at(const GBufIn& g, int o, const float* __restrict__ lut) { return normal_index(lut[__ldg(g.n + o)]); }
+VXD int block_at(const GBufIn& g, int o, const float* __restrict__ lut) { return iclamp(cvt_trunc(floorf(lut[__ldg(g.b + o)] * 255.0f)), 0, 127); }
+
+// k / 255 for k = 0..255 (unorm8 -> float exactly as the samplers define it); blockDim.x == 256
+VXD void fill_unorm_lut(float* lut) {
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+}
+
+#ifndef VX_SVGF_OCC
+#define VX_SVGF_OCC 4   // CTAs per SM the temporal / spatial kernels are compiled for (register cap 64 / 48 / 40 at 4 / 5 / 6)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // TemporalFilter.glsl main() (:133-344)
 struct TemporalArgs {
     float inv_view[16], inv_proj[16], prev_pv[16];
     int width, height, row0, row1, be_useful;
-    SetIn cur, hist;
+    SetIn cur, hist;   // both width x height
     GBufIn g, pg;
     SetOut out;
 };
 
-__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ TemporalArgs a) {
+__global__ void __launch_bounds__(256, VX_SVGF_OCC) svgf_temporal_kernel(const __grid_constant__ TemporalArgs a) {
+    __shared__ float lut[256];
+    fill_unorm_lut(lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
     const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (px >= a.width || py >= a.row1) return;
+    const bool same = a.g.w == a.width && a.g.h == a.height;
     const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
     const f3 origin = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
-    const float BaseDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
+    const Tap ts = make_tap(a.width, a.height, tc);
+    Tap tg = ts;
+    if (!same) tg = make_tap(a.g.w, a.g.h, tc);
+    const int ng = nearest_offset(a.g.w, a.g.h, tc);
+    const float BaseDist = sample_r16(a.g.t, tg);
     const f3 BasePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * BaseDist;
-    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
-    float BaseSH[4], BaseCoCg[2], BaseAO[2], lum[1];
-    att_half_bilinear<4>(a.cur.sh, a.cur.w, a.cur.h, tc, BaseSH);
-    att_half_bilinear<2>(a.cur.cocg, a.cur.w, a.cur.h, tc, BaseCoCg);
-    att_unorm8_bilinear<2>(a.cur.aosky, a.cur.w, a.cur.h, tc, BaseAO);
-    att_half_bilinear<1>(a.cur.x, a.cur.w, a.cur.h, tc, lum);
-    const float BaseLuminosity = lum[0];
-    const int BaseBlock = block_at(a.g, tc);
+    const int BaseNormal = normal_at(a.g, ng, lut);
+    const int BaseBlock = block_at(a.g, ng, lut);
+    float BaseSH[4], BaseCoCg[2], BaseAO[2];
+    sample_rgba16(a.cur.sh, ts, BaseSH);
+    sample_rg16(a.cur.cocg, ts, BaseCoCg);
+    sample_rg8(a.cur.aosky, ts, lut, BaseAO);
+    const float BaseLuminosity = sample_r16(a.cur.x, ts);
     const f4 Proj = mat4_mul(a.prev_pv, F4(BasePos.x, BasePos.y, BasePos.z, 1.0f));
     const f2 Reproj = F2((Proj.x / Proj.w) * 0.5f + 0.5f, (Proj.y / Proj.w) * 0.5f + 0.5f);
 
@@ -102,22 +189,26 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
         const f2 sc = F2(Reproj.x + (ox + 0.0f) * Texel.x, Reproj.y + (oy + 0.0f) * Texel.y);
         const float b = 0.0035f;
         if (!(sc.x < 1.0f - b && sc.x > b && sc.y < 1.0f - b && sc.y > b)) continue;
-        const float PrevDist = att_r16f_bilinear(a.pg.t, a.pg.w, a.pg.h, sc);
+        const Tap hs = make_tap(a.width, a.height, sc);
+        Tap hg = hs;
+        if (!same) hg = make_tap(a.pg.w, a.pg.h, sc);
+        const float PrevDist = sample_r16(a.pg.t, hg);
         const f3 PrevPos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, sc)) * PrevDist;
         const f3 e = F3(fabsf(BasePos.x - PrevPos.x), fabsf(BasePos.y - PrevPos.y), fabsf(BasePos.z - PrevPos.z));
         const float PositionError = dot(e, e);
         if (!(PositionError < Tol && ((PrevDist < 0.0f) == (BaseDist < 0.0f)))) continue;
-        if (DoNormalWeight && normal_index(att_r8_nearest(a.pg.n, a.pg.w, a.pg.h, sc)) != BaseNormal) continue;
-        if (DoBlockWeight && block_at(a.pg, sc) != BaseBlock) continue;
-        float u[3], s[4], c2[2], a2[2];
-        att_half_bilinear<3>(a.hist.x, a.hist.w, a.hist.h, sc, u);
-        att_half_bilinear<4>(a.hist.sh, a.hist.w, a.hist.h, sc, s);
-        att_half_bilinear<2>(a.hist.cocg, a.hist.w, a.hist.h, sc, c2);
-        att_unorm8_bilinear<2>(a.hist.aosky, a.hist.w, a.hist.h, sc, a2);
+        const int np = nearest_offset(a.pg.w, a.pg.h, sc);
+        if (DoNormalWeight && normal_at(a.pg, np, lut) != BaseNormal) continue;
+        if (DoBlockWeight && block_at(a.pg, np, lut) != BaseBlock) continue;
+        float s[4], c2[2], a2[2];
+        sample_rgba16(a.hist.sh, hs, s);
+        sample_rg16(a.hist.cocg, hs, c2);
+        sample_rg8(a.hist.aosky, hs, lut, a2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) SumSH[k] += s[k] * w;
         SumCoCg[0] += c2[0] * w; SumCoCg[1] += c2[1] * w;
-        SumSPP += u[0] * w; SumMoment += u[1] * w; SumLuminosity += u[2] * w;
+        SumSPP += sample_rgb16_ch(a.hist.x, hs, 0) * w; SumMoment += sample_rgb16_ch(a.hist.x, hs, 1) * w;
+        SumLuminosity += sample_rgb16_ch(a.hist.x, hs, 2) * w;
         SumAO[0] += a2[0] * w; SumAO[1] += a2[1] * w;
         TotalWeight += w;
         Successful++;
@@ -165,6 +256,9 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
 
 // ---------------------------------------------------------------------------------------------------------------
 // VarianceEstimate.glsl main() (:75-184).  GetPositionAt(SampleCoord) is only consumed through .w (the sampled distance).
+// The 9 x 9 bilateral pre-filter only runs for pixels with fewer than 12 accumulated frames; a CTA in which some pixel
+// needs it stages its 32 x 8 tile plus a 5-texel apron in shared memory (converted to float once), and every tap
+// is four shared-memory texels away.
 struct VarianceArgs {
     int width, height, row0, row1, do_spatial, aggressive;
     SetIn in;  // temporal set: x = utility RGB16F
@@ -174,77 +268,137 @@ struct VarianceArgs {
 
 // pow(max(dot(n0, n1), 0), 16) over the values a pair of GetNormalFromID normals can produce (0, 1, 3): exact like powf
 VXD float normal_weight16(int n0, int n1) {
-    if (n0 == 6 && n1 == 6) return 43046720.0f;                      // powf(3, 16)
+    if (n0 == 6 && n1 == 6) return 43046720.0f;                         // powf(3, 16)
     if (n0 == 6) return (n1 == 0 || n1 == 2 || n1 == 5) ? 1.0f : 0.0f;  // (1,1,1) . axis = sign of the axis
     if (n1 == 6) return (n0 == 0 || n0 == 2 || n0 == 5) ? 1.0f : 0.0f;
     return n0 == n1 ? 1.0f : 0.0f;
 }
 
+constexpr int VAR_HALO = 5, VAR_TW = 32 + 2 * VAR_HALO, VAR_TH = 8 + 2 * VAR_HALO;
+
 __global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constant__ VarianceArgs a) {
+    __shared__ float lut[256];
+    __shared__ float4 s_sh[VAR_TH * VAR_TW];    // SH
+    __shared__ float4 s_aux[VAR_TH * VAR_TW];   // CoCg.x, CoCg.y, second moment, distance
+    __shared__ uint8_t s_n[VAR_TH * VAR_TW];    // normal index
+    fill_unorm_lut(lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-    if (px >= a.width || py >= a.row1) return;
+    const int x0 = blockIdx.x * 32, y0 = a.row0 + blockIdx.y * 8;
+    const int px = x0 + (warp & 3) * 8 + (lane & 7);
+    const int py = y0 + (warp >> 2) * 4 + (lane >> 3);
+    const bool active = px < a.width && py < a.row1;
+    const bool same = a.g.w == a.in.w && a.g.h == a.in.h;
     const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
-    const float BaseDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
-    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
-    float BaseUt[3], BaseSH[4], BaseCC[2];
-    att_half_bilinear<3>(a.in.x, a.in.w, a.in.h, tc, BaseUt);
-    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, tc, BaseSH);
-    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, tc, BaseCC);
-    const float BaseLum = sh_to_y(BaseSH[3]);
-    const float Frames = BaseUt[0], BaseMoment = BaseUt[1];
-    float oSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, oCC[2] = {BaseCC[0], BaseCC[1]};
+    float BaseDist = 0.0f, BaseLum = 0.0f, Frames = 0.0f, BaseMoment = 0.0f;
+    int BaseNormal = 0;
+    float oSH[4] = {0.0f, 0.0f, 0.0f, 0.0f}, oCC[2] = {0.0f, 0.0f};
+    if (active) {
+        const Tap ts = make_tap(a.in.w, a.in.h, tc);
+        Tap tg = ts;
+        if (!same) tg = make_tap(a.g.w, a.g.h, tc);
+        BaseDist = sample_r16(a.g.t, tg);
+        BaseNormal = normal_at(a.g, nearest_offset(a.g.w, a.g.h, tc), lut);
+        Frames = sample_rgb16_ch(a.in.x, ts, 0);
+        BaseMoment = sample_rgb16_ch(a.in.x, ts, 1);
+        sample_rgba16(a.in.sh, ts, oSH);
+        sample_rg16(a.in.cocg, ts, oCC);
+        BaseLum = sh_to_y(oSH[3]);
+    }
     float Variance = BaseMoment - BaseLum * BaseLum;
-    if (a.do_spatial) {
-        const float THRESH = a.aggressive ? 4.0f + 4.0f + 4.0f : 4.0f + 4.0f;
-        if (Frames < THRESH) {
-            const float ColorPhi = a.aggressive ? 5.0f : 5.0f * 2.0f;
-            const int K = a.aggressive ? 4 : 1;
-            const f2 Texel = F2(1.0f / (float)a.in.w, 1.0f / (float)a.in.h);
-            float TotalWeight = 0.0f, TotalMoment = 0.0f, TotalLum = 0.0f, TotalWeight2 = 0.0f;
-            float TotalSH[4] = {0.0f, 0.0f, 0.0f, 0.0f}, TotalCC[2] = {0.0f, 0.0f};
-#pragma unroll 1
-            for (int x = -K; x <= K; ++x)
-#pragma unroll 1
-                for (int y = -K; y <= K; ++y) {
-                    const f2 sc = F2(tc.x + (float)x * Texel.x, tc.y + (float)y * Texel.y);
-                    if (!in_screen_space(sc)) continue;
-                    const float SampleDist = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, sc);
-                    const int SampleNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, sc));
-                    float ut[3], sh[4], cc[2];
-                    att_half_bilinear<3>(a.in.x, a.in.w, a.in.h, sc, ut);
-                    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, sc, sh);
-                    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, sc, cc);
-                    const float SampleLum = sh_to_y(sh[3]);
-                    const float NormalWeight = normal_weight16(BaseNormal, SampleNormal);
-                    const float ed = expf(-fabsf(SampleDist - BaseDist));
-                    const float DepthWeight = ed * ed;
-                    const float LumWeight = fabsf(SampleLum - BaseLum) / ColorPhi;
-                    float Weight = expf(-LumWeight) * NormalWeight * DepthWeight;
-                    const float Weight_2 = gmax(Weight, 0.0000000015f);
-                    Weight = gmax(Weight, 0.000000015f);
-                    TotalWeight += Weight;
-                    TotalMoment += ut[1] * Weight_2;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) TotalSH[k] += sh[k] * Weight;
-                    TotalCC[0] += cc[0] * Weight; TotalCC[1] += cc[1] * Weight;
-                    TotalLum += SampleLum * Weight_2;
-                    TotalWeight2 += Weight_2;
-                }
-            if (TotalWeight > 0.0f) {
-                TotalMoment /= TotalWeight2;
-                TotalLum /= TotalWeight2;
-                TotalCC[0] /= TotalWeight; TotalCC[1] /= TotalWeight;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) TotalSH[k] /= TotalWeight;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) oSH[k] = TotalSH[k];
-            oCC[0] = TotalCC[0]; oCC[1] = TotalCC[1];
-            Variance = TotalMoment - TotalLum * TotalLum;
-            Variance *= 3.0f;
+    const float THRESH = a.aggressive ? 4.0f + 4.0f + 4.0f : 4.0f + 4.0f;
+    const bool filter = active && a.do_spatial && Frames < THRESH;
+    const bool tiled = same && a.aggressive;   // the apron is sized for the 9 x 9 kernel
+    if (__syncthreads_or(filter) && tiled) {
+        for (int idx = threadIdx.x; idx < VAR_TH * VAR_TW; idx += 256) {
+            const int ty = idx / VAR_TW, tx = idx - ty * VAR_TW;
+            const int o = wrap_repeat(y0 - VAR_HALO + ty, a.in.h) * a.in.w + wrap_repeat(x0 - VAR_HALO + tx, a.in.w);
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(a.in.sh) + o);
+            const float2 s0 = h2f(q.x), s1 = h2f(q.y), c = h2f(__ldg(reinterpret_cast<const uint32_t*>(a.in.cocg) + o));
+            s_sh[idx] = make_float4(s0.x, s0.y, s1.x, s1.y);
+            s_aux[idx] = make_float4(c.x, c.y, hf(__ldg(a.in.x + 3 * o + 1)), hf(__ldg(a.g.t + o)));
+            s_n[idx] = (uint8_t)normal_at(a.g, o, lut);
         }
+        __syncthreads();
+    }
+    if (filter) {
+        const float ColorPhi = a.aggressive ? 5.0f : 5.0f * 2.0f;
+        const int K = a.aggressive ? 4 : 1;
+        const f2 Texel = F2(1.0f / (float)a.in.w, 1.0f / (float)a.in.h);
+        float TotalWeight = 0.0f, TotalMoment = 0.0f, TotalLum = 0.0f, TotalWeight2 = 0.0f;
+        float TotalSH[4] = {0.0f, 0.0f, 0.0f, 0.0f}, TotalCC[2] = {0.0f, 0.0f};
+#pragma unroll 1
+        for (int x = -K; x <= K; ++x) {
+            const float scx = tc.x + (float)x * Texel.x;
+            if (!(scx < 1.0f && scx > 0.0f)) continue;
+            // column set-up of the tap (shared by the 9 taps of this column)
+            const float u = scx * (float)a.in.w - 0.5f, fu = floorf(u);
+            const float wa = u - fu, wia = 1.0f - wa;
+            const int ci = iclamp(cvt_floor(fu) - (x0 - VAR_HALO), 0, VAR_TW - 2);
+            const int cn = iclamp(cvt_floor(scx * (float)a.in.w) - (x0 - VAR_HALO), 0, VAR_TW - 1);
+#pragma unroll 1
+            for (int y = -K; y <= K; ++y) {
+                const float scy = tc.y + (float)y * Texel.y;
+                if (!(scy < 1.0f && scy > 0.0f)) continue;
+                float sh[4], cc[2], SampleMoment, SampleDist;
+                int SampleNormal;
+                if (tiled) {
+                    const float v = scy * (float)a.in.h - 0.5f, fv = floorf(v);
+                    const float wb = v - fv, wib = 1.0f - wb;
+                    const int rj = iclamp(cvt_floor(fv) - (y0 - VAR_HALO), 0, VAR_TH - 2);
+                    const int rn = iclamp(cvt_floor(scy * (float)a.in.h) - (y0 - VAR_HALO), 0, VAR_TH - 1);
+                    const int o = rj * VAR_TW + ci;
+                    const float4 p00 = s_sh[o], p10 = s_sh[o + 1], p01 = s_sh[o + VAR_TW], p11 = s_sh[o + VAR_TW + 1];
+                    const float4 q00 = s_aux[o], q10 = s_aux[o + 1], q01 = s_aux[o + VAR_TW], q11 = s_aux[o + VAR_TW + 1];
+#define VX_BL(c00, c10, c01, c11) (((c00) * wia + (c10) * wa) * wib + ((c01) * wia + (c11) * wa) * wb)
+                    sh[0] = VX_BL(p00.x, p10.x, p01.x, p11.x); sh[1] = VX_BL(p00.y, p10.y, p01.y, p11.y);
+                    sh[2] = VX_BL(p00.z, p10.z, p01.z, p11.z); sh[3] = VX_BL(p00.w, p10.w, p01.w, p11.w);
+                    cc[0] = VX_BL(q00.x, q10.x, q01.x, q11.x); cc[1] = VX_BL(q00.y, q10.y, q01.y, q11.y);
+                    SampleMoment = VX_BL(q00.z, q10.z, q01.z, q11.z); SampleDist = VX_BL(q00.w, q10.w, q01.w, q11.w);
+#undef VX_BL
+                    SampleNormal = s_n[rn * VAR_TW + cn];
+                } else {
+                    const f2 sc = F2(scx, scy);
+                    const Tap ss = make_tap(a.in.w, a.in.h, sc);
+                    Tap sg = ss;
+                    if (!same) sg = make_tap(a.g.w, a.g.h, sc);
+                    SampleDist = sample_r16(a.g.t, sg);
+                    SampleNormal = normal_at(a.g, nearest_offset(a.g.w, a.g.h, sc), lut);
+                    SampleMoment = sample_rgb16_ch(a.in.x, ss, 1);
+                    sample_rgba16(a.in.sh, ss, sh);
+                    sample_rg16(a.in.cocg, ss, cc);
+                }
+                const float SampleLum = sh_to_y(sh[3]);
+                const float NormalWeight = normal_weight16(BaseNormal, SampleNormal);
+                const float ed = expf(-fabsf(SampleDist - BaseDist));
+                const float DepthWeight = ed * ed;
+                const float LumWeight = fabsf(SampleLum - BaseLum) / ColorPhi;
+                float Weight = expf(-LumWeight) * NormalWeight * DepthWeight;
+                const float Weight_2 = gmax(Weight, 0.0000000015f);
+                Weight = gmax(Weight, 0.000000015f);
+                TotalWeight += Weight;
+                TotalMoment += SampleMoment * Weight_2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) TotalSH[k] += sh[k] * Weight;
+                TotalCC[0] += cc[0] * Weight; TotalCC[1] += cc[1] * Weight;
+                TotalLum += SampleLum * Weight_2;
+                TotalWeight2 += Weight_2;
+            }
+        }
+        if (TotalWeight > 0.0f) {
+            TotalMoment /= TotalWeight2;
+            TotalLum /= TotalWeight2;
+            TotalCC[0] /= TotalWeight; TotalCC[1] /= TotalWeight;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) TotalSH[k] /= TotalWeight;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oSH[k] = TotalSH[k];
+        oCC[0] = TotalCC[0]; oCC[1] = TotalCC[1];
+        Variance = TotalMoment - TotalLum * TotalLum;
+        Variance *= 3.0f;
+    }
+    if (!active) return;
+    if (a.do_spatial) {
         Variance *= THRESH / Frames;
 #pragma unroll
         for (int k = 0; k < 4; ++k) oSH[k] = gclamp(oSH[k], -100.0f, 100.0f);
@@ -267,57 +421,71 @@ struct SpatialArgs {
     int width, height, row0, row1;
     int step, large_kernel, do_spatial, aggressive;
     float phi_bias, time_offset, additional_scale;
-    SetIn in;                           // sh, cocg, x = u_VarianceTexture (R16F), aosky = u_AO
-    const uint16_t* __restrict__ temporal_utility;  // u_TemporalMoment RGB16F
-    int tw, th;
+    SetIn in;                           // sh, cocg, x = u_VarianceTexture (R16F), aosky = u_AO; width x height
+    const uint16_t* __restrict__ temporal_utility;  // u_TemporalMoment RGB16F, width x height
     GBufIn g;
     SetOut out;
 };
 
-__global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant__ SpatialArgs a) {
+__global__ void __launch_bounds__(256, VX_SVGF_OCC) svgf_spatial_kernel(const __grid_constant__ SpatialArgs a) {
+    __shared__ float lut[256];
+    fill_unorm_lut(lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
     const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (px >= a.width || py >= a.row1) return;
+    const bool same = a.g.w == a.width && a.g.h == a.height;
     const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
     // GradientNoise (:163-168); Jitter = ivec2(float) has both components equal
     const float cx = ((float)px + 0.5f) + a.time_offset, cy = ((float)py + 0.5f) + a.time_offset;
     const float noise = gfract(52.9829189f * gfract(0.06711056f * cx + 0.00583715f * cy));
     const float jf = (float)cvt_trunc((noise - 0.5f) * ((float)a.step * 0.8f)) * 0.5f;
-    const float BaseDepth = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, tc);
-    const int BaseNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, tc));
+    const Tap ts = make_tap(a.width, a.height, tc);
+    Tap tg = ts;
+    if (!same) tg = make_tap(a.g.w, a.g.h, tc);
+    const float BaseDepth = sample_r16(a.g.t, tg);
+    const int BaseNormal = normal_at(a.g, nearest_offset(a.g.w, a.g.h, tc), lut);
     float BaseSH[4], BaseCC[2], BaseAO[2];
-    att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, tc, BaseSH);
-    att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, tc, BaseCC);
+    sample_rgba16(a.in.sh, ts, BaseSH);
+    sample_rg16(a.in.cocg, ts, BaseCC);
     const float BaseLum = sh_to_y(BaseSH[3]);
-    // GaussianVariance (:98-133)
+    // GaussianVariance (:98-133): 3 x 3 taps at whole-texel offsets, set up per column and per row
     float BaseVariance = 0.0f, VarianceSum = 0.0f, TotalKernel = 0.0f;
+    const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);   // 1 / u_Dimensions == 1 / textureSize(u_SH, 0)
     {
-        const f2 TexelSH = F2(1.0f / (float)a.in.w, 1.0f / (float)a.in.h);
+        Axis gy[3];
+        bool oky[3];
 #pragma unroll
-        for (int x = -1; x <= 1; ++x)
+        for (int y = -1; y <= 1; ++y) {
+            const float scy = tc.y + (float)y * Texel.y;
+            oky[y + 1] = scy < 1.0f && scy > 0.0f;
+            gy[y + 1] = make_axis(a.height, scy);
+        }
+#pragma unroll
+        for (int x = -1; x <= 1; ++x) {
+            const float scx = tc.x + (float)x * Texel.x;
+            if (!(scx < 1.0f && scx > 0.0f)) continue;
+            const Axis gx = make_axis(a.width, scx);
 #pragma unroll
             for (int y = -1; y <= 1; ++y) {
-                const f2 sc = F2(tc.x + (float)x * TexelSH.x, tc.y + (float)y * TexelSH.y);
-                if (!in_screen_space(sc)) continue;
+                if (!oky[y + 1]) continue;
                 const float kx = x == 0 ? 0.60283f : 0.198585f, ky = y == 0 ? 0.60283f : 0.198585f;
                 const float KernelValue = kx * ky;
-                const float V = att_r16f_bilinear(a.in.x, a.in.w, a.in.h, sc);
+                const float V = sample_r16(a.in.x, join_axes(gx, gy[y + 1], a.width));
                 if (x == 0 && y == 0) BaseVariance = V;
                 VarianceSum += V * KernelValue;
                 TotalKernel += KernelValue;
             }
+        }
     }
     const float VarianceEstimate = VarianceSum / gmax(TotalKernel, 0.01f);
-    att_unorm8_bilinear<2>(a.in.aosky, a.in.w, a.in.h, tc, BaseAO);
+    sample_rg8(a.in.aosky, ts, lut, BaseAO);
     float oSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, oCC[2] = {BaseCC[0], BaseCC[1]}, oVar = BaseVariance, oAO[2] = {BaseAO[0], BaseAO[1]};
     if (a.do_spatial) {
         const bool FilterAO = a.step <= 4;
         float TotalSH[4] = {BaseSH[0], BaseSH[1], BaseSH[2], BaseSH[3]}, TotalCC[2] = {BaseCC[0], BaseCC[1]};
         float TotalWeight = 1.0f, TotalVariance = BaseVariance, TotalAO[2] = {BaseAO[0], BaseAO[1]}, TotalAOWeight = 1.0f;
-        float tu[3];
-        att_half_bilinear<3>(a.temporal_utility, a.tw, a.th, tc, tu);
-        const bool Strong = tu[0] <= 8.0f && a.aggressive && a.step <= 8;
+        const bool Strong = sample_rgb16_ch(a.temporal_utility, ts, 0) <= 8.0f && a.aggressive && a.step <= 8;
         float CurveExponent = 0.0f;
         if (VarianceEstimate < 0.01f) CurveExponent = 128.0f;
         else if (VarianceEstimate < 0.025f) CurveExponent = 112.0f;
@@ -332,32 +500,40 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
         float PhiColor = sqrtf(gmax(0.0f, 0.000001f + Tweaked));
         PhiColor /= gmax(a.phi_bias, 0.1f);
         const int K = a.large_kernel ? 2 : 1;
-        const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);
         const float fstep = (float)a.step;
 #pragma unroll 1
-        for (int x = -K; x <= K; ++x)
+        for (int x = -K; x <= K; ++x) {
+            const float scx = tc.x + (((float)x * fstep) * a.additional_scale + jf) * Texel.x;
+            if (!(scx > 0.0f && scx < 1.0f)) continue;
+            const Axis sx = make_axis(a.width, scx);
+            Axis gx = sx;
+            if (!same) gx = make_axis(a.g.w, scx);
+            const int nx = wrap_near(cvt_floor(scx * (float)a.g.w), a.g.w);
 #pragma unroll 1
             for (int y = -K; y <= K; ++y) {
                 if (x == 0 && y == 0) continue;
-                const f2 sc = F2(tc.x + (((float)x * fstep) * a.additional_scale + jf) * Texel.x,
-                                 tc.y + (((float)y * fstep) * a.additional_scale + jf) * Texel.y);
-                if (!in_screen_space(sc)) continue;
-                const float SampleDepth = att_r16f_bilinear(a.g.t, a.g.w, a.g.h, sc);
+                const float scy = tc.y + (((float)y * fstep) * a.additional_scale + jf) * Texel.y;
+                if (!(scy > 0.0f && scy < 1.0f)) continue;
+                const Axis sy = make_axis(a.height, scy);
+                const Tap ss = join_axes(sx, sy, a.width);
+                Tap sg = ss;
+                if (!same) sg = join_axes(gx, make_axis(a.g.h, scy), a.g.w);
+                const float SampleDepth = sample_r16(a.g.t, sg);
                 const float DepthDiff = fabsf(SampleDepth - BaseDepth);
                 // `BaseDepth < 0.0f == DepthDiff < 0.0f` parses as (BaseDepth < 0) == (DepthDiff < 0)
                 if ((BaseDepth < 0.0f) != (DepthDiff < 0.0f)) continue;
-                const int SampleNormal = normal_index(att_r8_nearest(a.g.n, a.g.w, a.g.h, sc));
+                const int SampleNormal = normal_at(a.g, wrap_near(cvt_floor(scy * (float)a.g.h), a.g.h) * a.g.w + nx, lut);
                 float sh[4], cc[2];
-                att_half_bilinear<4>(a.in.sh, a.in.w, a.in.h, sc, sh);
-                att_half_bilinear<2>(a.in.cocg, a.in.w, a.in.h, sc, cc);
+                sample_rgba16(a.in.sh, ss, sh);
+                sample_rg16(a.in.cocg, ss, cc);
                 const float SampleLum = sh_to_y(sh[3]);
-                const float SampleVariance = att_r16f_bilinear(a.in.x, a.in.w, a.in.h, sc);
+                const float SampleVariance = sample_r16(a.in.x, ss);
                 // pow(max(dot, 0), 32) in {0, 1, 3^32}, clamped to [0.001, 1]
                 const float NormalWeight = normal_weight16(BaseNormal, SampleNormal) > 0.0f ? 1.0f : 0.001f;
-                const float LumWeight = fabsf(SampleLum - BaseLum) / PhiColor;
                 const float ed = expf(-gmax(DepthDiff, 0.00001f));
                 const float DepthWeight = gclamp(ed * ed, 0.0001f, 1.0f);
-                float Weight = Strong ? (NormalWeight * DepthWeight) : (expf(-LumWeight) * NormalWeight * DepthWeight);
+                float Weight = NormalWeight * DepthWeight;
+                if (!Strong) Weight = expf(-(fabsf(SampleLum - BaseLum) / PhiColor)) * NormalWeight * DepthWeight;
                 Weight = gclamp(Weight, 0.001f, 1.0f);
                 const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
                 const float XW = ax == 0 ? 1.0f : (ax == 1 ? 2.0f / 3.0f : 1.0f / 6.0f), YW = ay == 0 ? 1.0f : (ay == 1 ? 2.0f / 3.0f : 1.0f / 6.0f);
@@ -371,11 +547,12 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
                 if (a.step <= 6) {  // FilterSky || FilterAO
                     const float AOW = gclamp((XW * YW) * NormalWeight * DepthWeight, 0.000001f, 1.0f);
                     float ao[2];
-                    att_unorm8_bilinear<2>(a.in.aosky, a.in.w, a.in.h, sc, ao);
+                    sample_rg8(a.in.aosky, ss, lut, ao);
                     TotalAO[0] += ao[0] * AOW; TotalAO[1] += ao[1] * AOW;
                     TotalAOWeight += AOW;
                 }
             }
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) oSH[k] = gclamp(TotalSH[k] / TotalWeight, -100.0f, 100.0f);
         oCC[0] = gclamp(TotalCC[0] / TotalWeight, -10.0f, 100.0f); oCC[1] = gclamp(TotalCC[1] / TotalWeight, -10.0f, 100.0f);
@@ -457,6 +634,7 @@ int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
     TemporalArgs a;
     int rc;
     if ((rc = set_in(c, fn, p.in_set, 2, true, &a.cur))) return rc;
+    if (a.cur.w != p.width || a.cur.h != p.height) return vxrt_fail(VXRT_E_STATE, "%s: image set is %dx%d, the pass runs at %dx%d", fn, a.cur.w, a.cur.h, p.width, p.height);
     if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
     // first frame: no history yet.  The engine's FBOs start out zero-filled, so do these.
     if (!c->att[p.history_set].ptr || c->att[p.history_set].width != p.width || c->att[p.history_set].height != p.height) {
@@ -472,6 +650,7 @@ int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
         }
     }
     if ((rc = set_in(c, fn, p.history_set, 6, true, &a.hist))) return rc;
+    if (a.hist.w != p.width || a.hist.h != p.height) return vxrt_fail(VXRT_E_STATE, "%s: image set is %dx%d, the pass runs at %dx%d", fn, a.hist.w, a.hist.h, p.width, p.height);
     if ((rc = gbuf_in(c, fn, VXRT_ATT_PREV_INITIAL_T, VXRT_ATT_PREV_INITIAL_NORMAL, VXRT_ATT_PREV_INITIAL_BLOCK, &a.pg))) return rc;
     if ((rc = set_out(c, fn, p.out_set, p.width, p.height, true, &a.out))) return rc;
     for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
@@ -497,6 +676,7 @@ int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p) {
     int rc;
     if (!is_temporal_set(p.in_set)) return vxrt_fail(VXRT_E_INVALID, "%s: in_set must be a temporal set", fn);
     if ((rc = set_in(c, fn, p.in_set, 6, false, &a.in))) return rc;
+    if (a.in.w != p.width || a.in.h != p.height) return vxrt_fail(VXRT_E_STATE, "%s: image set is %dx%d, the pass runs at %dx%d", fn, a.in.w, a.in.h, p.width, p.height);
     if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
     if ((rc = set_out(c, fn, VXRT_ATT_SVGF_VARIANCE, p.width, p.height, false, &a.out))) return rc;
     a.width = p.width; a.height = p.height; a.do_spatial = p.do_spatial; a.aggressive = p.aggressive_disocclusion;
@@ -519,11 +699,13 @@ int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p) {
     SetIn ao, tmp;
     int rc;
     if ((rc = set_in(c, fn, p.in_set, 2, false, &a.in))) return rc;
+    if (a.in.w != p.width || a.in.h != p.height) return vxrt_fail(VXRT_E_STATE, "%s: image set is %dx%d, the pass runs at %dx%d", fn, a.in.w, a.in.h, p.width, p.height);
     if ((rc = set_in(c, fn, p.ao_set, is_temporal_set(p.ao_set) ? 6 : 2, true, &ao))) return rc;
     if ((rc = set_in(c, fn, p.temporal_set, 6, false, &tmp))) return rc;
     if (ao.w != a.in.w || ao.h != a.in.h) return vxrt_fail(VXRT_E_STATE, "%s: ao_set and in_set differ in size", fn);
     a.in.aosky = ao.aosky;
-    a.temporal_utility = tmp.x; a.tw = tmp.w; a.th = tmp.h;
+    if (tmp.w != a.in.w || tmp.h != a.in.h) return vxrt_fail(VXRT_E_STATE, "%s: temporal_set and in_set differ in size", fn);
+    a.temporal_utility = tmp.x;
     if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
     if ((rc = set_out(c, fn, p.out_set, p.width, p.height, true, &a.out))) return rc;
     a.width = p.width; a.height = p.height;
