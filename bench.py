@@ -524,6 +524,35 @@ def main():
                 "stages": stages, "stages_warm": warm, "bytes_per_pixel": SvgfChain.STAGE_BYTES, "l2": "flushed before each chain",
                 "note": "ms_per_chain: frames 2..7 after a cold start (9 x 9 variance pre-filter on every pixel); warm: frames 14..19"}
 
+    # ---- sun-shadow denoiser: temporal + spatial filter of the soft-shadow trace, per-stage CUDA events ----
+    shadow_dn = None
+    if world_size == 1 and "shadow" in cfg.passes and not args.no_svgf:
+        from voxeltracing_b200.pipeline import ShadowDenoiser
+        den = ShadowDenoiser(ctx, W, H, select=False)
+        den_ev = []
+        for k in range(12):
+            cam = camera_for(wl, 2000 + k) if wl["camera"] != "rooms" else camera_for(wl, 0)
+            fr.render(cam, 2000 + k)
+            prep = den.prepare(cam, k)
+            evs = {}
+
+            def hook(name, where, evs=evs):
+                e = ev(); e.record(stream)
+                evs.setdefault(name, []).append(e)
+            flush_buf.zero_()
+            den.submit(prep, hook=hook)
+            ctx.end_frame()
+            den_ev.append(evs)
+        torch.cuda.synchronize()
+        stages = {}
+        for key in ("temporal", "filter"):
+            ms_stage = float(np.mean([evs[key][0].elapsed_time(evs[key][1]) for evs in den_ev[4:]]))
+            by = ShadowDenoiser.STAGE_BYTES[key] * W * H
+            stages[key] = {"ms_per_launch": ms_stage, "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms_stage * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": by / (ms_stage * 1e-3) / 1e9 / measured_peaks()[0]}
+        shadow_dn = {"ms_per_frame": sum(st["ms_per_launch"] for st in stages.values()), "resolution": [W, H], "stages": stages,
+                     "bytes_per_pixel": ShadowDenoiser.STAGE_BYTES, "l2": "flushed before each frame's two launches"}
+
     # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera,
     # every output attachment read back to pinned host memory, inside the timed region ----
     if world_size > 1:
@@ -639,6 +668,8 @@ def main():
                             "l2": "flushed before each regeneration", "launches_per_regeneration": 2}
         if svgf:
             line["svgf"] = svgf
+        if shadow_dn:
+            line["shadow_denoiser"] = shadow_dn
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_arm(blocks, wl, inputs)
             v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)

@@ -148,7 +148,11 @@ typedef enum vxrt_attachment {
     VXRT_ATT_PREV_INITIAL_T = 38,      /* previous frame's primary G-buffer (the engine ping-pongs InitialTraceFBO_1/_2, */
     VXRT_ATT_PREV_INITIAL_NORMAL = 39, /*   Core/Pipeline.cpp:2046-2048); filled by vxrt_cuda_svgf_end_frame */
     VXRT_ATT_PREV_INITIAL_BLOCK = 40,
-    VXRT_ATT_COUNT = 41
+    /* sun-shadow denoiser (Core/Pipeline.cpp:1201-1202): a temporal set is two consecutive ids */
+    VXRT_ATT_SHADOW_TEMPORAL_A = 41, /* ShadowTemporalFBO_1: +0 shadow R8, +1 accumulated frames R16F */
+    VXRT_ATT_SHADOW_TEMPORAL_B = 43, /* ShadowTemporalFBO_2 */
+    VXRT_ATT_SHADOW_FILTERED = 45,   /* ShadowFiltered: R8 */
+    VXRT_ATT_COUNT = 46
 } vxrt_attachment;
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
@@ -388,6 +392,39 @@ typedef struct vxrt_svgf_spatial_params {    /* Pipeline.cpp:2592-2700 */
 int vxrt_cuda_svgf_spatial(vxrt_ctx* ctx, const vxrt_svgf_spatial_params* p);
 /* end of frame: this frame's primary G-buffer (INITIAL_T / NORMAL / BLOCK) becomes VXRT_ATT_PREV_INITIAL_* */
 int vxrt_cuda_svgf_end_frame(vxrt_ctx* ctx);
+
+/* same hand-over under its general name: every temporal filter (SVGF, shadow) reprojects into VXRT_ATT_PREV_INITIAL_* */
+int vxrt_cuda_end_frame(vxrt_ctx* ctx);
+
+/* ---- sun-shadow denoiser: Core/Shaders/ShadowTemporalFilter.glsl and ShadowFilter.glsl, dispatched at
+ * Core/Pipeline.cpp:2947-3044 when SoftShadows (and DenoiseSunShadows) are on ----
+ * temporal: consumes SHADOW + SHADOW_TRANSVERSAL of vxrt_cuda_shadow_trace, INITIAL_T / INITIAL_NORMAL, PREV_INITIAL_T and
+ * the previous frame's temporal set (ping-ponged by frame parity like ShadowTemporalFBO_1 / _2, Pipeline.cpp:1862-1863;
+ * zero-filled on first use); writes out_set.  The raw trace may be smaller than the temporal images
+ * (ShadowTraceResolution <= ShadowSupersampleRes, Pipeline.cpp:1691).                                                  */
+typedef struct vxrt_shadow_temporal_params {   /* Pipeline.cpp:2949-3005 */
+    float inv_view[16], inv_projection[16];
+    float prev_view[16], prev_projection[16];  /* u_PrevView, u_PrevProjection */
+    int32_t width, height;                     /* size of the temporal images */
+    int32_t history_set;                       /* VXRT_ATT_SHADOW_TEMPORAL_A / _B: previous frame's */
+    int32_t out_set;                           /* the other one */
+    int32_t shadow_temporal;                   /* u_ShadowTemporal (true at the only call site) */
+    vxrt_tile tile;
+} vxrt_shadow_temporal_params;
+int vxrt_cuda_shadow_temporal(vxrt_ctx* ctx, const vxrt_shadow_temporal_params* p);
+
+typedef struct vxrt_shadow_filter_params {     /* Pipeline.cpp:3009-3044 */
+    float inv_view[16], inv_projection[16];
+    int32_t width, height;                     /* size of VXRT_ATT_SHADOW_FILTERED */
+    int32_t in_set;                            /* this frame's temporal set (shadow + frame count) */
+    float filter_scale;                        /* u_ShadowFilterScale (1.0, Pipeline.cpp:137) */
+    vxrt_tile tile;
+} vxrt_shadow_filter_params;                   /* writes VXRT_ATT_SHADOW_FILTERED */
+int vxrt_cuda_shadow_filter(vxrt_ctx* ctx, const vxrt_shadow_filter_params* p);
+/* Which R8 image vxrt_cuda_reflection_trace and vxrt_cuda_shade_direct sample as the shadow texture — the engine binds
+ * `SoftShadows ? (DenoiseSunShadows ? ShadowFiltered : ShadowTemporalFBO) : ShadowRawTrace` (Pipeline.cpp:3231, 3838):
+ * VXRT_ATT_SHADOW (default), VXRT_ATT_SHADOW_TEMPORAL_A / _B or VXRT_ATT_SHADOW_FILTERED.  Sticky until changed.     */
+int vxrt_cuda_select_shadow(vxrt_ctx* ctx, int32_t attachment);
 
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {

@@ -252,6 +252,31 @@ def svgf_spatial(p: "abi.SvgfSpatialParams", prev: dict, ao: np.ndarray, tempora
     return out
 
 
+def shadow_temporal(p: "abi.ShadowTemporalParams", raw: dict, hist: dict, g: dict, prev_t: np.ndarray, fn=None) -> dict:
+    """ShadowTemporalFilter.glsl.  raw: {"shadow": u8 (sh, sw), "transversal": f16} of the shadow trace; hist: previous temporal
+    set {"shadow": u8 (h, w), "frames": f16}; g: {"t": f16, "normal": u8}; prev_t: previous frame's hit distance."""
+    out = {"shadow": np.zeros((p.height, p.width), np.uint8), "frames": np.zeros((p.height, p.width), np.float16)}
+    sh, sw = raw["shadow"].shape
+    gh, gw = g["t"].shape
+    assert hist["shadow"].shape == (p.height, p.width) and prev_t.shape == (gh, gw)
+    (fn or lib().vxo_shadow_temporal)(C.byref(p), _p(np.ascontiguousarray(raw["shadow"])), _p(np.ascontiguousarray(raw["transversal"])), sw, sh,
+                                     _p(np.ascontiguousarray(hist["shadow"])), _p(np.ascontiguousarray(hist["frames"])), _p(np.ascontiguousarray(g["t"])),
+                                     _p(np.ascontiguousarray(g["normal"])), _p(np.ascontiguousarray(prev_t)), gw, gh, _p(out["shadow"]), _p(out["frames"]))
+    return out
+
+
+def shadow_filter(p: "abi.ShadowFilterParams", temporal: dict, raw_transversal: np.ndarray, g: dict, fn=None) -> np.ndarray:
+    """ShadowFilter.glsl.  temporal: this frame's temporal set; returns the filtered R8 image (p.height, p.width)."""
+    out = np.zeros((p.height, p.width), np.uint8)
+    ih, iw = temporal["shadow"].shape
+    sh, sw = raw_transversal.shape
+    gh, gw = g["t"].shape
+    (fn or lib().vxo_shadow_filter)(C.byref(p), _p(np.ascontiguousarray(temporal["shadow"])), _p(np.ascontiguousarray(temporal["frames"])), iw, ih,
+                                   _p(np.ascontiguousarray(raw_transversal)), sw, sh, _p(np.ascontiguousarray(g["t"])), _p(np.ascontiguousarray(g["normal"])),
+                                   gw, gh, _p(out))
+    return out
+
+
 class OracleScene:
     """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
 

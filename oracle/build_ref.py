@@ -40,6 +40,9 @@ SHADERS = {
     "SVGFTemporal": ("SVGF/TemporalFilter.glsl", "fragment"),
     "SVGFVariance": ("SVGF/VarianceEstimate.glsl", "fragment"),
     "SVGFSpatial": ("SVGF/SpatialFilter.glsl", "fragment"),
+    # sun-shadow denoiser
+    "ShadowTemporal": ("ShadowTemporalFilter.glsl", "fragment"),
+    "ShadowFilter": ("ShadowFilter.glsl", "fragment"),
     # the colour pass composites sky / clouds / denoised GI (out of scope); only its Cook-Torrance
     # functions are compiled: they are cut out of the file by name, unmodified
     "ColorPassDirect": ("ColorPassFrag.glsl", "extract"),

@@ -48,6 +48,12 @@ thread_local uvec3 gl_GlobalInvocationID;
 #undef sqr   /* a function in SpatialFilter.glsl, a macro in ReflectionTraceFrag.glsl (one translation unit here) */
 #include "SVGFSpatial.cpp"
 #endif
+#ifdef VXREF_HAVE_ShadowTemporal
+#include "ShadowTemporal.cpp"
+#endif
+#ifdef VXREF_HAVE_ShadowFilter
+#include "ShadowFilter.cpp"
+#endif
 #ifdef VXREF_HAVE_ColorPassDirect
 #include "ColorPassDirect.cpp"
 #endif
@@ -97,6 +103,12 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_SVGFSpatial
     m |= 4096;
+#endif
+#ifdef VXREF_HAVE_ShadowTemporal
+    m |= 8192;
+#endif
+#ifdef VXREF_HAVE_ShadowFilter
+    m |= 16384;
 #endif
 #ifdef VXREF_HAVE_RaycastDetect
     m |= 512;   /* World::RaycastDetect, host C++ lifted from Core/World.cpp (vxref_raycast_detect, generated unit) */
@@ -586,6 +598,68 @@ extern "C" void vxref_svgf_spatial(const vxrt_svgf_spatial_params* p, const vxre
             for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
             out->x[i] = vxo::float_to_half(S::o_Variance);
             for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOAndSkylighting[c]);
+        }
+}
+#endif
+
+/* ---- sun-shadow denoiser (Core/Pipeline.cpp:2947-3044).  raw = ShadowRawTrace (R8 shadow + R16F transversals, sw x sh),
+ * hist / out = a ShadowTemporalFBO (R8 shadow + R16F frame count, width x height), G-buffer gw x gh ---- */
+#ifdef VXREF_HAVE_ShadowTemporal
+extern "C" void vxref_shadow_temporal(const vxrt_shadow_temporal_params* p, const uint8_t* raw_shadow, const uint16_t* raw_transversal, int sw, int sh,
+                                      const uint8_t* hist_shadow, const uint16_t* hist_frames, const uint16_t* g_t, const uint8_t* g_normal,
+                                      const uint16_t* prev_t, int gw, int gh, uint8_t* out_shadow, uint16_t* out_frames) {
+    namespace S = shader_ShadowTemporal;
+    const int W = p->width, H = p->height;
+    auto fs = svgf_u8(raw_shadow, (size_t)sw * sh), ftr = svgf_half(raw_transversal, (size_t)sw * sh);
+    auto hs = svgf_u8(hist_shadow, (size_t)W * H), hf = svgf_half(hist_frames, (size_t)W * H);
+    auto ft = svgf_half(g_t, (size_t)gw * gh), fn = svgf_u8(g_normal, (size_t)gw * gh), pt = svgf_half(prev_t, (size_t)gw * gh);
+    bind2d(S::u_CurrentColorTexture, fs.data(), sw, sh, 1, true); bind2d(S::u_ShadowTransversals, ftr.data(), sw, sh, 1, true);
+    bind2d(S::u_DenoisedTransversals, ftr.data(), sw, sh, 1, true);   /* declared, never sampled */
+    bind2d(S::u_PreviousColorTexture, hs.data(), W, H, 1, true); bind2d(S::u_FrameCount, hf.data(), W, H, 1, true);
+    bind2d(S::u_CurrentPositionTexture, ft.data(), gw, gh, 1, true); bind2d(S::u_PreviousFramePositionTexture, pt.data(), gw, gh, 1, true);
+    bind2d(S::u_NormalTexture, fn.data(), gw, gh, 1, false);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_PrevView.load(p->prev_view); S::u_PrevProjection.load(p->prev_projection);
+    S::u_ShadowTemporal = p->shadow_temporal != 0; S::u_ShouldFilterShadows = true;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam; S::v_RayDirection = vec3(0.0f, 0.0f, 1.0f);
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            out_shadow[i] = vxo::float_to_unorm8(S::o_Color[0]);
+            out_frames[i] = vxo::float_to_half(S::o_Frames);
+        }
+}
+#endif
+
+#ifdef VXREF_HAVE_ShadowFilter
+extern "C" void vxref_shadow_filter(const vxrt_shadow_filter_params* p, const uint8_t* in_shadow, const uint16_t* in_frames, int iw, int ih,
+                                    const uint16_t* raw_transversal, int sw, int sh, const uint16_t* g_t, const uint8_t* g_normal, int gw, int gh,
+                                    uint8_t* out_shadow) {
+    namespace S = shader_ShadowFilter;
+    const int W = p->width, H = p->height;
+    auto fs = svgf_u8(in_shadow, (size_t)iw * ih), ff = svgf_half(in_frames, (size_t)iw * ih), ftr = svgf_half(raw_transversal, (size_t)sw * sh);
+    auto ft = svgf_half(g_t, (size_t)gw * gh), fn = svgf_u8(g_normal, (size_t)gw * gh);
+    bind2d(S::u_InputTexture, fs.data(), iw, ih, 1, true); bind2d(S::u_FrameCount, ff.data(), iw, ih, 1, true);
+    bind2d(S::u_IntersectionTransversals, ftr.data(), sw, sh, 1, true);
+    bind2d(S::u_PositionTexture, ft.data(), gw, gh, 1, true); bind2d(S::u_NormalTexture, fn.data(), gw, gh, 1, false);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_ShadowFilterScale = p->filter_scale;
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::shader_reset(); S::shader_main();
+            out_shadow[(size_t)py * W + px] = vxo::float_to_unorm8(S::o_Color);
         }
 }
 #endif

@@ -26,6 +26,8 @@ ATT_REFL_COLOR, ATT_REFL_HITDIST, ATT_REFL_EMISSIVE = 15, 16, 17
 # SVGF image sets: +0 SH, +1 CoCg, +2 utility (temporal) / variance, +3 AO/sky
 ATT_SVGF_TEMPORAL_A, ATT_SVGF_TEMPORAL_B, ATT_SVGF_VARIANCE, ATT_SVGF_DENOISE_A, ATT_SVGF_DENOISE_B = 18, 22, 26, 30, 34
 ATT_PREV_INITIAL_T, ATT_PREV_INITIAL_NORMAL, ATT_PREV_INITIAL_BLOCK = 38, 39, 40
+# shadow denoiser: temporal sets are (shadow R8, accumulated frames R16F)
+ATT_SHADOW_TEMPORAL_A, ATT_SHADOW_TEMPORAL_B, ATT_SHADOW_FILTERED = 41, 43, 45
 
 TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
@@ -125,6 +127,17 @@ class SvgfSpatialParams(C.Structure):
                 ("color_phi_bias", C.c_float), ("time", C.c_float), ("resolution_scale", C.c_float), ("tile", Tile)]
 
 
+class ShadowTemporalParams(C.Structure):
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("prev_view", C.c_float * 16),
+                ("prev_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32), ("history_set", C.c_int32),
+                ("out_set", C.c_int32), ("shadow_temporal", C.c_int32), ("tile", Tile)]
+
+
+class ShadowFilterParams(C.Structure):
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+                ("in_set", C.c_int32), ("filter_scale", C.c_float), ("tile", Tile)]
+
+
 class RayHit(C.Structure):
     _fields_ = [("t", C.c_float), ("normal", C.c_float * 3), ("end", C.c_float * 3), ("block", C.c_int32),
                 ("intersection", C.c_int32), ("iterations", C.c_int32)]
@@ -192,6 +205,10 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_svgf_variance": (C.c_int, [vp, P(SvgfVarianceParams)]),
         "vxrt_cuda_svgf_spatial": (C.c_int, [vp, P(SvgfSpatialParams)]),
         "vxrt_cuda_svgf_end_frame": (C.c_int, [vp]),
+        "vxrt_cuda_end_frame": (C.c_int, [vp]),
+        "vxrt_cuda_shadow_temporal": (C.c_int, [vp, P(ShadowTemporalParams)]),
+        "vxrt_cuda_shadow_filter": (C.c_int, [vp, P(ShadowFilterParams)]),
+        "vxrt_cuda_select_shadow": (C.c_int, [vp, i32]),
         "vxrt_cuda_write_attachment": (C.c_int, [vp, i32, i32, i32, i32, vp]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),

@@ -535,7 +535,7 @@ int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
     if (rc) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_INVT, "vxrt_cuda_initial_trace"))) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_ALBEDO, "vxrt_cuda_generate_gbuffer"))) return rc;
-    if ((rc = require_att(c, __func__, VXRT_ATT_SHADOW, "vxrt_cuda_shadow_trace"))) return rc;
+    if ((rc = require_att(c, __func__, c->shadow_source, c->shadow_source == VXRT_ATT_SHADOW ? "vxrt_cuda_shadow_trace" : "the shadow denoiser"))) return rc;
     return vxrt_launch_shade_direct(c, *p);
 }
 int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
@@ -573,6 +573,29 @@ int vxrt_cuda_svgf_end_frame(vxrt_ctx* c) {
     REQUIRE_CTX(c);
     return vxrt_launch_svgf_end_frame(c);
 }
+int vxrt_cuda_end_frame(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    return vxrt_launch_svgf_end_frame(c);
+}
+int vxrt_cuda_select_shadow(vxrt_ctx* c, int32_t id) {
+    REQUIRE_CTX(c);
+    if (id != VXRT_ATT_SHADOW && id != VXRT_ATT_SHADOW_TEMPORAL_A && id != VXRT_ATT_SHADOW_TEMPORAL_B && id != VXRT_ATT_SHADOW_FILTERED)
+        return vxrt_fail(VXRT_E_INVALID, "select_shadow: attachment %d is not a shadow image", id);
+    c->shadow_source = id;
+    return VXRT_OK;
+}
+int vxrt_cuda_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_shadow_temporal(c, *p);
+}
+int vxrt_cuda_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_shadow_filter(c, *p);
+}
 int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs a world and a distance field");
@@ -581,7 +604,7 @@ int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
     if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_T, "vxrt_cuda_initial_trace"))) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_NORMAL, "vxrt_cuda_generate_gbuffer"))) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_GI_SH, "vxrt_cuda_diffuse_trace"))) return rc;
-    if ((rc = require_att(c, __func__, VXRT_ATT_SHADOW, "vxrt_cuda_shadow_trace"))) return rc;
+    if ((rc = require_att(c, __func__, c->shadow_source, c->shadow_source == VXRT_ATT_SHADOW ? "vxrt_cuda_shadow_trace" : "the shadow denoiser"))) return rc;
     if ((rc = require_textures(c, __func__, true))) return rc;
     if (!c->d_blue_noise) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs vxrt_cuda_set_blue_noise");
     if (!c->sky.data) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs vxrt_cuda_set_skymap");

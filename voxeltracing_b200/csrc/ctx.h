@@ -89,6 +89,7 @@ struct vxrt_ctx {
     size_t ray_cap = 0;
 
     Attachment att[VXRT_ATT_COUNT];
+    int shadow_source = VXRT_ATT_SHADOW;  // the image the reflection / colour passes read as the shadow texture (vxrt_cuda_select_shadow)
     // asynchronous read-back (vxrt_cuda_read_attachment_async): copies run on their own stream, ordered against
     // the passes by one event pair per attachment
     cudaStream_t copy_stream = nullptr;
@@ -147,6 +148,8 @@ int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p);
 int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p);
 int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p);
 int vxrt_launch_svgf_end_frame(vxrt_ctx* c);
+int vxrt_launch_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params& p);
+int vxrt_launch_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params& p);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);
 // host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)

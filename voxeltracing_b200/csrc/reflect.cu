@@ -221,7 +221,7 @@ int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
     const Attachment& gs = c->att[VXRT_ATT_GI_SH];
     a.gi_sh = (const uint16_t*)gs.ptr; a.gi_cocg = (const uint16_t*)c->att[VXRT_ATT_GI_COCG].ptr; a.gi_aosky = (const uint8_t*)c->att[VXRT_ATT_GI_AOSKY].ptr;
     a.iw = gs.width; a.ih = gs.height;
-    const Attachment& sh = c->att[VXRT_ATT_SHADOW];
+    const Attachment& sh = c->att[c->shadow_source];
     a.shadow = (const uint8_t*)sh.ptr; a.sw = sh.width; a.sh = sh.height;
     for (int k = 0; k < 4; ++k) a.tex[k] = c->tex[k];
     a.sky = c->sky;

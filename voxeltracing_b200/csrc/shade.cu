@@ -206,7 +206,7 @@ int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p) {
     a.albedo = (const uint16_t*)ga.ptr; a.normal = (const uint16_t*)c->att[VXRT_ATT_GBUF_NORMAL].ptr;
     a.pbr = (const uint8_t*)c->att[VXRT_ATT_GBUF_PBR].ptr; a.texao = (const uint8_t*)c->att[VXRT_ATT_GBUF_TEXAO].ptr;
     a.mw = ga.width; a.mh = ga.height;
-    const Attachment& sh = c->att[VXRT_ATT_SHADOW];
+    const Attachment& sh = c->att[c->shadow_source];
     a.shadow = (const uint8_t*)sh.ptr; a.sw = sh.width; a.sh = sh.height;
     a.direct = (uint16_t*)c->att[VXRT_ATT_DIRECT].ptr;
     if (a.row1 <= a.row0) return VXRT_OK;

@@ -42,6 +42,9 @@ _ATT_DTYPES = {
     abi.ATT_PREV_INITIAL_NORMAL: (np.uint8, 1),
     abi.ATT_PREV_INITIAL_BLOCK: (np.uint8, 1),
 }
+_ATT_DTYPES.update({abi.ATT_SHADOW_TEMPORAL_A: (np.uint8, 1), abi.ATT_SHADOW_TEMPORAL_A + 1: (np.float16, 1),
+                    abi.ATT_SHADOW_TEMPORAL_B: (np.uint8, 1), abi.ATT_SHADOW_TEMPORAL_B + 1: (np.float16, 1),
+                    abi.ATT_SHADOW_FILTERED: (np.uint8, 1)})
 # SVGF image sets (four consecutive ids): SH, CoCg, utility RGB16F (temporal sets) / variance R16F, AO + sky
 for _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_B):
     _ATT_DTYPES.update({_s: (np.float16, 4), _s + 1: (np.float16, 2),
@@ -249,6 +252,20 @@ class Context:
 
     def svgf_end_frame(self):
         self._check(self._lib.vxrt_cuda_svgf_end_frame(self._h))
+
+    def end_frame(self):
+        self._check(self._lib.vxrt_cuda_end_frame(self._h))
+
+    # -- sun-shadow denoiser (Core/Pipeline.cpp:2947-3044) --
+    def shadow_temporal(self, params: "abi.ShadowTemporalParams"):
+        self._check(self._lib.vxrt_cuda_shadow_temporal(self._h, C.byref(params)))
+
+    def shadow_filter(self, params: "abi.ShadowFilterParams"):
+        self._check(self._lib.vxrt_cuda_shadow_filter(self._h, C.byref(params)))
+
+    def select_shadow(self, att: int):
+        """The image the reflection / colour passes sample as the shadow texture (raw trace by default)."""
+        self._check(self._lib.vxrt_cuda_select_shadow(self._h, att))
 
     def read_set(self, first: int, with_ao: bool = True) -> dict:
         d = {"sh": self.read_attachment(first), "cocg": self.read_attachment(first + 1), "x": self.read_attachment(first + 2)}

@@ -282,3 +282,46 @@ class SvgfChain:
 
     def run(self, cam: host_api.Camera, frame: int, time: float | None = None, tile=(0, 0), hook=None):
         self.submit(self.prepare(cam, frame, time, tile), hook)
+
+
+class ShadowDenoiser:
+    """The sun-shadow denoiser in the order of Core/Pipeline.cpp:2947-3044: temporal filter (temporal sets ping-ponged by
+    frame parity, :1862-1863), then the spatial filter; `select=True` makes the result the shadow texture of the reflection
+    and colour passes, as the engine binds it (:3231, :3838).  Consumes `primary` and `shadow` of the same frame."""
+
+    STAGE_BYTES = {"temporal": 16, "filter": 9}   # bytes read + written per pixel when each image is touched once
+
+    def __init__(self, ctx: Context, width: int, height: int, filter_scale: float = 1.0, select: bool = True):
+        self.ctx, self.width, self.height, self.filter_scale, self.select = ctx, width, height, filter_scale, select
+        self.prev_cam = None
+
+    def prepare(self, cam: host_api.Camera, frame: int, tile=(0, 0)):
+        lib = self.ctx._lib
+        prev = self.prev_cam or cam
+        self.prev_cam = cam
+        hist, out = (abi.ATT_SHADOW_TEMPORAL_B, abi.ATT_SHADOW_TEMPORAL_A) if frame % 2 == 0 else (abi.ATT_SHADOW_TEMPORAL_A, abi.ATT_SHADOW_TEMPORAL_B)
+        tp = abi.ShadowTemporalParams()
+        _fill(tp.inv_view, cam.inv_view); _fill(tp.inv_projection, cam.inv_projection)
+        _fill(tp.prev_view, prev.view); _fill(tp.prev_projection, prev.projection)
+        tp.width, tp.height, tp.history_set, tp.out_set, tp.shadow_temporal = self.width, self.height, hist, out, 1
+        tp.tile.row0, tp.tile.rows = tile
+        fp = abi.ShadowFilterParams()
+        _fill(fp.inv_view, cam.inv_view); _fill(fp.inv_projection, cam.inv_projection)
+        fp.width, fp.height, fp.in_set, fp.filter_scale = self.width, self.height, out, self.filter_scale
+        fp.tile.row0, fp.tile.rows = tile
+        return [("temporal", lib.vxrt_cuda_shadow_temporal, tp), ("filter", lib.vxrt_cuda_shadow_filter, fp)]
+
+    def submit(self, prepared, hook=None):
+        import ctypes as C
+
+        for name, fn, params in prepared:
+            if hook:
+                hook(name, "begin")
+            self.ctx._check(fn(self.ctx._h, C.byref(params)))
+            if hook:
+                hook(name, "end")
+        if self.select:
+            self.ctx.select_shadow(abi.ATT_SHADOW_FILTERED)
+
+    def run(self, cam: host_api.Camera, frame: int, tile=(0, 0), hook=None):
+        self.submit(self.prepare(cam, frame, tile), hook)
