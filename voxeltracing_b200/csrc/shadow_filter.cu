@@ -25,6 +25,12 @@ struct ShadowTemporalArgs {
     uint16_t* __restrict__ out_frames;
 };
 
+// pow(x, n) for the small integer exponents the shaders use, by multiplication (<= 3 ulp for n = 48, below the error of the
+// general powf; the reference's own pow() is implementation defined)
+VXD float pow3(float x) { return (x * x) * x; }
+VXD float pow7(float x) { const float x2 = x * x, x4 = x2 * x2; return (x4 * x2) * x; }
+VXD float pow48(float x) { const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8; return (x16 * x16) * x16; }
+
 VXD f3 position_at(const float* inv_view, const float* inv_proj, f3 origin, f2 uv, float dist) {
     return origin + normalize(ray_direction_at(inv_view, inv_proj, uv)) * dist;
 }
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
                     if (SampleNormal == BaseNormal && fabsf(SampleDepth - Dist) < 1.0f) {
                         const float Sample = sample_r8(a.raw.p, make_tap(a.raw.w, a.raw.h, sc), lut);
                         float WeightAt = gclamp(1.0f - gclamp(fabsf(Sample - Base) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
-                        WeightAt = gclamp(powf(WeightAt, 7.0f), 0.000001f, 1.0f);
+                        WeightAt = gclamp(pow7(WeightAt), 0.000001f, 1.0f);
                         Total += Sample * WeightAt;
                         Weight += WeightAt;
                     }
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
             BlendFactor *= VRF;
             float DepthRejection = 1.0f;
             if (d > 0.4f) {
-                DepthRejection = powf(expf(-d), 48.0f);
+                DepthRejection = pow48(expf(-d));
                 BlendFactor *= gclamp(DepthRejection, 0.0f, 1.0f);
             }
             oColor = gmix(CurrentColor, PrevColor, gclamp(BlendFactor, 0.0f, 0.97f));
@@ -193,14 +199,14 @@ __global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constan
                 const float SampleDepth = sample_r16(a.g_t.p, sg);
                 const int SampleNormal = normal_index(lut[__ldg(a.g_n.p + wrap_near(cvt_floor(scy * (float)a.g_n.h), a.g_n.h) * a.g_n.w + nx)]);
                 const float ed = expf(-(fabsf(CenterDist - SampleDepth)));
-                const float DepthWeight = powf(ed, 3.0f);
+                const float DepthWeight = pow3(ed);
                 // pow(max(dot, 1e-9), 32): 1e-288 underflows to 0, 1, or powf(3, 32)
                 const float nd = normal_dot(CenterNormal, SampleNormal);
                 const float NormalWeight = nd <= 0.0f ? 0.0f : (nd == 1.0f ? 1.0f : 1853020153315328.0f);
                 const float ShadowAt = sample_r8(a.in.p, si, lut);
                 const float LuminanceError = gclamp(1.0f - gclamp(fabsf(ShadowAt - CenterShadow) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
                 float Weight = 1.0f;
-                Weight *= gclamp(powf(LuminanceError, LumaExponent), 0.0f, 1.0f);
+                Weight *= LuminanceError == 1.0f ? 1.0f : gclamp(powf(LuminanceError, LumaExponent), 0.0f, 1.0f);   // pow(1, y) == 1 exactly
                 Weight *= DepthWeight;
                 Weight *= NormalWeight;
                 Weight = gclamp(Weight, 0.000000001f, 1.0f);
