@@ -426,6 +426,39 @@ int vxrt_cuda_shadow_filter(vxrt_ctx* ctx, const vxrt_shadow_filter_params* p);
  * VXRT_ATT_SHADOW (default), VXRT_ATT_SHADOW_TEMPORAL_A / _B or VXRT_ATT_SHADOW_FILTERED.  Sticky until changed.     */
 int vxrt_cuda_select_shadow(vxrt_ctx* ctx, int32_t attachment);
 
+/* ---- world producers: the grid is produced in device memory instead of on the host + vxrt_cuda_upload_world.
+ * Each of them leaves the context as after upload_world (distance field invalid). ---- */
+
+/* VoxelRT::GenerateWorld (Core/WorldGenerator.cpp:208-313, called from Core/Pipeline.cpp:1276) without structures
+ * (gen_structures = false; trees / cacti / cobblestone patches are drawn from rand() and a random_device-seeded
+ * mt19937 in column order and are not reproducible in the reference itself).  One FastNoise simplex-fractal height per
+ * column (frequency 0.00385, 6 octaves, lacunarity 2, gain 0.5, :237-239), one simplex biome value (frequency 0.01 at
+ * x/2, z/2, :253-256), columns filled like SetVerticalBlocks (:49-88).  The permutation tables are FastNoise::SetSeed's
+ * (std::mt19937_64), built on the host.  Heights and biomes are bit-identical to FastNoise compiled without contraction. */
+typedef struct vxrt_worldgen_params {
+    int32_t gen_type;                 /* 1: plains (:230-298); 0: flat world of height 50, all biome 1 (:301-312) */
+    int32_t noise_seed, biome_seed;   /* the reference draws them as rand() % 50000 (:217-218) */
+    int32_t grass_id, dirt_id, stone_id, sand_id;   /* BlockDatabase::GetBlockID of Grass / Dirt / Stone / Sand (:224-227) */
+} vxrt_worldgen_params;
+int vxrt_cuda_generate_world(vxrt_ctx* ctx, const vxrt_worldgen_params* p);
+
+/* MCWorldImporter::ImportWorld (Core/NBT/Importer.cpp:85-166, called from Core/Pipeline.cpp:1294): the host side
+ * (vxh_mca_*, voxeltracing_b200/host) inflates the Anvil region files and hands over every chunk section as it is stored —
+ * 4096 block ids in YZX order, 2048 bytes of 4-bit data values (low nibble first) and its world-space origin — and this
+ * scatters them into the grid: a voxel is written when its data value is 0, its id maps (lut[id], GetIDFromMCID,
+ * Core/BlockDatabase.cpp:599-612) to a non-zero block and (position - import_origin + (nx/2, 0, nz/2)) lies inside the
+ * grid (WriteVoxel, Importer.cpp:67-83).  All arrays are HOST memory.  clear_first = 1 zero-fills the grid first, as
+ * ImportWorld does; 0 adds to the existing world.  has_data[i] = 0: section i carries no Data array (values read as 0). */
+int vxrt_cuda_import_sections(vxrt_ctx* ctx, const uint8_t* block_ids /* n*4096 */, const uint8_t* data_nibbles /* n*2048 */,
+                              const uint8_t* has_data /* n */, const int32_t* section_origins /* 3*n */, int32_t n,
+                              const int32_t import_origin[3], const uint8_t lut[256], int32_t clear_first);
+
+/* LightLocations of LoadWorld (Core/WorldFileHandler.cpp:53-69, called from Core/Pipeline.cpp:1254): the voxels whose block has an emissive texture
+ * (BlockDataSSBO emissive row >= 0, vxrt_cuda_set_block_data), in ascending order of x + y*nx + z*nx*ny like the
+ * reference's scan.  xyz_out: HOST memory for 3*capacity ints (may be NULL when capacity = 0); *count receives the
+ * number found, of which min(count, capacity) are written. */
+int vxrt_cuda_collect_lights(vxrt_ctx* ctx, int32_t* xyz_out, int32_t capacity, int32_t* count);
+
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {
     uint64_t rays;        /* VoxelTraversalDF invocations */

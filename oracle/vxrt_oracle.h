@@ -128,6 +128,19 @@ typedef struct vxo_reflection_inputs {
 void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_params* p, const vxo_reflection_inputs* in,
                           uint16_t* color_h4, uint16_t* hitdist_h, uint8_t* emissive_u8, vxrt_trace_stats* stats);
 
+/* ---- world producers (vxrt_oracle_world.cpp) ---- */
+/* FastNoise::GetNoise(x, y) for the Simplex (fractal = 0) / SimplexFractal FBM (fractal = 1) types; xy = 2*n floats */
+void vxo_fastnoise_2d(int32_t seed, int32_t fractal, float frequency, int32_t octaves, const float* xy, int32_t n, float* out);
+/* VoxelRT::GenerateWorld without structures (Core/WorldGenerator.cpp:208-313) */
+void vxo_generate_world(uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, const vxrt_worldgen_params* p);
+/* MCWorldImporter::ImportRegionFile voxel loop + WriteVoxel (Core/NBT/Importer.cpp:67-83, 112-141) over inflated sections */
+void vxo_import_sections(uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, const uint8_t* ids, const uint8_t* nibbles,
+                         const uint8_t* has_data, const int32_t* origins, int32_t n, const int32_t* import_origin, const uint8_t* lut,
+                         int32_t clear_first);
+/* LightLocations of LoadWorld (Core/WorldFileHandler.cpp:53-69); returns the number found, writes min(found, capacity) */
+int32_t vxo_collect_lights(const uint8_t* blocks, int32_t nx, int32_t ny, int32_t nz, const int32_t* table6x128, int32_t* xyz_out,
+                           int32_t capacity);
+
 /* format helpers */
 uint16_t vxo_float_to_half(float f);
 float vxo_half_to_float(uint16_t h);

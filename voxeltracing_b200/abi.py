@@ -143,6 +143,12 @@ class RayHit(C.Structure):
                 ("intersection", C.c_int32), ("iterations", C.c_int32)]
 
 
+class WorldGenParams(C.Structure):
+    """vxrt_worldgen_params"""
+    _fields_ = [("gen_type", C.c_int32), ("noise_seed", C.c_int32), ("biome_seed", C.c_int32), ("grass_id", C.c_int32),
+                ("dirt_id", C.c_int32), ("stone_id", C.c_int32), ("sand_id", C.c_int32)]
+
+
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("iterations", C.c_uint64), ("dda_steps", C.c_uint64), ("hits", C.c_uint64)]
 
@@ -219,6 +225,9 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_shadow_trace": (C.c_int, [vp, P(ShadowParams)]),
         "vxrt_cuda_trace_rays": (C.c_int, [vp, vp, vp, i32, i32, vp]),
         "vxrt_cuda_raycast_detect": (C.c_int, [vp, vp, vp, i32, vp]),
+        "vxrt_cuda_generate_world": (C.c_int, [vp, P(WorldGenParams)]),
+        "vxrt_cuda_import_sections": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, i32]),
+        "vxrt_cuda_collect_lights": (C.c_int, [vp, vp, i32, P(i32)]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
         "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
         "vxrt_cuda_gather_peak": (C.c_int, [vp, i32, P(C.c_double)]),
@@ -265,6 +274,18 @@ def load_host() -> C.CDLL:
         "vxh_blockdb_face_props": (None, [vp, C.c_char_p, vp]),
         "vxh_blockdb_minecraft_lut": (None, [vp, vp]),
         "vxh_gen_texture_array": (None, [u32, i32, i32, i32, vp]),
+        "vxh_mca_open": (vp, []),
+        "vxh_mca_free": (None, [vp]),
+        "vxh_mca_add_region_file": (i32, [vp, C.c_char_p]),
+        "vxh_mca_add_region_dir": (i32, [vp, C.c_char_p]),
+        "vxh_mca_section_count": (i32, [vp]),
+        "vxh_mca_chunk_count": (i32, [vp]),
+        "vxh_mca_palette_section_count": (i32, [vp]),
+        "vxh_mca_bad_chunk_count": (i32, [vp]),
+        "vxh_mca_block_ids": (vp, [vp]),
+        "vxh_mca_data_nibbles": (vp, [vp]),
+        "vxh_mca_has_data": (vp, [vp]),
+        "vxh_mca_section_origins": (vp, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -93,7 +93,7 @@ def build_host(force: bool = False) -> Path:
     stamp = _digest(deps, " ".join(flags))
     if not force and _up_to_date(HOST_LIB, stamp):
         return HOST_LIB
-    _run(["g++"] + flags + ["-o", str(HOST_LIB)] + [str(s) for s in srcs])
+    _run(["g++"] + flags + ["-o", str(HOST_LIB)] + [str(s) for s in srcs] + ["-lz"])  # zlib: region-file chunks (vxrt_mca.cpp)
     _write_stamp(HOST_LIB, stamp)
     return HOST_LIB
 
@@ -118,6 +118,9 @@ def build_ref(force: bool = False):
     if not script.exists() or not Path(os.environ.get("VXRT_REFERENCE", "/root/reference")).exists():
         return None
     _run([sys.executable, str(script)] + (["--force"] if force else []))
+    world = ROOT / "oracle" / "build_ref_world.py"   # world producers: FastNoise, enkiMI, WorldGenerator.cpp, Importer.cpp
+    if world.exists():
+        _run([sys.executable, str(world)] + (["--force"] if force else []))
     return ROOT / "oracle" / "_ref" / "libvxrt_ref.so"
 
 

@@ -632,6 +632,83 @@ int vxrt_cuda_stats_read(vxrt_ctx* c, vxrt_trace_stats* out, int32_t reset) {
     }
     return VXRT_OK;
 }
+// ---- world producers (world.cu) ----
+static int ensure_staging(vxrt_ctx* c, size_t need) {
+    if (need > c->ray_cap) {
+        if (c->d_ray_buf) VX_CUDA(cudaFree(c->d_ray_buf));
+        c->d_ray_buf = nullptr; c->ray_cap = 0;
+        VX_CUDA(cudaMalloc(&c->d_ray_buf, need));
+        c->ray_cap = need;
+    }
+    return VXRT_OK;
+}
+
+int vxrt_cuda_generate_world(vxrt_ctx* c, const vxrt_worldgen_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    const int ids[4] = {p->grass_id, p->dirt_id, p->stone_id, p->sand_id};
+    for (int k = 0; k < 4; ++k)
+        if (ids[k] < 0 || ids[k] > 255) return vxrt_fail(VXRT_E_INVALID, "generate_world: block id %d out of range", ids[k]);
+    int rc = vxrt_launch_generate_world(c, *p);
+    if (rc) return rc;
+    c->world_uploaded = true;
+    c->df_valid = false;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_import_sections(vxrt_ctx* c, const uint8_t* block_ids, const uint8_t* data_nibbles, const uint8_t* has_data,
+                              const int32_t* section_origins, int32_t n, const int32_t import_origin[3], const uint8_t lut[256],
+                              int32_t clear_first) {
+    REQUIRE_CTX(c);
+    if (n < 0) return vxrt_fail(VXRT_E_INVALID, "import_sections: n < 0");
+    REQUIRE_PTR(import_origin); REQUIRE_PTR(lut);
+    if (!clear_first && !c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "import_sections without clear_first needs a world");
+    if (clear_first) VX_CUDA(cudaMemsetAsync(c->d_blocks, 0, c->nvox, c->stream));
+    if (n > 0) {
+        REQUIRE_PTR(block_ids); REQUIRE_PTR(data_nibbles); REQUIRE_PTR(has_data); REQUIRE_PTR(section_origins);
+        const size_t b_ids = (size_t)n * 4096, b_nib = (size_t)n * 2048, b_org = ((size_t)n * 3 * sizeof(int32_t) + 255) / 256 * 256;
+        int rc = ensure_staging(c, b_ids + b_nib + b_org + (size_t)n);
+        if (rc) return rc;
+        uint8_t* base = (uint8_t*)c->d_ray_buf;
+        uint8_t* d_ids = base; uint8_t* d_nib = base + b_ids; int32_t* d_org = (int32_t*)(base + b_ids + b_nib); uint8_t* d_has = base + b_ids + b_nib + b_org;
+        VX_CUDA(cudaMemcpyAsync(d_ids, block_ids, b_ids, cudaMemcpyHostToDevice, c->stream));
+        VX_CUDA(cudaMemcpyAsync(d_nib, data_nibbles, b_nib, cudaMemcpyHostToDevice, c->stream));
+        VX_CUDA(cudaMemcpyAsync(d_org, section_origins, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        VX_CUDA(cudaMemcpyAsync(d_has, has_data, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        rc = vxrt_launch_import_sections(c, d_ids, d_nib, d_has, d_org, n, import_origin, lut);
+        if (rc) return rc;
+        VX_CUDA(cudaStreamSynchronize(c->stream));  // host buffers are only borrowed for the call
+    }
+    c->world_uploaded = true;
+    c->df_valid = false;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_collect_lights(vxrt_ctx* c, int32_t* xyz_out, int32_t capacity, int32_t* count) {
+    REQUIRE_CTX(c); REQUIRE_PTR(count);
+    if (capacity < 0) return vxrt_fail(VXRT_E_INVALID, "collect_lights: capacity < 0");
+    if (capacity > 0) REQUIRE_PTR(xyz_out);
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "collect_lights before a world exists");
+    if (!c->d_block_data) return vxrt_fail(VXRT_E_STATE, "collect_lights needs the block table (vxrt_cuda_set_block_data)");
+    const int chunks = vxrt_lights_chunks(c);
+    const size_t b_counts = ((size_t)(chunks + 1) * sizeof(unsigned) + 255) / 256 * 256;
+    int rc = ensure_staging(c, b_counts + (size_t)capacity * 3 * sizeof(int32_t));
+    if (rc) return rc;
+    unsigned* d_counts = (unsigned*)c->d_ray_buf;
+    int32_t* d_out = (int32_t*)((uint8_t*)c->d_ray_buf + b_counts);
+    rc = vxrt_launch_collect_lights(c, d_counts, d_out, capacity);
+    if (rc) return rc;
+    unsigned total = 0;
+    VX_CUDA(cudaMemcpyAsync(&total, d_counts + chunks, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    *count = (int32_t)total;
+    const size_t wr = (size_t)(total < (unsigned)capacity ? total : (unsigned)capacity);
+    if (wr) {
+        VX_CUDA(cudaMemcpyAsync(xyz_out, d_out, wr * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return VXRT_OK;
+}
+
 int vxrt_cuda_gather_peak(vxrt_ctx* c, int32_t rounds, double* sectors_per_second) {
     REQUIRE_CTX(c); REQUIRE_PTR(sectors_per_second);
     if (rounds < 1 || rounds > (1 << 16)) return vxrt_fail(VXRT_E_INVALID, "gather_peak: rounds out of range");

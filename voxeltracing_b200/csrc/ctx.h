@@ -150,6 +150,11 @@ int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p);
 int vxrt_launch_svgf_end_frame(vxrt_ctx* c);
 int vxrt_launch_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params& p);
 int vxrt_launch_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params& p);
+int vxrt_launch_generate_world(vxrt_ctx* c, const vxrt_worldgen_params& p);
+int vxrt_launch_import_sections(vxrt_ctx* c, const uint8_t* d_ids, const uint8_t* d_nibbles, const uint8_t* d_has_data,
+                                const int32_t* d_origins, int n, const int32_t origin[3], const uint8_t lut[256]);
+int vxrt_lights_chunks(const vxrt_ctx* c);
+int vxrt_launch_collect_lights(vxrt_ctx* c, unsigned* d_counts, int32_t* d_out, int capacity);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);
 // host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)

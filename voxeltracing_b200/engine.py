@@ -346,6 +346,31 @@ class Context:
         self._check(self._lib.vxrt_cuda_raycast_detect(self._h, _p(o), _p(d), len(o), _p(out)))
         return out
 
+    # -- world producers --
+    def generate_world(self, gen_type: int, noise_seed: int, biome_seed: int, grass: int = 1, dirt: int = 2, stone: int = 3, sand: int = 5):
+        """VoxelRT::GenerateWorld without structures, in device memory (Core/WorldGenerator.cpp:208-313)."""
+        p = abi.WorldGenParams(int(gen_type), int(noise_seed), int(biome_seed), int(grass), int(dirt), int(stone), int(sand))
+        self._check(self._lib.vxrt_cuda_generate_world(self._h, p))
+
+    def import_sections(self, sections, import_origin, lut, clear_first: bool = True):
+        """MCWorldImporter::ImportWorld over the chunk sections of host_api.RegionSections (Core/NBT/Importer.cpp:85-166)."""
+        ids = np.ascontiguousarray(sections.block_ids, dtype=np.uint8)
+        nib = np.ascontiguousarray(sections.data_nibbles, dtype=np.uint8)
+        has = np.ascontiguousarray(sections.has_data, dtype=np.uint8)
+        org = np.ascontiguousarray(sections.origins, dtype=np.int32)
+        o = np.ascontiguousarray(import_origin, dtype=np.int32).reshape(3)
+        l = np.ascontiguousarray(lut, dtype=np.uint8).reshape(256)
+        self._check(self._lib.vxrt_cuda_import_sections(self._h, _p(ids), _p(nib), _p(has), _p(org), len(has), _p(o), _p(l), int(bool(clear_first))))
+
+    def collect_lights(self, capacity: int = 1 << 20) -> np.ndarray:
+        """LightLocations of LoadWorld (Core/WorldFileHandler.cpp:53-69): int32 (n,3) voxel coordinates in scan order."""
+        out = np.zeros((max(int(capacity), 1), 3), dtype=np.int32)
+        n = C.c_int32(0)
+        self._check(self._lib.vxrt_cuda_collect_lights(self._h, _p(out), int(capacity), C.byref(n)))
+        if n.value > capacity:
+            return self.collect_lights(n.value)
+        return out[: n.value].copy()
+
     # -- statistics --
     def stats_enable(self, on: bool):
         self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))

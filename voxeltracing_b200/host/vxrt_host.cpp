@@ -469,11 +469,13 @@ void vxh_blockdb_face_props(const vxh_blockdb* db, const char* name, int32_t* o)
         for (int k = 0; k < 3; ++k) o[1 + g * 3 + k] = id ? vxh_blockdb_texture(db, k, id, faces[g]) : -1;
 }
 void vxh_blockdb_minecraft_lut(const vxh_blockdb* db, uint8_t* out256) {
-    memset(out256, 0, 256);
+    // unlisted ids -> GetBlockID("INVALID_BLOCK") (BlockDatabase.cpp:605-608); id 0 -> 0 (:601-603)
+    memset(out256, (uint8_t)vxh_blockdb_block_id(db, "INVALID_BLOCK"), 256);
     for (const BlockRec& b : db->blocks) {
         if (!rec_by_id(db, b.id)) continue;
         for (int mc : b.mc_ids) out256[(uint8_t)mc] = (uint8_t)b.id;
     }
+    out256[0] = 0;
 }
 
 void vxh_gen_texture_array(uint32_t seed, int32_t kind, int32_t layers, int32_t size, uint8_t* rgba) {

@@ -60,8 +60,26 @@ int32_t vxh_blockdb_texture(const vxh_blockdb* db, int32_t kind, int32_t block_i
 void vxh_blockdb_table(const vxh_blockdb* db, int32_t* out6x128);
 /* u_GrassBlockProps / u_CactusBlockProps layout (Core/Pipeline.cpp:2166-2186): {id, top a/n/p, front a/n/p, bottom a/n/p} */
 void vxh_blockdb_face_props(const vxh_blockdb* db, const char* name, int32_t* out10);
-/* MC_ID lookup table (Core/BlockDatabase.cpp:93-103): out256[mc_id] = block id or 0 */
+/* BlockDatabase::GetIDFromMCID for every 8-bit Minecraft id (Core/BlockDatabase.cpp:93-103, 599-612): out256[0] = 0,
+ * out256[mc_id] = the block that lists mc_id, or the id of "INVALID_BLOCK" for ids no block lists */
 void vxh_blockdb_minecraft_lut(const vxh_blockdb* db, uint8_t* out256);
+
+/* ---- Minecraft Anvil region reader: host half of MCWorldImporter::ImportWorld (Core/NBT/Importer.cpp:85-166);
+ * see vxrt_mca.cpp.  A vxh_mca accumulates chunk sections in the layout vxrt_cuda_import_sections takes. ---- */
+typedef struct vxh_mca vxh_mca;
+vxh_mca* vxh_mca_open(void);
+void vxh_mca_free(vxh_mca* m);
+/* number of sections added, -1 if the file / directory cannot be opened, -2 on a short read */
+int32_t vxh_mca_add_region_file(vxh_mca* m, const char* path);
+int32_t vxh_mca_add_region_dir(vxh_mca* m, const char* dir);   /* every *.mca of the directory (Importer.cpp:152-159) */
+int32_t vxh_mca_section_count(const vxh_mca* m);
+int32_t vxh_mca_chunk_count(const vxh_mca* m);
+int32_t vxh_mca_palette_section_count(const vxh_mca* m);       /* 1.13+ palette sections met and skipped */
+int32_t vxh_mca_bad_chunk_count(const vxh_mca* m);             /* chunks whose stream does not inflate */
+const uint8_t* vxh_mca_block_ids(const vxh_mca* m);            /* n * 4096, YZX */
+const uint8_t* vxh_mca_data_nibbles(const vxh_mca* m);         /* n * 2048, low nibble first (zeros where has_data = 0) */
+const uint8_t* vxh_mca_has_data(const vxh_mca* m);             /* n */
+const int32_t* vxh_mca_section_origins(const vxh_mca* m);      /* 3 * n: chunk x * 16, section Y * 16, chunk z * 16 */
 
 /* deterministic synthetic 'block textures' (the reference's PNGs do not travel to the GPU box):
  * layers*size*size RGBA8, kind-appropriate content (albedo colours, tangent-space normals,

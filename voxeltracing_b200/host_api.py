@@ -154,6 +154,39 @@ class BlockDatabase:
         return o
 
 
+class RegionSections:
+    """Chunk sections of Minecraft Anvil region files, inflated on the host (vxrt_mca.cpp): the input of
+    Context.import_sections.  block_ids (n,4096) YZX, data_nibbles (n,2048), has_data (n,), origins (n,3)."""
+
+    def __init__(self, path):
+        lib = abi.load_host()
+        h = lib.vxh_mca_open()
+        try:
+            path = Path(path)
+            rc = lib.vxh_mca_add_region_dir(h, str(path).encode()) if path.is_dir() else lib.vxh_mca_add_region_file(h, str(path).encode())
+            if rc < 0:
+                raise OSError(f"could not read region data at {path} (rc {rc})")
+            n = lib.vxh_mca_section_count(h)
+            self.chunks = lib.vxh_mca_chunk_count(h)
+            self.palette_sections = lib.vxh_mca_palette_section_count(h)
+            self.bad_chunks = lib.vxh_mca_bad_chunk_count(h)
+
+            def view(ptr, shape, dtype):
+                if n == 0:
+                    return np.zeros(shape, dtype=dtype)
+                nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).reshape(shape).copy()
+            self.block_ids = view(lib.vxh_mca_block_ids(h), (n, 4096), np.uint8)
+            self.data_nibbles = view(lib.vxh_mca_data_nibbles(h), (n, 2048), np.uint8)
+            self.has_data = view(lib.vxh_mca_has_data(h), (n,), np.uint8)
+            self.origins = view(lib.vxh_mca_section_origins(h), (n, 3), np.int32)
+        finally:
+            lib.vxh_mca_free(h)
+
+    def __len__(self):
+        return len(self.has_data)
+
+
 def gen_texture_array(kind: int, layers: int, size: int = 512, seed: int = 7) -> np.ndarray:
     """Deterministic synthetic block textures [layers, size, size, 4] uint8 (the reference's PNGs do not
     travel to the GPU box; with the reference mounted, load the PNGs named by BlockDatabase.layer_paths)."""
