@@ -282,6 +282,67 @@ def run_reference_arm(args, wl, rank):
 # our arm
 # --------------------------------------------------------------------------------------------------
 
+def world_producers_block(local_rank, stream, flush_buf, ev, peak):
+    """World producers on their own context: the terrain generator (writes the whole grid: N algorithmic
+    bytes), the scatter of a batch of chunk sections (reads 6,148 B per section, writes up to 4,096) and the light scan
+    (reads N); CUDA events on the stream, L2 flushed before every launch.  The section batch is synthetic (seeded)."""
+    from types import SimpleNamespace
+
+    import torch
+
+    from voxeltracing_b200 import engine
+    c = engine.Context(local_rank)
+    c.set_stream(stream.cuda_stream)
+    nvox = c.nvox
+    rng = np.random.default_rng(9)
+    n_sec = 2544   # the section count of the engine's 'Test MC Worlds/Medival'
+    ids = np.where(rng.random((n_sec, 4096)) < 0.002, 12, rng.integers(0, 2, (n_sec, 4096)) * 3).astype(np.uint8)   # air, stone, 0.2 % lamps
+    org = np.stack([rng.integers(-12, 12, n_sec) * 16, rng.integers(0, 8, n_sec) * 16, rng.integers(-12, 12, n_sec) * 16], axis=1).astype(np.int32)
+    sec = SimpleNamespace(block_ids=ids, data_nibbles=np.zeros((n_sec, 2048), np.uint8), has_data=np.ones(n_sec, np.uint8), origins=org)
+    lut = np.arange(256, dtype=np.uint8)
+    table = np.full((6, 128), -1, dtype=np.int32)
+    table[3, 12] = 0
+    c.set_block_data(table)
+
+    def timed(fn, reps):
+        pairs = []
+        for _ in range(reps):
+            flush_buf.zero_()
+            a, b = ev(), ev()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            pairs.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in pairs])) * 1e3
+
+    gen_us = timed(lambda: c.generate_world(1, 4242, 999), 20)
+    t0 = time.perf_counter()
+    c.import_sections(sec, (0, 0, 0), lut)     # host arrays -> staging -> scatter, synchronous like ImportWorld
+    imp_ms = (time.perf_counter() - t0) * 1e3
+    c.generate_world(1, 4242, 999)
+    c.import_sections(sec, (0, 0, 0), lut, clear_first=False)
+    lights = c.collect_lights()
+    flush_buf.zero_()
+    a, b = ev(), ev()
+    a.record(stream)
+    t0 = time.perf_counter()
+    lights = c.collect_lights(capacity=len(lights))
+    lights_ms = (time.perf_counter() - t0) * 1e3
+    b.record(stream)
+    torch.cuda.synchronize()
+    lights_dev_us = a.elapsed_time(b) * 1e3
+    c.close()
+    return {"generate_world": {"us_per_world": gen_us, "algorithmic_bytes": nvox, "achieved_gbs": nvox / (gen_us * 1e-6) / 1e9,
+                               "frac_of_hbm_peak": nvox / (gen_us * 1e-6) / 1e9 / peak, "launches": 1},
+            "import_sections": {"ms_end_to_end": imp_ms, "sections": n_sec, "h2d_bytes": int(ids.nbytes + sec.data_nibbles.nbytes + org.nbytes + n_sec),
+                                "note": "wall clock around the ABI call: pageable host arrays -> device staging -> scatter kernel, synchronous"},
+            "collect_lights": {"ms_end_to_end": lights_ms, "us_on_device": lights_dev_us, "lights": int(len(lights)), "algorithmic_bytes": nvox,
+                               "achieved_gbs": nvox / (lights_dev_us * 1e-6) / 1e9, "launches": 3,
+                               "note": "count + scan + write kernels and the read-back of the list; the grid is read twice (second pass from L2)"},
+            "l2": "flushed before each generate_world launch"}
+
+
 def emit(line: dict):
     """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, which prints its version
     banner to stdout) writes to fd 1 has been redirected to stderr by quiet_stdout()."""
@@ -670,6 +731,8 @@ def main():
             line["svgf"] = svgf
         if shadow_dn:
             line["shadow_denoiser"] = shadow_dn
+        if world_size == 1 and not args.no_svgf:
+            line["world_producers"] = world_producers_block(local_rank, stream, flush_buf, ev, peak)
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_arm(blocks, wl, inputs)
             v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)

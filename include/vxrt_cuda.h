@@ -454,7 +454,7 @@ int vxrt_cuda_import_sections(vxrt_ctx* ctx, const uint8_t* block_ids /* n*4096 
                               const int32_t import_origin[3], const uint8_t lut[256], int32_t clear_first);
 
 /* LightLocations of LoadWorld (Core/WorldFileHandler.cpp:53-69, called from Core/Pipeline.cpp:1254): the voxels whose block has an emissive texture
- * (BlockDataSSBO emissive row >= 0, vxrt_cuda_set_block_data), in ascending order of x + y*nx + z*nx*ny like the
+ * (BlockDataSSBO emissive row >= 0, vxrt_cuda_set_block_data; -1 everywhere until it is set), in ascending order of x + y*nx + z*nx*ny like the
  * reference's scan.  xyz_out: HOST memory for 3*capacity ints (may be NULL when capacity = 0); *count receives the
  * number found, of which min(count, capacity) are written. */
 int vxrt_cuda_collect_lights(vxrt_ctx* ctx, int32_t* xyz_out, int32_t capacity, int32_t* count);

@@ -688,7 +688,6 @@ int vxrt_cuda_collect_lights(vxrt_ctx* c, int32_t* xyz_out, int32_t capacity, in
     if (capacity < 0) return vxrt_fail(VXRT_E_INVALID, "collect_lights: capacity < 0");
     if (capacity > 0) REQUIRE_PTR(xyz_out);
     if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "collect_lights before a world exists");
-    if (!c->d_block_data) return vxrt_fail(VXRT_E_STATE, "collect_lights needs the block table (vxrt_cuda_set_block_data)");
     const int chunks = vxrt_lights_chunks(c);
     const size_t b_counts = ((size_t)(chunks + 1) * sizeof(unsigned) + 255) / 256 * 256;
     int rc = ensure_staging(c, b_counts + (size_t)capacity * 3 * sizeof(int32_t));

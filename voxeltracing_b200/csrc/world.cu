@@ -66,17 +66,6 @@ __device__ float simplex2(const NoiseTables& tb, unsigned offset, float x, float
     return 70.0f * (n0 + n1 + n2);
 }
 
-// SingleSimplexFractalFBM (:1191-1208)
-__device__ float simplex_fbm2(const NoiseTables& tb, float x, float y, int octaves, float lacunarity, float gain, float bounding) {
-    float sum = simplex2(tb, tb.perm[0], x, y), amp = 1.0f;
-    for (int i = 1; i < octaves; ++i) {
-        x *= lacunarity; y *= lacunarity;
-        amp *= gain;
-        sum += simplex2(tb, tb.perm[i], x, y) * amp;
-    }
-    return sum * bounding;
-}
-
 struct WorldGenArgs {
     uint8_t* blocks;
     int nx, ny, nz;
@@ -87,13 +76,24 @@ struct WorldGenArgs {
     NoiseTables height_tab, biome_tab;
 };
 
-constexpr int WG_THREADS = 128;
-constexpr int WG_ROWS = 32;  // y rows per CTA
+constexpr int WG_THREADS = 256;
+constexpr int WG_MAX_NX = 1024;
+constexpr int WG_MAX_OCTAVES = 8;
 
-// One CTA per (z, band of WG_ROWS rows); a thread owns word columns (4 consecutive x), so a warp's store is 128 bytes
-// of one row.  The column heights are recomputed by each of the ny / WG_ROWS bands (a few hundred flops against 128 stores).
+// One CTA per z-plane (a contiguous nx * ny byte block).
+// Phase 1: one task per (column, noise evaluation) — the octaves of the height noise and the biome value are independent
+//   SingleSimplex calls, so the plane's nx * (octaves + 1) evaluations are spread over the CTA instead of one thread walking
+//   a column's 7 evaluations in series; the results wait in shared memory.
+// Phase 2: per column, the octaves are summed in FastNoise's order (same roundings) -> surface level + biome; per 16-column
+//   quad the highest level and the lowest stone top.
+// Phase 3: the plane is written in memory order with 16-byte stores; a quad above all of its columns is zeros, one below
+//   all of their stone tops is a stone splat, only the rows in between look at the columns (heights span 8..48 of 128 rows).
 __global__ void __launch_bounds__(WG_THREADS) worldgen_kernel(const __grid_constant__ WorldGenArgs a) {
     __shared__ NoiseTables tabs[2];
+    __shared__ float octave[(WG_MAX_OCTAVES + 1) * WG_MAX_NX];   // [evaluation][column]; the last row is the biome value
+    __shared__ short level[WG_MAX_NX];
+    __shared__ unsigned char biome_of[WG_MAX_NX];
+    __shared__ short quad_top[WG_MAX_NX / 16], quad_stone[WG_MAX_NX / 16];
     {
         const unsigned* src0 = reinterpret_cast<const unsigned*>(&a.height_tab);
         const unsigned* src1 = reinterpret_cast<const unsigned*>(&a.biome_tab);
@@ -101,38 +101,78 @@ __global__ void __launch_bounds__(WG_THREADS) worldgen_kernel(const __grid_const
         for (int i = threadIdx.x; i < 256; i += WG_THREADS) { dst[i] = src0[i]; dst[256 + i] = src1[i]; }
     }
     __syncthreads();
-    const int z = blockIdx.x, y_begin = blockIdx.y * WG_ROWS, y_end = min(y_begin + WG_ROWS, a.ny);
-    const int nxw = a.nx >> 2;
-    unsigned* plane = reinterpret_cast<unsigned*>(a.blocks + (size_t)z * a.nx * a.ny);
-    for (int wc = threadIdx.x; wc < nxw; wc += WG_THREADS) {
-        int level[4];
-        unsigned top[4], mid[4], depth[4];  // block at the surface row, below it, and how far the second layer reaches
-        for (int k = 0; k < 4; ++k) {
-            int Yc = 50, biome = 1;  // flat world: SetVerticalBlocks(world, x, z, 50, 1, false) (:309)
-            if (a.gen_type) {
-                const float real_x = (float)(wc * 4 + k), real_z = (float)z;
-                const float h = simplex_fbm2(tabs[0], real_x * a.frequency, real_z * a.frequency, a.octaves, a.lacunarity, a.gain, a.bounding);
-                const float height = ((h + 1.0f) / 2.0f) * 40.0f;                                        // :246-247
-                float column_noise = simplex2(tabs[1], 0u, (real_x / 2.0f) * a.biome_frequency, (real_z / 2.0f) * a.biome_frequency);
-                column_noise = ((column_noise + 1.0f) / 2.0f) * 240.0f;                                  // :249-250
-                biome = column_noise < 90.0f ? 0 : 1;                                                      // GetBiome (:33-47)
-                Yc = __float2int_rz(height + 8.0f);                                                        // :257
+    const int z = blockIdx.x;
+    if (a.gen_type) {
+        const int evals = a.octaves + 1;
+        for (int task = threadIdx.x; task < evals * a.nx; task += WG_THREADS) {
+            const int e = task / a.nx, x = task - e * a.nx;
+            const float real_x = (float)x, real_z = (float)z;
+            float v;
+            if (e < a.octaves) {   // octave e of SingleSimplexFractalFBM (:1191-1208): coordinates scaled e times by the lacunarity
+                float fx = real_x * a.frequency, fz = real_z * a.frequency;
+                for (int i = 0; i < e; ++i) { fx *= a.lacunarity; fz *= a.lacunarity; }
+                v = simplex2(tabs[0], tabs[0].perm[e], fx, fz);
+            } else {               // BiomeGenerator.GetNoise(real_x / 2, real_z / 2) (:249)
+                v = simplex2(tabs[1], 0u, (real_x / 2.0f) * a.biome_frequency, (real_z / 2.0f) * a.biome_frequency);
             }
-            level[k] = Yc;
-            top[k] = biome == 1 ? a.grass : a.sand;   // y >= level - 1
-            mid[k] = biome == 1 ? a.dirt : a.sand;    // y >= level - 5 (biome 1) / level - 8 (biome 0)
-            depth[k] = biome == 1 ? 5 : 8;
+            octave[e * WG_MAX_NX + x] = v;
         }
-        for (int y = y_begin; y < y_end; ++y) {
-            unsigned w = 0;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < a.nx; x += WG_THREADS) {
+        int Yc = 50, biome = 1;  // flat world: SetVerticalBlocks(world, x, z, 50, 1, false) (:309)
+        if (a.gen_type) {
+            float sum = octave[x], amp = 1.0f;
+            for (int i = 1; i < a.octaves; ++i) {
+                amp *= a.gain;
+                sum += octave[i * WG_MAX_NX + x] * amp;
+            }
+            const float h = sum * a.bounding;
+            const float height = ((h + 1.0f) / 2.0f) * 40.0f;                       // :246-247
+            const float column_noise = ((octave[a.octaves * WG_MAX_NX + x] + 1.0f) / 2.0f) * 240.0f;   // :250
+            biome = column_noise < 90.0f ? 0 : 1;                                     // GetBiome (:33-47)
+            Yc = __float2int_rz(height + 8.0f);                                       // :257
+        }
+        level[x] = (short)max(-32000, min(Yc, 32000));
+        biome_of[x] = (unsigned char)biome;
+    }
+    __syncthreads();
+    const int qpr = a.nx >> 4;
+    for (int q = threadIdx.x; q < qpr; q += WG_THREADS) {
+        int top = -32768, stone = 32767;
+        for (int k = 0; k < 16; ++k) {
+            const int L = level[q * 16 + k];
+            top = max(top, L);
+            stone = min(stone, L - (biome_of[q * 16 + k] ? 5 : 8));   // rows below level - 5 (biome 1) / level - 8 (biome 0) are stone
+        }
+        quad_top[q] = (short)top; quad_stone[q] = (short)max(stone, -32768);
+    }
+    __syncthreads();
+    uint4* plane = reinterpret_cast<uint4*>(a.blocks + (size_t)z * a.nx * a.ny);
+    const unsigned stone4 = a.stone * 0x01010101u;
+    const int items = qpr * a.ny;                               // <= 4096 (nx * ny <= 65536)
+    const unsigned rdiv = ((1u << 20) + qpr - 1) / qpr;         // it / qpr == (it * rdiv) >> 20 for it < 4096, qpr <= 64
+    for (int it = threadIdx.x; it < items; it += WG_THREADS) {
+        const int y = (int)(((unsigned)it * rdiv) >> 20), q = it - y * qpr;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (y < quad_stone[q]) v = make_uint4(stone4, stone4, stone4, stone4);
+        else if (y < quad_top[q]) {
+            unsigned w[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                unsigned id = 0;
-                if (y < level[k]) id = y >= level[k] - 1 ? top[k] : (y >= level[k] - (int)depth[k] ? mid[k] : a.stone);
-                w |= id << (8 * k);
+            for (int j = 0; j < 4; ++j) {
+                w[j] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int x = q * 16 + j * 4 + k, L = level[x];
+                    const bool b1 = biome_of[x] != 0;
+                    unsigned id = 0;   // SetVerticalBlocks (:49-88), swapstone = false
+                    if (y < L) id = y >= L - 1 ? (b1 ? a.grass : a.sand) : (y >= L - (b1 ? 5 : 8) ? (b1 ? a.dirt : a.sand) : a.stone);
+                    w[j] |= id << (8 * k);
+                }
             }
-            plane[(size_t)y * nxw + wc] = w;
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        plane[it] = v;
     }
 }
 
@@ -289,8 +329,7 @@ int vxrt_launch_generate_world(vxrt_ctx* c, const vxrt_worldgen_params& p) {
     a.stone = (unsigned)p.stone_id & 0xffu; a.sand = (unsigned)p.sand_id & 0xffu;
     build_tables(p.noise_seed, &a.height_tab);
     build_tables(p.biome_seed, &a.biome_tab);
-    dim3 grid(c->nz, (c->ny + WG_ROWS - 1) / WG_ROWS);
-    worldgen_kernel<<<grid, WG_THREADS, 0, c->stream>>>(a);
+    worldgen_kernel<<<c->nz, WG_THREADS, 0, c->stream>>>(a);   // nx <= 1024, nx % 16 == 0 (vxrt_cuda_create)
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;
