@@ -152,7 +152,11 @@ typedef enum vxrt_attachment {
     VXRT_ATT_SHADOW_TEMPORAL_A = 41, /* ShadowTemporalFBO_1: +0 shadow R8, +1 accumulated frames R16F */
     VXRT_ATT_SHADOW_TEMPORAL_B = 43, /* ShadowTemporalFBO_2 */
     VXRT_ATT_SHADOW_FILTERED = 45,   /* ShadowFiltered: R8 */
-    VXRT_ATT_COUNT = 46
+    /* reflection temporal filter (Core/Pipeline.cpp:1191-1192): a temporal set is three consecutive ids */
+    VXRT_ATT_REFL_TEMPORAL_A = 46,   /* ReflectionTemporalFBO_1: +0 colour RGBA16F, +1 accumulation factor R16F, +2 stabilised hit distance R16F */
+    VXRT_ATT_REFL_TEMPORAL_B = 49,   /* ReflectionTemporalFBO_2 */
+    VXRT_ATT_PREV_REFL_HITDIST = 52, /* previous frame's REFL_HITDIST (the engine ping-pongs ReflectionTraceFBO_1 / _2, :1864-1865); filled by vxrt_cuda_end_frame */
+    VXRT_ATT_COUNT = 53
 } vxrt_attachment;
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
@@ -393,7 +397,8 @@ int vxrt_cuda_svgf_spatial(vxrt_ctx* ctx, const vxrt_svgf_spatial_params* p);
 /* end of frame: this frame's primary G-buffer (INITIAL_T / NORMAL / BLOCK) becomes VXRT_ATT_PREV_INITIAL_* */
 int vxrt_cuda_svgf_end_frame(vxrt_ctx* ctx);
 
-/* same hand-over under its general name: every temporal filter (SVGF, shadow) reprojects into VXRT_ATT_PREV_INITIAL_* */
+/* same hand-over under its general name: every temporal filter (SVGF, shadow, reflection) reprojects into VXRT_ATT_PREV_INITIAL_*;
+ * when a reflection trace exists its hit distance also becomes VXRT_ATT_PREV_REFL_HITDIST */
 int vxrt_cuda_end_frame(vxrt_ctx* ctx);
 
 /* ---- sun-shadow denoiser: Core/Shaders/ShadowTemporalFilter.glsl and ShadowFilter.glsl, dispatched at
@@ -458,6 +463,30 @@ int vxrt_cuda_import_sections(vxrt_ctx* ctx, const uint8_t* block_ids /* n*4096 
  * reference's scan.  xyz_out: HOST memory for 3*capacity ints (may be NULL when capacity = 0); *count receives the
  * number found, of which min(count, capacity) are written. */
 int vxrt_cuda_collect_lights(vxrt_ctx* ctx, int32_t* xyz_out, int32_t capacity, int32_t* count);
+
+/* ---- reflection temporal filter: Core/Shaders/SpecularTemporalFilter.glsl, dispatched at
+ * Core/Pipeline.cpp:3316-3400 ----
+ * Consumes REFL_COLOR / REFL_HITDIST / REFL_EMISSIVE of vxrt_cuda_reflection_trace, INITIAL_T / INITIAL_NORMAL, GBUF_PBR,
+ * PREV_INITIAL_T / PREV_INITIAL_NORMAL, PREV_REFL_HITDIST and the previous frame's temporal set (ping-ponged by frame parity
+ * like ReflectionTemporalFBO_1 / _2, :1858-1859; the history images start out zero-filled like the engine's FBOs).  Reprojects
+ * along the reflected ray (hit-distance reprojection), clips the history to the 3 x 3 neighbourhood of the current trace
+ * (ReflectionClipping), rejects fireflies next to emissive hits and writes out_set.  The spatial pass
+ * (ReflectionDenoiserNew.glsl) is not covered yet.                                                                        */
+typedef struct vxrt_specular_temporal_params {   /* Pipeline.cpp:3319-3359 */
+    float inv_view[16], inv_projection[16];      /* u_InverseView, u_InverseProjection (v_RayOrigin = u_InverseView[3]) */
+    float prev_view[16], prev_projection[16];    /* u_PrevView, u_PrevProjection */
+    float current_camera_pos[3], prev_camera_pos[3];   /* u_CurrentCameraPos, u_PrevCameraPos */
+    int32_t width, height;                       /* size of the temporal images (ReflectionSuperSampleResolution) */
+    int32_t history_set, out_set;                /* VXRT_ATT_REFL_TEMPORAL_A / _B */
+    int32_t temporal_spec;                       /* TEMPORAL_SPEC (true, :129) */
+    int32_t firefly_rejection;                   /* u_FireflyRejection (ReflectionFireflyRejection, true) */
+    int32_t aggressive_firefly_rejection;        /* u_AggressiveFireflyRejection (true) */
+    int32_t smart_clip;                          /* u_SmartClip (SmartReflectionClip, true) */
+    int32_t roughness_weight;                    /* u_RoughnessWeight (RoughReflections, true) */
+    int32_t stabilize_hit_distance;              /* u_TemporallyStabializeHitDistance (true) */
+    vxrt_tile tile;
+} vxrt_specular_temporal_params;
+int vxrt_cuda_specular_temporal(vxrt_ctx* ctx, const vxrt_specular_temporal_params* p);
 
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {

@@ -277,6 +277,28 @@ def shadow_filter(p: "abi.ShadowFilterParams", temporal: dict, raw_transversal: 
     return out
 
 
+def specular_temporal(p: "abi.SpecularTemporalParams", cur: dict, prev_hitdist: np.ndarray, hist: dict, g: dict, prev_g: dict, pbr: np.ndarray,
+                      fn=None) -> dict:
+    """SpecularTemporalFilter.glsl.  cur: {"color": f16 (rh, rw, 4), "hitdist": f16, "mask": u8} of the reflection trace; prev_hitdist:
+    the previous frame's hit distance (rh, rw); hist: previous temporal set {"color": f16 (h, w, 4), "frames": f16, "hitdist": f16};
+    g / prev_g: {"t": f16, "normal": u8} of this / the previous frame; pbr: u8 (mh, mw, 4).  Returns this frame's temporal set."""
+    out = {"color": np.zeros((p.height, p.width, 4), np.float16), "frames": np.zeros((p.height, p.width), np.float16),
+           "hitdist": np.zeros((p.height, p.width), np.float16)}
+    rh, rw = cur["hitdist"].shape
+    gh, gw = g["t"].shape
+    mh, mw = pbr.shape[:2]
+    assert hist["color"].shape == (p.height, p.width, 4) and prev_hitdist.shape == (rh, rw) and prev_g["t"].shape == (gh, gw)
+    c = np.ascontiguousarray
+    f = fn
+    if f is None:
+        f = lib().vxo_specular_temporal
+        f.restype = None
+    f(C.byref(p), _p(c(cur["color"])), _p(c(cur["hitdist"])), _p(c(cur["mask"])), _p(c(prev_hitdist)), rw, rh, _p(c(hist["color"])), _p(c(hist["hitdist"])),
+      _p(c(g["t"])), _p(c(g["normal"])), _p(c(prev_g["t"])), _p(c(prev_g["normal"])), gw, gh, _p(c(pbr)), mw, mh, _p(out["color"]), _p(out["frames"]),
+      _p(out["hitdist"]))
+    return out
+
+
 class OracleScene:
     """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
 

@@ -43,6 +43,8 @@ SHADERS = {
     # sun-shadow denoiser
     "ShadowTemporal": ("ShadowTemporalFilter.glsl", "fragment"),
     "ShadowFilter": ("ShadowFilter.glsl", "fragment"),
+    # reflection temporal filter
+    "SpecularTemporal": ("SpecularTemporalFilter.glsl", "fragment"),
     # the colour pass composites sky / clouds / denoised GI (out of scope); only its Cook-Torrance
     # functions are compiled: they are cut out of the file by name, unmodified
     "ColorPassDirect": ("ColorPassFrag.glsl", "extract"),

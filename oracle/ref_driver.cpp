@@ -54,6 +54,9 @@ thread_local uvec3 gl_GlobalInvocationID;
 #ifdef VXREF_HAVE_ShadowFilter
 #include "ShadowFilter.cpp"
 #endif
+#ifdef VXREF_HAVE_SpecularTemporal
+#include "SpecularTemporal.cpp"
+#endif
 #ifdef VXREF_HAVE_ColorPassDirect
 #include "ColorPassDirect.cpp"
 #endif
@@ -109,6 +112,9 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_ShadowFilter
     m |= 16384;
+#endif
+#ifdef VXREF_HAVE_SpecularTemporal
+    m |= 32768;
 #endif
 #ifdef VXREF_HAVE_RaycastDetect
     m |= 512;   /* World::RaycastDetect, host C++ lifted from Core/World.cpp (vxref_raycast_detect, generated unit) */
@@ -660,6 +666,54 @@ extern "C" void vxref_shadow_filter(const vxrt_shadow_filter_params* p, const ui
             S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
             S::shader_reset(); S::shader_main();
             out_shadow[(size_t)py * W + px] = vxo::float_to_unorm8(S::o_Color);
+        }
+}
+#endif
+
+/* ---- reflection temporal filter (Core/Pipeline.cpp:3316-3400).  cur = ReflectionTraceFBO (colour RGBA16F, hit distance R16F,
+ * emissive mask R8, rw x rh) + the previous frame's hit distance; hist = PrevReflectionTemporalFBO images 0 and 2 (width x height);
+ * primary G-buffer of this and the previous frame (gw x gh); GeneratedGBuffer PBR (mw x mh) ---- */
+#ifdef VXREF_HAVE_SpecularTemporal
+extern "C" void vxref_specular_temporal(const vxrt_specular_temporal_params* p, const uint16_t* cur_color_h4, const uint16_t* cur_hitdist,
+                                        const uint8_t* cur_mask, const uint16_t* prev_hitdist, int rw, int rh, const uint16_t* hist_color_h4,
+                                        const uint16_t* hist_hitdist, const uint16_t* g_t, const uint8_t* g_normal, const uint16_t* prev_t,
+                                        const uint8_t* prev_normal, int gw, int gh, const uint8_t* pbr_u8x4, int mw, int mh,
+                                        uint16_t* out_color_h4, uint16_t* out_frames, uint16_t* out_hitdist) {
+    namespace S = shader_SpecularTemporal;
+    const int W = p->width, H = p->height;
+    auto fc = svgf_half(cur_color_h4, (size_t)rw * rh * 4), fh = svgf_half(cur_hitdist, (size_t)rw * rh), fm = svgf_u8(cur_mask, (size_t)rw * rh);
+    auto fph = svgf_half(prev_hitdist, (size_t)rw * rh);
+    auto hc = svgf_half(hist_color_h4, (size_t)W * H * 4), hh = svgf_half(hist_hitdist, (size_t)W * H);
+    auto ft = svgf_half(g_t, (size_t)gw * gh), fn = svgf_u8(g_normal, (size_t)gw * gh), pt = svgf_half(prev_t, (size_t)gw * gh), pn = svgf_u8(prev_normal, (size_t)gw * gh);
+    auto fp = svgf_u8(pbr_u8x4, (size_t)mw * mh * 4);
+    bind2d(S::u_CurrentColorTexture, fc.data(), rw, rh, 4, true); bind2d(S::u_SpecularHitDist, fh.data(), rw, rh, 1, true);
+    bind2d(S::u_EmissivityIntersectionMask, fm.data(), rw, rh, 1, true); bind2d(S::u_PrevSpecularHitDist, fph.data(), rw, rh, 1, true);
+    bind2d(S::u_PreviousColorTexture, hc.data(), W, H, 4, true); bind2d(S::u_TemporalHitDist, hh.data(), W, H, 1, true);
+    bind2d(S::u_CurrentPositionTexture, ft.data(), gw, gh, 1, true); bind2d(S::u_PreviousFramePositionTexture, pt.data(), gw, gh, 1, true);
+    bind2d(S::u_NormalTexture, fn.data(), gw, gh, 1, false); bind2d(S::u_PreviousNormalTexture, pn.data(), gw, gh, 1, false);
+    bind2d(S::u_PBRTex, fp.data(), mw, mh, 4, true);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_PrevView.load(p->prev_view); S::u_PrevProjection.load(p->prev_projection);
+    S::u_MinimumMix = 0.0f; S::u_MaximumMix = 0.95f; S::u_TemporalQuality = 1; S::u_ReflectionTemporal = true;   /* Pipeline.cpp:3342-3345 */
+    S::TEMPORAL_SPEC = p->temporal_spec != 0; S::u_FireflyRejection = p->firefly_rejection != 0;
+    S::u_AggressiveFireflyRejection = p->aggressive_firefly_rejection != 0; S::u_SmartClip = p->smart_clip != 0;
+    S::u_RoughnessWeight = p->roughness_weight != 0; S::u_TemporallyStabializeHitDistance = p->stabilize_hit_distance != 0;
+    S::u_PrevCameraPos = vec3(p->prev_camera_pos[0], p->prev_camera_pos[1], p->prev_camera_pos[2]);
+    S::u_CurrentCameraPos = vec3(p->current_camera_pos[0], p->current_camera_pos[1], p->current_camera_pos[2]);
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam; S::v_RayDirection = vec3(0.0f, 0.0f, 1.0f);
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out_color_h4[4 * i + c] = vxo::float_to_half(S::o_Color[c]);
+            out_frames[i] = vxo::float_to_half(S::o_AccumulatedFrames);
+            out_hitdist[i] = vxo::float_to_half(S::o_HitDistanceStable);
         }
 }
 #endif

@@ -128,6 +128,14 @@ typedef struct vxo_reflection_inputs {
 void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_params* p, const vxo_reflection_inputs* in,
                           uint16_t* color_h4, uint16_t* hitdist_h, uint8_t* emissive_u8, vxrt_trace_stats* stats);
 
+/* SpecularTemporalFilter.glsl main() (vxrt_oracle_refl_filter.cpp): reflection trace images (rw x rh), previous temporal
+ * set (width x height), primary G-buffers of this and the previous frame (gw x gh), GeneratedGBuffer PBR (mw x mh) */
+void vxo_specular_temporal(const vxrt_specular_temporal_params* p, const uint16_t* cur_color_h4, const uint16_t* cur_hitdist,
+                           const uint8_t* cur_mask, const uint16_t* prev_hitdist, int rw, int rh, const uint16_t* hist_color_h4,
+                           const uint16_t* hist_hitdist, const uint16_t* g_t, const uint8_t* g_normal, const uint16_t* prev_t,
+                           const uint8_t* prev_normal, int gw, int gh, const uint8_t* pbr_u8x4, int mw, int mh,
+                           uint16_t* out_color_h4, uint16_t* out_frames, uint16_t* out_hitdist);
+
 /* ---- world producers (vxrt_oracle_world.cpp) ---- */
 /* FastNoise::GetNoise(x, y) for the Simplex (fractal = 0) / SimplexFractal FBM (fractal = 1) types; xy = 2*n floats */
 void vxo_fastnoise_2d(int32_t seed, int32_t fractal, float frequency, int32_t octaves, const float* xy, int32_t n, float* out);

@@ -28,6 +28,8 @@ ATT_SVGF_TEMPORAL_A, ATT_SVGF_TEMPORAL_B, ATT_SVGF_VARIANCE, ATT_SVGF_DENOISE_A,
 ATT_PREV_INITIAL_T, ATT_PREV_INITIAL_NORMAL, ATT_PREV_INITIAL_BLOCK = 38, 39, 40
 # shadow denoiser: temporal sets are (shadow R8, accumulated frames R16F)
 ATT_SHADOW_TEMPORAL_A, ATT_SHADOW_TEMPORAL_B, ATT_SHADOW_FILTERED = 41, 43, 45
+# reflection temporal filter: temporal sets are (colour RGBA16F, accumulation factor R16F, stabilised hit distance R16F)
+ATT_REFL_TEMPORAL_A, ATT_REFL_TEMPORAL_B, ATT_PREV_REFL_HITDIST = 46, 49, 52
 
 TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
@@ -133,6 +135,15 @@ class ShadowTemporalParams(C.Structure):
                 ("out_set", C.c_int32), ("shadow_temporal", C.c_int32), ("tile", Tile)]
 
 
+class SpecularTemporalParams(C.Structure):
+    """vxrt_specular_temporal_params"""
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("prev_view", C.c_float * 16),
+                ("prev_projection", C.c_float * 16), ("current_camera_pos", C.c_float * 3), ("prev_camera_pos", C.c_float * 3),
+                ("width", C.c_int32), ("height", C.c_int32), ("history_set", C.c_int32), ("out_set", C.c_int32),
+                ("temporal_spec", C.c_int32), ("firefly_rejection", C.c_int32), ("aggressive_firefly_rejection", C.c_int32),
+                ("smart_clip", C.c_int32), ("roughness_weight", C.c_int32), ("stabilize_hit_distance", C.c_int32), ("tile", Tile)]
+
+
 class ShadowFilterParams(C.Structure):
     _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
                 ("in_set", C.c_int32), ("filter_scale", C.c_float), ("tile", Tile)]
@@ -215,6 +226,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_shadow_temporal": (C.c_int, [vp, P(ShadowTemporalParams)]),
         "vxrt_cuda_shadow_filter": (C.c_int, [vp, P(ShadowFilterParams)]),
         "vxrt_cuda_select_shadow": (C.c_int, [vp, i32]),
+        "vxrt_cuda_specular_temporal": (C.c_int, [vp, P(SpecularTemporalParams)]),
         "vxrt_cuda_write_attachment": (C.c_int, [vp, i32, i32, i32, i32, vp]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),

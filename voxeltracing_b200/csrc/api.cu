@@ -584,6 +584,12 @@ int vxrt_cuda_select_shadow(vxrt_ctx* c, int32_t id) {
     c->shadow_source = id;
     return VXRT_OK;
 }
+int vxrt_cuda_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_specular_temporal(c, *p);
+}
 int vxrt_cuda_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
     int rc = check_frame(__func__, p->width, p->height, p->tile);

@@ -1,0 +1,281 @@
+// refl_filter.cu — reflection temporal filter: Core/Shaders/SpecularTemporalFilter.glsl, dispatched at
+// Core/Pipeline.cpp:3316-3400.  Hit-distance reprojection of the reflected ray, neighbourhood clipping of the history
+// (ReflectionClipping), firefly rejection next to emissive hits, accumulation factor from the screen-space velocity.  One thread
+// per pixel, a warp covers an 8 x 4 pixel tile; samplers of filter_sampler.cuh.  The trace images, the temporal images, the
+// primary G-buffer and the material G-buffer may each have their own size.  The only transcendental is one expf per pixel:
+// R16F outputs agree with the oracle to one half-ulp (tests/test_gpu_refl_filter.py).
+#include "ctx.h"
+#include "filter_sampler.cuh"
+
+namespace {
+
+struct Img8 { const uint8_t* __restrict__ p; int w, h; };
+struct Img16 { const uint16_t* __restrict__ p; int w, h; };
+
+struct SpecTemporalArgs {
+    float inv_view[16], inv_proj[16], prev_pv[16];
+    float cam_cur[3], cam_prev[3];
+    int width, height, row0, row1;
+    int temporal_spec, firefly, aggressive, smart_clip, rough_weight, stabilize;
+    Img16 cur_color;   // ReflectionTraceFBO[0] RGBA16F
+    Img16 cur_hit;     // [1] R16F
+    Img8 cur_mask;     // [2] R8
+    Img16 prev_hit;    // previous frame's [1]
+    Img16 hist_color;  // previous temporal set +0
+    Img16 hist_hit;    // previous temporal set +2
+    Img16 g_t, prev_t;
+    Img8 g_n, prev_n;
+    Img8 pbr;          // GeneratedGBuffer[2] RGBA8
+    uint16_t* __restrict__ out_color;
+    uint16_t* __restrict__ out_frames;
+    uint16_t* __restrict__ out_hit;
+};
+
+struct c4 { float x, y, z, w; };
+VXD c4 sample4(const Img16& im, f2 uv) {
+    float o[4];
+    sample_rgba16(im.p, make_tap(im.w, im.h, uv), o);
+    c4 r; r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3];
+    return r;
+}
+VXD float sample1(const Img16& im, f2 uv) { return sample_r16(im.p, make_tap(im.w, im.h, uv)); }
+VXD float sample1(const Img8& im, f2 uv, const float* lut) { return sample_r8(im.p, make_tap(im.w, im.h, uv), lut); }
+VXD int normal_at(const Img8& im, f2 uv, const float* lut) { return normal_index(lut[__ldg(im.p + nearest_offset(im.w, im.h, uv))]); }
+// .xy of a bilinear RGBA8 sample
+VXD f2 sample_pbr_xy(const Img8& im, f2 uv, const float* lut) {
+    const Tap t = make_tap(im.w, im.h, uv);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(im.p);
+    const uint32_t q00 = __ldg(p + t.o00), q10 = __ldg(p + t.o10), q01 = __ldg(p + t.o01), q11 = __ldg(p + t.o11);
+    return F2(bl(t, lut[q00 & 255], lut[q10 & 255], lut[q01 & 255], lut[q11 & 255]),
+              bl(t, lut[(q00 >> 8) & 255], lut[(q10 >> 8) & 255], lut[(q01 >> 8) & 255], lut[(q11 >> 8) & 255]));
+}
+VXD f3 xyz(const c4& v) { return F3(v.x, v.y, v.z); }
+VXD void set_xyz(c4& v, f3 a) { v.x = a.x; v.y = a.y; v.z = a.z; }
+VXD c4 add4(c4 a, float s) { a.x += s; a.y += s; a.z += s; a.w += s; return a; }
+VXD float dist_sq(f3 a, f3 b) { const f3 c = a - b; return dot(c, c); }
+VXD f2 project_prev(const float* pv, f3 pos) {
+    const f4 P = mat4_mul(pv, F4(pos.x, pos.y, pos.z, 1.0f));
+    return F2((P.x / P.w) * 0.5f + 0.5f, (P.y / P.w) * 0.5f + 0.5f);
+}
+// ClipToAABB (:126-135)
+VXD f3 clip_to_aabb(f3 prev, f3 mn, f3 mx) {
+    const f3 pClip = 0.5f * (mx + mn), eClip = 0.5f * (mx - mn);
+    const f3 vClip = prev - pClip, vUnit = vClip / eClip;
+    const float denom = gmax(fabsf(vUnit.x), gmax(fabsf(vUnit.y), fabsf(vUnit.z)));
+    return denom > 1.0f ? pClip + vClip / denom : prev;
+}
+
+// SpecularTemporalFilter.glsl main() (:285-417)
+__global__ void __launch_bounds__(256) specular_temporal_kernel(const __grid_constant__ SpecTemporalArgs a) {
+    __shared__ float lut[256];
+    fill_unorm_lut(lut);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    const f3 origin = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+    const float CurDist = sample1(a.g_t, tc);
+    const f3 CurPos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * CurDist;   // GetPositionAt (:94-98)
+    const int InitialNormal = normal_at(a.g_n, tc, lut);
+    c4 CurrentColor = sample4(a.cur_color, tc);
+    float oFrames = 0.0f, oHit;
+    c4 oColor;
+    const float HitDistanceCurrent = sample1(a.cur_hit, tc);
+    const f2 TexelSize = F2(1.0f / (float)a.cur_color.w, 1.0f / (float)a.cur_color.h);
+    if (a.firefly && sample1(a.cur_mask, tc, lut) > 0.05f) {   // FireflyReject (:246-277)
+        const int SampleThreshold = a.aggressive ? 3 : 4;
+        c4 NonLit; NonLit.x = NonLit.y = NonLit.z = NonLit.w = 0.0f;
+        int Unlit = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float ox = i == 0 ? 1.0f : (i == 2 ? -1.0f : 0.0f), oy = i == 1 ? 1.0f : (i == 3 ? -1.0f : 0.0f);
+            const f2 sc = F2(tc.x + ox * TexelSize.x, tc.y + oy * TexelSize.y);
+            const float Mask = sample1(a.cur_mask, sc, lut);
+            const c4 Color = sample4(a.cur_color, sc);
+            if (Mask < 0.01f) { NonLit.x += Color.x; NonLit.y += Color.y; NonLit.z += Color.z; NonLit.w += Color.w; ++Unlit; }
+        }
+        if (Unlit >= SampleThreshold) {
+            const float n = (float)Unlit;
+            CurrentColor.x = NonLit.x / n; CurrentColor.y = NonLit.y / n; CurrentColor.z = NonLit.z / n; CurrentColor.w = NonLit.w / n;
+        }
+    }
+    if (CurDist > 0.0f && a.temporal_spec) {
+        const bool SkySample = HitDistanceCurrent < 0.0f;
+        const f2 pxy = sample_pbr_xy(a.pbr, tc, lut);
+        const float RoughnessAt = gmix(0.095f, pxy.x, a.rough_weight ? 1.0f : 0.0f);
+        const float MetalnessAt = pxy.y;
+        bool LessValid = false;
+        f2 R = F2(0.0f, 0.0f);
+        if (HitDistanceCurrent > 0.0f && !SkySample && RoughnessAt <= 0.875f + 0.01f) {   // reproject along the reflected ray
+            const f3 I = normalize(origin - CurPos);
+            R = project_prev(a.prev_pv, CurPos - I * HitDistanceCurrent);
+            const float PreviousT = sample1(a.prev_hit, R);
+            if (fabsf(PreviousT - HitDistanceCurrent) >= 3.8f) LessValid = true;
+        } else if (!SkySample) {
+            f3 CameraOffset = F3(a.cam_cur[0], a.cam_cur[1], a.cam_cur[2]) - F3(a.cam_prev[0], a.cam_prev[1], a.cam_prev[2]);
+            CameraOffset = CameraOffset * 0.6f;
+            R = project_prev(a.prev_pv, CurPos - CameraOffset);
+        }
+        if (SkySample) {
+            const f3 I = normalize(origin - CurPos);
+            R = project_prev(a.prev_pv, CurPos - I * 64.0f);
+        }
+        const float PrevDist = sample1(a.prev_t, R);
+        const f3 PrevPos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, R)) * PrevDist;
+        const float d = fabsf(distance(PrevPos, CurPos));
+        const float Bias = 0.01f;
+        const int PrevNormal = normal_at(a.prev_n, R, lut);
+        if (R.x > 0.0f + Bias && R.x < 1.0f - Bias && R.y > 0.0f + Bias && R.y < 1.0f - Bias && d < 1.0f && PrevNormal == InitialNormal) {
+            c4 PrevColor = sample4(a.hist_color, R);
+            const f3 BasePrevColor = xyz(PrevColor);
+            const f3 CamCur = F3(a.cam_cur[0], a.cam_cur[1], a.cam_cur[2]), CamPrev = F3(a.cam_prev[0], a.cam_prev[1], a.cam_prev[2]);
+            const bool Moved = dist_sq(CamCur, CamPrev) > 0.0001f;
+            const bool TryClipping = RoughnessAt < 0.5f + 0.01f;
+            if (TryClipping && Moved && a.smart_clip) {   // ReflectionClipping (:143-225), called with v_TexCoords
+                const float RoughnessThreshold = 0.275f + 0.01f;
+                c4 MinColor, MaxColor;
+                MinColor.x = MinColor.y = MinColor.z = MinColor.w = 1000.0f;
+                MaxColor.x = MaxColor.y = MaxColor.z = MaxColor.w = -1000.0f;
+                float AdditionalMaxBias = 0.0f;
+#pragma unroll 1
+                for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
+                    for (int y = -1; y <= 1; ++y) {
+                        const f2 sc = F2(tc.x + (float)x * TexelSize.x, tc.y + (float)y * TexelSize.y);
+                        if (!(sample1(a.cur_mask, sc, lut) < 0.01f)) AdditionalMaxBias += 0.1f;
+                        const c4 S = sample4(a.cur_color, sc);
+                        MinColor.x = gmin(S.x, MinColor.x); MinColor.y = gmin(S.y, MinColor.y); MinColor.z = gmin(S.z, MinColor.z); MinColor.w = gmin(S.w, MinColor.w);
+                        MaxColor.x = gmax(S.x, MaxColor.x); MaxColor.y = gmax(S.y, MaxColor.y); MaxColor.z = gmax(S.z, MaxColor.z); MaxColor.w = gmax(S.w, MaxColor.w);
+                    }
+                const f3 OriginalMin = xyz(MinColor), OriginalMax = xyz(MaxColor);
+                const bool Smoothish = RoughnessAt < RoughnessThreshold;
+                const bool Roughish = RoughnessAt > RoughnessThreshold && RoughnessAt < 0.50f + 0.01f;
+                if (Smoothish) {
+                    const float Perceived = RoughnessAt * RoughnessAt;
+                    const float RT2 = RoughnessThreshold * RoughnessThreshold;
+                    const float Remapped = 0.0f + (gclamp((Perceived - 0.0f) / (RT2 - 0.0f), 0.0f, 1.0f) * (1.0f - 0.0f));   // remap (:121-124)
+                    float B = gmix(0.01f, 0.085f, Remapped);
+                    if (RoughnessAt > 0.235f) B *= 1.55f;
+                    MinColor = add4(MinColor, -(B * 0.95f));
+                    MaxColor = add4(MaxColor, (B * 0.95f) + AdditionalMaxBias);
+                } else if (Roughish) {
+                    MinColor = add4(MinColor, -0.37f);
+                    MaxColor = add4(MaxColor, 0.37f + (AdditionalMaxBias * 1.1f));
+                }
+                const float m = gmix(0.05f, 0.25f, MetalnessAt > 0.05f ? 1.0f : 0.0f);
+                set_xyz(MinColor, gmix(xyz(MinColor), OriginalMin, m));
+                set_xyz(MaxColor, gmix(xyz(MaxColor), OriginalMax, m));
+                const float BiasMixer = LessValid ? 0.5f : 0.0f;
+                set_xyz(MinColor, gmix(xyz(MinColor), OriginalMin, BiasMixer));
+                set_xyz(MaxColor, gmix(xyz(MaxColor), OriginalMax, BiasMixer));
+                const f3 Prev3 = xyz(PrevColor);
+                const f3 Clamped = clip_to_aabb(Prev3, xyz(MinColor), xyz(MaxColor));
+                if (Clamped.x != Prev3.x || Clamped.y != Prev3.y || Clamped.z != Prev3.z)
+                    PrevColor = dist_sq(Clamped, xyz(MinColor)) > dist_sq(Clamped, xyz(MaxColor)) ? MaxColor : MinColor;
+            }
+            // GetAccumulationFactor (:279-283)
+            const float vx = (tc.x - R.x) * (float)a.cur_color.w, vy = (tc.y - R.y) * (float)a.cur_color.h;
+            float AF = gclamp(expf(-sqrtf(vx * vx + vy * vy)) * 0.9f + 0.750f, 0.00000001f, 0.96f);
+            AF = gclamp(AF, 0.001f, 0.95f);
+            CurrentColor.x = gmax(CurrentColor.x, 0.0f); CurrentColor.y = gmax(CurrentColor.y, 0.0f);
+            CurrentColor.z = gmax(CurrentColor.z, 0.0f); CurrentColor.w = gmax(CurrentColor.w, 0.0f);
+            PrevColor.x = gmax(PrevColor.x, 0.0f); PrevColor.y = gmax(PrevColor.y, 0.0f); PrevColor.z = gmax(PrevColor.z, 0.0f); PrevColor.w = gmax(PrevColor.w, 0.0f);
+            oColor.x = gmix(CurrentColor.x, PrevColor.x, AF); oColor.y = gmix(CurrentColor.y, PrevColor.y, AF);
+            oColor.z = gmix(CurrentColor.z, PrevColor.z, AF); oColor.w = gmix(CurrentColor.w, PrevColor.w, AF);
+            oFrames = AF;
+            oHit = HitDistanceCurrent;
+            if (dist_sq(BasePrevColor, xyz(PrevColor)) < 0.2f && a.stabilize)
+                oHit = gmix(HitDistanceCurrent, sample1(a.hist_hit, R), gclamp(AF * 1.1f, 0.0f, 0.9f));
+        } else {
+            oColor = CurrentColor; oFrames = 0.0f; oHit = HitDistanceCurrent;
+        }
+    } else {
+        oColor = CurrentColor; oHit = HitDistanceCurrent;
+    }
+    if (!a.temporal_spec) oFrames = -1.0f;
+    const size_t i = (size_t)py * a.width + px;
+    uint2 packed;
+    packed.x = (uint32_t)float_to_half_bits(oColor.x) | ((uint32_t)float_to_half_bits(oColor.y) << 16);
+    packed.y = (uint32_t)float_to_half_bits(oColor.z) | ((uint32_t)float_to_half_bits(oColor.w) << 16);
+    reinterpret_cast<uint2*>(a.out_color)[i] = packed;
+    a.out_frames[i] = float_to_half_bits(oFrames);
+    a.out_hit[i] = float_to_half_bits(oHit);
+}
+
+inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+}
+inline bool is_refl_set(int id) { return id == VXRT_ATT_REFL_TEMPORAL_A || id == VXRT_ATT_REFL_TEMPORAL_B; }
+
+template <typename I>
+int image_in(vxrt_ctx* c, const char* fn, int id, int bpp, I* img) {
+    const Attachment& a = c->att[id];
+    if (!a.ptr || a.width <= 0) return vxrt_fail(VXRT_E_STATE, "%s: attachment %d has not been written", fn, id);
+    if (a.bpp != bpp) return vxrt_fail(VXRT_E_STATE, "%s: attachment %d has %d bytes per pixel, expected %d", fn, id, a.bpp, bpp);
+    img->p = (decltype(img->p))a.ptr; img->w = a.width; img->h = a.height;
+    return VXRT_OK;
+}
+
+// an image of the previous frame that does not exist yet (first frame) starts out zero-filled, like the engine's FBOs
+int zero_if_missing(vxrt_ctx* c, int id, int w, int h, int bpp) {
+    const Attachment& a = c->att[id];
+    if (a.ptr && a.width == w && a.height == h && a.bpp == bpp) return VXRT_OK;
+    int rc = vxrt_ensure_attachment(c, id, w, h, bpp);
+    if (rc) return rc;
+    VX_CUDA(cudaMemsetAsync(c->att[id].ptr, 0, (size_t)w * h * bpp, c->stream));
+    return VXRT_OK;
+}
+
+}  // namespace
+
+int vxrt_launch_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params& p) {
+    static const char* fn = "vxrt_cuda_specular_temporal";
+    if (!is_refl_set(p.history_set) || !is_refl_set(p.out_set) || p.history_set == p.out_set)
+        return vxrt_fail(VXRT_E_INVALID, "%s: history_set / out_set must be the two of VXRT_ATT_REFL_TEMPORAL_A / _B", fn);
+    SpecTemporalArgs a;
+    int rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_REFL_COLOR, 8, &a.cur_color))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_REFL_HITDIST, 2, &a.cur_hit))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_REFL_EMISSIVE, 1, &a.cur_mask))) return rc;
+    if (a.cur_hit.w != a.cur_color.w || a.cur_hit.h != a.cur_color.h || a.cur_mask.w != a.cur_color.w || a.cur_mask.h != a.cur_color.h)
+        return vxrt_fail(VXRT_E_STATE, "%s: the reflection trace images differ in size", fn);
+    if ((rc = image_in(c, fn, VXRT_ATT_INITIAL_T, 2, &a.g_t))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_INITIAL_NORMAL, 1, &a.g_n))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_GBUF_PBR, 4, &a.pbr))) return rc;
+    if ((rc = zero_if_missing(c, p.history_set, p.width, p.height, 8))) return rc;
+    if ((rc = zero_if_missing(c, p.history_set + 1, p.width, p.height, 2))) return rc;
+    if ((rc = zero_if_missing(c, p.history_set + 2, p.width, p.height, 2))) return rc;
+    if ((rc = zero_if_missing(c, VXRT_ATT_PREV_INITIAL_T, a.g_t.w, a.g_t.h, 2))) return rc;
+    if ((rc = zero_if_missing(c, VXRT_ATT_PREV_INITIAL_NORMAL, a.g_n.w, a.g_n.h, 1))) return rc;
+    if ((rc = zero_if_missing(c, VXRT_ATT_PREV_REFL_HITDIST, a.cur_hit.w, a.cur_hit.h, 2))) return rc;
+    if ((rc = image_in(c, fn, p.history_set, 8, &a.hist_color))) return rc;
+    if ((rc = image_in(c, fn, p.history_set + 2, 2, &a.hist_hit))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_PREV_INITIAL_T, 2, &a.prev_t))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_PREV_INITIAL_NORMAL, 1, &a.prev_n))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_PREV_REFL_HITDIST, 2, &a.prev_hit))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, p.out_set, p.width, p.height, 8))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, p.out_set + 1, p.width, p.height, 2))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, p.out_set + 2, p.width, p.height, 2))) return rc;
+    a.out_color = (uint16_t*)c->att[p.out_set].ptr;
+    a.out_frames = (uint16_t*)c->att[p.out_set + 1].ptr;
+    a.out_hit = (uint16_t*)c->att[p.out_set + 2].ptr;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    for (int j = 0; j < 4; ++j) {   // u_PrevProjection * u_PrevView, column by column (mat4 * vec4 association of vmath.cuh)
+        const float* v = p.prev_view + 4 * j;
+        const float* m = p.prev_projection;
+        for (int r = 0; r < 4; ++r) a.prev_pv[4 * j + r] = (m[r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]);
+    }
+    for (int k = 0; k < 3; ++k) { a.cam_cur[k] = p.current_camera_pos[k]; a.cam_prev[k] = p.prev_camera_pos[k]; }
+    a.width = p.width; a.height = p.height;
+    a.temporal_spec = p.temporal_spec; a.firefly = p.firefly_rejection; a.aggressive = p.aggressive_firefly_rejection;
+    a.smart_clip = p.smart_clip; a.rough_weight = p.roughness_weight; a.stabilize = p.stabilize_hit_distance;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    specular_temporal_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}

@@ -649,5 +649,13 @@ int vxrt_launch_svgf_end_frame(vxrt_ctx* c) {
         if ((rc = vxrt_ensure_attachment(c, prev[k], a.width, a.height, a.bpp))) return rc;
         VX_CUDA(cudaMemcpyAsync(b.ptr, a.ptr, (size_t)a.width * a.height * a.bpp, cudaMemcpyDeviceToDevice, c->stream));
     }
+    // the reflection trace's hit distance of this frame is what the reflection temporal filter reprojects into next frame
+    // (PrevReflectionTraceFBO.GetTexture(1), Core/Pipeline.cpp:1864-1865, 3381)
+    const Attachment& h = c->att[VXRT_ATT_REFL_HITDIST];
+    if (h.ptr && h.width > 0) {
+        int rc;
+        if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_PREV_REFL_HITDIST, h.width, h.height, h.bpp))) return rc;
+        VX_CUDA(cudaMemcpyAsync(c->att[VXRT_ATT_PREV_REFL_HITDIST].ptr, h.ptr, (size_t)h.width * h.height * h.bpp, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return VXRT_OK;
 }

@@ -325,3 +325,46 @@ class ShadowDenoiser:
 
     def run(self, cam: host_api.Camera, frame: int, tile=(0, 0), hook=None):
         self.submit(self.prepare(cam, frame, tile), hook)
+
+
+class ReflectionTemporal:
+    """The reflection temporal filter in the order of Core/Pipeline.cpp:3316-3400: temporal sets ping-ponged by frame parity
+    (:1858-1859).  Consumes `primary`, `gbuffer` and `reflection` of the same frame; `ctx.end_frame()` hands this frame's
+    G-buffer and reflection hit distance to the next one."""
+
+    STAGE_BYTES = {"temporal": 11 + 8 + 2 + 2 + 2 + 1 + 1 + 4 + 12}   # trace (8+2+1), history colour + hit distance, G-buffers, PBR, outputs (8+2+2)
+
+    def __init__(self, ctx: Context, width: int, height: int):
+        self.ctx, self.width, self.height = ctx, width, height
+        self.prev_cam = None
+
+    def prepare(self, cam: host_api.Camera, frame: int, tile=(0, 0), **flags):
+        lib = self.ctx._lib
+        prev = self.prev_cam or cam
+        self.prev_cam = cam
+        hist, out = (abi.ATT_REFL_TEMPORAL_B, abi.ATT_REFL_TEMPORAL_A) if frame % 2 == 0 else (abi.ATT_REFL_TEMPORAL_A, abi.ATT_REFL_TEMPORAL_B)
+        p = abi.SpecularTemporalParams()
+        _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
+        _fill(p.prev_view, prev.view); _fill(p.prev_projection, prev.projection)
+        _fill(p.current_camera_pos, np.asarray(cam.inv_view, dtype=np.float32).reshape(-1)[12:15])
+        _fill(p.prev_camera_pos, np.asarray(prev.inv_view, dtype=np.float32).reshape(-1)[12:15])
+        p.width, p.height, p.history_set, p.out_set = self.width, self.height, hist, out
+        for k, v in {"temporal_spec": 1, "firefly_rejection": 1, "aggressive_firefly_rejection": 1, "smart_clip": 1, "roughness_weight": 1,
+                     "stabilize_hit_distance": 1, **flags}.items():
+            setattr(p, k, int(v))
+        p.tile.row0, p.tile.rows = tile
+        self.out_set = out
+        return [("temporal", lib.vxrt_cuda_specular_temporal, p)]
+
+    def submit(self, prepared, hook=None):
+        import ctypes as C
+
+        for name, fn, params in prepared:
+            if hook:
+                hook(name, "begin")
+            self.ctx._check(fn(self.ctx._h, C.byref(params)))
+            if hook:
+                hook(name, "end")
+
+    def run(self, cam: host_api.Camera, frame: int, tile=(0, 0), hook=None):
+        self.submit(self.prepare(cam, frame, tile), hook)
