@@ -619,25 +619,30 @@ def main():
     if world_size == 1 and "reflection" in cfg.passes and not args.no_svgf:
         from voxeltracing_b200.pipeline import ReflectionTemporal
         # the temporal images of the engine are ReflectionSuperSampleResolution-sized; here they take the size of the trace
-        rt = ReflectionTemporal(ctx, W, H)
+        rt = ReflectionTemporal(ctx, W, H, denoise=True)
         rt_ev = []
         for k in range(12):
             cam = camera_for(wl, 3000 + k) if wl["camera"] != "rooms" else camera_for(wl, 0)
             fr.render(cam, 3000 + k)
             prep = rt.prepare(cam, k)
-            a, b = ev(), ev()
+            evs = {}
+
+            def hook(name, where, evs=evs):
+                e = ev(); e.record(stream)
+                evs.setdefault(name, []).append(e)
             flush_buf.zero_()
-            a.record(stream)
-            rt.submit(prep)
-            b.record(stream)
+            rt.submit(prep, hook=hook)
             ctx.end_frame()
-            rt_ev.append((a, b))
+            rt_ev.append(evs)
         torch.cuda.synchronize()
-        ms_stage = float(np.mean([a.elapsed_time(b) for a, b in rt_ev[4:]]))
-        by = ReflectionTemporal.STAGE_BYTES["temporal"] * W * H
-        refl_dn = {"ms_per_frame": ms_stage, "resolution": [W, H], "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms_stage * 1e-3) / 1e9,
-                   "frac_of_hbm_peak": by / (ms_stage * 1e-3) / 1e9 / measured_peaks()[0], "bytes_per_pixel": ReflectionTemporal.STAGE_BYTES["temporal"],
-                   "l2": "flushed before each launch"}
+        stages = {}
+        for key in ("temporal", "denoise_x", "denoise_y"):
+            ms_stage = float(np.mean([evs[key][0].elapsed_time(evs[key][1]) for evs in rt_ev[4:]]))
+            by = ReflectionTemporal.STAGE_BYTES[key] * W * H
+            stages[key] = {"ms_per_launch": ms_stage, "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms_stage * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": by / (ms_stage * 1e-3) / 1e9 / measured_peaks()[0]}
+        refl_dn = {"ms_per_frame": sum(st["ms_per_launch"] for st in stages.values()), "resolution": [W, H], "stages": stages,
+                   "bytes_per_pixel": ReflectionTemporal.STAGE_BYTES, "l2": "flushed before each frame's three launches"}
 
     # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera,
     # every output attachment read back to pinned host memory, inside the timed region ----
@@ -757,7 +762,7 @@ def main():
         if shadow_dn:
             line["shadow_denoiser"] = shadow_dn
         if refl_dn:
-            line["reflection_temporal"] = refl_dn
+            line["reflection_denoiser"] = refl_dn
         if world_size == 1 and not args.no_svgf:
             line["world_producers"] = world_producers_block(local_rank, stream, flush_buf, ev, peak)
         if not args.no_cpu_baseline and world_size == 1:

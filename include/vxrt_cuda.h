@@ -156,7 +156,9 @@ typedef enum vxrt_attachment {
     VXRT_ATT_REFL_TEMPORAL_A = 46,   /* ReflectionTemporalFBO_1: +0 colour RGBA16F, +1 accumulation factor R16F, +2 stabilised hit distance R16F */
     VXRT_ATT_REFL_TEMPORAL_B = 49,   /* ReflectionTemporalFBO_2 */
     VXRT_ATT_PREV_REFL_HITDIST = 52, /* previous frame's REFL_HITDIST (the engine ping-pongs ReflectionTraceFBO_1 / _2, :1864-1865); filled by vxrt_cuda_end_frame */
-    VXRT_ATT_COUNT = 53
+    VXRT_ATT_REFL_DENOISED_A = 53,   /* ReflectionDenoised_1: RGBA16F (x pass, :1193) */
+    VXRT_ATT_REFL_DENOISED_B = 54,   /* ReflectionDenoised_2: RGBA16F (y pass: the denoised reflections) */
+    VXRT_ATT_COUNT = 55
 } vxrt_attachment;
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
@@ -470,8 +472,7 @@ int vxrt_cuda_collect_lights(vxrt_ctx* ctx, int32_t* xyz_out, int32_t capacity, 
  * PREV_INITIAL_T / PREV_INITIAL_NORMAL, PREV_REFL_HITDIST and the previous frame's temporal set (ping-ponged by frame parity
  * like ReflectionTemporalFBO_1 / _2, :1858-1859; the history images start out zero-filled like the engine's FBOs).  Reprojects
  * along the reflected ray (hit-distance reprojection), clips the history to the 3 x 3 neighbourhood of the current trace
- * (ReflectionClipping), rejects fireflies next to emissive hits and writes out_set.  The spatial pass
- * (ReflectionDenoiserNew.glsl) is not covered yet.                                                                        */
+ * (ReflectionClipping), rejects fireflies next to emissive hits and writes out_set.                                        */
 typedef struct vxrt_specular_temporal_params {   /* Pipeline.cpp:3319-3359 */
     float inv_view[16], inv_projection[16];      /* u_InverseView, u_InverseProjection (v_RayOrigin = u_InverseView[3]) */
     float prev_view[16], prev_projection[16];    /* u_PrevView, u_PrevProjection */
@@ -487,6 +488,38 @@ typedef struct vxrt_specular_temporal_params {   /* Pipeline.cpp:3319-3359 */
     vxrt_tile tile;
 } vxrt_specular_temporal_params;
 int vxrt_cuda_specular_temporal(vxrt_ctx* ctx, const vxrt_specular_temporal_params* p);
+
+/* ---- reflection spatial denoiser: Core/Shaders/ReflectionDenoiserNew.glsl, the x and the y pass of
+ * Core/Pipeline.cpp:3404-3560 (DenoiseReflections && RoughReflections, USE_NEW_SPECULAR_SPATIAL) ----
+ * One direction of a separable bilateral filter (up to 33 taps) whose radius follows roughness, the reflected ray's length
+ * and the accumulation factor; weights from depth, face normal, normal-mapped normal, luminance and roughness.  Consumes
+ * INITIAL_T / INITIAL_NORMAL, GBUF_NORMAL / GBUF_PBR and the reflection temporal set of this frame (the block-id plane the
+ * shader binds only feeds a value it never reads).  The
+ * shader's jitter term (:204) truncates to 0 for every pixel and time, so u_Time is not a parameter.                      */
+typedef struct vxrt_reflection_denoise_params {
+    float inv_view[16], inv_projection[16];      /* u_InverseView, u_InverseProjection (v_RayOrigin = u_InverseView[3]) */
+    float view[16];                              /* u_View */
+    int32_t width, height;                       /* size of the output = u_Dimensions (:3426) */
+    int32_t in_attachment;                       /* u_InputTexture: the temporal set's colour (x pass), VXRT_ATT_REFL_DENOISED_A (y pass) */
+    int32_t out_attachment;                      /* VXRT_ATT_REFL_DENOISED_A (x pass) / _B (y pass) */
+    int32_t temporal_set;                        /* this frame's temporal set: u_Frames is its +1 image */
+    int32_t hit_distance_attachment;             /* u_SpecularHitData: temporal_set + 2 if TEMPORAL_SPEC && TemporallyStabializeHitDistance,
+                                                    else VXRT_ATT_REFL_HITDIST (:3466-3471) */
+    int32_t dir;                                 /* u_Dir: 1 = x pass, 0 = y pass */
+    int32_t roughness_bias;                      /* u_RoughnessBias (ReflectionRoughnessBias, true) */
+    int32_t normal_map_aware;                    /* u_NormalMapAware (ReflectionNormalMapWeight, true) */
+    int32_t handle_lobe_deviation;               /* u_HandleLobeDeviation (true) */
+    int32_t derive_from_diffuse_sh;              /* u_DeriveFromDiffuseSH (false) */
+    int32_t amplify_transversal_weight;          /* u_AmplifyReflectionTransversalWeight (true) */
+    int32_t temporal_weight;                     /* u_TemporalWeight (ReflectionTemporalWeight && TEMPORAL_SPEC, true) */
+    int32_t radius_bias;                         /* u_ReflectionDenoisingRadiusBias (0) */
+    float normal_map_weight_strength;            /* u_NormalMapWeightStrength (0.75) */
+    float denoiser_scale;                        /* u_ReflectionDenoiserScale (1.0) */
+    float resolution_scale;                      /* u_ResolutionScale (ReflectionSuperSampleResolution, 0.25) */
+    float roughness_normal_weight_bias_strength; /* u_RoughnessNormalWeightBiasStrength (1.075) */
+    vxrt_tile tile;
+} vxrt_reflection_denoise_params;
+int vxrt_cuda_reflection_denoise(vxrt_ctx* ctx, const vxrt_reflection_denoise_params* p);
 
 /* traversal statistics of the most recent pass run with stats enabled */
 typedef struct vxrt_trace_stats {

@@ -299,6 +299,28 @@ def specular_temporal(p: "abi.SpecularTemporalParams", cur: dict, prev_hitdist: 
     return out
 
 
+def reflection_denoise(p: "abi.ReflectionDenoiseParams", in_color: np.ndarray, frames: np.ndarray, hitdist: np.ndarray, f: dict, fn=None,
+                       time: float | None = None) -> np.ndarray:
+    """ReflectionDenoiserNew.glsl, one direction.  in_color: f16 (ih, iw, 4); frames: f16 u_Frames; hitdist: f16 u_SpecularHitData; f: the frame
+    {"g": {t, normal, block}, "gb_normal": f16 (mh, mw, 3), "pbr": u8 (mh, mw, 4)}.  Returns f16 (p.height, p.width, 4)."""
+    out = np.zeros((p.height, p.width, 4), np.float16)
+    ih, iw = in_color.shape[:2]
+    th, tw = frames.shape
+    hh, hw = hitdist.shape
+    gh, gw = f["g"]["t"].shape
+    mh, mw = f["pbr"].shape[:2]
+    c = np.ascontiguousarray
+    args = [C.byref(p), _p(c(in_color)), iw, ih, _p(c(frames)), _p(c(hitdist)), tw, th, hw, hh, _p(c(f["g"]["t"])), _p(c(f["g"]["normal"])),
+            _p(c(f["g"]["block"])), gw, gh, _p(c(f["gb_normal"])), _p(c(f["pbr"])), mw, mh, _p(out)]
+    if fn is None:
+        g = lib().vxo_reflection_denoise
+        g.restype = None
+        g(*args)
+    else:
+        fn(*args, C.c_float(12.345 if time is None else time))   # the compiled shader also takes u_Time
+    return out
+
+
 class OracleScene:
     """The GL resources the material / GI / reflection shaders bind, on top of an OracleWorld."""
 

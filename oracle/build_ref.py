@@ -45,6 +45,7 @@ SHADERS = {
     "ShadowFilter": ("ShadowFilter.glsl", "fragment"),
     # reflection temporal filter
     "SpecularTemporal": ("SpecularTemporalFilter.glsl", "fragment"),
+    "ReflectionDenoise": ("ReflectionDenoiserNew.glsl", "fragment"),
     # the colour pass composites sky / clouds / denoised GI (out of scope); only its Cook-Torrance
     # functions are compiled: they are cut out of the file by name, unmodified
     "ColorPassDirect": ("ColorPassFrag.glsl", "extract"),

@@ -57,6 +57,11 @@ thread_local uvec3 gl_GlobalInvocationID;
 #ifdef VXREF_HAVE_SpecularTemporal
 #include "SpecularTemporal.cpp"
 #endif
+#ifdef VXREF_HAVE_ReflectionDenoise
+#undef sqr
+#undef EPS
+#include "ReflectionDenoise.cpp"
+#endif
 #ifdef VXREF_HAVE_ColorPassDirect
 #include "ColorPassDirect.cpp"
 #endif
@@ -115,6 +120,9 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_SpecularTemporal
     m |= 32768;
+#endif
+#ifdef VXREF_HAVE_ReflectionDenoise
+    m |= 65536;
 #endif
 #ifdef VXREF_HAVE_RaycastDetect
     m |= 512;   /* World::RaycastDetect, host C++ lifted from Core/World.cpp (vxref_raycast_detect, generated unit) */
@@ -714,6 +722,47 @@ extern "C" void vxref_specular_temporal(const vxrt_specular_temporal_params* p, 
             for (int c = 0; c < 4; ++c) out_color_h4[4 * i + c] = vxo::float_to_half(S::o_Color[c]);
             out_frames[i] = vxo::float_to_half(S::o_AccumulatedFrames);
             out_hitdist[i] = vxo::float_to_half(S::o_HitDistanceStable);
+        }
+}
+#endif
+
+/* ---- reflection spatial denoiser (Core/Pipeline.cpp:3404-3560): one direction per call; `time` feeds u_Time, which the shader's
+ * jitter term consumes and then truncates away ---- */
+#ifdef VXREF_HAVE_ReflectionDenoise
+extern "C" void vxref_reflection_denoise(const vxrt_reflection_denoise_params* p, const uint16_t* in_color_h4, int iw, int ih, const uint16_t* frames,
+                                         const uint16_t* hitdist, int tw, int th, int hw, int hh, const uint16_t* g_t, const uint8_t* g_normal,
+                                         const uint8_t* g_block, int gw, int gh, const uint16_t* gb_normal_h3, const uint8_t* pbr_u8x4, int mw, int mh,
+                                         uint16_t* out_color_h4, float time) {
+    namespace S = shader_ReflectionDenoise;
+    const int W = p->width, H = p->height;
+    auto fc = svgf_half(in_color_h4, (size_t)iw * ih * 4), ffr = svgf_half(frames, (size_t)tw * th), fhd = svgf_half(hitdist, (size_t)hw * hh);
+    auto ft = svgf_half(g_t, (size_t)gw * gh), fn = svgf_u8(g_normal, (size_t)gw * gh), fb = svgf_u8(g_block, (size_t)gw * gh);
+    auto fgn = svgf_half(gb_normal_h3, (size_t)mw * mh * 3), fp = svgf_u8(pbr_u8x4, (size_t)mw * mh * 4);
+    bind2d(S::u_InputTexture, fc.data(), iw, ih, 4, true); bind2d(S::u_Frames, ffr.data(), tw, th, 1, true);
+    bind2d(S::u_SpecularHitData, fhd.data(), hw, hh, 1, true);
+    bind2d(S::u_PositionTexture, ft.data(), gw, gh, 1, true); bind2d(S::u_NormalTexture, fn.data(), gw, gh, 1, false);
+    bind2d(S::u_BlockIDTex, fb.data(), gw, gh, 1, false);
+    bind2d(S::u_GBufferNormals, fgn.data(), mw, mh, 3, true); bind2d(S::u_GBufferPBR, fp.data(), mw, mh, 4, true);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection); S::u_View.load(p->view);
+    S::u_Dir = p->dir != 0; S::u_RoughnessBias = p->roughness_bias != 0; S::u_NormalMapAware = p->normal_map_aware != 0;
+    S::u_HandleLobeDeviation = p->handle_lobe_deviation != 0; S::u_DeriveFromDiffuseSH = p->derive_from_diffuse_sh != 0;
+    S::u_AmplifyReflectionTransversalWeight = p->amplify_transversal_weight != 0; S::u_TemporalWeight = p->temporal_weight != 0;
+    S::u_Dimensions = vec2((float)W, (float)H); S::u_Step = 1; S::u_Time = time;
+    S::u_ReflectionDenoisingRadiusBias = p->radius_bias; S::u_NormalMapWeightStrength = p->normal_map_weight_strength;
+    S::u_ReflectionDenoiserScale = p->denoiser_scale; S::u_ResolutionScale = p->resolution_scale;
+    S::u_RoughnessNormalWeightBiasStrength = p->roughness_normal_weight_bias_strength;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam; S::v_RayDirection = vec3(0.0f, 0.0f, 1.0f);
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out_color_h4[4 * i + c] = vxo::float_to_half(S::o_SpatialResult[c]);
         }
 }
 #endif

@@ -136,6 +136,13 @@ void vxo_specular_temporal(const vxrt_specular_temporal_params* p, const uint16_
                            const uint8_t* prev_normal, int gw, int gh, const uint8_t* pbr_u8x4, int mw, int mh,
                            uint16_t* out_color_h4, uint16_t* out_frames, uint16_t* out_hitdist);
 
+/* ReflectionDenoiserNew.glsl main(): input colour (iw x ih), u_Frames (tw x th), u_SpecularHitData (hw x hh), primary G-buffer (gw x gh),
+ * GeneratedGBuffer normals RGB16F + PBR RGBA8 (mw x mh) */
+void vxo_reflection_denoise(const vxrt_reflection_denoise_params* p, const uint16_t* in_color_h4, int iw, int ih, const uint16_t* frames,
+                            const uint16_t* hitdist, int tw, int th, int hw, int hh, const uint16_t* g_t, const uint8_t* g_normal,
+                            const uint8_t* g_block, int gw, int gh, const uint16_t* gb_normal_h3, const uint8_t* pbr_u8x4, int mw, int mh,
+                            uint16_t* out_color_h4);
+
 /* ---- world producers (vxrt_oracle_world.cpp) ---- */
 /* FastNoise::GetNoise(x, y) for the Simplex (fractal = 0) / SimplexFractal FBM (fractal = 1) types; xy = 2*n floats */
 void vxo_fastnoise_2d(int32_t seed, int32_t fractal, float frequency, int32_t octaves, const float* xy, int32_t n, float* out);

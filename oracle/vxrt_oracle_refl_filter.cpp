@@ -206,3 +206,180 @@ extern "C" void vxo_specular_temporal(const vxrt_specular_temporal_params* p, co
             out_hitdist[i] = float_to_half(oHit);
         }
 }
+
+/* ReflectionDenoiserNew.glsl main() (:97-364): one direction of the separable bilateral filter of the reflection colour.
+ * `int Jitter = int((GradientNoise() - 0.5f) * 0.75f)` (:204) truncates a value in (-0.375, 0.375): it is 0 for every pixel and
+ * every u_Time, and `SampleCoord += Jitter * TexelSize * 0.75f` adds +0.0 — neither the noise nor u_Time reach the output. */
+extern "C" void vxo_reflection_denoise(const vxrt_reflection_denoise_params* p, const uint16_t* in_color_h4, int iw, int ih,
+                                       const uint16_t* frames, const uint16_t* hitdist, int tw, int th, int hw, int hh,
+                                       const uint16_t* g_t, const uint8_t* g_normal, const uint8_t* g_block, int gw, int gh,
+                                       const uint16_t* gb_normal_h3, const uint8_t* pbr_u8x4, int mw, int mh, uint16_t* out_color_h4) {
+    const int W = p->width, H = p->height;
+    auto fc = from_half(in_color_h4, (size_t)iw * ih * 4), ffr = from_half(frames, (size_t)tw * th), fhd = from_half(hitdist, (size_t)hw * hh);
+    auto ft = from_half(g_t, (size_t)gw * gh), fn = from_u8(g_normal, (size_t)gw * gh), fb = from_u8(g_block, (size_t)gw * gh);
+    auto fgn = from_half(gb_normal_h3, (size_t)mw * mh * 3), fp = from_u8(pbr_u8x4, (size_t)mw * mh * 4);
+    const Tex2D tIn = view(fc, iw, ih, 4, true), tFrames = view(ffr, tw, th, 1, true), tHit = view(fhd, hw, hh, 1, true);
+    const Tex2D tT = view(ft, gw, gh, 1, true), tN = view(fn, gw, gh, 1, false), tGN = view(fgn, mw, mh, 3, true), tPBR = view(fp, mw, mh, 4, true);
+    const v3 origin = V3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    static const float Gauss[33] = {0.004013f, 0.005554f, 0.007527f, 0.00999f, 0.012984f, 0.016524f, 0.020594f, 0.025133f, 0.030036f, 0.035151f, 0.040283f,
+                                    0.045207f, 0.049681f, 0.053463f, 0.056341f, 0.058141f, 0.058754f, 0.058141f, 0.056341f, 0.053463f, 0.049681f, 0.045207f,
+                                    0.040283f, 0.035151f, 0.030036f, 0.025133f, 0.020594f, 0.016524f, 0.012984f, 0.00999f, 0.007527f, 0.005554f, 0.004013f};
+    static const v3 Normals[7] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}, {1, 1, 1}};
+    const v3 LumaW = V3(0.299f, 0.587f, 0.114f);
+    auto block_id = [&](v2 c) {   /* GetBlockID (:79-83): texelFetch at ivec2(txc * size) */
+        const int x = (int)(c.x * (float)gw), y = (int)(c.y * (float)gh);
+        const float id = fb[(size_t)y * gw + x];
+        return iclamp((int)floorf(id * 255.0f), 0, 127);
+    };
+    const bool Dir = p->dir != 0;
+    const float EPS = 0.001f;
+    int r0, r1;
+    tile_rows(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const v2 tc = V2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            const float BaseDist = tex1(tT, tc);
+            const v3 BasePos = origin + normalize(ray_direction_at(p->inv_view, p->inv_projection, tc)) * BaseDist;
+            const v3 BaseNormal = Normals[normal_index(tex1(tN, tc))];
+            const int BaseBlockID = block_id(tc);
+            (void)BaseBlockID;   /* BlockValidity (:251) is computed and never used */
+            const bool BaseIsSky = BaseDist < 0.0f;
+            const v4 BaseColor = tex4(tIn, tc);
+            const float BaseLuminance = dot(xyz(BaseColor), LumaW);
+            float TotalWeight = 0.0f;
+            const float TexelSize = Dir ? 1.0f / (float)W : 1.0f / (float)H;   /* u_Dimensions = size of the output (Pipeline.cpp:3426) */
+            const v4 SampledPBR = tex4(tPBR, tc);
+            float BaseRoughness = SampledPBR.x;
+            const float RawRoughness = BaseRoughness;
+            BaseRoughness *= gmix(1.0f, 0.91f, p->roughness_bias ? 1.0f : 0.0f);
+            const v3 NormalMappedBase = xyz(tex4(tGN, tc));
+            float HitDistanceFetch = tex1(tHit, tc) + 0.0001f;
+            const float LobeDistanceCurveBias = 1.0f / 1.3f;
+            if (HitDistanceFetch < 0.001f) HitDistanceFetch = 1.75f;
+            else HitDistanceFetch = powf(HitDistanceFetch, LobeDistanceCurveBias);
+            if (p->handle_lobe_deviation) {
+                if (BaseRoughness <= 0.25f + 0.05f) HitDistanceFetch = gclamp(HitDistanceFetch, 0.0f, 8.0f);
+                if (BaseRoughness <= 0.2f) HitDistanceFetch = gclamp(HitDistanceFetch, 0.0f, 5.5f);
+            }
+            const float SpecularHitDistance = gmax(HitDistanceFetch, 0.01f) * (RawRoughness < 0.51f ? 0.5f : 0.85f);
+            const v4 vs = mat4_mul(p->view, V4(BasePos.x, BasePos.y, BasePos.z, 1.0f));
+            const float ViewLength = length(V3(vs.x, vs.y, vs.z));
+            float ViewLengthWeight = 0.001f + ViewLength;
+            if (BaseRoughness > 0.135f) ViewLengthWeight = gmax(ViewLengthWeight, 0.750f);
+            else ViewLengthWeight = gmax(ViewLengthWeight, 3.0f);
+            if (BaseRoughness < 0.125f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 6.0f);
+            else if (BaseRoughness < 0.25f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 8.0f + 1.0f);
+            else if (BaseRoughness < 0.5f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 16.0f);
+            else if (BaseRoughness < 0.75f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 24.0f);
+            else ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 32.0f);
+            float TransversalContrib = SpecularHitDistance / gmax((SpecularHitDistance + ViewLengthWeight), 0.00001f);
+            if (RawRoughness < 0.535f && p->amplify_transversal_weight && BaseDist < 50.0f) {
+                const float Remapped = (((RawRoughness - 0.0f) / (0.535f - 0.0f)) * (1.0f - 0.0f)) + 0.0f;   /* remap (:93-96) */
+                const float TransversalExponent = gmix(3.5f, 2.0f, powf(Remapped, 4.0f));
+                TransversalContrib = powf(TransversalContrib, TransversalExponent + 0.8125f);
+            }
+            const float RadiusExponent = powf((1.0f - BaseRoughness), 1.0f / 1.4f) * 5.0f;
+            const float Radius = gclamp(powf(gmix(1.0f * BaseRoughness, 1.0f, TransversalContrib), RadiusExponent), 0.0f, 1.0f);
+            const float NormalMapRadius = 1.0f - gclamp(powf(gmix(1.0f * BaseRoughness, 1.0f, TransversalContrib), RadiusExponent), 0.0f, 1.0f);
+            int EffectiveRadius = (int)floorf(Radius * 15.0f);
+            EffectiveRadius = iclamp(EffectiveRadius, 1, 15);
+            const bool BaseTooRough = BaseRoughness > 0.897511f;
+            EffectiveRadius = BaseTooRough ? 15 : EffectiveRadius;
+            float Scale = gmix(1.0f, 2.0f, gclamp(p->resolution_scale, 0.0000001f, 1.0f)) + 0.5f;
+            int RadiusBias = 0;
+            if (SampledPBR.y > 0.1f - EPS && BaseRoughness > 0.4f - EPS) RadiusBias += 2;
+            EffectiveRadius = iclamp(EffectiveRadius + RadiusBias + p->radius_bias, 1, 15);
+            if (RawRoughness >= 0.5f - 0.01f) EffectiveRadius += 1;
+            if (p->derive_from_diffuse_sh && RawRoughness >= 0.865f) { EffectiveRadius = 4; Scale *= 1.25f; }
+            Scale *= p->denoiser_scale;
+            float TemporalWeight = 0.0f, AccumulatedFramesClamped = 0.01f;
+            if (p->temporal_weight) {
+                const float AccumulatedFrames = tex1(tFrames, tc);
+                AccumulatedFramesClamped = AccumulatedFrames < -0.1f ? 0.0f : (1.0f - AccumulatedFrames);
+                AccumulatedFramesClamped = gclamp(AccumulatedFramesClamped, 0.000001f, 1.0f);
+                TemporalWeight = gclamp(AccumulatedFramesClamped * 0.85f, 0.0f, 1.0f);
+                float FLT_radius = (float)EffectiveRadius;
+                FLT_radius = gmix(FLT_radius, FLT_radius + 2.0f, AccumulatedFramesClamped * 1.05f);
+                EffectiveRadius = cvt_trunc(FLT_radius);
+            }
+            float HF_e = 64.0f * p->normal_map_weight_strength * 1.350f;
+            HF_e *= powf(NormalMapRadius, 1.0f / 1.33f);
+            float HF_WeightAdder = gmix(0.0f, 0.005f, BaseRoughness > 0.45f ? 1.0f : 0.0f);
+            HF_WeightAdder += gmix(0.0f, 0.0125f, BaseRoughness > 0.525f ? 1.0f : 0.0f);
+            HF_WeightAdder += gmix(0.0f, 0.022f, BaseRoughness > 0.625f ? 1.0f : 0.0f);
+            HF_WeightAdder += gmix(0.0f, 0.026f, BaseRoughness > 0.725f ? 1.0f : 0.0f);
+            HF_WeightAdder += gmix(0.0f, 0.031f, BaseRoughness > 0.75f ? 1.0f : 0.0f);
+            EffectiveRadius = iclamp(EffectiveRadius, 1, 15);
+            if (RawRoughness < 0.002f) EffectiveRadius = 0;
+            v4 Filtered = V4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int Sample = -EffectiveRadius; Sample <= EffectiveRadius; Sample++) {
+                const float SampleOffset = (float)Sample;
+                const v2 sc = Dir ? V2(tc.x + (SampleOffset * Scale * TexelSize), tc.y) : V2(tc.x, tc.y + (SampleOffset * Scale * TexelSize));
+                const float bias = 0.01f;
+                if (!(sc.x > 0.0f + bias && sc.x < 1.0f - bias && sc.y > 0.0f + bias && sc.y < 1.0f - bias)) continue;
+                const float SampleDepth = tex1(tT, sc);
+                const bool SampleIsSky = SampleDepth < 0.0f;
+                if (SampleIsSky != BaseIsSky) continue;
+                const v4 SampleData = tex4(tIn, sc);
+                const float DepthDifference = fabsf(SampleDepth - BaseDist) * 1.5f;
+                const float DepthWeight = powf(expf(-DepthDifference), 2.0f);
+                const v3 SampleNormal = Normals[normal_index(tex1(tN, sc))];
+                const float NormalWeight = powf(gmax(dot(BaseNormal, SampleNormal), 0.00000000001f), 32.0f);
+                float LuminanceWeight = 1.0f;
+                const float SampleRoughness = tex4(tPBR, sc).x;
+                const bool SampleTooRough = SampleRoughness >= 0.89f;
+                if (!SampleTooRough) {
+                    const float LumaAt = dot(xyz(SampleData), LumaW);
+                    float LuminanceError = 1.0f / fabsf(LumaAt - BaseLuminance);
+                    LuminanceError = powf(LuminanceError, 1.7f);
+                    const float LumaWeightExponent = gmix(0.001f, 8.0f, powf(SampleRoughness, 16.0f));
+                    LuminanceWeight = powf(LuminanceError, LumaWeightExponent + 0.8f);
+                    LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+                    LuminanceWeight = gmix(LuminanceWeight, 1.0f, TemporalWeight);
+                    LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+                }
+                float HFNormalWeight = 1.0f;
+                if (p->normal_map_aware && !SampleTooRough && BaseRoughness < 0.8f && AccumulatedFramesClamped <= 0.185f + 0.001f + 0.001f + 0.0001f) {
+                    const v3 NormalMapAt = xyz(tex4(tGN, sc));
+                    const float Angle = dot(NormalMapAt, NormalMappedBase);
+                    HFNormalWeight = powf(gclamp(Angle, 0.00000001f, 1.0f), HF_e);
+                    HFNormalWeight = gclamp(HFNormalWeight + (HF_WeightAdder * p->roughness_normal_weight_bias_strength * 1.4f), 0.00000000001f, 1.0f);
+                }
+                const float RoughnessError = fabsf(SampleRoughness - BaseRoughness);
+                float RoughnessTransversalWeight = 1.0f / RoughnessError;
+                RoughnessTransversalWeight = powf(RoughnessTransversalWeight, 12.0f);
+                RoughnessTransversalWeight = gclamp(RoughnessTransversalWeight, 0.00000000001f, 1.0f);
+                const float CurrentKernelWeight = Gauss[iclamp(16 + Sample, 0, 32)];
+                float CurrentWeight = 1.0f;
+                CurrentWeight *= DepthWeight;
+                CurrentWeight *= NormalWeight;
+                CurrentWeight *= HFNormalWeight;
+                CurrentWeight *= LuminanceWeight;
+                CurrentWeight *= RoughnessTransversalWeight;
+                CurrentWeight *= CurrentKernelWeight;
+                CurrentWeight = gclamp(CurrentWeight, 0.000000001f, 1.0f);
+                Filtered = V4(Filtered.x + SampleData.x * CurrentWeight, Filtered.y + SampleData.y * CurrentWeight, Filtered.z + SampleData.z * CurrentWeight,
+                              Filtered.w + SampleData.w * CurrentWeight);
+                TotalWeight += CurrentWeight;
+            }
+            const bool DoSpatial = !(RawRoughness < 0.002f);
+            v4 o;
+            if (TotalWeight > 0.001f && DoSpatial) {
+                Filtered = V4(Filtered.x / TotalWeight, Filtered.y / TotalWeight, Filtered.z / TotalWeight, Filtered.w / TotalWeight);
+                float Smooth = 1.0f;
+                if (BaseRoughness <= 0.1f + 0.007f) {
+                    Smooth = BaseRoughness * 16.0f;
+                    Smooth = 1.0f - Smooth;
+                    Smooth = powf(Smooth, 4.0f);
+                    Smooth = gclamp(Smooth, 0.1f, 0.999f);
+                }
+                o = V4(gmix(BaseColor.x, Filtered.x, Smooth), gmix(BaseColor.y, Filtered.y, Smooth), gmix(BaseColor.z, Filtered.z, Smooth), gmix(BaseColor.w, Filtered.w, Smooth));
+            } else {
+                o = BaseColor;
+            }
+            const size_t i = (size_t)py * W + px;
+            out_color_h4[4 * i] = float_to_half(o.x); out_color_h4[4 * i + 1] = float_to_half(o.y);
+            out_color_h4[4 * i + 2] = float_to_half(o.z); out_color_h4[4 * i + 3] = float_to_half(o.w);
+        }
+}

@@ -45,8 +45,15 @@ def frames(world_blocks):
         hit[(sel >= 0.15) & (sel < 0.18)] = 0.0
         pbr = np.zeros((H, W, 4), np.uint8)
         pbr[..., 0] = np.round(rough * 255); pbr[..., 1] = np.round(metal * 255); pbr[..., 2] = 128; pbr[..., 3] = 0
-        out.append({"cam": cam, "pos": np.array(pos, np.float32), "g": {"t": np.ascontiguousarray(g["t"]), "normal": np.ascontiguousarray(g["normal"])},
-                    "refl": {"color": color.astype(np.float16), "hitdist": hit.astype(np.float16), "mask": mask}, "pbr": pbr})
+        # normal-mapped normals of the material G-buffer: the face normal, perturbed
+        face = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [-1, 0, 0], [1, 0, 0], [1, 1, 1]], np.float32)
+        idx = np.minimum(np.round(g["normal"].astype(np.float32) / 255.0 * 10.0).astype(np.int32), 6)
+        nm = face[idx] + 0.25 * np.stack([_field(rng, H, W, 3, -1.0, 1.0) for _ in range(3)], axis=2)
+        nm /= np.linalg.norm(nm, axis=2, keepdims=True)
+        out.append({"cam": cam, "pos": np.array(pos, np.float32),
+                    "g": {"t": np.ascontiguousarray(g["t"]), "normal": np.ascontiguousarray(g["normal"]), "block": np.ascontiguousarray(g["block"])},
+                    "refl": {"color": color.astype(np.float16), "hitdist": hit.astype(np.float16), "mask": mask}, "pbr": pbr,
+                    "gb_normal": nm.astype(np.float16)})
     return out
 
 
@@ -86,3 +93,28 @@ def run_chain(seq, temporal_fn, **flags):
         outs.append(t)
         hist, prev, prev_g, prev_hit = t, f, f["g"], f["refl"]["hitdist"]
     return outs
+
+
+DENOISE_DEFAULTS = dict(roughness_bias=1, normal_map_aware=1, handle_lobe_deviation=1, derive_from_diffuse_sh=0, amplify_transversal_weight=1,
+                        temporal_weight=1, radius_bias=0, normal_map_weight_strength=0.75, denoiser_scale=1.0, resolution_scale=0.25,
+                        roughness_normal_weight_bias_strength=1.075)
+
+
+def denoise_params(f, direction: int, in_att: int, out_att: int, temporal_set: int, hit_att: int, **flags) -> abi.ReflectionDenoiseParams:
+    p = abi.ReflectionDenoiseParams()
+    su.fill(p.inv_view, f["cam"].inv_view); su.fill(p.inv_projection, f["cam"].inv_projection); su.fill(p.view, f["cam"].view)
+    p.width, p.height, p.in_attachment, p.out_attachment, p.temporal_set, p.hit_distance_attachment, p.dir = W, H, in_att, out_att, temporal_set, hit_att, direction
+    for k, v in {**DENOISE_DEFAULTS, **flags}.items():
+        setattr(p, k, v)
+    return p
+
+
+def run_denoise(f, temporal: dict, temporal_set: int, denoise_fn, stabilized: bool = True, **flags):
+    """x pass then y pass over one frame's temporal set (Pipeline.cpp:3404-3560); returns (x result, y result)."""
+    hit = temporal["hitdist"] if stabilized else f["refl"]["hitdist"]
+    hit_att = temporal_set + 2 if stabilized else abi.ATT_REFL_HITDIST
+    px = denoise_params(f, 1, temporal_set, abi.ATT_REFL_DENOISED_A, temporal_set, hit_att, **flags)
+    x = denoise_fn(px, temporal["color"], temporal["frames"], hit, f)
+    py = denoise_params(f, 0, abi.ATT_REFL_DENOISED_A, abi.ATT_REFL_DENOISED_B, temporal_set, hit_att, **flags)
+    y = denoise_fn(py, x, temporal["frames"], hit, f)
+    return x, y

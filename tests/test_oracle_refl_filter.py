@@ -59,3 +59,46 @@ def test_oracle_matches_golden(seq):
     for k, o in enumerate(rf.run_chain(seq, ob.specular_temporal)):
         for name in ("color", "frames", "hitdist"):
             assert np.array_equal(bits(o[name]), z[f"{name}{k}"]), (k, name)
+
+
+# ---- spatial pass: ReflectionDenoiserNew.glsl ----
+DENOISE_FLAG_SETS = [{}, {"temporal_weight": 0, "normal_map_aware": 0}, {"roughness_bias": 0, "handle_lobe_deviation": 0, "amplify_transversal_weight": 0},
+                     {"derive_from_diffuse_sh": 1, "radius_bias": 1, "denoiser_scale": 2.5}, {"resolution_scale": 1.0, "normal_map_weight_strength": 0.3}]
+
+
+@pytest.fixture(scope="module")
+def temporal_sets(seq):
+    return rf.run_chain(seq, ob.specular_temporal)
+
+
+def test_denoiser_filters(seq, temporal_sets):
+    k = 3
+    x, y = rf.run_denoise(seq[k], temporal_sets[k], rf.sets_for(k)[1], ob.reflection_denoise)
+    src = np.asarray(temporal_sets[k]["color"], np.float32)
+    xf, yf = np.asarray(x, np.float32), np.asarray(y, np.float32)
+    assert np.isfinite(yf).all() and (bits(x) != bits(temporal_sets[k]["color"])).mean() > 0.5 and (bits(y) != bits(x)).mean() > 0.5
+    # a weighted average never leaves the range of its inputs
+    assert yf.min() >= src.min() - 1e-3 and yf.max() <= src.max() + 1e-3
+    # smoothing: the filtered image has less high-frequency energy than its input
+    hf = lambda a: float(np.abs(np.diff(a[..., 0], axis=1)).mean())
+    assert hf(xf) < hf(src) and hf(yf) <= hf(xf) * 1.05
+
+
+@pytest.mark.skipif(not rb.available("reflection_denoise"), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("flags", DENOISE_FLAG_SETS)
+def test_denoiser_oracle_equals_compiled_reference_shader(seq, temporal_sets, flags):
+    L = rb.lib()
+    L.vxref_reflection_denoise.restype = None
+    for k, stabilized in ((1, True), (3, False), (4, True)):
+        a = rf.run_denoise(seq[k], temporal_sets[k], rf.sets_for(k)[1], ob.reflection_denoise, stabilized, **flags)
+        b = rf.run_denoise(seq[k], temporal_sets[k], rf.sets_for(k)[1], lambda *x: ob.reflection_denoise(*x, fn=L.vxref_reflection_denoise, time=3.7 * k),
+                           stabilized, **flags)
+        for name, x, y in (("x", a[0], b[0]), ("y", a[1], b[1])):
+            assert np.array_equal(bits(x), bits(y)), (flags, k, name, int((bits(x) != bits(y)).sum()))
+
+
+def test_denoiser_matches_golden(seq, temporal_sets):
+    z = np.load(GOLD)
+    for k in (1, 3, 4):
+        x, y = rf.run_denoise(seq[k], temporal_sets[k], rf.sets_for(k)[1], ob.reflection_denoise)
+        assert np.array_equal(bits(x), z[f"denoise_x{k}"]) and np.array_equal(bits(y), z[f"denoise_y{k}"]), k

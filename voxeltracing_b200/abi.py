@@ -30,6 +30,7 @@ ATT_PREV_INITIAL_T, ATT_PREV_INITIAL_NORMAL, ATT_PREV_INITIAL_BLOCK = 38, 39, 40
 ATT_SHADOW_TEMPORAL_A, ATT_SHADOW_TEMPORAL_B, ATT_SHADOW_FILTERED = 41, 43, 45
 # reflection temporal filter: temporal sets are (colour RGBA16F, accumulation factor R16F, stabilised hit distance R16F)
 ATT_REFL_TEMPORAL_A, ATT_REFL_TEMPORAL_B, ATT_PREV_REFL_HITDIST = 46, 49, 52
+ATT_REFL_DENOISED_A, ATT_REFL_DENOISED_B = 53, 54
 
 TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
@@ -144,6 +145,16 @@ class SpecularTemporalParams(C.Structure):
                 ("smart_clip", C.c_int32), ("roughness_weight", C.c_int32), ("stabilize_hit_distance", C.c_int32), ("tile", Tile)]
 
 
+class ReflectionDenoiseParams(C.Structure):
+    """vxrt_reflection_denoise_params"""
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("view", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+                ("in_attachment", C.c_int32), ("out_attachment", C.c_int32), ("temporal_set", C.c_int32), ("hit_distance_attachment", C.c_int32),
+                ("dir", C.c_int32), ("roughness_bias", C.c_int32), ("normal_map_aware", C.c_int32), ("handle_lobe_deviation", C.c_int32),
+                ("derive_from_diffuse_sh", C.c_int32), ("amplify_transversal_weight", C.c_int32), ("temporal_weight", C.c_int32),
+                ("radius_bias", C.c_int32), ("normal_map_weight_strength", C.c_float), ("denoiser_scale", C.c_float),
+                ("resolution_scale", C.c_float), ("roughness_normal_weight_bias_strength", C.c_float), ("tile", Tile)]
+
+
 class ShadowFilterParams(C.Structure):
     _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
                 ("in_set", C.c_int32), ("filter_scale", C.c_float), ("tile", Tile)]
@@ -227,6 +238,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_shadow_filter": (C.c_int, [vp, P(ShadowFilterParams)]),
         "vxrt_cuda_select_shadow": (C.c_int, [vp, i32]),
         "vxrt_cuda_specular_temporal": (C.c_int, [vp, P(SpecularTemporalParams)]),
+        "vxrt_cuda_reflection_denoise": (C.c_int, [vp, P(ReflectionDenoiseParams)]),
         "vxrt_cuda_write_attachment": (C.c_int, [vp, i32, i32, i32, i32, vp]),
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),

@@ -590,6 +590,12 @@ int vxrt_cuda_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params
     if (rc) return rc;
     return vxrt_launch_specular_temporal(c, *p);
 }
+int vxrt_cuda_reflection_denoise(vxrt_ctx* c, const vxrt_reflection_denoise_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_reflection_denoise(c, *p);
+}
 int vxrt_cuda_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
     int rc = check_frame(__func__, p->width, p->height, p->tile);

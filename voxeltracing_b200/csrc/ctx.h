@@ -151,6 +151,7 @@ int vxrt_launch_svgf_end_frame(vxrt_ctx* c);
 int vxrt_launch_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params& p);
 int vxrt_launch_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params& p);
 int vxrt_launch_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params& p);
+int vxrt_launch_reflection_denoise(vxrt_ctx* c, const vxrt_reflection_denoise_params& p);
 int vxrt_launch_generate_world(vxrt_ctx* c, const vxrt_worldgen_params& p);
 int vxrt_launch_import_sections(vxrt_ctx* c, const uint8_t* d_ids, const uint8_t* d_nibbles, const uint8_t* d_has_data,
                                 const int32_t* d_origins, int n, const int32_t origin[3], const uint8_t lut[256]);

@@ -203,6 +203,187 @@ __global__ void __launch_bounds__(256) specular_temporal_kernel(const __grid_con
     a.out_hit[i] = float_to_half_bits(oHit);
 }
 
+// ---- spatial pass: ReflectionDenoiserNew.glsl main() (:97-364), one direction per launch ------------------------------------
+struct ReflDenoiseArgs {
+    float inv_view[16], inv_proj[16], view[16];
+    int width, height, row0, row1;
+    int dir, roughness_bias, normal_map_aware, handle_lobe_deviation, derive_from_diffuse_sh, amplify, temporal_weight, radius_bias;
+    float normal_map_weight_strength, denoiser_scale, resolution_scale, rnw_bias_strength;
+    Img16 in_color;   // u_InputTexture RGBA16F
+    Img16 frames;     // u_Frames R16F
+    Img16 hit;        // u_SpecularHitData R16F
+    Img16 g_t;
+    Img8 g_n;         // (u_BlockIDTex only feeds BlockValidity (:251), which nothing reads)
+    Img16 gb_normal;  // GeneratedGBuffer[1] RGB16F
+    Img8 pbr;         // GeneratedGBuffer[2] RGBA8
+    uint16_t* __restrict__ out;
+};
+
+__constant__ float c_gauss[33] = {0.004013f, 0.005554f, 0.007527f, 0.00999f, 0.012984f, 0.016524f, 0.020594f, 0.025133f, 0.030036f, 0.035151f, 0.040283f,
+                                  0.045207f, 0.049681f, 0.053463f, 0.056341f, 0.058141f, 0.058754f, 0.058141f, 0.056341f, 0.053463f, 0.049681f, 0.045207f,
+                                  0.040283f, 0.035151f, 0.030036f, 0.025133f, 0.020594f, 0.016524f, 0.012984f, 0.00999f, 0.007527f, 0.005554f, 0.004013f};
+
+VXD f3 sample_rgb16(const Img16& im, const Tap& t) {
+    return F3(sample_rgb16_ch(im.p, t, 0), sample_rgb16_ch(im.p, t, 1), sample_rgb16_ch(im.p, t, 2));
+}
+VXD float luma(f3 c) { return dot(c, F3(0.299f, 0.587f, 0.114f)); }
+
+__global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_constant__ ReflDenoiseArgs a) {
+    __shared__ float lut[256];
+    fill_unorm_lut(lut);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    const f3 origin = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+    const float BaseDist = sample1(a.g_t, tc);
+    const f3 BasePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * BaseDist;
+    const int BaseNormal = normal_at(a.g_n, tc, lut);
+    const bool BaseIsSky = BaseDist < 0.0f;
+    const c4 BaseColor = sample4(a.in_color, tc);
+    const float BaseLuminance = luma(xyz(BaseColor));
+    float TotalWeight = 0.0f;
+    const bool Dir = a.dir != 0;
+    const float TexelSize = Dir ? 1.0f / (float)a.width : 1.0f / (float)a.height;   // u_Dimensions = the output's size
+    const f2 pxy = sample_pbr_xy(a.pbr, tc, lut);
+    float BaseRoughness = pxy.x;
+    const float RawRoughness = BaseRoughness;
+    BaseRoughness *= gmix(1.0f, 0.91f, a.roughness_bias ? 1.0f : 0.0f);
+    const f3 NormalMappedBase = sample_rgb16(a.gb_normal, make_tap(a.gb_normal.w, a.gb_normal.h, tc));
+    float HitDistanceFetch = sample1(a.hit, tc) + 0.0001f;
+    if (HitDistanceFetch < 0.001f) HitDistanceFetch = 1.75f;
+    else HitDistanceFetch = powf(HitDistanceFetch, 1.0f / 1.3f);
+    if (a.handle_lobe_deviation) {
+        if (BaseRoughness <= 0.25f + 0.05f) HitDistanceFetch = gclamp(HitDistanceFetch, 0.0f, 8.0f);
+        if (BaseRoughness <= 0.2f) HitDistanceFetch = gclamp(HitDistanceFetch, 0.0f, 5.5f);
+    }
+    const float SpecularHitDistance = gmax(HitDistanceFetch, 0.01f) * (RawRoughness < 0.51f ? 0.5f : 0.85f);
+    const f4 vs = mat4_mul(a.view, F4(BasePos.x, BasePos.y, BasePos.z, 1.0f));
+    const float ViewLength = length(F3(vs.x, vs.y, vs.z));
+    float ViewLengthWeight = 0.001f + ViewLength;
+    if (BaseRoughness > 0.135f) ViewLengthWeight = gmax(ViewLengthWeight, 0.750f);
+    else ViewLengthWeight = gmax(ViewLengthWeight, 3.0f);
+    if (BaseRoughness < 0.125f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 6.0f);
+    else if (BaseRoughness < 0.25f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 8.0f + 1.0f);
+    else if (BaseRoughness < 0.5f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 16.0f);
+    else if (BaseRoughness < 0.75f) ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 24.0f);
+    else ViewLengthWeight = gclamp(ViewLengthWeight, 0.000001f, 32.0f);
+    float TransversalContrib = SpecularHitDistance / gmax((SpecularHitDistance + ViewLengthWeight), 0.00001f);
+    if (RawRoughness < 0.535f && a.amplify && BaseDist < 50.0f) {
+        const float Remapped = (((RawRoughness - 0.0f) / (0.535f - 0.0f)) * (1.0f - 0.0f)) + 0.0f;   // remap (:93-96)
+        const float TransversalExponent = gmix(3.5f, 2.0f, powf(Remapped, 4.0f));
+        TransversalContrib = powf(TransversalContrib, TransversalExponent + 0.8125f);
+    }
+    const float RadiusExponent = powf((1.0f - BaseRoughness), 1.0f / 1.4f) * 5.0f;
+    const float RadiusPow = gclamp(powf(gmix(1.0f * BaseRoughness, 1.0f, TransversalContrib), RadiusExponent), 0.0f, 1.0f);
+    const float Radius = RadiusPow, NormalMapRadius = 1.0f - RadiusPow;
+    int EffectiveRadius = cvt_floor(Radius * 15.0f);
+    EffectiveRadius = iclamp(EffectiveRadius, 1, 15);
+    EffectiveRadius = BaseRoughness > 0.897511f ? 15 : EffectiveRadius;
+    float Scale = gmix(1.0f, 2.0f, gclamp(a.resolution_scale, 0.0000001f, 1.0f)) + 0.5f;
+    int RadiusBias = 0;
+    if (pxy.y > 0.1f - 0.001f && BaseRoughness > 0.4f - 0.001f) RadiusBias += 2;
+    EffectiveRadius = iclamp(EffectiveRadius + RadiusBias + a.radius_bias, 1, 15);
+    if (RawRoughness >= 0.5f - 0.01f) EffectiveRadius += 1;
+    if (a.derive_from_diffuse_sh && RawRoughness >= 0.865f) { EffectiveRadius = 4; Scale *= 1.25f; }
+    Scale *= a.denoiser_scale;
+    float TemporalWeight = 0.0f, AccumulatedFramesClamped = 0.01f;
+    if (a.temporal_weight) {
+        const float AccumulatedFrames = sample1(a.frames, tc);
+        AccumulatedFramesClamped = AccumulatedFrames < -0.1f ? 0.0f : (1.0f - AccumulatedFrames);
+        AccumulatedFramesClamped = gclamp(AccumulatedFramesClamped, 0.000001f, 1.0f);
+        TemporalWeight = gclamp(AccumulatedFramesClamped * 0.85f, 0.0f, 1.0f);
+        float FLT_radius = (float)EffectiveRadius;
+        FLT_radius = gmix(FLT_radius, FLT_radius + 2.0f, AccumulatedFramesClamped * 1.05f);
+        EffectiveRadius = __float2int_rz(FLT_radius);
+    }
+    float HF_e = 64.0f * a.normal_map_weight_strength * 1.350f;
+    HF_e *= powf(NormalMapRadius, 1.0f / 1.33f);
+    float HF_WeightAdder = BaseRoughness > 0.45f ? 0.005f : 0.0f;   // mix(0, c, float(cond)) is exactly c or 0
+    HF_WeightAdder += BaseRoughness > 0.525f ? 0.0125f : 0.0f;
+    HF_WeightAdder += BaseRoughness > 0.625f ? 0.022f : 0.0f;
+    HF_WeightAdder += BaseRoughness > 0.725f ? 0.026f : 0.0f;
+    HF_WeightAdder += BaseRoughness > 0.75f ? 0.031f : 0.0f;
+    const float HF_bias = HF_WeightAdder * a.rnw_bias_strength * 1.4f;
+    EffectiveRadius = iclamp(EffectiveRadius, 1, 15);
+    if (RawRoughness < 0.002f) EffectiveRadius = 0;
+    const bool hf_pixel = a.normal_map_aware && BaseRoughness < 0.8f && AccumulatedFramesClamped <= 0.185f + 0.001f + 0.001f + 0.0001f;
+    const bool same_m = a.gb_normal.w == a.pbr.w && a.gb_normal.h == a.pbr.h;   // both planes of the material G-buffer: one tap set-up
+    c4 Filtered; Filtered.x = Filtered.y = Filtered.z = Filtered.w = 0.0f;
+#pragma unroll 1
+    for (int Sample = -EffectiveRadius; Sample <= EffectiveRadius; ++Sample) {
+        const float step = ((float)Sample * Scale) * TexelSize;
+        const f2 sc = Dir ? F2(tc.x + step, tc.y) : F2(tc.x, tc.y + step);
+        const float bias = 0.01f;
+        if (!(sc.x > 0.0f + bias && sc.x < 1.0f - bias && sc.y > 0.0f + bias && sc.y < 1.0f - bias)) continue;
+        const float SampleDepth = sample1(a.g_t, sc);
+        if ((SampleDepth < 0.0f) != BaseIsSky) continue;
+        const c4 SampleData = sample4(a.in_color, sc);
+        const float DepthDifference = fabsf(SampleDepth - BaseDist) * 1.5f;
+        const float ed = expf(-DepthDifference);
+        const float DepthWeight = ed * ed;   // pow(x, 2.0f)
+        // pow(max(dot, 1e-11), 32): 0 (underflow), 1, or 3^32
+        const float nd = normal_dot(BaseNormal, normal_at(a.g_n, sc, lut));
+        const float NormalWeight = nd <= 0.0f ? 0.0f : (nd == 1.0f ? 1.0f : 1853020153315328.0f);
+        float LuminanceWeight = 1.0f;
+        const Tap tp = make_tap(a.pbr.w, a.pbr.h, sc);
+        const uint32_t* pp = reinterpret_cast<const uint32_t*>(a.pbr.p);
+        const float SampleRoughness = bl(tp, lut[__ldg(pp + tp.o00) & 255], lut[__ldg(pp + tp.o10) & 255], lut[__ldg(pp + tp.o01) & 255], lut[__ldg(pp + tp.o11) & 255]);
+        const bool SampleTooRough = SampleRoughness >= 0.89f;
+        if (!SampleTooRough) {
+            const float LumaAt = luma(xyz(SampleData));
+            float LuminanceError = 1.0f / fabsf(LumaAt - BaseLuminance);
+            LuminanceError = powf(LuminanceError, 1.7f);
+            const float LumaWeightExponent = gmix(0.001f, 8.0f, powf(SampleRoughness, 16.0f));
+            LuminanceWeight = powf(LuminanceError, LumaWeightExponent + 0.8f);
+            LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+            LuminanceWeight = gmix(LuminanceWeight, 1.0f, TemporalWeight);
+            LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+        }
+        float HFNormalWeight = 1.0f;
+        if (hf_pixel && !SampleTooRough) {
+            const f3 NormalMapAt = sample_rgb16(a.gb_normal, same_m ? tp : make_tap(a.gb_normal.w, a.gb_normal.h, sc));
+            const float Angle = dot(NormalMapAt, NormalMappedBase);
+            HFNormalWeight = powf(gclamp(Angle, 0.00000001f, 1.0f), HF_e);
+            HFNormalWeight = gclamp(HFNormalWeight + HF_bias, 0.00000000001f, 1.0f);
+        }
+        const float RoughnessError = fabsf(SampleRoughness - BaseRoughness);
+        float RoughnessTransversalWeight = 1.0f / RoughnessError;
+        RoughnessTransversalWeight = powf(RoughnessTransversalWeight, 12.0f);
+        RoughnessTransversalWeight = gclamp(RoughnessTransversalWeight, 0.00000000001f, 1.0f);
+        const float CurrentKernelWeight = c_gauss[iclamp(16 + Sample, 0, 32)];
+        float CurrentWeight = 1.0f;
+        CurrentWeight *= DepthWeight;
+        CurrentWeight *= NormalWeight;
+        CurrentWeight *= HFNormalWeight;
+        CurrentWeight *= LuminanceWeight;
+        CurrentWeight *= RoughnessTransversalWeight;
+        CurrentWeight *= CurrentKernelWeight;
+        CurrentWeight = gclamp(CurrentWeight, 0.000000001f, 1.0f);
+        Filtered.x += SampleData.x * CurrentWeight; Filtered.y += SampleData.y * CurrentWeight;
+        Filtered.z += SampleData.z * CurrentWeight; Filtered.w += SampleData.w * CurrentWeight;
+        TotalWeight += CurrentWeight;
+    }
+    c4 o = BaseColor;
+    if (TotalWeight > 0.001f && !(RawRoughness < 0.002f)) {
+        Filtered.x /= TotalWeight; Filtered.y /= TotalWeight; Filtered.z /= TotalWeight; Filtered.w /= TotalWeight;
+        float Smooth = 1.0f;
+        if (BaseRoughness <= 0.1f + 0.007f) {
+            Smooth = BaseRoughness * 16.0f;
+            Smooth = 1.0f - Smooth;
+            Smooth = powf(Smooth, 4.0f);
+            Smooth = gclamp(Smooth, 0.1f, 0.999f);
+        }
+        o.x = gmix(BaseColor.x, Filtered.x, Smooth); o.y = gmix(BaseColor.y, Filtered.y, Smooth);
+        o.z = gmix(BaseColor.z, Filtered.z, Smooth); o.w = gmix(BaseColor.w, Filtered.w, Smooth);
+    }
+    uint2 packed;
+    packed.x = (uint32_t)float_to_half_bits(o.x) | ((uint32_t)float_to_half_bits(o.y) << 16);
+    packed.y = (uint32_t)float_to_half_bits(o.z) | ((uint32_t)float_to_half_bits(o.w) << 16);
+    reinterpret_cast<uint2*>(a.out)[(size_t)py * a.width + px] = packed;
+}
+
 inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
     if (t.rows <= 0) { *r0 = 0; *r1 = height; }
     else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
@@ -275,6 +456,40 @@ int vxrt_launch_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_para
     if (a.row1 <= a.row0) return VXRT_OK;
     dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     specular_temporal_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_reflection_denoise(vxrt_ctx* c, const vxrt_reflection_denoise_params& p) {
+    static const char* fn = "vxrt_cuda_reflection_denoise";
+    if (p.out_attachment != VXRT_ATT_REFL_DENOISED_A && p.out_attachment != VXRT_ATT_REFL_DENOISED_B)
+        return vxrt_fail(VXRT_E_INVALID, "%s: out_attachment must be VXRT_ATT_REFL_DENOISED_A / _B", fn);
+    if (p.in_attachment == p.out_attachment) return vxrt_fail(VXRT_E_INVALID, "%s: in_attachment == out_attachment", fn);
+    if (!is_refl_set(p.temporal_set)) return vxrt_fail(VXRT_E_INVALID, "%s: temporal_set must be VXRT_ATT_REFL_TEMPORAL_A / _B", fn);
+    if (p.in_attachment < 0 || p.in_attachment >= VXRT_ATT_COUNT || p.hit_distance_attachment < 0 || p.hit_distance_attachment >= VXRT_ATT_COUNT)
+        return vxrt_fail(VXRT_E_INVALID, "%s: bad attachment id", fn);
+    ReflDenoiseArgs a;
+    int rc;
+    if ((rc = image_in(c, fn, p.in_attachment, 8, &a.in_color))) return rc;
+    if ((rc = image_in(c, fn, p.temporal_set + 1, 2, &a.frames))) return rc;
+    if ((rc = image_in(c, fn, p.hit_distance_attachment, 2, &a.hit))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_INITIAL_T, 2, &a.g_t))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_INITIAL_NORMAL, 1, &a.g_n))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_GBUF_NORMAL, 6, &a.gb_normal))) return rc;
+    if ((rc = image_in(c, fn, VXRT_ATT_GBUF_PBR, 4, &a.pbr))) return rc;
+    if ((rc = vxrt_ensure_attachment(c, p.out_attachment, p.width, p.height, 8))) return rc;
+    a.out = (uint16_t*)c->att[p.out_attachment].ptr;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; a.view[i] = p.view[i]; }
+    a.width = p.width; a.height = p.height;
+    a.dir = p.dir; a.roughness_bias = p.roughness_bias; a.normal_map_aware = p.normal_map_aware; a.handle_lobe_deviation = p.handle_lobe_deviation;
+    a.derive_from_diffuse_sh = p.derive_from_diffuse_sh; a.amplify = p.amplify_transversal_weight; a.temporal_weight = p.temporal_weight;
+    a.radius_bias = p.radius_bias; a.normal_map_weight_strength = p.normal_map_weight_strength; a.denoiser_scale = p.denoiser_scale;
+    a.resolution_scale = p.resolution_scale; a.rnw_bias_strength = p.roughness_normal_weight_bias_strength;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    reflection_denoise_kernel<<<grid, 256, 0, c->stream>>>(a);
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;

@@ -48,6 +48,7 @@ _ATT_DTYPES.update({abi.ATT_SHADOW_TEMPORAL_A: (np.uint8, 1), abi.ATT_SHADOW_TEM
 for _s in (abi.ATT_REFL_TEMPORAL_A, abi.ATT_REFL_TEMPORAL_B):
     _ATT_DTYPES.update({_s: (np.float16, 4), _s + 1: (np.float16, 1), _s + 2: (np.float16, 1)})
 _ATT_DTYPES[abi.ATT_PREV_REFL_HITDIST] = (np.float16, 1)
+_ATT_DTYPES.update({abi.ATT_REFL_DENOISED_A: (np.float16, 4), abi.ATT_REFL_DENOISED_B: (np.float16, 4)})
 # SVGF image sets (four consecutive ids): SH, CoCg, utility RGB16F (temporal sets) / variance R16F, AO + sky
 for _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_B):
     _ATT_DTYPES.update({_s: (np.float16, 4), _s + 1: (np.float16, 2),
@@ -269,6 +270,9 @@ class Context:
     # -- reflection temporal filter (Core/Pipeline.cpp:3316-3400) --
     def specular_temporal(self, params: "abi.SpecularTemporalParams"):
         self._check(self._lib.vxrt_cuda_specular_temporal(self._h, C.byref(params)))
+
+    def reflection_denoise(self, params: "abi.ReflectionDenoiseParams"):
+        self._check(self._lib.vxrt_cuda_reflection_denoise(self._h, C.byref(params)))
 
     def select_shadow(self, att: int):
         """The image the reflection / colour passes sample as the shadow texture (raw trace by default)."""

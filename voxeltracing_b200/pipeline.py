@@ -332,10 +332,13 @@ class ReflectionTemporal:
     (:1858-1859).  Consumes `primary`, `gbuffer` and `reflection` of the same frame; `ctx.end_frame()` hands this frame's
     G-buffer and reflection hit distance to the next one."""
 
-    STAGE_BYTES = {"temporal": 11 + 8 + 2 + 2 + 2 + 1 + 1 + 4 + 12}   # trace (8+2+1), history colour + hit distance, G-buffers, PBR, outputs (8+2+2)
+    # bytes read + written per pixel when each image is touched once.  temporal: trace (8+2+1), history colour + hit distance (8+2),
+    # previous hit distance 2, both G-buffers (2+1+2+1), PBR 4, outputs (8+2+2); denoise: colour in / out (8+8), frames 2, hit distance 2,
+    # G-buffer (2+1), material normals 6, PBR 4
+    STAGE_BYTES = {"temporal": 45, "denoise_x": 33, "denoise_y": 33}
 
-    def __init__(self, ctx: Context, width: int, height: int):
-        self.ctx, self.width, self.height = ctx, width, height
+    def __init__(self, ctx: Context, width: int, height: int, denoise: bool = True, resolution_scale: float = 0.25):
+        self.ctx, self.width, self.height, self.denoise, self.resolution_scale = ctx, width, height, denoise, resolution_scale
         self.prev_cam = None
 
     def prepare(self, cam: host_api.Camera, frame: int, tile=(0, 0), **flags):
@@ -354,7 +357,20 @@ class ReflectionTemporal:
             setattr(p, k, int(v))
         p.tile.row0, p.tile.rows = tile
         self.out_set = out
-        return [("temporal", lib.vxrt_cuda_specular_temporal, p)]
+        passes = [("temporal", lib.vxrt_cuda_specular_temporal, p)]
+        if self.denoise:   # x then y pass of ReflectionDenoiserNew.glsl (Pipeline.cpp:3404-3560)
+            stabilized = bool(p.temporal_spec and p.stabilize_hit_distance)
+            for name, direction, src, dst in (("denoise_x", 1, out, abi.ATT_REFL_DENOISED_A), ("denoise_y", 0, abi.ATT_REFL_DENOISED_A, abi.ATT_REFL_DENOISED_B)):
+                d = abi.ReflectionDenoiseParams()
+                _fill(d.inv_view, cam.inv_view); _fill(d.inv_projection, cam.inv_projection); _fill(d.view, cam.view)
+                d.width, d.height, d.in_attachment, d.out_attachment, d.temporal_set, d.dir = self.width, self.height, src, dst, out, direction
+                d.hit_distance_attachment = out + 2 if stabilized else abi.ATT_REFL_HITDIST
+                d.roughness_bias = d.normal_map_aware = d.handle_lobe_deviation = d.amplify_transversal_weight = 1
+                d.temporal_weight, d.derive_from_diffuse_sh, d.radius_bias = int(bool(p.temporal_spec)), 0, 0
+                d.normal_map_weight_strength, d.denoiser_scale, d.resolution_scale, d.roughness_normal_weight_bias_strength = 0.75, 1.0, self.resolution_scale, 1.075
+                d.tile.row0, d.tile.rows = tile
+                passes.append((name, lib.vxrt_cuda_reflection_denoise, d))
+        return passes
 
     def submit(self, prepared, hook=None):
         import ctypes as C
