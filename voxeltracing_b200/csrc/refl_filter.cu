@@ -227,6 +227,11 @@ VXD f3 sample_rgb16(const Img16& im, const Tap& t) {
     return F3(sample_rgb16_ch(im.p, t, 0), sample_rgb16_ch(im.p, t, 1), sample_rgb16_ch(im.p, t, 2));
 }
 VXD float luma(f3 c) { return dot(c, F3(0.299f, 0.587f, 0.114f)); }
+// pow(x, n) for the integer exponents of the shader, by multiplication (within the error of the general powf, whose accuracy the
+// reference leaves to the driver; inf and 0 behave like pow's)
+VXD float pow4(float x) { const float x2 = x * x; return x2 * x2; }
+VXD float pow12(float x) { const float x2 = x * x, x4 = x2 * x2; return (x4 * x4) * x4; }
+VXD float pow16(float x) { const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4; return x8 * x8; }
 
 __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_constant__ ReflDenoiseArgs a) {
     __shared__ float lut[256];
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_co
     float TransversalContrib = SpecularHitDistance / gmax((SpecularHitDistance + ViewLengthWeight), 0.00001f);
     if (RawRoughness < 0.535f && a.amplify && BaseDist < 50.0f) {
         const float Remapped = (((RawRoughness - 0.0f) / (0.535f - 0.0f)) * (1.0f - 0.0f)) + 0.0f;   // remap (:93-96)
-        const float TransversalExponent = gmix(3.5f, 2.0f, powf(Remapped, 4.0f));
+        const float TransversalExponent = gmix(3.5f, 2.0f, pow4(Remapped));
         TransversalContrib = powf(TransversalContrib, TransversalExponent + 0.8125f);
     }
     const float RadiusExponent = powf((1.0f - BaseRoughness), 1.0f / 1.4f) * 5.0f;
@@ -309,48 +314,68 @@ __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_co
     EffectiveRadius = iclamp(EffectiveRadius, 1, 15);
     if (RawRoughness < 0.002f) EffectiveRadius = 0;
     const bool hf_pixel = a.normal_map_aware && BaseRoughness < 0.8f && AccumulatedFramesClamped <= 0.185f + 0.001f + 0.001f + 0.0001f;
-    const bool same_m = a.gb_normal.w == a.pbr.w && a.gb_normal.h == a.pbr.h;   // both planes of the material G-buffer: one tap set-up
+    // The taps move along one axis only: the other axis of every sampler is set up once per pixel, and images of the same size
+    // (G-buffer planes; input colour; the two material planes) share the moving axis too.
+    const bool sameI = a.in_color.w == a.g_t.w && a.in_color.h == a.g_t.h, sameM = a.pbr.w == a.g_t.w && a.pbr.h == a.g_t.h;
+    const bool sameN = a.gb_normal.w == a.pbr.w && a.gb_normal.h == a.pbr.h;
+    const float fixed = Dir ? tc.y : tc.x, moving0 = Dir ? tc.x : tc.y;
+    const Axis fG = make_axis(Dir ? a.g_t.h : a.g_t.w, fixed);
+    const Axis fI = sameI ? fG : make_axis(Dir ? a.in_color.h : a.in_color.w, fixed);
+    const Axis fM = sameM ? fG : make_axis(Dir ? a.pbr.h : a.pbr.w, fixed);
+    const Axis fB = sameN ? fM : make_axis(Dir ? a.gb_normal.h : a.gb_normal.w, fixed);
+    const int fNrm = wrap_near(cvt_floor(fixed * (float)(Dir ? a.g_n.h : a.g_n.w)), Dir ? a.g_n.h : a.g_n.w);
+    const uint32_t* pp = reinterpret_cast<const uint32_t*>(a.pbr.p);
+    const float lw_of_one = gclamp(gmix(1.0f, 1.0f, TemporalWeight), 0.0000000001f, 1.0f);   // the luminance weight of a tap whose clamped pow() is 1
     c4 Filtered; Filtered.x = Filtered.y = Filtered.z = Filtered.w = 0.0f;
 #pragma unroll 1
     for (int Sample = -EffectiveRadius; Sample <= EffectiveRadius; ++Sample) {
-        const float step = ((float)Sample * Scale) * TexelSize;
-        const f2 sc = Dir ? F2(tc.x + step, tc.y) : F2(tc.x, tc.y + step);
+        const float m = moving0 + ((float)Sample * Scale) * TexelSize;
         const float bias = 0.01f;
-        if (!(sc.x > 0.0f + bias && sc.x < 1.0f - bias && sc.y > 0.0f + bias && sc.y < 1.0f - bias)) continue;
-        const float SampleDepth = sample1(a.g_t, sc);
+        if (!(m > 0.0f + bias && m < 1.0f - bias && fixed > 0.0f + bias && fixed < 1.0f - bias)) continue;
+        const Axis mG = make_axis(Dir ? a.g_t.w : a.g_t.h, m);
+        const float SampleDepth = sample_r16(a.g_t.p, Dir ? join_axes(mG, fG, a.g_t.w) : join_axes(fG, mG, a.g_t.w));
         if ((SampleDepth < 0.0f) != BaseIsSky) continue;
-        const c4 SampleData = sample4(a.in_color, sc);
+        const Axis mI = sameI ? mG : make_axis(Dir ? a.in_color.w : a.in_color.h, m);
+        float sd[4];
+        sample_rgba16(a.in_color.p, Dir ? join_axes(mI, fI, a.in_color.w) : join_axes(fI, mI, a.in_color.w), sd);
         const float DepthDifference = fabsf(SampleDepth - BaseDist) * 1.5f;
         const float ed = expf(-DepthDifference);
         const float DepthWeight = ed * ed;   // pow(x, 2.0f)
         // pow(max(dot, 1e-11), 32): 0 (underflow), 1, or 3^32
-        const float nd = normal_dot(BaseNormal, normal_at(a.g_n, sc, lut));
+        const int mNrm = wrap_near(cvt_floor(m * (float)(Dir ? a.g_n.w : a.g_n.h)), Dir ? a.g_n.w : a.g_n.h);
+        const int SampleNormal = normal_index(lut[__ldg(a.g_n.p + (Dir ? fNrm * a.g_n.w + mNrm : mNrm * a.g_n.w + fNrm))]);
+        const float nd = normal_dot(BaseNormal, SampleNormal);
         const float NormalWeight = nd <= 0.0f ? 0.0f : (nd == 1.0f ? 1.0f : 1853020153315328.0f);
         float LuminanceWeight = 1.0f;
-        const Tap tp = make_tap(a.pbr.w, a.pbr.h, sc);
-        const uint32_t* pp = reinterpret_cast<const uint32_t*>(a.pbr.p);
+        const Axis mM = sameM ? mG : make_axis(Dir ? a.pbr.w : a.pbr.h, m);
+        const Tap tp = Dir ? join_axes(mM, fM, a.pbr.w) : join_axes(fM, mM, a.pbr.w);
         const float SampleRoughness = bl(tp, lut[__ldg(pp + tp.o00) & 255], lut[__ldg(pp + tp.o10) & 255], lut[__ldg(pp + tp.o01) & 255], lut[__ldg(pp + tp.o11) & 255]);
         const bool SampleTooRough = SampleRoughness >= 0.89f;
         if (!SampleTooRough) {
-            const float LumaAt = luma(xyz(SampleData));
+            const float LumaAt = luma(F3(sd[0], sd[1], sd[2]));
             float LuminanceError = 1.0f / fabsf(LumaAt - BaseLuminance);
-            LuminanceError = powf(LuminanceError, 1.7f);
-            const float LumaWeightExponent = gmix(0.001f, 8.0f, powf(SampleRoughness, 16.0f));
-            LuminanceWeight = powf(LuminanceError, LumaWeightExponent + 0.8f);
-            LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
-            LuminanceWeight = gmix(LuminanceWeight, 1.0f, TemporalWeight);
-            LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+            if (LuminanceError >= 1.0f) {
+                // luminances less than 1 apart (every tap but fireflies): pow(x >= 1, y > 0) >= 1 twice, so the clamp yields exactly 1
+                LuminanceWeight = lw_of_one;
+            } else {
+                LuminanceError = powf(LuminanceError, 1.7f);
+                const float LumaWeightExponent = gmix(0.001f, 8.0f, pow16(SampleRoughness));
+                LuminanceWeight = powf(LuminanceError, LumaWeightExponent + 0.8f);
+                LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+                LuminanceWeight = gmix(LuminanceWeight, 1.0f, TemporalWeight);
+                LuminanceWeight = gclamp(LuminanceWeight, 0.0000000001f, 1.0f);
+            }
         }
         float HFNormalWeight = 1.0f;
         if (hf_pixel && !SampleTooRough) {
-            const f3 NormalMapAt = sample_rgb16(a.gb_normal, same_m ? tp : make_tap(a.gb_normal.w, a.gb_normal.h, sc));
+            const Axis mB = sameN ? mM : make_axis(Dir ? a.gb_normal.w : a.gb_normal.h, m);
+            const f3 NormalMapAt = sample_rgb16(a.gb_normal, sameN ? tp : (Dir ? join_axes(mB, fB, a.gb_normal.w) : join_axes(fB, mB, a.gb_normal.w)));
             const float Angle = dot(NormalMapAt, NormalMappedBase);
             HFNormalWeight = powf(gclamp(Angle, 0.00000001f, 1.0f), HF_e);
             HFNormalWeight = gclamp(HFNormalWeight + HF_bias, 0.00000000001f, 1.0f);
         }
         const float RoughnessError = fabsf(SampleRoughness - BaseRoughness);
-        float RoughnessTransversalWeight = 1.0f / RoughnessError;
-        RoughnessTransversalWeight = powf(RoughnessTransversalWeight, 12.0f);
+        float RoughnessTransversalWeight = pow12(1.0f / RoughnessError);
         RoughnessTransversalWeight = gclamp(RoughnessTransversalWeight, 0.00000000001f, 1.0f);
         const float CurrentKernelWeight = c_gauss[iclamp(16 + Sample, 0, 32)];
         float CurrentWeight = 1.0f;
@@ -361,8 +386,8 @@ __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_co
         CurrentWeight *= RoughnessTransversalWeight;
         CurrentWeight *= CurrentKernelWeight;
         CurrentWeight = gclamp(CurrentWeight, 0.000000001f, 1.0f);
-        Filtered.x += SampleData.x * CurrentWeight; Filtered.y += SampleData.y * CurrentWeight;
-        Filtered.z += SampleData.z * CurrentWeight; Filtered.w += SampleData.w * CurrentWeight;
+        Filtered.x += sd[0] * CurrentWeight; Filtered.y += sd[1] * CurrentWeight;
+        Filtered.z += sd[2] * CurrentWeight; Filtered.w += sd[3] * CurrentWeight;
         TotalWeight += CurrentWeight;
     }
     c4 o = BaseColor;
@@ -372,7 +397,7 @@ __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_co
         if (BaseRoughness <= 0.1f + 0.007f) {
             Smooth = BaseRoughness * 16.0f;
             Smooth = 1.0f - Smooth;
-            Smooth = powf(Smooth, 4.0f);
+            Smooth = pow4(Smooth);
             Smooth = gclamp(Smooth, 0.1f, 0.999f);
         }
         o.x = gmix(BaseColor.x, Filtered.x, Smooth); o.y = gmix(BaseColor.y, Filtered.y, Smooth);
