@@ -343,6 +343,66 @@ def world_producers_block(local_rank, stream, flush_buf, ev, peak):
             "l2": "flushed before each generate_world launch"}
 
 
+def lpv_block(local_rank, stream, flush_buf, ev, peak, with_cpu):
+    """Light propagation volume flood fill on its own context: the full repropagation of a world with lamps (start-up
+    sequence / World::RepropogateLPV_: clear both volumes = 2 N algorithmic bytes, light scan of the grid = N, then the waves) and one
+    block edit (a lamp placed, then broken); CUDA events on the stream, L2 flushed before every repropagation.  The CPU figure is the
+    oracle restatement of Core/VolumetricFloodFill.cpp (one thread, like the reference) on the same world."""
+    import torch
+
+    from voxeltracing_b200 import engine, host_api
+    c = engine.Context(local_rank)
+    c.set_stream(stream.cuda_stream)
+    nvox = c.nvox
+    blocks = host_api.gen_world("rooms", 2)
+    rng = np.random.default_rng(4)
+    nz, ny, nx = blocks.shape
+    n_lamps = 2000
+    blocks[rng.integers(1, nz, n_lamps), rng.integers(1, ny, n_lamps), rng.integers(1, nx, n_lamps)] = 12
+    table = np.full((6, 128), -1, dtype=np.int32)
+    table[3, 12] = 0
+    c.set_block_data(table)
+    c.upload_world(blocks)
+    out = {"world": f"stand-in:rooms(seed=2) + {n_lamps} lamps", "l2": "flushed before each repropagation"}
+    for limit in (4, 8):
+        c.lpv_repropagate(None, limit)
+        pairs = []
+        for _ in range(10):
+            flush_buf.zero_()
+            a, b = ev(), ev()
+            a.record(stream)
+            c.lpv_repropagate(None, limit)
+            b.record(stream)
+            pairs.append((a, b))
+        torch.cuda.synchronize()
+        us = float(np.median([a.elapsed_time(b) for a, b in pairs])) * 1e3
+        lit = int(np.count_nonzero(c.lpv_download()[0]))
+        alg = 3 * nvox + 4 * lit
+        out[f"repropagate_limit{limit}"] = {"us": us, "lit_voxels": lit, "launches": 1 + 3 + 1 + 4 * max(0, min(limit, 8) - 2), "algorithmic_bytes": alg,
+                                            "achieved_gbs": alg / (us * 1e-6) / 1e9, "frac_of_hbm_peak": alg / (us * 1e-6) / 1e9 / peak}
+    lamp = np.argwhere(blocks == 12)[len(np.argwhere(blocks == 12)) // 2]
+    z, y, x = (int(v) for v in lamp)
+    times = []
+    for _ in range(5):   # break the lamp, place it again (limit 8: the largest removal)
+        for op, blk in ((0, 0), (1, 12)):
+            c.edit_blocks(np.array([[x, y, z, blk]], dtype=np.int32))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c.lpv_edit(op, (x, y, z), 12, 8)
+            times.append((time.perf_counter() - t0) * 1e3)
+    out["edit_limit8"] = {"ms_break_lamp": float(np.median(times[0::2])), "ms_place_lamp": float(np.median(times[1::2])),
+                          "note": "wall clock around the synchronous ABI call; one warp replays the reference's queues in order"}
+    if with_cpu:
+        from oracle import world_binding as wb
+        lights = wb.collect_lights(blocks, table)
+        for limit in (4, 8):
+            t0 = time.perf_counter()
+            wb.lpv_repropagate(blocks, lights, limit)
+            out[f"repropagate_limit{limit}"]["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+    c.close()
+    return out
+
+
 def emit(line: dict):
     """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, which prints its version
     banner to stdout) writes to fd 1 has been redirected to stderr by quiet_stdout()."""
@@ -765,6 +825,7 @@ def main():
             line["reflection_denoiser"] = refl_dn
         if world_size == 1 and not args.no_svgf:
             line["world_producers"] = world_producers_block(local_rank, stream, flush_buf, ev, peak)
+            line["lpv"] = lpv_block(local_rank, stream, flush_buf, ev, peak, not args.no_cpu_baseline)
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_arm(blocks, wl, inputs)
             v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)

@@ -466,6 +466,26 @@ int vxrt_cuda_import_sections(vxrt_ctx* ctx, const uint8_t* block_ids /* n*4096 
  * number found, of which min(count, capacity) are written. */
 int vxrt_cuda_collect_lights(vxrt_ctx* ctx, int32_t* xyz_out, int32_t capacity, int32_t* count);
 
+/* ---- light propagation volume: Core/VolumetricFloodFill.cpp ----
+ * Two byte volumes of the grid's size, x-fastest like the grid: the light level (VolumetricFloodFillVolume, R8) and the block type of
+ * the lamp that lit the voxel (ColorDataFloodFillVolume, R8UI).  The reference floods them on the host with FIFO queues and mirrors
+ * every voxel with a 1-byte glTexSubImage3D (UploadLight :172-188); here they live in HBM and the flood fill runs on the device,
+ * reproducing the order of the reference's queues (the block type of a voxel depends on it).
+ *
+ * lpv_repropagate = the start-up sequence Core/Pipeline.cpp:1602-1611 and World::RepropogateLPV_ Core/World.cpp:554-572: both volumes
+ * cleared, every light location seeded with min(distance_limit, 8) (VoxelRT_FloodFillDistanceLimit, Pipeline.cpp:53) and the block at
+ * it, PropogateVolume.  lights_xyz: HOST memory, 3*n ints in queue order; NULL = the LightLocations scan of the device grid
+ * (vxrt_cuda_collect_lights order, at most 2^20 lights), consumed on the device without a round trip. */
+int vxrt_cuda_lpv_repropagate(vxrt_ctx* ctx, const int32_t* lights_xyz, int32_t n_lights, int32_t distance_limit);
+/* The light-volume half of a block edit in World::Raycast: op 1 = `block` was placed at (x, y, z) (Core/World.cpp:273-333), op 0 =
+ * `block` was broken there (:395-446); then 4 x DepropogateVolume + PropogateVolume (:482-485).  Call it after vxrt_cuda_edit_blocks
+ * has applied the edit to the grid (SetBlock precedes the propagation in the reference).  Whether `block` is a lamp comes from the
+ * emissive row of vxrt_cuda_set_block_data.  (x, y, z) must lie strictly inside the grid (:267-271), else VXRT_E_INVALID.          */
+int vxrt_cuda_lpv_edit(vxrt_ctx* ctx, int32_t op, int32_t x, int32_t y, int32_t z, int32_t block, int32_t distance_limit);
+/* The volumes to / from HOST memory (nx*ny*nz bytes each; download: either may be NULL).  Upload = Volumetrics::Reupload (:207-216). */
+int vxrt_cuda_lpv_download(vxrt_ctx* ctx, uint8_t* level, uint8_t* block_type);
+int vxrt_cuda_lpv_upload(vxrt_ctx* ctx, const uint8_t* level, const uint8_t* block_type);
+
 /* ---- reflection temporal filter: Core/Shaders/SpecularTemporalFilter.glsl, dispatched at
  * Core/Pipeline.cpp:3316-3400 ----
  * Consumes REFL_COLOR / REFL_HITDIST / REFL_EMISSIVE of vxrt_cuda_reflection_trace, INITIAL_T / INITIAL_NORMAL, GBUF_PBR,

@@ -12,6 +12,9 @@ stub declarations replacing the headers that drag in OpenGL).
     LCG); `srand(time(0))` becomes a no-op; the three function-local `static FastNoise` objects are made automatic so the
     function can be called with more than one seed triple per process.  World / Block are the minimal container the
     function needs (World.h:46-70: unchecked SetBlock / GetBlock over the x-fastest array).
+  * VolumetricFloodFill.h/.cpp: the OpenGL calls (texture mirrors of the two host arrays) become no-ops and World is
+    the read-only block array; the entry points replay the call sequences of Pipeline.cpp:1602-1611 / World.cpp:554-572 and of the
+    block edit in World.cpp:273-485 around the unmodified PropogateVolume / DepropogateVolume.
   * Importer.cpp: BlockDatabase::GetIDFromMCID answers from the 256-entry table the caller passes (the oracle and the
     product build that table from blockdb.txt, vxh_blockdb_minecraft_lut).
 """
@@ -144,6 +147,106 @@ extern "C" int32_t vxref_import_world(const char* dir, const float* origin3, con
     return out
 
 
+def gen_floodfill() -> Path:
+    hdr = body_after_includes((REF / "Core" / "VolumetricFloodFill.h").read_text(errors="replace"))
+    src = body_after_includes((REF / "Core" / "VolumetricFloodFill.cpp").read_text(errors="replace"))
+    gl_enums = ["GL_TEXTURE_3D", "GL_TEXTURE_MIN_FILTER", "GL_TEXTURE_MAG_FILTER", "GL_LINEAR", "GL_NEAREST", "GL_TEXTURE_WRAP_S",
+                "GL_TEXTURE_WRAP_T", "GL_TEXTURE_WRAP_R", "GL_CLAMP_TO_EDGE", "GL_RED", "GL_UNSIGNED_BYTE", "GL_R8UI", "GL_RED_INTEGER",
+                "GL_TRUE", "GL_READ_WRITE", "GL_R8", "GL_SHADER_IMAGE_ACCESS_BARRIER_BIT", "GL_SHADER_STORAGE_BUFFER", "GL_STATIC_DRAW",
+                "GL_TEXTURE4", "GL_TEXTURE_2D_ARRAY"]
+    gl_calls = ["glGenTextures", "glBindTexture", "glTexParameteri", "glTexImage3D", "glBindImageTexture", "glDispatchCompute",
+                "glMemoryBarrier", "glGenBuffers", "glBindBuffer", "glBufferData", "glActiveTexture", "glBindBufferBase", "glFinish",
+                "glTexSubImage3D"]
+    out = GEN / "VolumetricFloodFill.cpp"
+    out.write_text(f"""// GENERATED from Core/VolumetricFloodFill.h/.cpp by oracle/build_ref_world.py -- do not commit
+#include <stdint.h>
+#include <string.h>
+#include <array>
+#include <iostream>
+#include <memory>
+#include <queue>
+#include <glm/glm.hpp>
+{sizes()}
+// the OpenGL side of the file (texture creation, per-voxel glTexSubImage3D mirrors of the host arrays) is stubbed out: the arrays are
+// the authoritative state (Reupload copies them whole)
+typedef unsigned GLuint; typedef float GLfloat;
+enum {{ {", ".join(f"{e} = {i + 1}" for i, e in enumerate(gl_enums))} }};
+{chr(10).join(f"template <class... A> static void {c}(A...) {{}}" for c in gl_calls)}
+namespace GLClasses {{ struct ComputeShader {{ void CreateComputeShader(const char*) {{}} void Compile() {{}} void Use() {{}} void SetInteger(const char*, int) {{}} }}; }}
+namespace VoxelRT {{
+struct Block {{ uint8_t block; }};
+struct World {{
+    const Block* m_WorldData;
+    const Block& GetBlock(const glm::ivec3& p) {{ return m_WorldData[p.x + p.y * WORLD_SIZE_X + p.z * WORLD_SIZE_X * WORLD_SIZE_Y]; }}
+}};
+}}
+int VoxelRT_FloodFillDistanceLimit = 4;   // Pipeline.cpp:53
+{hdr}
+{src}
+namespace {{
+VoxelRT::World g_world;
+bool g_created = false;
+void bind(const uint8_t* blocks, int32_t limit) {{
+    g_world.m_WorldData = reinterpret_cast<const VoxelRT::Block*>(blocks);
+    VoxelRT_FloodFillDistanceLimit = limit;
+    if (!g_created) {{ VoxelRT::Volumetrics::CreateVolume(&g_world, 0, 0); g_created = true; }}
+    while (!VoxelRT::LightBFS.empty()) VoxelRT::LightBFS.pop();
+    while (!VoxelRT::LightRemovalBFS.empty()) VoxelRT::LightRemovalBFS.pop();
+}}
+const size_t kN = (size_t)WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z;
+}}
+// World::RepropogateLPV_ (World.cpp:554-572) / the start-up sequence Pipeline.cpp:1602-1611, `iterations` PropogateVolume calls
+extern "C" void vxref_lpv_repropagate(const uint8_t* blocks, const int32_t* xyz, int32_t n, int32_t limit, int32_t iterations,
+                                      uint8_t* level, uint8_t* color) {{
+    using namespace VoxelRT;
+    bind(blocks, limit);
+    Volumetrics::ClearEntireVolume();
+    for (int32_t i = 0; i < n; ++i) {{
+        const glm::ivec3 e(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        const uint8_t block_at = g_world.GetBlock(e).block;
+        Volumetrics::AddLightToVolume(e, block_at);
+    }}
+    for (int32_t i = 0; i < iterations; ++i) Volumetrics::PropogateVolume();
+    memcpy(level, WorldVolumetricDensityData->data(), kN);
+    memcpy(color, WorldVolumetricColorData->data(), kN);
+}}
+// the LPV statements of the block edit in World::Raycast, in the order of World.cpp:273-333 (op 1) and :395-446 (op 0), then :482-485
+extern "C" void vxref_lpv_edit(const uint8_t* blocks_after, int32_t op, int32_t x, int32_t y, int32_t z, int32_t block, int32_t emissive,
+                               int32_t limit, uint8_t* level, uint8_t* color) {{
+    using namespace VoxelRT;
+    bind(blocks_after, limit);
+    memcpy(WorldVolumetricDensityData->data(), level, kN);
+    memcpy(WorldVolumetricColorData->data(), color, kN);
+    const glm::vec3 position((float)x, (float)y, (float)z);
+    auto& LightRemovalBFS = Volumetrics::GetLightRemovalBFSQueue();
+    auto& LightPropogateBFS = Volumetrics::GetLightBFSQueue();
+    const float d[6][3] = {{{{1, 0, 0}}, {{-1, 0, 0}}, {{0, 1, 0}}, {{0, -1, 0}}, {{0, 0, 1}}, {{0, 0, -1}}}};
+    if (op == 1) {{
+        LightRemovalBFS.push(LightRemovalNode(glm::floor(position), Volumetrics::GetLightValue(glm::ivec3(glm::floor(position)))));
+        for (int k = 0; k < 6; ++k) {{
+            const glm::vec3 q = glm::floor(position + glm::vec3(d[k][0], d[k][1], d[k][2]));
+            LightRemovalBFS.push(LightRemovalNode(q, Volumetrics::GetLightValue(glm::ivec3(q))));
+        }}
+        if (emissive) Volumetrics::AddLightToVolume(glm::ivec3((int)position.x, (int)position.y, (int)position.z), (uint8_t)block);
+    }} else {{
+        if (emissive) {{
+            LightRemovalBFS.push(LightRemovalNode(glm::floor(position), Volumetrics::GetLightValue(glm::ivec3(glm::floor(position)))));
+            Volumetrics::SetLightValue(glm::ivec3(glm::floor(position)), 0, 0);
+            Volumetrics::UploadLight(glm::ivec3(glm::floor(position)), 0, 0, true);
+        }}
+        for (int k = 0; k < 6; ++k) LightPropogateBFS.push(LightNode(glm::floor(position + glm::vec3(d[k][0], d[k][1], d[k][2]))));
+    }}
+    for (int it = 0; it < 4; ++it) {{
+        Volumetrics::DepropogateVolume();
+        Volumetrics::PropogateVolume();
+    }}
+    memcpy(level, WorldVolumetricDensityData->data(), kN);
+    memcpy(color, WorldVolumetricColorData->data(), kN);
+}}
+""")
+    return out
+
+
 def main() -> int:
     force = "--force" in sys.argv
     if not REF.exists():
@@ -154,7 +257,8 @@ def main() -> int:
     enki = REF / "Dependencies" / "enkiMI"
     glm = REF / "Dependencies" / "glm"
     inputs = [Path(__file__), fn / "FastNoise.cpp", fn / "FastNoise.h", enki / "enkimi.c", enki / "enkimi.h", enki / "miniz.c", enki / "miniz.h",
-              REF / "Core" / "WorldGenerator.cpp", REF / "Core" / "NBT" / "Importer.cpp", REF / "Core" / "Macros.h"]
+              REF / "Core" / "WorldGenerator.cpp", REF / "Core" / "NBT" / "Importer.cpp", REF / "Core" / "Macros.h",
+              REF / "Core" / "VolumetricFloodFill.cpp", REF / "Core" / "VolumetricFloodFill.h"]
     if not all(p.exists() for p in inputs) or not (glm / "glm" / "glm.hpp").exists():
         print("[build_ref_world] reference sources missing; skipped")
         return 0
@@ -178,6 +282,7 @@ def main() -> int:
     compile_(CC + [f"-I{enki}"], enki / "miniz.c", "miniz.o")
     compile_(CXX + [f"-I{fn}", f"-I{glm}"], gen_worldgen(), "WorldGenerator.o")
     compile_(CXX + [f"-I{enki}", f"-I{glm}"], gen_importer(), "Importer.o")
+    compile_(CXX + [f"-I{glm}"], gen_floodfill(), "VolumetricFloodFill.o")
     r = subprocess.run(["g++", "-shared", "-o", str(LIB)] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         print(r.stderr[:4000])

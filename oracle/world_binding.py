@@ -36,6 +36,10 @@ def _oracle():
     L.vxo_import_sections.restype = None
     L.vxo_collect_lights.argtypes = [vp, i32, i32, i32, vp, vp, i32]
     L.vxo_collect_lights.restype = i32
+    L.vxo_lpv_repropagate.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp, vp]
+    L.vxo_lpv_repropagate.restype = None
+    L.vxo_lpv_edit.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.vxo_lpv_edit.restype = None
     return L
 
 
@@ -78,6 +82,24 @@ def collect_lights(blocks: np.ndarray, table: np.ndarray) -> np.ndarray:
     return out[:n]
 
 
+def lpv_repropagate(blocks: np.ndarray, lights: np.ndarray, limit: int = 4):
+    """Light level and block-type volumes after clear + seed + propagate (vxrt_oracle_lpv.cpp)."""
+    nz, ny, nx = blocks.shape
+    b = np.ascontiguousarray(blocks)
+    l = np.ascontiguousarray(lights, dtype=np.int32).reshape(-1, 3)
+    level, color = np.zeros_like(b), np.zeros_like(b)
+    _oracle().vxo_lpv_repropagate(_p(b), nx, ny, nz, _p(l), len(l), int(limit), _p(level), _p(color))
+    return level, color
+
+
+def lpv_edit(blocks_after: np.ndarray, op: int, xyz, block: int, emissive: bool, limit: int, level: np.ndarray, color: np.ndarray):
+    """The LPV half of one block edit, in place on level / color."""
+    nz, ny, nx = blocks_after.shape
+    b = np.ascontiguousarray(blocks_after)
+    assert level.flags.c_contiguous and color.flags.c_contiguous
+    _oracle().vxo_lpv_edit(_p(b), nx, ny, nz, int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(emissive), int(limit), _p(level), _p(color))
+
+
 # ---- the reference's own code (oracle/_ref) ----
 def ref_available() -> bool:
     return REF_LIB.exists()
@@ -94,6 +116,11 @@ def ref():
         L.vxref_fastnoise_2d.restype = None
         L.vxref_import_world.argtypes = [C.c_char_p, vp, vp, vp]
         L.vxref_import_world.restype = i32
+        if hasattr(L, "vxref_lpv_repropagate"):
+            L.vxref_lpv_repropagate.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+            L.vxref_lpv_repropagate.restype = None
+            L.vxref_lpv_edit.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+            L.vxref_lpv_edit.restype = None
         _ref = L
     return _ref
 
@@ -282,3 +309,19 @@ class PySections:
         if not ("x" in found and "z" in found and "s" in found):
             return None
         return found["x"], found["z"], sections
+
+
+def ref_lpv_repropagate(blocks: np.ndarray, lights: np.ndarray, limit: int = 4, iterations: int = 3):
+    """Core/VolumetricFloodFill.cpp as compiled, driven like Pipeline.cpp:1602-1611 / World::RepropogateLPV_ (384 x 128 x 384 only)."""
+    assert blocks.shape == (DIMS[2], DIMS[1], DIMS[0])
+    b = np.ascontiguousarray(blocks)
+    l = np.ascontiguousarray(lights, dtype=np.int32).reshape(-1, 3)
+    level, color = np.zeros_like(b), np.zeros_like(b)
+    ref().vxref_lpv_repropagate(_p(b), _p(l), len(l), int(limit), int(iterations), _p(level), _p(color))
+    return level, color
+
+
+def ref_lpv_edit(blocks_after: np.ndarray, op: int, xyz, block: int, emissive: bool, limit: int, level: np.ndarray, color: np.ndarray):
+    assert blocks_after.shape == (DIMS[2], DIMS[1], DIMS[0])
+    b = np.ascontiguousarray(blocks_after)
+    ref().vxref_lpv_edit(_p(b), int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(emissive), int(limit), _p(level), _p(color))

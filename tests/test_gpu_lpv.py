@@ -1,0 +1,160 @@
+"""Light propagation volume flood fill on the GPU through the C ABI: vxrt_cuda_lpv_repropagate (ordered level-synchronous
+flood fill) and vxrt_cuda_lpv_edit (the exact queue of the block edit) against the oracle and against the golden outputs of the
+reference's own Core/VolumetricFloodFill.cpp (tests/golden/lpv_ref.npz).  Byte work: bit-exact, both volumes."""
+import numpy as np
+import pytest
+
+import lpv_util as lu
+import world_util as wu
+from oracle import world_binding as wb
+from voxeltracing_b200 import engine
+
+pytestmark = pytest.mark.gpu
+TABLE = wu.emissive_table()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = engine.Context(0)
+    c.set_block_data(TABLE)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def case0():
+    blocks = lu.lamp_world(2, 400, "rooms")
+    return blocks, wb.collect_lights(blocks, TABLE)
+
+
+def test_repropagate_matches_golden_and_oracle(ctx, case0):
+    g = lu.golden()
+    blocks, lights = case0
+    ctx.upload_world(blocks)
+    for limit in (4, 8, 2, 3, 0, 11):
+        ctx.lpv_repropagate(None, limit)       # light list scanned on the device
+        level, color = ctx.lpv_download()
+        assert np.array_equal(lu.crc(level, color), g[f"c0_l{limit}_crc"]), limit
+        lo, co = wb.lpv_repropagate(blocks, lights, limit)
+        assert np.array_equal(level, lo) and np.array_equal(color, co), limit
+    ctx.lpv_repropagate(lights, 4)             # light list from the host
+    level, color = ctx.lpv_download()
+    assert np.array_equal(level, lu.dense(g["c0_l4_level_idx"], g["c0_l4_level_val"], blocks.shape))
+    assert np.array_equal(color, lu.dense(g["c0_l4_color_idx"], g["c0_l4_color_val"], blocks.shape))
+
+
+def test_repropagate_follows_the_queue_order(ctx, case0):
+    g = lu.golden()
+    blocks, lights = case0
+    ctx.upload_world(blocks)
+    ctx.lpv_repropagate(lights[::-1], 8)
+    assert np.array_equal(lu.crc(*ctx.lpv_download()), g["c0_rev_crc"])
+    rng = np.random.default_rng(3)
+    order = lights[rng.permutation(len(lights))]
+    order = np.concatenate([order, order[:50]])   # lights queued twice
+    ctx.lpv_repropagate(order, 7)
+    level, color = ctx.lpv_download()
+    lo, co = wb.lpv_repropagate(blocks, order, 7)
+    assert np.array_equal(level, lo) and np.array_equal(color, co)
+
+
+def test_repropagate_dense_lights(ctx):
+    g = lu.golden()
+    blocks = lu.lamp_world(1, 3000, "plains")
+    ctx.upload_world(blocks)
+    for limit in (4, 8):
+        ctx.lpv_repropagate(None, limit)
+        assert np.array_equal(lu.crc(*ctx.lpv_download()), g[f"c1_l{limit}_crc"]), limit
+    # a wall of lamps: frontiers of several hundred thousand voxels, many CTAs in the ordered compaction
+    blocks = np.zeros_like(blocks)
+    blocks[100:140, 30, :] = 12
+    blocks[100:140:3, 30, ::5] = 41
+    blocks[:, 90, 200] = 41
+    ctx.upload_world(blocks)
+    ctx.lpv_repropagate(None, 8)
+    level, color = ctx.lpv_download()
+    lo, co = wb.lpv_repropagate(blocks, wb.collect_lights(blocks, TABLE), 8)
+    assert np.array_equal(level, lo) and np.array_equal(color, co)
+
+
+def test_repropagate_edge_cases(ctx):
+    blocks = np.zeros((384, 128, 384), dtype=np.uint8).reshape(384, 128, 384)
+    ctx.upload_world(blocks)
+    ctx.lpv_repropagate(None, 8)               # no lights
+    level, color = ctx.lpv_download()
+    assert not level.any() and not color.any()
+    ctx.lpv_repropagate(np.zeros((0, 3), dtype=np.int32), 8)
+    assert not ctx.lpv_download()[0].any()
+    # lamps on and next to the faces, a lamp sealed in stone, lights given at air voxels and outside the grid
+    blocks[:, :50, :] = 3
+    for x, y, z in ((0, 60, 60), (1, 60, 90), (383, 60, 60), (60, 127, 60), (60, 0, 60), (60, 60, 0), (60, 60, 383), (200, 20, 200)):
+        blocks[z, y, x] = 12
+    ctx.upload_world(blocks)
+    lights = np.concatenate([wb.collect_lights(blocks, TABLE), np.array([[100, 100, 100], [-1, 5, 5], [400, 5, 5]], dtype=np.int32)])
+    ctx.lpv_repropagate(lights, 8)
+    level, color = ctx.lpv_download()
+    lo, co = wb.lpv_repropagate(blocks, lights, 8)
+    assert np.array_equal(level, lo) and np.array_equal(color, co)
+    assert level[200, 20, 200] == 8 and level[200, 21, 200] == 0
+    with pytest.raises(engine.VxrtError):
+        ctx.lpv_repropagate(None, -1)
+
+
+def test_repropagate_other_dims():
+    dims = (64, 48, 32)
+    c = engine.Context(0, dims)
+    c.set_block_data(TABLE)
+    rng = np.random.default_rng(9)
+    blocks = (rng.random((dims[2], dims[1], dims[0])) < 0.3).astype(np.uint8) * 3
+    for _ in range(40):
+        blocks[rng.integers(0, dims[2]), rng.integers(0, dims[1]), rng.integers(0, dims[0])] = 12
+    c.upload_world(blocks)
+    c.lpv_repropagate(None, 8)
+    level, color = c.lpv_download()
+    lo, co = wb.lpv_repropagate(blocks, wb.collect_lights(blocks, TABLE), 8)
+    assert np.array_equal(level, lo) and np.array_equal(color, co)
+    c.close()
+
+
+def test_edit_sequence_matches_golden_and_oracle(ctx, case0):
+    g = lu.golden()
+    blocks, lights = case0
+    for limit in (8, 4):
+        b = blocks.copy()
+        ctx.upload_world(b)
+        ctx.lpv_repropagate(None, limit)
+        lo, co = wb.lpv_repropagate(b, lights, limit)
+        for k, e in enumerate(lu.edit_sequence(blocks, TABLE, 48, seed=5)):
+            op, (x, y, z), blk, emissive = e
+            lu.apply_edit(b, e)
+            ctx.edit_blocks(np.array([[x, y, z, blk if op == 1 else 0]], dtype=np.int32))
+            ctx.lpv_edit(op, (x, y, z), blk, limit)
+            wb.lpv_edit(b, op, (x, y, z), blk, emissive, limit, lo, co)
+            if k % 6 == 5 or k == 47:
+                level, color = ctx.lpv_download()
+                assert np.array_equal(level, lo) and np.array_equal(color, co), (limit, k, e)
+                assert np.array_equal(lu.crc(level, color), g[f"edit_l{limit}_crc"][k]), (limit, k)
+    level, color = ctx.lpv_download()
+    assert np.array_equal(level, lu.dense(g["edit_l4_level_idx"], g["edit_l4_level_val"], blocks.shape))
+    assert np.array_equal(color, lu.dense(g["edit_l4_color_idx"], g["edit_l4_color_val"], blocks.shape))
+
+
+def test_edit_after_upload_and_argument_checks(ctx, case0):
+    blocks, lights = case0
+    b = blocks.copy()
+    ctx.upload_world(b)
+    lo, co = wb.lpv_repropagate(b, lights[::-1], 8)
+    ctx.lpv_upload(lo, co)                     # Volumetrics::Reupload: volumes handed over by the caller
+    e = (1, (int(lights[5][0]) + 2, int(lights[5][1]), int(lights[5][2])), 41, True)
+    if b[e[1][2], e[1][1], e[1][0]] == 0:
+        lu.apply_edit(b, e)
+        ctx.edit_blocks(np.array([[*e[1], 41]], dtype=np.int32))
+        ctx.lpv_edit(1, e[1], 41, 8)
+        wb.lpv_edit(b, 1, e[1], 41, True, 8, lo, co)
+    level, color = ctx.lpv_download()
+    assert np.array_equal(level, lo) and np.array_equal(color, co)
+    for bad in ((0, 5, 5), (5, 0, 5), (5, 5, 0), (384, 5, 5), (5, 128, 5), (5, 5, 384)):
+        with pytest.raises(engine.VxrtError):
+            ctx.lpv_edit(1, bad, 12, 8)
+    with pytest.raises(engine.VxrtError):
+        ctx.lpv_edit(2, (5, 5, 5), 12, 8)

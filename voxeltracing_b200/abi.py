@@ -252,6 +252,10 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_generate_world": (C.c_int, [vp, P(WorldGenParams)]),
         "vxrt_cuda_import_sections": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, i32]),
         "vxrt_cuda_collect_lights": (C.c_int, [vp, vp, i32, P(i32)]),
+        "vxrt_cuda_lpv_repropagate": (C.c_int, [vp, vp, i32, i32]),
+        "vxrt_cuda_lpv_edit": (C.c_int, [vp, i32, i32, i32, i32, i32, i32]),
+        "vxrt_cuda_lpv_download": (C.c_int, [vp, vp, vp]),
+        "vxrt_cuda_lpv_upload": (C.c_int, [vp, vp, vp]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),
         "vxrt_cuda_stats_read": (C.c_int, [vp, P(TraceStats), i32]),
         "vxrt_cuda_gather_peak": (C.c_int, [vp, i32, P(C.c_double)]),

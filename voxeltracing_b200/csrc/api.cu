@@ -140,6 +140,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
+    cudaFree(c->d_lpv); cudaFree(c->d_lpv_work);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
@@ -717,6 +718,78 @@ int vxrt_cuda_collect_lights(vxrt_ctx* c, int32_t* xyz_out, int32_t capacity, in
         VX_CUDA(cudaMemcpyAsync(xyz_out, d_out, wr * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         VX_CUDA(cudaStreamSynchronize(c->stream));
     }
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_repropagate(vxrt_ctx* c, const int32_t* lights_xyz, int32_t n_lights, int32_t distance_limit) {
+    REQUIRE_CTX(c);
+    if (distance_limit < 0 || distance_limit > 255) return vxrt_fail(VXRT_E_INVALID, "lpv_repropagate: distance_limit out of range");
+    if (n_lights < 0) return vxrt_fail(VXRT_E_INVALID, "lpv_repropagate: n_lights < 0");
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "lpv_repropagate before a world exists");
+    const int chunks = vxrt_lights_chunks(c);
+    const size_t b_counts = ((size_t)(chunks + 2) * sizeof(unsigned) + 255) / 256 * 256;
+    int rc;
+    if (lights_xyz) {
+        rc = ensure_staging(c, b_counts + (size_t)(n_lights > 0 ? n_lights : 1) * 3 * sizeof(int32_t));
+        if (rc) return rc;
+        unsigned* d_count = (unsigned*)c->d_ray_buf;
+        int32_t* d_lights = (int32_t*)((uint8_t*)c->d_ray_buf + b_counts);
+        const unsigned n = (unsigned)n_lights;
+        VX_CUDA(cudaMemcpyAsync(d_count, &n, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+        if (n_lights) VX_CUDA(cudaMemcpyAsync(d_lights, lights_xyz, (size_t)n_lights * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        rc = vxrt_launch_lpv_repropagate(c, d_lights, d_count, n_lights, distance_limit);
+        if (rc) return rc;
+        VX_CUDA(cudaStreamSynchronize(c->stream));   // host buffers are only borrowed for the call
+    } else {
+        // the light list of LoadWorld, scanned on the device and consumed there: nothing comes back to the host
+        const int capacity = 1 << 20;
+        rc = ensure_staging(c, b_counts + (size_t)capacity * 3 * sizeof(int32_t));
+        if (rc) return rc;
+        unsigned* d_counts = (unsigned*)c->d_ray_buf;
+        int32_t* d_lights = (int32_t*)((uint8_t*)c->d_ray_buf + b_counts);
+        rc = vxrt_launch_collect_lights(c, d_counts, d_lights, capacity);
+        if (rc) return rc;
+        rc = vxrt_launch_lpv_repropagate(c, d_lights, d_counts + chunks, capacity, distance_limit);
+        if (rc) return rc;
+    }
+    c->lpv_valid = true;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_edit(vxrt_ctx* c, int32_t op, int32_t x, int32_t y, int32_t z, int32_t block, int32_t distance_limit) {
+    REQUIRE_CTX(c);
+    if (op != 0 && op != 1) return vxrt_fail(VXRT_E_INVALID, "lpv_edit: op must be 0 (break) or 1 (place)");
+    if (distance_limit < 0 || distance_limit > 255) return vxrt_fail(VXRT_E_INVALID, "lpv_edit: distance_limit out of range");
+    if (block < 0 || block > 255) return vxrt_fail(VXRT_E_INVALID, "lpv_edit: block id out of range");
+    // World::Raycast returns before touching anything when the voxel is on or outside the faces of the grid (World.cpp:267-271)
+    if (x <= 0 || y <= 0 || z <= 0 || x >= c->nx || y >= c->ny || z >= c->nz) return vxrt_fail(VXRT_E_INVALID, "lpv_edit: position not strictly inside the grid");
+    if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "lpv_edit before a world exists");
+    int overflowed = 0;
+    int rc = vxrt_launch_lpv_edit(c, op, x, y, z, block, distance_limit, &overflowed);
+    if (rc) return rc;
+    if (overflowed) return vxrt_fail(VXRT_E_NOMEM, "lpv_edit: queue capacity exceeded");
+    c->lpv_valid = true;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_download(vxrt_ctx* c, uint8_t* level, uint8_t* block_type) {
+    REQUIRE_CTX(c);
+    int rc = vxrt_lpv_ensure(c);
+    if (rc) return rc;
+    if (level) VX_CUDA(cudaMemcpyAsync(level, c->d_lpv, c->nvox, cudaMemcpyDeviceToHost, c->stream));
+    if (block_type) VX_CUDA(cudaMemcpyAsync(block_type, c->d_lpv + c->nvox, c->nvox, cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_upload(vxrt_ctx* c, const uint8_t* level, const uint8_t* block_type) {
+    REQUIRE_CTX(c); REQUIRE_PTR(level); REQUIRE_PTR(block_type);
+    int rc = vxrt_lpv_ensure(c);
+    if (rc) return rc;
+    VX_CUDA(cudaMemcpyAsync(c->d_lpv, level, c->nvox, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(c->d_lpv + c->nvox, block_type, c->nvox, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->lpv_valid = true;
     return VXRT_OK;
 }
 

@@ -85,6 +85,10 @@ struct vxrt_ctx {
     int32_t* d_edit_buf = nullptr;
     size_t edit_cap = 0;
 
+    uint8_t* d_lpv = nullptr;       // light propagation volume (lpv.cu): light level [nvox], then block type [nvox]
+    void* d_lpv_work = nullptr;     // claim keys, the two frontiers / edit queues, scan scratch
+    bool lpv_valid = false;
+
     void* d_ray_buf = nullptr;  // staging of vxrt_cuda_trace_rays: origins | directions | hits
     size_t ray_cap = 0;
 
@@ -157,6 +161,9 @@ int vxrt_launch_import_sections(vxrt_ctx* c, const uint8_t* d_ids, const uint8_t
                                 const int32_t* d_origins, int n, const int32_t origin[3], const uint8_t lut[256]);
 int vxrt_lights_chunks(const vxrt_ctx* c);
 int vxrt_launch_collect_lights(vxrt_ctx* c, unsigned* d_counts, int32_t* d_out, int capacity);
+int vxrt_lpv_ensure(vxrt_ctx* c);
+int vxrt_launch_lpv_repropagate(vxrt_ctx* c, const int32_t* d_lights, const unsigned* d_count, int capacity, int limit);
+int vxrt_launch_lpv_edit(vxrt_ctx* c, int op, int x, int y, int z, int block, int limit, int* overflowed);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);
 // host-side evaluation of texture(u_Skymap, dir) on the context's copy of the sky (resources.cu)

@@ -382,6 +382,33 @@ class Context:
             return self.collect_lights(n.value)
         return out[: n.value].copy()
 
+    # -- light propagation volume (Core/VolumetricFloodFill.cpp) --
+    def lpv_repropagate(self, lights=None, distance_limit: int = 4):
+        """Start-up sequence Core/Pipeline.cpp:1602-1611 / World::RepropogateLPV_ (Core/World.cpp:554-572).  lights: (n,3) int32 voxel
+        coordinates in queue order, or None for the LightLocations scan of the device grid."""
+        if lights is None:
+            self._check(self._lib.vxrt_cuda_lpv_repropagate(self._h, None, 0, int(distance_limit)))
+            return
+        l = np.ascontiguousarray(lights, dtype=np.int32).reshape(-1, 3)
+        self._check(self._lib.vxrt_cuda_lpv_repropagate(self._h, _p(l) if len(l) else _p(np.zeros(3, dtype=np.int32)), len(l), int(distance_limit)))
+
+    def lpv_edit(self, op: int, xyz, block: int, distance_limit: int = 4):
+        """The light-volume half of one block edit (Core/World.cpp:273-333 place, :395-446 break, :482-485); the grid already holds the edit."""
+        self._check(self._lib.vxrt_cuda_lpv_edit(self._h, int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(distance_limit)))
+
+    def lpv_download(self):
+        """(level, block_type) volumes indexed [z, y, x]."""
+        nx, ny, nz = self.dims
+        level = np.zeros((nz, ny, nx), dtype=np.uint8)
+        color = np.zeros_like(level)
+        self._check(self._lib.vxrt_cuda_lpv_download(self._h, _p(level), _p(color)))
+        return level, color
+
+    def lpv_upload(self, level: np.ndarray, block_type: np.ndarray):
+        l, b = np.ascontiguousarray(level, dtype=np.uint8), np.ascontiguousarray(block_type, dtype=np.uint8)
+        assert l.size == self.dims[0] * self.dims[1] * self.dims[2] and b.size == l.size
+        self._check(self._lib.vxrt_cuda_lpv_upload(self._h, _p(l), _p(b)))
+
     # -- statistics --
     def stats_enable(self, on: bool):
         self._check(self._lib.vxrt_cuda_stats_enable(self._h, int(on)))
