@@ -596,12 +596,12 @@ def main():
     torch.cuda.synchronize()
     df_us = float(np.median([a.elapsed_time(b) for a, b in df_ev])) * 1e3
 
-    # ---- SVGF denoiser chain of the GI output: temporal, variance, 5 a-trous iterations, per-stage CUDA
+    # ---- SVGF denoiser chain of the GI output: 3 x 3 pre-pass, temporal, variance, 5 a-trous iterations, per-stage CUDA
     # events, L2 flushed before each chain; runs on consecutive frames of the camera path so the history is live ----
     svgf = None
     if world_size == 1 and "gi" in cfg.passes and not args.no_svgf:
         from voxeltracing_b200.pipeline import SvgfChain
-        chain = SvgfChain(ctx, W, H)
+        chain = SvgfChain(ctx, W, H, pre_spatial=True)   # PreTemporalSpatialPass is on by default (Pipeline.cpp:246)
         n_chain = 20
         stage_ev = []
         for k in range(n_chain):

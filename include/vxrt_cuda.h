@@ -158,7 +158,8 @@ typedef enum vxrt_attachment {
     VXRT_ATT_PREV_REFL_HITDIST = 52, /* previous frame's REFL_HITDIST (the engine ping-pongs ReflectionTraceFBO_1 / _2, :1864-1865); filled by vxrt_cuda_end_frame */
     VXRT_ATT_REFL_DENOISED_A = 53,   /* ReflectionDenoised_1: RGBA16F (x pass, :1193) */
     VXRT_ATT_REFL_DENOISED_B = 54,   /* ReflectionDenoised_2: RGBA16F (y pass: the denoised reflections) */
-    VXRT_ATT_COUNT = 55
+    VXRT_ATT_SVGF_PRESPATIAL = 55,   /* DiffusePreTemporal_SpatialFBO (:1153): +0 SH, +1 CoCg, +2 utility R16F, +3 AO/sky */
+    VXRT_ATT_COUNT = 59
 } vxrt_attachment;
 
 /* glGetTexImage equivalent: copies the whole attachment (width*height*bytes_per_pixel). */
@@ -368,6 +369,18 @@ typedef struct vxrt_svgf_temporal_params {   /* Pipeline.cpp:2428-2528 */
     vxrt_tile tile;
 } vxrt_svgf_temporal_params;
 int vxrt_cuda_svgf_temporal(vxrt_ctx* ctx, const vxrt_svgf_temporal_params* p);
+
+/* The 3 x 3 edge-stopping pass in front of the temporal filter (Core/Shaders/Spatial3x3Initial.glsl, dispatched at
+ * Core/Pipeline.cpp:2381-2424 when PreTemporalSpatialPass is on, the engine's default): reads the raw trace set and the primary
+ * G-buffer, writes VXRT_ATT_SVGF_PRESPATIAL, which the temporal filter then takes as its in_set (:2488-2520).                */
+typedef struct vxrt_svgf_prespatial_params {
+    float inv_view[16], inv_projection[16];  /* u_InverseView, u_InverseProjection (v_RayOrigin = u_VertInverseView[3]) */
+    int32_t width, height;                   /* size of the GI images */
+    int32_t in_set;                          /* VXRT_ATT_GI_SH */
+    float time;                              /* u_Time: only feeds a jitter the shader computes and never uses */
+    vxrt_tile tile;
+} vxrt_svgf_prespatial_params;               /* writes VXRT_ATT_SVGF_PRESPATIAL */
+int vxrt_cuda_svgf_prespatial(vxrt_ctx* ctx, const vxrt_svgf_prespatial_params* p);
 
 typedef struct vxrt_svgf_variance_params {   /* Pipeline.cpp:2532-2567 */
     float inv_view[16], inv_projection[16];

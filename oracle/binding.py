@@ -232,6 +232,15 @@ def svgf_temporal(p: "abi.SvgfTemporalParams", cur: dict, hist: dict, g: dict, p
     return out
 
 
+def svgf_prespatial(p: "abi.SvgfPreSpatialParams", raw: dict, g: dict, fn=None) -> dict:
+    """Spatial3x3Initial.glsl.  raw: the GI trace set (x = utility R16F); g: {"t": f16, "normal": u8} of any size."""
+    out = svgf_alloc(p.height, p.width, 1)
+    a, o = svgf_set(raw), svgf_set(out)
+    gh, gw = g["t"].shape
+    (fn or lib().vxo_svgf_prespatial)(C.byref(p), C.byref(a), _p(g["t"]), _p(g["normal"]), gw, gh, C.byref(o))
+    return out
+
+
 def svgf_variance(p: "abi.SvgfVarianceParams", temporal: dict, g: dict, fn=None) -> dict:
     """VarianceEstimate.glsl.  temporal: this frame's temporal set (x = utility RGB16F).  Returns sh, cocg, x = variance R16F
     (aosky stays zero: VarianceFBO has no fourth attachment)."""

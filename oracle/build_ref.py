@@ -40,6 +40,7 @@ SHADERS = {
     "SVGFTemporal": ("SVGF/TemporalFilter.glsl", "fragment"),
     "SVGFVariance": ("SVGF/VarianceEstimate.glsl", "fragment"),
     "SVGFSpatial": ("SVGF/SpatialFilter.glsl", "fragment"),
+    "SVGFPreSpatial": ("Spatial3x3Initial.glsl", "fragment"),   # the 3 x 3 pass in front of the temporal filter (Pipeline.cpp:2381-2424)
     # sun-shadow denoiser
     "ShadowTemporal": ("ShadowTemporalFilter.glsl", "fragment"),
     "ShadowFilter": ("ShadowFilter.glsl", "fragment"),

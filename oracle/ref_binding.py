@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 from voxeltracing_b200 import abi  # noqa: E402  (struct layouts only)
 
 LIB_PATH = ROOT / "oracle" / "_ref" / "libvxrt_ref.so"
-HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256, "raycast": 512, "svgf_temporal": 1024, "svgf_variance": 2048, "svgf_spatial": 4096, "shadow_temporal": 8192, "shadow_filter": 16384, "specular_temporal": 32768, "reflection_denoise": 65536}
+HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256, "raycast": 512, "svgf_temporal": 1024, "svgf_variance": 2048, "svgf_spatial": 4096, "shadow_temporal": 8192, "shadow_filter": 16384, "specular_temporal": 32768, "reflection_denoise": 65536, "svgf_prespatial": 131072}
 _lib = None
 
 

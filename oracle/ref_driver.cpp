@@ -48,6 +48,10 @@ thread_local uvec3 gl_GlobalInvocationID;
 #undef sqr   /* a function in SpatialFilter.glsl, a macro in ReflectionTraceFrag.glsl (one translation unit here) */
 #include "SVGFSpatial.cpp"
 #endif
+#ifdef VXREF_HAVE_SVGFPreSpatial
+#undef sqr
+#include "SVGFPreSpatial.cpp"
+#endif
 #ifdef VXREF_HAVE_ShadowTemporal
 #include "ShadowTemporal.cpp"
 #endif
@@ -111,6 +115,9 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_SVGFSpatial
     m |= 4096;
+#endif
+#ifdef VXREF_HAVE_SVGFPreSpatial
+    m |= 131072;
 #endif
 #ifdef VXREF_HAVE_ShadowTemporal
     m |= 8192;
@@ -612,6 +619,40 @@ extern "C" void vxref_svgf_spatial(const vxrt_svgf_spatial_params* p, const vxre
             for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
             out->x[i] = vxo::float_to_half(S::o_Variance);
             for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOAndSkylighting[c]);
+        }
+}
+#endif
+
+#ifdef VXREF_HAVE_SVGFPreSpatial
+/* Spatial3x3Initial.glsl as dispatched at Core/Pipeline.cpp:2381-2424: in = DiffuseRawTraceFBO (x = R16F utility), out = DiffusePreTemporal_SpatialFBO */
+extern "C" void vxref_svgf_prespatial(const vxrt_svgf_prespatial_params* p, const vxref_svgf_set* in, const uint16_t* g_t, const uint8_t* g_normal,
+                                      int gw, int gh, const vxref_svgf_out* out) {
+    namespace S = shader_SVGFPreSpatial;
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H;
+    auto fsh = svgf_half(in->sh, 4 * n), fcc = svgf_half(in->cocg, 2 * n), fut = svgf_half(in->x, n), fao = svgf_u8(in->aosky, 2 * n);
+    auto ft = svgf_half(g_t, (size_t)gw * gh), fn = svgf_u8(g_normal, (size_t)gw * gh);
+    bind2d(S::u_SH, fsh.data(), W, H, 4, true); bind2d(S::u_CoCg, fcc.data(), W, H, 2, true);
+    bind2d(S::u_Utility, fut.data(), W, H, 1, true); bind2d(S::u_AO, fao.data(), W, H, 2, true);
+    bind2d(S::u_PositionTexture, ft.data(), gw, gh, 1, true); bind2d(S::u_NormalTexture, fn.data(), gw, gh, 1, false);
+    S::u_InverseView.load(p->inv_view); S::u_InverseProjection.load(p->inv_projection);
+    S::u_Dimensions = vec2((float)W, (float)H);
+    S::u_DeltaTime = 0.0f; S::u_Time = p->time;
+    const vec3 cam = vec3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    rows_of(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, 0.5f, 1.0f);
+            S::v_TexCoords = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            S::v_RayOrigin = cam; S::v_RayDirection = vec3(0.0f, 0.0f, 1.0f);
+            S::shader_reset(); S::shader_main();
+            const size_t i = (size_t)py * W + px;
+            for (int c = 0; c < 4; ++c) out->sh[4 * i + c] = vxo::float_to_half(S::o_SH[c]);
+            for (int c = 0; c < 2; ++c) out->cocg[2 * i + c] = vxo::float_to_half(S::o_CoCg[c]);
+            out->x[i] = vxo::float_to_half(S::o_Utility);
+            for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOSky[c]);
         }
 }
 #endif

@@ -402,3 +402,75 @@ extern "C" void vxo_svgf_spatial(const vxrt_svgf_spatial_params* p, const vxo_sv
             out->aosky[2 * i] = float_to_unorm8(oAO.x); out->aosky[2 * i + 1] = float_to_unorm8(oAO.y);
         }
 }
+
+/* Spatial3x3Initial.glsl main() (:103-175), the 3 x 3 pass in front of the temporal filter (Core/Pipeline.cpp:2381-2424).
+ * in->x = u_Utility (R16F, passed through).  The eight neighbours are taken x-major (x = -1, 0, 1 outside, y inside); a tap counts
+ * when its world position is less than 1 from the centre's (GetPositionAt :34-38 with v_RayOrigin = u_VertInverseView[3],
+ * FBOVert.glsl:21).  Weight = exp(-|dY| / 4 - pow(max(n.n', 0), 16)): the normal term is SUBTRACTED in the exponent (:137-139), so
+ * equal normals lower the weight; kept as written.  Jitter (:120) is computed and never used. */
+extern "C" void vxo_svgf_prespatial(const vxrt_svgf_prespatial_params* p, const vxo_svgf_set* in, const uint16_t* g_t, const uint8_t* g_normal,
+                                    int32_t gw, int32_t gh, const vxo_svgf_out* out) {
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H, ng = (size_t)gw * gh;
+    auto fsh = from_half(in->sh, 4 * n), fcc = from_half(in->cocg, 2 * n), fao = from_u8(in->aosky, 2 * n), fut = from_half(in->x, n);
+    auto ft = from_half(g_t, ng), fn = from_u8(g_normal, ng);
+    const Tex2D tSH = view(fsh, W, H, 4, true), tCC = view(fcc, W, H, 2, true), tAO = view(fao, W, H, 2, true), tUt = view(fut, W, H, 1, true);
+    const Tex2D tT = view(ft, gw, gh, 1, true), tN = view(fn, gw, gh, 1, false);
+    const float AtrousWeights[3] = {1.0f, 2.0f / 3.0f, 1.0f / 6.0f};
+    const v2 TexelSize = V2(1.0f / (float)W, 1.0f / (float)H);
+    const float PhiColor = 4.0f;
+    GBuf g;
+    g.inv_view = p->inv_view; g.inv_proj = p->inv_projection;
+    g.origin = V3(p->inv_view[12], p->inv_view[13], p->inv_view[14]);
+    int r0, r1;
+    tile_rows(p->tile, H, &r0, &r1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = r0; py < r1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const v2 tc = V2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+            const v4 BasePosition = g.position_at(tT, tc);
+            const v3 BaseNormal = normal_from_id(tex2d_sample(tN, tc.x, tc.y).x);
+            const v4 BaseSH = tex2d_sample(tSH, tc.x, tc.y);
+            const v4 bcc = tex2d_sample(tCC, tc.x, tc.y);
+            const float BaseLuminance = sh_to_y(BaseSH);
+            const v4 bao = tex2d_sample(tAO, tc.x, tc.y);
+            v4 TotalSH = BaseSH;
+            v2 TotalCoCg = V2(bcc.x, bcc.y), TotalAOSky = V2(bao.x, bao.y);
+            float TotalWeight = 1.0f, TotalAOWeight = 1.0f;
+            for (int x = -1; x <= 1; ++x)
+                for (int y = -1; y <= 1; ++y) {
+                    if (x == 0 && y == 0) continue;
+                    const v2 sc = V2(tc.x + ((float)x * 1.0f) * TexelSize.x, tc.y + ((float)y * 1.0f) * TexelSize.y);
+                    if (!(sc.x > 0.0f && sc.x < 1.0f && sc.y > 0.0f && sc.y < 1.0f)) continue;
+                    const v4 sp = g.position_at(tT, sc);
+                    const v3 d = V3(fabsf(sp.x - BasePosition.x), fabsf(sp.y - BasePosition.y), fabsf(sp.z - BasePosition.z));
+                    const float DistSqr = dot(d, d);
+                    if (!(DistSqr < 1.0f)) continue;
+                    const v4 SampleSH = tex2d_sample(tSH, sc.x, sc.y);
+                    const v4 scc = tex2d_sample(tCC, sc.x, sc.y);
+                    const v3 SampleNormal = normal_from_id(tex2d_sample(tN, sc.x, sc.y).x);
+                    const float SampleLuma = sh_to_y(SampleSH);
+                    const float NormalWeight = powf(gmax(dot(BaseNormal, SampleNormal), 0.0f), 16.0f);
+                    const float LuminosityWeight = fabsf(SampleLuma - BaseLuminance) / PhiColor;
+                    float Weight = expf(-LuminosityWeight - NormalWeight);
+                    Weight = gmax(Weight, 0.01f);
+                    Weight = (AtrousWeights[x < 0 ? -x : x] * AtrousWeights[y < 0 ? -y : y]) * Weight;
+                    Weight = gmax(Weight, 0.01f);
+                    Weight = gclampf(Weight, 0.0f, 1.0f);
+                    TotalSH = V4(TotalSH.x + SampleSH.x * Weight, TotalSH.y + SampleSH.y * Weight, TotalSH.z + SampleSH.z * Weight, TotalSH.w + SampleSH.w * Weight);
+                    TotalCoCg = V2(TotalCoCg.x + scc.x * Weight, TotalCoCg.y + scc.y * Weight);
+                    TotalWeight += Weight;
+                    const v4 sao = tex2d_sample(tAO, sc.x, sc.y);
+                    TotalAOSky = V2(TotalAOSky.x + sao.x * Weight, TotalAOSky.y + sao.y * Weight);
+                    TotalAOWeight += Weight;
+                }
+            TotalWeight = gmax(TotalWeight, 0.01f);
+            const float aw = gmax(TotalAOWeight, 0.01f);
+            const size_t i = (size_t)py * W + px;
+            out->sh[4 * i] = float_to_half(TotalSH.x / TotalWeight); out->sh[4 * i + 1] = float_to_half(TotalSH.y / TotalWeight);
+            out->sh[4 * i + 2] = float_to_half(TotalSH.z / TotalWeight); out->sh[4 * i + 3] = float_to_half(TotalSH.w / TotalWeight);
+            out->cocg[2 * i] = float_to_half(TotalCoCg.x / TotalWeight); out->cocg[2 * i + 1] = float_to_half(TotalCoCg.y / TotalWeight);
+            out->x[i] = float_to_half(tex2d_sample(tUt, tc.x, tc.y).x);   /* o_Utility = BaseUtility */
+            out->aosky[2 * i] = float_to_unorm8(TotalAOSky.x / aw); out->aosky[2 * i + 1] = float_to_unorm8(TotalAOSky.y / aw);
+        }
+}

@@ -48,6 +48,13 @@ def zero_gbuf():
     return {"t": np.zeros((H, W), np.float16), "normal": np.zeros((H, W), np.uint8), "block": np.zeros((H, W), np.uint8)}
 
 
+def prespatial_params(cam, in_set=abi.ATT_GI_SH, time=0.0) -> abi.SvgfPreSpatialParams:
+    p = abi.SvgfPreSpatialParams()
+    fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
+    p.width, p.height, p.in_set, p.time = W, H, in_set, time
+    return p
+
+
 def variance_params(cam, in_set, do_spatial=True, aggressive=True) -> abi.SvgfVarianceParams:
     p = abi.SvgfVarianceParams()
     fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)

@@ -80,6 +80,48 @@ def test_temporal_bit_exact(seq, be_useful):
         c.close()
 
 
+def test_prespatial_pass(ctx, seq):
+    """Spatial3x3Initial.glsl (one expf per tap): against the oracle with the svgf tolerance, against the compiled shader's output in
+    the golden fixture, at a G-buffer resolution different from the GI images, and feeding the temporal filter."""
+    z = np.load(str(sv.__file__).rsplit("/", 1)[0] + "/golden/svgf_ref.npz")
+    for k, f in enumerate(seq):
+        _load_frame(ctx, f)
+        p = sv.prespatial_params(f["cam"], time=1.0)
+        ctx.svgf_prespatial(p)
+        got = ctx.read_set(abi.ATT_SVGF_PRESPATIAL)
+        _close_sets(got, ob.svgf_prespatial(p, f["raw"], f["g"]), ("sh", "cocg", "x", "aosky"))
+        assert np.array_equal(got["x"].view(np.uint16), ob.svgf_prespatial(p, f["raw"], f["g"])["x"].view(np.uint16))   # utility: no transcendental
+        if k == 0:
+            _close_sets(got, {n: z[f"prespatial0_{n}"] for n in ("sh", "cocg", "x", "aosky")}, ("sh", "cocg", "x", "aosky"))
+    # half-resolution G-buffer
+    g2 = {"t": np.ascontiguousarray(f["g"]["t"][::2, ::2]), "normal": np.ascontiguousarray(f["g"]["normal"][::2, ::2]),
+          "block": np.ascontiguousarray(f["g"]["block"][::2, ::2])}
+    c = engine.Context(0)
+    try:
+        _load_frame(c, {"g": g2, "raw": f["raw"]})
+        c.svgf_prespatial(p)
+        _close_sets(c.read_set(abi.ATT_SVGF_PRESPATIAL), ob.svgf_prespatial(p, f["raw"], g2), ("sh", "cocg", "x", "aosky"))
+        # the temporal filter takes the pre-filtered set as its input (Pipeline.cpp:2488-2520); full-size G-buffer again
+        _load_frame(c, f)
+        c.svgf_prespatial(p)
+        pre = c.read_set(abi.ATT_SVGF_PRESPATIAL)
+        tp = sv.temporal_params(f["cam"], f["cam"], abi.ATT_SVGF_PRESPATIAL, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_TEMPORAL_A)
+        c.svgf_temporal(tp)
+        want = ob.svgf_temporal(tp, pre, ob.svgf_alloc(sv.H, sv.W, 3), f["g"], sv.zero_gbuf())
+        assert sv.same_bits(c.read_set(abi.ATT_SVGF_TEMPORAL_A), want)
+        with pytest.raises(engine.VxrtError):
+            bad = sv.prespatial_params(f["cam"], in_set=abi.ATT_SVGF_TEMPORAL_A)
+            c.svgf_prespatial(bad)
+    finally:
+        c.close()
+    with pytest.raises(engine.VxrtError):
+        c2 = engine.Context(0)
+        try:
+            c2.svgf_prespatial(p)   # nothing traced yet
+        finally:
+            c2.close()
+
+
 @pytest.fixture(scope="module")
 def after_temporal(ctx, seq):
     """context holding frame 2's G-buffer and temporal set (TEMPORAL_A)"""

@@ -127,6 +127,33 @@ def test_oracle_spatial_chain_equals_compiled_reference_shader(seq, temporal, kw
     assert all(sv.same_bits(x, y) for x, y in zip(a, b))
 
 
+@pytest.mark.skipif(not rb.available("svgf_prespatial"), reason="oracle/_ref not built on this box")
+def test_oracle_prespatial_equals_compiled_reference_shader(seq):
+    L = rb.lib()
+    for k, f in enumerate(seq):
+        p = sv.prespatial_params(f["cam"], time=0.4 + k)
+        a = ob.svgf_prespatial(p, f["raw"], f["g"])
+        assert sv.same_bits(a, ob.svgf_prespatial(p, f["raw"], f["g"], L.vxref_svgf_prespatial)), k
+        # G-buffer at another resolution than the GI images (InitialTraceFBO is full size, the GI trace is not)
+        g2 = {"t": np.ascontiguousarray(f["g"]["t"][::2, ::2]), "normal": np.ascontiguousarray(f["g"]["normal"][::2, ::2])}
+        assert sv.same_bits(ob.svgf_prespatial(p, f["raw"], g2), ob.svgf_prespatial(p, f["raw"], g2, L.vxref_svgf_prespatial)), k
+
+
+def test_oracle_prespatial_behaviour_and_golden(seq):
+    """the 3 x 3 pass smooths the raw trace inside surfaces, leaves isolated pixels alone, and equals the compiled shader's output
+    stored in tests/golden/svgf_ref.npz"""
+    f = seq[0]
+    out = ob.svgf_prespatial(sv.prespatial_params(f["cam"], time=1.0), f["raw"], f["g"])
+    lum_in, lum_out = f["raw"]["sh"][..., 3].astype(np.float32), out["sh"][..., 3].astype(np.float32)
+    hit = f["g"]["t"].astype(np.float32) > 0
+    assert np.abs(np.diff(lum_out, axis=1))[hit[:, 1:]].mean() < 0.9 * np.abs(np.diff(lum_in, axis=1))[hit[:, 1:]].mean()
+    assert 0.1 < (out["sh"].view(np.uint16) != f["raw"]["sh"].view(np.uint16)).any(axis=-1).mean() < 0.9
+    z = np.load(str(sv.__file__).rsplit("/", 1)[0] + "/golden/svgf_ref.npz")
+    for k in ("sh", "cocg", "x"):
+        assert np.array_equal(out[k].view(np.uint16), z[f"prespatial0_{k}"].view(np.uint16)), k
+    assert np.array_equal(out["aosky"], z["prespatial0_aosky"])
+
+
 def test_oracle_chain_equals_golden_fixture(seq):
     """tests/golden/svgf_ref.npz was produced by the reference's own shaders (tests/golden/make_golden_svgf.py)."""
     import sys

@@ -31,6 +31,7 @@ ATT_SHADOW_TEMPORAL_A, ATT_SHADOW_TEMPORAL_B, ATT_SHADOW_FILTERED = 41, 43, 45
 # reflection temporal filter: temporal sets are (colour RGBA16F, accumulation factor R16F, stabilised hit distance R16F)
 ATT_REFL_TEMPORAL_A, ATT_REFL_TEMPORAL_B, ATT_PREV_REFL_HITDIST = 46, 49, 52
 ATT_REFL_DENOISED_A, ATT_REFL_DENOISED_B = 53, 54
+ATT_SVGF_PRESPATIAL = 55
 
 TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
@@ -128,6 +129,12 @@ class SvgfSpatialParams(C.Structure):
                 ("in_set", C.c_int32), ("ao_set", C.c_int32), ("temporal_set", C.c_int32), ("out_set", C.c_int32), ("step", C.c_int32),
                 ("large_kernel", C.c_int32), ("do_spatial", C.c_int32), ("aggressive_disocclusion", C.c_int32),
                 ("color_phi_bias", C.c_float), ("time", C.c_float), ("resolution_scale", C.c_float), ("tile", Tile)]
+
+
+class SvgfPreSpatialParams(C.Structure):
+    """vxrt_svgf_prespatial_params"""
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_projection", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
+                ("in_set", C.c_int32), ("time", C.c_float), ("tile", Tile)]
 
 
 class ShadowTemporalParams(C.Structure):
@@ -232,6 +239,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_svgf_temporal": (C.c_int, [vp, P(SvgfTemporalParams)]),
         "vxrt_cuda_svgf_variance": (C.c_int, [vp, P(SvgfVarianceParams)]),
         "vxrt_cuda_svgf_spatial": (C.c_int, [vp, P(SvgfSpatialParams)]),
+        "vxrt_cuda_svgf_prespatial": (C.c_int, [vp, P(SvgfPreSpatialParams)]),
         "vxrt_cuda_svgf_end_frame": (C.c_int, [vp]),
         "vxrt_cuda_end_frame": (C.c_int, [vp]),
         "vxrt_cuda_shadow_temporal": (C.c_int, [vp, P(ShadowTemporalParams)]),

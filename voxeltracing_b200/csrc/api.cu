@@ -558,6 +558,12 @@ int vxrt_cuda_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params* p) {
     if (rc) return rc;
     return vxrt_launch_svgf_temporal(c, *p);
 }
+int vxrt_cuda_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params* p) {
+    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    if (rc) return rc;
+    return vxrt_launch_svgf_prespatial(c, *p);
+}
 int vxrt_cuda_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
     int rc = check_frame(__func__, p->width, p->height, p->tile);

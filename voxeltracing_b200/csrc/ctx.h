@@ -149,6 +149,7 @@ int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p);
 int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p);
 int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p);
 int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p);
+int vxrt_launch_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params& p);
 int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p);
 int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p);
 int vxrt_launch_svgf_end_frame(vxrt_ctx* c);

@@ -485,6 +485,90 @@ __global__ void __launch_bounds__(256, VX_SVGF_OCC) svgf_spatial_kernel(const __
     reinterpret_cast<uchar2*>(a.out.aosky)[i] = ao;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Spatial3x3Initial.glsl main() (:103-175): the 3 x 3 pass in front of the temporal filter (Core/Pipeline.cpp:2381-2424).
+// Eight neighbours, x-major; a tap counts when its world position is less than 1 from the centre's.  The normal term is subtracted
+// in the exponent as the shader writes it (:137-139).  13 algorithmic bytes per pixel in (SH, CoCg, utility, AO/sky, hit distance,
+// face) and 16 out.
+struct PreSpatialArgs {
+    float inv_view[16], inv_proj[16];
+    int width, height, row0, row1;
+    SetIn in;   // raw trace set: x = utility R16F
+    GBufIn g;
+    SetOut out;
+};
+
+__global__ void __launch_bounds__(256, VX_SVGF_OCC) svgf_prespatial_kernel(const __grid_constant__ PreSpatialArgs a) {
+    __shared__ float lut[256];
+    fill_unorm_lut(lut);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int py = a.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= a.width || py >= a.row1) return;
+    const bool same = a.g.w == a.width && a.g.h == a.height;
+    const f2 tc = F2(((float)px + 0.5f) / (float)a.width, ((float)py + 0.5f) / (float)a.height);
+    const f3 origin = F3(a.inv_view[12], a.inv_view[13], a.inv_view[14]);
+    const Tap ts = make_tap(a.width, a.height, tc);
+    Tap tg = ts;
+    if (!same) tg = make_tap(a.g.w, a.g.h, tc);
+    const f3 BasePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, tc)) * sample_r16(a.g.t, tg);
+    const int BaseNormal = normal_at(a.g, nearest_offset(a.g.w, a.g.h, tc), lut);
+    float TotalSH[4], TotalCoCg[2], TotalAO[2];
+    sample_rgba16(a.in.sh, ts, TotalSH);
+    sample_rg16(a.in.cocg, ts, TotalCoCg);
+    sample_rg8(a.in.aosky, ts, lut, TotalAO);
+    const float BaseUtility = sample_r16(a.in.x, ts);
+    const float BaseLuminance = gmax(0.0f, 3.544905f * TotalSH[3]);   // SHToY
+    float TotalWeight = 1.0f, TotalAOWeight = 1.0f;
+    const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        if (k == 4) continue;
+        const int x = k / 3 - 1, y = k - (k / 3) * 3 - 1;
+        const f2 sc = F2(tc.x + ((float)x * 1.0f) * Texel.x, tc.y + ((float)y * 1.0f) * Texel.y);
+        if (!(sc.x > 0.0f && sc.x < 1.0f && sc.y > 0.0f && sc.y < 1.0f)) continue;
+        const Tap ss = make_tap(a.width, a.height, sc);
+        Tap sg = ss;
+        if (!same) sg = make_tap(a.g.w, a.g.h, sc);
+        const f3 SamplePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, sc)) * sample_r16(a.g.t, sg);
+        const f3 e = F3(fabsf(SamplePos.x - BasePos.x), fabsf(SamplePos.y - BasePos.y), fabsf(SamplePos.z - BasePos.z));
+        if (!(dot(e, e) < 1.0f)) continue;
+        float s[4], c2[2], a2[2];
+        sample_rgba16(a.in.sh, ss, s);
+        sample_rg16(a.in.cocg, ss, c2);
+        const float SampleLuma = gmax(0.0f, 3.544905f * s[3]);
+        const float NormalWeight = normal_weight16(BaseNormal, normal_at(a.g, nearest_offset(a.g.w, a.g.h, sc), lut));
+        const float LuminosityWeight = fabsf(SampleLuma - BaseLuminance) / 4.0f;
+        float Weight = expf(-LuminosityWeight - NormalWeight);
+        Weight = gmax(Weight, 0.01f);
+        const float wx = x == 0 ? 1.0f : 2.0f / 3.0f, wy = y == 0 ? 1.0f : 2.0f / 3.0f;   // AtrousWeights[abs(x)], [abs(y)]
+        Weight = (wx * wy) * Weight;
+        Weight = gmax(Weight, 0.01f);
+        Weight = gclamp(Weight, 0.0f, 1.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) TotalSH[j] += s[j] * Weight;
+        TotalCoCg[0] += c2[0] * Weight; TotalCoCg[1] += c2[1] * Weight;
+        TotalWeight += Weight;
+        sample_rg8(a.in.aosky, ss, lut, a2);
+        TotalAO[0] += a2[0] * Weight; TotalAO[1] += a2[1] * Weight;
+        TotalAOWeight += Weight;
+    }
+    TotalWeight = gmax(TotalWeight, 0.01f);
+    const float aw = gmax(TotalAOWeight, 0.01f);
+    const size_t i = (size_t)py * a.width + px;
+    ushort4 o4;
+    o4.x = float_to_half_bits(TotalSH[0] / TotalWeight); o4.y = float_to_half_bits(TotalSH[1] / TotalWeight);
+    o4.z = float_to_half_bits(TotalSH[2] / TotalWeight); o4.w = float_to_half_bits(TotalSH[3] / TotalWeight);
+    reinterpret_cast<ushort4*>(a.out.sh)[i] = o4;
+    ushort2 o2;
+    o2.x = float_to_half_bits(TotalCoCg[0] / TotalWeight); o2.y = float_to_half_bits(TotalCoCg[1] / TotalWeight);
+    reinterpret_cast<ushort2*>(a.out.cocg)[i] = o2;
+    a.out.x[i] = float_to_half_bits(BaseUtility);
+    uchar2 ao;
+    ao.x = float_to_unorm8(TotalAO[0] / aw); ao.y = float_to_unorm8(TotalAO[1] / aw);
+    reinterpret_cast<uchar2*>(a.out.aosky)[i] = ao;
+}
+
 inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
     if (t.rows <= 0) { *r0 = 0; *r1 = height; }
     else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
@@ -499,7 +583,7 @@ inline bool is_svgf_set(int id) {
 }
 
 int set_in(vxrt_ctx* c, const char* fn, int id, int x_bpp, bool need_ao, SetIn* s) {
-    if (!(is_svgf_set(id) || id == VXRT_ATT_GI_SH)) return vxrt_fail(VXRT_E_INVALID, "%s: %d does not name an image set", fn, id);
+    if (!(is_svgf_set(id) || id == VXRT_ATT_GI_SH || id == VXRT_ATT_SVGF_PRESPATIAL)) return vxrt_fail(VXRT_E_INVALID, "%s: %d does not name an image set", fn, id);
     const Attachment& a0 = c->att[id];
     if (!a0.ptr || a0.width <= 0) return vxrt_fail(VXRT_E_STATE, "%s: image set %d has not been written", fn, id);
     for (int k = 0; k < 4; ++k) {
@@ -576,6 +660,29 @@ int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
     if (a.row1 <= a.row0) return VXRT_OK;
     dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     svgf_temporal_kernel<<<grid, 256, 0, c->stream>>>(a);
+    VX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params& p) {
+    static const char* fn = "vxrt_cuda_svgf_prespatial";
+    if (p.in_set != VXRT_ATT_GI_SH) return vxrt_fail(VXRT_E_INVALID, "%s: in_set must be VXRT_ATT_GI_SH (the raw trace)", fn);
+    PreSpatialArgs a;
+    int rc;
+    if ((rc = set_in(c, fn, p.in_set, 2, true, &a.in))) return rc;
+    if (a.in.w != p.width || a.in.h != p.height) return vxrt_fail(VXRT_E_STATE, "%s: image set is %dx%d, the pass runs at %dx%d", fn, a.in.w, a.in.h, p.width, p.height);
+    if ((rc = gbuf_in(c, fn, VXRT_ATT_INITIAL_T, VXRT_ATT_INITIAL_NORMAL, VXRT_ATT_INITIAL_BLOCK, &a.g))) return rc;
+    for (int k = 0; k < 4; ++k)   // DiffusePreTemporal_SpatialFBO (Pipeline.cpp:1153): RGBA16F, RG16F, R16F, RG8
+        if ((rc = vxrt_ensure_attachment(c, VXRT_ATT_SVGF_PRESPATIAL + k, p.width, p.height, set_bpp(k, false)))) return rc;
+    a.out.sh = (uint16_t*)c->att[VXRT_ATT_SVGF_PRESPATIAL].ptr; a.out.cocg = (uint16_t*)c->att[VXRT_ATT_SVGF_PRESPATIAL + 1].ptr;
+    a.out.x = (uint16_t*)c->att[VXRT_ATT_SVGF_PRESPATIAL + 2].ptr; a.out.aosky = (uint8_t*)c->att[VXRT_ATT_SVGF_PRESPATIAL + 3].ptr;
+    for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
+    a.width = p.width; a.height = p.height;
+    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    if (a.row1 <= a.row0) return VXRT_OK;
+    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    svgf_prespatial_kernel<<<grid, 256, 0, c->stream>>>(a);
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;

@@ -50,7 +50,7 @@ for _s in (abi.ATT_REFL_TEMPORAL_A, abi.ATT_REFL_TEMPORAL_B):
 _ATT_DTYPES[abi.ATT_PREV_REFL_HITDIST] = (np.float16, 1)
 _ATT_DTYPES.update({abi.ATT_REFL_DENOISED_A: (np.float16, 4), abi.ATT_REFL_DENOISED_B: (np.float16, 4)})
 # SVGF image sets (four consecutive ids): SH, CoCg, utility RGB16F (temporal sets) / variance R16F, AO + sky
-for _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_B):
+for _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_VARIANCE, abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_B, abi.ATT_SVGF_PRESPATIAL):
     _ATT_DTYPES.update({_s: (np.float16, 4), _s + 1: (np.float16, 2),
                         _s + 2: (np.float16, 3 if _s in (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B) else 1), _s + 3: (np.uint8, 2)})
 
@@ -247,6 +247,9 @@ class Context:
     # -- SVGF chain of the diffuse GI (Core/Pipeline.cpp:2428-2700) --
     def svgf_temporal(self, params: "abi.SvgfTemporalParams"):
         self._check(self._lib.vxrt_cuda_svgf_temporal(self._h, C.byref(params)))
+
+    def svgf_prespatial(self, params: "abi.SvgfPreSpatialParams"):
+        self._check(self._lib.vxrt_cuda_svgf_prespatial(self._h, C.byref(params)))
 
     def svgf_variance(self, params: "abi.SvgfVarianceParams"):
         self._check(self._lib.vxrt_cuda_svgf_variance(self._h, C.byref(params)))

@@ -220,18 +220,20 @@ def band_rows(height: int, rank: int, world: int, band: int = 8):
 
 class SvgfChain:
     """The SVGF denoiser chain of the diffuse GI in the order of Core/Pipeline.cpp:2428-2700: temporal accumulation
-    (temporal sets ping-ponged by frame parity, :2420-2426), variance estimate, five a-trous iterations with steps
+    (temporal sets ping-ponged by frame parity, :2420-2426; with pre_spatial, the engine's default PreTemporalSpatialPass, the 3 x 3
+    pass of Spatial3x3Initial.glsl runs first, :2381-2424, and the temporal filter reads its output, :2488-2520), variance estimate, five a-trous iterations with steps
     16, 8, 4, 2, 1 ping-ponging the two denoise sets (:2592-2700), then the G-buffer hand-over to the next frame.
     Consumes the attachments of `primary` and `gi` of the same frame; the denoised result is `final_set`."""
 
     STEPS = (16, 8, 4, 2, 1)                    # Pipeline.cpp:2583-2589 (WiderSVGF off)
     # bytes every stage reads + writes per pixel when each image is touched once (DESIGN.md §3.4)
-    STAGE_BYTES = {"temporal": 64, "variance": 35, "spatial": 41}
+    STAGE_BYTES = {"prespatial": 35, "temporal": 64, "variance": 35, "spatial": 41}
     final_set = abi.ATT_SVGF_DENOISE_A          # iteration 4 writes DiffuseDenoiseFBO
 
     def __init__(self, ctx: Context, width: int, height: int, color_phi_bias: float = 2.8, resolution_scale: float = 0.25,
-                 large_kernel: bool = False, aggressive: bool = True):
+                 large_kernel: bool = False, aggressive: bool = True, pre_spatial: bool = False):
         self.ctx, self.width, self.height = ctx, width, height
+        self.pre_spatial = pre_spatial
         self.color_phi_bias, self.resolution_scale = color_phi_bias, resolution_scale     # Pipeline.cpp:86, 112
         self.large_kernel, self.aggressive = large_kernel, aggressive
         self.prev_cam = None
@@ -242,10 +244,18 @@ class SvgfChain:
         self.prev_cam = cam
         cur_t, hist_t = (abi.ATT_SVGF_TEMPORAL_A, abi.ATT_SVGF_TEMPORAL_B) if frame % 2 == 0 else (abi.ATT_SVGF_TEMPORAL_B, abi.ATT_SVGF_TEMPORAL_A)
         out = []
+        if self.pre_spatial:
+            pp = abi.SvgfPreSpatialParams()
+            _fill(pp.inv_view, cam.inv_view); _fill(pp.inv_projection, cam.inv_projection)
+            pp.width, pp.height, pp.in_set = self.width, self.height, abi.ATT_GI_SH
+            pp.time = frame / 60.0 if time is None else time
+            pp.tile.row0, pp.tile.rows = tile
+            out.append(("prespatial", lib.vxrt_cuda_svgf_prespatial, pp))
         tp = abi.SvgfTemporalParams()
         _fill(tp.inv_view, cam.inv_view); _fill(tp.inv_projection, cam.inv_projection)
         _fill(tp.prev_view, prev.view); _fill(tp.prev_projection, prev.projection)
-        tp.width, tp.height, tp.in_set, tp.history_set, tp.out_set, tp.be_useful = self.width, self.height, abi.ATT_GI_SH, hist_t, cur_t, 1
+        tp.width, tp.height, tp.history_set, tp.out_set, tp.be_useful = self.width, self.height, hist_t, cur_t, 1
+        tp.in_set = abi.ATT_SVGF_PRESPATIAL if self.pre_spatial else abi.ATT_GI_SH
         tp.tile.row0, tp.tile.rows = tile
         out.append(("temporal", lib.vxrt_cuda_svgf_temporal, tp))
         vp = abi.SvgfVarianceParams()
