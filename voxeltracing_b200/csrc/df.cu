@@ -10,8 +10,8 @@
 //     thread's loads in flight before the first use, converted to the solid?0:254 seed and staged in shared
 //     memory as rows of uint4 with an odd row stride (in uint4 units), which makes the per-row X sweep
 //     (LDS.128, one thread per row), the per-column Y sweep (LDS.32, one thread per 4-voxel word column) and the
-//     16-byte load / store phases all bank-conflict free.  X sweep: running value in a register, one VIADDMNMX
-//     per voxel.  Y sweep: two VIADDMNMX.U16x2 per 4 voxels per direction (bytes unpacked to u16 lanes with PRMT).
+//     16-byte load / store phases all bank-conflict free.  X: from the solid mask of the row (quad carries + nibble
+//     table, see the kernel).  Y sweep: two VIADDMNMX.U16x2 per 4 voxels per direction (bytes unpacked to u16 lanes with PRMT).
 //   kernel 2 (z_tile): one CTA per tile of 32 word columns (128 bytes of x) x all planes.  The tile is staged in
 //     shared memory (128-byte rows are full sectors; the field is L2 resident after kernel 1), the z range is
 //     cut into 8 segments, one warp each: local forward + backward min-plus sweeps per segment, then the carries
@@ -31,6 +31,12 @@ __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w
 __device__ __forceinline__ unsigned pack_lanes(unsigned e, unsigned o) { return o * 256u + e; }
 __device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {
     return (b3 * 256u + b2) * 65536u + (b1 * 256u + b0);
+}
+
+// bit i = byte i of w is non-zero
+__device__ __forceinline__ unsigned solid_nibble(unsigned w) {
+    const unsigned nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;  // bit7 set where byte != 0
+    return (((nz >> 7) * 0x00204081u) >> 21) & 15u;                              // bits 0, 8, 16, 24 -> 21..24 (no carries between the terms)
 }
 
 // solid ? 0 : maxd for the four bytes of w
@@ -61,15 +67,19 @@ __device__ __forceinline__ unsigned sweep_word_down(unsigned w, unsigned& c) {
 // ---- kernel 1: X and Y sweeps of one z-slice in shared memory ---------------------------------
 // ManhattanDistanceX.comp:53-68 and ManhattanDistanceY.comp:35-49.
 // All slices are resident at once (one wave), so the kernel lasts as long as one CTA's chain of phases: every phase
-// has to keep all 12 warps busy.  Rows are cut into sx segments and columns into sy segments (3 x 128 voxels and
-// 4 x 32 rows for the 384 x 128 slice) so both sweeps have 384 independent chains; the segments are joined exactly by
-// carries, like the Z kernels: after the local two-sided sweeps a segment's boundary value + distance is what any
-// other segment can see of it.  The X carries are folded into the first touch of the Y sweep, the Y carries into
-// the write-out, so no extra pass over the slice is needed.
-//   stage   16-byte loads (8 per thread, all in flight), seeds -> shared memory rows (odd stride in quads)
-//   X       local forward + backward sweep per (row, x-segment)
-//   xcarry  per (row, x-segment): value arriving from the left / right segments
-//   Y       local forward (X carries applied on the fly) + backward sweep per (word column, y-segment)
+// has to keep all 12 warps busy.
+// X needs no sweep over voxels: the 1-D distance to the nearest solid voxel of a row follows from the row's solid mask.  A quad
+// (16 voxels) keeps its 16-bit mask; the carries that enter a quad from the left / right come from a scan over the row's quads
+// (2 x 24 steps per row instead of 2 x 384); inside the quad the carries advance word by word through a 16-entry table indexed
+// by the word's 4-bit mask (distance inside the word as u16 lanes, carry leaving the word on either side), and every voxel is
+// min(inside the word, left carry + offset, right carry + offset): 2 + 4 VIADDMNMX per word against 8 + 8 PRMT for the byte chain,
+// and no pass over the slice in shared memory.  Columns are cut into sy segments (4 x 32 rows for the 384 x 128 slice) so the Y sweep
+// has 384 independent chains; the segments are joined exactly by carries, like the Z kernels: after the local two-sided sweeps a
+// segment's boundary value + distance is what any other segment can see of it; the Y carries are folded into the write-out.
+//   stage   16-byte loads (8 per thread, all in flight) -> solid mask per quad, carries leaving the quad
+//   xcarry  per row: scan of the quad carries, both directions
+//   X       per quad: distances from the mask, the two carries and the nibble table -> shared memory rows (odd stride in quads)
+//   Y       local forward + backward sweep per (word column, y-segment)
 //   ycarry  per (word column, y-segment): values arriving from above / below
 //   store   Y carries applied, 16-byte stores
 #ifndef VX_XY_THREADS
@@ -93,11 +103,10 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
     const int sw = sq << 2;        // row stride in words
     const int nxw = nx >> 2;       // words per row
     const int nq = qpr * ny;       // quads in the slice (<= 4096)
-    const int qps = qpr / sx;      // quads per x-segment
-    const int segvox = qps << 4;   // voxels per x-segment
     const int rps = ny / sy;       // rows per y-segment
-    unsigned* xcar = smem + ny * sw;                                   // [ny][sx]: fwd | bwd << 16
-    uint4* ycar = reinterpret_cast<uint4*>(xcar + ((ny * sx + 3) & ~3));  // [sy][4][qpr]: (fwd.e, fwd.o, bwd.e, bwd.o)
+    unsigned* qcar = smem + ny * sw;                                   // [ny][sq]: per quad, carry from the left | from the right << 16
+    uint4* lut = reinterpret_cast<uint4*>(qcar + ((ny * sq + 3) & ~3));   // [16]
+    uint4* ycar = lut + 16;                                            // [sy][4][qpr]: (fwd.e, fwd.o, bwd.e, bwd.o)
     const unsigned rdiv = ((1u << 20) + qpr - 1) / qpr;  // q / qpr == (q * rdiv) >> 20 for q < 4096, qpr <= 64
     const unsigned ydiv = ((1u << 20) + rps - 1) / rps;  // row / rps likewise (row < 4096)
     const int z = z_begin + blockIdx.x;
@@ -105,7 +114,25 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
     const uint4* src = reinterpret_cast<const uint4*>(blocks + slice_off);
     const unsigned maxd4 = maxd * 0x01010101u;
 
-    // ---- stage ----
+    // ---- lut: per 4-voxel nibble of the solid mask (bit i = voxel i solid): x, y = distance of every voxel to the nearest solid of
+    // the nibble as u16 lanes (v0 | v2 << 16, v1 | v3 << 16; maxd when the nibble is empty), z = carry leaving the word to the right
+    // (4 - highest solid) | carry leaving it to the left (lowest solid + 1) << 16, NO_CARRY when empty ----
+    if (threadIdx.x < 16) {
+        const unsigned n = threadIdx.x;
+        unsigned d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned best = maxd;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n >> j & 1u) best = min(best, (unsigned)(i > j ? i - j : j - i));
+            d[i] = best;
+        }
+        const unsigned f = n ? (unsigned)(4 - (31 - __clz(n))) : NO_CARRY, b = n ? (unsigned)__ffs(n) : NO_CARRY;
+        lut[n] = make_uint4(d[0] | (d[2] << 16), d[1] | (d[3] << 16), f | (b << 16), 0u);
+    }
+
+    // ---- stage: 16-byte loads (all in flight), solid mask of the quad -> its slot of the slice, carries leaving the quad -> qcar ----
     for (int base = 0; base < nq; base += XY_THREADS * XY_BATCH) {
         uint4 v[XY_BATCH];
 #pragma unroll
@@ -118,68 +145,71 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
             const int q = base + i * XY_THREADS + threadIdx.x;
             if (q < nq) {
                 const int row = (int)(((unsigned)q * rdiv) >> 20), col = q - row * qpr;
-                smem4[row * sq + col] = make_uint4(seed_word(v[i].x, maxd4), seed_word(v[i].y, maxd4), seed_word(v[i].z, maxd4),
-                                                   seed_word(v[i].w, maxd4));
+                const unsigned m16 = solid_nibble(v[i].x) | (solid_nibble(v[i].y) << 4) | (solid_nibble(v[i].z) << 8) | (solid_nibble(v[i].w) << 12);
+                smem[(row * sq + col) << 2] = m16;
+                // to the right: 16 - highest solid voxel; to the left: lowest solid voxel + 1
+                qcar[row * sq + col] = m16 ? (unsigned)(__clz(m16) - 15) | ((unsigned)__ffs(m16) << 16) : NO_CARRY | (NO_CARRY << 16);
             }
         }
     }
     __syncthreads();
 
-    // ---- X: local sweeps per (row, x-segment); consecutive threads take consecutive rows (conflict-free LDS.128) ----
-    for (int item = threadIdx.x; item < ny * sx; item += XY_THREADS) {
-        const int seg = item / ny, row = item - seg * ny;
-        uint4* r = smem4 + row * sq + seg * qps;
-        unsigned c = 255u;  // min(seed, 256) == seed for the first voxel
-#pragma unroll 2
-        for (int j = 0; j < qps; ++j) {
-            uint4 w = r[j];
-            w.x = sweep_word_up(w.x, c); w.y = sweep_word_up(w.y, c); w.z = sweep_word_up(w.z, c); w.w = sweep_word_up(w.w, c);
-            r[j] = w;
-        }
-        c = 255u;
-#pragma unroll 2
-        for (int j = qps - 1; j >= 0; --j) {
-            uint4 w = r[j];
-            w.w = sweep_word_down(w.w, c); w.z = sweep_word_down(w.z, c); w.y = sweep_word_down(w.y, c); w.x = sweep_word_down(w.x, c);
-            r[j] = w;
+    // ---- X carries: per row, what reaches the first voxel of every quad from the left and its last voxel from the right
+    // (ManhattanDistanceX.comp:53-68 at quad granularity: 2 * qpr steps per row instead of 2 * nx) ----
+    {
+        unsigned short* qc = reinterpret_cast<unsigned short*>(qcar);
+        for (int item = threadIdx.x; item < 2 * ny; item += XY_THREADS) {
+            const int back = item >= ny, row = item - back * ny;
+            unsigned short* r = qc + ((row * sq) << 1) + back;
+            unsigned c = NO_CARRY;
+            if (!back) {
+                for (int j = 0; j < qpr; ++j) { const unsigned f = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(f, c + 16u); }
+            } else {
+                for (int j = qpr - 1; j >= 0; --j) { const unsigned b = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(b, c + 16u); }
+            }
         }
     }
     __syncthreads();
 
-    // ---- xcarry: what reaches the first / last voxel of (row, seg) from the other segments of the row ----
-    for (int item = threadIdx.x; item < ny * sx; item += XY_THREADS) {
-        const int seg = item / ny, row = item - seg * ny;
-        const unsigned* r = smem + row * sw;
-        unsigned cf = NO_CARRY, cb = NO_CARRY;
-        for (int t = 0; t < sx; ++t) {
-            if (t < seg) cf = min(cf, (r[(t + 1) * (qps << 2) - 1] >> 24) + (unsigned)((seg - t - 1) * segvox + 1));       // last voxel of t
-            else if (t > seg) cb = min(cb, (r[t * (qps << 2)] & 0xffu) + (unsigned)((t - seg - 1) * segvox + 1));        // first voxel of t
+    // ---- X distances of every quad from its mask and the two carries: word by word the carries advance through the nibble table,
+    // every voxel is min(inside the word, carry from the left + offset, carry from the right + offset) ----
+    for (int q = threadIdx.x; q < nq; q += XY_THREADS) {
+        const int row = (int)(((unsigned)q * rdiv) >> 20), col = q - row * qpr;
+        const int slot = row * sq + col;
+        const unsigned m16 = smem[slot << 2], cin = qcar[slot];
+        uint4 l[4];
+        unsigned cf[4], cb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) l[k] = lut[(m16 >> (4 * k)) & 15u];
+        unsigned c = cin & 0xffffu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cf[k] = c; c = __viaddmin_u32(c, 4u, l[k].z & 0xffffu); }
+        c = cin >> 16;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) { cb[k] = c; c = __viaddmin_u32(c, 4u, l[k].z >> 16); }
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned f2 = cf[k] * 0x00010001u, b2 = cb[k] * 0x00010001u;
+            unsigned e = __viaddmin_u16x2(f2, 0x00020000u, l[k].x), o = __viaddmin_u16x2(f2, 0x00030001u, l[k].y);
+            e = __viaddmin_u16x2(b2, 0x00010003u, e); o = __viaddmin_u16x2(b2, 0x00000002u, o);
+            w[k] = pack_lanes(e, o);
         }
-        xcar[row * sx + seg] = cf | (cb << 16);
+        smem4[slot] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     __syncthreads();
 
     // ---- Y: local sweeps per (word column, y-segment), two u16x2 lane pairs per word ----
     for (int item = threadIdx.x; item < nxw * sy; item += XY_THREADS) {
         const int ys = item / nxw, col = item - ys * nxw;
-        const int xseg = col / (qps << 2);
-        const unsigned d0 = (unsigned)(col * 4 - xseg * segvox);              // distance of byte 0 from the segment's first voxel
-        const unsigned b0 = (unsigned)(segvox - 1) - d0;                      // ... from its last voxel (>= 3)
-        const unsigned offFe = d0 | ((d0 + 2) << 16), offFo = (d0 + 1) | ((d0 + 3) << 16);
-        const unsigned offBe = b0 | ((b0 - 2) << 16), offBo = (b0 - 1) | ((b0 - 3) << 16);
         unsigned* cptr = smem + col;
-        const unsigned* xc = xcar + xseg;
         const int y0 = ys * rps, y1 = y0 + rps;
         unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first row
 #pragma unroll 4
         for (int y = y0; y < y1; ++y) {
-            const unsigned w = cptr[y * sw], c = xc[y * sx];
-            const unsigned cf2 = __byte_perm(c, 0u, 0x1010), cb2 = __byte_perm(c, 0u, 0x3232);
-            unsigned ve = even_lanes(w), vo = odd_lanes(w);
-            ve = __viaddmin_u16x2(cf2, offFe, ve); vo = __viaddmin_u16x2(cf2, offFo, vo);   // the row's X transform, completed
-            ve = __viaddmin_u16x2(cb2, offBe, ve); vo = __viaddmin_u16x2(cb2, offBo, vo);
-            e = __viaddmin_u16x2(e, 0x00010001u, ve);
-            o = __viaddmin_u16x2(o, 0x00010001u, vo);
+            const unsigned w = cptr[y * sw];
+            e = __viaddmin_u16x2(e, 0x00010001u, even_lanes(w));
+            o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
             cptr[y * sw] = pack_lanes(e, o);
         }
 #pragma unroll 4
@@ -481,8 +511,8 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     if (c->df_sy > 0) sy = c->df_sy;
     while (qpr % sx) --sx;
     while (ny % sy) --sy;
-    const size_t smem_xy = (size_t)ny * (qpr | 1) * sizeof(uint4) + (((size_t)ny * sx + 3) & ~(size_t)3) * sizeof(unsigned) +
-                           (size_t)sy * 4 * qpr * sizeof(uint4);
+    const size_t smem_xy = (size_t)ny * (qpr | 1) * sizeof(uint4) + (((size_t)ny * (qpr | 1) + 3) & ~(size_t)3) * sizeof(unsigned) +
+                           16 * sizeof(uint4) + (size_t)sy * 4 * qpr * sizeof(uint4);
     int rc = set_smem_attrs();
     if (rc) return rc;
     if (c->df_stage != 2)
