@@ -33,10 +33,10 @@ __device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigne
     return (b3 * 256u + b2) * 65536u + (b1 * 256u + b0);
 }
 
-// bit i = byte i of w is non-zero
-__device__ __forceinline__ unsigned solid_nibble(unsigned w) {
+// byte 3 of the result = the solid mask of the four bytes of w (bit i = byte i non-zero), its high nibble 0; the other bytes are junk
+__device__ __forceinline__ unsigned solid_nibble_top(unsigned w) {
     const unsigned nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;  // bit7 set where byte != 0
-    return (((nz >> 7) * 0x00204081u) >> 21) & 15u;                              // bits 0, 8, 16, 24 -> 21..24 (no carries between the terms)
+    return (nz >> 7) * 0x01020408u;   // bits 0, 8, 16, 24 -> 24..27: the 16 partial products land on distinct bits, none on 28..31
 }
 
 // solid ? 0 : maxd for the four bytes of w
@@ -93,6 +93,7 @@ constexpr int XY_BATCH = 8;   // 16-byte loads in flight per thread
 constexpr int XY_MAX_SEG = 8;
 constexpr unsigned NO_CARRY = 0x03ffu;  // above every distance, small enough to add offsets in a u16 lane
 
+template <bool EXACT>   // the slice is a whole number of XY_THREADS * XY_BATCH quads: no guards in the stage
 __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
                                                                     uint8_t* __restrict__ df, int nx, int ny,
                                                                     int z_begin, unsigned maxd, int sx, int sy) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
 
     // ---- lut: per 4-voxel nibble of the solid mask (bit i = voxel i solid): x, y = distance of every voxel to the nearest solid of
     // the nibble as u16 lanes (v0 | v2 << 16, v1 | v3 << 16; maxd when the nibble is empty), z = carry leaving the word to the right
-    // (4 - highest solid) | carry leaving it to the left (lowest solid + 1) << 16, NO_CARRY when empty ----
+    // (4 - highest solid), w = carry leaving it to the left (lowest solid + 1), NO_CARRY when empty ----
     if (threadIdx.x < 16) {
         const unsigned n = threadIdx.x;
         unsigned d[4];
@@ -129,24 +130,28 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
             d[i] = best;
         }
         const unsigned f = n ? (unsigned)(4 - (31 - __clz(n))) : NO_CARRY, b = n ? (unsigned)__ffs(n) : NO_CARRY;
-        lut[n] = make_uint4(d[0] | (d[2] << 16), d[1] | (d[3] << 16), f | (b << 16), 0u);
+        lut[n] = make_uint4(d[0] | (d[2] << 16), d[1] | (d[3] << 16), f, b);
     }
 
-    // ---- stage: 16-byte loads (all in flight), solid mask of the quad -> its slot of the slice, carries leaving the quad -> qcar ----
+    // ---- stage: 16-byte loads (all in flight); per quad the four 4-bit solid masks, kept as byte offsets into the table (mask * 16)
+    // in the quad's slot of the slice, and the carries leaving the quad -> qcar ----
     for (int base = 0; base < nq; base += XY_THREADS * XY_BATCH) {
         uint4 v[XY_BATCH];
 #pragma unroll
         for (int i = 0; i < XY_BATCH; ++i) {
             const int q = base + i * XY_THREADS + threadIdx.x;
-            if (q < nq) v[i] = __ldg(src + q);
+            if (EXACT || q < nq) v[i] = __ldg(src + q);
         }
 #pragma unroll
         for (int i = 0; i < XY_BATCH; ++i) {
             const int q = base + i * XY_THREADS + threadIdx.x;
-            if (q < nq) {
+            if (EXACT || q < nq) {
                 const int row = (int)(((unsigned)q * rdiv) >> 20), col = q - row * qpr;
-                const unsigned m16 = solid_nibble(v[i].x) | (solid_nibble(v[i].y) << 4) | (solid_nibble(v[i].z) << 8) | (solid_nibble(v[i].w) << 12);
-                smem[(row * sq + col) << 2] = m16;
+                const unsigned nb = __byte_perm(__byte_perm(solid_nibble_top(v[i].x), solid_nibble_top(v[i].y), 0x4473),
+                                                __byte_perm(solid_nibble_top(v[i].z), solid_nibble_top(v[i].w), 0x4473), 0x5410);   // one mask per byte
+                const unsigned t = nb | (nb >> 4);
+                const unsigned m16 = __byte_perm(t, 0u, 0x4420);                      // bit j = voxel j of the quad solid
+                smem[(row * sq + col) << 2] = nb << 4;
                 // to the right: 16 - highest solid voxel; to the left: lowest solid voxel + 1
                 qcar[row * sq + col] = m16 ? (unsigned)(__clz(m16) - 15) | ((unsigned)__ffs(m16) << 16) : NO_CARRY | (NO_CARRY << 16);
             }
@@ -176,17 +181,17 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
     for (int q = threadIdx.x; q < nq; q += XY_THREADS) {
         const int row = (int)(((unsigned)q * rdiv) >> 20), col = q - row * qpr;
         const int slot = row * sq + col;
-        const unsigned m16 = smem[slot << 2], cin = qcar[slot];
+        const unsigned off4 = smem[slot << 2], cin = qcar[slot];
         uint4 l[4];
         unsigned cf[4], cb[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) l[k] = lut[(m16 >> (4 * k)) & 15u];
+        for (int k = 0; k < 4; ++k) l[k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(lut) + ((off4 >> (8 * k)) & 0xffu));
         unsigned c = cin & 0xffffu;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { cf[k] = c; c = __viaddmin_u32(c, 4u, l[k].z & 0xffffu); }
+        for (int k = 0; k < 4; ++k) { cf[k] = c; c = __viaddmin_u32(c, 4u, l[k].z); }
         c = cin >> 16;
 #pragma unroll
-        for (int k = 3; k >= 0; --k) { cb[k] = c; c = __viaddmin_u32(c, 4u, l[k].z >> 16); }
+        for (int k = 3; k >= 0; --k) { cb[k] = c; c = __viaddmin_u32(c, 4u, l[k].w); }
         unsigned w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -491,7 +496,8 @@ __global__ void edit_blocks_kernel(uint8_t* __restrict__ blocks, const int32_t* 
 static int set_smem_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
-        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
@@ -515,8 +521,10 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
                            16 * sizeof(uint4) + (size_t)sy * 4 * qpr * sizeof(uint4);
     int rc = set_smem_attrs();
     if (rc) return rc;
-    if (c->df_stage != 2)
-        df_xy_slice_kernel<<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+    if (c->df_stage != 2) {
+        if ((qpr * ny) % (XY_THREADS * XY_BATCH) == 0) df_xy_slice_kernel<true><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+        else df_xy_slice_kernel<false><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+    }
     VX_CUDA(cudaGetLastError());
     if (c->df_stage == 1) return VXRT_OK;
     const int wpp = (nx * ny) >> 2, nzr = z1 - z0;
