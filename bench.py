@@ -184,6 +184,18 @@ class CpuFrame:
         if self.use_ref:
             rb.set_scene(blocks, self.ow.df, inputs.table, inputs.blue, inputs.textures, inputs.sky)
         self.kind = "reference" if self.use_ref else "port"
+        # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the CPU
+        # arm on one core.  The oracle and oracle/_ref share one OpenMP runtime, so one omp_set_num_threads covers both.
+        try:
+            n_threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_threads = os.cpu_count() or 1
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n_threads))
+        except OSError:
+            pass
+        ob.set_threads(int(n_threads))
         self.cores = ob.get_threads()
         # parameter marshalling is shared with the GPU arm (params_for needs no Context)
         self.fr = FrameRenderer(None, frame_config(wl), inputs.grass, inputs.cactus)
