@@ -390,8 +390,16 @@ def lpv_block(local_rank, stream, flush_buf, ev, peak, with_cpu):
         us = float(np.median([a.elapsed_time(b) for a, b in pairs])) * 1e3
         lit = int(np.count_nonzero(c.lpv_download()[0]))
         alg = 3 * nvox + 4 * lit
-        out[f"repropagate_limit{limit}"] = {"us": us, "lit_voxels": lit, "launches": 1 + 3 + 1 + 4 * max(0, min(limit, 8) - 2), "algorithmic_bytes": alg,
+        out[f"repropagate_limit{limit}"] = {"us": us, "lit_voxels": lit, "launches": 1, "algorithmic_bytes": alg,
                                             "achieved_gbs": alg / (us * 1e-6) / 1e9, "frac_of_hbm_peak": alg / (us * 1e-6) / 1e9 / peak}
+        c.set_option("lpv_coop", 0)   # the same work as one kernel per phase (memset, 3 scan kernels, seed, 4 per level)
+        c.lpv_repropagate(None, limit)
+        a, b = ev(), ev()
+        flush_buf.zero_()
+        a.record(stream); c.lpv_repropagate(None, limit); b.record(stream)
+        torch.cuda.synchronize()
+        out[f"repropagate_limit{limit}"]["us_kernel_per_phase"] = a.elapsed_time(b) * 1e3
+        c.set_option("lpv_coop", 1)
     lamp = np.argwhere(blocks == 12)[len(np.argwhere(blocks == 12)) // 2]
     z, y, x = (int(v) for v in lamp)
     times = []

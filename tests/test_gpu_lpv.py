@@ -27,7 +27,15 @@ def case0():
     return blocks, wb.collect_lights(blocks, TABLE)
 
 
-def test_repropagate_matches_golden_and_oracle(ctx, case0):
+@pytest.fixture(params=[1, 0], ids=["cooperative", "kernel-per-phase"])
+def coop(ctx, request):
+    """both implementations of the repropagation: one persistent cooperative kernel (default) and one kernel per phase"""
+    ctx.set_option("lpv_coop", request.param)
+    yield request.param
+    ctx.set_option("lpv_coop", 1)
+
+
+def test_repropagate_matches_golden_and_oracle(ctx, case0, coop):
     g = lu.golden()
     blocks, lights = case0
     ctx.upload_world(blocks)
@@ -43,7 +51,7 @@ def test_repropagate_matches_golden_and_oracle(ctx, case0):
     assert np.array_equal(color, lu.dense(g["c0_l4_color_idx"], g["c0_l4_color_val"], blocks.shape))
 
 
-def test_repropagate_follows_the_queue_order(ctx, case0):
+def test_repropagate_follows_the_queue_order(ctx, case0, coop):
     g = lu.golden()
     blocks, lights = case0
     ctx.upload_world(blocks)
@@ -58,7 +66,7 @@ def test_repropagate_follows_the_queue_order(ctx, case0):
     assert np.array_equal(level, lo) and np.array_equal(color, co)
 
 
-def test_repropagate_dense_lights(ctx):
+def test_repropagate_dense_lights(ctx, coop):
     g = lu.golden()
     blocks = lu.lamp_world(1, 3000, "plains")
     ctx.upload_world(blocks)
@@ -77,7 +85,7 @@ def test_repropagate_dense_lights(ctx):
     assert np.array_equal(level, lo) and np.array_equal(color, co)
 
 
-def test_repropagate_edge_cases(ctx):
+def test_repropagate_edge_cases(ctx, coop):
     blocks = np.zeros((384, 128, 384), dtype=np.uint8).reshape(384, 128, 384)
     ctx.upload_world(blocks)
     ctx.lpv_repropagate(None, 8)               # no lights

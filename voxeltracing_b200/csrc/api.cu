@@ -171,6 +171,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "wavefront")) { c->wavefront = value != 0; return VXRT_OK; }
     if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
     if (!strcmp(name, "l2_persist")) { c->l2_persist = value != 0; return vxrt_apply_l2_policy(c); }
+    if (!strcmp(name, "lpv_coop")) { c->lpv_coop = value != 0; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
     if (!strcmp(name, "df_sx")) { c->df_sx = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
     if (!strcmp(name, "df_sy")) { c->df_sy = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
@@ -730,7 +731,7 @@ int vxrt_cuda_collect_lights(vxrt_ctx* c, int32_t* xyz_out, int32_t capacity, in
 int vxrt_cuda_lpv_repropagate(vxrt_ctx* c, const int32_t* lights_xyz, int32_t n_lights, int32_t distance_limit) {
     REQUIRE_CTX(c);
     if (distance_limit < 0 || distance_limit > 255) return vxrt_fail(VXRT_E_INVALID, "lpv_repropagate: distance_limit out of range");
-    if (n_lights < 0) return vxrt_fail(VXRT_E_INVALID, "lpv_repropagate: n_lights < 0");
+    if (n_lights < 0 || (size_t)n_lights > c->nvox) return vxrt_fail(VXRT_E_INVALID, "lpv_repropagate: n_lights out of range");
     if (!c->world_uploaded) return vxrt_fail(VXRT_E_STATE, "lpv_repropagate before a world exists");
     const int chunks = vxrt_lights_chunks(c);
     const size_t b_counts = ((size_t)(chunks + 2) * sizeof(unsigned) + 255) / 256 * 256;
@@ -743,11 +744,19 @@ int vxrt_cuda_lpv_repropagate(vxrt_ctx* c, const int32_t* lights_xyz, int32_t n_
         const unsigned n = (unsigned)n_lights;
         VX_CUDA(cudaMemcpyAsync(d_count, &n, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
         if (n_lights) VX_CUDA(cudaMemcpyAsync(d_lights, lights_xyz, (size_t)n_lights * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        rc = vxrt_launch_lpv_repropagate(c, d_lights, d_count, n_lights, distance_limit);
+        rc = c->lpv_coop ? vxrt_launch_lpv_repropagate_coop(c, d_lights, n_lights, distance_limit) : VXRT_E_UNSUPPORTED;
+        if (rc == VXRT_E_UNSUPPORTED) rc = vxrt_launch_lpv_repropagate(c, d_lights, d_count, n_lights, distance_limit);
         if (rc) return rc;
         VX_CUDA(cudaStreamSynchronize(c->stream));   // host buffers are only borrowed for the call
     } else {
         // the light list of LoadWorld, scanned on the device and consumed there: nothing comes back to the host
+        if (c->lpv_coop) {
+            rc = vxrt_launch_lpv_repropagate_coop(c, nullptr, 0, distance_limit);
+            if (rc != VXRT_E_UNSUPPORTED) {
+                if (rc == VXRT_OK) c->lpv_valid = true;
+                return rc;
+            }
+        }
         const int capacity = 1 << 20;
         rc = ensure_staging(c, b_counts + (size_t)capacity * 3 * sizeof(int32_t));
         if (rc) return rc;

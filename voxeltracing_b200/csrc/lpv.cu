@@ -16,6 +16,11 @@
 //    entries fetched 32 at a time.  An edit touches at most a few thousand voxels around it.
 #include "ctx.h"
 
+#include <stdlib.h>
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace {
 
 constexpr int LPV_THREADS = 256;
@@ -188,6 +193,242 @@ __global__ void __launch_bounds__(LPV_THREADS) lpv_write_kernel(LpvGrid g, unsig
     }
 }
 
+// ---- full repropagation as one persistent cooperative kernel --------------------------------------------------------------------
+// The multi-kernel version above runs 13 (limit 4) to 29 (limit 8) small kernels back to back, i.e. at launch latency.  Here one grid of
+// co-resident CTAs walks the same phases with grid-wide barriers: clear both volumes + count the lamps of the grid (LoadWorld's scan,
+// WorldFileHandler.cpp:53-69) | seed the lamps in scan order | per level: claim | count wins | ordered write.  Frontier sizes and
+// prefix sums are recomputed by every CTA from the per-CTA totals, so nothing but the totals crosses a barrier.
+constexpr int LPV_SCAN_VOX = 64;                               // consecutive voxels a thread owns in the lamp scan
+constexpr int LPV_SCAN_CHUNK = LPV_THREADS * LPV_SCAN_VOX;     // voxels per chunk (a chunk is scanned by one CTA)
+
+struct LpvCoopArgs {
+    LpvGrid g;
+    unsigned* claim;
+    int* front0;
+    int* front1;
+    uint8_t* wins;
+    unsigned* counts;         // per CTA (wave phases)
+    unsigned* chunk_counts;   // per chunk (lamp scan)
+    const int32_t* block_data;
+    const int32_t* lights;    // device list of a caller-provided queue order, or nullptr: scan the grid
+    int n_lights;
+    int seed_level;
+    unsigned nvox;
+};
+
+// sums of a and b over the CTA, returned to every thread
+__device__ __forceinline__ void lpv_block_sum2(unsigned& a, unsigned& b, unsigned (*sh)[LPV_THREADS / 32]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    __syncthreads();   // sh may still be read from a previous call
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    a = 0; b = 0;
+#pragma unroll
+    for (int w = 0; w < LPV_THREADS / 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
+}
+// exclusive prefix of v over the threads of the CTA; total to every thread
+__device__ __forceinline__ unsigned lpv_block_excl(unsigned v, unsigned& total, unsigned (*sh)[LPV_THREADS / 32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    __syncthreads();
+    if (lane == 31) sh[0][warp] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < LPV_THREADS / 32; ++w) {
+        const unsigned s = sh[0][w];
+        if (w < warp) before += s;
+        total += s;
+    }
+    return before + incl - v;
+}
+// lamp masks of the 64 voxels a thread owns in chunk c (bit k of m[q] = voxel 16 q + k has an emissive texture)
+__device__ __forceinline__ unsigned lpv_lamp_masks(const LpvCoopArgs& a, int c, const unsigned char* em, unsigned m[4]) {
+    const size_t first = (size_t)c * LPV_SCAN_CHUNK + (size_t)threadIdx.x * LPV_SCAN_VOX;
+    unsigned n = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        m[q] = 0;
+        if (first + 16 * q < a.nvox) {   // nvox % 16 == 0
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.g.blocks + first + 16 * q));
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[q] |= (unsigned)em[(w[k >> 2] >> (8 * (k & 3))) & 0xffu] << k;
+        }
+        n += __popc(m[q]);
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(LPV_THREADS) lpv_repropagate_coop_kernel(const LpvCoopArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned char em[256];
+    __shared__ unsigned sh[2][LPV_THREADS / 32];
+    const LpvGrid& g = a.g;
+    const int tid = threadIdx.x, G = gridDim.x;
+    const bool scan = a.lights == nullptr;
+    const int chunks = (int)((a.nvox + LPV_SCAN_CHUNK - 1) / LPV_SCAN_CHUNK), cpc = (chunks + G - 1) / G;
+    const int c0 = min(chunks, (int)blockIdx.x * cpc), c1 = min(chunks, c0 + cpc);
+    // BlockEmissiveData[id] >= 0 (row 3 of the table); ids >= 128 have no entry
+    em[tid] = tid < 128 ? (a.block_data[3 * 128 + tid] >= 0 ? 1 : 0) : 0;
+    __syncthreads();
+
+    // ---- clear both volumes (ClearEntireVolume :228-232); count the lamps of this CTA's chunks ----
+    {
+        uint4* vol = reinterpret_cast<uint4*>(g.level);   // level, then block type: 2 * nvox bytes
+        const unsigned nq = a.nvox / 8, stride = G * LPV_THREADS;
+        unsigned i = blockIdx.x * LPV_THREADS + tid;
+        for (; i + 3 * stride < nq; i += 4 * stride) {   // four stores in flight per thread: few CTAs have to cover the store latency
+            vol[i] = make_uint4(0u, 0u, 0u, 0u); vol[i + stride] = make_uint4(0u, 0u, 0u, 0u);
+            vol[i + 2 * stride] = make_uint4(0u, 0u, 0u, 0u); vol[i + 3 * stride] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (; i < nq; i += stride) vol[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (scan)
+        for (int c = c0; c < c1; ++c) {
+            unsigned m[4], mine = lpv_lamp_masks(a, c, em, m), zero = 0;
+            lpv_block_sum2(mine, zero, sh);
+            if (tid == 0) a.chunk_counts[c] = mine;
+        }
+    grid.sync();
+
+    // ---- seeds (AddLightToVolume :190-205) in queue order: the scan's ascending voxel order, or the caller's list ----
+    unsigned n;
+    if (scan) {
+        unsigned before = 0, total = 0;
+        for (int i = tid; i < chunks; i += LPV_THREADS) {
+            const unsigned v = a.chunk_counts[i];
+            total += v;
+            if (i < c0) before += v;
+        }
+        lpv_block_sum2(before, total, sh);
+        n = total;
+        unsigned running = before;
+        for (int c = c0; c < c1; ++c) {
+            unsigned m[4], chunk_total;
+            const unsigned mine = lpv_lamp_masks(a, c, em, m);
+            unsigned at = running + lpv_block_excl(mine, chunk_total, sh);
+            const size_t first = (size_t)c * LPV_SCAN_CHUNK + (size_t)tid * LPV_SCAN_VOX;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned mq = m[q];
+                while (mq) {
+                    const int k = __ffs(mq) - 1;
+                    mq &= mq - 1;
+                    const int idx = (int)(first + 16 * q + k);
+                    const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
+                    const bool in = lpv_inside(g, x, y, z);
+                    if (in) { g.level[idx] = (uint8_t)a.seed_level; g.color[idx] = g.blocks[idx]; }
+                    a.front0[at++] = in ? idx : -1;
+                }
+            }
+            running += chunk_total;
+        }
+    } else {
+        n = (unsigned)a.n_lights;
+        for (unsigned i = blockIdx.x * LPV_THREADS + tid; i < n; i += G * LPV_THREADS) {
+            const int x = a.lights[3 * i], y = a.lights[3 * i + 1], z = a.lights[3 * i + 2];
+            int idx = -1;
+            if (lpv_inside(g, x, y, z)) {
+                idx = lpv_index(g, x, y, z);
+                g.level[idx] = (uint8_t)a.seed_level;
+                g.color[idx] = g.blocks[idx];
+            }
+            a.front0[i] = idx;
+        }
+    }
+    grid.sync();
+
+    // ---- one wave per level ----
+    const int* front = a.front0;
+    int* next = a.front1;
+    for (int wave = 0; wave + 3 <= a.seed_level && n > 0; ++wave) {
+        // claim
+        for (unsigned i = blockIdx.x * LPV_THREADS + tid; i < n; i += G * LPV_THREADS) {
+            const int idx = front[i];
+            if (idx < 0) continue;
+            const int cur = g.level[idx];
+            if (cur < 3) continue;
+            const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                int dx, dy, dz;
+                lpv_dir(k, true, dx, dy, dz);
+                if (!lpv_inside(g, x + dx, y + dy, z + dz)) continue;
+                const int q = lpv_index(g, x + dx, y + dy, z + dz);
+                if (g.blocks[q] == 0 && (int)g.level[q] + 2 < cur) atomicMin(a.claim + q, i * 6u + (unsigned)k);
+            }
+        }
+        grid.sync();
+        // which claims were won; per-CTA totals
+        unsigned begin, end;
+        lpv_chunk(n, begin, end);
+        {
+            unsigned mine = 0, zero = 0;
+            for (unsigned i = begin + tid; i < end; i += LPV_THREADS) {
+                const int idx = front[i];
+                unsigned m = 0;
+                if (idx >= 0 && g.level[idx] >= 3) {
+                    const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        int dx, dy, dz;
+                        lpv_dir(k, true, dx, dy, dz);
+                        if (lpv_inside(g, x + dx, y + dy, z + dz) && __ldcg(a.claim + lpv_index(g, x + dx, y + dy, z + dz)) == i * 6u + (unsigned)k) m |= 1u << k;
+                    }
+                }
+                a.wins[i] = (uint8_t)m;
+                mine += __popc(m);
+            }
+            lpv_block_sum2(mine, zero, sh);
+            if (tid == 0) a.counts[blockIdx.x] = mine;
+        }
+        grid.sync();
+        // ordered write of the winners: this CTA's offset and the size of the next wave from the per-CTA totals
+        unsigned before = 0, total = 0;
+        for (int i = tid; i < G; i += LPV_THREADS) {
+            const unsigned v = __ldcg(a.counts + i);
+            total += v;
+            if (i < (int)blockIdx.x) before += v;
+        }
+        lpv_block_sum2(before, total, sh);
+        unsigned running = before;
+        for (unsigned base = begin; base < end; base += LPV_THREADS) {
+            const unsigned i = base + tid;
+            unsigned m = i < end ? a.wins[i] : 0u, tile_total;
+            const unsigned cnt = __popc(m);
+            unsigned at = running + lpv_block_excl(cnt, tile_total, sh);
+            if (m) {
+                const int idx = front[i];
+                const uint8_t next_level = (uint8_t)(g.level[idx] - 1), type = g.color[idx];
+                const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    int dx, dy, dz;
+                    lpv_dir(k, true, dx, dy, dz);
+                    const int q = lpv_index(g, x + dx, y + dy, z + dz);
+                    g.color[q] = type;
+                    g.level[q] = next_level;
+                    a.claim[q] = NO_CLAIM;
+                    next[at++] = q;
+                }
+            }
+            running += tile_total;
+        }
+        n = total;
+        const int* t = front; front = next; next = const_cast<int*>(t);
+        grid.sync();
+    }
+}
+
 // ---- block edits: the exact FIFO of DepropogateVolume / PropogateVolume, one warp -------------------------------------------------
 
 // a queue entry: x + 1, y + 1, z + 1 in 16 bits each (the edit queues the six neighbours of a voxel unchecked, so -1 .. n occur) and,
@@ -305,7 +546,7 @@ __global__ void __launch_bounds__(32) lpv_edit_kernel(LpvGrid g, const int32_t* 
 
 }  // namespace
 
-// work memory: claim[N] u32 | front[2][N] i32 | wins[N] u8 | counts[1024] | sizes[16] | overflow
+// work memory: claim[N] u32 | front[2][N] i32 | wins[N] u8 | counts[1024] | sizes[16] | overflow[16] | chunk_counts[N / 16384]
 static int lpv_ensure(vxrt_ctx* c) {
     const size_t n = c->nvox;
     if (!c->d_lpv) {
@@ -313,7 +554,7 @@ static int lpv_ensure(vxrt_ctx* c) {
         VX_CUDA(cudaMemsetAsync(c->d_lpv, 0, 2 * n, c->stream));   // CreateVolume clears both volumes (:76-91, :99-100)
     }
     if (!c->d_lpv_work) {
-        const size_t bytes = 4 * n + 8 * n + n + (1024 + 16 + 16) * sizeof(unsigned);
+        const size_t bytes = 4 * n + 8 * n + n + (1024 + 16 + 16 + (n + LPV_SCAN_CHUNK - 1) / LPV_SCAN_CHUNK) * sizeof(unsigned);
         VX_CUDA(cudaMalloc(&c->d_lpv_work, bytes));
         VX_CUDA(cudaMemsetAsync(c->d_lpv_work, 0xff, 4 * n, c->stream));   // claim[] = NO_CLAIM; every wave leaves it that way
     }
@@ -328,6 +569,7 @@ struct LpvWork {
     unsigned* counts;
     unsigned* sizes;
     int* overflow;
+    unsigned* chunk_counts;
 };
 LpvWork lpv_work(const vxrt_ctx* c) {
     LpvWork w;
@@ -340,6 +582,7 @@ LpvWork lpv_work(const vxrt_ctx* c) {
     w.counts = (unsigned*)(p + 13 * n);   // nvox % 16 == 0 (vxrt_cuda_create)
     w.sizes = w.counts + 1024;
     w.overflow = (int*)(w.sizes + 16);
+    w.chunk_counts = (unsigned*)(w.overflow + 16);
     return w;
 }
 LpvGrid lpv_grid(const vxrt_ctx* c) {
@@ -373,6 +616,34 @@ int vxrt_launch_lpv_repropagate(vxrt_ctx* c, const int32_t* d_lights, const unsi
         c->launches += 4;
     }
     VX_CUDA(cudaGetLastError());
+    return VXRT_OK;
+}
+
+// d_lights == nullptr: the lamps are scanned from the grid inside the kernel.  Returns VXRT_E_UNSUPPORTED when the device cannot
+// launch cooperatively (the caller falls back to the multi-kernel path).
+int vxrt_launch_lpv_repropagate_coop(vxrt_ctx* c, const int32_t* d_lights, int n_lights, int limit) {
+    static int coop_grid = -1;   // 0: unsupported
+    if (coop_grid < 0) {
+        int supported = 0, per_sm = 0;
+        if (cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess) supported = 0;
+        if (supported && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lpv_repropagate_coop_kernel, LPV_THREADS, 0) != cudaSuccess) per_sm = 0;
+        int cap = 2;                  // the cost of a grid-wide barrier grows with the number of CTAs (tools/debug/time_lpv.py)
+        if (const char* e = getenv("VXRT_LPV_CTAS_PER_SM")) cap = atoi(e) > 0 ? atoi(e) : cap;
+        if (per_sm > cap) per_sm = cap;
+        coop_grid = supported ? per_sm * c->sm_count : 0;
+        if (coop_grid > 1024) coop_grid = 1024;
+    }
+    if (coop_grid <= 0) return VXRT_E_UNSUPPORTED;
+    int rc = lpv_ensure(c);
+    if (rc) return rc;
+    const LpvWork w = lpv_work(c);
+    LpvCoopArgs a;
+    a.g = lpv_grid(c); a.claim = w.claim; a.front0 = w.front[0]; a.front1 = w.front[1]; a.wins = w.wins; a.counts = w.counts;
+    a.chunk_counts = w.chunk_counts; a.block_data = c->d_block_data; a.lights = d_lights; a.n_lights = n_lights;
+    a.seed_level = limit > 8 ? 8 : limit; a.nvox = (unsigned)c->nvox;
+    void* args[] = {&a};
+    VX_CUDA(cudaLaunchCooperativeKernel((void*)lpv_repropagate_coop_kernel, dim3(coop_grid), dim3(LPV_THREADS), args, 0, c->stream));
+    c->launches += 1;
     return VXRT_OK;
 }
 
