@@ -141,6 +141,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
     cudaFree(c->d_lpv); cudaFree(c->d_lpv_work);
+    if (c->h_lpv_flag) cudaFreeHost(c->h_lpv_flag);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);

@@ -87,6 +87,8 @@ struct vxrt_ctx {
 
     uint8_t* d_lpv = nullptr;       // light propagation volume (lpv.cu): light level [nvox], then block type [nvox]
     void* d_lpv_work = nullptr;     // claim keys, the two frontiers / edit queues, scan scratch
+    int* h_lpv_flag = nullptr;      // pinned, device-mapped: queue-overflow flag of the edit kernel
+    int* d_lpv_flag = nullptr;
     bool lpv_valid = false;
     bool lpv_coop = true;           // one cooperative kernel for the repropagation (set_option "lpv_coop"); 0 = one kernel per phase
 

@@ -446,11 +446,11 @@ struct LpvQueue {
     unsigned mask;          // capacity - 1 (power of two)
     unsigned head, tail;    // warp-uniform
     // entries of the lanes with `pred`, in lane order (the reference pushes in direction order)
-    __device__ __forceinline__ void push(bool pred, unsigned long long e, int* overflow) {
+    __device__ __forceinline__ void push(bool pred, unsigned long long e, int& overflow) {
         const unsigned m = __ballot_sync(0xffffffffu, pred);
         if (pred) __stcg(q + ((tail + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))) & mask), e);
         tail += __popc(m);
-        if (tail - head > mask && (threadIdx.x & 31) == 0) *overflow = 1;
+        if (tail - head > mask) overflow = 1;
     }
 };
 
@@ -460,8 +460,9 @@ __device__ __forceinline__ int lpv_get_level(const LpvGrid& g, int x, int y, int
 
 __global__ void __launch_bounds__(32) lpv_edit_kernel(LpvGrid g, const int32_t* __restrict__ block_data, int op, int px, int py, int pz, int block,
                                                       int seed_level, unsigned long long* light_q, unsigned long long* removal_q, unsigned mask,
-                                                      int* overflow) {
+                                                      int* overflow_out) {
     const int lane = threadIdx.x;
+    int overflow = 0;   // warp-uniform; reported through host-mapped memory at the end
     LpvQueue lq{light_q, mask, 0u, 0u}, rq{removal_q, mask, 0u, 0u};
     // GetBlockEmissiveTexture(block) >= 0 / HasEmissiveTexture(block): the emissive row of the block table; ids without an entry have none
     const bool emissive = block >= 0 && block < 128 && block_data[3 * 128 + block] >= 0;
@@ -542,6 +543,7 @@ __global__ void __launch_bounds__(32) lpv_edit_kernel(LpvGrid g, const int32_t* 
             lq.head += batch;
         }
     }
+    if (lane == 0) { *overflow_out = overflow; __threadfence_system(); }
 }
 
 }  // namespace
@@ -654,14 +656,16 @@ int vxrt_launch_lpv_edit(vxrt_ctx* c, int op, int x, int y, int z, int block, in
     // the two queues share the frontier buffers: 4 N bytes each = N / 2 entries, rounded down to a power of two
     unsigned cap = 1;
     while ((size_t)cap * 2 * sizeof(unsigned long long) <= 4 * c->nvox) cap *= 2;
-    VX_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), c->stream));
+    // the kernel reports queue overflow through pinned host memory it writes directly: one launch + one stream synchronisation per edit
+    if (!c->h_lpv_flag) {
+        VX_CUDA(cudaHostAlloc((void**)&c->h_lpv_flag, sizeof(int), cudaHostAllocMapped));
+        VX_CUDA(cudaHostGetDevicePointer((void**)&c->d_lpv_flag, c->h_lpv_flag, 0));
+    }
     lpv_edit_kernel<<<1, 32, 0, c->stream>>>(lpv_grid(c), c->d_block_data, op, x, y, z, block, limit > 8 ? 8 : limit,
-                                             (unsigned long long*)w.front[0], (unsigned long long*)w.front[1], cap - 1, w.overflow);
+                                             (unsigned long long*)w.front[0], (unsigned long long*)w.front[1], cap - 1, c->d_lpv_flag);
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
-    int h = 0;
-    VX_CUDA(cudaMemcpyAsync(&h, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
-    *overflowed = h;
+    *overflowed = *(volatile int*)c->h_lpv_flag;
     return VXRT_OK;
 }
