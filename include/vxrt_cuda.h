@@ -495,6 +495,11 @@ int vxrt_cuda_lpv_repropagate(vxrt_ctx* ctx, const int32_t* lights_xyz, int32_t 
  * has applied the edit to the grid (SetBlock precedes the propagation in the reference).  Whether `block` is a lamp comes from the
  * emissive row of vxrt_cuda_set_block_data.  (x, y, z) must lie strictly inside the grid (:267-271), else VXRT_E_INVALID.          */
 int vxrt_cuda_lpv_edit(vxrt_ctx* ctx, int32_t op, int32_t x, int32_t y, int32_t z, int32_t block, int32_t distance_limit);
+/* BlockAverageColorData of Core/Shaders/Volumetrics/PrecomputeAverageBlockColor.comp (dispatched once by Volumetrics::CreateVolume,
+ * VolumetricFloodFill.cpp:102-123): per block id the average colour of its albedo layer (ten trilinear samples at LOD 5.5 ... 8, / 10,
+ * pow 1.8; zero for ids without an albedo layer), from the albedo array of vxrt_cuda_set_texture_array and the table of
+ * vxrt_cuda_set_block_data.  Kept on the device for the consumers of the block-type volume; rgba_out: HOST memory for 128*4 floats or NULL. */
+int vxrt_cuda_lpv_average_colors(vxrt_ctx* ctx, float* rgba_out);
 /* The volumes to / from HOST memory (nx*ny*nz bytes each; download: either may be NULL).  Upload = Volumetrics::Reupload (:207-216). */
 int vxrt_cuda_lpv_download(vxrt_ctx* ctx, uint8_t* level, uint8_t* block_type);
 int vxrt_cuda_lpv_upload(vxrt_ctx* ctx, const uint8_t* level, const uint8_t* block_type);

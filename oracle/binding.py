@@ -378,6 +378,14 @@ class OracleScene:
         f = np.ascontiguousarray(faces, dtype=np.float32)
         self.L.vxo_scene_set_skymap(self.h, f.shape[1], _p(f))
 
+    def lpv_average_colors(self) -> np.ndarray:
+        """BlockAverageColorData of PrecomputeAverageBlockColor.comp: (128, 4) float32"""
+        out = np.zeros((128, 4), dtype=np.float32)
+        self.L.vxo_scene_lpv_average_colors.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.vxo_scene_lpv_average_colors.restype = None
+        self.L.vxo_scene_lpv_average_colors(self.h, _p(out))
+        return out
+
     def texture_level(self, kind, level, layers, size):
         s = max(size >> level, 1)
         out = np.zeros((layers, s, s, 4), dtype=np.uint8)

@@ -40,7 +40,9 @@ SHADERS = {
     "SVGFTemporal": ("SVGF/TemporalFilter.glsl", "fragment"),
     "SVGFVariance": ("SVGF/VarianceEstimate.glsl", "fragment"),
     "SVGFSpatial": ("SVGF/SpatialFilter.glsl", "fragment"),
-    "SVGFPreSpatial": ("Spatial3x3Initial.glsl", "fragment"),   # the 3 x 3 pass in front of the temporal filter (Pipeline.cpp:2381-2424)
+    "SVGFPreSpatial": ("Spatial3x3Initial.glsl", "fragment"),
+    # average colour per block type for the light propagation volume (Volumetrics::CreateVolume, VolumetricFloodFill.cpp:102-123)
+    "LPVAverageColor": ("Volumetrics/PrecomputeAverageBlockColor.comp", "compute"),   # the 3 x 3 pass in front of the temporal filter (Pipeline.cpp:2381-2424)
     # sun-shadow denoiser
     "ShadowTemporal": ("ShadowTemporalFilter.glsl", "fragment"),
     "ShadowFilter": ("ShadowFilter.glsl", "fragment"),
@@ -371,7 +373,11 @@ def main():
         text = (sdir / SHADERS[n][0]).read_text(errors="replace")
         if SHADERS[n][1] == "extract":
             text = EXTRACT[n]["prelude"] + extract_functions(text, EXTRACT[n]["functions"])
-        cpp.write_text(transform(n, text, SHADERS[n][1]))
+        code = transform(n, text, SHADERS[n][1])
+        if n == "LPVAverageColor":   # the one buffer a shader of this set writes: a plain array instead of the read-only SSBO view
+            code, k = re.subn(r"ssbo_array<vec4,\s*\(128\)>\s+BlockAverageColorData;", "vec4 BlockAverageColorData[128];", code)
+            assert k == 1
+        cpp.write_text(code)
         obj = GEN / f"{n}.o"
         cmd = ["g++", "-std=gnu++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fopenmp", "-w", "-fpermissive",
                "-c", str(cpp), "-o", str(obj)]

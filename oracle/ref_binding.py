@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 from voxeltracing_b200 import abi  # noqa: E402  (struct layouts only)
 
 LIB_PATH = ROOT / "oracle" / "_ref" / "libvxrt_ref.so"
-HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256, "raycast": 512, "svgf_temporal": 1024, "svgf_variance": 2048, "svgf_spatial": 4096, "shadow_temporal": 8192, "shadow_filter": 16384, "specular_temporal": 32768, "reflection_denoise": 65536, "svgf_prespatial": 131072}
+HAVE = {"df": 7, "initial": 8, "shadow": 16, "gbuffer": 32, "diffuse": 64, "reflection": 128, "color": 256, "raycast": 512, "svgf_temporal": 1024, "svgf_variance": 2048, "svgf_spatial": 4096, "shadow_temporal": 8192, "shadow_filter": 16384, "specular_temporal": 32768, "reflection_denoise": 65536, "svgf_prespatial": 131072, "lpv_average": 262144}
 _lib = None
 
 
@@ -98,6 +98,13 @@ def set_scene(blocks, df, table, blue_noise, textures, skymap):
         L.vxref_set_texture_array(kind, tex.shape[0], tex.shape[2], tex.shape[1], _p(tex))
     f = np.ascontiguousarray(skymap, np.float32)
     L.vxref_set_skymap(f.shape[1], _p(f))
+
+
+def lpv_average_colors() -> np.ndarray:
+    """PrecomputeAverageBlockColor.comp on the scene of set_scene(): (128, 4) float32"""
+    out = np.zeros((128, 4), dtype=np.float32)
+    lib().vxref_lpv_average_colors(_p(out))
+    return out
 
 
 def generate_gbuffer(p: abi.GBufferParams, g_inv_t, g_normal, g_block):

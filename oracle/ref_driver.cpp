@@ -52,6 +52,9 @@ thread_local uvec3 gl_GlobalInvocationID;
 #undef sqr
 #include "SVGFPreSpatial.cpp"
 #endif
+#ifdef VXREF_HAVE_LPVAverageColor
+#include "LPVAverageColor.cpp"
+#endif
 #ifdef VXREF_HAVE_ShadowTemporal
 #include "ShadowTemporal.cpp"
 #endif
@@ -118,6 +121,9 @@ int32_t vxref_available(void) {
 #endif
 #ifdef VXREF_HAVE_SVGFPreSpatial
     m |= 131072;
+#endif
+#ifdef VXREF_HAVE_LPVAverageColor
+    m |= 262144;
 #endif
 #ifdef VXREF_HAVE_ShadowTemporal
     m |= 8192;
@@ -654,6 +660,19 @@ extern "C" void vxref_svgf_prespatial(const vxrt_svgf_prespatial_params* p, cons
             out->x[i] = vxo::float_to_half(S::o_Utility);
             for (int c = 0; c < 2; ++c) out->aosky[2 * i + c] = vxo::float_to_unorm8(S::o_AOSky[c]);
         }
+}
+#endif
+
+#ifdef VXREF_HAVE_LPVAverageColor
+/* PrecomputeAverageBlockColor.comp as dispatched by Volumetrics::CreateVolume (VolumetricFloodFill.cpp:102-123): one invocation, the scene's
+ * albedo array and block table; out = BlockAverageColorData, 128 x vec4 */
+extern "C" void vxref_lpv_average_colors(float* out512) {
+    namespace S = shader_LPVAverageColor;
+    S::u_BlockAlbedo.t = &g_scene.tex[0];
+    BIND_BLOCK_SSBO(S)
+    S::shader_reset(); S::shader_main();
+    for (int i = 0; i < 128; ++i)
+        for (int c = 0; c < 4; ++c) out512[4 * i + c] = S::BlockAverageColorData[i][c];
 }
 #endif
 

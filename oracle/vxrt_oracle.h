@@ -104,6 +104,7 @@ void vxo_scene_set_blue_noise(vxo_scene* s, const int32_t* data, int32_t count);
 void vxo_scene_set_texture_array(vxo_scene* s, int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba);
 void vxo_scene_set_skymap(vxo_scene* s, int32_t res, const float* rgb_faces);
 /* mip level `level` of array `kind` as built by the pinned glGenerateMipmap model (for tests) */
+void vxo_scene_lpv_average_colors(const vxo_scene* s, float* out512);
 int32_t vxo_scene_texture_level(const vxo_scene* s, int32_t kind, int32_t level, uint8_t* out, int64_t out_bytes);
 
 /* GenerateGBuffer.glsl main(); inputs = primary attachments (1/t R32F, face R8, block R8) at gw x gh */

@@ -65,6 +65,31 @@ int32_t vxo_scene_texture_level(const vxo_scene* s, int32_t kind, int32_t level,
     return 0;
 }
 
+/* PrecomputeAverageBlockColor.comp main() (:23-54), dispatched once by Volumetrics::CreateVolume (VolumetricFloodFill.cpp:102-123):
+ * BlockAverageColorData[id] = pow((five samples of the block's albedo layer at LOD 8 + five at LOD 6 / 6.5 / 6.5 / 5.5 / 5.5) / 10, 1.8);
+ * (0, 0, 0, 0) for ids without an albedo layer.  The samples sit at (0.5, 0.25, 0.75, 1.0, 0.0)^2 of the layer. */
+void vxo_scene_lpv_average_colors(const vxo_scene* s, float* out512) {
+    static const float at[5] = {0.5f, 0.25f, 0.75f, 1.0f, 0.0f};
+    static const float lod2[5] = {6.0f, 6.5f, 6.5f, 5.5f, 5.5f};
+    for (int id = 0; id < 128; ++id) {
+        float* o = out512 + 4 * id;
+        o[0] = o[1] = o[2] = o[3] = 0.0f;
+        const int layer = s->block_data[id];   /* BlockAlbedoData */
+        if (layer < 0) continue;
+        v3 a = V3(0.0f, 0.0f, 0.0f), b = a;
+        for (int k = 0; k < 5; ++k) {
+            const v4 t = texarray_sample(s->tex[0], at[k], at[k], (float)layer, 8.0f);
+            a = k == 0 ? V3(t.x, t.y, t.z) : V3(a.x + t.x, a.y + t.y, a.z + t.z);
+        }
+        for (int k = 0; k < 5; ++k) {
+            const v4 t = texarray_sample(s->tex[0], at[k], at[k], (float)layer, lod2[k]);
+            b = k == 0 ? V3(t.x, t.y, t.z) : V3(b.x + t.x, b.y + t.y, b.z + t.z);
+        }
+        const float d = 5.0f * 2.0f;
+        o[0] = powf((a.x + b.x) / d, 1.8f); o[1] = powf((a.y + b.y) / d, 1.8f); o[2] = powf((a.z + b.z) / d, 1.8f);
+    }
+}
+
 }  // extern "C"
 
 /* ------------------------------------------------------------------------------------------------

@@ -55,6 +55,16 @@ def main():
         if limit == 4:
             out[f"edit_l{limit}_level_idx"], out[f"edit_l{limit}_level_val"] = lu.sparse(level)
             out[f"edit_l{limit}_color_idx"], out[f"edit_l{limit}_color_val"] = lu.sparse(color)
+    # BlockAverageColorData of PrecomputeAverageBlockColor.comp (compiled through oracle/_ref) on the seeded test textures
+    import scene_util as su
+    from oracle import binding as ob
+    from oracle import ref_binding as rb
+    assert rb.available("lpv_average")
+    for size in (64, 512):
+        inp = su.SceneInputs(size)
+        ow = ob.OracleWorld(np.zeros((16, 16, 16), np.uint8))
+        rb.set_scene(np.zeros((384, 128, 384), np.uint8), np.zeros((384, 128, 384), np.uint8), inp.table, inp.blue, inp.textures, inp.sky)
+        out[f"average_colors_{size}"] = rb.lpv_average_colors()
     np.savez_compressed(lu.GOLD, **out)
     print("wrote", lu.GOLD, lu.GOLD.stat().st_size, "bytes")
 

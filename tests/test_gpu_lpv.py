@@ -166,3 +166,25 @@ def test_edit_after_upload_and_argument_checks(ctx, case0):
             ctx.lpv_edit(1, bad, 12, 8)
     with pytest.raises(engine.VxrtError):
         ctx.lpv_edit(2, (5, 5, 5), 12, 8)
+
+
+def test_average_block_colors():
+    """vxrt_cuda_lpv_average_colors (PrecomputeAverageBlockColor.comp): ten trilinear samples are exact arithmetic shared with the oracle,
+    the final pow(x, 1.8) is CUDA's powf vs libm's: 4 float ulps."""
+    import scene_util as su
+    from oracle import binding as ob
+    g = lu.golden()
+    for size in (64, 512):
+        inp = su.SceneInputs(size)
+        c = engine.Context(0, (64, 32, 64))
+        try:
+            with pytest.raises(engine.VxrtError):
+                c.lpv_average_colors()            # no albedo array yet
+            inp.apply_to_context(c)
+            got = c.lpv_average_colors()
+        finally:
+            c.close()
+        want = g[f"average_colors_{size}"]
+        assert np.array_equal(got == 0, want == 0)
+        assert np.all(np.abs(got - want) <= 4 * np.spacing(np.abs(want))), np.abs(got - want).max()
+        assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.9

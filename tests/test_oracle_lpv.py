@@ -105,3 +105,18 @@ def test_edit_sequence_matches_reference(case0):
         wb.lpv_edit(b, e[0], e[1], e[2], e[3], 6, lo, co)
         wb.ref_lpv_edit(b, e[0], e[1], e[2], e[3], 6, lr, cr)
         assert np.array_equal(lo, lr) and np.array_equal(co, cr), e
+
+
+def test_average_block_colors_match_golden():
+    """BlockAverageColorData (PrecomputeAverageBlockColor.comp): oracle == the compiled shader's output in the fixture, bit for bit"""
+    import scene_util as su
+    from oracle import binding as ob
+    g = lu.golden()
+    for size in (64, 512):
+        inp = su.SceneInputs(size)
+        sc = ob.OracleScene(ob.OracleWorld(np.zeros((16, 16, 16), np.uint8)))
+        inp.apply_to_oracle(sc)
+        a = sc.lpv_average_colors()
+        assert np.array_equal(a.view(np.uint32), g[f"average_colors_{size}"].view(np.uint32)), size
+        has = inp.table[0] >= 0
+        assert (a[~has] == 0).all() and (a[has, :3] > 0).all() and (a[:, 3] == 0).all() and a.max() <= 1.0

@@ -142,6 +142,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
     cudaFree(c->d_lpv); cudaFree(c->d_lpv_work);
     if (c->h_lpv_flag) cudaFreeHost(c->h_lpv_flag);
+    cudaFree(c->d_lpv_avg);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
@@ -785,6 +786,18 @@ int vxrt_cuda_lpv_edit(vxrt_ctx* c, int32_t op, int32_t x, int32_t y, int32_t z,
     if (rc) return rc;
     if (overflowed) return vxrt_fail(VXRT_E_NOMEM, "lpv_edit: queue capacity exceeded");
     c->lpv_valid = true;
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_average_colors(vxrt_ctx* c, float* rgba_out) {
+    REQUIRE_CTX(c);
+    if (!c->tex_set[VXRT_TEX_ALBEDO]) return vxrt_fail(VXRT_E_STATE, "lpv_average_colors: the albedo texture array has not been set");
+    int rc = vxrt_launch_lpv_average_colors(c);
+    if (rc) return rc;
+    if (rgba_out) {
+        VX_CUDA(cudaMemcpyAsync(rgba_out, c->d_lpv_avg, 128 * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return VXRT_OK;
 }
 

@@ -87,6 +87,7 @@ struct vxrt_ctx {
 
     uint8_t* d_lpv = nullptr;       // light propagation volume (lpv.cu): light level [nvox], then block type [nvox]
     void* d_lpv_work = nullptr;     // claim keys, the two frontiers / edit queues, scan scratch
+    float* d_lpv_avg = nullptr;     // BlockAverageColorData: 128 x vec4 (PrecomputeAverageBlockColor.comp)
     int* h_lpv_flag = nullptr;      // pinned, device-mapped: queue-overflow flag of the edit kernel
     int* d_lpv_flag = nullptr;
     bool lpv_valid = false;
@@ -168,6 +169,7 @@ int vxrt_launch_collect_lights(vxrt_ctx* c, unsigned* d_counts, int32_t* d_out, 
 int vxrt_lpv_ensure(vxrt_ctx* c);
 int vxrt_launch_lpv_repropagate(vxrt_ctx* c, const int32_t* d_lights, const unsigned* d_count, int capacity, int limit);
 int vxrt_launch_lpv_repropagate_coop(vxrt_ctx* c, const int32_t* d_lights, int n_lights, int limit);
+int vxrt_launch_lpv_average_colors(vxrt_ctx* c);
 int vxrt_launch_lpv_edit(vxrt_ctx* c, int op, int x, int y, int z, int block, int limit, int* overflowed);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);

@@ -15,6 +15,7 @@
 //    a node are distinct voxels, so handling them together is the sequential order), pushes in direction order by ballot, queue
 //    entries fetched 32 at a time.  An edit touches at most a few thousand voxels around it.
 #include "ctx.h"
+#include "texture.cuh"
 
 #include <stdlib.h>
 
@@ -429,6 +430,33 @@ __global__ void __launch_bounds__(LPV_THREADS) lpv_repropagate_coop_kernel(const
     }
 }
 
+// ---- PrecomputeAverageBlockColor.comp main() (:23-54), dispatched once by Volumetrics::CreateVolume (VolumetricFloodFill.cpp:102-123) ----
+// One thread per block id: ten trilinear samples of the block's albedo layer (five at LOD 8, five at LOD 6 / 6.5 / 6.5 / 5.5 / 5.5),
+// summed in the shader's order, / 10, pow 1.8.  The consumers (u_LPVGI of the reflection trace, the colour pass) index it with the block type
+// volume.
+__global__ void __launch_bounds__(128) lpv_average_colors_kernel(TexArrayDev albedo, const int32_t* __restrict__ block_data, float4* __restrict__ out) {
+    const int id = threadIdx.x;
+    const int layer = block_data[id];   // BlockAlbedoData
+    float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (layer >= 0) {
+        const float at[5] = {0.5f, 0.25f, 0.75f, 1.0f, 0.0f}, lod2[5] = {6.0f, 6.5f, 6.5f, 5.5f, 5.5f};
+        f3 a = F3(0.0f, 0.0f, 0.0f), b = a;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const f4 t = texarray_sample(albedo, at[k], at[k], (float)layer, 8.0f);
+            a = k == 0 ? F3(t.x, t.y, t.z) : F3(a.x + t.x, a.y + t.y, a.z + t.z);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const f4 t = texarray_sample(albedo, at[k], at[k], (float)layer, lod2[k]);
+            b = k == 0 ? F3(t.x, t.y, t.z) : F3(b.x + t.x, b.y + t.y, b.z + t.z);
+        }
+        const float d = 5.0f * 2.0f;
+        o = make_float4(powf((a.x + b.x) / d, 1.8f), powf((a.y + b.y) / d, 1.8f), powf((a.z + b.z) / d, 1.8f), 0.0f);
+    }
+    out[id] = o;
+}
+
 // ---- block edits: the exact FIFO of DepropogateVolume / PropogateVolume, one warp -------------------------------------------------
 
 // a queue entry: x + 1, y + 1, z + 1 in 16 bits each (the edit queues the six neighbours of a voxel unchecked, so -1 .. n occur) and,
@@ -645,6 +673,14 @@ int vxrt_launch_lpv_repropagate_coop(vxrt_ctx* c, const int32_t* d_lights, int n
     a.seed_level = limit > 8 ? 8 : limit; a.nvox = (unsigned)c->nvox;
     void* args[] = {&a};
     VX_CUDA(cudaLaunchCooperativeKernel((void*)lpv_repropagate_coop_kernel, dim3(coop_grid), dim3(LPV_THREADS), args, 0, c->stream));
+    c->launches += 1;
+    return VXRT_OK;
+}
+
+int vxrt_launch_lpv_average_colors(vxrt_ctx* c) {
+    if (!c->d_lpv_avg) VX_CUDA(cudaMalloc(&c->d_lpv_avg, 128 * sizeof(float4)));
+    lpv_average_colors_kernel<<<1, 128, 0, c->stream>>>(c->tex[0], c->d_block_data, (float4*)c->d_lpv_avg);
+    VX_CUDA(cudaGetLastError());
     c->launches += 1;
     return VXRT_OK;
 }

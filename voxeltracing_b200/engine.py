@@ -399,6 +399,12 @@ class Context:
         """The light-volume half of one block edit (Core/World.cpp:273-333 place, :395-446 break, :482-485); the grid already holds the edit."""
         self._check(self._lib.vxrt_cuda_lpv_edit(self._h, int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(distance_limit)))
 
+    def lpv_average_colors(self) -> np.ndarray:
+        """BlockAverageColorData (PrecomputeAverageBlockColor.comp, VolumetricFloodFill.cpp:102-123): (128, 4) float32."""
+        out = np.zeros((128, 4), dtype=np.float32)
+        self._check(self._lib.vxrt_cuda_lpv_average_colors(self._h, _p(out)))
+        return out
+
     def lpv_download(self):
         """(level, block_type) volumes indexed [z, y, x]."""
         nx, ny, nz = self.dims
