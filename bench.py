@@ -402,16 +402,23 @@ def lpv_block(local_rank, stream, flush_buf, ev, peak, with_cpu):
         c.set_option("lpv_coop", 1)
     lamp = np.argwhere(blocks == 12)[len(np.argwhere(blocks == 12)) // 2]
     z, y, x = (int(v) for v in lamp)
-    times = []
+    times, dev = [], []
     for _ in range(5):   # break the lamp, place it again (limit 8: the largest removal)
         for op, blk in ((0, 0), (1, 12)):
             c.edit_blocks(np.array([[x, y, z, blk]], dtype=np.int32))
             torch.cuda.synchronize()
+            a, b = ev(), ev()
             t0 = time.perf_counter()
+            a.record(stream)
             c.lpv_edit(op, (x, y, z), 12, 8)
+            b.record(stream)
             times.append((time.perf_counter() - t0) * 1e3)
+            torch.cuda.synchronize()
+            dev.append(a.elapsed_time(b) * 1e3)
     out["edit_limit8"] = {"ms_break_lamp": float(np.median(times[0::2])), "ms_place_lamp": float(np.median(times[1::2])),
-                          "note": "wall clock around the synchronous ABI call; one warp replays the reference's queues in order"}
+                          "us_on_device_break_lamp": float(np.median(dev[0::2])), "us_on_device_place_lamp": float(np.median(dev[1::2])),
+                          "note": "ms: wall clock around the synchronous ABI call (launch + stream synchronisation from an idle GPU); us_on_device: CUDA "
+                                  "events around the same call; one warp replays the reference's queues in order"}
     if with_cpu:
         from oracle import world_binding as wb
         lights = wb.collect_lights(blocks, table)

@@ -351,12 +351,12 @@ __global__ void __launch_bounds__(LPV_THREADS) lpv_repropagate_coop_kernel(const
     const int* front = a.front0;
     int* next = a.front1;
     for (int wave = 0; wave + 3 <= a.seed_level && n > 0; ++wave) {
+        // every node of a wave carries the same level (the seeds min(limit, 8), each wave one less): no need to load it
+        const int cur = a.seed_level - wave;
         // claim
         for (unsigned i = blockIdx.x * LPV_THREADS + tid; i < n; i += G * LPV_THREADS) {
             const int idx = front[i];
             if (idx < 0) continue;
-            const int cur = g.level[idx];
-            if (cur < 3) continue;
             const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(LPV_THREADS) lpv_repropagate_coop_kernel(const
             for (unsigned i = begin + tid; i < end; i += LPV_THREADS) {
                 const int idx = front[i];
                 unsigned m = 0;
-                if (idx >= 0 && g.level[idx] >= 3) {
+                if (idx >= 0) {
                     const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(LPV_THREADS) lpv_repropagate_coop_kernel(const
             unsigned at = running + lpv_block_excl(cnt, tile_total, sh);
             if (m) {
                 const int idx = front[i];
-                const uint8_t next_level = (uint8_t)(g.level[idx] - 1), type = g.color[idx];
+                const uint8_t next_level = (uint8_t)(cur - 1), type = g.color[idx];
                 const int z = idx / (g.nx * g.ny), r = idx - z * g.nx * g.ny, y = r / g.nx, x = r - y * g.nx;
                 while (m) {
                     const int k = __ffs(m) - 1;
