@@ -522,36 +522,45 @@ __global__ void __launch_bounds__(256, VX_SVGF_OCC) svgf_prespatial_kernel(const
     float TotalWeight = 1.0f, TotalAOWeight = 1.0f;
     const f2 Texel = F2(1.0f / (float)a.width, 1.0f / (float)a.height);
 #pragma unroll 1
-    for (int k = 0; k < 9; ++k) {
-        if (k == 4) continue;
-        const int x = k / 3 - 1, y = k - (k / 3) * 3 - 1;
-        const f2 sc = F2(tc.x + ((float)x * 1.0f) * Texel.x, tc.y + ((float)y * 1.0f) * Texel.y);
-        if (!(sc.x > 0.0f && sc.x < 1.0f && sc.y > 0.0f && sc.y < 1.0f)) continue;
-        const Tap ss = make_tap(a.width, a.height, sc);
-        Tap sg = ss;
-        if (!same) sg = make_tap(a.g.w, a.g.h, sc);
-        const f3 SamplePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, sc)) * sample_r16(a.g.t, sg);
-        const f3 e = F3(fabsf(SamplePos.x - BasePos.x), fabsf(SamplePos.y - BasePos.y), fabsf(SamplePos.z - BasePos.z));
-        if (!(dot(e, e) < 1.0f)) continue;
-        float s[4], c2[2], a2[2];
-        sample_rgba16(a.in.sh, ss, s);
-        sample_rg16(a.in.cocg, ss, c2);
-        const float SampleLuma = gmax(0.0f, 3.544905f * s[3]);
-        const float NormalWeight = normal_weight16(BaseNormal, normal_at(a.g, nearest_offset(a.g.w, a.g.h, sc), lut));
-        const float LuminosityWeight = fabsf(SampleLuma - BaseLuminance) / 4.0f;
-        float Weight = expf(-LuminosityWeight - NormalWeight);
-        Weight = gmax(Weight, 0.01f);
-        const float wx = x == 0 ? 1.0f : 2.0f / 3.0f, wy = y == 0 ? 1.0f : 2.0f / 3.0f;   // AtrousWeights[abs(x)], [abs(y)]
-        Weight = (wx * wy) * Weight;
-        Weight = gmax(Weight, 0.01f);
-        Weight = gclamp(Weight, 0.0f, 1.0f);
+    for (int x = -1; x <= 1; ++x) {
+        const float scx = tc.x + ((float)x * 1.0f) * Texel.x;
+        if (!(scx > 0.0f && scx < 1.0f)) continue;
+        const Axis sx = make_axis(a.width, scx);   // the column set-up is shared by the three taps of the column
+        Axis gx = sx;
+        if (!same) gx = make_axis(a.g.w, scx);
+        const int nx = wrap_near(cvt_floor(scx * (float)a.g.w), a.g.w);
+        const float wx = x == 0 ? 1.0f : 2.0f / 3.0f;   // AtrousWeights[abs(x)]
+#pragma unroll 1
+        for (int y = -1; y <= 1; ++y) {
+            if (x == 0 && y == 0) continue;
+            const f2 sc = F2(scx, tc.y + ((float)y * 1.0f) * Texel.y);
+            if (!(sc.y > 0.0f && sc.y < 1.0f)) continue;
+            const Tap ss = join_axes(sx, make_axis(a.height, sc.y), a.width);
+            Tap sg = ss;
+            if (!same) sg = join_axes(gx, make_axis(a.g.h, sc.y), a.g.w);
+            const f3 SamplePos = origin + normalize(ray_direction_at(a.inv_view, a.inv_proj, sc)) * sample_r16(a.g.t, sg);
+            const f3 e = F3(fabsf(SamplePos.x - BasePos.x), fabsf(SamplePos.y - BasePos.y), fabsf(SamplePos.z - BasePos.z));
+            if (!(dot(e, e) < 1.0f)) continue;
+            float s[4], c2[2], a2[2];
+            sample_rgba16(a.in.sh, ss, s);
+            sample_rg16(a.in.cocg, ss, c2);
+            const float SampleLuma = gmax(0.0f, 3.544905f * s[3]);
+            const float NormalWeight = normal_weight16(BaseNormal, normal_at(a.g, wrap_near(cvt_floor(sc.y * (float)a.g.h), a.g.h) * a.g.w + nx, lut));
+            const float LuminosityWeight = fabsf(SampleLuma - BaseLuminance) / 4.0f;
+            float Weight = expf(-LuminosityWeight - NormalWeight);
+            Weight = gmax(Weight, 0.01f);
+            const float wy = y == 0 ? 1.0f : 2.0f / 3.0f;
+            Weight = (wx * wy) * Weight;
+            Weight = gmax(Weight, 0.01f);
+            Weight = gclamp(Weight, 0.0f, 1.0f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) TotalSH[j] += s[j] * Weight;
-        TotalCoCg[0] += c2[0] * Weight; TotalCoCg[1] += c2[1] * Weight;
-        TotalWeight += Weight;
-        sample_rg8(a.in.aosky, ss, lut, a2);
-        TotalAO[0] += a2[0] * Weight; TotalAO[1] += a2[1] * Weight;
-        TotalAOWeight += Weight;
+            for (int j = 0; j < 4; ++j) TotalSH[j] += s[j] * Weight;
+            TotalCoCg[0] += c2[0] * Weight; TotalCoCg[1] += c2[1] * Weight;
+            TotalWeight += Weight;
+            sample_rg8(a.in.aosky, ss, lut, a2);
+            TotalAO[0] += a2[0] * Weight; TotalAO[1] += a2[1] * Weight;
+            TotalAOWeight += Weight;
+        }
     }
     TotalWeight = gmax(TotalWeight, 0.01f);
     const float aw = gmax(TotalAOWeight, 0.01f);
