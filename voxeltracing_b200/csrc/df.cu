@@ -93,12 +93,15 @@ constexpr int XY_BATCH = 8;   // 16-byte loads in flight per thread
 constexpr int XY_MAX_SEG = 8;
 constexpr unsigned NO_CARRY = 0x03ffu;  // above every distance, small enough to add offsets in a u16 lane
 
-template <bool EXACT>   // the slice is a whole number of XY_THREADS * XY_BATCH quads: no guards in the stage
+// EXACT: the slice is a whole number of XY_THREADS * XY_BATCH quads (no guards in the stage).  CNX / CNY / CSY != 0: slice size and
+// number of Y segments as compile-time constants (the engine's 384 x 128 slice: every stride and quotient folds into the instructions).
+template <bool EXACT, int CNX, int CNY, int CSY>
 __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(const uint8_t* __restrict__ blocks,
-                                                                    uint8_t* __restrict__ df, int nx, int ny,
-                                                                    int z_begin, unsigned maxd, int sx, int sy) {
+                                                                    uint8_t* __restrict__ df, int nx_arg, int ny_arg,
+                                                                    int z_begin, unsigned maxd, int sx, int sy_arg) {
     extern __shared__ uint4 smem4[];
     unsigned* smem = reinterpret_cast<unsigned*>(smem4);
+    const int nx = CNX ? CNX : nx_arg, ny = CNY ? CNY : ny_arg, sy = CSY ? CSY : sy_arg;
     const int qpr = nx >> 4;       // 16-byte quads per row
     const int sq = qpr | 1;        // row stride in quads (odd)
     const int sw = sq << 2;        // row stride in words
@@ -496,8 +499,9 @@ __global__ void edit_blocks_kernel(uint8_t* __restrict__ blocks, const int32_t* 
 static int set_smem_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
-        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<true, 384, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<true, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<false, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
@@ -522,8 +526,12 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     int rc = set_smem_attrs();
     if (rc) return rc;
     if (c->df_stage != 2) {
-        if ((qpr * ny) % (XY_THREADS * XY_BATCH) == 0) df_xy_slice_kernel<true><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
-        else df_xy_slice_kernel<false><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+        if (nx == 384 && ny == 128 && sy == 4 && XY_THREADS * XY_BATCH == 3072)   // the engine's slice (WORLD_SIZE_X x WORLD_SIZE_Y, Macros.h)
+            df_xy_slice_kernel<true, 384, 128, 4><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+        else if ((qpr * ny) % (XY_THREADS * XY_BATCH) == 0)
+            df_xy_slice_kernel<true, 0, 0, 0><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
+        else
+            df_xy_slice_kernel<false, 0, 0, 0><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
     }
     VX_CUDA(cudaGetLastError());
     if (c->df_stage == 1) return VXRT_OK;
