@@ -388,8 +388,9 @@ __global__ void __launch_bounds__(Z_THREADS) df_z_tile_kernel(uint8_t* __restric
 constexpr int ZR_WARPS = 16;
 constexpr int ZR_THREADS = ZR_WARPS * 32;
 
-template <int SEG>
-__global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __restrict__ df, int words_per_plane, int z0) {
+template <int SEG, int CWPP>   // CWPP != 0: words per plane as a compile-time constant (plane offsets become load / store immediates)
+__global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __restrict__ df, int words_per_plane_arg, int z0) {
+    const int words_per_plane = CWPP ? CWPP : words_per_plane_arg;
     __shared__ uint4 bnd[ZR_WARPS][32];  // per segment and column: first-plane (e, o), last-plane (e, o) after the local sweeps
     const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = blockIdx.x * 32 + lane;
@@ -398,7 +399,10 @@ __global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __rest
     const size_t ps = (size_t)words_per_plane;
 
     unsigned w[SEG];
-    {
+    if (CWPP) {
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) w[i] = base[(size_t)i * CWPP];   // one address register, SEG immediates
+    } else {
         const unsigned* p = base;  // running pointer: one live address instead of SEG of them
 #pragma unroll
         for (int i = 0; i < SEG; ++i) {
@@ -451,8 +455,12 @@ __global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __rest
         vo = __viaddmin_u16x2(fo, (unsigned)i * 0x00010001u, vo);
         ve = __viaddmin_u16x2(be, (unsigned)(SEG - 1 - i) * 0x00010001u, ve);
         vo = __viaddmin_u16x2(bo, (unsigned)(SEG - 1 - i) * 0x00010001u, vo);
-        if (col_ok) *base = pack_lanes(ve, vo);
-        base += ps;
+        if (CWPP) {
+            if (col_ok) base[(size_t)i * CWPP] = pack_lanes(ve, vo);
+        } else {
+            if (col_ok) *base = pack_lanes(ve, vo);
+            base += ps;
+        }
     }
 }
 
@@ -537,10 +545,11 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     if (c->df_stage == 1) return VXRT_OK;
     const int wpp = (nx * ny) >> 2, nzr = z1 - z0;
     const int ztiles = (wpp + 31) / 32;
-    if (nzr == ZR_WARPS * 24) df_z_reg_kernel<24><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
-    else if (nzr == ZR_WARPS * 12) df_z_reg_kernel<12><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
-    else if (nzr == ZR_WARPS * 6) df_z_reg_kernel<6><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
-    else if (nzr == ZR_WARPS * 3) df_z_reg_kernel<3><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    if (nzr == ZR_WARPS * 24 && wpp == 12288) df_z_reg_kernel<24, 12288><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);   // the engine's 384 x 128 x 384 grid
+    else if (nzr == ZR_WARPS * 24) df_z_reg_kernel<24, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 12) df_z_reg_kernel<12, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 6) df_z_reg_kernel<6, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
+    else if (nzr == ZR_WARPS * 3) df_z_reg_kernel<3, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
     else {
         const int seg = (nzr + Z_SEGS - 1) / Z_SEGS;
         const size_t smem_z = ((size_t)nzr * Z_TILE_QUADS + (size_t)Z_SEGS * Z_TILE_WORDS) * sizeof(uint4);
