@@ -500,6 +500,14 @@ int vxrt_cuda_lpv_edit(vxrt_ctx* ctx, int32_t op, int32_t x, int32_t y, int32_t 
  * pow 1.8; zero for ids without an albedo layer), from the albedo array of vxrt_cuda_set_texture_array and the table of
  * vxrt_cuda_set_block_data.  Kept on the device for the consumers of the block-type volume; rgba_out: HOST memory for 128*4 floats or NULL. */
 int vxrt_cuda_lpv_average_colors(vxrt_ctx* ctx, float* rgba_out);
+/* the same table handed over by the caller (glBufferData on AverageColorSSBO): 128*4 floats, HOST memory */
+int vxrt_cuda_lpv_set_average_colors(vxrt_ctx* ctx, const float* rgba);
+/* SampleLPVData of Core/Shaders/ReflectionTraceFrag.glsl:1516-1528 (with SampleLPVColor :1484-1487 and InterpolateLPVColorDithered
+ * :1490-1509) as a function on caller points: the light the engine's reflections take from the volumes (ApproximateGILPV :673-700 adds the
+ * base ambient term to it).  points: 3*n floats in voxel units (HitPosition + Normal * 0.5 at the call site :882), dither: LPVDither
+ * (:714-723), rgb_out: 3*n floats; all HOST memory.  Needs the volumes (lpv_repropagate / lpv_upload) and lpv_average_colors.  The shader
+ * scales coordinates by its hard-coded 384 x 128 x 384 resolution; the volumes are addressed with the context's dimensions.        */
+int vxrt_cuda_lpv_sample(vxrt_ctx* ctx, const float* points, int32_t n, const float dither[3], float* rgb_out);
 /* The volumes to / from HOST memory (nx*ny*nz bytes each; download: either may be NULL).  Upload = Volumetrics::Reupload (:207-216). */
 int vxrt_cuda_lpv_download(vxrt_ctx* ctx, uint8_t* level, uint8_t* block_type);
 int vxrt_cuda_lpv_upload(vxrt_ctx* ctx, const uint8_t* level, const uint8_t* block_type);

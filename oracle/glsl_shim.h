@@ -347,7 +347,7 @@ template <class T, int N> struct arr {
 /* ---- resources ---- */
 struct sampler3D { const uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };     /* R8 unorm, NEAREST (Texture3D.cpp:20-27) */
 struct image3D { uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };             /* r8 image */
-struct usampler3D { const uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };    /* LPV block ids: never bound (LPV is off for parity) */
+struct usampler3D { const uint8_t* data = nullptr; int w = 0, h = 0, d = 0; };    /* LPV block types: R8UI, NEAREST, CLAMP_TO_EDGE (VolumetricFloodFill.cpp:51-58) */
 typedef vxo::Tex2D sampler2D;
 struct sampler2DArray { const vxo::TexArray* t = nullptr; };
 typedef vxo::TexCube samplerCube;
@@ -361,10 +361,36 @@ inline vec4 imageLoad(const image3D& s, const ivec3& p) {
 inline void imageStore(image3D& s, const ivec3& p, const vec4& v) {
     s.data[p.x + (size_t)p.y * s.w + (size_t)p.z * s.w * s.h] = vxo::float_to_unorm8(v.x);
 }
-/* filtered reads of 3-D textures only occur on the lava / LPV paths, which are disabled for parity */
-inline vec4 texture(const sampler3D&, const vec3&) { return vec4(0.0f); }
-inline uvec4 texture(const usampler3D&, const vec3&) { return uvec4(0u); }
-inline uvec4 texelFetch(const usampler3D&, const ivec3&, int) { return uvec4(0u); }
+/* filtered reads of 3-D textures only occur on the LPV path: the light-level volume is R8 unorm, LINEAR, CLAMP_TO_EDGE
+ * (VolumetricFloodFill.cpp:41-48); texel centres at +0.5, weights in full float, x then y then z like the 2-D model of vxo_texture.h.
+ * An unbound sampler reads 0. */
+inline int clamp_texel(int i, int n) { return i < 0 ? 0 : (i > n - 1 ? n - 1 : i); }
+inline vec4 texture(const sampler3D& s, const vec3& c) {
+    if (!s.data) return vec4(0.0f);
+    const float u = c.x * (float)s.w - 0.5f, v = c.y * (float)s.h - 0.5f, w = c.z * (float)s.d - 0.5f;
+    const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+    const float a = u - fu, b = v - fv, g = w - fw;
+    const int i0 = clamp_texel(vxo::cvt_floor(fu), s.w), i1 = clamp_texel(vxo::cvt_floor(fu) + 1, s.w);
+    const int j0 = clamp_texel(vxo::cvt_floor(fv), s.h), j1 = clamp_texel(vxo::cvt_floor(fv) + 1, s.h);
+    const int k0 = clamp_texel(vxo::cvt_floor(fw), s.d), k1 = clamp_texel(vxo::cvt_floor(fw) + 1, s.d);
+    auto at = [&](int i, int j, int k) { return vxo::unorm8_to_float(s.data[i + (size_t)j * s.w + (size_t)k * s.w * s.h]); };
+    auto plane = [&](int k) {
+        const float top = at(i0, j0, k) * (1.0f - a) + at(i1, j0, k) * a;
+        const float bot = at(i0, j1, k) * (1.0f - a) + at(i1, j1, k) * a;
+        return top * (1.0f - b) + bot * b;
+    };
+    return vec4(plane(k0) * (1.0f - g) + plane(k1) * g, 0.0f, 0.0f, 1.0f);
+}
+inline uvec4 texture(const usampler3D& s, const vec3& c) {
+    if (!s.data) return uvec4(0u);
+    const int i = clamp_texel(vxo::cvt_floor(c.x * (float)s.w), s.w), j = clamp_texel(vxo::cvt_floor(c.y * (float)s.h), s.h);
+    const int k = clamp_texel(vxo::cvt_floor(c.z * (float)s.d), s.d);
+    return uvec4((unsigned)s.data[i + (size_t)j * s.w + (size_t)k * s.w * s.h], 0u, 0u, 1u);
+}
+inline uvec4 texelFetch(const usampler3D& s, const ivec3& p, int) {
+    if (!s.data) return uvec4(0u);
+    return uvec4((unsigned)s.data[p.x + (size_t)p.y * s.w + (size_t)p.z * s.w * s.h], 0u, 0u, 1u);
+}
 inline vec4 to4(const vxo::v4& v) { return vec4(v.x, v.y, v.z, v.w); }
 inline vec4 texture(const sampler2D& s, const vec2& uv) { return to4(vxo::tex2d_sample(s, uv.x, uv.y)); }
 inline vec4 textureLod(const sampler2D& s, const vec2& uv, float) { return to4(vxo::tex2d_sample(s, uv.x, uv.y)); }

@@ -663,6 +663,26 @@ extern "C" void vxref_svgf_prespatial(const vxrt_svgf_prespatial_params* p, cons
 }
 #endif
 
+#ifdef VXREF_HAVE_ReflectionTraceFrag
+/* SampleLPVData of ReflectionTraceFrag.glsl (:1484-1528; the light the engine's reflections take from the propagation volume), called
+ * as a function on caller points: u_LPV = level volume (R8, LINEAR), u_LPVBlocks = block-type volume (R8UI, NEAREST), BlockAverageColorData =
+ * avg512 (binding 4, Pipeline.cpp:3240-3251); LPVDither (:714-723) is the caller's.  Points are in voxel units like HitPosition. */
+extern "C" void vxref_lpv_sample(const uint8_t* level, const uint8_t* block_type, const float* avg512, const float* points, int32_t n,
+                                 const float dither[3], float* rgb_out) {
+    namespace S = shader_ReflectionTraceFrag;
+    S::u_LPV.data = level; S::u_LPV.w = 384; S::u_LPV.h = 128; S::u_LPV.d = 384;
+    S::u_LPVBlocks.data = block_type; S::u_LPVBlocks.w = 384; S::u_LPVBlocks.h = 128; S::u_LPVBlocks.d = 384;
+    S::BlockAverageColorData.data = reinterpret_cast<const vec4*>(avg512);
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+        S::LPVDither = vec3(dither[0], dither[1], dither[2]);   /* thread-local, like every mutable global of a shader */
+        const vec3 r = S::SampleLPVData(vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+        rgb_out[3 * i] = r.x; rgb_out[3 * i + 1] = r.y; rgb_out[3 * i + 2] = r.z;
+    }
+    S::u_LPV.data = nullptr; S::u_LPVBlocks.data = nullptr; S::BlockAverageColorData.data = nullptr;
+}
+#endif
+
 #ifdef VXREF_HAVE_LPVAverageColor
 /* PrecomputeAverageBlockColor.comp as dispatched by Volumetrics::CreateVolume (VolumetricFloodFill.cpp:102-123): one invocation, the scene's
  * albedo array and block table; out = BlockAverageColorData, 128 x vec4 */

@@ -40,6 +40,8 @@ def _oracle():
     L.vxo_lpv_repropagate.restype = None
     L.vxo_lpv_edit.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.vxo_lpv_edit.restype = None
+    L.vxo_lpv_sample.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.vxo_lpv_sample.restype = None
     return L
 
 
@@ -98,6 +100,17 @@ def lpv_edit(blocks_after: np.ndarray, op: int, xyz, block: int, emissive: bool,
     b = np.ascontiguousarray(blocks_after)
     assert level.flags.c_contiguous and color.flags.c_contiguous
     _oracle().vxo_lpv_edit(_p(b), nx, ny, nz, int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(emissive), int(limit), _p(level), _p(color))
+
+
+def lpv_sample(level: np.ndarray, block_type: np.ndarray, avg: np.ndarray, points: np.ndarray, dither) -> np.ndarray:
+    """SampleLPVData (ReflectionTraceFrag.glsl:1516-1528) at points given in voxel units: (n, 3) float32"""
+    nz, ny, nx = level.shape
+    l, b = np.ascontiguousarray(level, np.uint8), np.ascontiguousarray(block_type, np.uint8)
+    a, p = np.ascontiguousarray(avg, np.float32).reshape(128, 4), np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dither, np.float32).reshape(3)
+    out = np.zeros_like(p)
+    _oracle().vxo_lpv_sample(_p(l), _p(b), nx, ny, nz, _p(a), _p(p), len(p), _p(d), _p(out))
+    return out
 
 
 # ---- the reference's own code (oracle/_ref) ----
@@ -325,3 +338,18 @@ def ref_lpv_edit(blocks_after: np.ndarray, op: int, xyz, block: int, emissive: b
     assert blocks_after.shape == (DIMS[2], DIMS[1], DIMS[0])
     b = np.ascontiguousarray(blocks_after)
     ref().vxref_lpv_edit(_p(b), int(op), int(xyz[0]), int(xyz[1]), int(xyz[2]), int(block), int(emissive), int(limit), _p(level), _p(color))
+
+
+def ref_lpv_sample(level: np.ndarray, block_type: np.ndarray, avg: np.ndarray, points: np.ndarray, dither) -> np.ndarray:
+    """SampleLPVData of the reference's ReflectionTraceFrag.glsl compiled in oracle/_ref/libvxrt_ref.so, called as a function"""
+    from oracle import ref_binding as rb
+    assert level.shape == (DIMS[2], DIMS[1], DIMS[0])
+    l, b = np.ascontiguousarray(level, np.uint8), np.ascontiguousarray(block_type, np.uint8)
+    a, p = np.ascontiguousarray(avg, np.float32).reshape(128, 4), np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dither, np.float32).reshape(3)
+    out = np.zeros_like(p)
+    L = rb.lib()
+    L.vxref_lpv_sample.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]
+    L.vxref_lpv_sample.restype = None
+    L.vxref_lpv_sample(_p(l), _p(b), _p(a), _p(p), len(p), _p(d), _p(out))
+    return out

@@ -65,6 +65,10 @@ def main():
         ow = ob.OracleWorld(np.zeros((16, 16, 16), np.uint8))
         rb.set_scene(np.zeros((384, 128, 384), np.uint8), np.zeros((384, 128, 384), np.uint8), inp.table, inp.blue, inp.textures, inp.sky)
         out[f"average_colors_{size}"] = rb.lpv_average_colors()
+    # SampleLPVData of ReflectionTraceFrag.glsl (compiled through oracle/_ref) on case 0 at limit 8
+    level, color = wb.ref_lpv_repropagate(blocks, lights, 8)
+    avg, pts, dithers = lu.sample_case(level)
+    out["sample_rgb"] = np.stack([wb.ref_lpv_sample(level, color, avg, pts, d) for d in dithers])
     np.savez_compressed(lu.GOLD, **out)
     print("wrote", lu.GOLD, lu.GOLD.stat().st_size, "bytes")
 

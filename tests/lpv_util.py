@@ -87,5 +87,20 @@ def crc(level: np.ndarray, color: np.ndarray) -> np.ndarray:
                      int(np.count_nonzero(level))], dtype=np.int64)
 
 
+def sample_case(level: np.ndarray):
+    """Seeded inputs of the SampleLPVData tests: a colour table, points in and around the lit voxels plus the corners / faces / outside of
+    the volume, three dither vectors."""
+    rng = np.random.default_rng(0)
+    avg = np.zeros((128, 4), np.float32)
+    avg[:, :3] = rng.random((128, 3)).astype(np.float32)
+    lit = np.argwhere(level > 0)
+    pts = (lit[rng.integers(0, len(lit), 20000)][:, ::-1] + rng.random((20000, 3)) * 1.5 - 0.25).astype(np.float32)
+    pts[:50] = rng.random((50, 3)).astype(np.float32) * np.array([384, 128, 384], np.float32)
+    pts[50:60] = [[0, 0, 0], [384, 128, 384], [-3, 5, 5], [400, 5, 5], [0.5, 0.5, 0.5], [383.5, 127.5, 383.5], [1, 1, 1], [383, 127, 383],
+                  [192, 64, 192], [10.25, 20.5, 30.75]]
+    dithers = np.array([[0, 0, 0], [0.5 / 384, 0.5 / 128, 0.5 / 384], [0.9 / 384, 0.1 / 128, 0.3 / 384]], np.float32)
+    return avg, pts, dithers
+
+
 def golden():
     return np.load(GOLD)

@@ -188,3 +188,38 @@ def test_average_block_colors():
         assert np.array_equal(got == 0, want == 0)
         assert np.all(np.abs(got - want) <= 4 * np.spacing(np.abs(want))), np.abs(got - want).max()
         assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.9
+
+
+def test_sample_lpv_data(ctx, case0):
+    """vxrt_cuda_lpv_sample (SampleLPVData, ReflectionTraceFrag.glsl:1516-1528): exact float arithmetic only, so bit-identical to the oracle
+    and to the compiled shader function's output in the golden fixture"""
+    import scene_util as su
+    g = lu.golden()
+    blocks, lights = case0
+    ctx.upload_world(blocks)
+    ctx.lpv_repropagate(None, 8)
+    level, color = ctx.lpv_download()
+    avg, pts, dithers = lu.sample_case(level)
+    c = engine.Context(0)
+    try:
+        with pytest.raises(engine.VxrtError):
+            c.lpv_sample(pts[:4])                    # no volume yet
+        c.lpv_upload(level, color)
+        with pytest.raises(engine.VxrtError):
+            c.lpv_sample(pts[:4])                    # no colour table yet
+        # the colour table comes from lpv_average_colors: give the context an albedo array whose averages we then replace by the seeded table
+        su.SceneInputs(64).apply_to_context(c)
+        c.lpv_average_colors()
+        table = c.lpv_average_colors()
+        for k, d in enumerate(dithers):
+            got = c.lpv_sample(pts, d)
+            want = wb.lpv_sample(level, color, table, pts, d)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), k
+        c.lpv_set_average_colors(avg)                # the seeded table of the fixture
+        for k, d in enumerate(dithers):
+            got = c.lpv_sample(pts, d)
+            assert np.array_equal(got.view(np.uint32), g["sample_rgb"][k].view(np.uint32)), k
+        assert (got.sum(axis=1) > 0).mean() > 0.9
+        assert c.lpv_sample(np.zeros((0, 3), np.float32)).shape == (0, 3)
+    finally:
+        c.close()

@@ -120,3 +120,26 @@ def test_average_block_colors_match_golden():
         assert np.array_equal(a.view(np.uint32), g[f"average_colors_{size}"].view(np.uint32)), size
         has = inp.table[0] >= 0
         assert (a[~has] == 0).all() and (a[has, :3] > 0).all() and (a[:, 3] == 0).all() and a.max() <= 1.0
+
+
+def test_sample_lpv_data_matches_golden(case0):
+    """SampleLPVData (ReflectionTraceFrag.glsl:1516-1528): oracle == the compiled shader function's output in the fixture, bit for bit"""
+    g = lu.golden()
+    blocks, lights = case0
+    level, color = wb.lpv_repropagate(blocks, lights, 8)
+    avg, pts, dithers = lu.sample_case(level)
+    for k, d in enumerate(dithers):
+        got = wb.lpv_sample(level, color, avg, pts, d)
+        assert np.array_equal(got.view(np.uint32), g["sample_rgb"][k].view(np.uint32)), k
+    assert (got.sum(axis=1) > 0).mean() > 0.9 and np.isfinite(got).all()
+    # dark voxels give no light; the light scales with the level
+    assert not wb.lpv_sample(np.zeros_like(level), color, avg, pts[:100], dithers[0]).any()
+
+
+@needs_ref
+def test_sample_lpv_data_matches_reference(case0):
+    blocks, lights = case0
+    level, color = wb.lpv_repropagate(blocks, lights[::-1], 5)
+    avg, pts, dithers = lu.sample_case(level)
+    for d in dithers:
+        assert np.array_equal(wb.lpv_sample(level, color, avg, pts, d).view(np.uint32), wb.ref_lpv_sample(level, color, avg, pts, d).view(np.uint32))

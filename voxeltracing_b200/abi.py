@@ -263,6 +263,8 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_lpv_repropagate": (C.c_int, [vp, vp, i32, i32]),
         "vxrt_cuda_lpv_edit": (C.c_int, [vp, i32, i32, i32, i32, i32, i32]),
         "vxrt_cuda_lpv_average_colors": (C.c_int, [vp, vp]),
+        "vxrt_cuda_lpv_set_average_colors": (C.c_int, [vp, vp]),
+        "vxrt_cuda_lpv_sample": (C.c_int, [vp, vp, i32, vp, vp]),
         "vxrt_cuda_lpv_download": (C.c_int, [vp, vp, vp]),
         "vxrt_cuda_lpv_upload": (C.c_int, [vp, vp, vp]),
         "vxrt_cuda_stats_enable": (C.c_int, [vp, i32]),

@@ -801,6 +801,34 @@ int vxrt_cuda_lpv_average_colors(vxrt_ctx* c, float* rgba_out) {
     return VXRT_OK;
 }
 
+int vxrt_cuda_lpv_set_average_colors(vxrt_ctx* c, const float* rgba) {
+    REQUIRE_CTX(c); REQUIRE_PTR(rgba);
+    if (!c->d_lpv_avg) VX_CUDA(cudaMalloc(&c->d_lpv_avg, 128 * 4 * sizeof(float)));
+    VX_CUDA(cudaMemcpyAsync(c->d_lpv_avg, rgba, 128 * 4 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+int vxrt_cuda_lpv_sample(vxrt_ctx* c, const float* points, int32_t n, const float dither[3], float* rgb_out) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dither);
+    if (n < 0) return vxrt_fail(VXRT_E_INVALID, "lpv_sample: n < 0");
+    if (n == 0) return VXRT_OK;
+    REQUIRE_PTR(points); REQUIRE_PTR(rgb_out);
+    if (!c->lpv_valid) return vxrt_fail(VXRT_E_STATE, "lpv_sample: no light propagation volume yet (lpv_repropagate / lpv_upload)");
+    if (!c->d_lpv_avg) return vxrt_fail(VXRT_E_STATE, "lpv_sample: no average block colours yet (lpv_average_colors)");
+    const size_t bytes = ((size_t)n * 3 * sizeof(float) + 255) / 256 * 256;
+    int rc = ensure_staging(c, 2 * bytes);
+    if (rc) return rc;
+    float* d_points = (float*)c->d_ray_buf;
+    float* d_out = (float*)((uint8_t*)c->d_ray_buf + bytes);
+    VX_CUDA(cudaMemcpyAsync(d_points, points, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = vxrt_launch_lpv_sample(c, d_points, n, dither, d_out);
+    if (rc) return rc;
+    VX_CUDA(cudaMemcpyAsync(rgb_out, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
 int vxrt_cuda_lpv_download(vxrt_ctx* c, uint8_t* level, uint8_t* block_type) {
     REQUIRE_CTX(c);
     int rc = vxrt_lpv_ensure(c);

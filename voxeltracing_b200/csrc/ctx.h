@@ -170,6 +170,7 @@ int vxrt_lpv_ensure(vxrt_ctx* c);
 int vxrt_launch_lpv_repropagate(vxrt_ctx* c, const int32_t* d_lights, const unsigned* d_count, int capacity, int limit);
 int vxrt_launch_lpv_repropagate_coop(vxrt_ctx* c, const int32_t* d_lights, int n_lights, int limit);
 int vxrt_launch_lpv_average_colors(vxrt_ctx* c);
+int vxrt_launch_lpv_sample(vxrt_ctx* c, const float* d_points, int n, const float dither[3], float* d_out);
 int vxrt_launch_lpv_edit(vxrt_ctx* c, int op, int x, int y, int z, int block, int limit, int* overflowed);
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* gi_args);
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* refl_args);

@@ -405,6 +405,19 @@ class Context:
         self._check(self._lib.vxrt_cuda_lpv_average_colors(self._h, _p(out)))
         return out
 
+    def lpv_set_average_colors(self, rgba: np.ndarray):
+        t = np.ascontiguousarray(rgba, dtype=np.float32)
+        assert t.size == 512
+        self._check(self._lib.vxrt_cuda_lpv_set_average_colors(self._h, _p(t)))
+
+    def lpv_sample(self, points, dither=(0.0, 0.0, 0.0)) -> np.ndarray:
+        """SampleLPVData (ReflectionTraceFrag.glsl:1516-1528) at (n, 3) points in voxel units: (n, 3) float32."""
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dither, dtype=np.float32).reshape(3)
+        out = np.zeros_like(p)
+        self._check(self._lib.vxrt_cuda_lpv_sample(self._h, _p(p), len(p), _p(d), _p(out)))
+        return out
+
     def lpv_download(self):
         """(level, block_type) volumes indexed [z, y, x]."""
         nx, ny, nz = self.dims
