@@ -419,6 +419,24 @@ def lpv_block(local_rank, stream, flush_buf, ev, peak, with_cpu):
                           "us_on_device_break_lamp": float(np.median(dev[0::2])), "us_on_device_place_lamp": float(np.median(dev[1::2])),
                           "note": "ms: wall clock around the synchronous ABI call (launch + stream synchronisation from an idle GPU); us_on_device: CUDA "
                                   "events around the same call; one warp replays the reference's queues in order"}
+    # SampleLPVData on 2 M points around the lit voxels (host buffers in, host buffers out: the call copies both ways)
+    c.lpv_repropagate(None, 8)
+    level = c.lpv_download()[0]
+    lit = np.argwhere(level > 0)
+    n_pts = 1 << 21
+    pts = (lit[rng.integers(0, len(lit), n_pts)][:, ::-1] + rng.random((n_pts, 3)) * 1.5 - 0.25).astype(np.float32)
+    avg = np.zeros((128, 4), np.float32)
+    avg[:, :3] = rng.random((128, 3)).astype(np.float32)
+    c.lpv_set_average_colors(avg)
+    c.lpv_sample(pts[:1024])
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        c.lpv_sample(pts, (0.5 / 384, 0.5 / 128, 0.5 / 384))
+        ts.append(time.perf_counter() - t0)
+    out["sample"] = {"points": n_pts, "ms_end_to_end": float(np.median(ts)) * 1e3, "mpoints_per_s_end_to_end": n_pts / float(np.median(ts)) / 1e6,
+                     "h2d_bytes": int(pts.nbytes), "d2h_bytes": int(pts.nbytes),
+                     "note": "wall clock around vxrt_cuda_lpv_sample with pageable host arrays (copy in, kernel, copy out, synchronous)"}
     if with_cpu:
         from oracle import world_binding as wb
         lights = wb.collect_lights(blocks, table)
