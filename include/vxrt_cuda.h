@@ -110,7 +110,7 @@ typedef enum vxrt_texture_kind {
 } vxrt_texture_kind;
 /* TextureArray::CreateArray (Core/GLClasses/TextureArray.cpp:10-69): level-0 texels
  * layers*h*w*4 bytes, file row 0 first; the mip chain is built inside (2x2 box filter,
- * albedo averaged in linear light).  w == h, power of two.                                   */
+ * albedo averaged in linear light).  w == h, power of two, at most 2048.                     */
 int vxrt_cuda_set_texture_array(vxrt_ctx* ctx, int32_t kind, int32_t layers, int32_t w, int32_t h,
                                 const uint8_t* rgba8);
 /* Sky cubemap consumed by GI / reflections (Core/Pipeline.cpp:1468-1470, 2339, 3207):
@@ -357,7 +357,8 @@ int vxrt_cuda_raycast_detect(vxrt_ctx* ctx, const float* positions, const float*
  * VXRT_ATT_SVGF_*); the caller sequences them like the engine: temporal (current raw set + previous temporal set ->
  * current temporal set, ping-ponged by frame parity), variance, five spatial iterations with steps 16, 8, 4, 2, 1
  * ping-ponging DENOISE_A / DENOISE_B, then vxrt_cuda_svgf_end_frame.  The optional 3x3 pre-pass
- * (Spatial3x3Initial.glsl, PreTemporalSpatialPass) is not covered: the temporal pass takes the raw trace output. */
+ * (Spatial3x3Initial.glsl, PreTemporalSpatialPass) is vxrt_cuda_svgf_prespatial below: it writes VXRT_ATT_SVGF_PRESPATIAL, which
+ * the temporal pass then takes as its in_set instead of the raw trace output. */
 typedef struct vxrt_svgf_temporal_params {   /* Pipeline.cpp:2428-2528 */
     float inv_view[16], inv_projection[16];  /* u_InverseView, u_InverseProjection (v_RayOrigin = u_InverseView[3]) */
     float prev_view[16], prev_projection[16];/* u_PrevView, u_PrevProjection */

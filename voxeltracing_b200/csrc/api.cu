@@ -24,8 +24,24 @@ int vxrt_check_cuda(cudaError_t e, const char* what) {
     return vxrt_fail(VXRT_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
 }
 
-#define REQUIRE_CTX(c) \
-    if (!(c)) return vxrt_fail(VXRT_E_INVALID, "%s: ctx is NULL", __func__)
+// Every entry point runs with the context's device current and restores the caller's device on return, so contexts on
+// different GPUs can live in one process, be called from any thread, and survive a cudaSetDevice / torch.cuda.set_device
+// of the caller in between.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define REQUIRE_CTX(c)                                                          \
+    if (!(c)) return vxrt_fail(VXRT_E_INVALID, "%s: ctx is NULL", __func__);    \
+    DeviceGuard _device_guard((c)->device)
 #define REQUIRE_PTR(p) \
     if (!(p)) return vxrt_fail(VXRT_E_INVALID, "%s: %s is NULL", __func__, #p)
 
@@ -106,6 +122,7 @@ int vxrt_cuda_create(vxrt_ctx** out, int device, const int32_t* dims) {
     int ndev = 0;
     VX_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return vxrt_fail(VXRT_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard _device_guard(device);  // the caller's current device is restored on return
     VX_CUDA(cudaSetDevice(device));
     vxrt_ctx* c = new (std::nothrow) vxrt_ctx();
     if (!c) return vxrt_fail(VXRT_E_NOMEM, "out of host memory");
@@ -136,7 +153,7 @@ int vxrt_cuda_create(vxrt_ctx** out, int device, const int32_t* dims) {
 
 int vxrt_cuda_destroy(vxrt_ctx* c) {
     if (!c) return VXRT_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard _device_guard(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
@@ -159,8 +176,10 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
 
 int vxrt_cuda_set_stream(vxrt_ctx* c, void* s) {
     REQUIRE_CTX(c);
+    cudaStream_t next = s ? (cudaStream_t)s : c->own_stream;
+    if (next == c->stream) return VXRT_OK;
     VX_CUDA(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = next;
     return vxrt_apply_l2_policy(c);
 }
 int vxrt_cuda_synchronize(vxrt_ctx* c) {
@@ -390,12 +409,17 @@ int vxrt_cuda_wait_reads(vxrt_ctx* c) {
 int vxrt_cuda_bind_attachment(vxrt_ctx* c, int32_t id, void* dev_ptr, size_t capacity) {
     REQUIRE_CTX(c);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    if (dev_ptr && capacity == 0) return vxrt_fail(VXRT_E_INVALID, "bind_attachment: capacity is 0");  // before anything is released
     if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
     c->att_read_pending[id] = false;
     Attachment& a = c->att[id];
-    if (a.ptr && !a.external) VX_CUDA(cudaFree(a.ptr));
+    if (a.ptr && !a.external) {
+        VX_CUDA(cudaStreamSynchronize(c->stream));  // passes in flight may still use the old storage
+        void* old = a.ptr;
+        a.ptr = nullptr; a.capacity = 0; a.width = a.height = a.bpp = 0;
+        VX_CUDA(cudaFree(old));
+    }
     if (dev_ptr) {
-        if (capacity == 0) return vxrt_fail(VXRT_E_INVALID, "bind_attachment: capacity is 0");
         a.ptr = dev_ptr; a.capacity = capacity; a.external = true;
     } else {
         a.ptr = nullptr; a.capacity = 0; a.external = false; a.width = a.height = a.bpp = 0;
@@ -503,8 +527,8 @@ int vxrt_cuda_set_texture_array(vxrt_ctx* c, int32_t kind, int32_t layers, int32
     REQUIRE_CTX(c); REQUIRE_PTR(rgba8);
     if (kind < 0 || kind > 3) return vxrt_fail(VXRT_E_INVALID, "set_texture_array: bad kind %d", kind);
     if (layers < 1 || layers > 255) return vxrt_fail(VXRT_E_INVALID, "set_texture_array: %d layers (1..255, TextureArray.cpp:17-23)", layers);
-    if (w < 1 || h < 1 || w > 4096 || h > 4096 || (w & (w - 1)) || (h & (h - 1)) || w != h)
-        return vxrt_fail(VXRT_E_INVALID, "set_texture_array: size %dx%d must be a square power of two", w, h);
+    if (w < 1 || h < 1 || w > 2048 || h > 2048 || (w & (w - 1)) || (h & (h - 1)) || w != h)
+        return vxrt_fail(VXRT_E_INVALID, "set_texture_array: size %dx%d must be a square power of two, at most 2048", w, h);
     return vxrt_set_texture_array(c, kind, layers, w, h, rgba8);
 }
 int vxrt_cuda_set_skymap(vxrt_ctx* c, int32_t res, const float* rgb_faces) {

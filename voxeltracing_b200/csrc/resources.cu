@@ -38,11 +38,12 @@ int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, cons
     for (int i = 0; i < 256; ++i) { decode[i] = srgb ? srgb_decode(i) : (float)i / 255.0f; lin[i] = (float)i / 255.0f; }
 
     // level sizes / offsets
+    // the validated size limit of vxrt_cuda_set_texture_array is 2048 (12 levels)
     unsigned offsets[12];
     int lw[12], lh[12], levels = 0;
     size_t total = 0;
     for (int cw = w, ch = h;; ) {
-        if (levels >= 12) return vxrt_fail(VXRT_E_INVALID, "texture array too large");
+        if (levels >= 12) return vxrt_fail(VXRT_E_INVALID, "texture array too large (at most 2048 x 2048)");
         lw[levels] = cw; lh[levels] = ch; offsets[levels] = (unsigned)total;
         total += (size_t)layers * cw * ch * 4;
         ++levels;
@@ -51,7 +52,12 @@ int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, cons
         ch = ch > 1 ? ch / 2 : 1;
     }
     if (total > 0xffffffffull) return vxrt_fail(VXRT_E_INVALID, "texture array exceeds 4 GiB");
-    std::vector<uint8_t> all(total);
+    std::vector<uint8_t> all;
+    try {
+        all.resize(total);
+    } catch (...) {  // extern "C" callers never see an exception
+        return vxrt_fail(VXRT_E_NOMEM, "set_texture_array: out of host memory for the %zu-byte mip chain", total);
+    }
     memcpy(all.data(), rgba8, (size_t)layers * w * h * 4);
     for (int l = 1; l < levels; ++l) {
         const uint8_t* src = all.data() + offsets[l - 1];
@@ -75,7 +81,13 @@ int vxrt_set_texture_array(vxrt_ctx* c, int kind, int layers, int w, int h, cons
                     o[3] = unorm_encode(a);
                 }
     }
-    if (c->d_tex_data[kind]) { VX_CUDA(cudaFree(c->d_tex_data[kind])); c->d_tex_data[kind] = nullptr; }
+    if (c->d_tex_data[kind]) {
+        // the array is unusable from here until the new upload has succeeded
+        uint8_t* old = c->d_tex_data[kind];
+        c->d_tex_data[kind] = nullptr; c->tex[kind].data = nullptr; c->tex_set[kind] = false;
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+        VX_CUDA(cudaFree(old));
+    }
     if (!c->d_tex_decode[kind]) VX_CUDA(cudaMalloc(&c->d_tex_decode[kind], 256 * sizeof(float)));
     VX_CUDA(cudaMalloc(&c->d_tex_data[kind], total));
     VX_CUDA(cudaMemcpyAsync(c->d_tex_data[kind], all.data(), total, cudaMemcpyHostToDevice, c->stream));

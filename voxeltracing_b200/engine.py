@@ -84,6 +84,7 @@ class Context:
         if dims is not None:
             d = (C.c_int32 * 3)(*dims)
         self.dims = tuple(dims) if dims is not None else (384, 128, 384)
+        self.device = int(device)
         self._check(self._lib.vxrt_cuda_create(C.byref(self._h), device, d))
 
     # -- plumbing --
@@ -165,7 +166,9 @@ class Context:
         self._check(self._lib.vxrt_cuda_df_commit(self._h))
 
     def df_device_array(self):
-        """Zero-copy [nz, ny, nx] uint8 view of the distance field for torch.as_tensor (NCCL all-gather of slabs)."""
+        """Zero-copy [nz, ny, nx] uint8 view of the distance field for torch.as_tensor (NCCL all-gather of slabs).
+        The view is NOT ordered against this context's kernels unless the consumer runs on the context's stream: put the
+        context on the consumer's stream first (set_stream / sharding.bind_streams) or synchronize() before using it."""
         blocks, df = C.c_void_p(), C.c_void_p()
         self._check(self._lib.vxrt_cuda_grid_device(self._h, C.byref(blocks), C.byref(df)))
         nx, ny, nz = self.dims
@@ -331,7 +334,8 @@ class Context:
         self._check(self._lib.vxrt_cuda_wait_reads(self._h))
 
     def attachment_as_device_array(self, att: int):
-        """Zero-copy view for torch.as_tensor(..., device='cuda') (NCCL tile gathers)."""
+        """Zero-copy view for torch.as_tensor(..., device='cuda') (NCCL tile gathers).  Same stream contract as
+        df_device_array: consumers on another stream must be ordered by the caller (set_stream / sharding.bind_streams)."""
         ptr, w, h, bpp = self.attachment_info(att)
         dt, ch = _ATT_DTYPES[att]
         shape = (h, w) if ch == 1 else (h, w, ch)

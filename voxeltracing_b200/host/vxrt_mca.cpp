@@ -180,7 +180,10 @@ bool inflate_all(const uint8_t* src, size_t n, int compression, std::vector<uint
     if (inflateInit2(&zs, 15 + 32) != Z_OK) return false;  // zlib (type 2) or gzip (type 1) framing
     zs.next_in = const_cast<Bytef*>(src);
     zs.avail_in = (uInt)n;
-    out.resize(std::max<size_t>(n * 8, 1 << 16));
+    // a chunk's NBT is a few hundred KB at most; a stream that inflates past the cap is rejected (counted as a bad chunk)
+    // instead of doubling the buffer without bound
+    const size_t kMaxInflated = (size_t)16 << 20;
+    out.resize(std::min(kMaxInflated, std::max<size_t>(n * 8, 1 << 16)));
     int rc = Z_OK;
     for (;;) {
         zs.next_out = out.data() + zs.total_out;
@@ -188,8 +191,10 @@ bool inflate_all(const uint8_t* src, size_t n, int compression, std::vector<uint
         rc = inflate(&zs, Z_NO_FLUSH);
         if (rc == Z_STREAM_END) break;
         if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); return false; }
-        if (zs.avail_out == 0) out.resize(out.size() * 2);
-        else if (zs.avail_in == 0) { inflateEnd(&zs); return false; }  // truncated stream
+        if (zs.avail_out == 0) {
+            if (out.size() >= kMaxInflated) { inflateEnd(&zs); return false; }
+            out.resize(std::min(kMaxInflated, out.size() * 2));
+        } else if (zs.avail_in == 0) { inflateEnd(&zs); return false; }  // truncated stream
     }
     out.resize(zs.total_out);
     inflateEnd(&zs);

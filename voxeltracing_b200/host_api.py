@@ -170,6 +170,11 @@ class RegionSections:
             self.chunks = lib.vxh_mca_chunk_count(h)
             self.palette_sections = lib.vxh_mca_palette_section_count(h)
             self.bad_chunks = lib.vxh_mca_bad_chunk_count(h)
+            if n == 0 and self.palette_sections > 0:
+                # Palette / BlockStates sections (Minecraft 1.13+) have no legacy ids for the engine's 8-bit MC-id table; an import
+                # that would silently produce an empty grid is an error
+                raise ValueError(f"{path}: {self.palette_sections} palette-format (1.13+) sections and no pre-flattening sections: "
+                                 "only the legacy Blocks / Data chunk format is supported")
 
             def view(ptr, shape, dtype):
                 if n == 0:

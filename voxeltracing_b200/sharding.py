@@ -23,9 +23,26 @@ def slab_bounds(nz: int, world: int) -> list[int]:
     return z0
 
 
-def gather_bands(full: torch.Tensor, height: int, rank: int, world: int, dst: int = 0, band: int = 8, group=None):
+def bind_streams(ctx, device=None) -> None:
+    """Stream contract of everything in this module: torch's collectives are ordered against torch's CURRENT stream only, while an
+    engine.Context launches on its own non-blocking stream by default.  Zero-copy views of the context's memory
+    (Context.df_device_array, Context.attachment_as_device_array) handed to a collective are therefore only ordered against the
+    passes that wrote them when both use one stream.  This puts the context on torch's current stream of its device; the sharded
+    entry points below call it themselves, so a caller in the default state cannot get a collective that overtakes a kernel."""
+    dev = torch.device("cuda", ctx.device) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        return
+    # torch's default stream is the NULL stream; set_stream(NULL) means "the context's own stream", so name it by the
+    # runtime's explicit handle for the legacy default stream (cudaStreamLegacy == 0x1)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 0x1)
+
+
+def gather_bands(full: torch.Tensor, height: int, rank: int, world: int, dst: int = 0, band: int = 8, group=None, ctx=None):
     """`full` is a full-frame attachment [H, ...] of which this rank rendered rows band_rows(height, rank, world).
-    After the call rank `dst` holds every band (rows are contiguous in memory, so the receives land in place)."""
+    After the call rank `dst` holds every band (rows are contiguous in memory, so the receives land in place).
+    Pass the `ctx` that rendered `full` so the transfer is ordered behind its passes (see bind_streams)."""
+    if ctx is not None and full.is_cuda:
+        bind_streams(ctx, full.device)
     if world == 1:
         return full
     result = full
@@ -59,16 +76,21 @@ class CudaSlabBackend:
         self.nz = nz
         self.df = torch.as_tensor(ctx.df_device_array(), device=device)  # zero-copy [nz, ny, nx] view
 
+    # every phase re-binds the context to torch's current stream: the all-gathers between the phases read / write the
+    # context's field through zero-copy views and are ordered against that stream only (bind_streams)
     def phase_a(self, slab, z0):
+        bind_streams(self.ctx, self.device)
         self.ctx.df_slab_phase_a(slab, z0)
 
     def plane(self, z):
         return self.df[z]
 
     def phase_b(self, slab, z0, firsts: torch.Tensor, lasts: torch.Tensor):
+        bind_streams(self.ctx, self.device)
         self.ctx.df_slab_phase_b(slab, z0, firsts.data_ptr(), lasts.data_ptr())
 
     def commit(self):
+        bind_streams(self.ctx, self.device)
         self.ctx.df_commit()
 
 
