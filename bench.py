@@ -631,7 +631,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     pass_ms = {p: float(np.mean([pe[p][0].elapsed_time(pe[p][1]) for pe in pass_ev])) for p in cfg.passes}
 
-    # ---- distance-field regeneration (BASELINE config 2), L2 flushed before every regeneration ----
+    # ---- distance-field regeneration (BASELINE config 2) ----
+    # (a) the figure of round 1: one regeneration between a CUDA-event pair after a 256 MiB memset.  Events tick in ~2 us steps on this
+    #     driver, the memset leaves the L2 full of DIRTY lines the regeneration then pays the write-back of, and the two launches
+    #     come from the host one after the other; kept as "us_single_launch_after_write_flush" for comparison with BENCH_r01.
     df_ev = [(ev(), ev()) for _ in range(30)]
     for a, b in df_ev:
         flush_buf.zero_()
@@ -639,7 +642,33 @@ def main():
         ctx.generate_distance_field()
         b.record(stream)
     torch.cuda.synchronize()
-    df_us = float(np.median([a.elapsed_time(b) for a, b in df_ev])) * 1e3
+    df_us_flush = float(np.median([a.elapsed_time(b) for a, b in df_ev])) * 1e3
+    # (b) the reported figure: inputs larger than the L2 instead of a flush.  8 contexts (8 x 37.7 MB of grids against 126 MB of L2)
+    #     regenerate in turn, so every regeneration finds its block grid evicted and its output evicting older dirty fields (HBM
+    #     traffic = the algorithmic 2 N per regeneration); 4 rounds are captured in a CUDA graph (no host launch gaps) and one event
+    #     pair brackets the 32 regenerations of a replay, which also takes the event granularity out.
+    df_ctxs = [ctx] + [engine.Context(local_rank) for _ in range(7)]
+    for c in df_ctxs[1:]:
+        c.set_stream(stream.cuda_stream)
+        c.upload_world(blocks)
+    for c in df_ctxs:
+        c.generate_distance_field()
+    torch.cuda.synchronize()
+    df_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(df_graph, stream=stream):
+        for _ in range(4):
+            for c in df_ctxs:
+                c.generate_distance_field()
+    df_ev = [(ev(), ev()) for _ in range(12)]
+    for a, b in df_ev:
+        a.record(stream)
+        df_graph.replay()
+        b.record(stream)
+    torch.cuda.synchronize()
+    df_us = float(np.median([a.elapsed_time(b) for a, b in df_ev[2:]])) * 1e3 / 32
+    del df_graph
+    for c in df_ctxs[1:]:
+        c.close()
 
     # ---- SVGF denoiser chain of the GI output: 3 x 3 pre-pass, temporal, variance, 5 a-trous iterations, per-stage CUDA
     # events, L2 flushed before each chain; runs on consecutive frames of the camera path so the history is live ----
@@ -861,7 +890,8 @@ def main():
         nvox = blocks.size
         line["df_regen"] = {"us_per_regeneration": df_us, "algorithmic_bytes": 2 * nvox,
                             "achieved_gbs": 2 * nvox / (df_us * 1e-6) / 1e9, "frac_of_hbm_peak": 2 * nvox / (df_us * 1e-6) / 1e9 / peak,
-                            "l2": "flushed before each regeneration", "launches_per_regeneration": 2}
+                            "method": "8 contexts regenerate in turn (302 MB of grids > L2), 32 regenerations per CUDA-graph replay between one event pair, median of 10 replays",
+                            "us_single_launch_after_write_flush": df_us_flush, "launches_per_regeneration": 2}
         if svgf:
             line["svgf"] = svgf
         if shadow_dn:

@@ -101,3 +101,26 @@ def test_worlds_other_than_plains(ctx):
         ctx.upload_world(w)
         ctx.generate_distance_field()
         assert np.array_equal(ctx.download_distance_field(), ob.distance_field(w)), kind
+
+
+@pytest.mark.parametrize("xyver,zver", [(1, 1), (2, 1), (1, 2), (2, 2), (2, 4), (2, 5), (2, 9)])
+def test_every_kernel_version_is_bit_exact(xyver, zver, plains0):
+    """The kernel generations stay selectable (set_option df_xyver / df_zver) as each other's cross-check: every combination equals the
+    oracle on a terrain world, an enclosed world, sparse voxels with block ids >= 128 (the mask multiply must ignore the high bit
+    it builds on), dense noise and single voxels on the faces of the grid."""
+    c = engine.Context(0)
+    c.set_option("df_xyver", xyver); c.set_option("df_zver", zver)
+    nz, ny, nx = 384, 128, 384
+    rng = np.random.default_rng(17)
+    sparse = np.zeros((nz, ny, nx), np.uint8)
+    idx = rng.integers(0, sparse.size, 600)
+    sparse.reshape(-1)[idx] = rng.integers(1, 256, 600).astype(np.uint8)
+    dense = (rng.random((nz, ny, nx)) < 0.3).astype(np.uint8) * rng.integers(1, 256, (nz, ny, nx)).astype(np.uint8)
+    faces = np.zeros((nz, ny, nx), np.uint8)
+    for p in [(0, 64, 200), (383, 5, 3), (100, 0, 0), (200, 127, 383), (191, 63, 0), (192, 64, 383)]:
+        faces[p] = 255
+    for name, w in (("plains0", plains0), ("rooms2", host_api.gen_world("rooms", 2)), ("sparse", sparse), ("dense", dense), ("faces", faces)):
+        c.upload_world(w)
+        c.generate_distance_field()
+        assert np.array_equal(c.download_distance_field(), ob.distance_field(w)), (xyver, zver, name)
+    c.close()

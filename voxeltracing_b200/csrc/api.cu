@@ -194,6 +194,9 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "l2_persist")) { c->l2_persist = value != 0; return vxrt_apply_l2_policy(c); }
     if (!strcmp(name, "lpv_coop")) { c->lpv_coop = value != 0; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
+    if (!strcmp(name, "df_dbg")) { c->df_dbg = value; return VXRT_OK; }
+    if (!strcmp(name, "df_zver")) { c->df_zver = value; return VXRT_OK; }
+    if (!strcmp(name, "df_xyver")) { c->df_xyver = value; return VXRT_OK; }
     if (!strcmp(name, "df_sx")) { c->df_sx = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
     if (!strcmp(name, "df_sy")) { c->df_sy = value < 0 ? 0 : (value > 8 ? 8 : value); return VXRT_OK; }
     return vxrt_fail(VXRT_E_INVALID, "unknown option '%s'", name);

@@ -58,6 +58,9 @@ struct vxrt_ctx {
     bool world_uploaded = false;
     bool df_valid = false;
     int df_sx = 0, df_sy = 0;  // measurement aid: override the segment counts of the XY kernel (0 = automatic)
+    int df_zver = 2;   // measurement aid (set_option "df_zver"): 1 = df_z_reg_kernel, 2 = df_z_reg2_kernel (u16 lanes kept unpacked)
+    int df_dbg = 0;    // measurement aid (set_option "df_dbg"): phases of df_xy2_kernel to skip (bit 0: Y down, 1: Y up, 2: X)
+    int df_xyver = 2;  // set_option "df_xyver": 1 = df_xy_slice_kernel, 2 = df_xy2_kernel (the engine's 384 x 128 slice only)
     int df_stage = 0;  // measurement aid (set_option "df_stage"): 1 = XY kernel only, 2 = Z kernel only, 0 = both
 
     int32_t* d_block_data = nullptr;      // 6*128

@@ -25,6 +25,7 @@ namespace {
 
 __device__ __forceinline__ unsigned even_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4240); }  // (b0, b2)
 __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4341); }   // (b1, b3)
+__device__ __forceinline__ unsigned even_lanes_lop(unsigned w) { return w & 0x00ff00ffu; }          // LOP3 issues at twice the rate of PRMT
 // lanes hold values < 256, so the pack is e + 256 * o: one IMAD on the FMA pipe.  Both kernels are bound by the
 // half-rate integer (ALU) pipe that VIADDMNMX / PRMT / LOP3 share (ncu: pipe_alu 62 %, math-pipe throttle the top
 // stall), so everything that can be a multiply-add is one.
@@ -37,6 +38,14 @@ __device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigne
 __device__ __forceinline__ unsigned solid_nibble_top(unsigned w) {
     const unsigned nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;  // bit7 set where byte != 0
     return (nz >> 7) * 0x01020408u;   // bits 0, 8, 16, 24 -> 24..27: the 16 partial products land on distinct bits, none on 28..31
+}
+
+// bits 28..31 of the result = the solid mask of the four bytes of w (bit 28 + i = byte i non-zero), bits 24..27 zero, the rest junk:
+// the flags sit at bits 7, 15, 23, 31 and the multiplier's shifts 21, 14, 7, 0 send them to 28..31; the other twelve partial products
+// land on the distinct bits 7, 14, 15, 21, 22, 23 or overflow, so nothing carries into the top byte.  No shift: LOP3, add, LOP3, IMAD.
+__device__ __forceinline__ unsigned solid_nibble_hi(unsigned w) {
+    const unsigned nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+    return nz * 0x00204081u;
 }
 
 // solid ? 0 : maxd for the four bytes of w
@@ -268,6 +277,176 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
     }
 }
 
+// ---- kernel 1, second version (the engine's 384 x 128 slice) -------------------------------------------------------------
+// Same arithmetic as df_xy_slice_kernel, reorganised around what the pipes of an SM can do per clock (tools/debug/pipe_bench.cu:
+// VIADDMNMX / VIMNMX3 / PRMT / SHF 64 lanes / clk / SM on the ALU pipe, IMAD / VIADD 64 on the FMA pipe beside it, LDS.128 one warp
+// instruction per 4 clocks):
+//   * a thread owns 8 consecutive rows of one quad column, loads them with 8 x LDG.128 in flight and keeps the quads' nibble masks in
+//     registers from the mask phase to the X phase (no staging pass through shared memory);
+//   * X: the inside-the-word distances come from an 8-byte table entry (one conflict-free LDS.64), the carries leaving a word from a
+//     4-byte one; "carry + offset" for the four lanes of a word are multiply-adds (FMA pipe) feeding one VIMNMX3 per lane pair;
+//   * Y is one unsegmented chain per word column (no segment carries, no fold): 3 warps sweep the 96 columns down and back up through
+//     the slice in shared memory (7 instructions per word and direction) while the SM's other CTAs are in their mask / X phases; which
+//     3 of the first 4 warps do it rotates per CTA on an SM, so the Y warps of the co-resident CTAs spread over the 4 schedulers;
+//   * the result leaves through the bulk-copy engine: as soon as the upward sweep has finished a 32-row chunk, one thread issues
+//     cp.async.bulk.global.shared::cta for its 12 KB, so the store overlaps the rest of the sweep and costs no thread instructions.
+constexpr int XY2_THREADS = 384;
+constexpr int XY2_QPR = 24, XY2_ROWS = 128, XY2_WPR = 96;       // quads / rows / words per slice row
+constexpr int XY2_QSTRIDE = 27;                                   // row stride of the quad-carry array (odd, and 8 rows apart never alias a row's 24 banks)
+constexpr int XY2_SMEM = XY2_ROWS * XY2_QPR * 16 + XY2_ROWS * XY2_QSTRIDE * 4 + 16 * 8 + 16 * 4 + 16;
+__device__ unsigned g_xy2_rotation[1024];   // per SM: CTAs that have started there (only its low two bits are used)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(XY2_THREADS, 3) df_xy2_kernel(const uint8_t* __restrict__ blocks, uint8_t* __restrict__ df, int z_begin, unsigned maxd, int dbg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* slice4 = reinterpret_cast<uint4*>(smem_raw);                                      // [128][24] quads, dense
+    unsigned* slice = reinterpret_cast<unsigned*>(smem_raw);
+    unsigned* qcar = reinterpret_cast<unsigned*>(smem_raw + XY2_ROWS * XY2_QPR * 16);         // [128][27]: carry from the left | from the right << 16
+    uint2* lut_eo = reinterpret_cast<uint2*>(qcar + XY2_ROWS * XY2_QSTRIDE);                  // [16]: distances inside the word (v0 | v2 << 16, v1 | v3 << 16)
+    unsigned* lut_zw = reinterpret_cast<unsigned*>(lut_eo + 16);                              // [16]: carry leaving to the right | to the left << 16
+    int* rot_s = reinterpret_cast<int*>(lut_zw + 16);
+    const int tid = threadIdx.x;
+    if (dbg & 64) return;   // measurement aid: what a launch of this grid costs by itself 
+    const int c0 = tid % XY2_QPR, rseg = tid / XY2_QPR;     // quad column, rows rseg * 8 .. + 7
+    const size_t slice_off = (size_t)(z_begin + blockIdx.x) * (XY2_ROWS * XY2_QPR * 16);
+    const uint4* src = reinterpret_cast<const uint4*>(blocks + slice_off) + (rseg * 8) * XY2_QPR + c0;
+
+    // Ordering the load bursts of the co-resident CTAs (tickets per SM, each CTA issuing after the one before it) was measured and
+    // dropped: 14.9 -> 15.9 us; the memory system does not serve the requests in issue order at this scale and the hand-over costs
+    // two block barriers.
+    if (tid == 32) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        *rot_s = (int)(atomicAdd(&g_xy2_rotation[smid & 1023u], 1u) & 3u);
+    }
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(src + i * XY2_QPR);
+
+    if (tid < 16) {
+        const unsigned n = tid;
+        unsigned d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned best = maxd;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n >> j & 1u) best = min(best, (unsigned)(i > j ? i - j : j - i));
+            d[i] = best;
+        }
+        const unsigned f = n ? (unsigned)(4 - (31 - __clz(n))) : NO_CARRY, b = n ? (unsigned)__ffs(n) : NO_CARRY;
+        lut_eo[n] = make_uint2(d[0] | (d[2] << 16), d[1] | (d[3] << 16));
+        lut_zw[n] = f | (b << 16);
+    }
+
+    // ---- masks: per quad the four 4-bit solid masks as byte offsets into the 8-byte table (mask * 8), and the carries leaving the quad ----
+    unsigned nb8[8];   // per byte: mask << 4
+    if (dbg & 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { nb8[i] = v[i].x ^ v[i].y ^ v[i].z ^ v[i].w; slice4[(rseg * 8 + i) * XY2_QPR + c0] = v[i]; }
+    } else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned nbh = __byte_perm(__byte_perm(solid_nibble_hi(v[i].x), solid_nibble_hi(v[i].y), 0x4473),
+                                         __byte_perm(solid_nibble_hi(v[i].z), solid_nibble_hi(v[i].w), 0x4473), 0x5410);   // mask << 4 per byte
+        const unsigned t = (nbh >> 4) | (nbh >> 8);
+        const unsigned m16 = __byte_perm(t, 0u, 0x4420);                      // bit j = voxel j of the quad solid
+        nb8[i] = nbh;
+        // to the right: 16 - highest solid voxel; to the left: lowest solid voxel + 1
+        qcar[(rseg * 8 + i) * XY2_QSTRIDE + c0] = m16 ? (unsigned)(__clz(m16) - 15) | ((unsigned)__ffs(m16) << 16) : NO_CARRY | (NO_CARRY << 16);
+    }
+    __syncthreads();
+
+    // ---- X carries per row at quad granularity (ManhattanDistanceX.comp:53-68): what reaches the first voxel of every quad from the
+    // left and its last voxel from the right ----
+    if (tid < 2 * XY2_ROWS) {
+        const int back = tid >= XY2_ROWS, row = tid - back * XY2_ROWS;
+        unsigned short* r = reinterpret_cast<unsigned short*>(qcar) + ((row * XY2_QSTRIDE) << 1) + back;
+        unsigned c = NO_CARRY;
+        if (!back) {
+#pragma unroll 8
+            for (int j = 0; j < XY2_QPR; ++j) { const unsigned f = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(f, c + 16u); }
+        } else {
+#pragma unroll 8
+            for (int j = XY2_QPR - 1; j >= 0; --j) { const unsigned b = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(b, c + 16u); }
+        }
+    }
+    __syncthreads();
+
+    // ---- X distances: word by word the carries advance through the table; every voxel is
+    // min(inside the word, carry from the left + offset, carry from the right + offset) ----
+    if (!(dbg & 4)) {
+        const unsigned k1 = 0x00010001u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = rseg * 8 + i;
+            const unsigned cin = qcar[row * XY2_QSTRIDE + c0];
+            uint2 eo[4];
+            unsigned zw[4], cf[4], cb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned off = (nb8[i] >> (8 * k + 1)) & 0x78u;
+                eo[k] = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(lut_eo) + off);
+                zw[k] = *reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(lut_zw) + (off >> 1));
+            }
+            unsigned c = cin & 0xffffu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { cf[k] = c; c = __viaddmin_u32(c, 4u, zw[k] & 0xffffu); }
+            c = cin >> 16;
+#pragma unroll
+            for (int k = 3; k >= 0; --k) { cb[k] = c; c = __viaddmin_u32(c, 4u, zw[k] >> 16); }
+            unsigned w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // lanes (v0, v2) and (v1, v3): from the left + (0, 2) / (1, 3), from the right + (3, 1) / (2, 0)
+                const unsigned e = __vimin3_u16x2(eo[k].x, cf[k] * k1 + 0x00020000u, cb[k] * k1 + 0x00010003u);
+                const unsigned o = __vimin3_u16x2(eo[k].y, cf[k] * k1 + 0x00030001u, cb[k] * k1 + 0x00000002u);
+                w[k] = pack_lanes(e, o);
+            }
+            slice4[row * XY2_QPR + c0] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- Y (ManhattanDistanceY.comp:35-49): one chain per word column, down and back up; bulk stores chunk by chunk on the way up ----
+    const int warp = tid >> 5;
+    const int yw = (warp - *rot_s) & 3;
+    if (warp >= 4 || yw == 3) return;
+    const int col = yw * 32 + (tid & 31);
+    unsigned* cptr = slice + col;
+    unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first row
+    if (!(dbg & 1))
+#pragma unroll 8
+    for (int y = 0; y < XY2_ROWS; ++y) {
+        const unsigned w = cptr[y * XY2_WPR];
+        e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
+        o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
+        cptr[y * XY2_WPR] = pack_lanes(e, o);
+    }
+    uint8_t* dst = df + slice_off;
+    for (int chunk = 3; chunk >= 0; --chunk) {
+        const int y_hi = chunk == 3 ? XY2_ROWS - 2 : chunk * 32 + 31;
+        if (!(dbg & 2))
+#pragma unroll 8
+        for (int y = y_hi; y >= chunk * 32; --y) {
+            const unsigned w = cptr[y * XY2_WPR];
+            e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
+            o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
+            cptr[y * XY2_WPR] = pack_lanes(e, o);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the chunk's bytes become visible to the bulk-copy engine
+        asm volatile("bar.sync 1, 96;" ::: "memory");
+        if (yw == 0 && (tid & 31) == 0 && !(dbg & 8)) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + chunk * 32 * XY2_WPR * 4),
+                         "r"(smem_u32(slice + chunk * 32 * XY2_WPR)), "n"(32 * XY2_WPR * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (yw == 0 && (tid & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+}
+
 // ---- kernel 2: Z sweeps (ManhattanDistanceZ.comp:31-46) ----------------------------------------
 // Planes [z0, z1) of one tile of Z_TILE_WORDS word columns.  Warp s owns the planes [s*seg, (s+1)*seg) of the
 // range (local index); lane = word column.
@@ -464,6 +643,180 @@ __global__ void __launch_bounds__(ZR_THREADS, 3) df_z_reg_kernel(uint8_t* __rest
     }
 }
 
+// ---- kernel 2, second register-resident variant: u16 lanes stay unpacked from the load to the store --------------------
+// df_z_reg_kernel re-packs the column to bytes after each local sweep and unpacks it again (6 PRMT + 3 IMAD of its 34
+// instructions per word).  Here a lane keeps the even / odd u16 lanes of its SEG words in 2 * SEG registers from the load to
+// the store: per word 2 PRMT (unpack), 4 VIADDMNMX (local sweeps), 2 VIMNMX3 (fold: min of the value and both carries, whose
+// "+ distance" terms are multiply-adds on the FMA pipe, which runs beside the ALU pipe that VIADDMNMX / PRMT occupy) and one
+// multiply-add for the pack.
+__device__ __forceinline__ unsigned opaque_u32(unsigned v) {
+    unsigned r;
+    asm("mov.u32 %0, %1;" : "=r"(r) : "r"(v));   // a value the compiler cannot fold: keeps k * i + c a multiply-add (FMA pipe)
+    return r;
+}
+
+#ifndef VX_ZR2_OCC
+#define VX_ZR2_OCC 2
+#endif
+// FOLD selects how "carry + distance" reaches the 3-input minimum (measured alternatives):
+//   0: two VIADDMNMX per lane pair;  1: adds with immediates + VIMNMX3;  2: multiply-adds by the opaque constant k1 = 0x00010001 + VIMNMX3
+// COLS = word columns per CTA (8, 16 or 32; a CTA has COLS * 16 threads, 64 registers each): 384 tiles of 32 columns leave a 148-SM
+// GPU with 2 or 3 CTAs per SM (the slower SMs set the time); 1536 tiles of 8 columns (one 32-byte sector per plane row) balance to 6 %.
+template <int SEG, int CWPP, int FOLD, int COLS>
+__global__ void __launch_bounds__(COLS * ZR_WARPS, 1024 / (COLS * ZR_WARPS)) df_z_reg2_kernel(uint8_t* __restrict__ df, int words_per_plane_arg, int z0, unsigned k1) {
+    const int words_per_plane = CWPP ? CWPP : words_per_plane_arg;
+    if (k1 == 1) return;   // measurement aid: what a launch of this grid costs by itself
+    __shared__ uint2 bnd_last[ZR_WARPS][COLS];   // per segment and column: last plane after the local sweeps, + 1 per lane (e, o)
+    __shared__ uint2 bnd_first[ZR_WARPS][COLS];  // first plane likewise
+    const int s = threadIdx.x / COLS, lane = threadIdx.x % COLS;
+    const int col = blockIdx.x * COLS + lane;
+    const bool col_ok = col < words_per_plane;
+    unsigned* base = reinterpret_cast<unsigned*>(df) + (size_t)(z0 + s * SEG) * words_per_plane + (col_ok ? col : 0);
+    const size_t ps = (size_t)words_per_plane;
+
+    unsigned e[SEG], o[SEG];
+    {
+        unsigned w[SEG];
+        if (CWPP) {
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) w[i] = base[(size_t)i * CWPP];
+        } else {
+            const unsigned* p = base;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) { w[i] = *p; p += ps; }
+        }
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) { e[i] = even_lanes_lop(w[i]); o[i] = odd_lanes(w[i]); }
+    }
+    if (k1 == 0) {   // measurement aid: load + unpack + pack + store only
+        asm volatile("" : "+l"(base));
+#pragma unroll
+        for (int i = 0; i < SEG; ++i)
+            if (col_ok) base[(size_t)i * CWPP] = pack_lanes(e[i], o[i]);
+        return;
+    }
+    // local forward sweep, then backward
+#pragma unroll
+    for (int i = 1; i < SEG; ++i) {
+        e[i] = __viaddmin_u16x2(e[i - 1], 0x00010001u, e[i]);
+        o[i] = __viaddmin_u16x2(o[i - 1], 0x00010001u, o[i]);
+    }
+    bnd_last[s][lane] = make_uint2(e[SEG - 1] + 0x00010001u, o[SEG - 1] + 0x00010001u);
+#pragma unroll
+    for (int i = SEG - 2; i >= 0; --i) {
+        e[i] = __viaddmin_u16x2(e[i + 1], 0x00010001u, e[i]);
+        o[i] = __viaddmin_u16x2(o[i + 1], 0x00010001u, o[i]);
+    }
+    bnd_first[s][lane] = make_uint2(e[0] + 0x00010001u, o[0] + 0x00010001u);
+    __syncthreads();
+
+    // carries of the other segments as min-plus chains over the segments (warp-uniform trip counts):
+    //   fwd arriving at this segment's first plane = min over t < s of last_t + 1 + (s - 1 - t) * SEG,  bwd likewise from t > s
+    constexpr unsigned SEG2 = (unsigned)SEG * 0x00010001u;
+    unsigned fe = 0x03ff03ffu, fo = 0x03ff03ffu, be = 0x03ff03ffu, bo = 0x03ff03ffu;   // "no carry": above every distance
+#pragma unroll 1
+    for (int t = 0; t < s; ++t) {
+        const uint2 v = bnd_last[t][lane];
+        fe = __viaddmin_u16x2(fe, SEG2, v.x);
+        fo = __viaddmin_u16x2(fo, SEG2, v.y);
+    }
+#pragma unroll 1
+    for (int t = ZR_WARPS - 1; t > s; --t) {
+        const uint2 v = bnd_first[t][lane];
+        be = __viaddmin_u16x2(be, SEG2, v.x);
+        bo = __viaddmin_u16x2(bo, SEG2, v.y);
+    }
+    // fold + pack + store: plane i sees fwd + i and bwd + (SEG - 1 - i); the sums stay below 2^16 per lane
+    asm volatile("" : "+l"(base));
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+        unsigned ve, vo;
+        if (FOLD == 0) {
+            ve = __viaddmin_u16x2(fe, (unsigned)i * 0x00010001u, e[i]);
+            vo = __viaddmin_u16x2(fo, (unsigned)i * 0x00010001u, o[i]);
+            ve = __viaddmin_u16x2(be, (unsigned)(SEG - 1 - i) * 0x00010001u, ve);
+            vo = __viaddmin_u16x2(bo, (unsigned)(SEG - 1 - i) * 0x00010001u, vo);
+        } else if (FOLD == 1) {
+            ve = __vimin3_u16x2(e[i], fe + (unsigned)i * 0x00010001u, be + (unsigned)(SEG - 1 - i) * 0x00010001u);
+            vo = __vimin3_u16x2(o[i], fo + (unsigned)i * 0x00010001u, bo + (unsigned)(SEG - 1 - i) * 0x00010001u);
+        } else {
+            ve = __vimin3_u16x2(e[i], k1 * (unsigned)i + fe, k1 * (unsigned)(SEG - 1 - i) + be);
+            vo = __vimin3_u16x2(o[i], k1 * (unsigned)i + fo, k1 * (unsigned)(SEG - 1 - i) + bo);
+        }
+        if (CWPP) {
+            if (col_ok) base[(size_t)i * CWPP] = pack_lanes(ve, vo);
+        } else {
+            if (col_ok) *base = pack_lanes(ve, vo);
+            base += ps;
+        }
+    }
+}
+
+// ---- kernel 2, persistent variant: one CTA per SM loops over the column tiles and loads the words of its NEXT tile into registers
+// before it works on the current one, so the L2 round trip of a tile overlaps the sweeps of the one before it (in df_z_reg2_kernel a
+// CTA loads, computes and stores strictly one after the other, and with 2 or 3 tiles per SM nothing else fills the gaps).
+template <int SEG, int CWPP>
+__global__ void __launch_bounds__(ZR_THREADS, 1) df_z_persist_kernel(uint8_t* __restrict__ df, int z0, int ntiles) {
+    __shared__ uint2 bnd_last[2][ZR_WARPS][32];   // double-buffered by tile parity: one barrier per tile is enough
+    __shared__ uint2 bnd_first[2][ZR_WARPS][32];
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned* plane0 = reinterpret_cast<unsigned*>(df) + (size_t)(z0 + s * SEG) * CWPP + lane;
+    constexpr unsigned SEG2 = (unsigned)SEG * 0x00010001u;
+
+    unsigned wn[SEG];
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) wn[i] = plane0[(size_t)i * CWPP + tile * 32];
+    }
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        unsigned e[SEG], o[SEG];
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) { e[i] = even_lanes_lop(wn[i]); o[i] = odd_lanes(wn[i]); }
+        const int next = tile + gridDim.x;
+        if (next < ntiles) {
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) wn[i] = plane0[(size_t)i * CWPP + next * 32];
+        }
+#pragma unroll
+        for (int i = 1; i < SEG; ++i) {
+            e[i] = __viaddmin_u16x2(e[i - 1], 0x00010001u, e[i]);
+            o[i] = __viaddmin_u16x2(o[i - 1], 0x00010001u, o[i]);
+        }
+        const int par = it & 1;
+        bnd_last[par][s][lane] = make_uint2(e[SEG - 1] + 0x00010001u, o[SEG - 1] + 0x00010001u);
+#pragma unroll
+        for (int i = SEG - 2; i >= 0; --i) {
+            e[i] = __viaddmin_u16x2(e[i + 1], 0x00010001u, e[i]);
+            o[i] = __viaddmin_u16x2(o[i + 1], 0x00010001u, o[i]);
+        }
+        bnd_first[par][s][lane] = make_uint2(e[0] + 0x00010001u, o[0] + 0x00010001u);
+        __syncthreads();   // the buffers of this parity are next written two tiles later, after the barrier of the tile in between
+        unsigned fe = 0x03ff03ffu, fo = 0x03ff03ffu, be = 0x03ff03ffu, bo = 0x03ff03ffu;
+#pragma unroll 1
+        for (int t = 0; t < s; ++t) {
+            const uint2 v = bnd_last[par][t][lane];
+            fe = __viaddmin_u16x2(fe, SEG2, v.x);
+            fo = __viaddmin_u16x2(fo, SEG2, v.y);
+        }
+#pragma unroll 1
+        for (int t = ZR_WARPS - 1; t > s; --t) {
+            const uint2 v = bnd_first[par][t][lane];
+            be = __viaddmin_u16x2(be, SEG2, v.x);
+            bo = __viaddmin_u16x2(bo, SEG2, v.y);
+        }
+        unsigned* out = plane0 + tile * 32;
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+            unsigned ve = __viaddmin_u16x2(fe, (unsigned)i * 0x00010001u, e[i]);
+            unsigned vo = __viaddmin_u16x2(fo, (unsigned)i * 0x00010001u, o[i]);
+            ve = __viaddmin_u16x2(be, (unsigned)(SEG - 1 - i) * 0x00010001u, ve);
+            vo = __viaddmin_u16x2(bo, (unsigned)(SEG - 1 - i) * 0x00010001u, vo);
+            out[(size_t)i * CWPP] = pack_lanes(ve, vo);
+        }
+    }
+}
+
 // ---- z-slab sharding (multi-GPU regeneration) -------------------------------------
 // After the slab-local sweeps every rank holds L[z] = min over its own planes z' of xy[z'] + |z - z'|.
 // With B_t = L on the last plane of slab t and F_t = L on the first plane of slab t (all-gathered, one
@@ -511,6 +864,7 @@ static int set_smem_attrs() {
         VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<true, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<false, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VX_CUDA(cudaFuncSetAttribute(df_xy2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XY2_SMEM));
         attr_set = true;
     }
     return VXRT_OK;
@@ -534,7 +888,9 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     int rc = set_smem_attrs();
     if (rc) return rc;
     if (c->df_stage != 2) {
-        if (nx == 384 && ny == 128 && sy == 4 && XY_THREADS * XY_BATCH == 3072)   // the engine's slice (WORLD_SIZE_X x WORLD_SIZE_Y, Macros.h)
+        if (c->df_xyver == 2 && nx == 384 && ny == 128)
+            df_xy2_kernel<<<z1 - z0, XY2_THREADS, XY2_SMEM, c->stream>>>(c->d_blocks, c->d_df, z0, maxd, c->df_dbg);
+        else if (nx == 384 && ny == 128 && sy == 4 && XY_THREADS * XY_BATCH == 3072)   // the engine's slice (WORLD_SIZE_X x WORLD_SIZE_Y, Macros.h)
             df_xy_slice_kernel<true, 384, 128, 4><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
         else if ((qpr * ny) % (XY_THREADS * XY_BATCH) == 0)
             df_xy_slice_kernel<true, 0, 0, 0><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
@@ -545,7 +901,18 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     if (c->df_stage == 1) return VXRT_OK;
     const int wpp = (nx * ny) >> 2, nzr = z1 - z0;
     const int ztiles = (wpp + 31) / 32;
-    if (nzr == ZR_WARPS * 24 && wpp == 12288) df_z_reg_kernel<24, 12288><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);   // the engine's 384 x 128 x 384 grid
+    const bool engine_grid = nzr == ZR_WARPS * 24 && wpp == 12288;
+#define Z2(FOLD, COLS) df_z_reg2_kernel<24, 12288, FOLD, COLS><<<wpp / COLS, COLS * ZR_WARPS, 0, c->stream>>>(c->d_df, wpp, z0, (c->df_dbg & 64) ? 1u : (c->df_dbg & 32) ? 0u : 0x00010001u)
+    if (engine_grid && c->df_zver == 2) Z2(0, 32);
+    else if (engine_grid && c->df_zver == 3) Z2(1, 32);
+    else if (engine_grid && c->df_zver == 4) Z2(2, 32);
+    else if (engine_grid && c->df_zver == 5) Z2(0, 16);
+    else if (engine_grid && c->df_zver == 6) Z2(2, 16);
+    else if (engine_grid && c->df_zver == 7) Z2(0, 8);
+    else if (engine_grid && c->df_zver == 8) Z2(2, 8);
+    else if (engine_grid && c->df_zver == 9) df_z_persist_kernel<24, 12288><<<c->sm_count < 384 ? c->sm_count : 384, ZR_THREADS, 0, c->stream>>>(c->d_df, z0, 384);
+#undef Z2
+    else if (nzr == ZR_WARPS * 24 && wpp == 12288) df_z_reg_kernel<24, 12288><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);   // the engine's 384 x 128 x 384 grid
     else if (nzr == ZR_WARPS * 24) df_z_reg_kernel<24, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
     else if (nzr == ZR_WARPS * 12) df_z_reg_kernel<12, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
     else if (nzr == ZR_WARPS * 6) df_z_reg_kernel<6, 0><<<ztiles, ZR_THREADS, 0, c->stream>>>(c->d_df, wpp, z0);
