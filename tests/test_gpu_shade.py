@@ -232,3 +232,36 @@ def test_wavefront_reflections_are_bit_identical_to_the_per_pixel_kernel(request
     for a, b in zip(res[0][0], res[1][0]):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
     assert res[0][1] == res[1][1]
+
+
+@pytest.mark.parametrize("caps", [(), (12, 24), (1, 2, 3), (5,), (47,), (30, 100), (200, 250)])
+def test_capped_trace_passes_do_not_change_a_bit(rooms, inputs, caps):
+    """Iteration-capped passes with compaction between launches (trace_queue.cuh, set_option "trace_caps"): every cap schedule - none,
+    the default, caps of one iteration, a cap next to the GI trace length (48), caps beyond the reflection trace length (64) but inside
+    the shadow lengths (128 / 150), caps beyond every length - gives the attachments and the traversal statistics of the uncapped kernels."""
+    c, ow, sc = rooms
+    cam = host_api.camera([188.3, 61.0, 172.9], 115.0, -8.0, W / H)
+    c.initial_trace(cam, W, H)
+    c.shadow_trace(cam, W, H, host_api.sun_direction(50.0)[2], soft=False)
+    c.generate_gbuffer(su.gbuffer_params(cam, W, H, inputs))
+    ip = su.gi_params(cam, W, H, frame=6, spp=2, checkerboard=True)
+    rp = su.reflection_params(cam, W, H, inputs=inputs, frame=6, spp=2)
+    atts = (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY, abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE)
+
+    def run(packed):
+        c.set_option("trace_caps", packed)
+        c.stats_enable(True); c.stats_read(True)
+        c.diffuse_trace(ip)
+        c.reflection_trace(rp)
+        st = c.stats_read(True); c.stats_enable(False)
+        return [c.read_attachment(a).copy() for a in atts], st
+
+    try:
+        want, want_st = run(0)
+        got, got_st = run(sum(k << (8 * j) for j, k in enumerate(caps)))
+    finally:
+        c.set_option("trace_caps", 0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert got_st == want_st
+    assert want_st["rays"] > 100000

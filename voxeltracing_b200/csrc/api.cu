@@ -97,6 +97,21 @@ int vxrt_apply_l2_policy(vxrt_ctx* c) {
     return VXRT_OK;
 }
 
+int vxrt_ensure_trace_cont(vxrt_ctx* c, size_t rays, TraceCont* out) {
+    if (rays > c->trace_cont_cap) {
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_trace_cont) VX_CUDA(cudaFree(c->d_trace_cont));
+        c->d_trace_cont = nullptr; c->trace_cont_cap = 0;
+        VX_CUDA(cudaMalloc(&c->d_trace_cont, 2 * rays * sizeof(float4) + 256));
+        c->trace_cont_cap = rays;
+    }
+    uint8_t* p = (uint8_t*)c->d_trace_cont;
+    out->count = reinterpret_cast<int*>(p);
+    out->q[0] = reinterpret_cast<float4*>(p + 256);
+    out->q[1] = out->q[0] + c->trace_cont_cap;
+    return VXRT_OK;
+}
+
 cudaEvent_t vxrt_probe_event(vxrt_ctx* c) {
     if (!c->probe_on) return nullptr;
     if (c->probe_used == c->probe_ev.size()) {
@@ -157,7 +172,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_df); cudaFree(c->d_block_data); cudaFree(c->d_blue_noise);
     cudaFree(c->d_blue_tex); cudaFree(c->d_edit_buf); cudaFree(c->d_stats); cudaFree(c->d_sky); cudaFree(c->d_slab_z0); cudaFree(c->d_wf); cudaFree(c->d_ray_buf);
-    cudaFree(c->d_lpv); cudaFree(c->d_lpv_work);
+    cudaFree(c->d_lpv); cudaFree(c->d_lpv_work); cudaFree(c->d_trace_cont);
     if (c->h_lpv_flag) cudaFreeHost(c->h_lpv_flag);
     cudaFree(c->d_lpv_avg);
     for (int k = 0; k < 4; ++k) { cudaFree(c->d_tex_data[k]); cudaFree(c->d_tex_decode[k]); }
@@ -193,6 +208,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
     if (!strcmp(name, "l2_persist")) { c->l2_persist = value != 0; return vxrt_apply_l2_policy(c); }
     if (!strcmp(name, "lpv_coop")) { c->lpv_coop = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
     if (!strcmp(name, "df_dbg")) { c->df_dbg = value; return VXRT_OK; }
     if (!strcmp(name, "df_zver")) { c->df_zver = value; return VXRT_OK; }

@@ -96,6 +96,13 @@ struct vxrt_ctx {
     bool lpv_valid = false;
     bool lpv_coop = true;           // one cooperative kernel for the repropagation (set_option "lpv_coop"); 0 = one kernel per phase
 
+    // iteration-capped passes of the queue trace kernels (trace_queue.cuh): caps as bytes, low byte first (0 = end of list);
+    // 0 = one uncapped pass per queue.  set_option "trace_caps".  Off by default: bit-identical, but measured no faster
+    // (profiles/r2_k_sweep_caps.txt).
+    int trace_caps = 0;
+    void* d_trace_cont = nullptr;   // 2 continuation queues + counters
+    size_t trace_cont_cap = 0;      // rays each queue holds
+
     void* d_ray_buf = nullptr;  // staging of vxrt_cuda_trace_rays: origins | directions | hits
     size_t ray_cap = 0;
 
@@ -133,6 +140,13 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
         int _rc = vxrt_check_cuda((call), #call);                  \
         if (_rc != VXRT_OK) return _rc;                            \
     } while (0)
+
+// continuation storage of the iteration-capped trace passes (trace_queue.cuh), allocated on demand (api.cu)
+struct TraceCont {
+    float4* q[2];      // ping-pong continuation queues (capacity = rays of the largest pass)
+    int* count;        // [pass]: entries appended for pass + 1
+};
+int vxrt_ensure_trace_cont(vxrt_ctx* c, size_t rays, TraceCont* out);
 
 cudaEvent_t vxrt_probe_event(vxrt_ctx* c);
 int vxrt_apply_l2_policy(vxrt_ctx* c);  // next pooled event (nullptr when the probe is off or on error)

@@ -398,17 +398,28 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     const bool st = c->stats_on;
     cudaStream_t s = c->stream;
     // the path-ray kernel is the probed kernel: its own stats slot, event pairs around each launch when the probe is on
+    // (with trace_caps set, a "launch" of the probed kernel is the sequence of its capped passes)
 #define TRACE_PATHS(list, cnt, iters)                                                                                     \
     do {                                                                                                                  \
         cudaEvent_t e0 = vxrt_probe_event(c), e1 = vxrt_probe_event(c);                                                   \
         if (e0 && e1) cudaEventRecord(e0, s);                                                                             \
-        if (st) wf_trace_paths_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1); \
+        if (c->trace_caps) {                                                                                              \
+            const PathRays pol = {w, list};                                                                               \
+            const int rc_ = launch_trace_capped(c, g, pol, cnt, n, iters, c->d_stats + 1);                                \
+            if (rc_ != VXRT_OK) return rc_;                                                                               \
+            c->launches -= 1;                                                                                             \
+        } else if (st) wf_trace_paths_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1); \
         else wf_trace_paths_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1);   \
         if (e0 && e1) cudaEventRecord(e1, s);                                                                             \
     } while (0)
 #define TRACE_SHADOW()                                                                                                    \
     do {                                                                                                                  \
-        if (st) wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);       \
+        if (c->trace_caps) {                                                                                              \
+            const ShadowRays pol = {w, light};                                                                            \
+            const int rc_ = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);         \
+            if (rc_ != VXRT_OK) return rc_;                                                                               \
+            c->launches -= 1;                                                                                             \
+        } else if (st) wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);       \
         else wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);         \
     } while (0)
     for (int sample = 0; sample < max_spp; ++sample) {

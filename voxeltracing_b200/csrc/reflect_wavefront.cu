@@ -379,10 +379,20 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         rf_wf_gen_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);
-        if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
+        if (c->trace_caps) {
+            const ReflRays pol = {w};
+            const int rc = launch_trace_capped(c, g, pol, nullptr, n, a.trace_length, c->d_stats);
+            if (rc != VXRT_OK) return rc;
+            c->launches -= 1;
+        } else if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         rf_wf_shade_a_kernel<<<pgrid, 256, 0, s>>>(a, w);
-        if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
+        if (c->trace_caps) {
+            const ReflShadowRays pol = {w, strong};
+            const int rc = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);
+            if (rc != VXRT_OK) return rc;
+            c->launches -= 1;
+        } else if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         else rf_wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w);
         c->launches += 5;

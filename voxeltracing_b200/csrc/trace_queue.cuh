@@ -22,3 +22,108 @@ __device__ __forceinline__ void trace_queue(const GridView& g, Policy& pol, int 
     f3 o, d;
     if (tid < count && pol.fetch(tid, o, d)) pol.store(tid, traverse_df<STATS>(g, o, d, max_iter, st));
 }
+
+// ---- iteration-capped passes with compaction BETWEEN launches -------------------------------------------------------------------
+// A warp of trace_queue runs until its slowest ray ends; the bounce rays of a warp end after 5 ... 47 iterations, so 13 of 32 lanes
+// execute the average instruction (profiles/r1_s_ncu_full_summary.txt).  Both in-kernel remedies above paid for the compaction inside
+// the kernel.  Here the queue is walked in passes: pass j runs every ray it is given for the iterations [cap[j-1], cap[j]) of ITS loop;
+// a ray that ends inside the pass is finished exactly as before, a survivor is appended (warp-aggregated, 16 bytes: current position +
+// queue index + loop state) to a continuation queue, and the next launch starts from that dense queue.  The sequence of iterations of a
+// ray, its arithmetic and therefore its result are unchanged bit for bit; only which thread of which launch executes an iteration differs.
+// tools/analysis/lane_replay.py replays the oracle's per-ray iteration counts: caps (12, 24, max) leave 62 - 68 % of the warp-iterations
+// of the uncapped kernel on the rooms world, (6, 12, 24, max) 60 - 66 %; sorting the queue by direction octant and coarse origin cell
+// instead would leave 88 - 93 %.
+// MEASURED (config 4, 1080p, profiles/r2_k_sweep_caps.txt): bit-identical for every schedule, and not faster - GI 1.047 ms uncapped,
+// 1.044 (16, 32), 1.064 (12), 1.077 (12, 24), 1.244 (6, 12, 24); reflections 0.639 / 0.649 / 0.639 / 0.655 / 0.717.  What the replay
+// does not see: a warp-iteration costs ~78 instructions, not ~36, because lanes in a DDA step and lanes in a skip step of the same
+// iteration execute both blocks (that divergence survives any compaction of finished rays), every pass repeats the ray set-up and three
+// dependent loads (continuation -> queue entry -> ray) in front of a loop that is now short, and each extra launch adds a tail.  Kept as
+// an option (set_option "trace_caps"), off by default; tests/test_gpu_shade.py holds every schedule to bit identity.
+template <bool STATS, class Policy>
+__global__ void __launch_bounds__(VX_TRACE_CTA) trace_capped_kernel(GridView g, Policy pol, const int* __restrict__ count_ptr, int n_fixed, int it_begin,
+                                                                    int it_end, int max_iter, const float4* __restrict__ cin, float4* __restrict__ cout,
+                                                                    int* __restrict__ cout_count, TraceStatsDev* stats) {
+    const int count = count_ptr ? *count_ptr : n_fixed;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    LaneStats ls = {0u, 0u, 0u, 0u};
+    bool survivor = false;
+    f3 cur = F3(0.0f);
+    int idx = tid, state = 0;
+    if (tid < count) {
+        f3 o, d;
+        bool have;
+        if (cin) {
+            const float4 e = cin[tid];
+            const unsigned bits = __float_as_uint(e.w);
+            idx = (int)(bits & 0x0fffffffu);
+            state = (int)(bits >> 28);
+            cur = F3(e.x, e.y, e.z);
+            have = pol.fetch(idx, o, d);   // o = where the ray started (t is measured from there)
+        } else {
+            have = pol.fetch(idx, o, d);
+            cur = o;
+        }
+        if (have) {
+            const RaySetup rs = ray_setup(g, d);
+            bool ended = false;
+            for (int itr = it_begin; itr < it_end; ++itr) {
+                const int c = df_iteration<STATS>(g, rs, cur, state, &ls);
+                if (c == VX_ITER_CONTINUE) continue;
+                if (c == VX_ITER_TAIL) {
+                    bool Intersection = (state & 4) != 0;
+                    int MinIdx = state & 3;
+                    run_tail<STATS>(g, cur, d, itr, max_iter, Intersection, MinIdx, &ls);
+                    state = MinIdx | (Intersection ? 4 : 0);
+                }
+                ended = true;
+                break;
+            }
+            if (ended || it_end >= max_iter) pol.store(idx, trace_result<STATS>(g, rs, cur, o, state, &ls));
+            else survivor = true;
+        }
+    }
+    if (cout) {
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned m = __ballot_sync(0xffffffffu, survivor);
+        if (m) {
+            int base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(cout_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (survivor) cout[base + __popc(m & ((1u << lane) - 1u))] = make_float4(cur.x, cur.y, cur.z, __uint_as_float((unsigned)idx | ((unsigned)state << 28)));
+        }
+    }
+    if (STATS) flush_stats(stats, ls);
+}
+
+
+// Walks a queue of `n` entries (or *count_ptr of them) through the passes c->trace_caps describes.  Queue indices must fit 28 bits.
+template <class Policy>
+int launch_trace_capped(vxrt_ctx* c, const GridView& g, const Policy& pol, const int* count_ptr, size_t n, int max_iter, TraceStatsDev* stats) {
+    int caps[4], ncaps = 0;
+    for (int j = 0; j < 3; ++j) {
+        const int k = (c->trace_caps >> (8 * j)) & 0xff;
+        if (k > 0 && k < max_iter && (ncaps == 0 || k > caps[ncaps - 1])) caps[ncaps++] = k;
+    }
+    caps[ncaps++] = max_iter;
+    TraceCont tc = {{nullptr, nullptr}, nullptr};
+    if (ncaps > 1) {
+        if (n >= (1u << 28)) return vxrt_fail(VXRT_E_INVALID, "trace queue of %zu rays exceeds the 28-bit continuation index", n);
+        const int rc = vxrt_ensure_trace_cont(c, n, &tc);
+        if (rc != VXRT_OK) return rc;
+        VX_CUDA(cudaMemsetAsync(tc.count, 0, 4 * sizeof(int), c->stream));
+    }
+    const int grid = trace_queue_grid(n);
+    const bool st = c->stats_on;
+    int begin = 0;
+    for (int j = 0; j < ncaps; ++j) {
+        const float4* cin = j ? tc.q[(j - 1) & 1] : nullptr;
+        float4* cout = j + 1 < ncaps ? tc.q[j & 1] : nullptr;
+        int* cc = j + 1 < ncaps ? tc.count + j : nullptr;
+        const int* cnt = j ? tc.count + (j - 1) : count_ptr;
+        if (st) trace_capped_kernel<true, Policy><<<grid, VX_TRACE_CTA, 0, c->stream>>>(g, pol, cnt, (int)n, begin, caps[j], max_iter, cin, cout, cc, stats);
+        else trace_capped_kernel<false, Policy><<<grid, VX_TRACE_CTA, 0, c->stream>>>(g, pol, cnt, (int)n, begin, caps[j], max_iter, cin, cout, cc, stats);
+        begin = caps[j];
+    }
+    c->launches += ncaps;
+    return VXRT_OK;
+}
