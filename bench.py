@@ -54,6 +54,17 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="only warm-up + steps of the plain step (for ncu)")
     ap.add_argument("--tex-size", type=int, default=512)
     ap.add_argument("--no-svgf", action="store_true", help="skip the SVGF denoiser-chain measurement")
+    ap.add_argument("--sharding", default="auto", choices=["auto", "frames", "tiles"],
+                    help="N > 1: 'frames' = one frame of the camera path per rank per step (weak scaling); 'tiles' = row strips of ONE frame "
+                         "per step spread over the ranks (strong scaling; BASELINE config 5).  auto: tiles for config5, frames otherwise")
+    ap.add_argument("--strips", type=int, default=4, help="tiles sharding: strips per rank (interleaved over the frame for balance)")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
+                    help="N > 1: 'push' = every rank copies its outputs into rank 0's buffer with the copy engines over NVLink as each pass "
+                         "finishes; 'nccl' = round 1's one NCCL gather per frame on a side stream")
+    ap.add_argument("--outputs", default="final", choices=["final", "all"],
+                    help="what is gathered to rank 0 / read back in the end-to-end leg: 'final' = G-buffer, shadow, GI, reflection and direct "
+                         "attachments (44 B/px); 'all' adds the material G-buffer intermediates only later passes on the device consume (61 B/px)")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
@@ -267,6 +278,16 @@ def cpu_arm(blocks, wl, inputs):
     return CpuFrame(blocks, wl, inputs, prefer_ref=not any(p in wl["passes"] for p in ("gi", "reflection")))
 
 
+def config_block(args, wl, world_desc):
+    """The workload keys both arms print (identical, so the driver's same_config comparison holds)."""
+    cfg = frame_config(wl)
+    return {"workload": args.workload, "world": world_desc, "width": wl["width"], "height": wl["height"], "passes": list(wl["passes"]),
+            "gi_spp": cfg.gi_spp, "reflection_spp": cfg.refl_spp, "texture_size": args.tex_size}
+
+
+CPU_FRAME_BUDGET_S = 1.0   # one band of rows per frame sized to about this much CPU work, in BOTH the --impl reference arm and the in-line cpu_baseline leg
+
+
 def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
@@ -277,14 +298,15 @@ def run_reference_arm(args, wl, rank):
     cpu = cpu_arm(blocks, wl, inputs)
     for i in range(min(args.warmup, 2)):
         cpu.run(i, rows=(wl["height"] // 2 - 32, 64))
-    mrays, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, 120.0, 0.5)
+    mrays, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, 120.0, CPU_FRAME_BUDGET_S)
     line = {
         "impl": "reference", "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": n, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "world": world_desc, "width": wl["width"], "height": wl["height"], "passes": list(wl["passes"])},
+        "config": config_block(args, wl, world_desc),
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind,
-                         "sample": f"rows [{band[0]},{band[0] + band[1]}) of each {wl['width']}x{wl['height']} frame (every pass restricted to the band), {n} frames"},
+                         "sample": f"rows [{band[0]},{band[0] + band[1]}) of each {wl['width']}x{wl['height']} frame (every pass restricted to the band), {n} frames",
+                         "note": "the CPU implementation of the path on THIS box's host cores (one box, whatever --gpus says): at N GPUs the driver's ratio is N GPUs over one host"},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -448,6 +470,80 @@ def lpv_block(local_rank, stream, flush_buf, ev, peak, with_cpu):
     return out
 
 
+def parity_check(ctx, fr, wl, blocks, inputs, frame, read_full, rows=32):
+    """Post-timing self-check (outside every timed region): a band of `rows` rows of one frame of the benched workload, rendered by
+    the CUDA path at the benched resolution / texture size / spp, against the CPU oracle on the same inputs.  Tolerances are the ones
+    of tests/test_gpu_shade*.py: integer / texture-fetch attachments bit exact; soft shadows, GI hit masks >= 99.9 % identical; R16F
+    radiance within 1e-2 relative (+1e-3) on >= 99.5 % of pixels; direct term within 2^-9 relative on >= 99.9 %.
+    read_full(att) returns the full-frame attachment (from this GPU, or from rank 0's gathered frame in tiles mode).
+    The oracle is test infrastructure: it is only the checker here."""
+    from oracle import binding as ob
+    from voxeltracing_b200 import abi
+
+    W, H = wl["width"], wl["height"]
+    band = ((H - rows) // 2 // 8 * 8, rows)
+    sl = slice(band[0], band[0] + band[1])
+    cam = camera_for(wl, frame)
+    ow = ob.OracleWorld(blocks)
+    sc = ob.OracleScene(ow)
+    inputs.apply_to_oracle(sc)
+    res, ok = {}, True
+
+    def close(got, want, rtol, atol):
+        a, b = got.astype(np.float32), want.astype(np.float32)
+        c = np.abs(a - b) <= rtol * np.abs(b) + atol
+        return c.all(axis=-1) if c.ndim == 3 else c
+
+    def exact(name, got, want):
+        nonlocal ok
+        if got is None:
+            res[name] = "not among the gathered outputs"
+            return
+        same = bool(np.array_equal(np.ascontiguousarray(got[sl]).view(np.uint8), np.ascontiguousarray(want[sl]).view(np.uint8)))
+        res[name] = "bit-exact" if same else "DIFFERS"
+        ok = ok and same
+
+    def frac(name, mask, need):
+        nonlocal ok
+        f = float(mask.mean())
+        res[name] = round(f, 5)
+        ok = ok and f >= need
+
+    passes = wl["passes"]
+    g = ow.initial_trace(fr.params_for("primary", cam, frame, band))
+    for att, k in ((abi.ATT_INITIAL_T, "t"), (abi.ATT_INITIAL_NORMAL, "normal"), (abi.ATT_INITIAL_BLOCK, "block"), (abi.ATT_INITIAL_INVT, "inv_t")):
+        exact("primary." + k, read_full(att), g[k])
+    sh = None
+    if "shadow" in passes:
+        sh = ow.shadow_trace(fr.params_for("shadow", cam, frame, band), g["t"], g["normal"], BLUE_TEX)
+        frac("shadow.identical", read_full(abi.ATT_SHADOW)[sl] == sh["shadow"][sl], 0.999)
+    gb = None
+    if "gbuffer" in passes:
+        gb = sc.generate_gbuffer(fr.params_for("gbuffer", cam, frame, band), g["inv_t"], g["normal"], g["block"])
+        for att, k in ((abi.ATT_GBUF_ALBEDO, "albedo"), (abi.ATT_GBUF_NORMAL, "normal"), (abi.ATT_GBUF_PBR, "pbr"), (abi.ATT_GBUF_TEXAO, "texao")):
+            exact("gbuffer." + k, read_full(att), gb[k])
+    gi_cuda = None
+    if "gi" in passes:
+        want = sc.diffuse_trace(fr.params_for("gi", cam, frame, band), g["t"], g["normal"])
+        gi_cuda = {"sh": read_full(abi.ATT_GI_SH), "cocg": read_full(abi.ATT_GI_COCG), "utility": read_full(abi.ATT_GI_UTILITY),
+                   "aosky": read_full(abi.ATT_GI_AOSKY)}
+        frac("gi.paths_identical", (gi_cuda["aosky"][sl] == want["aosky"][sl]).all(axis=-1), 0.999)
+        for k in ("sh", "cocg", "utility"):
+            frac("gi." + k + "_within_1e-2", close(gi_cuda[k][sl], want[k][sl], 1e-2, 1e-3), 0.995)
+    if "reflection" in passes and gb is not None and gi_cuda is not None and sh is not None:
+        # the oracle's reflection pass reads the CUDA path's GI and shadow attachments, so only this pass is under test
+        want = sc.reflection_trace(fr.params_for("reflection", cam, frame, band), g["t"], g["normal"], gb,
+                                   {k: np.ascontiguousarray(v) for k, v in gi_cuda.items()}, np.ascontiguousarray(read_full(abi.ATT_SHADOW)))
+        got_c, got_h, got_e = read_full(abi.ATT_REFL_COLOR), read_full(abi.ATT_REFL_HITDIST), read_full(abi.ATT_REFL_EMISSIVE)
+        frac("reflection.mask_identical", got_e[sl] == want["emissive"][sl], 0.999)
+        frac("reflection.hit_identical", (got_h[sl].astype(np.float32) > 0) == (want["hitdist"][sl].astype(np.float32) > 0), 0.999)
+        frac("reflection.color_within_1e-2", close(got_c[sl], want["color"][sl], 1e-2, 1e-3), 0.995)
+    if "direct" in passes and gb is not None and sh is not None:
+        want = sc.shade_direct(fr.params_for("direct", cam, frame, band), g["inv_t"], gb, np.ascontiguousarray(read_full(abi.ATT_SHADOW)))
+        frac("direct.within_2^-9", close(read_full(abi.ATT_DIRECT)[sl], want[sl], 2.0 ** -9, 1e-6), 0.999)
+    return ("ok" if ok else "FAILED"), {"frame": frame, "rows": [band[0], band[0] + band[1]], "checks": res}
+
+
 def emit(line: dict):
     """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, which prints its version
     banner to stdout) writes to fd 1 has been redirected to stderr by quiet_stdout()."""
@@ -481,7 +577,7 @@ def main():
 
     import scene_util as su
     from voxeltracing_b200 import engine
-    from voxeltracing_b200.pipeline import PASS_KERNEL, PASS_OUTPUT_BYTES, FrameRenderer
+    from voxeltracing_b200.pipeline import PASS_KERNEL, PASS_OUTPUT_BYTES, PASS_OUTPUTS, FrameRenderer, band_rows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -505,15 +601,35 @@ def main():
     cfg = frame_config(wl)
     fr = FrameRenderer(ctx, cfg, inputs.grass, inputs.cactus)
 
-    def frame_of(step):  # every rank renders its own frame of the camera path per step (weak scaling)
-        return step * world_size + rank
+    # ---- work decomposition over the ranks ----
+    # frames: every rank renders its own frame of the camera path per step (weak scaling)
+    # tiles:  every rank renders `strips` row strips of THE SAME frame per step, interleaved over the frame so that sky and ground
+    #         rows are spread over the ranks (strong scaling, BASELINE config 5); the strips are passed as the vxrt_tile of every pass
+    tiles = world_size > 1 and (args.sharding == "tiles" or (args.sharding == "auto" and args.workload.startswith("config5")))
+    n_strips = max(1, args.strips) if tiles else 1
 
+    def frame_of(step):
+        return step if tiles else step * world_size + rank
+
+    def strips_of(r):
+        out = []
+        for j in range(n_strips):
+            row0, rows = band_rows(H, r + j * world_size, world_size * n_strips)
+            if rows > 0:
+                out.append((row0, rows))
+        return out
+
+    my_tiles = strips_of(rank) if tiles else [(0, 0)]
     n_total = args.warmup + args.steps
-    prepared = [fr.prepare(camera_for(wl, frame_of(s)), frame_of(s)) for s in range(n_total)]
+    prepared = [[fr.prepare(camera_for(wl, frame_of(s)), frame_of(s), t) for t in my_tiles] for s in range(n_total)]
+
+    def submit(s, hook_for=None):
+        for k, prep in enumerate(prepared[s]):
+            fr.submit(prep, hook=hook_for(k) if hook_for else None)
 
     if args.profile:
         for s in range(n_total):
-            fr.submit(prepared[s])
+            submit(s)
         torch.cuda.synchronize()
         ctx.close()
         return
@@ -537,23 +653,65 @@ def main():
                 pass_stats[name]["iterations"] += st["iterations"]
                 acc[0] += st["rays"]
 
-        fr.submit(prepared[s], hook=stat_hook)
+        submit(s, lambda k: stat_hook)
         rays_per_step.append(acc[0])
     probe_stats = ctx.probe_read(reset=True)   # rays / iterations of the probed kernel's launches alone
     ctx.stats_enable(False)
     total_rays = int(sum(rays_per_step))
     total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
 
-    # Output attachments.  With N > 1 the passes render straight into one of two packed communication
-    # buffers (vxrt_cuda_bind_attachment: the FBO ping-pong of Pipeline.cpp:2046-2048), so each frame is sent
-    # to rank 0 with ONE gather on a side stream while the next frame renders into the other buffer.
-    layout, total_bytes = [], 0
-    for att in fr.outputs:
+    # ---- what leaves the GPU ----
+    # 'final': the attachments later stages outside this path consume (primary G-buffer, shadow, GI, reflection, direct term: 44 B/px);
+    # the material G-buffer of GenerateGBuffer.glsl (17 B/px) only feeds the reflection / direct passes on the same device.
+    FINAL_PASSES = ("primary", "shadow", "gi", "reflection", "direct")
+    out_atts = [a for p_ in cfg.passes if (args.outputs == "all" or p_ in FINAL_PASSES) for a in PASS_OUTPUTS[p_]]
+    layout, slot_bytes = {}, 0        # attachment -> (offset in a frame slot, bytes per row, rows)
+    for att in out_atts:
         _, aw, ah, bpp = ctx.attachment_info(att)
-        layout.append((att, total_bytes, aw * ah * bpp))
-        total_bytes += (aw * ah * bpp + 255) // 256 * 256
+        layout[att] = (slot_bytes, aw * bpp, ah)
+        slot_bytes += (aw * ah * bpp + 255) // 256 * 256
+    out_bytes_px = sum(rb for _, rb, _ in layout.values()) / W
+
+    # ---- gather to rank 0 ----
+    # push (default): rank 0 owns a buffer of 2 frame slots (x world_size frames in 'frames' mode) that every rank has mapped
+    #   (vxrt_cuda_shared_alloc / _open); as soon as a pass is queued its attachments - whole, or the strip's rows - are copied into the
+    #   slot by the copy engines over NVLink (vxrt_cuda_copy_attachment_rows_async): no SM on either side, no kernel on rank 0, the copy
+    #   overlaps the rest of the frame, and only what the consumer needs travels.
+    # nccl: round 1's path (frames mode only) - the passes render into a packed buffer, one dist.gather per frame on a side stream.
+    push = world_size > 1 and args.gather == "push"
+    nccl_gather = world_size > 1 and not push
+    if nccl_gather and tiles:
+        raise SystemExit("--gather nccl is the frames-mode path of round 1; use --gather push with --sharding tiles")
+    per_slot = slot_bytes * (1 if tiles else world_size)
+    shared_base = None
+    if push:
+        handle = None
+        if rank == 0:
+            shared_base, handle = ctx.shared_alloc(2 * per_slot)
+        box = [handle]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            shared_base = ctx.shared_open(box[0])
+
+    def push_hook(s, tile):
+        row0, rows = tile
+        slot_off = (s & 1) * per_slot + (0 if tiles else rank * slot_bytes)
+
+        def hook(name, where):
+            if where == "end":
+                for att in PASS_OUTPUTS[name]:
+                    if att in layout:
+                        off, row_bytes, _ = layout[att]
+                        ctx.copy_attachment_rows_async(att, shared_base + slot_off + off + row0 * row_bytes, row0, rows)
+        return hook
+
     packed, gather_dst, comm = None, None, None
-    if world_size > 1:
+    if nccl_gather:
+        nl, total_bytes = [], 0
+        for att in out_atts:
+            off, rb, ah = layout[att]
+            nl.append((att, total_bytes, rb * ah))
+            total_bytes += (rb * ah + 255) // 256 * 256
         packed = [torch.empty(total_bytes, dtype=torch.uint8, device=f"cuda:{local_rank}") for _ in range(2)]
         gather_dst = list(torch.empty(world_size * total_bytes, dtype=torch.uint8, device=f"cuda:{local_rank}").chunk(world_size)) if rank == 0 else None
         comm = torch.cuda.Stream(device=local_rank)
@@ -563,44 +721,56 @@ def main():
             e.record(stream)
 
     def bind_set(k):
-        for att, off, n in layout:
+        for att, off, n in nl:
             ctx.bind_attachment(att, packed[k].data_ptr() + off, n)
-
-    outs = [torch.as_tensor(ctx.attachment_as_device_array(a), device=f"cuda:{local_rank}") for a in fr.outputs]
 
     # the inputs (37.7 MB of grids + the touched texture mips) are smaller than L2, so L2 is flushed between
     # timed steps by overwriting a 256 MiB buffer; the flush is outside the per-step event pairs
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
-    def step(s, hook=None):
-        if world_size == 1:
-            fr.submit(prepared[s], hook=hook)
-            return
-        k = s & 1
-        stream.wait_event(gather_done[k])      # the gather that last read this buffer must be finished
-        bind_set(k)
-        fr.submit(prepared[s], hook=hook)
-        render_done[k].record(stream)
-        with torch.cuda.stream(comm):
-            comm.wait_event(render_done[k])
-            dist.gather(packed[k], gather_dst, dst=0)
-            gather_done[k].record(comm)
+    def step(s, time_hook_for=None):
+        def hook_for(k):
+            hooks = []
+            if time_hook_for:
+                hooks.append(time_hook_for(k))
+            if push:
+                hooks.append(push_hook(s, my_tiles[k]))
+            if not hooks:
+                return None
+            return lambda name, where: [h(name, where) for h in hooks]
+
+        if nccl_gather:
+            k = s & 1
+            stream.wait_event(gather_done[k])      # the gather that last read this buffer must be finished
+            bind_set(k)
+            submit(s, hook_for)
+            render_done[k].record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(render_done[k])
+                dist.gather(packed[k], gather_dst, dst=0)
+                gather_done[k].record(comm)
+        else:
+            submit(s, hook_for)
 
     for s in range(args.warmup):
         step(s)
+    if push:
+        ctx.wait_reads()
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident ----
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    pass_ev = [{p: (ev(), ev()) for p in cfg.passes} for _ in range(args.steps)]
+    pass_ev = [[{p_: (ev(), ev()) for p_ in cfg.passes} for _ in my_tiles] for _ in range(args.steps)]
     step_ev = [(ev(), ev()) for _ in range(args.steps)]
 
     def make_hook(i):
-        def hook(name, where):
-            pass_ev[i][name][0 if where == "begin" else 1].record(stream)
-        return hook
+        def for_strip(k):
+            def hook(name, where):
+                pass_ev[i][k][name][0 if where == "begin" else 1].record(stream)
+            return hook
+        return for_strip
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -615,12 +785,18 @@ def main():
         step_ev[i][0].record(stream)
         step(args.warmup + i, make_hook(i))
         step_ev[i][1].record(stream)
+    tail = ev()
+    if push:
+        ctx.join_reads()                   # the stream waits (on the device) for the exports still in flight
+        tail.record(stream)
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
-    ms = float(sum(a.elapsed_time(b) for a, b in step_ev))  # exactly K steps, flushes excluded
-    if world_size > 1:  # + whatever of the last gather is still in flight after the last step ended
-        tail = torch.cuda.Event(enable_timing=True)
+    step_ms = [a.elapsed_time(b) for a, b in step_ev]
+    ms = float(sum(step_ms))  # exactly K steps, flushes excluded
+    if push:
+        ms += max(0.0, step_ev[-1][1].elapsed_time(tail))
+    if nccl_gather:  # + whatever of the last gather is still in flight after the last step ended
         with torch.cuda.stream(comm):
             tail.record(comm)
         torch.cuda.synchronize()
@@ -629,7 +805,43 @@ def main():
     probe_time = ctx.probe_read(reset=True)    # summed CUDA-event time of the probed kernel inside the timed region
     ctx.set_option("probe", 0)
     clocks = sampler.stop() if rank == 0 else None
-    pass_ms = {p: float(np.mean([pe[p][0].elapsed_time(pe[p][1]) for pe in pass_ev])) for p in cfg.passes}
+    pass_ms = {p_: float(np.mean([sum(strip[p_][0].elapsed_time(strip[p_][1]) for strip in pe) for pe in pass_ev])) for p_ in cfg.passes}
+
+    # ---- did rank 0 receive what was sent?  (outside the timed region) position-weighted checksums of every exported attachment
+    # (or strip) of the last two steps on the sender vs the same bytes in rank 0's buffer ----
+    gather_check = None
+    if push:
+        ctx.wait_reads()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+        def csum(t):
+            v = t.reshape(-1).view(torch.uint8).to(torch.int64)
+            w_ = torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 8191 + 1
+            return int((v * w_).sum().item())
+
+        s_last = args.warmup + args.steps - 1
+        mine = {}
+        # the last step's attachments are still in the context; re-render the one before it is not needed: slot (s_last & 1) only
+        for att in out_atts:
+            off, rb, ah = layout[att]
+            full = torch.as_tensor(ctx.attachment_as_device_array(att), device=f"cuda:{local_rank}").reshape(ah, -1).view(torch.uint8)
+            for (row0, rows) in my_tiles:
+                r0, nr = (row0, rows) if rows else (0, ah)
+                mine[(att, r0, nr)] = csum(full[r0:r0 + nr])
+        gathered = [None] * world_size
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            buf = torch.as_tensor(engine._DeviceArray(shared_base, (2 * per_slot,), "|u1"), device=f"cuda:{local_rank}")
+            bad = 0
+            for r in range(world_size):
+                slot_off = (s_last & 1) * per_slot + (0 if tiles else r * slot_bytes)
+                for (att, r0, nr), want in gathered[r].items():
+                    off, rb, ah = layout[att]
+                    got = csum(buf[slot_off + off + r0 * rb: slot_off + off + (r0 + nr) * rb])
+                    bad += got != want
+            n_chk = sum(len(g) for g in gathered)
+            gather_check = "ok (%d attachment%s of %d ranks, checksums equal)" % (n_chk, " strips" if tiles else "s", world_size) if bad == 0 else "FAILED: %d of %d differ" % (bad, n_chk)
 
     # ---- distance-field regeneration (BASELINE config 2) ----
     # (a) the figure of round 1: one regeneration between a CUDA-event pair after a 256 MiB memset.  Events tick in ~2 us steps on this
@@ -778,32 +990,34 @@ def main():
         refl_dn = {"ms_per_frame": sum(st["ms_per_launch"] for st in stages.values()), "resolution": [W, H], "stages": stages,
                    "bytes_per_pixel": ReflectionTemporal.STAGE_BYTES, "l2": "flushed before each frame's three launches"}
 
-    # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera,
-    # every output attachment read back to pinned host memory, inside the timed region ----
-    if world_size > 1:
+    # ---- end to end through the C ABI with host buffers: parameter blocks marshalled from the camera per step, the output
+    # attachments (--outputs) read back to pinned host memory, inside the timed region.  Every rank reads back what it rendered
+    # (its frame, or its strips of the frame) over its own PCIe link. ----
+    if nccl_gather:
         torch.cuda.synchronize()
-        for att, off, n in layout:
+        for att, off, n in nl:
             ctx.bind_attachment(att, None)      # back to context-owned attachments for the end-to-end leg
-        fr.submit(prepared[0])
-    # two sets of page-locked host buffers: frame k is copied out (vxrt_cuda_read_attachment_async, the PBO + fence
+        submit(0)
+    # two sets of page-locked host buffers: frame k is copied out (vxrt_cuda_copy_attachment_rows_async, the PBO + fence
     # pattern) while frame k+1 renders; a pass that overwrites an attachment waits on the device for its copy
-    host_out = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs] for _ in range(2)]
-    host_np = [[h.numpy() for h in hs] for hs in host_out]
-    d2h = sum(h.nbytes for h in host_np[0])
-    h2d = sum(ctypes.sizeof(p) for _, _, p in prepared[0])
-
-    from voxeltracing_b200.pipeline import PASS_OUTPUTS
-    host_of = [dict(zip(fr.outputs, bufs)) for bufs in host_np]
+    host_out = [{att: torch.empty(layout[att][1] * layout[att][2], dtype=torch.uint8).pin_memory() for att in out_atts} for _ in range(2)]
+    host_ptr = [{att: t.data_ptr() for att, t in hs.items()} for hs in host_out]
+    my_rows = sum(rows for _, rows in my_tiles) if tiles else H
+    d2h = int(sum(layout[att][1] * my_rows for att in out_atts))
+    h2d = sum(ctypes.sizeof(p_) for prep in prepared[0] for _, _, p_ in prep)
 
     def e2e_step(s):
-        prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s))
+        for tile in my_tiles:
+            prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s), tile)
+            row0, rows = tile
 
-        def read_pass_outputs(name, where):   # a pass's attachments start their way to the host as soon as it is queued
-            if where == "end":
-                for att in PASS_OUTPUTS[name]:
-                    ctx.read_attachment_async(att, host_of[s & 1][att])
+            def read_pass_outputs(name, where, row0=row0, rows=rows):   # a pass's attachments start their way to the host as soon as it is queued
+                if where == "end":
+                    for att in PASS_OUTPUTS[name]:
+                        if att in layout:
+                            ctx.copy_attachment_rows_async(att, host_ptr[s & 1][att] + row0 * layout[att][1], row0, rows)
 
-        fr.submit(prep, hook=read_pass_outputs)
+            fr.submit(prep, hook=read_pass_outputs)
 
     for s in range(min(3, args.warmup)):
         e2e_step(s)
@@ -820,15 +1034,112 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_rays = int(sum(rays_per_step[:e2e_steps]))
 
+    # ---- parity of what was just timed (outside every timed region): the first timed frame against the CPU oracle ----
+    parity = None
+    if not args.no_parity_check:
+        s_chk = args.warmup
+        f_chk = frame_of(s_chk)
+        if tiles:
+            # every rank renders and exports its strips of the frame once more; rank 0 checks the ASSEMBLED frame in its buffer
+            for k, prep in enumerate(prepared[s_chk]):
+                fr.submit(prep, hook=push_hook(s_chk, my_tiles[k]))
+            ctx.wait_reads()
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                buf = torch.as_tensor(engine._DeviceArray(shared_base, (2 * per_slot,), "|u1"), device=f"cuda:{local_rank}")
+                dt = engine._ATT_DTYPES
+
+                def read_full(att):
+                    if att not in layout:
+                        return None
+                    off, rb, ah = layout[att]
+                    raw = buf[(s_chk & 1) * per_slot + off:(s_chk & 1) * per_slot + off + rb * ah].cpu().numpy()
+                    d, ch = dt[att]
+                    a = raw.view(d)
+                    return a.reshape(ah, -1, ch) if ch > 1 else a.reshape(ah, -1)
+        else:
+            if rank == 0:
+                fr.render(camera_for(wl, f_chk), f_chk)
+
+                def read_full(att):
+                    try:
+                        return ctx.read_attachment(att)
+                    except engine.VxrtError:
+                        return None
+        if rank == 0:
+            status, detail = parity_check(ctx, fr, wl, blocks, inputs, f_chk, read_full)
+            parity = {"status": status, **detail}
+        if world_size > 1:
+            dist.barrier()
+
+    # ---- N > 1: distance-field regeneration sharded by z-slabs with one boundary-plane exchange, phase by phase, beside
+    # the replicated regeneration above (every rank applying the same edits and regenerating the whole field: no communication) ----
+    df_sharded = None
+    if world_size > 1 and 384 % world_size == 0:
+        from voxeltracing_b200 import sharding
+        backend = sharding.CudaSlabBackend(ctx, f"cuda:{local_rank}")
+        z0 = sharding.slab_bounds(backend.nz, world_size)
+        want_df = ctx.download_distance_field()
+        names = ("phase_a_slab_local_sweeps", "boundary_planes_all_gather", "phase_b_apply_carries", "slabs_all_gather")
+        acc = {k: [] for k in names}
+        tot = []
+        for it in range(12):
+            flush_buf.zero_()
+            dist.barrier()
+            e = [ev() for _ in range(5)]
+            e[0].record(stream)
+            backend.phase_a(rank, z0)
+            e[1].record(stream)
+            first = backend.plane(z0[rank]).contiguous()
+            last = backend.plane(z0[rank + 1] - 1).contiguous()
+            firsts = torch.empty((world_size,) + tuple(first.shape), dtype=first.dtype, device=first.device)
+            lasts = torch.empty_like(firsts)
+            dist.all_gather_into_tensor(firsts.view(-1), first.view(-1))
+            dist.all_gather_into_tensor(lasts.view(-1), last.view(-1))
+            e[2].record(stream)
+            backend.phase_b(rank, z0, firsts, lasts)
+            e[3].record(stream)
+            dist.all_gather_into_tensor(backend.df.view(-1), backend.df[z0[rank]:z0[rank + 1]].clone().view(-1))
+            backend.commit()
+            e[4].record(stream)
+            torch.cuda.synchronize()
+            if it >= 2:
+                for j, k in enumerate(names):
+                    acc[k].append(e[j].elapsed_time(e[j + 1]) * 1e3)
+                tot.append(e[0].elapsed_time(e[4]) * 1e3)
+        same = bool(np.array_equal(ctx.download_distance_field(), want_df))
+        t = torch.tensor([float(np.median(acc[k])) for k in names] + [float(np.median(tot)), 0.0 if same else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        df_sharded = {"us_per_regeneration": float(t[4]), "phases_us": {k: float(t[j]) for j, k in enumerate(names)},
+                      "slabs": world_size, "planes_per_slab": 384 // world_size, "boundary_bytes_per_rank": 2 * 384 * 128,
+                      "slab_bytes_per_rank": blocks.size // world_size, "identical_to_replicated": float(t[5]) == 0.0,
+                      "timing": "CUDA events on the stream the kernels and the NCCL collectives share, max over ranks of the per-phase medians of 10 regenerations, L2 flushed"}
+
     # ---- reduce over ranks ----
     if world_size > 1:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        r = torch.tensor([total_rays, e2e_rays, launches, total_iters], device="cuda", dtype=torch.int64)
+        r = torch.tensor([total_rays, e2e_rays, launches, total_iters, d2h], device="cuda", dtype=torch.int64)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        total_rays, e2e_rays, launches, total_iters = int(r[0]), int(r[1]), int(r[2]), int(r[3])
+        total_rays, e2e_rays, launches, total_iters, d2h_all = int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4])
+        all_pass_ms = [None] * world_size
+        dist.all_gather_object(all_pass_ms, pass_ms)
+    else:
+        d2h_all, all_pass_ms = d2h, [pass_ms]
 
+    if world_size == 1:
+        sharding_desc = "single GPU"
+    elif tiles:
+        sharding_desc = (f"tiles: every rank renders {n_strips} row strips of the SAME frame per step (interleaved over the frame, passed as the vxrt_tile of every pass); "
+                         "the strips' rows of the output attachments are copied into rank 0's frame by the copy engines over NVLink as each pass finishes")
+    elif push:
+        sharding_desc = ("frames: one frame of the camera path per rank per step; each pass's output attachments are copied into rank 0's buffer by the copy "
+                         "engines over NVLink (cudaIpc-mapped peer memory, no SM) as soon as the pass is queued, overlapping the rest of the frame")
+    else:
+        sharding_desc = ("frames: one frame of the camera path per rank per step; each frame's packed output attachments gathered to rank 0 "
+                         "with one NCCL gather on a side stream, overlapped with the next frame (double-buffered outputs)")
     if rank == 0:
         peak, peak_src = measured_peaks()
         mrays = total_rays / (ms * 1e-3) / 1e6
@@ -843,6 +1154,7 @@ def main():
             k_rays = probe_stats["rays"] / max(probe_stats["launches"], 1)
             S = probe_stats["iterations"] / max(probe_stats["rays"], 1)
             io_bytes = 40.0 * k_rays   # per ray: origin + direction (2 x float4) in, t + packed hit (8 B) out
+            io_bytes_w16 = 16.0 * k_rays   # SURVEY 8(d)'s W for a GI ray: the 16 output bytes of the GI pixel, no queue I/O
         else:
             kname = PASS_KERNEL[dom]
             st = pass_stats[dom]
@@ -850,7 +1162,9 @@ def main():
             k_rays = st["rays"] / args.steps
             k_ms = pass_ms[dom]
             io_bytes = PASS_OUTPUT_BYTES[dom] * W * H
+            io_bytes_w16 = io_bytes
         alg_bytes = k_rays * (S + 1) + io_bytes
+        alg_bytes_w16 = k_rays * (S + 1) + io_bytes_w16
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         sector_bytes = k_rays * 32 * (S + 1) + io_bytes
         gather_peak_gbs = ctx.gather_peak(256) * 32 / 1e9
@@ -861,23 +1175,31 @@ def main():
         line = {
             "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "world": world_desc, "width": W, "height": H, "passes": list(cfg.passes),
-                       "gi_spp": cfg.gi_spp, "reflection_spp": cfg.refl_spp, "texture_size": args.tex_size,
+            "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**config_block(args, wl, world_desc),
                        "rays_per_step_per_gpu": total_rays / args.steps / world_size,
                        "mean_iterations_per_ray": total_iters / max(total_rays, 1),
-                       "sharding": ("one frame of the camera path per rank per step; each frame's packed output attachments gathered to rank 0 "
-                                    "with one NCCL gather on a side stream, overlapped with the next frame (double-buffered outputs)"
-                                    if world_size > 1 else "single GPU"),
+                       "sharding": sharding_desc,
+                       "outputs": {"set": args.outputs, "bytes_per_pixel": out_bytes_px, "bytes_per_frame": int(out_bytes_px * W * H)},
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); camera pose changes every step"},
             "clocks": clocks,
-            "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "rank0_numa_node": numa_node},
+            "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * (world_size if not tiles else 1), "d2h_bytes_per_step": d2h_all,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "rank0_numa_node": numa_node,
+                    "d2h_gbs_per_rank": d2h / (e2e_s / e2e_steps) / 1e9,
+                    "note": "every rank reads back what it rendered (its frame / its strips) over its own PCIe link; bytes are summed over the ranks"},
             "gpu_launches": launches,
+            "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)), "of": "rank 0's K timed steps"},
+            "parity_check": parity["status"] if parity else None, "parity": parity,
+            "gather_check": gather_check,
             "pass_ms": pass_ms,
+            "pass_ms_last_rank": all_pass_ms[-1] if world_size > 1 else None,
             "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},
             "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_convention": "rays*(S+1) + 40 B/ray of queue I/O (origin + direction in, t + hit out); *_w16: SURVEY 8(d)'s W = 16 B/ray instead",
+                         "achieved_w16": alg_bytes_w16 / (k_ms * 1e-3) / 1e9, "frac_w16": alg_bytes_w16 / (k_ms * 1e-3) / 1e9 / peak,
+                         "l2_gather_achieved": sector_bytes / (k_ms * 1e-3) / 1e9, "l2_gather_peak": gather_peak_gbs,
+                         "l2_gather_frac": sector_bytes / (k_ms * 1e-3) / 1e9 / gather_peak_gbs,
                          "mean_iterations_per_ray": S, "rays_per_launch": k_rays, "avg_launch_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_mrays": k_rays / (k_ms * 1e-3) / 1e6,
@@ -892,6 +1214,9 @@ def main():
                             "achieved_gbs": 2 * nvox / (df_us * 1e-6) / 1e9, "frac_of_hbm_peak": 2 * nvox / (df_us * 1e-6) / 1e9 / peak,
                             "method": "8 contexts regenerate in turn (302 MB of grids > L2), 32 regenerations per CUDA-graph replay between one event pair, median of 10 replays",
                             "us_single_launch_after_write_flush": df_us_flush, "launches_per_regeneration": 2}
+        if df_sharded:
+            line["df_regen_sharded"] = {**df_sharded, "replicated_us_per_regeneration": df_us,
+                                        "note": "replicated = every rank applies the same edit list and regenerates the whole field (no communication): the fast path"}
         if svgf:
             line["svgf"] = svgf
         if shadow_dn:
@@ -903,13 +1228,21 @@ def main():
             line["lpv"] = lpv_block(local_rank, stream, flush_buf, ev, peak, not args.no_cpu_baseline)
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_arm(blocks, wl, inputs)
-            v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, 1.0)
+            v, ms_step, n, band = cpu_sample(cpu, wl, args.warmup, args.steps, args.cpu_seconds, CPU_FRAME_BUDGET_S)
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": f"rows [{band[0]},{band[0] + band[1]}) of {n} frames of the same camera path"}
         else:
             line["cpu_baseline"] = None
         emit(line)
 
+    if push:
+        ctx.wait_reads()
+        torch.cuda.synchronize()
+        if rank != 0:
+            ctx.shared_close(shared_base)
+        dist.barrier()
+        if rank == 0:
+            ctx.shared_free(shared_base)
     ctx.close()
     if world_size > 1:
         dist.destroy_process_group()

@@ -176,6 +176,24 @@ int vxrt_cuda_write_attachment(vxrt_ctx* ctx, int32_t attachment, int32_t width,
  * library until vxrt_cuda_wait_reads returns. */
 int vxrt_cuda_read_attachment_async(vxrt_ctx* ctx, int32_t id, void* dst, size_t bytes);
 int vxrt_cuda_wait_reads(vxrt_ctx* ctx);
+
+/* ---- multi-GPU export (the reference is single-GPU, this is the gather of its render targets to one GPU) ----
+ * One process per GPU: the gathering rank allocates a device buffer every other rank can WRITE over NVLink and hands its 64-byte
+ * handle to them (cudaIpc*; any byte transport will do - torch.distributed in bench.py); a rendering rank opens the handle and queues
+ * copies of its attachments - whole, or the rows of its screen band - into the buffer.  The copies are DMA transfers on the context's
+ * copy stream (the copy engines: no SM, no kernel on either GPU), ordered behind the pass that produced the attachment exactly
+ * like vxrt_cuda_read_attachment_async, and a later pass that overwrites the attachment waits for them on the device.
+ * vxrt_cuda_wait_reads returns when every queued copy has landed. */
+int vxrt_cuda_shared_alloc(vxrt_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t handle[64]);
+int vxrt_cuda_shared_free(vxrt_ctx* ctx, void* dev_ptr);
+int vxrt_cuda_shared_open(vxrt_ctx* ctx, const uint8_t handle[64], void** dev_ptr);   /* maps the peer's buffer, enabling peer access */
+int vxrt_cuda_shared_close(vxrt_ctx* ctx, void* dev_ptr);
+/* rows [row0, row0 + rows) of an attachment (rows == 0: the whole attachment) to `dst`, the address those rows have in the
+ * destination image: device memory of this GPU, of a peer (vxrt_cuda_shared_open) or page-locked host memory. */
+int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* ctx, int32_t id, int32_t row0, int32_t rows, void* dst);
+/* makes the context's stream wait (on the device) for every copy queued so far: an event recorded on the stream afterwards
+ * marks the moment the frame has left the GPU (device-side timing of the export; the host does not block). */
+int vxrt_cuda_join_reads(vxrt_ctx* ctx);
 /* device pointer + geometry of an attachment (valid until the pass that owns it is re-run at a
  * different size).  Used by the host side for NCCL tile gathers.                              */
 int vxrt_cuda_attachment_device(vxrt_ctx* ctx, int32_t attachment, void** dev_ptr, int32_t* width,

@@ -1,0 +1,58 @@
+"""Parity at the configurations bench.py times (not only at the small frames of the other tests): BASELINE config 4 (1920 x 1080, 512^2
+block textures, GI 1 spp, reflections) and config 5 (3840 x 2160, GI 4 spp - the sample index walks past the ranking tile,
+DiffuseRayTraceFrag.glsl:139-148), a 32-row band of one frame of the benched camera path against the oracle, through the same
+bench.parity_check the bench line's "parity_check" comes from; plus the band rendered as a vxrt_tile equals the band of the full frame."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+import scene_util as su  # noqa: E402
+from voxeltracing_b200 import abi, engine  # noqa: E402
+from voxeltracing_b200.pipeline import FrameRenderer  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def inputs512():
+    return {"constant": su.SceneInputs(512, sky="constant"), "gradient": None}
+
+
+def _setup(workload, inputs512):
+    wl = bench.WORKLOADS[workload]
+    sky = "constant" if wl["camera"] == "rooms" else "gradient"
+    if inputs512[sky] is None:
+        inputs512[sky] = su.SceneInputs(512, sky=sky)
+    inputs = inputs512[sky]
+    blocks, _ = bench.build_world(wl["world"])
+    ctx = engine.Context(0)
+    ctx.upload_world(blocks)
+    ctx.generate_distance_field()
+    ctx.set_blue_noise_texture(bench.BLUE_TEX)
+    inputs.apply_to_context(ctx)
+    fr = FrameRenderer(ctx, bench.frame_config(wl), inputs.grass, inputs.cactus)
+    return wl, blocks, inputs, ctx, fr
+
+
+@pytest.mark.parametrize("workload,frame", [("config4_1080p_gi", 3), ("config4_1080p_gi", 10), ("config5_4k_gi4", 5), ("config3_1080p_direct", 2)])
+def test_benched_configuration_matches_the_oracle_on_a_band(workload, frame, inputs512):
+    wl, blocks, inputs, ctx, fr = _setup(workload, inputs512)
+    try:
+        fr.render(bench.camera_for(wl, frame), frame)
+        status, detail = bench.parity_check(ctx, fr, wl, blocks, inputs, frame, ctx.read_attachment)
+        assert status == "ok", detail
+        assert len(detail["checks"]) >= 9
+        # the same band rendered as a screen tile (what --sharding tiles does per strip) equals the band of the full frame bit for bit
+        r0, r1 = detail["rows"]
+        full = {a: ctx.read_attachment(a).copy() for a in fr.outputs}
+        fr.render(bench.camera_for(wl, frame), frame, tile=(r0, r1 - r0))
+        for a in fr.outputs:
+            got = ctx.read_attachment(a)
+            assert np.array_equal(got[r0:r1].view(np.uint8), full[a][r0:r1].view(np.uint8)), (workload, a)
+    finally:
+        ctx.close()

@@ -251,6 +251,12 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_read_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_wait_reads": (C.c_int, [vp]),
+        "vxrt_cuda_join_reads": (C.c_int, [vp]),
+        "vxrt_cuda_copy_attachment_rows_async": (C.c_int, [vp, i32, i32, i32, vp]),
+        "vxrt_cuda_shared_alloc": (C.c_int, [vp, sz, C.POINTER(vp), vp]),
+        "vxrt_cuda_shared_free": (C.c_int, [vp, vp]),
+        "vxrt_cuda_shared_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "vxrt_cuda_shared_close": (C.c_int, [vp, vp]),
         "vxrt_cuda_bind_attachment": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_attachment_device": (C.c_int, [vp, i32, P(vp), P(i32), P(i32), P(i32)]),
         "vxrt_cuda_initial_trace": (C.c_int, [vp, P(PrimaryParams)]),

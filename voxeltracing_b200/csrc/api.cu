@@ -180,6 +180,7 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
     for (cudaEvent_t e : c->probe_ev) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->copies_joined) cudaEventDestroy(c->copies_joined);
     for (int i = 0; i < VXRT_ATT_COUNT; ++i) {
         if (c->att_ready[i]) cudaEventDestroy(c->att_ready[i]);
         if (c->att_read_done[i]) cudaEventDestroy(c->att_read_done[i]);
@@ -418,6 +419,66 @@ int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t b
     VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, c->copy_stream));
     VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
     c->att_read_pending[id] = true;
+    return VXRT_OK;
+}
+int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, void* dst) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    const Attachment& a = c->att[id];
+    if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
+    if (rows == 0) { row0 = 0; rows = a.height; }
+    if (row0 < 0 || rows < 0 || row0 + rows > a.height) return vxrt_fail(VXRT_E_INVALID, "copy_attachment_rows: rows [%d,+%d) of %d", row0, rows, a.height);
+    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->att_ready[id]) {
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
+    }
+    const size_t row_bytes = (size_t)a.width * a.bpp;
+    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));
+    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
+    VX_CUDA(cudaMemcpyAsync(dst, (const uint8_t*)a.ptr + (size_t)row0 * row_bytes, (size_t)rows * row_bytes, cudaMemcpyDefault, c->copy_stream));
+    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
+    c->att_read_pending[id] = true;
+    return VXRT_OK;
+}
+int vxrt_cuda_shared_alloc(vxrt_ctx* c, size_t bytes, void** dev_ptr, uint8_t handle[64]) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dev_ptr); REQUIRE_PTR(handle);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the IPC handle as 64 bytes");
+    if (bytes == 0) return vxrt_fail(VXRT_E_INVALID, "shared_alloc: 0 bytes");
+    void* p = nullptr;
+    VX_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return vxrt_check_cuda(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return VXRT_OK;
+}
+int vxrt_cuda_shared_free(vxrt_ctx* c, void* dev_ptr) {
+    REQUIRE_CTX(c);
+    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    VX_CUDA(cudaFree(dev_ptr));
+    return VXRT_OK;
+}
+int vxrt_cuda_shared_open(vxrt_ctx* c, const uint8_t handle[64], void** dev_ptr) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dev_ptr); REQUIRE_PTR(handle);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    VX_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VXRT_OK;
+}
+int vxrt_cuda_shared_close(vxrt_ctx* c, void* dev_ptr) {
+    REQUIRE_CTX(c);
+    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    VX_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return VXRT_OK;
+}
+int vxrt_cuda_join_reads(vxrt_ctx* c) {
+    REQUIRE_CTX(c);
+    if (!c->copy_stream) return VXRT_OK;
+    if (!c->copies_joined) VX_CUDA(cudaEventCreateWithFlags(&c->copies_joined, cudaEventDisableTiming));
+    VX_CUDA(cudaEventRecord(c->copies_joined, c->copy_stream));
+    VX_CUDA(cudaStreamWaitEvent(c->stream, c->copies_joined, 0));
     return VXRT_OK;
 }
 int vxrt_cuda_wait_reads(vxrt_ctx* c) {

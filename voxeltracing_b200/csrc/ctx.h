@@ -114,6 +114,7 @@ struct vxrt_ctx {
     cudaEvent_t att_ready[VXRT_ATT_COUNT] = {};      // recorded on `stream` when a read is requested
     cudaEvent_t att_read_done[VXRT_ATT_COUNT] = {};  // recorded on `copy_stream` after the copy
     bool att_read_pending[VXRT_ATT_COUNT] = {};
+    cudaEvent_t copies_joined = nullptr;             // vxrt_cuda_join_reads
 
     TraceStatsDev* d_stats = nullptr;  // [0] every trace kernel except the probed one, [1] the probed kernel
     bool stats_on = false;

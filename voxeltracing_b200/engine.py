@@ -330,6 +330,33 @@ class Context:
         assert out.nbytes == w * h * bpp and out.flags["C_CONTIGUOUS"]
         self._check(self._lib.vxrt_cuda_read_attachment_async(self._h, att, _p(out), out.nbytes))
 
+    def copy_attachment_rows_async(self, att: int, dst_ptr: int, row0: int = 0, rows: int = 0):
+        """Queues a DMA copy of rows [row0, row0 + rows) of an attachment (rows == 0: all of it) to `dst_ptr`, the address of those
+        rows in the destination: device memory here or on a peer GPU (shared_open), or page-locked host memory."""
+        self._check(self._lib.vxrt_cuda_copy_attachment_rows_async(self._h, att, row0, rows, C.c_void_p(dst_ptr)))
+
+    # -- multi-GPU export: a buffer of this GPU that other processes' GPUs write into over NVLink --
+    def shared_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte handle to hand to the other ranks)"""
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        self._check(self._lib.vxrt_cuda_shared_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shared_free(self, ptr: int):
+        self._check(self._lib.vxrt_cuda_shared_free(self._h, C.c_void_p(ptr)))
+
+    def shared_open(self, handle: bytes) -> int:
+        ptr, h = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self._lib.vxrt_cuda_shared_open(self._h, h, C.byref(ptr)))
+        return ptr.value
+
+    def shared_close(self, ptr: int):
+        self._check(self._lib.vxrt_cuda_shared_close(self._h, C.c_void_p(ptr)))
+
+    def join_reads(self):
+        """The context's stream waits on the device for the copies queued so far (see vxrt_cuda_join_reads)."""
+        self._check(self._lib.vxrt_cuda_join_reads(self._h))
+
     def wait_reads(self):
         self._check(self._lib.vxrt_cuda_wait_reads(self._h))
 
