@@ -127,8 +127,28 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(local_rank: int):
-    """Run this rank (and first-touch its pinned host buffers) on the CPU socket its GPU hangs off: with 8 ranks reading
-    126 MB per frame back over 8 PCIe links, remote-socket host memory is the bottleneck otherwise.  Best effort."""
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs its GPU hangs off: with 8 ranks reading their frames back
+    over 8 PCIe links, remote-socket host memory is the bottleneck otherwise.  Best effort: the GPU's CPU affinity from NVML
+    (what `nvidia-smi topo -m` prints), else the PCI device's numa_node in sysfs.  Returns a description or None."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        bus_id = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode() if hasattr(bus_id, "encode") else bus_id)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, w_ in enumerate(words) for b in range(64) if (int(w_) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return f"nvml cpu affinity: {len(allowed)} cpus ({allowed[0]}-{allowed[-1]})"
+        if allowed:
+            return f"nvml cpu affinity covers every allowed cpu ({len(allowed)}): single NUMA domain"
+    except Exception:
+        pass
     try:
         import torch
 
@@ -146,7 +166,7 @@ def bind_to_gpu_numa_node(local_rank: int):
         allowed = sorted(set(cpus) & os.sched_getaffinity(0))
         if allowed:
             os.sched_setaffinity(0, allowed)
-        return node
+        return f"sysfs numa node {node}"
     except Exception:
         return None
 
