@@ -339,6 +339,12 @@ typedef struct vxrt_reflection_params {
     float moon_strength_modifier;    /* u_MoonStrengthModifier */
     int32_t grass_props[10];
     vxrt_tile tile;
+    /* ApproximateGILPV (ReflectionTraceFrag.glsl:673-700, call site :881-883): where the screen-space reprojection of a reflection hit
+     * fails, its ambient term comes from the light propagation volume (vxrt_cuda_lpv_repropagate / _edit + the average block colours of
+     * vxrt_cuda_lpv_average_colors) instead of the pixel's own diffuse SH.  On by default in the engine (Pipeline.cpp:116,3162). */
+    int32_t lpv_gi;                          /* u_LPVGI */
+    int32_t use_decoupled_gi;                /* u_UseDecoupledGI (Pipeline.cpp:117,3168): sky light from the AO image's sky-hit channel + LPV */
+    int32_t screen_space_skylighting_valid;  /* u_ScreenSpaceSkylightingValid = USE_SVGF (Pipeline.cpp:3167) */
 } vxrt_reflection_params;
 int vxrt_cuda_reflection_trace(vxrt_ctx* ctx, const vxrt_reflection_params* p);
 

@@ -378,6 +378,14 @@ class OracleScene:
         f = np.ascontiguousarray(faces, dtype=np.float32)
         self.L.vxo_scene_set_skymap(self.h, f.shape[1], _p(f))
 
+    def set_lpv(self, level, block_type, avg512):
+        """Light propagation volume + BlockAverageColorData for ApproximateGILPV (params.lpv_gi of the reflection pass)."""
+        keep = (np.ascontiguousarray(level, np.uint8), np.ascontiguousarray(block_type, np.uint8), np.ascontiguousarray(avg512, np.float32))
+        self._keep.append(keep)
+        self.L.vxo_scene_set_lpv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.vxo_scene_set_lpv.restype = None
+        self.L.vxo_scene_set_lpv(self.h, *[_p(a) for a in keep])
+
     def lpv_average_colors(self) -> np.ndarray:
         """BlockAverageColorData of PrecomputeAverageBlockColor.comp: (128, 4) float32"""
         out = np.zeros((128, 4), dtype=np.float32)

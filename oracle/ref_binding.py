@@ -100,6 +100,13 @@ def set_scene(blocks, df, table, blue_noise, textures, skymap):
     L.vxref_set_skymap(f.shape[1], _p(f))
 
 
+def set_lpv(level, block_type, avg512):
+    """The propagation volume (two uint8 volumes) and BlockAverageColorData (128 x 4 float32) the reflection shader binds when
+    params.lpv_gi is set."""
+    _keep["lpv"] = (np.ascontiguousarray(level, np.uint8), np.ascontiguousarray(block_type, np.uint8), np.ascontiguousarray(avg512, np.float32))
+    lib().vxref_set_lpv(*[_p(a) for a in _keep["lpv"]])
+
+
 def lpv_average_colors() -> np.ndarray:
     """PrecomputeAverageBlockColor.comp on the scene of set_scene(): (128, 4) float32"""
     out = np.zeros((128, 4), dtype=np.float32)

@@ -449,6 +449,13 @@ struct vxref_reflection_inputs {
     const uint16_t* gi_sh_h4; const uint16_t* gi_cocg_h2; const uint8_t* gi_aosky_u8x2; int32_t iw, ih;
     const uint8_t* shadow_u8; int32_t sw, sh;
 };
+static const uint8_t* g_lpv_level = nullptr;
+static const uint8_t* g_lpv_type = nullptr;
+static const float* g_lpv_avg512 = nullptr;
+/* the propagation volume + average block colours the reflection shader binds when u_LPVGI is on (borrowed) */
+void vxref_set_lpv(const uint8_t* level, const uint8_t* block_type, const float* avg512) {
+    g_lpv_level = level; g_lpv_type = block_type; g_lpv_avg512 = avg512;
+}
 void vxref_reflection_trace(const vxrt_reflection_params* p, const vxref_reflection_inputs* in, uint16_t* color_h4, uint16_t* hitdist_h,
                             uint8_t* emissive_u8) {
     namespace S = shader_ReflectionTraceFrag;
@@ -485,8 +492,14 @@ void vxref_reflection_trace(const vxrt_reflection_params* p, const vxref_reflect
     S::u_View.load(p->view); S::u_Projection.load(p->projection);
     S::u_ReprojectToScreenSpace = p->reproject_to_screen_space != 0; S::u_UseBlueNoise = p->use_blue_noise != 0;
     S::u_ReflectPlayer = false; S::u_DeriveFromDiffuseSH = p->derive_from_diffuse_sh != 0;
-    S::u_LPVGI = false; S::u_QualityLPVGI = false; S::u_Halton = vec2(p->halton[0], p->halton[1]);
-    S::u_RoughnessBias = p->roughness_bias != 0; S::u_UseDecoupledGI = false;
+    S::u_LPVGI = p->lpv_gi != 0; S::u_QualityLPVGI = false; S::u_Halton = vec2(p->halton[0], p->halton[1]);
+    S::u_RoughnessBias = p->roughness_bias != 0; S::u_UseDecoupledGI = p->use_decoupled_gi != 0;
+    S::u_ScreenSpaceSkylightingValid = p->screen_space_skylighting_valid != 0;
+    if (p->lpv_gi) {   /* Pipeline.cpp:3115-3116,3240-3251: u_LPV (R8, LINEAR), u_LPVBlocks (R8UI, NEAREST), BlockAverageColorData (binding 4) */
+        S::u_LPV.data = g_lpv_level; S::u_LPV.w = 384; S::u_LPV.h = 128; S::u_LPV.d = 384;
+        S::u_LPVBlocks.data = g_lpv_type; S::u_LPVBlocks.w = 384; S::u_LPVBlocks.h = 128; S::u_LPVBlocks.d = 384;
+        S::BlockAverageColorData.data = reinterpret_cast<const vec4*>(g_lpv_avg512);
+    }
     BIND_BLOCK_SSBO(S)
     BIND_BLUE_SSBO(S)
     const int W = p->width, H = p->height;

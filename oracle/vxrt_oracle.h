@@ -105,6 +105,9 @@ void vxo_scene_set_texture_array(vxo_scene* s, int32_t kind, int32_t layers, int
 void vxo_scene_set_skymap(vxo_scene* s, int32_t res, const float* rgb_faces);
 /* mip level `level` of array `kind` as built by the pinned glGenerateMipmap model (for tests) */
 void vxo_scene_lpv_average_colors(const vxo_scene* s, float* out512);
+/* the two byte volumes of the light propagation volume + BlockAverageColorData (128 x 4 floats), borrowed: ApproximateGILPV of the
+ * reflection pass (vxrt_reflection_params.lpv_gi) */
+void vxo_scene_set_lpv(vxo_scene* s, const uint8_t* level, const uint8_t* block_type, const float* avg512);
 int32_t vxo_scene_texture_level(const vxo_scene* s, int32_t kind, int32_t level, uint8_t* out, int64_t out_bytes);
 
 /* GenerateGBuffer.glsl main(); inputs = primary attachments (1/t R32F, face R8, block R8) at gw x gh */

@@ -23,6 +23,10 @@ struct vxo_scene {
     TexArray tex[4];
     std::vector<float> sky;
     TexCube skymap;
+    /* light propagation volume + BlockAverageColorData for ApproximateGILPV (borrowed; vxo_scene_set_lpv) */
+    const uint8_t* lpv_level = nullptr;
+    const uint8_t* lpv_type = nullptr;
+    const float* lpv_avg512 = nullptr;
 };
 
 static const float PI = 3.14159265359f;
@@ -47,6 +51,9 @@ vxo_scene* vxo_scene_create(const vxo_world* w) {
     return s;
 }
 void vxo_scene_destroy(vxo_scene* s) { delete s; }
+void vxo_scene_set_lpv(vxo_scene* s, const uint8_t* level, const uint8_t* block_type, const float* avg512) {
+    s->lpv_level = level; s->lpv_type = block_type; s->lpv_avg512 = avg512;
+}
 void vxo_scene_set_block_data(vxo_scene* s, const int32_t* t) { memcpy(s->block_data, t, sizeof(s->block_data)); }
 void vxo_scene_set_blue_noise(vxo_scene* s, const int32_t* d, int32_t n) { s->blue_noise.assign(d, d + n); }
 void vxo_scene_set_texture_array(vxo_scene* s, int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba) {
@@ -911,6 +918,45 @@ inline bool in_thresholded_screen_space(v2 v) {
 
 }  // namespace
 
+extern "C" void vxo_lpv_sample(const uint8_t* level, const uint8_t* block_type, int32_t nx, int32_t ny, int32_t nz, const float* avg512,
+                               const float* points, int32_t n, const float dither[3], float* rgb_out);   /* vxrt_oracle_lpv.cpp */
+
+/* bayer2 .. bayer32 (ReflectionTraceFrag.glsl:21-29) */
+static inline float bayer2(float ax, float ay) {
+    ax = floorf(ax); ay = floorf(ay);
+    return gfract(ax * 0.5f + ay * (ay * 0.75f));   /* dot(a, vec2(0.5, a.y * 0.75)) */
+}
+static inline float bayer4(float ax, float ay) { return bayer2(0.5f * ax, 0.5f * ay) * 0.25f + bayer2(ax, ay); }
+static inline float bayer8(float ax, float ay) { return bayer4(0.5f * ax, 0.5f * ay) * 0.25f + bayer2(ax, ay); }
+static inline float bayer16(float ax, float ay) { return bayer8(0.5f * ax, 0.5f * ay) * 0.25f + bayer2(ax, ay); }
+static inline float bayer32(float ax, float ay) { return bayer16(0.5f * ax, 0.5f * ay) * 0.25f + bayer2(ax, ay); }
+
+/* ApproximateGILPV (ReflectionTraceFrag.glsl:673-700) with LPVDither of main() (:721-723) and SampleLPVData (vxo_lpv_sample) */
+static v3 approximate_gi_lpv(const vxo_scene* s, const vxrt_reflection_params* p, const Tex2D& tAO, int px, int py, v2 vtc, bool SunStronger,
+                             v3 SkyAmbientG, v3 P, v3 B) {
+    const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+    const float tf = p->temporal ? 1.0f : 0.0f;
+    const float b32 = bayer32(fx + ((float)p->current_frame * 0.75f) * tf, fy + ((float)p->current_frame * 0.5f) * tf);
+    const float dither[3] = {b32 / 384.0f, b32 / 128.0f, b32 / 384.0f};
+    const float pt[3] = {P.x, P.y, P.z};
+    float rgb[3];
+    vxo_lpv_sample(s->lpv_level, s->lpv_type, s->world.nx, s->world.ny, s->world.nz, s->lpv_avg512, pt, 1, dither, rgb);
+    const v3 LPV = V3(rgb[0], rgb[1], rgb[2]);
+    if (p->use_decoupled_gi) {
+        v3 Sky = SkyAmbientG;
+        const float L = dot(Sky, V3(0.2125f, 0.7154f, 0.0721f));
+        Sky = gmix(V3(L), Sky, SunStronger ? 0.3f : 0.6f);
+        v3 Skylighting = Sky * (tex2d_sample(tAO, vtc.x, vtc.y).y * (SunStronger ? 3.5f : 4.0f));
+        Skylighting = Skylighting + V3(bayer16(fx, fy) / 512.0f);
+        const v3 hi = B + V3(0.075f);
+        Skylighting = V3(gclamp(Skylighting.x * 13.0f, 0.0f, hi.x), gclamp(Skylighting.y * 13.0f, 0.0f, hi.y), gclamp(Skylighting.z * 13.0f, 0.0f, hi.z));
+        if (!p->screen_space_skylighting_valid) Skylighting = B;
+        return Skylighting + LPV;
+    }
+    const v3 BaseAmbient = B * 0.9f;
+    return LPV + BaseAmbient;
+}
+
 extern "C" void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_params* p, const vxo_reflection_inputs* in,
                                      uint16_t* color_h4, uint16_t* hitdist_h, uint8_t* emissive_u8, vxrt_trace_stats* stats) {
     const int W = p->width, H = p->height;
@@ -934,6 +980,8 @@ extern "C" void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_p
     float SunVisibility = gclamp(dot(sun, V3(0.0f, 1.0f, 0.0f)) + 0.05f, 0.0f, 0.1f) * 12.0f;
     SunVisibility = 1.0f - SunVisibility;
     const v3 SAMPLED_COLOR_MIXED = gmix(SAMPLED_SUN_COLOR, SAMPLED_MOON_COLOR, SunVisibility);
+    const bool SunStronger = strong.x == sun.x && strong.y == sun.y && strong.z == sun.z;   /* :809 */
+    const v3 SkyAmbientG = p->lpv_gi ? xyz(texcube_sample(s->skymap, 0.0f, 1.0f, 0.0f)) : V3(0.0f);   /* :719 */
     uint64_t s_rays = 0, s_it = 0, s_dda = 0, s_hits = 0;
 #pragma omp parallel for schedule(dynamic, 2) num_threads(nthreads()) reduction(+ : s_rays, s_it, s_dda, s_hits)
     for (int py = r0; py < r1; ++py)
@@ -1028,6 +1076,8 @@ extern "C" void vxo_reflection_trace(const vxo_scene* s, const vxrt_reflection_p
                                 }
                             }
                         }
+                        if (p->lpv_gi && !ReprojectionSuccessful)   /* :881-883 */
+                            Ambient = approximate_gi_lpv(s, p, tAO, px, py, vtc, SunStronger, SkyAmbientG, HitPosition + Normal * 0.5f, BaseIndirectDiffuse);
                         const int32_t* bd = s->block_data;
                         v4 ids = V4((float)bd[0 * 128 + reference_id], (float)bd[1 * 128 + reference_id], (float)bd[2 * 128 + reference_id], (float)bd[3 * 128 + reference_id]);
                         if (reference_id == p->grass_props[0]) {

@@ -39,6 +39,7 @@ class RefBackend:
     shade_direct = staticmethod(rb.shade_direct)
     diffuse_trace = staticmethod(rb.diffuse_trace)
     reflection_trace = staticmethod(rb.reflection_trace)
+    set_lpv = staticmethod(rb.set_lpv)
 
 
 def main():
@@ -57,6 +58,15 @@ def main():
                 out[f"{case['name']}_{k}"] = v
     np.savez_compressed(OUT / "shade_ref.npz", **out)
     print("wrote", OUT / "shade_ref.npz", (OUT / "shade_ref.npz").stat().st_size, "bytes,", len(out), "arrays")
+    # ApproximateGILPV: the reflection outputs with u_LPVGI on (the volume itself comes from the flood-fill restatement, which
+    # tests/test_oracle_lpv.py pins against the reference's VolumetricFloodFill.cpp)
+    case = sg.LPV_CASE
+    blocks = sg.world(case["world"])
+    be = RefBackend(blocks, rb.distance_field(blocks), inputs)
+    res = sg.run_case(be, case, inputs)
+    lpv = {f"{case['name']}_{k}": v for k, v in res.items() if k.startswith("refl")}
+    np.savez_compressed(OUT / "shade_lpv_ref.npz", **lpv)
+    print("wrote", OUT / "shade_lpv_ref.npz", (OUT / "shade_lpv_ref.npz").stat().st_size, "bytes,", len(lpv), "arrays")
 
 
 if __name__ == "__main__":

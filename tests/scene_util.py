@@ -94,7 +94,7 @@ def gi_params(cam, w, h, frame=0, spp=1, checkerboard=False, sun_tick=50.0, tile
 
 
 def reflection_params(cam, w, h, frame=0, spp=1, sun_tick=50.0, tile=(0, 0), inputs: SceneInputs = None, reproject=False,
-                      temporal=False) -> abi.ReflectionParams:
+                      temporal=False, lpv_gi=False, decoupled=False, ss_sky_valid=False) -> abi.ReflectionParams:
     p = abi.ReflectionParams()
     fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
     fill(p.view, cam.view); fill(p.projection, cam.projection)
@@ -103,6 +103,7 @@ def reflection_params(cam, w, h, frame=0, spp=1, sun_tick=50.0, tile=(0, 0), inp
     p.current_frame, p.current_frame_mod128 = frame, frame % 128
     p.use_blue_noise, p.rough_reflections, p.roughness_bias, p.temporal = 1, 1, 0, int(temporal)
     p.reproject_to_screen_space, p.derive_from_diffuse_sh = int(reproject), 0
+    p.lpv_gi, p.use_decoupled_gi, p.screen_space_skylighting_valid = int(lpv_gi), int(decoupled), int(ss_sky_valid)
     sun, moon, strong = host_api.sun_direction(sun_tick)
     fill(p.sun_direction, sun); fill(p.moon_direction, moon); fill(p.stronger_light_direction, strong)
     fill(p.viewer_position, cam.position)

@@ -16,6 +16,7 @@ import scene_util as su  # noqa: E402
 from voxeltracing_b200 import abi, host_api  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden" / "shade_ref.npz"
+GOLD_LPV = ROOT / "tests" / "golden" / "shade_lpv_ref.npz"
 W, H = 160, 90
 TEX = 64
 WORLDS = ("rooms2", "plains1")
@@ -29,6 +30,14 @@ CASES = [
          gi=[dict(frame=9, spp=3, checkerboard=True), dict(frame=2, spp=4, checkerboard=False)],
          refl=[dict(frame=9, spp=2, reproject=True, temporal=True)]),
 ]
+
+# ApproximateGILPV inside the reflection pass (ReflectionTraceFrag.glsl:673-700,881-883; u_LPVGI is on by default in the engine): the same
+# frame with the propagation volume of the world's lamps bound, in the plain and the decoupled form, with and without screen-space
+# reprojection (the LPV term only replaces the ambient term where the reprojection fails)
+LPV_CASE = dict(name="rooms_lpv", world="rooms2", pos=[200, 58, 200], yaw=30.0, pitch=-15.0, sun_ticks=(), lpv_limit=8,
+                gi=[dict(frame=0, spp=1, checkerboard=False)],
+                refl=[dict(frame=3, spp=1, lpv_gi=True), dict(frame=6, spp=2, lpv_gi=True, temporal=True, decoupled=True, ss_sky_valid=True),
+                      dict(frame=2, spp=1, lpv_gi=True, decoupled=True), dict(frame=9, spp=2, lpv_gi=True, reproject=True, temporal=True)])
 
 GB_KEYS = ("albedo", "normal", "pbr", "texao")
 GI_KEYS = ("sh", "cocg", "utility", "aosky")
@@ -46,6 +55,10 @@ def inputs() -> su.SceneInputs:
 
 def golden():
     return np.load(GOLD)
+
+
+def golden_lpv():
+    return np.load(GOLD_LPV)
 
 
 def camera(case):
@@ -68,6 +81,19 @@ def shadow_params(cam) -> abi.ShadowParams:
     return s
 
 
+def lpv_inputs(blocks, inp, limit):
+    """(light level, block type, BlockAverageColorData) of the world's lamps from the CPU restatements (pinned against the reference's own
+    VolumetricFloodFill.cpp / PrecomputeAverageBlockColor.comp by tests/test_oracle_lpv.py)."""
+    from oracle import binding as ob
+    from oracle import world_binding as wb
+
+    lights = wb.collect_lights(blocks, inp.table)
+    level, btype = wb.lpv_repropagate(blocks, lights, limit)
+    sc = ob.OracleScene(ob.OracleWorld(blocks, np.zeros_like(blocks)))
+    inp.apply_to_oracle(sc)
+    return level, btype, sc.lpv_average_colors(), lights
+
+
 def run_case(be, case, inp) -> dict:
     """All passes of a case through one executor `be` (methods initial_trace, shadow_trace, generate_gbuffer, shade_direct,
     diffuse_trace, reflection_trace with the signatures of oracle.ref_binding).  Returns {key: array} without the case prefix."""
@@ -86,6 +112,9 @@ def run_case(be, case, inp) -> dict:
         gis.append(gi)
         for k in GI_KEYS:
             out[f"gi{i}_{k}"] = gi[k]
+    if "lpv_limit" in case:
+        level, btype, avg, _ = lpv_inputs(be.blocks, inp, case["lpv_limit"])
+        be.set_lpv(level, btype, avg)
     for i, kw in enumerate(case["refl"]):
         rf = be.reflection_trace(su.reflection_params(cam, W, H, inputs=inp, **kw), g["t"], g["normal"], gb, gis[0], sh["shadow"])
         for k in RF_KEYS:

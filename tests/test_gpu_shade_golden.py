@@ -123,3 +123,41 @@ def test_reflections_vs_reference(case, contexts, gold, inputs):
         okc = _close(got_c, want_c, 1e-2, 1e-3).all(axis=-1)
         assert okc.mean() >= 0.995, (kw, okc.mean())
         assert (got_c.view(np.uint16) == want_c.view(np.uint16)).mean() > 0.9, kw
+
+
+def test_reflections_with_lpv_gi_vs_reference(contexts, gold, inputs):
+    """ApproximateGILPV inside the reflection shading (ReflectionTraceFrag.glsl:673-700,881-883): the CUDA pass with the propagation
+    volume bound against the compiled shader's outputs with u_LPVGI on (plain / decoupled, with / without reprojection).  The volume
+    and the average colours are uploaded from the CPU restatements, so the pass is judged on the fixture's exact inputs; the wavefront
+    and the per-pixel kernels must agree bit for bit."""
+    g = sg.golden_lpv()
+    case = sg.LPV_CASE
+    c = contexts[case["world"]]
+    cam = _front(c, sg.CASES[0], gold, inputs)        # same camera as rooms_a
+    n = case["name"]
+    c.diffuse_trace(su.gi_params(cam, W, H, **case["gi"][0]))
+    for att, k in ((abi.ATT_GI_SH, "sh"), (abi.ATT_GI_COCG, "cocg"), (abi.ATT_GI_UTILITY, "utility"), (abi.ATT_GI_AOSKY, "aosky")):
+        c.write_attachment(att, gold[f"rooms_a_gi0_{k}"])
+    rp0 = su.reflection_params(cam, W, H, inputs=inputs, **case["refl"][0])
+    with pytest.raises(engine.VxrtError):
+        c.reflection_trace(rp0)                        # lpv_gi without a volume
+    level, btype, avg, _ = sg.lpv_inputs(sg.world(case["world"]), inputs, case["lpv_limit"])
+    c.lpv_upload(level, btype)
+    c.lpv_set_average_colors(avg)
+    for i, kw in enumerate(case["refl"]):
+        rp = su.reflection_params(cam, W, H, inputs=inputs, **kw)
+        outs = {}
+        for mode in (1, 0):
+            c.set_option("wavefront", mode)
+            c.reflection_trace(rp)
+            outs[mode] = [c.read_attachment(a).copy() for a in (abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE)]
+        c.set_option("wavefront", 1)
+        for a, b in zip(outs[0], outs[1]):
+            assert sg.same_bits(a, b), kw
+        got_c, got_h, got_e = outs[1]
+        want_c, want_h, want_e = (g[f"{n}_refl{i}_{k}"] for k in sg.RF_KEYS)
+        assert (got_e == want_e).mean() >= 0.999
+        assert ((got_h.astype(np.float32) > 0) == (want_h.astype(np.float32) > 0)).mean() >= 0.999
+        okc = _close(got_c, want_c, 1e-2, 1e-3).all(axis=-1)
+        assert okc.mean() >= 0.995, (kw, okc.mean())
+        assert (got_c.view(np.uint16) == want_c.view(np.uint16)).mean() > 0.9, kw

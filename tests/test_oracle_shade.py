@@ -18,6 +18,7 @@ from voxeltracing_b200 import host_api
 
 class OracleBackend:
     def __init__(self, blocks, inputs, df=None):
+        self.blocks = blocks
         self.ow = ob.OracleWorld(blocks, df)
         self.sc = ob.OracleScene(self.ow)
         inputs.apply_to_oracle(self.sc)
@@ -39,6 +40,9 @@ class OracleBackend:
 
     def reflection_trace(self, *a):
         return self.sc.reflection_trace(*a)
+
+    def set_lpv(self, level, btype, avg):
+        self.sc.set_lpv(level, btype, avg)
 
 
 @pytest.fixture(scope="module")
@@ -95,6 +99,7 @@ class RefBackend:
     shade_direct = staticmethod(rb.shade_direct)
     diffuse_trace = staticmethod(rb.diffuse_trace)
     reflection_trace = staticmethod(rb.reflection_trace)
+    set_lpv = staticmethod(rb.set_lpv)
 
 
 LIVE_CASES = [
@@ -105,6 +110,34 @@ LIVE_CASES = [
          gi=[dict(frame=64, spp=3, checkerboard=False), dict(frame=7, spp=4, checkerboard=False)],
          refl=[dict(frame=11, spp=2, reproject=True, temporal=True)]),
 ]
+
+
+def test_oracle_lpv_gi_matches_reference_golden(inputs):
+    """ApproximateGILPV inside the reflection pass: the oracle against the compiled shader's outputs with u_LPVGI on."""
+    g = sg.golden_lpv()
+    case = sg.LPV_CASE
+    res = sg.run_case(OracleBackend(sg.world(case["world"]), inputs), case, inputs)
+    n = 0
+    for k, v in res.items():
+        if k.startswith("refl"):
+            assert sg.same_bits(v, g[f"{case['name']}_{k}"]), k
+            n += 1
+    assert n == 3 * len(case["refl"])
+    # the volume changes the picture: same frame / spp with and without the LPV term differ
+    plain = sg.golden()
+    assert not sg.same_bits(g["rooms_lpv_refl0_color"], plain["rooms_a_refl0_color"])
+
+
+@needs_ref
+def test_oracle_lpv_gi_equals_compiled_reference_shader_live(inputs):
+    case = dict(sg.LPV_CASE, name="live_lpv", pos=[188.3, 61.0, 172.9], yaw=115.0, pitch=-8.0, lpv_limit=4,
+                refl=[dict(frame=5, spp=2, lpv_gi=True, reproject=True), dict(frame=1, spp=1, lpv_gi=True, decoupled=True, ss_sky_valid=True, temporal=True)])
+    blocks = sg.world(case["world"])
+    df = ob.distance_field(blocks)
+    a = sg.run_case(OracleBackend(blocks, inputs, df), case, inputs)
+    b = sg.run_case(RefBackend(blocks, df, inputs), case, inputs)
+    for k in a:
+        assert sg.same_bits(a[k], b[k]), k
 
 
 @needs_ref

@@ -110,6 +110,7 @@ class ReflectionParams(C.Structure):
         ("sun_direction", C.c_float * 3), ("moon_direction", C.c_float * 3), ("stronger_light_direction", C.c_float * 3),
         ("viewer_position", C.c_float * 3), ("sun_strength_modifier", C.c_float), ("moon_strength_modifier", C.c_float),
         ("grass_props", C.c_int32 * 10), ("tile", Tile),
+        ("lpv_gi", C.c_int32), ("use_decoupled_gi", C.c_int32), ("screen_space_skylighting_valid", C.c_int32),
     ]
 
 

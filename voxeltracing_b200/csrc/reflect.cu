@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) reflection_trace_kernel(GridView g, const
                                 }
                             }
                         }
+                        if (a.lpv_gi && !ReprojectionSuccessful) Ambient = rf_approximate_gi_lpv(a, px, py, HitPosition + Normal * 0.5f, BaseIndirectDiffuse);
                         f4 ids = F4((float)__ldg(a.block_data + reference_id), (float)__ldg(a.block_data + 128 + reference_id),
                                     (float)__ldg(a.block_data + 256 + reference_id), (float)__ldg(a.block_data + 384 + reference_id));
                         if (reference_id == a.grass[0]) {
@@ -229,6 +230,21 @@ int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
     a.blue = c->d_blue_noise;
     a.color = (uint16_t*)c->att[VXRT_ATT_REFL_COLOR].ptr; a.hitdist = (uint16_t*)c->att[VXRT_ATT_REFL_HITDIST].ptr;
     a.emissive = (uint8_t*)c->att[VXRT_ATT_REFL_EMISSIVE].ptr;
+    // ApproximateGILPV: the propagation volume and the average block colours must be there (vxrt_cuda_lpv_repropagate,
+    // vxrt_cuda_lpv_average_colors / _set_average_colors)
+    a.lpv_gi = p.lpv_gi != 0; a.decoupled_gi = p.use_decoupled_gi != 0; a.ss_sky_valid = p.screen_space_skylighting_valid != 0;
+    a.sun_stronger = p.stronger_light_direction[0] == p.sun_direction[0] && p.stronger_light_direction[1] == p.sun_direction[1] &&
+                     p.stronger_light_direction[2] == p.sun_direction[2];   // SunStronger (:809)
+    a.lpv.level = nullptr; a.lpv.type = nullptr; a.lpv.avg = nullptr; a.lpv.nx = c->nx; a.lpv.ny = c->ny; a.lpv.nz = c->nz;
+    a.lpv.dx = a.lpv.dy = a.lpv.dz = 0.0f;
+    a.sky_ambient_g[0] = a.sky_ambient_g[1] = a.sky_ambient_g[2] = 0.0f;
+    if (a.lpv_gi) {
+        if (!c->lpv_valid || !c->d_lpv) return vxrt_fail(VXRT_E_STATE, "reflection_trace: lpv_gi needs the light propagation volume (vxrt_cuda_lpv_repropagate)");
+        if (!c->d_lpv_avg) return vxrt_fail(VXRT_E_STATE, "reflection_trace: lpv_gi needs the average block colours (vxrt_cuda_lpv_average_colors)");
+        a.lpv.level = c->d_lpv; a.lpv.type = c->d_lpv + c->nvox; a.lpv.avg = reinterpret_cast<const float4*>(c->d_lpv_avg);
+        const float up[3] = {0.0f, 1.0f, 0.0f};
+        vxrt_host_sky_sample(c, up, a.sky_ambient_g);
+    }
     if (a.row1 <= a.row0) return VXRT_OK;
     if (c->wavefront) return vxrt_launch_reflection_trace_wavefront(c, &a);
     dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);

@@ -1,6 +1,7 @@
 // reflect_common.cuh — argument block and shading terms of the reflection pass (ReflectionTraceFrag.glsl),
 // shared by the one-thread-per-pixel kernel (reflect.cu) and the wavefront pipeline (reflect_wavefront.cu).
 #pragma once
+#include "lpv_sample.cuh"
 #include "shading.cuh"
 
 namespace {
@@ -23,9 +24,49 @@ struct ReflArgs {
     const int32_t* block_data;
     const int32_t* blue;
     uint16_t* color; uint16_t* hitdist; uint8_t* emissive;
+    // ApproximateGILPV (:673-700)
+    int lpv_gi, decoupled_gi, ss_sky_valid, sun_stronger;
+    float sky_ambient_g[3];   // SkyAmbientG = texture(u_Skymap, vec3(0, 1, 0)).xyz (:719), evaluated once per pass on the host
+    LpvSampleArgs lpv;
 };
 
 struct RfState { int px, py, CurrentBLSample; };
+
+// bayer2 .. bayer32 (:21-29): fract(dot(floor(a), vec2(0.5, floor(a).y * 0.75))), each level adding a quarter of the level below at half
+// the coordinate
+VXD float rf_bayer2(float ax, float ay) {
+    ax = floorf(ax); ay = floorf(ay);
+    const float d = ax * 0.5f + ay * (ay * 0.75f);
+    return d - floorf(d);
+}
+VXD float rf_bayer4(float ax, float ay) { return rf_bayer2(0.5f * ax, 0.5f * ay) * 0.25f + rf_bayer2(ax, ay); }
+VXD float rf_bayer8(float ax, float ay) { return rf_bayer4(0.5f * ax, 0.5f * ay) * 0.25f + rf_bayer2(ax, ay); }
+VXD float rf_bayer16(float ax, float ay) { return rf_bayer8(0.5f * ax, 0.5f * ay) * 0.25f + rf_bayer2(ax, ay); }
+VXD float rf_bayer32(float ax, float ay) { return rf_bayer16(0.5f * ax, 0.5f * ay) * 0.25f + rf_bayer2(ax, ay); }
+
+// ApproximateGILPV(P, B) (:673-700) for the pixel (px, py); LPVDither as main() sets it (:721-723)
+VXD f3 rf_approximate_gi_lpv(const ReflArgs& a, int px, int py, f3 P, f3 B) {
+    const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;   // gl_FragCoord.xy
+    const float tf = a.temporal ? 1.0f : 0.0f;
+    const float b32 = rf_bayer32(fx + ((float)a.frame * 0.75f) * tf, fy + ((float)a.frame * 0.5f) * tf);
+    const f3 dither = F3(b32 / 384.0f, b32 / 128.0f, b32 / 384.0f);
+    const f3 LPV = lpv_sample_data(a.lpv, P, dither);
+    if (a.decoupled_gi) {
+        f3 Sky = F3(a.sky_ambient_g[0], a.sky_ambient_g[1], a.sky_ambient_g[2]);
+        const float L = dot(Sky, F3(0.2125f, 0.7154f, 0.0721f));
+        Sky = gmix(F3(L), Sky, a.sun_stronger ? 0.3f : 0.6f);
+        float ao[2];
+        att_unorm8_bilinear<2>(a.gi_aosky, a.iw, a.ih, pixel_uv(px, py, a.width, a.height), ao);
+        f3 Skylighting = Sky * (ao[1] * (a.sun_stronger ? 3.5f : 4.0f));
+        Skylighting = Skylighting + F3(rf_bayer16(fx, fy) / 512.0f);
+        const f3 hi = B + F3(0.075f);
+        Skylighting = F3(gclamp(Skylighting.x * 13.0f, 0.0f, hi.x), gclamp(Skylighting.y * 13.0f, 0.0f, hi.y), gclamp(Skylighting.z * 13.0f, 0.0f, hi.z));
+        if (!a.ss_sky_valid) Skylighting = B;
+        return Skylighting + LPV;
+    }
+    const f3 BaseAmbient = B * 0.9f;
+    return LPV + BaseAmbient;
+}
 
 // SampleBlueNoise2D (:606-614)
 VXD f2 rf_blue_noise_2d(const ReflArgs& a, RfState& st, int Index) {

@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
     w.rayD[i] = make_float4(R.x, R.y, R.z, 1.0f);
 }
 
+// LPVGI: ApproximateGILPV for hits whose reprojection failed (a.lpv_gi); a template flag so the default path compiles without it
+template <bool LPVGI>
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
     int px, py;
     tile_pixel(px, py, a.row0);
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
                     }
                 }
             }
+            if (LPVGI && !ReprojectionSuccessful) Ambient = rf_approximate_gi_lpv(a, px, py, HitPosition + Normal * 0.5f, F3(b4.x, b4.y, b4.z));
             f4 ids = F4((float)__ldg(a.block_data + reference_id), (float)__ldg(a.block_data + 128 + reference_id),
                         (float)__ldg(a.block_data + 256 + reference_id), (float)__ldg(a.block_data + 384 + reference_id));
             if (reference_id == a.grass[0]) {
@@ -386,7 +389,8 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
             c->launches -= 1;
         } else if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
-        rf_wf_shade_a_kernel<<<pgrid, 256, 0, s>>>(a, w);
+        if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w);
+        else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w);
         if (c->trace_caps) {
             const ReflShadowRays pol = {w, strong};
             const int rc = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);

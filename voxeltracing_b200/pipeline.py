@@ -27,6 +27,8 @@ class FrameConfig:
     gi_checkerboard: bool = False
     refl_spp: int = 1                    # BASELINE config 4 (engine default 2, Pipeline.cpp:108)
     refl_reproject: bool = False
+    refl_lpv_gi: bool = False            # ApproximateGILPV (engine default on, Pipeline.cpp:116); needs Context.lpv_repropagate + lpv_average_colors
+    refl_decoupled_gi: bool = False      # Pipeline.cpp:117
     passes: tuple = ("primary", "shadow")
 
 
@@ -137,6 +139,7 @@ class FrameRenderer:
         p.current_frame, p.current_frame_mod128 = frame, frame % 128
         p.use_blue_noise, p.rough_reflections, p.roughness_bias, p.temporal = 1, 1, 0, 0
         p.reproject_to_screen_space, p.derive_from_diffuse_sh = int(cfg.refl_reproject), 0
+        p.lpv_gi, p.use_decoupled_gi, p.screen_space_skylighting_valid = int(cfg.refl_lpv_gi), int(cfg.refl_decoupled_gi), 0
         _fill(p.sun_direction, self.sun); _fill(p.moon_direction, self.moon); _fill(p.stronger_light_direction, self.light)
         _fill(p.viewer_position, cam.position)
         p.sun_strength_modifier, p.moon_strength_modifier = 0.85, 1.0
