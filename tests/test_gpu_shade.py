@@ -265,3 +265,28 @@ def test_capped_trace_passes_do_not_change_a_bit(rooms, inputs, caps):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
     assert got_st == want_st
     assert want_st["rays"] > 100000
+
+
+@pytest.mark.parametrize("world,pos,frame,spp,checker", [("rooms", [200, 58, 200], 4, 1, False), ("rooms", [200, 58, 200], 7, 3, True),
+                                                         ("plains", [192, 80, 192], 1, 4, False)])
+def test_fused_final_gi_kernel_is_bit_identical(request, inputs, world, pos, frame, spp, checker):
+    """The last sample's shade<2> fused with resolve (gi_wf_final_kernel) and the bounce-0 terms carried in contrib / thr give the bits
+    of the separate kernels and of the one-thread-per-pixel kernel, at 1 spp (accumulators of live paths never touched), with a
+    checkerboard (pixels whose last sample is not the frame's last) and at 4 spp."""
+    c, ow, sc = request.getfixturevalue(world)
+    cam = host_api.camera(pos, 75.0, -12.0, W / H)
+    c.initial_trace(cam, W, H)
+    ip = su.gi_params(cam, W, H, frame=frame, spp=spp, checkerboard=checker)
+    atts = (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY)
+    res = []
+    try:
+        for wavefront, fuse in ((1, 1), (1, 0), (0, 0)):
+            c.set_option("wavefront", wavefront); c.set_option("gi_fuse_final", fuse)
+            c.diffuse_trace(ip)
+            res.append([c.read_attachment(a).copy() for a in atts])
+    finally:
+        c.set_option("wavefront", 1); c.set_option("gi_fuse_final", 1)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert res[0][0].astype(np.float32).std() > 1e-3

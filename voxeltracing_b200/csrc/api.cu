@@ -209,6 +209,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
     if (!strcmp(name, "l2_persist")) { c->l2_persist = value != 0; return vxrt_apply_l2_policy(c); }
     if (!strcmp(name, "lpv_coop")) { c->lpv_coop = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
     if (!strcmp(name, "df_dbg")) { c->df_dbg = value; return VXRT_OK; }

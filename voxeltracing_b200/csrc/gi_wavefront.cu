@@ -226,10 +226,16 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
             const float4 A4 = w.A[i];
             const float ShadowAt = A4.w >= 0.0f ? A4.w : w.shadowRes[i];
             const f3 SUNBRDF = F3(A4.x, A4.y, A4.z) * (1.0f - ShadowAt) * VX_PI;
-            const f3 Em = ld3(w.Em + i);
-            contrib = contrib + thr * SUNBRDF;
-            contrib = contrib + Em * thr;
-            thr = thr * ld3(w.thrF + i);
+            if (BOUNCE == 1) {
+                // bounce 0 left contrib = EmmisivityColor and thr = Albedo*Attenuation/PDF (see below): with RayContribution = 0 and
+                // RayThroughput = 1 the shader's (0 + 1 * SUNBRDF) + Em * 1 is SUNBRDF + Em and 1 * F is F, bit for bit
+                contrib = SUNBRDF + contrib;
+            } else {
+                const f3 Em = ld3(w.Em + i);
+                contrib = contrib + thr * SUNBRDF;
+                contrib = contrib + Em * thr;
+                thr = thr * ld3(w.thrF + i);
+            }
         }
         if (BOUNCE < 2) {
             const f3 light = a.sun_stronger ? F3(a.sun[0], a.sun[1], a.sun[2]) : F3(a.moon[0], a.moon[1], a.moon[2]);
@@ -276,8 +282,15 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
                 const f3 Attenuation = F3(1.0f) * diffuse_hammon(HitNormal, -rayD, NewDirection, PBR.x);
                 const f3 F = Albedo * Attenuation / PDF;
                 w.A[i] = make_float4(Apend.x, Apend.y, Apend.z, ShadowAt);
-                w.Em[i] = make_float4(EmmisivityColor.x, EmmisivityColor.y, EmmisivityColor.z, 0.0f);
-                w.thrF[i] = make_float4(F.x, F.y, F.z, 0.0f);
+                if (BOUNCE == 0) {
+                    // the pending terms of bounce 0 travel in contrib / thr themselves (16 + 16 bytes per path less to write and to read
+                    // back): at this point RayContribution is exactly 0 and RayThroughput exactly 1
+                    contrib = EmmisivityColor;
+                    thr = F;
+                } else {
+                    w.Em[i] = make_float4(EmmisivityColor.x, EmmisivityColor.y, EmmisivityColor.z, 0.0f);
+                    w.thrF[i] = make_float4(F.x, F.y, F.z, 0.0f);
+                }
                 if (BOUNCE == 0) {
                     const f3 no = IntersectionPosition + HitNormal * 0.06f;
                     w.rayO[i] = make_float4(no.x, no.y, no.z, 0.0f);
@@ -341,6 +354,58 @@ __global__ void __launch_bounds__(256) gi_wf_resolve_kernel(const __grid_constan
     const size_t pi = (size_t)py * a.width + px;
     const float n = (float)w.spp[i];
     const float4 s = w.accSH[i], r = w.accRadAO[i], c = w.accCoCgSky[i];
+    const float AccumulatedAO = r.w / n;
+    const f4 TotalSHy = F4(s.x / n, s.y / n, s.z / n, s.w / n);
+    const f2 CoCg = F2(c.x / n, c.y / n);
+    const f3 radiance = F3(r.x, r.y, r.z) / n;
+    const float Skyhits = c.z / n;
+    float oUtil = gmax(dot(radiance, F3(0.299f, 0.587f, 0.114f)), 0.01f);
+    oUtil = gclamp(oUtil, 0.001f, 64.0f);
+    reinterpret_cast<ushort4*>(a.sh)[pi] = make_ushort4(float_to_half_bits(gclamp(TotalSHy.x, -100.0f, 100.0f)), float_to_half_bits(gclamp(TotalSHy.y, -100.0f, 100.0f)),
+                                                        float_to_half_bits(gclamp(TotalSHy.z, -100.0f, 100.0f)), float_to_half_bits(gclamp(TotalSHy.w, -100.0f, 100.0f)));
+    reinterpret_cast<ushort2*>(a.cocg)[pi] = make_ushort2(float_to_half_bits(gclamp(CoCg.x, -100.0f, 100.0f)), float_to_half_bits(gclamp(CoCg.y, -100.0f, 100.0f)));
+    a.utility[pi] = float_to_half_bits(oUtil);
+    reinterpret_cast<uchar2*>(a.aosky)[pi] = make_uchar2(float_to_unorm8(gclamp(AccumulatedAO, 0.0f, 1.0f)), float_to_unorm8(gclamp(Skyhits, 0.0f, 1.0f)));
+}
+
+// ---- final: shade<2> of the LAST sample fused with resolve ------------------------------------------------------------------------
+// The last sample's pending bounce-1 terms, its epilogue (finish_sample) and the averages / clamps / attachment formats of resolve in
+// one pass: a path that is still alive never writes its sample into the accumulators nor reads them back (at 1 spp the accumulators
+// of such a pixel are not touched at all), and one launch less.  Same arithmetic in the same order, bit-identical.
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_final_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
+    int px, py;
+    tile_pixel(px, py, a.row0);
+    if (px >= a.width || py >= a.row1) return;
+    const int i = (py - a.row0) * a.width + px;
+    if (w.bl[i] < 0) return;  // sky pixel, written by gen
+    float4 s, r, c;
+    const float4 c4 = w.contrib[i];
+    if (c4.w != 0.0f) {
+        const float4 t4 = w.thr[i];
+        f3 contrib = F3(c4.x, c4.y, c4.z);
+        const f3 thr = F3(t4.x, t4.y, t4.z);
+        const float4 A4 = w.A[i];
+        const float ShadowAt = A4.w >= 0.0f ? A4.w : w.shadowRes[i];
+        const f3 SUNBRDF = F3(A4.x, A4.y, A4.z) * (1.0f - ShadowAt) * VX_PI;
+        const f3 Em = ld3(w.Em + i);
+        contrib = contrib + thr * SUNBRDF;
+        contrib = contrib + Em * thr;
+        // finish_sample
+        const float4 oa = w.odirAo[i];
+        const f3 xc = gclamp(contrib, 0.0f, 8.0f);
+        float SH[6];
+        irradiance_to_sh(xc, F3(oa.x, oa.y, oa.z), SH);
+        const bool first = sample == 0;
+        const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float4 s0 = first ? zero : w.accSH[i], r0 = first ? zero : w.accRadAO[i], c0 = first ? zero : w.accCoCgSky[i];
+        s = make_float4(s0.x + SH[0], s0.y + SH[1], s0.z + SH[2], s0.w + SH[3]);
+        r = make_float4(r0.x + xc.x, r0.y + xc.y, r0.z + xc.z, r0.w + oa.w);
+        c = make_float4(c0.x + SH[4], c0.y + SH[5], c0.z + t4.w, 0.0f);
+    } else {
+        s = w.accSH[i]; r = w.accRadAO[i]; c = w.accCoCgSky[i];
+    }
+    const size_t pi = (size_t)py * a.width + px;
+    const float n = (float)w.spp[i];
     const float AccumulatedAO = r.w / n;
     const f4 TotalSHy = F4(s.x / n, s.y / n, s.z / n, s.w / n);
     const f2 CoCg = F2(c.x / n, c.y / n);
@@ -432,13 +497,16 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         gi_wf_shade_kernel<1><<<pgrid, 256, 0, s>>>(a, w, sample);
         TRACE_SHADOW();
-        gi_wf_shade_kernel<2><<<pgrid, 256, 0, s>>>(a, w, sample);
+        if (sample + 1 < max_spp || !c->gi_fuse_final) gi_wf_shade_kernel<2><<<pgrid, 256, 0, s>>>(a, w, sample);
+        else gi_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);   // the last sample's shade<2> + resolve in one pass
         c->launches += 8;
     }
 #undef TRACE_PATHS
 #undef TRACE_SHADOW
-    gi_wf_resolve_kernel<<<pgrid, 256, 0, s>>>(a, w);
+    if (!c->gi_fuse_final) {
+        gi_wf_resolve_kernel<<<pgrid, 256, 0, s>>>(a, w);
+        c->launches += 1;
+    }
     VX_CUDA(cudaGetLastError());
-    c->launches += 1;
     return VXRT_OK;
 }
