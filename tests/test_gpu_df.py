@@ -103,7 +103,7 @@ def test_worlds_other_than_plains(ctx):
         assert np.array_equal(ctx.download_distance_field(), ob.distance_field(w)), kind
 
 
-@pytest.mark.parametrize("xyver,zver", [(1, 1), (2, 1), (1, 2), (2, 2), (2, 4), (2, 5), (2, 9)])
+@pytest.mark.parametrize("xyver,zver", [(1, 1), (2, 1), (1, 2), (2, 2), (2, 4), (2, 5), (2, 9), (3, 2), (3, 1)])
 def test_every_kernel_version_is_bit_exact(xyver, zver, plains0):
     """The kernel generations stay selectable (set_option df_xyver / df_zver) as each other's cross-check: every combination equals the
     oracle on a terrain world, an enclosed world, sparse voxels with block ids >= 128 (the mask multiply must ignore the high bit

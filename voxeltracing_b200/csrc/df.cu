@@ -277,6 +277,74 @@ __global__ void __launch_bounds__(XY_THREADS, VX_XY_OCC) df_xy_slice_kernel(cons
     }
 }
 
+// Y sweeps of one word column from both ends at once.  The two chains of the reference (down over all rows, then up over all rows) are
+// one dependent VIADDMNMX after the other - a warp that does nothing else issues 7.5 instructions per ~20 clocks.  The L1 transform
+// does not care in which order the sources reach a voxel, so: phase A sweeps rows 0 -> 63 downwards and rows 127 -> 64 upwards (four
+// independent lane chains in flight per thread), phase B continues the downward chain through rows 64 -> 127, which now hold their
+// distance to everything below them, and the upward chain through rows 63 -> 0, which hold their distance to everything above:
+// every row ends as min over all rows of value + distance, the exact transform, with half the chain length per phase.
+// `chunk_done(c)` is called when the 32-row chunk c holds final values (2 and 1 in the middle of phase B, 3 and 0 at its end).
+template <class F>
+__device__ __forceinline__ void y_sweep_bidir(unsigned* cptr, bool active, F&& chunk_done) {
+    unsigned ed = 0x00ff00ffu, od = 0x00ff00ffu, eu = 0x00ff00ffu, ou = 0x00ff00ffu;   // min(v, 256) == v for the first row of a chain
+    if (active) {
+#pragma unroll 8
+        for (int j = 0; j < 128 / 2; ++j) {
+            const unsigned wd = cptr[j * 96], wu = cptr[(128 - 1 - j) * 96];
+            ed = __viaddmin_u16x2(ed, 0x00010001u, even_lanes_lop(wd));
+            od = __viaddmin_u16x2(od, 0x00010001u, odd_lanes(wd));
+            eu = __viaddmin_u16x2(eu, 0x00010001u, even_lanes_lop(wu));
+            ou = __viaddmin_u16x2(ou, 0x00010001u, odd_lanes(wu));
+            cptr[j * 96] = pack_lanes(ed, od);
+            cptr[(128 - 1 - j) * 96] = pack_lanes(eu, ou);
+        }
+    }
+    for (int half = 0; half < 2; ++half) {
+        if (active) {
+#pragma unroll 8
+            for (int j = half * 32; j < half * 32 + 32; ++j) {
+                const unsigned wd = cptr[(128 / 2 + j) * 96], wu = cptr[(128 / 2 - 1 - j) * 96];
+                ed = __viaddmin_u16x2(ed, 0x00010001u, even_lanes_lop(wd));
+                od = __viaddmin_u16x2(od, 0x00010001u, odd_lanes(wd));
+                eu = __viaddmin_u16x2(eu, 0x00010001u, even_lanes_lop(wu));
+                ou = __viaddmin_u16x2(ou, 0x00010001u, odd_lanes(wu));
+                cptr[(128 / 2 + j) * 96] = pack_lanes(ed, od);
+                cptr[(128 / 2 - 1 - j) * 96] = pack_lanes(eu, ou);
+            }
+        }
+        chunk_done(2 + half);
+        chunk_done(1 - half);
+    }
+}
+
+// the two chains one after the other: down over all rows, then up, a 32-row chunk at a time (chunk_done(3), (2), (1), (0))
+template <class F>
+__device__ __forceinline__ void y_sweep_seq(unsigned* cptr, bool active, F&& chunk_done) {
+    unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first row
+    if (active) {
+#pragma unroll 8
+        for (int y = 0; y < 128; ++y) {
+            const unsigned w = cptr[y * 96];
+            e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
+            o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
+            cptr[y * 96] = pack_lanes(e, o);
+        }
+    }
+    for (int chunk = 3; chunk >= 0; --chunk) {
+        if (active) {
+            const int y_hi = chunk == 3 ? 128 - 2 : chunk * 32 + 31;
+#pragma unroll 8
+            for (int y = y_hi; y >= chunk * 32; --y) {
+                const unsigned w = cptr[y * 96];
+                e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
+                o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
+                cptr[y * 96] = pack_lanes(e, o);
+            }
+        }
+        chunk_done(chunk);
+    }
+}
+
 // ---- kernel 1, second version (the engine's 384 x 128 slice) -------------------------------------------------------------
 // Same arithmetic as df_xy_slice_kernel, reorganised around what the pipes of an SM can do per clock (tools/debug/pipe_bench.cu:
 // VIADDMNMX / VIMNMX3 / PRMT / SHF 64 lanes / clk / SM on the ALU pipe, IMAD / VIADD 64 on the FMA pipe beside it, LDS.128 one warp
@@ -415,36 +483,216 @@ __global__ void __launch_bounds__(XY2_THREADS, 3) df_xy2_kernel(const uint8_t* _
     if (warp >= 4 || yw == 3) return;
     const int col = yw * 32 + (tid & 31);
     unsigned* cptr = slice + col;
-    unsigned e = 0x00ff00ffu, o = 0x00ff00ffu;  // min(v, 256) == v for the first row
-    if (!(dbg & 1))
-#pragma unroll 8
-    for (int y = 0; y < XY2_ROWS; ++y) {
-        const unsigned w = cptr[y * XY2_WPR];
-        e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
-        o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
-        cptr[y * XY2_WPR] = pack_lanes(e, o);
-    }
     uint8_t* dst = df + slice_off;
-    for (int chunk = 3; chunk >= 0; --chunk) {
-        const int y_hi = chunk == 3 ? XY2_ROWS - 2 : chunk * 32 + 31;
-        if (!(dbg & 2))
-#pragma unroll 8
-        for (int y = y_hi; y >= chunk * 32; --y) {
-            const unsigned w = cptr[y * XY2_WPR];
-            e = __viaddmin_u16x2(e, 0x00010001u, even_lanes_lop(w));
-            o = __viaddmin_u16x2(o, 0x00010001u, odd_lanes(w));
-            cptr[y * XY2_WPR] = pack_lanes(e, o);
-        }
+    const bool issuer = yw == 0 && (tid & 31) == 0;
+    auto store_chunk = [&](int chunk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the chunk's bytes become visible to the bulk-copy engine
         asm volatile("bar.sync 1, 96;" ::: "memory");
-        if (yw == 0 && (tid & 31) == 0 && !(dbg & 8)) {
+        if (issuer && !(dbg & 8)) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + chunk * 32 * XY2_WPR * 4),
                          "r"(smem_u32(slice + chunk * 32 * XY2_WPR)), "n"(32 * XY2_WPR * 4)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-    }
+    };
+    // measured: the two chains one after the other 14.8 us, both ends at once (y_sweep_bidir, dbg & 256) 15.4 us - the column chains are
+    // not bound by the latency of their dependent VIADDMNMX but by the LDS / STS round trips of a warp that walks shared memory alone
+    if (dbg & 256) y_sweep_bidir(cptr, !(dbg & 1), store_chunk);
+    else y_sweep_seq(cptr, !(dbg & 1), store_chunk);
     if (yw == 0 && (tid & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+}
+
+// ---- kernel 1, third version: one persistent, warp-specialised CTA per SM ----------------------------------------------------------
+// df_xy2_kernel is one wave of 384 CTAs: every slice is loaded in one burst at the start (5.9 us until the last slice is complete),
+// then computed, then stored, and the measured 14.9 us are close to the SUM of the memory skeleton (8.5 us) and the sweeps (7.4 us).
+// Here a CTA walks its slices (blockIdx, + gridDim, ...) through a 3-slot ring in shared memory and the stages of consecutive slices
+// overlap:
+//   bulk loads   cp.async.bulk.shared::cta.global, 48 KB per slice, complete_tx on full[slot].  The first three are issued one after
+//                the other (each after the one before it has landed), so every SM has its first slice after a third of the burst.
+//   front group  24 warps: masks (LDS.128 from the raw slot) -> quad-carry scan -> X distances written over the raw bytes of the slot,
+//                then arrive on xdone[slot] and on to the next slice
+//   Y group      4 warps (one per scheduler, 24 columns each): waits for xdone[slot], sweeps the columns down and up, hands every
+//                finished 32-row chunk to a bulk store, and when the stores have read the slot issues the load of slice k + 3 into it
+// so the loads of slice k + 1 / k + 2, the masks / X of slice k + 1, the Y sweeps of slice k and the stores of slice k - 1 are in
+// flight together.  Same arithmetic as df_xy2_kernel, bit-exact.
+// MEASURED (profiles/r2_q_df_xy3_phases.txt): 20.0 us against the 14.9 us of df_xy2_kernel, so it is NOT the default (set_option
+// "df_xyver" 3).  Without the Y sweeps it takes 11.5 us, without masks / X 16.3 us, with neither 9.5 us: the Y stage is the bottleneck
+// (2.85 us per slice: one warp per scheduler walking a 128-row chain twice, competing for issue slots with six front warps), and at
+// 2.6 slices per SM the ring never reaches a steady state - the pipeline's fill and drain cost more than the overlap gains.
+constexpr int XY3_FRONT_WARPS = 24, XY3_Y_WARPS = 4;
+constexpr int XY3_FRONT = XY3_FRONT_WARPS * 32, XY3_THREADS = XY3_FRONT + XY3_Y_WARPS * 32;
+constexpr int XY3_SLOTS = 3;
+constexpr int XY3_SLICE = XY2_ROWS * XY2_QPR * 16;                        // 49152 bytes
+constexpr int XY3_QCAR = XY2_ROWS * XY2_QSTRIDE * 4;                      // 13824 bytes
+constexpr int XY3_SMEM = XY3_SLOTS * XY3_SLICE + 2 * XY3_QCAR + 16 * 8 + 16 * 4 + 2 * XY3_SLOTS * 8;
+
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(XY3_THREADS, 1) df_xy3_kernel(const uint8_t* __restrict__ blocks, uint8_t* __restrict__ df, int z_begin, int n_slices,
+                                                                 unsigned maxd, int dbg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* slots = smem_raw;
+    unsigned* qcar_base = reinterpret_cast<unsigned*>(smem_raw + XY3_SLOTS * XY3_SLICE);
+    uint2* lut_eo = reinterpret_cast<uint2*>(smem_raw + XY3_SLOTS * XY3_SLICE + 2 * XY3_QCAR);
+    unsigned* lut_zw = reinterpret_cast<unsigned*>(lut_eo + 16);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(lut_zw + 16);
+    unsigned long long* xdone = full + XY3_SLOTS;
+    const int tid = threadIdx.x;
+    const int n_my = (n_slices - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slices blockIdx, + gridDim, ...
+    if (n_my <= 0) return;
+
+    if (tid == 0) {
+        for (int b = 0; b < XY3_SLOTS; ++b) { mbar_init(full + b, 1); mbar_init(xdone + b, XY3_FRONT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 16) {
+        const unsigned n = tid;
+        unsigned d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned best = maxd;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n >> j & 1u) best = min(best, (unsigned)(i > j ? i - j : j - i));
+            d[i] = best;
+        }
+        const unsigned f = n ? (unsigned)(4 - (31 - __clz(n))) : NO_CARRY, b = n ? (unsigned)__ffs(n) : NO_CARRY;
+        lut_eo[n] = make_uint2(d[0] | (d[2] << 16), d[1] | (d[3] << 16));
+        lut_zw[n] = f | (b << 16);
+    }
+    __syncthreads();
+    const size_t slice0 = (size_t)(z_begin + (int)blockIdx.x) * XY3_SLICE, stride = (size_t)gridDim.x * XY3_SLICE;
+
+    if (tid < XY3_FRONT) {
+        // ================================ front group: masks, quad carries, X ================================
+        const int c0 = tid % XY2_QPR, rseg = tid / XY2_QPR;     // quad column, rows rseg * 4 .. + 3
+        for (int k = 0; k < n_my; ++k) {
+            const int b = k % XY3_SLOTS;
+            uint4* slice4 = reinterpret_cast<uint4*>(slots + b * XY3_SLICE);
+            unsigned* qcar = qcar_base + (k & 1) * (XY3_QCAR / 4);
+            mbar_wait(full + b, (unsigned)(k / XY3_SLOTS) & 1u);
+            if (dbg & 2) { mbar_arrive(xdone + b); continue; }   // measurement aid: no masks / scan / X
+            unsigned nb8[4];   // per byte: mask << 4
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = rseg * 4 + i;
+                const uint4 v = slice4[row * XY2_QPR + c0];
+                const unsigned nbh = __byte_perm(__byte_perm(solid_nibble_hi(v.x), solid_nibble_hi(v.y), 0x4473),
+                                                 __byte_perm(solid_nibble_hi(v.z), solid_nibble_hi(v.w), 0x4473), 0x5410);
+                const unsigned t = (nbh >> 4) | (nbh >> 8);
+                const unsigned m16 = __byte_perm(t, 0u, 0x4420);
+                nb8[i] = nbh;
+                qcar[row * XY2_QSTRIDE + c0] = m16 ? (unsigned)(__clz(m16) - 15) | ((unsigned)__ffs(m16) << 16) : NO_CARRY | (NO_CARRY << 16);
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(XY3_FRONT) : "memory");
+            if (tid < 2 * XY2_ROWS) {
+                const int back = tid >= XY2_ROWS, row = tid - back * XY2_ROWS;
+                unsigned short* r = reinterpret_cast<unsigned short*>(qcar) + ((row * XY2_QSTRIDE) << 1) + back;
+                unsigned c = NO_CARRY;
+                if (!back) {
+#pragma unroll 8
+                    for (int j = 0; j < XY2_QPR; ++j) { const unsigned f = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(f, c + 16u); }
+                } else {
+#pragma unroll 8
+                    for (int j = XY2_QPR - 1; j >= 0; --j) { const unsigned bb = r[j << 1]; r[j << 1] = (unsigned short)c; c = min(bb, c + 16u); }
+                }
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(XY3_FRONT) : "memory");
+            const unsigned k1 = 0x00010001u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = rseg * 4 + i;
+                const unsigned cin = qcar[row * XY2_QSTRIDE + c0];
+                uint2 eo[4];
+                unsigned zw[4], cf[4], cb[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const unsigned off = (nb8[i] >> (8 * kk + 1)) & 0x78u;
+                    eo[kk] = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(lut_eo) + off);
+                    zw[kk] = *reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(lut_zw) + (off >> 1));
+                }
+                unsigned c = cin & 0xffffu;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { cf[kk] = c; c = __viaddmin_u32(c, 4u, zw[kk] & 0xffffu); }
+                c = cin >> 16;
+#pragma unroll
+                for (int kk = 3; kk >= 0; --kk) { cb[kk] = c; c = __viaddmin_u32(c, 4u, zw[kk] >> 16); }
+                unsigned wv[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const unsigned e = __vimin3_u16x2(eo[kk].x, cf[kk] * k1 + 0x00020000u, cb[kk] * k1 + 0x00010003u);
+                    const unsigned o = __vimin3_u16x2(eo[kk].y, cf[kk] * k1 + 0x00030001u, cb[kk] * k1 + 0x00000002u);
+                    wv[kk] = pack_lanes(e, o);
+                }
+                slice4[row * XY2_QPR + c0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            }
+            mbar_arrive(xdone + b);   // release: the Y group's wait acquires the X distances of this slot
+        }
+    } else {
+        // ================================ Y group + loads / stores ================================
+        const int yw = (tid - XY3_FRONT) >> 5, lane = tid & 31;
+        const bool elected = yw == 0 && lane == 0;
+        const bool active = lane < 24;
+        const int col = yw * 24 + (active ? lane : 0);
+        if (elected) {
+            // the first loads one after the other: every SM's first slice is complete after a third of the burst
+            for (int k = 0; k < n_my && k < XY3_SLOTS; ++k) {
+                if (k > 0 && !(dbg & 4)) mbar_wait(full + (k - 1), 0u);
+                mbar_expect_tx(full + k, XY3_SLICE);
+                bulk_load(slots + k * XY3_SLICE, blocks + slice0 + (size_t)k * stride, XY3_SLICE, full + k);
+            }
+        }
+        for (int k = 0; k < n_my; ++k) {
+            const int b = k % XY3_SLOTS;
+            unsigned* slice = reinterpret_cast<unsigned*>(slots + b * XY3_SLICE);
+            mbar_wait(xdone + b, (unsigned)(k / XY3_SLOTS) & 1u);
+            unsigned* cptr = slice + col;
+            uint8_t* dst = df + slice0 + (size_t)k * stride;
+            y_sweep_seq(cptr, active && !(dbg & 1), [&](int chunk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(XY3_Y_WARPS * 32) : "memory");
+                if (elected) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + chunk * 32 * XY2_WPR * 4),
+                                 "r"(smem_u32(slice + chunk * 32 * XY2_WPR)), "n"(32 * XY2_WPR * 4)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            });
+            if (elected) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores have read the slot
+                if (k + XY3_SLOTS < n_my) {
+                    mbar_expect_tx(full + b, XY3_SLICE);
+                    bulk_load(slots + b * XY3_SLICE, blocks + slice0 + (size_t)(k + XY3_SLOTS) * stride, XY3_SLICE, full + b);
+                }
+            }
+        }
+    }
 }
 
 // ---- kernel 2: Z sweeps (ManhattanDistanceZ.comp:31-46) ----------------------------------------
@@ -865,6 +1113,7 @@ static int set_smem_attrs() {
         VX_CUDA(cudaFuncSetAttribute(df_xy_slice_kernel<false, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VX_CUDA(cudaFuncSetAttribute(df_xy2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XY2_SMEM));
+        VX_CUDA(cudaFuncSetAttribute(df_xy3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XY3_SMEM));
         attr_set = true;
     }
     return VXRT_OK;
@@ -888,7 +1137,9 @@ static int launch_df_range(vxrt_ctx* c, int z0, int z1) {
     int rc = set_smem_attrs();
     if (rc) return rc;
     if (c->df_stage != 2) {
-        if (c->df_xyver == 2 && nx == 384 && ny == 128)
+        if (c->df_xyver == 3 && nx == 384 && ny == 128)
+            df_xy3_kernel<<<(z1 - z0) < c->sm_count ? (z1 - z0) : c->sm_count, XY3_THREADS, XY3_SMEM, c->stream>>>(c->d_blocks, c->d_df, z0, z1 - z0, maxd, c->df_dbg);
+        else if (c->df_xyver == 2 && nx == 384 && ny == 128)
             df_xy2_kernel<<<z1 - z0, XY2_THREADS, XY2_SMEM, c->stream>>>(c->d_blocks, c->d_df, z0, maxd, c->df_dbg);
         else if (nx == 384 && ny == 128 && sy == 4 && XY_THREADS * XY_BATCH == 3072)   // the engine's slice (WORLD_SIZE_X x WORLD_SIZE_Y, Macros.h)
             df_xy_slice_kernel<true, 384, 128, 4><<<z1 - z0, XY_THREADS, smem_xy, c->stream>>>(c->d_blocks, c->d_df, nx, ny, z0, maxd, sx, sy);
