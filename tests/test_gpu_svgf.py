@@ -271,3 +271,37 @@ def test_cuda_chain_against_golden_fixture(seq):
             c.write_set(cur_id, gold(f"spatial{i}"))
     finally:
         c.close()
+
+
+def test_filter_snap_tolerance_mode_stays_within_one_percent():
+    """set_option("filter_snap", 256): bilinear weights below 1/256 snap to 0 and a tap with both weights 0 is one texel load
+    (filter_sampler.cuh).  Tolerance of the mode, stated here: every value of the SVGF chain's output within 1e-2 relative (+1e-2
+    absolute) of the bit-faithful mode on >= 99.9 % of the pixels; snap 0 restores the bit-faithful outputs exactly."""
+    import scene_util as su
+    W2, H2 = 320, 180
+    inputs = su.SceneInputs(64, sky="constant")
+    c = engine.Context(0)
+    try:
+        c.upload_world(host_api.gen_world("rooms", 2)); c.generate_distance_field(); inputs.apply_to_context(c)
+        fr = pipeline.FrameRenderer(c, pipeline.FrameConfig(width=W2, height=H2, passes=("primary", "gi")), inputs.grass, inputs.cactus)
+
+        def run(snap):
+            c.set_option("filter_snap", snap)
+            chain = pipeline.SvgfChain(c, W2, H2, pre_spatial=True)
+            for k in range(4):
+                cam = pipeline.rooms_camera(k // 2, W2 / H2)
+                fr.render(cam, k)
+                chain.run(cam, k)
+            return [c.read_attachment(a).astype(np.float32) for a in (abi.ATT_SVGF_DENOISE_A, abi.ATT_SVGF_DENOISE_A + 1, abi.ATT_SVGF_DENOISE_B)]
+
+        exact, snapped, again = run(0), run(256), run(0)
+        for a, b in zip(exact, again):
+            assert np.array_equal(a, b, equal_nan=True)
+        for a, b in zip(exact, snapped):
+            ok = np.isfinite(a) & np.isfinite(b)
+            close = np.abs(a - b)[ok] <= 1e-2 * np.abs(a)[ok] + 1e-2
+            assert close.mean() >= 0.999, close.mean()
+        with pytest.raises(engine.VxrtError):
+            c.set_option("filter_snap", 1 << 20)
+    finally:
+        c.close()

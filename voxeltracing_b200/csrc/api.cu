@@ -209,6 +209,11 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "probe")) { c->probe_on = value != 0; return VXRT_OK; }
     if (!strcmp(name, "l2_persist")) { c->l2_persist = value != 0; return vxrt_apply_l2_policy(c); }
     if (!strcmp(name, "lpv_coop")) { c->lpv_coop = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "filter_snap")) {   // value / 65536: 256 = 1 / 256 (the weight resolution of the hardware texture unit), 0 = bit-faithful
+        if (value < 0 || value > 16384) return vxrt_fail(VXRT_E_INVALID, "filter_snap %d outside [0, 16384] (units of 1 / 65536)", value);
+        c->filter_snap = (float)value / 65536.0f;
+        return VXRT_OK;
+    }
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }

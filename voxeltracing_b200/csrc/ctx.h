@@ -82,6 +82,7 @@ struct vxrt_ctx {
     void* d_wf = nullptr;
     size_t wf_cap = 0;
     bool wavefront = true;  // VXRT_WAVEFRONT=0 selects the one-thread-per-pixel GI / reflection kernels
+    float filter_snap = 0.0f;   // tolerance mode of the screen-space filters (filter_sampler.cuh); set_option "filter_snap" in units of 1 / 65536
     bool gi_fuse_final = true;  // last sample's shade<2> fused with resolve (set_option "gi_fuse_final"; 0 = the separate kernels)
 
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)

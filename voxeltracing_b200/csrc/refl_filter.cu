@@ -45,6 +45,10 @@ VXD int normal_at(const Img8& im, f2 uv, const float* lut) { return normal_index
 VXD f2 sample_pbr_xy(const Img8& im, f2 uv, const float* lut) {
     const Tap t = make_tap(im.w, im.h, uv);
     const uint32_t* p = reinterpret_cast<const uint32_t*>(im.p);
+    if (VX_TAP_SINGLE(t)) {
+        const uint32_t q = __ldg(p + t.o00);
+        return F2(lut[q & 255], lut[(q >> 8) & 255]);
+    }
     const uint32_t q00 = __ldg(p + t.o00), q10 = __ldg(p + t.o10), q01 = __ldg(p + t.o01), q11 = __ldg(p + t.o11);
     return F2(bl(t, lut[q00 & 255], lut[q10 & 255], lut[q01 & 255], lut[q11 & 255]),
               bl(t, lut[(q00 >> 8) & 255], lut[(q10 >> 8) & 255], lut[(q01 >> 8) & 255], lut[(q11 >> 8) & 255]));
@@ -349,7 +353,8 @@ __global__ void __launch_bounds__(256) reflection_denoise_kernel(const __grid_co
         float LuminanceWeight = 1.0f;
         const Axis mM = sameM ? mG : make_axis(Dir ? a.pbr.w : a.pbr.h, m);
         const Tap tp = Dir ? join_axes(mM, fM, a.pbr.w) : join_axes(fM, mM, a.pbr.w);
-        const float SampleRoughness = bl(tp, lut[__ldg(pp + tp.o00) & 255], lut[__ldg(pp + tp.o10) & 255], lut[__ldg(pp + tp.o01) & 255], lut[__ldg(pp + tp.o11) & 255]);
+        const float SampleRoughness = VX_TAP_SINGLE(tp) ? lut[__ldg(pp + tp.o00) & 255]
+                                                        : bl(tp, lut[__ldg(pp + tp.o00) & 255], lut[__ldg(pp + tp.o10) & 255], lut[__ldg(pp + tp.o01) & 255], lut[__ldg(pp + tp.o11) & 255]);
         const bool SampleTooRough = SampleRoughness >= 0.89f;
         if (!SampleTooRough) {
             const float LumaAt = luma(F3(sd[0], sd[1], sd[2]));
@@ -437,6 +442,7 @@ int zero_if_missing(vxrt_ctx* c, int id, int w, int h, int bpp) {
 }  // namespace
 
 int vxrt_launch_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_specular_temporal";
     if (!is_refl_set(p.history_set) || !is_refl_set(p.out_set) || p.history_set == p.out_set)
         return vxrt_fail(VXRT_E_INVALID, "%s: history_set / out_set must be the two of VXRT_ATT_REFL_TEMPORAL_A / _B", fn);
@@ -487,6 +493,7 @@ int vxrt_launch_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_para
 }
 
 int vxrt_launch_reflection_denoise(vxrt_ctx* c, const vxrt_reflection_denoise_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_reflection_denoise";
     if (p.out_attachment != VXRT_ATT_REFL_DENOISED_A && p.out_attachment != VXRT_ATT_REFL_DENOISED_B)
         return vxrt_fail(VXRT_E_INVALID, "%s: out_attachment must be VXRT_ATT_REFL_DENOISED_A / _B", fn);

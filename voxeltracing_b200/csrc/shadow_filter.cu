@@ -237,6 +237,7 @@ int image_in(vxrt_ctx* c, const char* fn, int id, int bpp, I* img) {
 }  // namespace
 
 int vxrt_launch_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_shadow_temporal";
     if (!is_shadow_set(p.history_set) || !is_shadow_set(p.out_set) || p.history_set == p.out_set)
         return vxrt_fail(VXRT_E_INVALID, "%s: history_set / out_set must be the two of VXRT_ATT_SHADOW_TEMPORAL_A / _B", fn);
@@ -284,6 +285,7 @@ int vxrt_launch_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params& 
 }
 
 int vxrt_launch_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_shadow_filter";
     if (!is_shadow_set(p.in_set)) return vxrt_fail(VXRT_E_INVALID, "%s: in_set must be VXRT_ATT_SHADOW_TEMPORAL_A / _B", fn);
     ShadowFilterArgs a;

@@ -632,6 +632,7 @@ int gbuf_in(vxrt_ctx* c, const char* fn, int t_id, int n_id, int b_id, GBufIn* g
 }  // namespace
 
 int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_svgf_temporal";
     if (p.out_set == p.history_set || p.out_set == p.in_set) return vxrt_fail(VXRT_E_INVALID, "%s: out_set aliases an input set", fn);
     if (!is_temporal_set(p.out_set) || !is_temporal_set(p.history_set)) return vxrt_fail(VXRT_E_INVALID, "%s: history_set / out_set must be VXRT_ATT_SVGF_TEMPORAL_A / _B", fn);
@@ -675,6 +676,7 @@ int vxrt_launch_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params& p) {
 }
 
 int vxrt_launch_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_svgf_prespatial";
     if (p.in_set != VXRT_ATT_GI_SH) return vxrt_fail(VXRT_E_INVALID, "%s: in_set must be VXRT_ATT_GI_SH (the raw trace)", fn);
     PreSpatialArgs a;
@@ -698,6 +700,7 @@ int vxrt_launch_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params& 
 }
 
 int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_svgf_variance";
     VarianceArgs a;
     int rc;
@@ -717,6 +720,7 @@ int vxrt_launch_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params& p) {
 }
 
 int vxrt_launch_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params& p) {
+    { const int rc_snap = vx_apply_filter_snap(c); if (rc_snap != VXRT_OK) return rc_snap; }
     static const char* fn = "vxrt_cuda_svgf_spatial";
     if (p.out_set == p.in_set || p.out_set == p.ao_set || p.out_set == p.temporal_set) return vxrt_fail(VXRT_E_INVALID, "%s: out_set aliases an input set", fn);
     if (p.out_set != VXRT_ATT_SVGF_DENOISE_A && p.out_set != VXRT_ATT_SVGF_DENOISE_B) return vxrt_fail(VXRT_E_INVALID, "%s: out_set must be VXRT_ATT_SVGF_DENOISE_A / _B", fn);
