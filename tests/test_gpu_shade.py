@@ -267,6 +267,41 @@ def test_capped_trace_passes_do_not_change_a_bit(rooms, inputs, caps):
     assert want_st["rays"] > 100000
 
 
+@pytest.mark.parametrize("thresholds", [(8,), (12, 8), (16, 12, 8), (1,), (31,), (31, 31, 31)])
+def test_adaptive_hand_over_does_not_change_a_bit(rooms, inputs, thresholds):
+    """Adaptive hand-over of the queue trace kernels (trace_queue.cuh, set_option "trace_spill"): a warp appends its stragglers to a
+    continuation queue once at most T lanes still have a ray and the next launch packs them.  Every threshold schedule - the measured
+    ones, a warp that only gives up its last ray, warps that hand over everything at once (T = 31: all rays travel through every
+    pass) - gives the attachments and the traversal statistics of the plain kernels."""
+    c, ow, sc = rooms
+    cam = host_api.camera([188.3, 61.0, 172.9], 115.0, -8.0, W / H)
+    c.initial_trace(cam, W, H)
+    c.shadow_trace(cam, W, H, host_api.sun_direction(50.0)[2], soft=False)
+    c.generate_gbuffer(su.gbuffer_params(cam, W, H, inputs))
+    ip = su.gi_params(cam, W, H, frame=6, spp=2, checkerboard=True)
+    rp = su.reflection_params(cam, W, H, inputs=inputs, frame=6, spp=2)
+    atts = (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY, abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE)
+
+    def run(packed):
+        c.set_option("trace_spill", packed)
+        c.stats_enable(True); c.stats_read(True)
+        c.diffuse_trace(ip)
+        c.reflection_trace(rp)
+        st = c.stats_read(True); c.stats_enable(False)
+        return [c.read_attachment(a).copy() for a in atts], st
+
+    default = c.get_option("trace_spill") if hasattr(c, "get_option") else None
+    try:
+        want, want_st = run(0)
+        got, got_st = run(sum(k << (8 * j) for j, k in enumerate(thresholds)))
+    finally:
+        c.set_option("trace_spill", default if default is not None else 0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert got_st == want_st
+    assert want_st["rays"] > 100000
+
+
 @pytest.mark.parametrize("world,pos,frame,spp,checker", [("rooms", [200, 58, 200], 4, 1, False), ("rooms", [200, 58, 200], 7, 3, True),
                                                          ("plains", [192, 80, 192], 1, 4, False)])
 def test_fused_final_gi_kernel_is_bit_identical(request, inputs, world, pos, frame, spp, checker):

@@ -64,6 +64,29 @@ def capped(iters, caps):
     return total
 
 
+def spill(iters, thresholds):
+    """warp-iterations when a warp hands its survivors to a continuation queue as soon as <= T lanes are still running
+    (thresholds[j] for pass j; the last pass runs to the end) and the next pass starts from the dense continuation queue"""
+    total, rem = 0, iters.copy()
+    moved = []
+    for j in range(len(thresholds) + 1):
+        if len(rem) == 0:
+            break
+        pad = (-len(rem)) % 32
+        m = np.concatenate([rem, np.zeros(pad, rem.dtype)]).reshape(-1, 32)
+        if j == len(thresholds):
+            total += int(m.max(axis=1).sum())
+            break
+        T = thresholds[j]
+        srt = np.sort(m, axis=1)[:, ::-1]          # descending: srt[:, T] = iteration count after which <= T lanes are running
+        stop = srt[:, T]                           # the warp runs `stop` iterations (lanes with more go on to the next pass)
+        total += int(stop.sum())
+        left = m - stop[:, None]
+        moved.append(int((left > 0).sum()))
+        rem = left[left > 0]
+    return total, moved
+
+
 def main():
     blocks = host_api.gen_world("rooms", 2)
     ow = ob.OracleWorld(blocks)
@@ -108,6 +131,9 @@ def main():
                  "max": int(it.max()), "baseline_warp_iters": base, "lane_eff": eff}
             for caps in ((8, 48), (12, 48), (16, 48), (8, 20, 48), (12, 24, 48), (6, 12, 24, 48), (4, 8, 16, 32, 48)):
                 r["cap" + "_".join(map(str, caps))] = capped(it, caps) / base
+            for th in ((4,), (8,), (12,), (16,), (8, 8), (12, 8), (16, 8), (16, 12, 8), (12, 12, 12)):
+                tot, moved = spill(it, th)
+                r["spill" + "_".join(map(str, th))] = (round(tot / base, 3), [round(x / len(it), 3) for x in moved])
             octant = (dd[:, 0] > 0).astype(int) | ((dd[:, 1] > 0).astype(int) << 1) | ((dd[:, 2] > 0).astype(int) << 2)
             cell = (o[:, 0].astype(int) >> 3) + ((o[:, 1].astype(int) >> 3) << 6) + ((o[:, 2].astype(int) >> 3) << 12)
             for kname, key in (("sort_octant", octant), ("sort_cell_octant", cell * 8 + octant), ("sort_octant_cell", octant * (1 << 20) + cell)):

@@ -1,5 +1,7 @@
 """Times the passes of a workload for several iteration-cap schedules of the queue trace kernels (set_option "trace_caps";
-caps as bytes, low byte first, 0 = the uncapped round-1 kernels).  usage: sweep_caps.py [workload] [caps,caps,...]"""
+caps as bytes, low byte first, 0 = the uncapped round-1 kernels) or, with VXRT_SWEEP_OPTION=trace_spill, for several hand-over thresholds
+of the adaptive variant.  usage: sweep_caps.py [workload] [caps,caps,...]"""
+import os
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[2]
@@ -23,7 +25,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
 for sc in sched:
     caps = [int(v) for v in sc.split("-")]
-    ctx.set_option("trace_caps", sum(k << (8 * j) for j, k in enumerate(caps)))
+    ctx.set_option(os.environ.get("VXRT_SWEEP_OPTION", "trace_caps"), sum(k << (8 * j) for j, k in enumerate(caps)))
     ev = [{p: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for p in wl["passes"]} for _ in range(N)]
     for s in range(2):
         fr.submit(prepared[s])

@@ -102,13 +102,15 @@ int vxrt_ensure_trace_cont(vxrt_ctx* c, size_t rays, TraceCont* out) {
         VX_CUDA(cudaStreamSynchronize(c->stream));
         if (c->d_trace_cont) VX_CUDA(cudaFree(c->d_trace_cont));
         c->d_trace_cont = nullptr; c->trace_cont_cap = 0;
-        VX_CUDA(cudaMalloc(&c->d_trace_cont, 2 * rays * sizeof(float4) + 256));
+        VX_CUDA(cudaMalloc(&c->d_trace_cont, 2 * rays * (sizeof(float4) + sizeof(unsigned)) + 256));
         c->trace_cont_cap = rays;
     }
     uint8_t* p = (uint8_t*)c->d_trace_cont;
     out->count = reinterpret_cast<int*>(p);
     out->q[0] = reinterpret_cast<float4*>(p + 256);
     out->q[1] = out->q[0] + c->trace_cont_cap;
+    out->meta[0] = reinterpret_cast<unsigned*>(out->q[1] + c->trace_cont_cap);
+    out->meta[1] = out->meta[0] + c->trace_cont_cap;
     return VXRT_OK;
 }
 
@@ -216,6 +218,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     }
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
+    if (!strcmp(name, "trace_spill")) { c->trace_spill = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
     if (!strcmp(name, "df_dbg")) { c->df_dbg = value; return VXRT_OK; }
     if (!strcmp(name, "df_zver")) { c->df_zver = value; return VXRT_OK; }

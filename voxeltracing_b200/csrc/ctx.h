@@ -102,6 +102,9 @@ struct vxrt_ctx {
     // 0 = one uncapped pass per queue.  set_option "trace_caps".  Off by default: bit-identical, but measured no faster
     // (profiles/r2_k_sweep_caps.txt).
     int trace_caps = 0;
+    // adaptive hand-over (trace_queue.cuh): a warp appends its stragglers to the continuation queue once at most T of its lanes still
+    // have a ray; thresholds per pass as bytes, low byte first.  set_option "trace_spill"; takes precedence over trace_caps.
+    int trace_spill = 0;
     void* d_trace_cont = nullptr;   // 2 continuation queues + counters
     size_t trace_cont_cap = 0;      // rays each queue holds
 
@@ -147,6 +150,7 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
 // continuation storage of the iteration-capped trace passes (trace_queue.cuh), allocated on demand (api.cu)
 struct TraceCont {
     float4* q[2];      // ping-pong continuation queues (capacity = rays of the largest pass)
+    unsigned* meta[2]; // per entry of q: loop state | iterations done << 3 (adaptive hand-over only)
     int* count;        // [pass]: entries appended for pass + 1
 };
 int vxrt_ensure_trace_cont(vxrt_ctx* c, size_t rays, TraceCont* out);

@@ -468,7 +468,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     do {                                                                                                                  \
         cudaEvent_t e0 = vxrt_probe_event(c), e1 = vxrt_probe_event(c);                                                   \
         if (e0 && e1) cudaEventRecord(e0, s);                                                                             \
-        if (c->trace_caps) {                                                                                              \
+        if (c->trace_caps | c->trace_spill) {                                                                                              \
             const PathRays pol = {w, list};                                                                               \
             const int rc_ = launch_trace_capped(c, g, pol, cnt, n, iters, c->d_stats + 1);                                \
             if (rc_ != VXRT_OK) return rc_;                                                                               \
@@ -479,7 +479,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     } while (0)
 #define TRACE_SHADOW()                                                                                                    \
     do {                                                                                                                  \
-        if (c->trace_caps) {                                                                                              \
+        if (c->trace_caps | c->trace_spill) {                                                                                              \
             const ShadowRays pol = {w, light};                                                                            \
             const int rc_ = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);         \
             if (rc_ != VXRT_OK) return rc_;                                                                               \

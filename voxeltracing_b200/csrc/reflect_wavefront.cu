@@ -382,7 +382,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         rf_wf_gen_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);
-        if (c->trace_caps) {
+        if (c->trace_caps | c->trace_spill) {
             const ReflRays pol = {w};
             const int rc = launch_trace_capped(c, g, pol, nullptr, n, a.trace_length, c->d_stats);
             if (rc != VXRT_OK) return rc;
@@ -391,7 +391,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w);
         else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w);
-        if (c->trace_caps) {
+        if (c->trace_caps | c->trace_spill) {
             const ReflShadowRays pol = {w, strong};
             const int rc = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);
             if (rc != VXRT_OK) return rc;
