@@ -57,7 +57,11 @@ def parse_args():
     ap.add_argument("--sharding", default="auto", choices=["auto", "frames", "tiles"],
                     help="N > 1: 'frames' = one frame of the camera path per rank per step (weak scaling); 'tiles' = row strips of ONE frame "
                          "per step spread over the ranks (strong scaling; BASELINE config 5).  auto: tiles for config5, frames otherwise")
-    ap.add_argument("--strips", type=int, default=4, help="tiles sharding: strips per rank (interleaved over the frame for balance)")
+    ap.add_argument("--tile-shape", default="cols", choices=["cols", "rows"],
+                    help="tiles sharding: 'cols' = column bands (every band holds sky and ground, so ONE tile per rank is balanced and every pass is "
+                         "one launch per rank); 'rows' = row strips, interleaved over the frame when --strips > 1 (round 2's first version: 4 strips, "
+                         "4 x the launches)")
+    ap.add_argument("--strips", type=int, default=0, help="tiles sharding: tiles per rank, interleaved over the frame (default: 1 for cols, 4 for rows)")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N > 1: 'push' = every rank copies its outputs into rank 0's buffer with the copy engines over NVLink as each pass "
                          "finishes; 'nccl' = round 1's one NCCL gather per frame on a side stream")
@@ -623,23 +627,34 @@ def main():
 
     # ---- work decomposition over the ranks ----
     # frames: every rank renders its own frame of the camera path per step (weak scaling)
-    # tiles:  every rank renders `strips` row strips of THE SAME frame per step, interleaved over the frame so that sky and ground
-    #         rows are spread over the ranks (strong scaling, BASELINE config 5); the strips are passed as the vxrt_tile of every pass
+    # tiles:  every rank renders its tile(s) of THE SAME frame per step (strong scaling, BASELINE config 5), passed as the vxrt_tile of every
+    #         pass: by default ONE column band per rank (sky and ground in every band; one launch per pass), or --tile-shape rows --strips k
+    #         = k row strips per rank interleaved over the frame (k x the launches: 4 strips measured 3.7 ms per 4K frame at N = 8)
     tiles = world_size > 1 and (args.sharding == "tiles" or (args.sharding == "auto" and args.workload.startswith("config5")))
-    n_strips = max(1, args.strips) if tiles else 1
+    n_strips = (args.strips if args.strips > 0 else (1 if args.tile_shape == "cols" else 4)) if tiles else 1
 
     def frame_of(step):
         return step if tiles else step * world_size + rank
 
     def strips_of(r):
+        """tiles (row0, rows, col0, cols) of rank r; zeros = every row / column"""
         out = []
         for j in range(n_strips):
-            row0, rows = band_rows(H, r + j * world_size, world_size * n_strips)
-            if rows > 0:
-                out.append((row0, rows))
+            if args.tile_shape == "cols":
+                col0, cols = band_rows(W, r + j * world_size, world_size * n_strips, band=32)   # edges on the 32-pixel CTA grid
+                if cols > 0:
+                    out.append((0, 0, col0, cols))
+            else:
+                row0, rows = band_rows(H, r + j * world_size, world_size * n_strips)
+                if rows > 0:
+                    out.append((row0, rows, 0, 0))
         return out
 
-    my_tiles = strips_of(rank) if tiles else [(0, 0)]
+    def rect_of(tile, ah, aw):
+        row0, rows, col0, cols = tile
+        return (row0, rows if rows else ah, col0, cols if cols else aw)
+
+    my_tiles = strips_of(rank) if tiles else [(0, 0, 0, 0)]
     n_total = args.warmup + args.steps
     prepared = [[fr.prepare(camera_for(wl, frame_of(s)), frame_of(s), t) for t in my_tiles] for s in range(n_total)]
 
@@ -714,7 +729,6 @@ def main():
             shared_base = ctx.shared_open(box[0])
 
     def push_hook(s, tile):
-        row0, rows = tile
         slot_off = (s & 1) * per_slot + (0 if tiles else rank * slot_bytes)
 
         def hook(name, where):
@@ -722,7 +736,7 @@ def main():
                 for att in PASS_OUTPUTS[name]:
                     if att in layout:
                         off, row_bytes, _ = layout[att]
-                        ctx.copy_attachment_rows_async(att, shared_base + slot_off + off + row0 * row_bytes, row0, rows)
+                        ctx.copy_attachment_rect_async(att, shared_base + slot_off + off, tile)   # one (strided) DMA copy per attachment
         return hook
 
     packed, gather_dst, comm = None, None, None
@@ -846,9 +860,10 @@ def main():
         for att in out_atts:
             off, rb, ah = layout[att]
             full = torch.as_tensor(ctx.attachment_as_device_array(att), device=f"cuda:{local_rank}").reshape(ah, -1).view(torch.uint8)
-            for (row0, rows) in my_tiles:
-                r0, nr = (row0, rows) if rows else (0, ah)
-                mine[(att, r0, nr)] = csum(full[r0:r0 + nr])
+            bpp = rb // W
+            for tile in my_tiles:
+                r0, nr, c0, nc = rect_of(tile, ah, W)
+                mine[(att, r0, nr, c0, nc)] = csum(full[r0:r0 + nr, c0 * bpp:(c0 + nc) * bpp].contiguous())
         gathered = [None] * world_size
         dist.all_gather_object(gathered, mine)
         if rank == 0:
@@ -856,12 +871,14 @@ def main():
             bad = 0
             for r in range(world_size):
                 slot_off = (s_last & 1) * per_slot + (0 if tiles else r * slot_bytes)
-                for (att, r0, nr), want in gathered[r].items():
+                for (att, r0, nr, c0, nc), want in gathered[r].items():
                     off, rb, ah = layout[att]
-                    got = csum(buf[slot_off + off + r0 * rb: slot_off + off + (r0 + nr) * rb])
+                    bpp = rb // W
+                    img = buf[slot_off + off: slot_off + off + ah * rb].view(ah, rb)
+                    got = csum(img[r0:r0 + nr, c0 * bpp:(c0 + nc) * bpp].contiguous())
                     bad += got != want
             n_chk = sum(len(g) for g in gathered)
-            gather_check = "ok (%d attachment%s of %d ranks, checksums equal)" % (n_chk, " strips" if tiles else "s", world_size) if bad == 0 else "FAILED: %d of %d differ" % (bad, n_chk)
+            gather_check = "ok (%d attachment%s of %d ranks, checksums equal)" % (n_chk, " tiles" if tiles else "s", world_size) if bad == 0 else "FAILED: %d of %d differ" % (bad, n_chk)
 
     # ---- distance-field regeneration (BASELINE config 2) ----
     # (a) the figure of round 1: one regeneration between a CUDA-event pair after a 256 MiB memset.  Events tick in ~2 us steps on this
@@ -1022,20 +1039,19 @@ def main():
     # pattern) while frame k+1 renders; a pass that overwrites an attachment waits on the device for its copy
     host_out = [{att: torch.empty(layout[att][1] * layout[att][2], dtype=torch.uint8).pin_memory() for att in out_atts} for _ in range(2)]
     host_ptr = [{att: t.data_ptr() for att, t in hs.items()} for hs in host_out]
-    my_rows = sum(rows for _, rows in my_tiles) if tiles else H
-    d2h = int(sum(layout[att][1] * my_rows for att in out_atts))
+    my_pixels = sum(r[1] * r[3] for r in (rect_of(t, H, W) for t in my_tiles))
+    d2h = int(sum(layout[att][1] // W * my_pixels for att in out_atts))
     h2d = sum(ctypes.sizeof(p_) for prep in prepared[0] for _, _, p_ in prep)
 
     def e2e_step(s):
         for tile in my_tiles:
             prep = fr.prepare(camera_for(wl, frame_of(s)), frame_of(s), tile)
-            row0, rows = tile
 
-            def read_pass_outputs(name, where, row0=row0, rows=rows):   # a pass's attachments start their way to the host as soon as it is queued
+            def read_pass_outputs(name, where, tile=tile):   # a pass's attachments start their way to the host as soon as it is queued
                 if where == "end":
                     for att in PASS_OUTPUTS[name]:
                         if att in layout:
-                            ctx.copy_attachment_rows_async(att, host_ptr[s & 1][att] + row0 * layout[att][1], row0, rows)
+                            ctx.copy_attachment_rect_async(att, host_ptr[s & 1][att], tile)
 
             fr.submit(prep, hook=read_pass_outputs)
 
@@ -1152,8 +1168,10 @@ def main():
     if world_size == 1:
         sharding_desc = "single GPU"
     elif tiles:
-        sharding_desc = (f"tiles: every rank renders {n_strips} row strips of the SAME frame per step (interleaved over the frame, passed as the vxrt_tile of every pass); "
-                         "the strips' rows of the output attachments are copied into rank 0's frame by the copy engines over NVLink as each pass finishes")
+        shape = ("column band" if args.tile_shape == "cols" else "row strip") + ("s" if n_strips > 1 else "")
+        sharding_desc = (f"tiles: every rank renders {n_strips} {shape} of the SAME frame per step ({'interleaved over the frame, ' if n_strips > 1 else ''}"
+                         "passed as the vxrt_tile rectangle of every pass, one launch per pass per tile); the tile's rectangle of each output attachment "
+                         "is copied into rank 0's frame by the copy engines over NVLink (one strided copy) as each pass finishes")
     elif push:
         sharding_desc = ("frames: one frame of the camera path per rank per step; each pass's output attachments are copied into rank 0's buffer by the copy "
                          "engines over NVLink (cudaIpc-mapped peer memory, no SM) as soon as the pass is queued, overlapping the rest of the frame")

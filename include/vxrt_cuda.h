@@ -191,6 +191,9 @@ int vxrt_cuda_shared_close(vxrt_ctx* ctx, void* dev_ptr);
 /* rows [row0, row0 + rows) of an attachment (rows == 0: the whole attachment) to `dst`, the address those rows have in the
  * destination image: device memory of this GPU, of a peer (vxrt_cuda_shared_open) or page-locked host memory. */
 int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* ctx, int32_t id, int32_t row0, int32_t rows, void* dst);
+/* the same for a rectangle (rows == 0: every row, cols == 0: every column): `dst_image` is the address of pixel (0, 0) of the
+ * destination image, which has the attachment's geometry; one strided copy (cudaMemcpy2DAsync) on the copy engines. */
+int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* ctx, int32_t id, int32_t row0, int32_t rows, int32_t col0, int32_t cols, void* dst_image);
 /* makes the context's stream wait (on the device) for every copy queued so far: an event recorded on the stream afterwards
  * marks the moment the frame has left the GPU (device-side timing of the export; the host does not block). */
 int vxrt_cuda_join_reads(vxrt_ctx* ctx);
@@ -206,11 +209,16 @@ int vxrt_cuda_attachment_device(vxrt_ctx* ctx, int32_t attachment, void** dev_pt
  * later passes of the frame can consume a set rendered earlier.                                        */
 int vxrt_cuda_bind_attachment(vxrt_ctx* ctx, int32_t attachment, void* dev_ptr, size_t capacity);
 
-/* Screen-tile sharding: a pass only shades rows [row0, row0+rows) of the frame;
- * rows == 0 means the whole frame.  Attachments always have full-frame geometry.             */
+/* Screen-tile sharding: a pass only shades the rectangle rows [row0, row0+rows) x columns [col0, col0+cols) of
+ * the frame; rows == 0 means every row, cols == 0 every column (a zeroed tile is the whole frame).  Attachments always have
+ * full-frame geometry.  Column bands keep sky and ground in every rank's tile, so one launch per pass per rank stays balanced.
+ * The ray passes (initial / shadow trace, G-buffer, direct term, GI, reflections) take any rectangle; the screen-space
+ * filters (SVGF, shadow and reflection denoisers) take row bands only and reject cols != 0.                                  */
 typedef struct vxrt_tile {
     int32_t row0;
     int32_t rows;
+    int32_t col0;
+    int32_t cols;
 } vxrt_tile;
 
 /* ---- primary G-buffer pass: InitialRayTraceFrag.glsl, Core/Pipeline.cpp:2051-2094 ---- */

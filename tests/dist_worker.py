@@ -33,14 +33,14 @@ def main():
         p.inv_view[i] = float(cam.inv_view[i]); p.inv_projection[i] = float(cam.inv_projection[i])
     p.width, p.height, p.render_distance = W, H, 350
     row0, rows = band_rows(H, rank, world)
-    p.tile.row0, p.tile.rows = row0, rows
+    abi.set_tile(p.tile, (row0, rows))
     part = ow.initial_trace(p)
     full_t = torch.from_numpy(part["t"].view(np.int16).copy())
     full_b = torch.from_numpy(part["block"].copy())
     sharding.gather_bands(full_t, H, rank, world)
     sharding.gather_bands(full_b, H, rank, world)
     if rank == 0:
-        p.tile.row0, p.tile.rows = 0, 0
+        abi.set_tile(p.tile, (0, 0))
         whole = ow.initial_trace(p)
         out["bands_t_equal"] = bool(np.array_equal(full_t.numpy().view(np.float16).view(np.uint16), whole["t"].view(np.uint16)))
         out["bands_block_equal"] = bool(np.array_equal(full_b.numpy(), whole["block"]))

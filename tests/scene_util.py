@@ -57,7 +57,7 @@ def gbuffer_params(cam, w, h, inputs: SceneInputs, tile=(0, 0)) -> abi.GBufferPa
     fill(p.inv_view, cam.inv_view); fill(p.inv_projection, cam.inv_projection)
     p.width, p.height = w, h
     fill(p.grass_props, inputs.grass); fill(p.cactus_props, inputs.cactus)
-    p.tile.row0, p.tile.rows = tile
+    abi.set_tile(p.tile, tile)
     return p
 
 
@@ -71,7 +71,7 @@ def direct_params(cam, w, h, sun_tick=50.0, tile=(0, 0)) -> abi.DirectParams:
     fill(p.sun_color, [c, c, c]); fill(p.moon_color, [0.12, 0.14, 0.25])
     p.texture_desat_amount = 0.1
     p.amplify_normal_map = 0
-    p.tile.row0, p.tile.rows = tile
+    abi.set_tile(p.tile, tile)
     return p
 
 
@@ -89,7 +89,7 @@ def gi_params(cam, w, h, frame=0, spp=1, checkerboard=False, sun_tick=50.0, tile
     p.sun_visibility, p.gi_sun_strength, p.gi_sky_strength, p.diffuse_light_intensity = sv, 1.0, 1.125, 1.25
     fill(p.viewer_position, cam.position)
     p.apply_player_shadow = 0
-    p.tile.row0, p.tile.rows = tile
+    abi.set_tile(p.tile, tile)
     return p
 
 
@@ -110,5 +110,5 @@ def reflection_params(cam, w, h, frame=0, spp=1, sun_tick=50.0, tile=(0, 0), inp
     p.sun_strength_modifier, p.moon_strength_modifier = 0.85, 1.0
     if inputs is not None:
         fill(p.grass_props, inputs.grass)
-    p.tile.row0, p.tile.rows = tile
+    abi.set_tile(p.tile, tile)
     return p

@@ -54,5 +54,17 @@ def test_benched_configuration_matches_the_oracle_on_a_band(workload, frame, inp
         for a in fr.outputs:
             got = ctx.read_attachment(a)
             assert np.array_equal(got[r0:r1].view(np.uint8), full[a][r0:r1].view(np.uint8)), (workload, a)
+        # ... and so does a column band crossing it, with edges off the CTA grid (what --sharding tiles does per rank)
+        Wf = wl["width"]
+        c0, cw = Wf // 3 + 5, Wf // 4 + 3
+        import torch
+        ctx.synchronize()
+        for a in fr.outputs:   # poison the rectangle (only it: passes read their inputs' neighbours across the tile edge): the tile must rewrite it
+            torch.as_tensor(ctx.attachment_as_device_array(a), device="cuda")[r0:r1, c0:c0 + cw].fill_(77)
+        torch.cuda.synchronize()
+        fr.render(bench.camera_for(wl, frame), frame, tile=(r0, r1 - r0, c0, cw))
+        for a in fr.outputs:
+            got = ctx.read_attachment(a)
+            assert np.array_equal(got[r0:r1, c0:c0 + cw].view(np.uint8), full[a][r0:r1, c0:c0 + cw].view(np.uint8)), (workload, a, "rect")
     finally:
         ctx.close()

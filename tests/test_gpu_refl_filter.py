@@ -85,7 +85,7 @@ def test_row_band_equals_full_frame_and_errors(seq):
         full = c.read_attachment(os_)
         c.write_attachment(os_, np.zeros_like(full))
         for row0, rows in ((0, 40), (40, 68)):
-            p.tile.row0, p.tile.rows = row0, rows
+            abi.set_tile(p.tile, (row0, rows))
             c.specular_temporal(p)
         assert np.array_equal(c.read_attachment(os_).view(np.uint16), full.view(np.uint16))
         bad = rf.params(f, seq[0], abi.ATT_REFL_TEMPORAL_A, abi.ATT_REFL_TEMPORAL_A)
@@ -171,7 +171,7 @@ def test_denoiser_row_band_and_errors(seq):
         full = c.read_attachment(abi.ATT_REFL_DENOISED_A)
         c.write_attachment(abi.ATT_REFL_DENOISED_A, np.zeros_like(full))
         for row0, rows in ((0, 50), (50, 58)):
-            p.tile.row0, p.tile.rows = row0, rows
+            abi.set_tile(p.tile, (row0, rows))
             c.reflection_denoise(p)
         assert np.array_equal(c.read_attachment(abi.ATT_REFL_DENOISED_A).view(np.uint16), full.view(np.uint16))
         for bad in (dict(out_att=abi.ATT_REFL_COLOR), dict(in_att=abi.ATT_REFL_DENOISED_A), dict(temporal_set=abi.ATT_GI_SH)):

@@ -114,11 +114,11 @@ def test_chain_on_gpu_traced_shadows_and_tile_sharding():
             tps, fps = [], []
             for row0, rows in bands:
                 tp = sf.temporal_params(cam, prev_cam, hs, os_); tp.width, tp.height = W, H
-                tp.tile.row0, tp.tile.rows = row0, rows
+                abi.set_tile(tp.tile, (row0, rows))
                 c.shadow_temporal(tp); tps.append(tp)
             for row0, rows in bands:
                 fp = sf.filter_params(cam, os_); fp.width, fp.height = W, H
-                fp.tile.row0, fp.tile.rows = row0, rows
+                abi.set_tile(fp.tile, (row0, rows))
                 c.shadow_filter(fp); fps.append(fp)
             if k == 2:
                 snap = {"tp": tps[0], "fp": fps[0], "t": {"shadow": c.read_attachment(os_), "frames": c.read_attachment(os_ + 1)},

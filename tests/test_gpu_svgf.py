@@ -180,7 +180,7 @@ def test_chain_on_gpu_rendered_frames_and_tile_sharding():
                 c.initial_trace(cam, W, H, tile=(row0, rows))
             for row0, rows in bands:
                 gp = su.gi_params(cam, W, H, frame=k, spp=1)
-                gp.tile.row0, gp.tile.rows = row0, rows
+                abi.set_tile(gp.tile, (row0, rows))
                 c.diffuse_trace(gp)
             prev_cam = chain.prev_cam or cam
             stages = []

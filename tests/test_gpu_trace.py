@@ -105,6 +105,48 @@ def test_tile_sharded_primary_equals_full_frame(scene):
     c2.close()
 
 
+def test_rectangle_tiles_equal_full_frame_and_rect_copy(scene):
+    """vxrt_tile as a rectangle (column bands, a 2 x 2 grid with edges that are not multiples of the 32 x 8 CTA tile): the union of the
+    tiles is the full frame bit for bit; vxrt_cuda_copy_attachment_rect_async moves exactly the rectangle; bad rectangles are rejected."""
+    import torch
+    c, ow, _ = scene
+    cam = host_api.camera([192, 75, 192], 135.0, -20.0, 16 / 9)
+    W, H = 640, 360
+    atts = (abi.ATT_INITIAL_T, abi.ATT_INITIAL_NORMAL, abi.ATT_INITIAL_BLOCK, abi.ATT_INITIAL_INVT)
+    c.initial_trace(cam, W, H)
+    c.shadow_trace(cam, W, H, host_api.sun_direction(50.0)[2], soft=False)
+    full = {a: c.read_attachment(a).copy() for a in atts + (abi.ATT_SHADOW,)}
+    c2 = engine.Context(0)
+    c2.upload_world(ow.blocks)
+    c2.generate_distance_field()
+    for tiles in ([(0, 0, 0, 213), (0, 0, 213, 214), (0, 0, 427, 213)], [(0, 101, 0, 333), (0, 101, 333, 307), (101, 259, 0, 333), (101, 259, 333, 307)]):
+        c2.initial_trace(cam, W, H, tile=(0, 1))       # allocate, then poison so that every pixel must be rewritten by a tile
+        c2.synchronize()
+        for a in atts:
+            torch.as_tensor(c2.attachment_as_device_array(a), device="cuda").fill_(77)
+        torch.cuda.synchronize()
+        for t in tiles:
+            c2.initial_trace(cam, W, H, tile=t)
+        for a in atts:
+            assert np.array_equal(c2.read_attachment(a).view(np.uint8), full[a].view(np.uint8)), (a, tiles)
+        for t in tiles:
+            c2.shadow_trace(cam, W, H, host_api.sun_direction(50.0)[2], soft=False, tile=t)
+        assert np.array_equal(c2.read_attachment(abi.ATT_SHADOW), full[abi.ATT_SHADOW])
+    # rectangle copy into a zeroed device image
+    _, w_, h_, bpp = c2.attachment_info(abi.ATT_INITIAL_INVT)
+    dst = torch.zeros((h_, w_), dtype=torch.float32, device="cuda")
+    c2.copy_attachment_rect_async(abi.ATT_INITIAL_INVT, dst.data_ptr(), (40, 100, 64, 200))
+    c2.wait_reads()
+    want = np.zeros((h_, w_), np.float32)
+    want[40:140, 64:264] = full[abi.ATT_INITIAL_INVT].reshape(h_, w_)[40:140, 64:264]
+    assert np.array_equal(dst.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    with pytest.raises(Exception):
+        c2.initial_trace(cam, W, H, tile=(0, 0, W, 10))
+    with pytest.raises(Exception):
+        c2.copy_attachment_rect_async(abi.ATT_INITIAL_INVT, dst.data_ptr(), (0, 0, 600, 100))
+    c2.close()
+
+
 def _shadow_case(c, ow, blue, cam, w, h, sw, sh, soft, frame, halton=(0.0, 0.0), light=None):
     c.initial_trace(cam, w, h)
     g_t = c.read_attachment(abi.ATT_INITIAL_T)

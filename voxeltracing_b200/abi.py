@@ -37,7 +37,13 @@ TEX_ALBEDO, TEX_NORMAL, TEX_PBR, TEX_EMISSIVE = 0, 1, 2, 3
 
 
 class Tile(C.Structure):
-    _fields_ = [("row0", C.c_int32), ("rows", C.c_int32)]
+    _fields_ = [("row0", C.c_int32), ("rows", C.c_int32), ("col0", C.c_int32), ("cols", C.c_int32)]
+
+
+def set_tile(t: "Tile", tile) -> None:
+    """tile = (row0, rows) or (row0, rows, col0, cols); zeros mean every row / every column (vxrt_tile)"""
+    tile = tuple(tile) + (0, 0) * (len(tuple(tile)) == 2)
+    t.row0, t.rows, t.col0, t.cols = (int(v) for v in tile)
 
 
 class PrimaryParams(C.Structure):
@@ -254,6 +260,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_wait_reads": (C.c_int, [vp]),
         "vxrt_cuda_join_reads": (C.c_int, [vp]),
         "vxrt_cuda_copy_attachment_rows_async": (C.c_int, [vp, i32, i32, i32, vp]),
+        "vxrt_cuda_copy_attachment_rect_async": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
         "vxrt_cuda_shared_alloc": (C.c_int, [vp, sz, C.POINTER(vp), vp]),
         "vxrt_cuda_shared_free": (C.c_int, [vp, vp]),
         "vxrt_cuda_shared_open": (C.c_int, [vp, vp, C.POINTER(vp)]),

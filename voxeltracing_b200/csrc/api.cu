@@ -450,6 +450,29 @@ int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* c, int32_t id, int32_t row0, 
     c->att_read_pending[id] = true;
     return VXRT_OK;
 }
+int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, int32_t col0, int32_t cols, void* dst_image) {
+    REQUIRE_CTX(c); REQUIRE_PTR(dst_image);
+    if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
+    const Attachment& a = c->att[id];
+    if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
+    if (rows == 0) { row0 = 0; rows = a.height; }
+    if (cols == 0) { col0 = 0; cols = a.width; }
+    if (row0 < 0 || rows < 0 || row0 + rows > a.height || col0 < 0 || cols < 0 || col0 + cols > a.width)
+        return vxrt_fail(VXRT_E_INVALID, "copy_attachment_rect: rows [%d,+%d) x columns [%d,+%d) of %dx%d", row0, rows, col0, cols, a.width, a.height);
+    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->att_ready[id]) {
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
+    }
+    const size_t pitch = (size_t)a.width * a.bpp, off = (size_t)row0 * pitch + (size_t)col0 * a.bpp;
+    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));
+    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
+    if (rows > 0 && cols > 0)
+        VX_CUDA(cudaMemcpy2DAsync((uint8_t*)dst_image + off, pitch, (const uint8_t*)a.ptr + off, pitch, (size_t)cols * a.bpp, (size_t)rows, cudaMemcpyDefault, c->copy_stream));
+    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
+    c->att_read_pending[id] = true;
+    return VXRT_OK;
+}
 int vxrt_cuda_shared_alloc(vxrt_ctx* c, size_t bytes, void** dev_ptr, uint8_t handle[64]) {
     REQUIRE_CTX(c); REQUIRE_PTR(dev_ptr); REQUIRE_PTR(handle);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the IPC handle as 64 bytes");
@@ -527,9 +550,11 @@ int vxrt_cuda_attachment_device(vxrt_ctx* c, int32_t id, void** p, int32_t* w, i
     return VXRT_OK;
 }
 
-static int check_frame(const char* fn, int w, int h, const vxrt_tile& t) {
+static int check_frame(const char* fn, int w, int h, const vxrt_tile& t, bool rows_only = false) {
     if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "%s: bad dimensions %dx%d", fn, w, h);
     if (t.rows < 0 || t.row0 < 0 || (t.rows > 0 && t.row0 >= h)) return vxrt_fail(VXRT_E_INVALID, "%s: bad tile rows [%d,+%d) of %d", fn, t.row0, t.rows, h);
+    if (t.cols < 0 || t.col0 < 0 || (t.cols > 0 && t.col0 >= w)) return vxrt_fail(VXRT_E_INVALID, "%s: bad tile columns [%d,+%d) of %d", fn, t.col0, t.cols, w);
+    if (rows_only && t.cols != 0) return vxrt_fail(VXRT_E_INVALID, "%s: the screen-space filters take row bands only (tile.cols must be 0)", fn);
     return VXRT_OK;
 }
 
@@ -670,25 +695,25 @@ int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
 }
 int vxrt_cuda_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_svgf_temporal(c, *p);
 }
 int vxrt_cuda_svgf_prespatial(vxrt_ctx* c, const vxrt_svgf_prespatial_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_svgf_prespatial(c, *p);
 }
 int vxrt_cuda_svgf_variance(vxrt_ctx* c, const vxrt_svgf_variance_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_svgf_variance(c, *p);
 }
 int vxrt_cuda_svgf_spatial(vxrt_ctx* c, const vxrt_svgf_spatial_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_svgf_spatial(c, *p);
 }
@@ -709,25 +734,25 @@ int vxrt_cuda_select_shadow(vxrt_ctx* c, int32_t id) {
 }
 int vxrt_cuda_specular_temporal(vxrt_ctx* c, const vxrt_specular_temporal_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_specular_temporal(c, *p);
 }
 int vxrt_cuda_reflection_denoise(vxrt_ctx* c, const vxrt_reflection_denoise_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_reflection_denoise(c, *p);
 }
 int vxrt_cuda_shadow_temporal(vxrt_ctx* c, const vxrt_shadow_temporal_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_shadow_temporal(c, *p);
 }
 int vxrt_cuda_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params* p) {
     REQUIRE_CTX(c); REQUIRE_PTR(p);
-    int rc = check_frame(__func__, p->width, p->height, p->tile);
+    int rc = check_frame(__func__, p->width, p->height, p->tile, true);
     if (rc) return rc;
     return vxrt_launch_shadow_filter(c, *p);
 }

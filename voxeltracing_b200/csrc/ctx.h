@@ -147,6 +147,14 @@ int vxrt_check_cuda(cudaError_t e, const char* what);
         if (_rc != VXRT_OK) return _rc;                            \
     } while (0)
 
+// rectangle of a vxrt_tile clipped to the frame (rows == 0: every row, cols == 0: every column)
+inline void vxrt_tile_rect(const vxrt_tile& t, int width, int height, int* r0, int* r1, int* c0, int* c1) {
+    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
+    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
+    if (t.cols <= 0) { *c0 = 0; *c1 = width; }
+    else { *c0 = t.col0; *c1 = t.col0 + t.cols; if (*c1 > width) *c1 = width; }
+}
+
 // continuation storage of the iteration-capped trace passes (trace_queue.cuh), allocated on demand (api.cu)
 struct TraceCont {
     float4* q[2];      // ping-pong continuation queues (capacity = rays of the largest pass)

@@ -92,8 +92,8 @@ VXD f4 calculate_diffuse(const GridView& g, const GiArgs& a, GiState& st, f3 ini
 template <bool STATS>
 __global__ void __launch_bounds__(256) diffuse_trace_kernel(GridView g, const __grid_constant__ GiArgs a, TraceStatsDev* stats) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    const bool active = px < a.width && py < a.row1;
+    tile_pixel(px, py, a.row0, a.col0);
+    const bool active = px < a.col1 && py < a.row1;
     LaneStats ls = {0u, 0u, 0u, 0u};
     if (active) {
         const size_t i = (size_t)py * a.width + px;
@@ -163,11 +163,6 @@ __global__ void __launch_bounds__(256) diffuse_trace_kernel(GridView g, const __
     if (STATS) flush_stats(stats, ls);
 }
 
-inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
-    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
-    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
-}
-
 }  // namespace
 
 int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p) {
@@ -179,7 +174,7 @@ int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p) {
     GiArgs a;
     for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
     a.width = p.width; a.height = p.height;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     a.spp = p.spp; a.checker_spp = p.checker_spp; a.checkerboard = p.checkerboard; a.trace_length = p.trace_length;
     a.shadow_trace_length = p.shadow_trace_length; a.frame = p.current_frame; a.frame_mod128 = p.current_frame_mod128;
     a.supersample = p.supersample;
@@ -199,9 +194,9 @@ int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p) {
     a.blue = c->d_blue_noise;
     a.sh = (uint16_t*)c->att[VXRT_ATT_GI_SH].ptr; a.cocg = (uint16_t*)c->att[VXRT_ATT_GI_COCG].ptr;
     a.utility = (uint16_t*)c->att[VXRT_ATT_GI_UTILITY].ptr; a.aosky = (uint8_t*)c->att[VXRT_ATT_GI_AOSKY].ptr;
-    if (a.row1 <= a.row0) return VXRT_OK;
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
     if (c->wavefront) return vxrt_launch_diffuse_trace_wavefront(c, &a);
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     if (c->stats_on) diffuse_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     else diffuse_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     VX_CUDA(cudaGetLastError());

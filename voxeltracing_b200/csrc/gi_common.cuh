@@ -7,7 +7,7 @@ namespace {
 
 struct GiArgs {
     float inv_view[16], inv_proj[16];
-    int width, height, row0, row1;
+    int width, height, row0, row1, col0, col1;
     int spp, checker_spp, checkerboard, trace_length, shadow_trace_length, frame, frame_mod128, supersample;
     float halton[2];
     float sun[3], moon[3], viewer[3], light_color[3];

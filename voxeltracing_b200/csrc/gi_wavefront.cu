@@ -85,7 +85,7 @@ struct PathRays {
     }
 };
 template <bool STATS>
-__global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_paths_kernel(GridView g, GiWf w, const int* __restrict__ list, const int* __restrict__ count_ptr,
+__global__ void VX_TRACE_BOUNDS wf_trace_paths_kernel(GridView g, GiWf w, const int* __restrict__ list, const int* __restrict__ count_ptr,
                                                              int n, int max_iter, TraceStatsDev* stats) {
     const int count = list ? *count_ptr : n;
     LaneStats ls = {0u, 0u, 0u, 0u};
@@ -107,7 +107,7 @@ struct ShadowRays {
     }
 };
 template <bool STATS>
-__global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_shadow_kernel(GridView g, GiWf w, f3 light, int max_iter, TraceStatsDev* stats) {
+__global__ void VX_TRACE_BOUNDS wf_trace_shadow_kernel(GridView g, GiWf w, f3 light, int max_iter, TraceStatsDev* stats) {
     const int count = w.counters[0];
     LaneStats ls = {0u, 0u, 0u, 0u};
     ShadowRays pol = {w, light};
@@ -118,9 +118,9 @@ __global__ void __launch_bounds__(VX_TRACE_CTA) wf_trace_shadow_kernel(GridView 
 // ---- gen: main() prologue per pixel (:910-969) + first direction of sample `sample` ------------------
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     if (sample == 0) {
         const size_t pi = (size_t)py * a.width + px;
         const f2 vtc = pixel_uv(px, py, a.width, a.height);
@@ -198,9 +198,9 @@ VXD void finish_sample(const GiWf& w, int i, f3 contrib, float skyhit, bool firs
 template <int BOUNCE>
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    const bool inside = px < a.width && py < a.row1;
-    const int i = inside ? (py - a.row0) * a.width + px : 0;
+    tile_pixel(px, py, a.row0, a.col0);
+    const bool inside = px < a.col1 && py < a.row1;
+    const int i = inside ? (py - a.row0) * (a.col1 - a.col0) + (px - a.col0) : 0;
     bool push_shadow = false, push_bounce = false;
     f3 shadow_o = F3(0.0f);
     // a path is alive at bounce 0 iff gen gave it a ray (rayD.w), later iff the previous stage left contrib.w set
@@ -347,9 +347,9 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
 // ---- resolve: averages, clamps and attachment formats of main() (:1003-1020) ------------------------
 __global__ void __launch_bounds__(256) gi_wf_resolve_kernel(const __grid_constant__ GiArgs a, GiWf w) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     if (w.bl[i] < 0) return;  // sky pixel, written by gen
     const size_t pi = (size_t)py * a.width + px;
     const float n = (float)w.spp[i];
@@ -374,9 +374,9 @@ __global__ void __launch_bounds__(256) gi_wf_resolve_kernel(const __grid_constan
 // of such a pixel are not touched at all), and one launch less.  Same arithmetic in the same order, bit-identical.
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_final_kernel(const __grid_constant__ GiArgs a, GiWf w, int sample) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     if (w.bl[i] < 0) return;  // sky pixel, written by gen
     float4 s, r, c;
     const float4 c4 = w.contrib[i];
@@ -432,9 +432,9 @@ T* carve(uint8_t*& p, size_t n) {
 // `a` is the fully populated argument block built by vxrt_launch_diffuse_trace (gi.cu)
 int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     const GiArgs& a = *reinterpret_cast<const GiArgs*>(args_blob);
-    const int rows = a.row1 - a.row0;
-    if (rows <= 0) return VXRT_OK;
-    const size_t n = (size_t)rows * a.width;
+    const int rows = a.row1 - a.row0, cols = a.col1 - a.col0;   // the tile rectangle; path state is indexed inside it
+    if (rows <= 0 || cols <= 0) return VXRT_OK;
+    const size_t n = (size_t)rows * cols;
     const size_t need = n * (16 * 13 + 4 * 6) + 256 * 32;
     if (need > c->wf_cap) {
         if (c->d_wf) VX_CUDA(cudaFree(c->d_wf));
@@ -452,7 +452,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     w.shadowRes = carve<float>(p, n); w.qBounce = carve<int>(p, n);
     w.counters = carve<int>(p, 16);
 
-    const dim3 pgrid((a.width + 31) / 32, (rows + 7) / 8);
+    const dim3 pgrid((cols + 31) / 32, (rows + 7) / 8);
     const int lgrid = trace_queue_grid(n);
     const GridView g = c->grid();
     f3 light;

@@ -12,8 +12,8 @@ namespace {
 template <bool STATS>
 __global__ void __launch_bounds__(256) reflection_trace_kernel(GridView g, const __grid_constant__ ReflArgs a, TraceStatsDev* stats) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    const bool active = px < a.width && py < a.row1;
+    tile_pixel(px, py, a.row0, a.col0);
+    const bool active = px < a.col1 && py < a.row1;
     LaneStats ls = {0u, 0u, 0u, 0u};
     if (active) {
         const size_t i = (size_t)py * a.width + px;
@@ -176,11 +176,6 @@ __global__ void __launch_bounds__(256) reflection_trace_kernel(GridView g, const
     if (STATS) flush_stats(stats, ls);
 }
 
-inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
-    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
-    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
-}
-
 }  // namespace
 
 int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
@@ -197,7 +192,7 @@ int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
             a.proj_view[4 * col + r] = (p.projection[r] * v[0] + p.projection[4 + r] * v[1]) + (p.projection[8 + r] * v[2] + p.projection[12 + r] * v[3]);
         }
     a.width = p.width; a.height = p.height;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     a.spp = p.spp; a.checkerboard = p.checkerboard; a.trace_length = p.trace_length; a.shadow_trace_length = p.shadow_trace_length;
     a.frame = p.current_frame; a.frame_mod128 = p.current_frame_mod128;
     a.rough = p.rough_reflections; a.roughness_bias = p.roughness_bias; a.temporal = p.temporal; a.reproject = p.reproject_to_screen_space;
@@ -245,9 +240,9 @@ int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
         const float up[3] = {0.0f, 1.0f, 0.0f};
         vxrt_host_sky_sample(c, up, a.sky_ambient_g);
     }
-    if (a.row1 <= a.row0) return VXRT_OK;
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
     if (c->wavefront) return vxrt_launch_reflection_trace_wavefront(c, &a);
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     if (c->stats_on) reflection_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     else reflection_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     VX_CUDA(cudaGetLastError());

@@ -8,7 +8,7 @@ namespace {
 
 struct ReflArgs {
     float inv_view[16], inv_proj[16], proj_view[16];
-    int width, height, row0, row1;
+    int width, height, row0, row1, col0, col1;
     int spp, checkerboard, trace_length, shadow_trace_length, frame, frame_mod128;
     int rough, roughness_bias, temporal, reproject, derive_sh;
     float halton[2];

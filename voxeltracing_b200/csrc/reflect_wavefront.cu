@@ -66,7 +66,7 @@ struct ReflRays {
     }
 };
 template <bool STATS>
-__global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_kernel(GridView g, RfWf w, int n, int max_iter, TraceStatsDev* stats) {
+__global__ void VX_TRACE_BOUNDS rf_wf_trace_kernel(GridView g, RfWf w, int n, int max_iter, TraceStatsDev* stats) {
     LaneStats ls = {0u, 0u, 0u, 0u};
     ReflRays pol = {w};
     trace_queue<STATS>(g, pol, n, max_iter, &ls);
@@ -85,7 +85,7 @@ struct ReflShadowRays {
     }
 };
 template <bool STATS>
-__global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_shadow_kernel(GridView g, RfWf w, f3 light, int max_iter, TraceStatsDev* stats) {
+__global__ void VX_TRACE_BOUNDS rf_wf_trace_shadow_kernel(GridView g, RfWf w, f3 light, int max_iter, TraceStatsDev* stats) {
     const int count = w.counters[0];
     LaneStats ls = {0u, 0u, 0u, 0u};
     ReflShadowRays pol = {w, light};
@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(VX_TRACE_CTA) rf_wf_trace_shadow_kernel(GridVi
 
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __grid_constant__ ReflArgs a, RfWf w, int sample) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     if (sample == 0) {
         const size_t pi = (size_t)py * a.width + px;
         const f2 vtc = pixel_uv(px, py, a.width, a.height);
@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
 template <bool LPVGI>
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    const bool inside = px < a.width && py < a.row1;
-    const int i = inside ? (py - a.row0) * a.width + px : 0;
+    tile_pixel(px, py, a.row0, a.col0);
+    const bool inside = px < a.col1 && py < a.row1;
+    const int i = inside ? (py - a.row0) * (a.col1 - a.col0) + (px - a.col0) : 0;
     bool push_shadow = false;
     f3 shadow_o = F3(0.0f);
     const float4 d4 = inside ? w.rayD[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
 
 __global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     const float4 amb = w.Amb[i];
     if (amb.w == 0.0f) return;
     const float4 res = w.Res[i];
@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constan
 
 __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
-    const int i = (py - a.row0) * a.width + px;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     const int4 cnt = w.cnt[i];
     if (cnt.w < 0) return;
     const size_t pi = (size_t)py * a.width + px;
@@ -353,9 +353,9 @@ T* carve(uint8_t*& p, size_t n) {
 
 int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     const ReflArgs& a = *reinterpret_cast<const ReflArgs*>(args_blob);
-    const int rows = a.row1 - a.row0;
-    if (rows <= 0) return VXRT_OK;
-    const size_t n = (size_t)rows * a.width;
+    const int rows = a.row1 - a.row0, cols = a.col1 - a.col0;   // the tile rectangle; path state is indexed inside it
+    if (rows <= 0 || cols <= 0) return VXRT_OK;
+    const size_t n = (size_t)rows * cols;
     const size_t need = n * (16 * 11 + 4 * 3) + 256 * 32;
     if (need > c->wf_cap) {
         if (c->d_wf) VX_CUDA(cudaFree(c->d_wf));
@@ -371,7 +371,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     w.hitT = carve<float>(p, n); w.hitInfo = carve<unsigned>(p, n); w.shadowRes = carve<float>(p, n);
     w.counters = carve<int>(p, 16);
 
-    const dim3 pgrid((a.width + 31) / 32, (rows + 7) / 8);
+    const dim3 pgrid((cols + 31) / 32, (rows + 7) / 8);
     const int lgrid = trace_queue_grid(n);
     const GridView g = c->grid();
     f3 strong;

@@ -7,7 +7,7 @@ namespace {
 
 struct GBufferArgs {
     float inv_view[16], inv_proj[16];
-    int width, height, row0, row1;
+    int width, height, row0, row1, col0, col1;
     int grass[10], cactus[10];
     const float* g_inv_t; const uint8_t* g_normal; const uint8_t* g_block; int gw, gh;
     TexArrayDev tex[4];
@@ -33,8 +33,8 @@ VXD f4 gbuffer_texture_ids(const GBufferArgs& a, int id, f3 n) {
 
 __global__ void __launch_bounds__(256) generate_gbuffer_kernel(const __grid_constant__ GBufferArgs a) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
     const size_t i = (size_t)py * a.width + px;
     const f2 tc = pixel_uv(px, py, a.width, a.height);
     const int BaseID = iclamp(cvt_floor(att_r8_nearest(a.g_block, a.gw, a.gh, tc) * 255.0f), 0, 127);
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) generate_gbuffer_kernel(const __grid_cons
 
 struct DirectArgs {
     float inv_view[16], inv_proj[16];
-    int width, height, row0, row1;
+    int width, height, row0, row1, col0, col1;
     float viewer[3], sun[3], moon[3], sun_color[3], moon_color[3];
     float desat; int amplify;
     const float* g_inv_t; int gw, gh;
@@ -113,8 +113,8 @@ VXD f3 color_directional_light(f3 viewer, f3 world_pos, f3 light_dir, f3 radianc
 
 __global__ void __launch_bounds__(256) shade_direct_kernel(const __grid_constant__ DirectArgs a) {
     int px, py;
-    tile_pixel(px, py, a.row0);
-    if (px >= a.width || py >= a.row1) return;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
     const size_t i = (size_t)py * a.width + px;
     const f2 tc = pixel_uv(px, py, a.width, a.height);
     const float Dist = 1.0f / att_r32f_bilinear(a.g_inv_t, a.gw, a.gh, tc);
@@ -155,11 +155,6 @@ __global__ void __launch_bounds__(256) shade_direct_kernel(const __grid_constant
     a.direct[3 * i] = float_to_half_bits(out.x); a.direct[3 * i + 1] = float_to_half_bits(out.y); a.direct[3 * i + 2] = float_to_half_bits(out.z);
 }
 
-inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
-    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
-    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
-}
-
 }  // namespace
 
 int vxrt_launch_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params& p) {
@@ -171,7 +166,7 @@ int vxrt_launch_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params& p) {
     GBufferArgs a;
     for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
     a.width = p.width; a.height = p.height;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     for (int i = 0; i < 10; ++i) { a.grass[i] = p.grass_props[i]; a.cactus[i] = p.cactus_props[i]; }
     const Attachment& gi = c->att[VXRT_ATT_INITIAL_INVT];
     a.g_inv_t = (const float*)gi.ptr; a.g_normal = (const uint8_t*)c->att[VXRT_ATT_INITIAL_NORMAL].ptr;
@@ -180,8 +175,8 @@ int vxrt_launch_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params& p) {
     a.block_data = c->d_block_data;
     a.albedo = (uint16_t*)c->att[VXRT_ATT_GBUF_ALBEDO].ptr; a.normal = (uint16_t*)c->att[VXRT_ATT_GBUF_NORMAL].ptr;
     a.pbr = (uint8_t*)c->att[VXRT_ATT_GBUF_PBR].ptr; a.texao = (uint8_t*)c->att[VXRT_ATT_GBUF_TEXAO].ptr;
-    if (a.row1 <= a.row0) return VXRT_OK;
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     generate_gbuffer_kernel<<<grid, 256, 0, c->stream>>>(a);
     VX_CUDA(cudaGetLastError());
     c->launches += 1;
@@ -194,7 +189,7 @@ int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p) {
     DirectArgs a;
     for (int i = 0; i < 16; ++i) { a.inv_view[i] = p.inv_view[i]; a.inv_proj[i] = p.inv_projection[i]; }
     a.width = p.width; a.height = p.height;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     for (int i = 0; i < 3; ++i) {
         a.viewer[i] = p.viewer_position[i]; a.sun[i] = p.sun_direction[i]; a.moon[i] = p.moon_direction[i];
         a.sun_color[i] = p.sun_color[i]; a.moon_color[i] = p.moon_color[i];
@@ -209,8 +204,8 @@ int vxrt_launch_shade_direct(vxrt_ctx* c, const vxrt_direct_params& p) {
     const Attachment& sh = c->att[c->shadow_source];
     a.shadow = (const uint8_t*)sh.ptr; a.sw = sh.width; a.sh = sh.height;
     a.direct = (uint16_t*)c->att[VXRT_ATT_DIRECT].ptr;
-    if (a.row1 <= a.row0) return VXRT_OK;
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     shade_direct_kernel<<<grid, 256, 0, c->stream>>>(a);
     VX_CUDA(cudaGetLastError());
     c->launches += 1;

@@ -16,9 +16,9 @@ VXD f3 ray_direction_at(const float* inv_view, const float* inv_proj, f2 ss) {
 VXD f2 pixel_uv(int px, int py, int W, int H) { return F2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H); }
 
 // pixel of this thread: CTA = 32x8 pixels, warp = 8x4 tile
-VXD void tile_pixel(int& px, int& py, int row0) {
+VXD void tile_pixel(int& px, int& py, int row0, int col0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    px = col0 + blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
     py = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
 }
 

@@ -19,7 +19,7 @@ struct PrimaryArgs {
     float jitter_x, jitter_y;
     int jitter_on;
     int max_iter;
-    int row0, row1;
+    int row0, row1, col0, col1;   // tile rectangle
     uint16_t* t_half;
     uint8_t* normal;
     uint8_t* block;
@@ -35,7 +35,7 @@ struct ShadowArgs {
     float halton_x, halton_y;
     int soft;
     int max_iter;
-    int row0, row1;
+    int row0, row1, col0, col1;   // tile rectangle
     const uint16_t* g_t;
     const uint8_t* g_normal;
     int gw, gh;
@@ -71,9 +71,9 @@ VXD float normal_id(f3 n) {
 }
 
 // pixel of this thread: CTA = 32x8 pixels, warp = 8x4 tile
-VXD void pixel_of_thread(int& px, int& py, int row0) {
+VXD void pixel_of_thread(int& px, int& py, int row0, int col0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    px = col0 + blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
     py = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
 }
 
@@ -81,8 +81,8 @@ template <bool STATS, bool ALPHA>
 __global__ void __launch_bounds__(256) initial_trace_kernel(GridView g, const __grid_constant__ PrimaryArgs a,
                                                             TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
-    pixel_of_thread(px, py, a.row0);
-    const bool active = px < a.width && py < a.row1;
+    pixel_of_thread(px, py, a.row0, a.col0);
+    const bool active = px < a.col1 && py < a.row1;
     LaneStats ls = {0u, 0u, 0u, 0u};
     if (active) {
         const float W = (float)a.width, H = (float)a.height;
@@ -159,8 +159,8 @@ template <bool STATS, bool ALPHA>
 __global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __grid_constant__ ShadowArgs a,
                                                            TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
-    pixel_of_thread(px, py, a.row0);
-    const bool active = px < a.width && py < a.row1;
+    pixel_of_thread(px, py, a.row0, a.col0);
+    const bool active = px < a.col1 && py < a.row1;
     LaneStats ls = {0u, 0u, 0u, 0u};
     if (active) {
         const size_t i = (size_t)py * a.width + px;
@@ -216,11 +216,6 @@ __global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __g
     if (STATS) flush_stats(stats, ls);
 }
 
-inline void tile_rows(const vxrt_tile& t, int height, int* r0, int* r1) {
-    if (t.rows <= 0) { *r0 = 0; *r1 = height; }
-    else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
-}
-
 }  // namespace
 
 // u_AlbedoTextures / SSBO 0 / u_FOV of the alpha-tested traversal.  g_K (InitialRayTraceFrag.glsl:438,
@@ -247,13 +242,13 @@ int vxrt_launch_initial_trace(vxrt_ctx* c, const vxrt_primary_params& p) {
     a.jitter_x = p.jitter[0]; a.jitter_y = p.jitter[1];
     a.jitter_on = p.jitter_on;
     a.max_iter = p.render_distance;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     a.t_half = (uint16_t*)c->att[VXRT_ATT_INITIAL_T].ptr;
     a.normal = (uint8_t*)c->att[VXRT_ATT_INITIAL_NORMAL].ptr;
     a.block = (uint8_t*)c->att[VXRT_ATT_INITIAL_BLOCK].ptr;
     a.inv_t = (float*)c->att[VXRT_ATT_INITIAL_INVT].ptr;
-    if (a.row1 <= a.row0) return VXRT_OK;
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     const AlphaCtx ax = make_alpha_ctx(c, p.inv_view, p.fov, p.width, 0);
     if (p.alpha_test) {
         if (c->stats_on) initial_trace_kernel<true, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);
@@ -279,7 +274,7 @@ int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p) {
     a.halton_x = p.halton[0]; a.halton_y = p.halton[1];
     a.soft = p.soft_shadows;
     a.max_iter = p.max_iterations;
-    tile_rows(p.tile, p.height, &a.row0, &a.row1);
+    vxrt_tile_rect(p.tile, p.width, p.height, &a.row0, &a.row1, &a.col0, &a.col1);
     const Attachment& gt = c->att[VXRT_ATT_INITIAL_T];
     const Attachment& gn = c->att[VXRT_ATT_INITIAL_NORMAL];
     a.g_t = (const uint16_t*)gt.ptr; a.g_normal = (const uint8_t*)gn.ptr;
@@ -287,8 +282,8 @@ int vxrt_launch_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params& p) {
     a.blue = c->d_blue_tex; a.bw = c->blue_w; a.bh = c->blue_h;
     a.shadow = (uint8_t*)c->att[VXRT_ATT_SHADOW].ptr;
     a.transversal = (uint16_t*)c->att[VXRT_ATT_SHADOW_TRANSVERSAL].ptr;
-    if (a.row1 <= a.row0) return VXRT_OK;
-    dim3 grid((p.width + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+    if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
+    dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     const AlphaCtx ax = make_alpha_ctx(c, p.inv_view, p.fov, p.width, 1);
     if (p.alpha_test) {
         if (c->stats_on) shadow_trace_kernel<true, true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats, ax);

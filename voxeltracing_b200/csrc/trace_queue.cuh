@@ -14,6 +14,21 @@
 #include "traverse.cuh"
 
 constexpr int VX_TRACE_CTA = 128;
+// Register allocation of the queue trace kernels.  With a bare __launch_bounds__(128) ptxas stops at 40 registers and pays for it inside
+// the loop (a spill / fill pair and the grid dimensions reloaded from the constant bank every iteration: 70 instructions per DDA
+// iteration).  Asking for ONE resident CTA lifts that target: 46 - 47 registers, no spill, 65 instructions per DDA iteration and 33
+// instead of 38 per skip iteration, 10 instead of 12 CTAs per SM.  Measured (config 4, profiles/r2_x_tocc_sweep.txt): GI 1.024 -> 1.006 ms;
+// asking for 10 / 11 / 12 CTAs (45 / 40 / 40 registers, the nudge constants then rebuilt per iteration) 1.022 / 1.030 / 1.031 ms.  Three
+// more instructions cut from the DDA path (k == 0 test moved to the skip side) changed nothing: the loop is bound by the latency of
+// its dependent chain at this occupancy as much as by issue slots.  0 = unspecified.
+#ifndef VX_TRACE_OCC
+#define VX_TRACE_OCC 1
+#endif
+#if VX_TRACE_OCC > 0
+#define VX_TRACE_BOUNDS __launch_bounds__(VX_TRACE_CTA, VX_TRACE_OCC)
+#else
+#define VX_TRACE_BOUNDS __launch_bounds__(VX_TRACE_CTA)
+#endif
 inline int trace_queue_grid(size_t n) { return (int)((n + VX_TRACE_CTA - 1) / VX_TRACE_CTA); }
 
 template <bool STATS, class Policy>

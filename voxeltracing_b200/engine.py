@@ -214,7 +214,7 @@ class Context:
         p.render_distance = render_distance
         p.alpha_test = int(alpha_test)
         p.fov = float(fov)
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         self._check(self._lib.vxrt_cuda_initial_trace(self._h, C.byref(p)))
         return p
 
@@ -231,7 +231,7 @@ class Context:
         p.alpha_test = int(alpha_test)
         p.fov = float(fov)
         p.max_iterations = max_iterations
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         self._check(self._lib.vxrt_cuda_shadow_trace(self._h, C.byref(p)))
         return p
 
@@ -334,6 +334,12 @@ class Context:
         """Queues a DMA copy of rows [row0, row0 + rows) of an attachment (rows == 0: all of it) to `dst_ptr`, the address of those
         rows in the destination: device memory here or on a peer GPU (shared_open), or page-locked host memory."""
         self._check(self._lib.vxrt_cuda_copy_attachment_rows_async(self._h, att, row0, rows, C.c_void_p(dst_ptr)))
+
+    def copy_attachment_rect_async(self, att: int, dst_image_ptr: int, tile=(0, 0, 0, 0)):
+        """The same for a rectangle tile = (row0, rows, col0, cols): `dst_image_ptr` is the address of pixel (0, 0) of the destination
+        image (same geometry as the attachment); one strided DMA copy."""
+        t = tuple(tile) + (0, 0) * (len(tuple(tile)) == 2)
+        self._check(self._lib.vxrt_cuda_copy_attachment_rect_async(self._h, att, t[0], t[1], t[2], t[3], C.c_void_p(dst_image_ptr)))
 
     # -- multi-GPU export: a buffer of this GPU that other processes' GPUs write into over NVLink --
     def shared_alloc(self, nbytes: int):

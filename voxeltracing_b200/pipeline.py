@@ -100,7 +100,7 @@ class FrameRenderer:
         _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
         p.width, p.height = self.cfg.width, self.cfg.height
         _fill(p.grass_props, self.grass); _fill(p.cactus_props, self.cactus)
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def _direct_params(self, cam, tile):
@@ -111,7 +111,7 @@ class FrameRenderer:
         c = np.float32(np.pi) * np.float32(2.2) * np.float32(0.85)  # constant sun radiance
         _fill(p.sun_color, np.array([c, c, c], np.float32)); _fill(p.moon_color, np.array([0.12, 0.14, 0.25], np.float32))
         p.texture_desat_amount, p.amplify_normal_map = 0.1, 0
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def _gi_params(self, cam, frame, tile):
@@ -126,7 +126,7 @@ class FrameRenderer:
         _fill(p.sun_direction, self.sun); _fill(p.moon_direction, self.moon)
         p.sun_visibility, p.gi_sun_strength, p.gi_sky_strength, p.diffuse_light_intensity = self.sun_visibility, 1.0, 1.125, 1.25
         _fill(p.viewer_position, cam.position)
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def _reflection_params(self, cam, frame, tile):
@@ -144,14 +144,14 @@ class FrameRenderer:
         _fill(p.viewer_position, cam.position)
         p.sun_strength_modifier, p.moon_strength_modifier = 0.85, 1.0
         _fill(p.grass_props, self.grass)
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def _primary_params(self, cam, tile):
         p = abi.PrimaryParams()
         _fill(p.inv_view, cam.inv_view); _fill(p.inv_projection, cam.inv_projection)
         p.width, p.height, p.render_distance = self.cfg.width, self.cfg.height, self.cfg.render_distance
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def _shadow_params(self, cam, frame, tile):
@@ -160,7 +160,7 @@ class FrameRenderer:
         p.width, p.height = self.cfg.width, self.cfg.height
         _fill(p.light_direction, self.light)
         p.current_frame, p.soft_shadows, p.max_iterations = frame, int(self.cfg.soft_shadows), self.cfg.shadow_iterations
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         return p
 
     def params_for(self, name: str, cam, frame: int = 0, tile=(0, 0)):
@@ -252,19 +252,19 @@ class SvgfChain:
             _fill(pp.inv_view, cam.inv_view); _fill(pp.inv_projection, cam.inv_projection)
             pp.width, pp.height, pp.in_set = self.width, self.height, abi.ATT_GI_SH
             pp.time = frame / 60.0 if time is None else time
-            pp.tile.row0, pp.tile.rows = tile
+            abi.set_tile(pp.tile, tile)
             out.append(("prespatial", lib.vxrt_cuda_svgf_prespatial, pp))
         tp = abi.SvgfTemporalParams()
         _fill(tp.inv_view, cam.inv_view); _fill(tp.inv_projection, cam.inv_projection)
         _fill(tp.prev_view, prev.view); _fill(tp.prev_projection, prev.projection)
         tp.width, tp.height, tp.history_set, tp.out_set, tp.be_useful = self.width, self.height, hist_t, cur_t, 1
         tp.in_set = abi.ATT_SVGF_PRESPATIAL if self.pre_spatial else abi.ATT_GI_SH
-        tp.tile.row0, tp.tile.rows = tile
+        abi.set_tile(tp.tile, tile)
         out.append(("temporal", lib.vxrt_cuda_svgf_temporal, tp))
         vp = abi.SvgfVarianceParams()
         _fill(vp.inv_view, cam.inv_view); _fill(vp.inv_projection, cam.inv_projection)
         vp.width, vp.height, vp.in_set, vp.do_spatial, vp.aggressive_disocclusion = self.width, self.height, cur_t, 1, int(self.aggressive)
-        vp.tile.row0, vp.tile.rows = tile
+        abi.set_tile(vp.tile, tile)
         out.append(("variance", lib.vxrt_cuda_svgf_variance, vp))
         for i, step in enumerate(self.STEPS):
             cur = abi.ATT_SVGF_DENOISE_A if i % 2 == 0 else abi.ATT_SVGF_DENOISE_B
@@ -276,7 +276,7 @@ class SvgfChain:
             sp.large_kernel, sp.do_spatial, sp.aggressive_disocclusion = int(self.large_kernel), 1, int(self.aggressive)
             sp.color_phi_bias, sp.resolution_scale = self.color_phi_bias, self.resolution_scale
             sp.time = frame / 60.0 if time is None else time
-            sp.tile.row0, sp.tile.rows = tile
+            abi.set_tile(sp.tile, tile)
             out.append((f"spatial{i}", lib.vxrt_cuda_svgf_spatial, sp))
         return out
 
@@ -317,11 +317,11 @@ class ShadowDenoiser:
         _fill(tp.inv_view, cam.inv_view); _fill(tp.inv_projection, cam.inv_projection)
         _fill(tp.prev_view, prev.view); _fill(tp.prev_projection, prev.projection)
         tp.width, tp.height, tp.history_set, tp.out_set, tp.shadow_temporal = self.width, self.height, hist, out, 1
-        tp.tile.row0, tp.tile.rows = tile
+        abi.set_tile(tp.tile, tile)
         fp = abi.ShadowFilterParams()
         _fill(fp.inv_view, cam.inv_view); _fill(fp.inv_projection, cam.inv_projection)
         fp.width, fp.height, fp.in_set, fp.filter_scale = self.width, self.height, out, self.filter_scale
-        fp.tile.row0, fp.tile.rows = tile
+        abi.set_tile(fp.tile, tile)
         return [("temporal", lib.vxrt_cuda_shadow_temporal, tp), ("filter", lib.vxrt_cuda_shadow_filter, fp)]
 
     def submit(self, prepared, hook=None):
@@ -368,7 +368,7 @@ class ReflectionTemporal:
         for k, v in {"temporal_spec": 1, "firefly_rejection": 1, "aggressive_firefly_rejection": 1, "smart_clip": 1, "roughness_weight": 1,
                      "stabilize_hit_distance": 1, **flags}.items():
             setattr(p, k, int(v))
-        p.tile.row0, p.tile.rows = tile
+        abi.set_tile(p.tile, tile)
         self.out_set = out
         passes = [("temporal", lib.vxrt_cuda_specular_temporal, p)]
         if self.denoise:   # x then y pass of ReflectionDenoiserNew.glsl (Pipeline.cpp:3404-3560)
@@ -381,7 +381,7 @@ class ReflectionTemporal:
                 d.roughness_bias = d.normal_map_aware = d.handle_lobe_deviation = d.amplify_transversal_weight = 1
                 d.temporal_weight, d.derive_from_diffuse_sh, d.radius_bias = int(bool(p.temporal_spec)), 0, 0
                 d.normal_map_weight_strength, d.denoiser_scale, d.resolution_scale, d.roughness_normal_weight_bias_strength = 0.75, 1.0, self.resolution_scale, 1.075
-                d.tile.row0, d.tile.rows = tile
+                abi.set_tile(d.tile, tile)
                 passes.append((name, lib.vxrt_cuda_reflection_denoise, d))
         return passes
 
