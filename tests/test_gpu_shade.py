@@ -315,12 +315,14 @@ def test_fused_final_gi_kernel_is_bit_identical(request, inputs, world, pos, fra
     atts = (abi.ATT_GI_SH, abi.ATT_GI_COCG, abi.ATT_GI_UTILITY, abi.ATT_GI_AOSKY)
     res = []
     try:
-        for wavefront, fuse in ((1, 1), (1, 0), (0, 0)):
-            c.set_option("wavefront", wavefront); c.set_option("gi_fuse_final", fuse)
-            c.diffuse_trace(ip)
-            res.append([c.read_attachment(a).copy() for a in atts])
+        # the default pipeline (shadow-queue trace on a side stream beside the bounce trace) first, then each simplification undone
+        for wavefront, fuse, overlap in ((1, 1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, 0, 0)):
+            c.set_option("wavefront", wavefront); c.set_option("gi_fuse_final", fuse); c.set_option("gi_overlap", overlap)
+            for _ in range(2 if overlap else 1):   # twice: a race between the two streams would not repeat itself
+                c.diffuse_trace(ip)
+                res.append([c.read_attachment(a).copy() for a in atts])
     finally:
-        c.set_option("wavefront", 1); c.set_option("gi_fuse_final", 1)
+        c.set_option("wavefront", 1); c.set_option("gi_fuse_final", 1); c.set_option("gi_overlap", 1)
     for other in res[1:]:
         for a, b in zip(res[0], other):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8))

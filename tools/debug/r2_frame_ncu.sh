@@ -4,7 +4,8 @@ mkdir -p gpurun_out
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct
 tag=${1:-w}
 shift
-ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r2_${tag}_frame_ncu.csv python tools/debug/one_frame.py config4_1080p_gi 2 "$@" > /dev/null 2>&1
+wl=${WORKLOAD:-config4_1080p_gi}
+ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r2_${tag}_frame_ncu.csv python tools/debug/one_frame.py $wl 2 "$@" > /dev/null 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open("gpurun_out/r2_${tag}_frame_ncu.csv")) if len(r)>10]

@@ -182,6 +182,9 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
     for (cudaEvent_t e : c->probe_ev) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+    if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->copies_joined) cudaEventDestroy(c->copies_joined);
     for (int i = 0; i < VXRT_ATT_COUNT; ++i) {
         if (c->att_ready[i]) cudaEventDestroy(c->att_ready[i]);
@@ -217,6 +220,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
         return VXRT_OK;
     }
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "gi_overlap")) { c->gi_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "trace_spill")) { c->trace_spill = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }

@@ -83,6 +83,11 @@ struct vxrt_ctx {
     size_t wf_cap = 0;
     bool wavefront = true;  // VXRT_WAVEFRONT=0 selects the one-thread-per-pixel GI / reflection kernels
     float filter_snap = 0.0f;   // tolerance mode of the screen-space filters (filter_sampler.cuh); set_option "filter_snap" in units of 1 / 65536
+    // GI wavefront: the shadow-queue trace of a bounce runs on a side stream beside the bounce-ray trace (both consume queues shade<0> wrote,
+    // neither reads what the other writes); set_option "gi_overlap", on by default, off while the probe brackets the path-ray kernel
+    bool gi_overlap = true;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     bool gi_fuse_final = true;  // last sample's shade<2> fused with resolve (set_option "gi_fuse_final"; 0 = the separate kernels)
 
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)

@@ -477,26 +477,43 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
         else wf_trace_paths_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, list, cnt, (int)n, iters, c->d_stats + 1);   \
         if (e0 && e1) cudaEventRecord(e1, s);                                                                             \
     } while (0)
-#define TRACE_SHADOW()                                                                                                    \
+#define TRACE_SHADOW(ss)                                                                                                  \
     do {                                                                                                                  \
-        if (c->trace_caps | c->trace_spill) {                                                                                              \
+        if (c->trace_caps | c->trace_spill) {                                                                             \
             const ShadowRays pol = {w, light};                                                                            \
             const int rc_ = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);         \
             if (rc_ != VXRT_OK) return rc_;                                                                               \
             c->launches -= 1;                                                                                             \
-        } else if (st) wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);       \
-        else wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, light, a.shadow_trace_length, c->d_stats);         \
+        } else if (st) wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, ss>>>(g, w, light, a.shadow_trace_length, c->d_stats);      \
+        else wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, ss>>>(g, w, light, a.shadow_trace_length, c->d_stats);        \
     } while (0)
+    // the shadow-queue trace of bounce 0 beside the bounce-ray trace: both read queues shade<0> has written, the first writes shadowRes,
+    // the second hitT / hitInfo; shade<1> needs both (the capped / hand-over variants keep their continuation storage on c->stream)
+    const bool overlap = c->gi_overlap && !c->probe_on && !(c->trace_caps | c->trace_spill);
+    if (overlap && !c->aux_stream) {
+        VX_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        VX_CUDA(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+        VX_CUDA(cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
+    }
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), s));
         gi_wf_gen_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);
         TRACE_PATHS(nullptr, nullptr, a.trace_length);
         gi_wf_shade_kernel<0><<<pgrid, 256, 0, s>>>(a, w, sample);
-        TRACE_SHADOW();
-        TRACE_PATHS(w.qBounce, w.counters + 1, a.trace_length);
+        if (overlap) {
+            VX_CUDA(cudaEventRecord(c->aux_fork, s));
+            VX_CUDA(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
+            TRACE_SHADOW(c->aux_stream);
+            VX_CUDA(cudaEventRecord(c->aux_join, c->aux_stream));
+            TRACE_PATHS(w.qBounce, w.counters + 1, a.trace_length);
+            VX_CUDA(cudaStreamWaitEvent(s, c->aux_join, 0));
+        } else {
+            TRACE_SHADOW(s);
+            TRACE_PATHS(w.qBounce, w.counters + 1, a.trace_length);
+        }
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         gi_wf_shade_kernel<1><<<pgrid, 256, 0, s>>>(a, w, sample);
-        TRACE_SHADOW();
+        TRACE_SHADOW(s);
         if (sample + 1 < max_spp || !c->gi_fuse_final) gi_wf_shade_kernel<2><<<pgrid, 256, 0, s>>>(a, w, sample);
         else gi_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);   // the last sample's shade<2> + resolve in one pass
         c->launches += 8;
