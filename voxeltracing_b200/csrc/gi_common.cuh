@@ -43,7 +43,7 @@ VXD f3 cos_weighted_hemisphere(const GiArgs& a, GiState& st, f3 n) {
     return normalize(rr);
 }
 // InverseSchlick / DiffuseHammon (:1391-1418)
-VXD float inverse_schlick(float f0, float VoH) { return 1.0f - gclamp(f0 + (1.0f - f0) * powf(1.0f - VoH, 5.0f), 0.0f, 1.0f); }
+VXD float inverse_schlick(float f0, float VoH) { return 1.0f - gclamp(f0 + (1.0f - f0) * pow5_mul(1.0f - VoH), 0.0f, 1.0f); }
 VXD float diffuse_hammon(f3 normal, f3 viewDir, f3 lightDir, float roughness) {
     float nDotL = gmax(dot(normal, lightDir), 0.0f);
     if (nDotL <= 0.0f) return 0.0f;

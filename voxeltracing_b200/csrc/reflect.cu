@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) reflection_trace_kernel(GridView g, const
                         const f3 Albedo = xyz(texarray_sample(a.tex[VXRT_TEX_ALBEDO], UV.x, UV.y, ids.x, 0.0f));
                         const f3 Radiance = MIXED * 0.6f;
                         const f4 SampledPBR = texarray_sample(a.tex[VXRT_TEX_PBR], UV.x, UV.y, ids.z, 0.0f);
-                        const float AO = powf(SampledPBR.w, 2.0f);
+                        const float AO = pow2_mul(SampledPBR.w);
                         const bool PlayerInShadow = get_player_intersect(viewer, HitPosition + Normal * 0.035f, strong);
                         if (ShadowItr < (SPP / 4 > 1 ? SPP / 4 : 1)) {
                             if (!PlayerInShadow) {

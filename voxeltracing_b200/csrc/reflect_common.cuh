@@ -160,7 +160,7 @@ VXD f3 derive_specular_from_diffuse_sh(f4 SHy, f3 IndirectDiffuse, f3 Eye, f3 No
     } else {
         f3 q = IncomingDir / (IncomingLen + 0.00001f);
         IncomingDir = F3(gmix(RawSpecularDir.x, q.x, Directionality), gmix(RawSpecularDir.y, q.y, Directionality), gmix(RawSpecularDir.z, q.z, Directionality));
-        Scale = powf(Roughness + 1.0f, 3.0f);
+        Scale = pow3_mul(Roughness + 1.0f);
     }
     float Sp = specular_ggx(Eye, IncomingDir, Normal, gmax(Roughness, 0.39f), 0.0f);
     f3 Integrated = powf(Sp, 1.2f) * IndirectDiffuse * 18.0f * Scale;
@@ -205,7 +205,7 @@ VXD f3 rf_directional_light(f3 viewer, f3 world_pos, f3 light_dir, f3 radiance, 
     f3 Lh = normalize(Li + Lo);
     float cosLi = gmax(0.0f, dot(N, Li));
     float cosLh = gmax(0.0f, dot(N, Lh));
-    float fc = powf(1.0f - gmax(0.0f, dot(Lh, Lo)), 5.0f);
+    float fc = pow5_mul(1.0f - gmax(0.0f, dot(Lh, Lo)));
     f3 F = F0 + (F3(1.0f) - F0) * fc;
     float D = ndf_ggx(cosLh, pbr.x);
     float G = ga_schlick_ggx(cosLi, cosLo, pbr.x);

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
             const f3 Albedo = xyz(texarray_sample(a.tex[VXRT_TEX_ALBEDO], UV.x, UV.y, ids.x, 0.0f));
             const f3 Radiance = F3(a.color_mixed[0], a.color_mixed[1], a.color_mixed[2]) * 0.6f;
             const f4 SampledPBR = texarray_sample(a.tex[VXRT_TEX_PBR], UV.x, UV.y, ids.z, 0.0f);
-            const float AO = powf(SampledPBR.w, 2.0f);
+            const float AO = pow2_mul(SampledPBR.w);
             const bool PlayerInShadow = get_player_intersect(viewer, HitPosition + Normal * 0.035f, strong);
             float from_ray = 0.0f;
             if (cnt.x < (SPP / 4 > 1 ? SPP / 4 : 1)) {

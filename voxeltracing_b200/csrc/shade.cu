@@ -84,7 +84,7 @@ struct DirectArgs {
 // FresnelSchlickRoughness (ColorPassFrag.glsl:1206-1210)
 VXD f3 fresnel_schlick_roughness(f3 Eye, f3 norm, f3 F0, float roughness) {
     float cosTheta = gclamp(dot(Eye, norm), 0.00001f, 1.0f);
-    float pw = powf(1.0f - cosTheta, 5.0f);
+    float pw = pow5_mul(1.0f - cosTheta);
     f3 m = F3(gmax(1.0f - roughness, F0.x), gmax(1.0f - roughness, F0.y), gmax(1.0f - roughness, F0.z));
     return F0 + (m - F0) * pw;
 }

@@ -74,7 +74,20 @@ VXD int cvt_floor(float x) { return __float2int_rd(x); }  // saturating, NaN -> 
 VXD int cvt_trunc(float x) { return __float2int_rz(x); }
 VXD int cvt_round(float x) { return __float2int_rn(x); }   // half-even
 
-VXD float unorm8_to_float(int k) { return (float)k / 255.0f; }
+// float(k) / 255.0f for a byte k, bit for bit, without the division sequence: q = k * RN(1 / 255) is within an ulp, one residual step with
+// two FMAs lands on the correctly rounded quotient (checked for all 256 codes with exact rational arithmetic; k and 255 are exact floats).
+// The screen-space samplers convert 4 - 16 bytes per tap; ncu's source view put 4.5 % of shade_direct_kernel's instructions on the division.
+VXD float unorm8_to_float(int k) {
+    const float fk = (float)k, c = 1.0f / 255.0f;
+    const float q = fk * c;
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, fk), c, q);
+}
+// pow(x, n) for the integer exponents the shaders write (Schlick's (1 - c)^5 and friends) by multiplication: 1 - 3 roundings, i.e. within
+// the 2 ulp of CUDA's powf that DESIGN.md 4 already states for this family, at 3 instructions instead of ~100 (ncu source view: 14.7 % of
+// gi_wf_shade_kernel's instructions were powf(x, 5.0f) inside inverse_schlick).  x * x is the correctly rounded pow(x, 2).
+VXD float pow2_mul(float x) { return x * x; }
+VXD float pow3_mul(float x) { return (x * x) * x; }
+VXD float pow5_mul(float x) { const float x2 = x * x; return (x2 * x2) * x; }
 VXD uint8_t float_to_unorm8(float f) {
     if (!(f > 0.0f)) return 0;
     if (f >= 1.0f) return 255;
@@ -83,4 +96,10 @@ VXD uint8_t float_to_unorm8(float f) {
 VXD uint16_t float_to_half_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
 VXD float half_bits_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
-VXD int wrap_repeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+// GL_REPEAT on a texel index.  Almost every index is already inside [0, n) (the taps of a tile straddle the image edge only on its border), and
+// `%` by a run-time n is ~20 instructions: 10 - 17 % of the shading kernels' instructions in ncu's source view.  One unsigned compare decides.
+VXD int wrap_repeat(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
