@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pass-overlap", action="store_true", help="issue every pass on one stream (round 1 / early round 2 behaviour)")
     ap.add_argument("--profile", action="store_true", help="only warm-up + steps of the plain step (for ncu)")
     ap.add_argument("--tex-size", type=int, default=512)
     ap.add_argument("--no-svgf", action="store_true", help="skip the SVGF denoiser-chain measurement")
@@ -692,6 +693,10 @@ def main():
         rays_per_step.append(acc[0])
     probe_stats = ctx.probe_read(reset=True)   # rays / iterations of the probed kernel's launches alone
     ctx.stats_enable(False)
+    ctx.set_option("probe", 0)
+    # pass-level concurrency (vxrt_cuda_set_option "pass_overlap"): shadow / reflection / direct passes on the context's second stream beside the GI
+    # wavefront; FrameRenderer.submit joins the lanes at the end of the frame, so the step events below bracket all of it
+    ctx.set_option("pass_overlap", 0 if args.no_pass_overlap else 1)
     total_rays = int(sum(rays_per_step))
     total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
 
@@ -812,12 +817,11 @@ def main():
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ctx.probe_read(reset=True)
     launches_before = ctx.launch_count
     for i in range(args.steps):
         flush_buf.zero_()
         step_ev[i][0].record(stream)
-        step(args.warmup + i, make_hook(i))
+        step(args.warmup + i)
         step_ev[i][1].record(stream)
     tail = ev()
     if push:
@@ -836,9 +840,22 @@ def main():
         torch.cuda.synchronize()
         ms += max(0.0, step_ev[-1][1].elapsed_time(tail))
     launches = ctx.launch_count - launches_before
-    probe_time = ctx.probe_read(reset=True)    # summed CUDA-event time of the probed kernel inside the timed region
-    ctx.set_option("probe", 0)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- the same K steps once more, serialised, for what cannot be read off overlapping kernels: per-pass times (event pairs around each
+    # pass) and the launch durations of the dominant kernel (the library's probe: an event pair around every launch of the GI path-ray trace
+    # kernel on its own stream).  The probe switches the pass-level and the in-GI overlap off, so each kernel runs alone, as under ncu. ----
+    ctx.set_option("probe", 1)
+    ctx.probe_read(reset=True)
+    for i in range(args.steps):
+        flush_buf.zero_()
+        step(args.warmup + i, make_hook(i))
+    if push:
+        ctx.join_reads()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    probe_time = ctx.probe_read(reset=True)    # summed CUDA-event time of the probed kernel over these K steps
+    ctx.set_option("probe", 0)
     pass_ms = {p_: float(np.mean([sum(strip[p_][0].elapsed_time(strip[p_][1]) for strip in pe) for pe in pass_ev])) for p_ in cfg.passes}
 
     # ---- did rank 0 receive what was sent?  (outside the timed region) position-weighted checksums of every exported attachment
@@ -1229,7 +1246,11 @@ def main():
             "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)), "of": "rank 0's K timed steps"},
             "parity_check": parity["status"] if parity else None, "parity": parity,
             "gather_check": gather_check,
+            "pass_overlap": not args.no_pass_overlap,
             "pass_ms": pass_ms,
+            "pass_ms_note": "passes timed one after the other in K extra steps after the timed region (CUDA-event pairs around each pass, pass-level overlap "
+                            "off); with pass_overlap the timed step is shorter than their sum because shadow / reflection / direct run beside the GI wavefront",
+            "pass_ms_sum": float(sum(pass_ms.values())),
             "pass_ms_last_rank": all_pass_ms[-1] if world_size > 1 else None,
             "pass_mrays": {p: pass_stats[p]["rays"] / args.steps / (pass_ms[p] * 1e-3) / 1e6 for p in trace_passes},
             "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -1239,6 +1260,8 @@ def main():
                          "l2_gather_achieved": sector_bytes / (k_ms * 1e-3) / 1e9, "l2_gather_peak": gather_peak_gbs,
                          "l2_gather_frac": sector_bytes / (k_ms * 1e-3) / 1e9 / gather_peak_gbs,
                          "mean_iterations_per_ray": S, "rays_per_launch": k_rays, "avg_launch_ms": k_ms,
+                         "timing": "CUDA-event pair around every launch of the kernel on its own stream (the library's probe), live in this run, over the K steps "
+                                   "repeated serialised right after the timed region (overlapping kernels have no launch duration of their own)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_mrays": k_rays / (k_ms * 1e-3) / 1e6,
                          "l2_gather": {"achieved": sector_bytes / (k_ms * 1e-3) / 1e9, "peak": gather_peak_gbs, "unit": "GB/s",

@@ -68,3 +68,39 @@ def test_benched_configuration_matches_the_oracle_on_a_band(workload, frame, inp
             assert np.array_equal(got[r0:r1, c0:c0 + cw].view(np.uint8), full[a][r0:r1, c0:c0 + cw].view(np.uint8)), (workload, a, "rect")
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("workload,reproject", [("config4_1080p_gi", False), ("config4_1080p_gi", True), ("config5_4k_gi4", False)])
+def test_pass_overlap_does_not_change_a_bit(workload, reproject, inputs512):
+    """set_option("pass_overlap", 1): the sun-shadow trace and the direct term on the context's second stream beside the GI / reflection wavefronts.
+    Every output attachment of the frame equals the single-stream frame bit for bit - with and without reprojection in the reflection pass, with a
+    read-back queued in the middle of the frame (the push hooks of the multi-GPU bench), and across frames (the next frame's primary pass
+    overwrites what lane 1 was reading)."""
+    import dataclasses
+    wl, blocks, inputs, ctx, fr = _setup(workload, inputs512)
+    try:
+        if reproject:
+            fr.cfg = dataclasses.replace(fr.cfg, refl_reproject=True)
+        frames = (3, 4, 5)
+
+        def run(overlap, mid_frame_read):
+            ctx.set_option("pass_overlap", overlap)
+            out = []
+            for f in frames:
+                sink = {}
+
+                def hook(name, where):
+                    if mid_frame_read and where == "end" and name == "gi":
+                        sink["gi"] = ctx.read_attachment(abi.ATT_GI_SH).copy()
+                fr.render(bench.camera_for(wl, f), f, hook=hook)
+                out.append({a: ctx.read_attachment(a).copy() for a in fr.outputs})
+            return out
+        want = run(0, False)
+        for mid in (False, True):
+            got = run(1, mid)
+            for fw, fg in zip(want, got):
+                for a in fr.outputs:
+                    assert np.array_equal(fw[a].view(np.uint8), fg[a].view(np.uint8)), (workload, reproject, mid, a)
+    finally:
+        ctx.set_option("pass_overlap", 0)
+        ctx.close()

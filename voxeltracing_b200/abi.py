@@ -259,6 +259,7 @@ def load_cuda() -> C.CDLL:
         "vxrt_cuda_read_attachment_async": (C.c_int, [vp, i32, vp, sz]),
         "vxrt_cuda_wait_reads": (C.c_int, [vp]),
         "vxrt_cuda_join_reads": (C.c_int, [vp]),
+        "vxrt_cuda_join_passes": (C.c_int, [vp]),
         "vxrt_cuda_copy_attachment_rows_async": (C.c_int, [vp, i32, i32, i32, vp]),
         "vxrt_cuda_copy_attachment_rect_async": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
         "vxrt_cuda_shared_alloc": (C.c_int, [vp, sz, C.POINTER(vp), vp]),

@@ -39,9 +39,62 @@ struct DeviceGuard {
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
-#define REQUIRE_CTX(c)                                                          \
+// lane 1 of the pass-level concurrency (ctx.h): `stream` waits for everything queued there
+static int vxrt_join_lane1(vxrt_ctx* c, bool keep_fork) {
+    if (c->lane1_pending) {
+        VX_CUDA(cudaStreamWaitEvent(c->stream, c->lane1_tail, 0));
+        c->lane1_pending = false;
+    }
+    if (!keep_fork) c->gi_fork_valid = false;
+    return VXRT_OK;
+}
+// Every entry point joins lane 1 first, except the ray passes that know about the lanes (REQUIRE_CTX_LANES).  Calls that only read what
+// passes have produced (read-backs, copies, statistics) keep the frame's fork point (REQUIRE_CTX_READER): a lane-1 pass issued after them
+// still waits only for what preceded the GI.  Anything else may produce inputs of a later lane-1 pass, so it drops the fork point and
+// that pass waits for everything queued on lane 0.
+#define REQUIRE_CTX_LANES(c)                                                    \
     if (!(c)) return vxrt_fail(VXRT_E_INVALID, "%s: ctx is NULL", __func__);    \
     DeviceGuard _device_guard((c)->device)
+#define REQUIRE_CTX(c)                                                          \
+    REQUIRE_CTX_LANES(c);                                                       \
+    if ((c)->lane1_pending || (c)->gi_fork_valid) { if (int _jrc = vxrt_join_lane1(c, false)) return _jrc; }
+#define REQUIRE_CTX_READER(c)                                                   \
+    REQUIRE_CTX_LANES(c);                                                       \
+    if ((c)->lane1_pending) { if (int _jrc = vxrt_join_lane1(c, true)) return _jrc; }
+
+static bool lanes_on(const vxrt_ctx* c) { return c->pass_overlap && !c->probe_on && !(c->trace_caps | c->trace_spill); }
+static int ensure_lanes(vxrt_ctx* c) {
+    if (c->lane1) return VXRT_OK;
+    VX_CUDA(cudaStreamCreateWithFlags(&c->lane1, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->gi_fork, &c->lane0_mark, &c->lane1_tail}) VX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return VXRT_OK;
+}
+// a lane-1 pass (sun-shadow trace, direct term): waits for what lane 0 had queued before the frame's diffuse_trace (or for everything, if there
+// was none), runs with c->stream swapped, leaves its tail event behind
+struct Lane1Pass {
+    vxrt_ctx* c; cudaStream_t saved; bool on;
+    explicit Lane1Pass(vxrt_ctx* c_) : c(c_), saved(c_->stream), on(lanes_on(c_)) {}
+    int begin() {
+        if (!on) return VXRT_OK;
+        if (int rc = ensure_lanes(c)) return rc;
+        if (c->gi_fork_valid) {
+            VX_CUDA(cudaStreamWaitEvent(c->lane1, c->gi_fork, 0));
+        } else {
+            VX_CUDA(cudaEventRecord(c->lane0_mark, c->stream));
+            VX_CUDA(cudaStreamWaitEvent(c->lane1, c->lane0_mark, 0));
+        }
+        c->stream = c->lane1;
+        return VXRT_OK;
+    }
+    int end(int rc) {
+        if (!on || c->stream != c->lane1) return rc;
+        c->stream = saved;
+        const cudaError_t e = cudaEventRecord(c->lane1_tail, c->lane1);
+        c->lane1_pending = true;
+        if (rc == VXRT_OK && e != cudaSuccess) return vxrt_check_cuda(e, "cudaEventRecord(lane1_tail)");
+        return rc;
+    }
+};
 #define REQUIRE_PTR(p) \
     if (!(p)) return vxrt_fail(VXRT_E_INVALID, "%s: %s is NULL", __func__, #p)
 
@@ -183,6 +236,8 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     for (cudaEvent_t e : c->probe_ev) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->lane1) { cudaStreamSynchronize(c->lane1); cudaStreamDestroy(c->lane1); }
+    for (cudaEvent_t e : {c->gi_fork, c->lane0_mark, c->lane1_tail}) if (e) cudaEventDestroy(e);
     if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->copies_joined) cudaEventDestroy(c->copies_joined);
@@ -204,7 +259,7 @@ int vxrt_cuda_set_stream(vxrt_ctx* c, void* s) {
     return vxrt_apply_l2_policy(c);
 }
 int vxrt_cuda_synchronize(vxrt_ctx* c) {
-    REQUIRE_CTX(c);
+    REQUIRE_CTX_READER(c);
     VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
@@ -221,6 +276,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     }
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "gi_overlap")) { c->gi_overlap = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "pass_overlap")) { c->pass_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "trace_spill")) { c->trace_spill = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }
@@ -395,7 +451,7 @@ int vxrt_cuda_set_blue_noise_texture(vxrt_ctx* c, const uint8_t* rgba, int32_t w
 }
 
 int vxrt_cuda_read_attachment(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
-    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -416,7 +472,7 @@ int vxrt_cuda_write_attachment(vxrt_ctx* c, int32_t id, int32_t width, int32_t h
     return VXRT_OK;
 }
 int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
-    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -435,7 +491,7 @@ int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t b
     return VXRT_OK;
 }
 int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, void* dst) {
-    REQUIRE_CTX(c); REQUIRE_PTR(dst);
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -455,7 +511,7 @@ int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* c, int32_t id, int32_t row0, 
     return VXRT_OK;
 }
 int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, int32_t col0, int32_t cols, void* dst_image) {
-    REQUIRE_CTX(c); REQUIRE_PTR(dst_image);
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst_image);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -510,7 +566,7 @@ int vxrt_cuda_shared_close(vxrt_ctx* c, void* dev_ptr) {
     return VXRT_OK;
 }
 int vxrt_cuda_join_reads(vxrt_ctx* c) {
-    REQUIRE_CTX(c);
+    REQUIRE_CTX_READER(c);
     if (!c->copy_stream) return VXRT_OK;
     if (!c->copies_joined) VX_CUDA(cudaEventCreateWithFlags(&c->copies_joined, cudaEventDisableTiming));
     VX_CUDA(cudaEventRecord(c->copies_joined, c->copy_stream));
@@ -518,7 +574,7 @@ int vxrt_cuda_join_reads(vxrt_ctx* c) {
     return VXRT_OK;
 }
 int vxrt_cuda_wait_reads(vxrt_ctx* c) {
-    REQUIRE_CTX(c);
+    REQUIRE_CTX_READER(c);
     if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
     return VXRT_OK;
 }
@@ -543,7 +599,7 @@ int vxrt_cuda_bind_attachment(vxrt_ctx* c, int32_t id, void* dev_ptr, size_t cap
     return VXRT_OK;
 }
 int vxrt_cuda_attachment_device(vxrt_ctx* c, int32_t id, void** p, int32_t* w, int32_t* h, int32_t* bpp) {
-    REQUIRE_CTX(c);
+    REQUIRE_CTX_READER(c);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -627,7 +683,7 @@ int vxrt_cuda_raycast_detect(vxrt_ctx* c, const float* positions, const float* d
 }
 
 int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
-    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "shadow_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
@@ -638,7 +694,9 @@ int vxrt_cuda_shadow_trace(vxrt_ctx* c, const vxrt_shadow_params* p) {
         return vxrt_fail(VXRT_E_STATE, "shadow_trace consumes the primary G-buffer: run initial_trace first");
     if (p->soft_shadows && !c->d_blue_tex) return vxrt_fail(VXRT_E_STATE, "soft shadows need set_blue_noise_texture");
     if (p->max_iterations < 0) return vxrt_fail(VXRT_E_INVALID, "max_iterations < 0");
-    return vxrt_launch_shadow_trace(c, *p);
+    Lane1Pass lane(c);
+    if ((rc = lane.begin())) return rc;
+    return lane.end(vxrt_launch_shadow_trace(c, *p));
 }
 
 int vxrt_cuda_set_texture_array(vxrt_ctx* c, int32_t kind, int32_t layers, int32_t w, int32_t h, const uint8_t* rgba8) {
@@ -676,16 +734,20 @@ int vxrt_cuda_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params* p) {
     return vxrt_launch_generate_gbuffer(c, *p);
 }
 int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
-    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_INVT, "vxrt_cuda_initial_trace"))) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_ALBEDO, "vxrt_cuda_generate_gbuffer"))) return rc;
     if ((rc = require_att(c, __func__, c->shadow_source, c->shadow_source == VXRT_ATT_SHADOW ? "vxrt_cuda_shadow_trace" : "the shadow denoiser"))) return rc;
-    return vxrt_launch_shade_direct(c, *p);
+    Lane1Pass lane(c);
+    if ((rc = lane.begin())) return rc;
+    return lane.end(vxrt_launch_shade_direct(c, *p));
 }
 int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
-    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
+    // lane 0.  The GI reads the primary G-buffer and writes the GI attachments and its own arena only, none of which lane 1 touches: no join
+    if (c->lane1_pending && !lanes_on(c)) { if (int jrc = vxrt_join_lane1(c, false)) return jrc; }
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
@@ -695,6 +757,12 @@ int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
     if (!c->sky.data) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs vxrt_cuda_set_skymap");
     if (!p->use_blue_noise) return vxrt_fail(VXRT_E_UNSUPPORTED, "the fract(sin()) hash RNG (u_UseBlueNoise = false) is not portable and not implemented");
     if (p->spp < 1 || p->trace_length < 0 || p->shadow_trace_length < 0) return vxrt_fail(VXRT_E_INVALID, "diffuse_trace: bad spp / trace length");
+    if (lanes_on(c)) {
+        if ((rc = ensure_lanes(c))) return rc;
+        if (!c->gi_fork_valid) { VX_CUDA(cudaEventRecord(c->gi_fork, c->stream)); c->gi_fork_valid = true; }   // what lane-1 passes of this frame wait for
+        rc = vxrt_launch_diffuse_trace(c, *p);
+        return rc;
+    }
     return vxrt_launch_diffuse_trace(c, *p);
 }
 int vxrt_cuda_svgf_temporal(vxrt_ctx* c, const vxrt_svgf_temporal_params* p) {
@@ -761,7 +829,9 @@ int vxrt_cuda_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params* p) {
     return vxrt_launch_shadow_filter(c, *p);
 }
 int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
-    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    // lane 0, after the GI whose SH attachments are its ambient base (ReflectionTraceFrag.glsl main(): SHToIrridiance of u_DiffuseSHy); it reads the
+    // sun shadow of lane 1, so it joins - keeping the frame's fork point, the direct term that follows may run beside it
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(p);
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
@@ -777,13 +847,17 @@ int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
     return vxrt_launch_reflection_trace(c, *p);
 }
 
+int vxrt_cuda_join_passes(vxrt_ctx* c) {
+    REQUIRE_CTX(c);   // the join itself
+    return VXRT_OK;
+}
 int vxrt_cuda_stats_enable(vxrt_ctx* c, int32_t on) {
     REQUIRE_CTX(c);
     c->stats_on = on != 0;
     return VXRT_OK;
 }
 int vxrt_cuda_stats_read(vxrt_ctx* c, vxrt_trace_stats* out, int32_t reset) {
-    REQUIRE_CTX(c); REQUIRE_PTR(out);
+    REQUIRE_CTX_READER(c); REQUIRE_PTR(out);
     TraceStatsDev h[2];
     VX_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
@@ -998,7 +1072,7 @@ int vxrt_cuda_gather_peak(vxrt_ctx* c, int32_t rounds, double* sectors_per_secon
     return vxrt_launch_gather_peak(c, rounds, sectors_per_second);
 }
 int vxrt_cuda_probe_read(vxrt_ctx* c, double* total_ms, int64_t* launches, vxrt_trace_stats* stats, int32_t reset) {
-    REQUIRE_CTX(c);
+    REQUIRE_CTX_READER(c);
     VX_CUDA(cudaStreamSynchronize(c->stream));
     double ms = 0.0;
     for (size_t i = 0; i + 1 < c->probe_used; i += 2) {

@@ -88,6 +88,15 @@ struct vxrt_ctx {
     bool gi_overlap = true;
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    // Pass-level concurrency (set_option "pass_overlap", off by default: it is the caller's opt-in, because work then runs on a stream the
+    // caller does not see until the next join).  Lane 0 is `stream`; the sun-shadow trace and the direct term are issued on lane 1 and wait only
+    // for what was queued before the frame's diffuse_trace, so they run beside the GI / reflection wavefronts (which read neither of their
+    // outputs before the reflection pass, and that one joins).  Every other entry point first makes `stream` wait for lane 1 (api.cu
+    // REQUIRE_CTX); vxrt_cuda_join_passes does only that.
+    bool pass_overlap = false;
+    cudaStream_t lane1 = nullptr;
+    cudaEvent_t gi_fork = nullptr, lane0_mark = nullptr, lane1_tail = nullptr;
+    bool gi_fork_valid = false, lane1_pending = false;
     bool gi_fuse_final = true;  // last sample's shade<2> fused with resolve (set_option "gi_fuse_final"; 0 = the separate kernels)
 
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)

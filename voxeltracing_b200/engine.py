@@ -359,6 +359,11 @@ class Context:
     def shared_close(self, ptr: int):
         self._check(self._lib.vxrt_cuda_shared_close(self._h, C.c_void_p(ptr)))
 
+    def join_passes(self):
+        """With set_option("pass_overlap", 1): the context's stream waits (on the device) for the passes queued on the second lane.  Only needed
+        before the caller's own work on that stream (timing events, torch kernels); every Context call joins by itself."""
+        self._check(self._lib.vxrt_cuda_join_passes(self._h))
+
     def join_reads(self):
         """The context's stream waits on the device for the copies queued so far (see vxrt_cuda_join_reads)."""
         self._check(self._lib.vxrt_cuda_join_reads(self._h))

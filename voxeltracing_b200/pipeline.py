@@ -197,6 +197,7 @@ class FrameRenderer:
             self.ctx._check(fn(h, C.byref(params)))
             if hook:
                 hook(name, "end")
+        self.ctx.join_passes()   # set_option("pass_overlap", 1): the caller's stream sees the whole frame from here on
 
     def render(self, cam: host_api.Camera, frame: int = 0, tile=(0, 0), hook=None):
         self.submit(self.prepare(cam, frame, tile), hook)
