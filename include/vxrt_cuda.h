@@ -197,11 +197,12 @@ int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* ctx, int32_t id, int32_t row0
 /* makes the context's stream wait (on the device) for every copy queued so far: an event recorded on the stream afterwards
  * marks the moment the frame has left the GPU (device-side timing of the export; the host does not block). */
 int vxrt_cuda_join_reads(vxrt_ctx* ctx);
-/* Pass-level concurrency, opted into with vxrt_cuda_set_option(ctx, "pass_overlap", 1): the sun-shadow trace and the direct term are then queued on a
- * second stream of the context and wait only for the passes queued before the frame's diffuse_trace, i.e. they run beside the GI and reflection
- * wavefronts like independent draw calls do on the reference's GL queue (the reflection pass itself follows the GI, whose SH attachments are its
- * ambient base, and the sun shadow).  Every other entry point first makes the context's stream wait for that work, so results never depend on
- * the option; a caller that orders its OWN work after a frame on the context's stream (an event, a kernel) calls vxrt_cuda_join_passes first. */
+/* Pass-level concurrency, opted into with vxrt_cuda_set_option(ctx, "pass_overlap", 1): the sun-shadow trace, the reflection pass and the direct term
+ * are then queued on a second stream of the context and wait only for the passes queued before the frame's diffuse_trace, i.e. they run beside
+ * the GI wavefront like independent draw calls do on the reference's GL queue; the reflection pass meets the GI where it first reads its SH
+ * attachments (its shading; at once with derive_from_diffuse_sh).  Every other entry point first makes the context's stream wait for that
+ * work, so results never depend on the option; a caller that orders its OWN work after a frame on the context's stream (an event, a kernel)
+ * calls vxrt_cuda_join_passes first. */
 int vxrt_cuda_join_passes(vxrt_ctx* ctx);
 /* device pointer + geometry of an attachment (valid until the pass that owns it is re-run at a
  * different size).  Used by the host side for NCCL tile gathers.                              */

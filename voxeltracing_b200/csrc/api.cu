@@ -43,7 +43,7 @@ struct DeviceGuard {
 static int vxrt_join_lane1(vxrt_ctx* c, bool keep_fork) {
     if (c->lane1_pending) {
         VX_CUDA(cudaStreamWaitEvent(c->stream, c->lane1_tail, 0));
-        c->lane1_pending = false;
+        c->lane1_pending = false; c->lane1_reads_gi = false;
     }
     if (!keep_fork) c->gi_fork_valid = false;
     return VXRT_OK;
@@ -66,28 +66,38 @@ static bool lanes_on(const vxrt_ctx* c) { return c->pass_overlap && !c->probe_on
 static int ensure_lanes(vxrt_ctx* c) {
     if (c->lane1) return VXRT_OK;
     VX_CUDA(cudaStreamCreateWithFlags(&c->lane1, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&c->gi_fork, &c->lane0_mark, &c->lane1_tail}) VX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&c->gi_fork, &c->gi_done, &c->lane0_mark, &c->lane1_tail}) VX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return VXRT_OK;
 }
 // a lane-1 pass (sun-shadow trace, direct term): waits for what lane 0 had queued before the frame's diffuse_trace (or for everything, if there
 // was none), runs with c->stream swapped, leaves its tail event behind
 struct Lane1Pass {
-    vxrt_ctx* c; cudaStream_t saved; bool on;
-    explicit Lane1Pass(vxrt_ctx* c_) : c(c_), saved(c_->stream), on(lanes_on(c_)) {}
-    int begin() {
+    vxrt_ctx* c; cudaStream_t saved; void* wf; size_t wf_cap; bool on, arena;
+    explicit Lane1Pass(vxrt_ctx* c_, bool own_arena = false) : c(c_), saved(c_->stream), wf(c_->d_wf), wf_cap(c_->wf_cap), on(lanes_on(c_)), arena(own_arena) {}
+    // reads_gi: the pass reads the GI attachments; gi_first: from its first kernel on (otherwise from the point where the launcher waits for
+    // c->refl_gi_event)
+    int begin(bool reads_gi = false, bool gi_first = false) {
         if (!on) return VXRT_OK;
         if (int rc = ensure_lanes(c)) return rc;
         if (c->gi_fork_valid) {
             VX_CUDA(cudaStreamWaitEvent(c->lane1, c->gi_fork, 0));
-        } else {
+            if (reads_gi) {
+                if (gi_first) VX_CUDA(cudaStreamWaitEvent(c->lane1, c->gi_done, 0));
+                else c->refl_gi_event = c->gi_done;
+            }
+        } else {   // no diffuse_trace since the last join: everything lane 0 has queued (a GI issued before an intervening call included)
             VX_CUDA(cudaEventRecord(c->lane0_mark, c->stream));
             VX_CUDA(cudaStreamWaitEvent(c->lane1, c->lane0_mark, 0));
         }
+        if (reads_gi) c->lane1_reads_gi = true;
         c->stream = c->lane1;
+        if (arena) { c->d_wf = c->d_wf1; c->wf_cap = c->wf1_cap; }
         return VXRT_OK;
     }
     int end(int rc) {
         if (!on || c->stream != c->lane1) return rc;
+        if (arena) { c->d_wf1 = c->d_wf; c->wf1_cap = c->wf_cap; c->d_wf = wf; c->wf_cap = wf_cap; }
+        c->refl_gi_event = nullptr;
         c->stream = saved;
         const cudaError_t e = cudaEventRecord(c->lane1_tail, c->lane1);
         c->lane1_pending = true;
@@ -237,7 +247,8 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->lane1) { cudaStreamSynchronize(c->lane1); cudaStreamDestroy(c->lane1); }
-    for (cudaEvent_t e : {c->gi_fork, c->lane0_mark, c->lane1_tail}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->gi_fork, c->gi_done, c->lane0_mark, c->lane1_tail}) if (e) cudaEventDestroy(e);
+    cudaFree(c->d_wf1);
     if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->copies_joined) cudaEventDestroy(c->copies_joined);
@@ -746,8 +757,9 @@ int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
 }
 int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
     REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
-    // lane 0.  The GI reads the primary G-buffer and writes the GI attachments and its own arena only, none of which lane 1 touches: no join
-    if (c->lane1_pending && !lanes_on(c)) { if (int jrc = vxrt_join_lane1(c, false)) return jrc; }
+    // lane 0.  The GI reads the primary G-buffer and writes the GI attachments and its own arena: it waits for lane 1 only when a reflection pass
+    // queued there (before this call) reads those attachments
+    if (c->lane1_pending && (c->lane1_reads_gi || !lanes_on(c))) { if (int jrc = vxrt_join_lane1(c, false)) return jrc; }
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "diffuse_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
@@ -761,6 +773,7 @@ int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {
         if ((rc = ensure_lanes(c))) return rc;
         if (!c->gi_fork_valid) { VX_CUDA(cudaEventRecord(c->gi_fork, c->stream)); c->gi_fork_valid = true; }   // what lane-1 passes of this frame wait for
         rc = vxrt_launch_diffuse_trace(c, *p);
+        VX_CUDA(cudaEventRecord(c->gi_done, c->stream));
         return rc;
     }
     return vxrt_launch_diffuse_trace(c, *p);
@@ -829,9 +842,9 @@ int vxrt_cuda_shadow_filter(vxrt_ctx* c, const vxrt_shadow_filter_params* p) {
     return vxrt_launch_shadow_filter(c, *p);
 }
 int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
-    // lane 0, after the GI whose SH attachments are its ambient base (ReflectionTraceFrag.glsl main(): SHToIrridiance of u_DiffuseSHy); it reads the
-    // sun shadow of lane 1, so it joins - keeping the frame's fork point, the direct term that follows may run beside it
-    REQUIRE_CTX_READER(c); REQUIRE_PTR(p);
+    // lane 1 (behind the sun shadow it reads).  The GI's SH attachments are its ambient base (ReflectionTraceFrag.glsl main(): SHToIrridiance of
+    // u_DiffuseSHy), read by the shading kernels; ray generation and the first trace run beside the GI unless DeriveFromDiffuseSH reads them at once
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
     if (!c->df_valid) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs a world and a distance field");
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
@@ -844,7 +857,9 @@ int vxrt_cuda_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params* p) {
     if (!c->sky.data) return vxrt_fail(VXRT_E_STATE, "reflection_trace needs vxrt_cuda_set_skymap");
     if (!p->use_blue_noise) return vxrt_fail(VXRT_E_UNSUPPORTED, "the fract(sin()) hash RNG is not implemented");
     if (p->spp < 1 || p->trace_length < 0 || p->shadow_trace_length < 0) return vxrt_fail(VXRT_E_INVALID, "reflection_trace: bad spp / trace length");
-    return vxrt_launch_reflection_trace(c, *p);
+    Lane1Pass lane(c, true);
+    if ((rc = lane.begin(true, p->derive_from_diffuse_sh != 0))) return rc;
+    return lane.end(vxrt_launch_reflection_trace(c, *p));
 }
 
 int vxrt_cuda_join_passes(vxrt_ctx* c) {

@@ -89,14 +89,20 @@ struct vxrt_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     // Pass-level concurrency (set_option "pass_overlap", off by default: it is the caller's opt-in, because work then runs on a stream the
-    // caller does not see until the next join).  Lane 0 is `stream`; the sun-shadow trace and the direct term are issued on lane 1 and wait only
-    // for what was queued before the frame's diffuse_trace, so they run beside the GI / reflection wavefronts (which read neither of their
-    // outputs before the reflection pass, and that one joins).  Every other entry point first makes `stream` wait for lane 1 (api.cu
-    // REQUIRE_CTX); vxrt_cuda_join_passes does only that.
+    // caller does not see until the next join).  Lane 0 is `stream`; the sun-shadow trace, the reflection pass and the direct term are issued on
+    // lane 1 and wait only for what was queued before the frame's diffuse_trace, so they run beside the GI wavefront; the reflection pass
+    // waits for the GI itself where it first reads its attachments (refl_gi_event below).  Every other entry point first makes `stream` wait
+    // for lane 1 (api.cu REQUIRE_CTX); vxrt_cuda_join_passes does only that.
     bool pass_overlap = false;
     cudaStream_t lane1 = nullptr;
-    cudaEvent_t gi_fork = nullptr, lane0_mark = nullptr, lane1_tail = nullptr;
-    bool gi_fork_valid = false, lane1_pending = false;
+    cudaEvent_t gi_fork = nullptr, gi_done = nullptr, lane0_mark = nullptr, lane1_tail = nullptr;
+    bool gi_fork_valid = false, lane1_pending = false, lane1_reads_gi = false;
+    // The reflection pass on lane 1: ray generation and the first closest-hit trace need only the G-buffer, the shading needs the GI's SH
+    // attachments (its ambient base).  When set, the wavefront launcher makes its stream wait for this event before the first shading kernel
+    // instead of the whole pass following the GI.  Own path-state arena (the GI wavefront is using d_wf at the same time).
+    cudaEvent_t refl_gi_event = nullptr;
+    void* d_wf1 = nullptr;
+    size_t wf1_cap = 0;
     bool gi_fuse_final = true;  // last sample's shade<2> fused with resolve (set_option "gi_fuse_final"; 0 = the separate kernels)
 
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)

@@ -24,7 +24,6 @@ struct RfWf {
     float4* P;        // biased hit position (xyz), roughness (w)
     float4* I;        // incident direction (xyz), metal flag PBRMap.y > 0.05 (w)
     float4* Nmap;     // normal-mapped G-buffer normal (xyz)
-    float4* Base;     // BaseIndirectDiffuse (xyz)
     float4* Total;    // TotalColor
     float4* misc;     // AveragedHitDistance, TotalMeaningfulHits, EmissivityMask, ComputedShadow
     int4* cnt;        // ShadowItr, total_hits, SPP, CurrentBLSample (-1: pixel has no paths)
@@ -124,15 +123,18 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
             const f4 PBRMap = F4(unorm8_to_float(pb.x), unorm8_to_float(pb.y), unorm8_to_float(pb.z), unorm8_to_float(pb.w));
             const f3 I = normalize(P - viewer);
             P = P + N0 * 0.035f;
-            float nv[3], shv[4], ccv[2];
+            float nv[3];
             att_half_bilinear<3>(a.gb_normal, a.mw, a.mh, vtc, nv);
-            att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, shv);
-            att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, ccv);
             const f3 Nmap = F3(nv[0], nv[1], nv[2]);
-            const f4 DiffuseSH = F4(shv[0], shv[1], shv[2], shv[3]);
-            const f2 DiffuseCoCg = F2(ccv[0], ccv[1]);
-            const f3 Base = sh_to_irradiance_a(DiffuseSH, DiffuseCoCg);
+            // The diffuse SH of the GI (u_DiffuseSHy / u_DiffuseCoCg at v_TexCoords) is read HERE only for the DeriveFromDiffuseSH shortcut; the
+            // ambient base of a hit (BaseIndirectDiffuse) is evaluated from the same texels in shade_a, so that without the shortcut gen and
+            // the first trace do not depend on the GI pass (api.cu runs them beside it).
             if (PBRMap.x >= 0.865f && a.derive_sh) {
+                float shv[4], ccv[2];
+                att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, shv);
+                att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, ccv);
+                const f4 DiffuseSH = F4(shv[0], shv[1], shv[2], shv[3]);
+                const f2 DiffuseCoCg = F2(ccv[0], ccv[1]);
                 f3 r = derive_specular_from_diffuse_sh(DiffuseSH, sh_to_irradiance(DiffuseSH, DiffuseCoCg, Nmap), I, Nmap);
                 oColor = F4(r.x, r.y, r.z, 0.0f); oHit = 0.5f; oMask = 0.0f;
                 done = true;
@@ -140,7 +142,6 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
                 w.P[i] = make_float4(P.x, P.y, P.z, PBRMap.x);
                 w.I[i] = make_float4(I.x, I.y, I.z, (PBRMap.y > 0.05f) ? 1.0f : 0.0f);
                 w.Nmap[i] = make_float4(Nmap.x, Nmap.y, Nmap.z, 0.0f);
-                w.Base[i] = make_float4(Base.x, Base.y, Base.z, 0.0f);
                 w.Total[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 w.misc[i] = make_float4(0.001f, 0.0f, 0.0f, 0.0f);
                 w.cnt[i] = make_int4(0, 0, SPP, 0);
@@ -204,8 +205,13 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
             const int reference_id = iclamp((int)(info & 0xffu), 0, 127);
             bool ReprojectionSuccessful = false;
             f2 SS = F2(-1.0f, -1.0f);
-            const float4 b4 = w.Base[i];
-            f3 Ambient = F3(b4.x, b4.y, b4.z);
+            // BaseIndirectDiffuse = SHToIrridiance(texture(u_DiffuseSHy, v_TexCoords), texture(u_DiffuseCoCg, v_TexCoords)) of main()
+            float bsh[4], bcc[2];
+            const f2 vtc = pixel_uv(px, py, a.width, a.height);
+            att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, bsh);
+            att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, bcc);
+            const f3 b4 = sh_to_irradiance_a(F4(bsh[0], bsh[1], bsh[2], bsh[3]), F2(bcc[0], bcc[1]));
+            f3 Ambient = b4;
             if (a.reproject) {
                 f4 pp = mat4_mul(a.proj_view, F4(HitPosition.x, HitPosition.y, HitPosition.z, 1.0f));
                 f3 q = F3(pp.x / pp.w, pp.y / pp.w, pp.z / pp.w);
@@ -356,7 +362,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     const int rows = a.row1 - a.row0, cols = a.col1 - a.col0;   // the tile rectangle; path state is indexed inside it
     if (rows <= 0 || cols <= 0) return VXRT_OK;
     const size_t n = (size_t)rows * cols;
-    const size_t need = n * (16 * 11 + 4 * 3) + 256 * 32;
+    const size_t need = n * (16 * 10 + 4 * 3) + 256 * 32;
     if (need > c->wf_cap) {
         if (c->d_wf) VX_CUDA(cudaFree(c->d_wf));
         c->d_wf = nullptr; c->wf_cap = 0;
@@ -365,7 +371,7 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     }
     uint8_t* p = (uint8_t*)c->d_wf;
     RfWf w;
-    w.P = carve<float4>(p, n); w.I = carve<float4>(p, n); w.Nmap = carve<float4>(p, n); w.Base = carve<float4>(p, n);
+    w.P = carve<float4>(p, n); w.I = carve<float4>(p, n); w.Nmap = carve<float4>(p, n);
     w.Total = carve<float4>(p, n); w.misc = carve<float4>(p, n); w.cnt = carve<int4>(p, n); w.rayD = carve<float4>(p, n);
     w.Amb = carve<float4>(p, n); w.Res = carve<float4>(p, n); w.qShadowO = carve<float4>(p, n);
     w.hitT = carve<float>(p, n); w.hitInfo = carve<unsigned>(p, n); w.shadowRes = carve<float>(p, n);
@@ -389,6 +395,8 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
             c->launches -= 1;
         } else if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
+        // the shading reads the GI attachments: on lane 1 of the pass-level concurrency this is where the pass meets the GI (ctx.h)
+        if (sample == 0 && c->refl_gi_event) VX_CUDA(cudaStreamWaitEvent(s, c->refl_gi_event, 0));
         if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w);
         else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w);
         if (c->trace_caps | c->trace_spill) {
