@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pass-overlap", action="store_true", help="issue every pass on one stream (round 1 / early round 2 behaviour)")
+    ap.add_argument("--wf-bands", type=int, default=2, help="row bands the GI / reflection wavefronts are pipelined in (set_option wf_bands)")
     ap.add_argument("--profile", action="store_true", help="only warm-up + steps of the plain step (for ncu)")
     ap.add_argument("--tex-size", type=int, default=512)
     ap.add_argument("--no-svgf", action="store_true", help="skip the SVGF denoiser-chain measurement")
@@ -697,6 +698,7 @@ def main():
     # pass-level concurrency (vxrt_cuda_set_option "pass_overlap"): shadow / reflection / direct passes on the context's second stream beside the GI
     # wavefront; FrameRenderer.submit joins the lanes at the end of the frame, so the step events below bracket all of it
     ctx.set_option("pass_overlap", 0 if args.no_pass_overlap else 1)
+    ctx.set_option("wf_bands", args.wf_bands)
     total_rays = int(sum(rays_per_step))
     total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
 
@@ -1247,6 +1249,7 @@ def main():
             "parity_check": parity["status"] if parity else None, "parity": parity,
             "gather_check": gather_check,
             "pass_overlap": not args.no_pass_overlap,
+            "wf_bands": args.wf_bands,
             "pass_ms": pass_ms,
             "pass_ms_note": "passes timed one after the other in K extra steps after the timed region (CUDA-event pairs around each pass, pass-level overlap "
                             "off); with pass_overlap the timed step is shorter than their sum because shadow / reflection / direct run beside the GI wavefront",

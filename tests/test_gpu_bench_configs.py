@@ -96,11 +96,13 @@ def test_pass_overlap_does_not_change_a_bit(workload, reproject, inputs512):
                 out.append({a: ctx.read_attachment(a).copy() for a in fr.outputs})
             return out
         want = run(0, False)
-        for mid in (False, True):
-            got = run(1, mid)
+        # ... and with the wavefront passes cut into row bands on their own streams (set_option "wf_bands"), alone and together with the lanes
+        for bands, overlap, mid in ((1, 1, False), (1, 1, True), (2, 0, False), (3, 1, True), (4, 1, False)):
+            ctx.set_option("wf_bands", bands)
+            got = run(overlap, mid)
             for fw, fg in zip(want, got):
                 for a in fr.outputs:
-                    assert np.array_equal(fw[a].view(np.uint8), fg[a].view(np.uint8)), (workload, reproject, mid, a)
+                    assert np.array_equal(fw[a].view(np.uint8), fg[a].view(np.uint8)), (workload, reproject, bands, overlap, mid, a)
     finally:
-        ctx.set_option("pass_overlap", 0)
+        ctx.set_option("pass_overlap", 0); ctx.set_option("wf_bands", 1)
         ctx.close()

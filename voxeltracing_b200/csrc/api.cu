@@ -249,6 +249,15 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     if (c->lane1) { cudaStreamSynchronize(c->lane1); cudaStreamDestroy(c->lane1); }
     for (cudaEvent_t e : {c->gi_fork, c->gi_done, c->lane0_mark, c->lane1_tail}) if (e) cudaEventDestroy(e);
     cudaFree(c->d_wf1);
+    for (int l = 0; l < 2; ++l) {
+        for (auto& b : c->band[l]) {
+            if (b.stream) { cudaStreamSynchronize(b.stream); cudaStreamDestroy(b.stream); }
+            if (b.aux) { cudaStreamSynchronize(b.aux); cudaStreamDestroy(b.aux); }
+            for (cudaEvent_t e : {b.done, b.aux_fork, b.aux_join}) if (e) cudaEventDestroy(e);
+            cudaFree(b.wf);
+        }
+        if (c->band_fork[l]) cudaEventDestroy(c->band_fork[l]);
+    }
     if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->copies_joined) cudaEventDestroy(c->copies_joined);
@@ -288,6 +297,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "gi_overlap")) { c->gi_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "pass_overlap")) { c->pass_overlap = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "wf_bands")) { if (value < 1 || value > 4) return vxrt_fail(VXRT_E_INVALID, "wf_bands: 1..4"); c->wf_bands = value; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "trace_spill")) { c->trace_spill = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "df_stage")) { c->df_stage = value; return VXRT_OK; }

@@ -3,6 +3,7 @@
 // tables and the pass attachments (the reference keeps these as GL textures, SSBOs and FBO
 // attachments: Core/World.h:167-171, Core/BlockDataSSBO.cpp, Core/Pipeline.cpp:1142-1202).
 #pragma once
+#include <utility>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -103,6 +104,18 @@ struct vxrt_ctx {
     cudaEvent_t refl_gi_event = nullptr;
     void* d_wf1 = nullptr;
     size_t wf1_cap = 0;
+    // Band pipelining of the wavefront passes (set_option "wf_bands", default 1 = off): the tile of a GI / reflection pass is cut into row
+    // bands, each band's whole kernel sequence is queued on its own stream with its own path-state arena, so while one band is in a shading
+    // kernel (waiting on memory, issue slots 58 % busy) another is in a trace kernel (issue bound) and the two fill each other's gaps and tails.
+    // Per-pixel arithmetic and sample order are untouched: bit-identical by construction (tests/test_gpu_bench_configs.py).
+    int wf_bands = 1;
+    struct BandSlot {
+        cudaStream_t stream = nullptr, aux = nullptr;
+        cudaEvent_t done = nullptr, aux_fork = nullptr, aux_join = nullptr;
+        void* wf = nullptr;
+        size_t wf_cap = 0;
+    } band[2][3];                       // [lane the pass runs on][band - 1]
+    cudaEvent_t band_fork[2] = {nullptr, nullptr};
     bool gi_fuse_final = true;  // last sample's shade<2> fused with resolve (set_option "gi_fuse_final"; 0 = the separate kernels)
 
     int32_t* d_slab_z0 = nullptr;  // slab boundaries of the sharded distance-field regeneration (<= 65 ints)
@@ -173,6 +186,40 @@ inline void vxrt_tile_rect(const vxrt_tile& t, int width, int height, int* r0, i
     else { *r0 = t.row0; *r1 = t.row0 + t.rows; if (*r1 > height) *r1 = height; }
     if (t.cols <= 0) { *c0 = 0; *c1 = width; }
     else { *c0 = t.col0; *c1 = t.col0 + t.cols; if (*c1 > width) *c1 = width; }
+}
+
+// Runs `launch(row0, row1)` (a wavefront launcher that queues on c->stream, carves its state from c->d_wf and uses c->aux_*) once per row band
+// of [row0, row1): band 0 as is, band k > 0 with the context's stream / arena / side stream swapped for the band's own (ctx.h wf_bands).
+template <class F>
+int vxrt_run_bands(vxrt_ctx* c, int row0, int row1, F launch) {
+    const int rows = row1 - row0;
+    int S = c->wf_bands < 1 ? 1 : (c->wf_bands > 4 ? 4 : c->wf_bands);
+    while (S > 1 && rows < 64 * S) --S;
+    if (S <= 1 || c->probe_on || (c->trace_caps | c->trace_spill)) return launch(row0, row1);
+    const int lane = (c->lane1 && c->stream == c->lane1) ? 1 : 0;
+    if (!c->band_fork[lane]) VX_CUDA(cudaEventCreateWithFlags(&c->band_fork[lane], cudaEventDisableTiming));
+    VX_CUDA(cudaEventRecord(c->band_fork[lane], c->stream));
+    int rc = VXRT_OK;
+    int edge[5];
+    for (int k = 0; k <= S; ++k) edge[k] = k == S ? row1 : row0 + ((rows * k / S) & ~7);   // bands on the 8-row CTA grid
+    for (int k = 0; k < S && rc == VXRT_OK; ++k) {
+        if (k == 0) { rc = launch(edge[0], edge[1]); continue; }
+        vxrt_ctx::BandSlot& b = c->band[lane][k - 1];
+        if (!b.stream) {
+            VX_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+            VX_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        }
+        VX_CUDA(cudaStreamWaitEvent(b.stream, c->band_fork[lane], 0));
+        std::swap(c->stream, b.stream); std::swap(c->d_wf, b.wf); std::swap(c->wf_cap, b.wf_cap);
+        std::swap(c->aux_stream, b.aux); std::swap(c->aux_fork, b.aux_fork); std::swap(c->aux_join, b.aux_join);
+        rc = launch(edge[k], edge[k + 1]);
+        std::swap(c->stream, b.stream); std::swap(c->d_wf, b.wf); std::swap(c->wf_cap, b.wf_cap);
+        std::swap(c->aux_stream, b.aux); std::swap(c->aux_fork, b.aux_fork); std::swap(c->aux_join, b.aux_join);
+        if (rc != VXRT_OK) break;
+        VX_CUDA(cudaEventRecord(b.done, b.stream));
+        VX_CUDA(cudaStreamWaitEvent(c->stream, b.done, 0));
+    }
+    return rc;
 }
 
 // continuation storage of the iteration-capped trace passes (trace_queue.cuh), allocated on demand (api.cu)

@@ -195,7 +195,7 @@ int vxrt_launch_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params& p) {
     a.sh = (uint16_t*)c->att[VXRT_ATT_GI_SH].ptr; a.cocg = (uint16_t*)c->att[VXRT_ATT_GI_COCG].ptr;
     a.utility = (uint16_t*)c->att[VXRT_ATT_GI_UTILITY].ptr; a.aosky = (uint8_t*)c->att[VXRT_ATT_GI_AOSKY].ptr;
     if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
-    if (c->wavefront) return vxrt_launch_diffuse_trace_wavefront(c, &a);
+    if (c->wavefront) return vxrt_run_bands(c, a.row0, a.row1, [&](int r0, int r1) { GiArgs b = a; b.row0 = r0; b.row1 = r1; return vxrt_launch_diffuse_trace_wavefront(c, &b); });
     dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     if (c->stats_on) diffuse_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     else diffuse_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);

@@ -241,7 +241,7 @@ int vxrt_launch_reflection_trace(vxrt_ctx* c, const vxrt_reflection_params& p) {
         vxrt_host_sky_sample(c, up, a.sky_ambient_g);
     }
     if (a.row1 <= a.row0 || a.col1 <= a.col0) return VXRT_OK;
-    if (c->wavefront) return vxrt_launch_reflection_trace_wavefront(c, &a);
+    if (c->wavefront) return vxrt_run_bands(c, a.row0, a.row1, [&](int r0, int r1) { ReflArgs b = a; b.row0 = r0; b.row1 = r1; return vxrt_launch_reflection_trace_wavefront(c, &b); });
     dim3 grid((a.col1 - a.col0 + 31) / 32, (a.row1 - a.row0 + 7) / 8);
     if (c->stats_on) reflection_trace_kernel<true><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
     else reflection_trace_kernel<false><<<grid, 256, 0, c->stream>>>(c->grid(), a, c->d_stats);
