@@ -307,8 +307,14 @@ def cpu_arm(blocks, wl, inputs):
 def config_block(args, wl, world_desc):
     """The workload keys both arms print (identical, so the driver's same_config comparison holds)."""
     cfg = frame_config(wl)
+    n = args.gpus
+    tiles = n > 1 and (args.sharding == "tiles" or (args.sharding == "auto" and args.workload.startswith("config5")))
+    sharding = "single GPU" if n == 1 else (f"tiles: {n} ranks render the tiles of ONE frame per step (strong scaling)" if tiles
+                                            else f"frames: each of {n} ranks renders its own frame per step (weak scaling)")
     return {"workload": args.workload, "world": world_desc, "width": wl["width"], "height": wl["height"], "passes": list(wl["passes"]),
-            "gi_spp": cfg.gi_spp, "reflection_spp": cfg.refl_spp, "texture_size": args.tex_size}
+            "gi_spp": cfg.gi_spp, "reflection_spp": cfg.refl_spp, "texture_size": args.tex_size, "sharding": sharding,
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs), camera pose changes every step; "
+                  "CPU arm: not applicable"}
 
 
 CPU_FRAME_BUDGET_S = 1.0   # one band of rows per frame sized to about this much CPU work, in BOTH the --impl reference arm and the in-line cpu_baseline leg
@@ -1233,12 +1239,11 @@ def main():
             "metric": "Mrays/s DF-DDA traversal", "value": mrays, "unit": "Mrays/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {**config_block(args, wl, world_desc),
-                       "rays_per_step_per_gpu": total_rays / args.steps / world_size,
-                       "mean_iterations_per_ray": total_iters / max(total_rays, 1),
-                       "sharding": sharding_desc,
-                       "outputs": {"set": args.outputs, "bytes_per_pixel": out_bytes_px, "bytes_per_frame": int(out_bytes_px * W * H)},
-                       "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); camera pose changes every step"},
+            "config": config_block(args, wl, world_desc),     # identical in both arms
+            "config_detail": {"rays_per_step_per_gpu": total_rays / args.steps / world_size,
+                              "mean_iterations_per_ray": total_iters / max(total_rays, 1),
+                              "sharding": sharding_desc,
+                              "outputs": {"set": args.outputs, "bytes_per_pixel": out_bytes_px, "bytes_per_frame": int(out_bytes_px * W * H)}},
             "clocks": clocks,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * (world_size if not tiles else 1), "d2h_bytes_per_step": d2h_all,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "rank0_numa_node": numa_node,
