@@ -39,9 +39,12 @@ struct GiWf {
     float4* odirAo;     // first-bounce direction (xyz), ao (w)
     float4* contrib;    // RayContribution (xyz), w = 1 while the path still has a ray in flight
     float4* thr;        // RayThroughput (xyz), w = sky-hit flag of the sample
-    float4* A;          // (Albedo*DiffuseHammon)*(LIGHT_COLOR*3.5) (xyz); w = ShadowAt if known, -1 = from shadowRes
-    float4* Em;         // EmmisivityColor (xyz)
-    float4* thrF;       // Albedo*Attenuation/PDF (xyz)
+    // After shade<1> the two hold the sample's FINAL contribution instead: the pending bounce-1 terms only wait for one bit, the result of the
+    // last sun-shadow ray, so shade<1> applies them for both outcomes with the shader's own expression (gi_apply_pending) -
+    // contrib = (lit result, w = 1: pick by shadowRes / 2: shadow known, take this one), thr = (shadowed result, sky-hit flag) - and shade<2> /
+    // final select.  32 instead of 80 bytes per path written by shade<1> and read back (Apend, EmmisivityColor and the throughput factor no
+    // longer travel), bit-identical: the selected value is the one the old sequence computed.
+    float4* A;          // bounce 0 -> 1 only: (Albedo*DiffuseHammon)*(LIGHT_COLOR*3.5) (xyz); w = ShadowAt if known, -1 = from shadowRes
     float4* rayO;       // current bounce ray
     float4* rayD;
     float* hitT;
@@ -51,6 +54,13 @@ struct GiWf {
     int* qBounce;       // compacted path indices whose bounce-1 ray is traced
     int* counters;      // [0] shadow rays, [1] bounce rays
 };
+
+// the tail of a bounce iteration once its sun-shadow term is known (:611-614): RayContribution += RayThroughput * SUNBRDF + EmmisivityColor * RayThroughput
+VXD f3 gi_apply_pending(f3 contrib, f3 thr, f3 Apend, float ShadowAt, f3 Em) {
+    const f3 SUNBRDF = Apend * (1.0f - ShadowAt) * VX_PI;
+    contrib = contrib + thr * SUNBRDF;
+    return contrib + Em * thr;
+}
 
 VXD unsigned pack_hit(const TraceResult& r) {
     unsigned face = 7u;
@@ -221,21 +231,19 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
         f3 thr = F3(t4.x, t4.y, t4.z);
         float skyhit = t4.w;
         bool still_alive = false;
-        if (BOUNCE > 0) {
+        float alive_flag_out = 1.0f;
+        if (BOUNCE == 1) {
             // the tail of the previous iteration: RayContribution += ..., RayThroughput *= ... (:611-614)
             const float4 A4 = w.A[i];
             const float ShadowAt = A4.w >= 0.0f ? A4.w : w.shadowRes[i];
             const f3 SUNBRDF = F3(A4.x, A4.y, A4.z) * (1.0f - ShadowAt) * VX_PI;
-            if (BOUNCE == 1) {
-                // bounce 0 left contrib = EmmisivityColor and thr = Albedo*Attenuation/PDF (see below): with RayContribution = 0 and
-                // RayThroughput = 1 the shader's (0 + 1 * SUNBRDF) + Em * 1 is SUNBRDF + Em and 1 * F is F, bit for bit
-                contrib = SUNBRDF + contrib;
-            } else {
-                const f3 Em = ld3(w.Em + i);
-                contrib = contrib + thr * SUNBRDF;
-                contrib = contrib + Em * thr;
-                thr = thr * ld3(w.thrF + i);
-            }
+            // bounce 0 left contrib = EmmisivityColor and thr = Albedo*Attenuation/PDF (see below): with RayContribution = 0 and
+            // RayThroughput = 1 the shader's (0 + 1 * SUNBRDF) + Em * 1 is SUNBRDF + Em and 1 * F is F, bit for bit
+            contrib = SUNBRDF + contrib;
+        }
+        if (BOUNCE == 2) {
+            // shade<1> left both outcomes of the last sun-shadow ray (GiWf): c4 = lit, t4 = shadowed
+            if (!(c4.w == 2.0f || w.shadowRes[i] == 0.0f)) contrib = thr;
         }
         if (BOUNCE < 2) {
             const f3 light = a.sun_stronger ? F3(a.sun[0], a.sun[1], a.sun[2]) : F3(a.moon[0], a.moon[1], a.moon[2]);
@@ -281,16 +289,27 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
                 const float PDF = gmax(CosTheta / VX_PI, 0.00001f);
                 const f3 Attenuation = F3(1.0f) * diffuse_hammon(HitNormal, -rayD, NewDirection, PBR.x);
                 const f3 F = Albedo * Attenuation / PDF;
-                w.A[i] = make_float4(Apend.x, Apend.y, Apend.z, ShadowAt);
+                float alive_flag = 1.0f;
                 if (BOUNCE == 0) {
                     // the pending terms of bounce 0 travel in contrib / thr themselves (16 + 16 bytes per path less to write and to read
                     // back): at this point RayContribution is exactly 0 and RayThroughput exactly 1
+                    w.A[i] = make_float4(Apend.x, Apend.y, Apend.z, ShadowAt);
                     contrib = EmmisivityColor;
                     thr = F;
                 } else {
-                    w.Em[i] = make_float4(EmmisivityColor.x, EmmisivityColor.y, EmmisivityColor.z, 0.0f);
-                    w.thrF[i] = make_float4(F.x, F.y, F.z, 0.0f);
+                    // last bounce: nothing is left to do but these pending terms, and they wait for one bit.  Both outcomes now (the
+                    // throughput factor F only fed a further bounce: RayThroughput is not read after the loop, :655-664)
+                    const f3 c_in = contrib, t_in = thr;
+                    if (ShadowAt >= 0.0f) {
+                        contrib = gi_apply_pending(c_in, t_in, Apend, ShadowAt, EmmisivityColor);
+                        thr = contrib;
+                        alive_flag = 2.0f;
+                    } else {
+                        contrib = gi_apply_pending(c_in, t_in, Apend, 0.0f, EmmisivityColor);
+                        thr = gi_apply_pending(c_in, t_in, Apend, 1.0f, EmmisivityColor);
+                    }
                 }
+                alive_flag_out = alive_flag;
                 if (BOUNCE == 0) {
                     const f3 no = IntersectionPosition + HitNormal * 0.06f;
                     w.rayO[i] = make_float4(no.x, no.y, no.z, 0.0f);
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
             }
         }
         if (still_alive) {
-            w.contrib[i] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
+            w.contrib[i] = make_float4(contrib.x, contrib.y, contrib.z, alive_flag_out);
             w.thr[i] = make_float4(thr.x, thr.y, thr.z, skyhit);
         } else {
             finish_sample(w, i, contrib, skyhit, sample == 0);
@@ -382,14 +401,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_final_kernel(const __
     const float4 c4 = w.contrib[i];
     if (c4.w != 0.0f) {
         const float4 t4 = w.thr[i];
-        f3 contrib = F3(c4.x, c4.y, c4.z);
-        const f3 thr = F3(t4.x, t4.y, t4.z);
-        const float4 A4 = w.A[i];
-        const float ShadowAt = A4.w >= 0.0f ? A4.w : w.shadowRes[i];
-        const f3 SUNBRDF = F3(A4.x, A4.y, A4.z) * (1.0f - ShadowAt) * VX_PI;
-        const f3 Em = ld3(w.Em + i);
-        contrib = contrib + thr * SUNBRDF;
-        contrib = contrib + Em * thr;
+        // shade<1> left both outcomes of the last sun-shadow ray (GiWf): c4 = lit (or the known one), t4 = shadowed
+        const f3 contrib = (c4.w == 2.0f || w.shadowRes[i] == 0.0f) ? F3(c4.x, c4.y, c4.z) : F3(t4.x, t4.y, t4.z);
         // finish_sample
         const float4 oa = w.odirAo[i];
         const f3 xc = gclamp(contrib, 0.0f, 8.0f);
@@ -435,7 +448,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     const int rows = a.row1 - a.row0, cols = a.col1 - a.col0;   // the tile rectangle; path state is indexed inside it
     if (rows <= 0 || cols <= 0) return VXRT_OK;
     const size_t n = (size_t)rows * cols;
-    const size_t need = n * (16 * 13 + 4 * 6) + 256 * 32;
+    const size_t need = n * (16 * 11 + 4 * 6) + 256 * 32;
     if (need > c->wf_cap) {
         if (c->d_wf) VX_CUDA(cudaFree(c->d_wf));
         c->d_wf = nullptr; c->wf_cap = 0;
@@ -446,7 +459,7 @@ int vxrt_launch_diffuse_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     GiWf w;
     w.pixP = carve<float4>(p, n); w.accSH = carve<float4>(p, n); w.accRadAO = carve<float4>(p, n); w.accCoCgSky = carve<float4>(p, n);
     w.odirAo = carve<float4>(p, n); w.contrib = carve<float4>(p, n); w.thr = carve<float4>(p, n); w.A = carve<float4>(p, n);
-    w.Em = carve<float4>(p, n); w.thrF = carve<float4>(p, n); w.rayO = carve<float4>(p, n); w.rayD = carve<float4>(p, n);
+    w.rayO = carve<float4>(p, n); w.rayD = carve<float4>(p, n);
     w.qShadowO = carve<float4>(p, n);
     w.bl = carve<int>(p, n); w.spp = carve<int>(p, n); w.hitT = carve<float>(p, n); w.hitInfo = carve<unsigned>(p, n);
     w.shadowRes = carve<float>(p, n); w.qBounce = carve<int>(p, n);
