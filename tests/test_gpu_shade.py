@@ -222,16 +222,18 @@ def test_wavefront_reflections_are_bit_identical_to_the_per_pixel_kernel(request
         rp.derive_from_diffuse_sh = 1
     atts = (abi.ATT_REFL_COLOR, abi.ATT_REFL_HITDIST, abi.ATT_REFL_EMISSIVE)
     res = {}
-    for mode in (0, 1):
-        c.set_option("wavefront", mode)
+    # per-pixel kernel, the wavefront with the last sample's shade_b fused with resolve (default), the wavefront with the separate kernels
+    for key, (mode, fuse) in enumerate(((0, 1), (1, 1), (1, 0))):
+        c.set_option("wavefront", mode); c.set_option("gi_fuse_final", fuse)
         c.stats_enable(True); c.stats_read(True)
         c.reflection_trace(rp)
-        res[mode] = ([c.read_attachment(a).copy() for a in atts], c.stats_read(True))
+        res[key] = ([c.read_attachment(a).copy() for a in atts], c.stats_read(True))
         c.stats_enable(False)
-    c.set_option("wavefront", 1)
-    for a, b in zip(res[0][0], res[1][0]):
-        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
-    assert res[0][1] == res[1][1]
+    c.set_option("wavefront", 1); c.set_option("gi_fuse_final", 1)
+    for other in (1, 2):
+        for a, b in zip(res[0][0], res[other][0]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        assert res[0][1] == res[other][1]
 
 
 @pytest.mark.parametrize("caps", [(), (12, 24), (1, 2, 3), (5,), (47,), (30, 100), (200, 250)])

@@ -309,23 +309,44 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
     }
 }
 
-__global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
-    int px, py;
-    tile_pixel(px, py, a.row0, a.col0);
-    if (px >= a.col1 || py >= a.row1) return;
-    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
+// shade_b of one path: the sample's sun-shadow term once the shadow ray is back; leaves the updated totals in Total / misc (written back
+// only when `store`)
+VXD bool rf_shade_b_path(const RfWf& w, int i, float4& Total, float4& misc, bool store) {
     const float4 amb = w.Amb[i];
-    if (amb.w == 0.0f) return;
+    if (amb.w == 0.0f) return false;
     const float4 res = w.Res[i];
-    float4 misc = w.misc[i];
-    if (res.w != 0.0f) { misc.w = w.shadowRes[i]; w.misc[i] = misc; }   // ComputedShadow = GetShadowAt(...)
+    misc = w.misc[i];
+    if (res.w != 0.0f) { misc.w = w.shadowRes[i]; if (store) w.misc[i] = misc; }   // ComputedShadow = GetShadowAt(...)
     f3 Direct = F3(amb.x, amb.y, amb.z);
     if (amb.w < 2.0f) {
         const float Shadow = gmin(misc.w, 1.0f);
         Direct = Direct + F3(res.x, res.y, res.z) * gclamp(1.0f - Shadow, 0.0f, 1.0f);
     }
-    float4 Total = w.Total[i];
-    w.Total[i] = make_float4(Total.x + Direct.x, Total.y + Direct.y, Total.z + Direct.z, Total.w + 1.0f);
+    Total = w.Total[i];
+    Total = make_float4(Total.x + Direct.x, Total.y + Direct.y, Total.z + Direct.z, Total.w + 1.0f);
+    if (store) w.Total[i] = Total;
+    return true;
+}
+// averages, clamps and attachment formats of main()
+VXD void rf_resolve_pixel(const ReflArgs& a, int px, int py, const int4 cnt, float4 Total, const float4 misc) {
+    const size_t pi = (size_t)py * a.width + px;
+    float AveragedHitDistance = misc.x / gmax(misc.y, 0.01f);
+    const float th = (float)cnt.y;
+    Total = make_float4(Total.x / th, Total.y / th, Total.z / th, Total.w / th);
+    const float oHit = gclamp(misc.y > 0.01f ? AveragedHitDistance : -1.0f, -10.0f, 200.0f);
+    reinterpret_cast<ushort4*>(a.color)[pi] = make_ushort4(float_to_half_bits(gclamp(Total.x, 0.0000001f, 100.0f)), float_to_half_bits(gclamp(Total.y, 0.0000001f, 100.0f)),
+                                                           float_to_half_bits(gclamp(Total.z, 0.0000001f, 100.0f)), float_to_half_bits(gclamp(Total.w, 0.0000001f, 100.0f)));
+    a.hitdist[pi] = float_to_half_bits(oHit);
+    a.emissive[pi] = float_to_unorm8(gclamp(misc.z, 0.0f, 1.0f));
+}
+
+__global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+    int px, py;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
+    float4 Total, misc;
+    rf_shade_b_path(w, i, Total, misc, true);
 }
 
 __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
@@ -335,17 +356,22 @@ __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constan
     const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     const int4 cnt = w.cnt[i];
     if (cnt.w < 0) return;
-    const size_t pi = (size_t)py * a.width + px;
-    float4 misc = w.misc[i];
-    float4 Total = w.Total[i];
-    float AveragedHitDistance = misc.x / gmax(misc.y, 0.01f);
-    const float th = (float)cnt.y;
-    Total = make_float4(Total.x / th, Total.y / th, Total.z / th, Total.w / th);
-    const float oHit = gclamp(misc.y > 0.01f ? AveragedHitDistance : -1.0f, -10.0f, 200.0f);
-    reinterpret_cast<ushort4*>(a.color)[pi] = make_ushort4(float_to_half_bits(gclamp(Total.x, 0.0000001f, 100.0f)), float_to_half_bits(gclamp(Total.y, 0.0000001f, 100.0f)),
-                                                           float_to_half_bits(gclamp(Total.z, 0.0000001f, 100.0f)), float_to_half_bits(gclamp(Total.w, 0.0000001f, 100.0f)));
-    a.hitdist[pi] = float_to_half_bits(oHit);
-    a.emissive[pi] = float_to_unorm8(gclamp(misc.z, 0.0f, 1.0f));
+    rf_resolve_pixel(a, px, py, cnt, w.Total[i], w.misc[i]);
+}
+
+// the LAST sample's shade_b fused with resolve (set_option "gi_fuse_final" governs both wavefronts): the totals of a path whose sample was still
+// waiting for its shadow ray go from registers into the attachments instead of through Total / misc and back; one launch less.  Same
+// arithmetic in the same order, bit-identical.
+__global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+    int px, py;
+    tile_pixel(px, py, a.row0, a.col0);
+    if (px >= a.col1 || py >= a.row1) return;
+    const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
+    const int4 cnt = w.cnt[i];
+    if (cnt.w < 0) return;
+    float4 Total, misc;
+    if (!rf_shade_b_path(w, i, Total, misc, false)) { Total = w.Total[i]; misc = w.misc[i]; }
+    rf_resolve_pixel(a, px, py, cnt, Total, misc);
 }
 
 template <typename T>
@@ -406,11 +432,14 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
             c->launches -= 1;
         } else if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         else rf_wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
-        rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w);
+        if (sample + 1 < max_spp || !c->gi_fuse_final) rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w);
+        else rf_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w);   // the last sample's shade_b + resolve in one pass
         c->launches += 5;
     }
-    rf_wf_resolve_kernel<<<pgrid, 256, 0, s>>>(a, w);
+    if (!c->gi_fuse_final) {
+        rf_wf_resolve_kernel<<<pgrid, 256, 0, s>>>(a, w);
+        c->launches += 1;
+    }
     VX_CUDA(cudaGetLastError());
-    c->launches += 1;
     return VXRT_OK;
 }
