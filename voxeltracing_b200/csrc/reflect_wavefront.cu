@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
                 w.P[i] = make_float4(P.x, P.y, P.z, PBRMap.x);
                 w.I[i] = make_float4(I.x, I.y, I.z, (PBRMap.y > 0.05f) ? 1.0f : 0.0f);
                 w.Nmap[i] = make_float4(Nmap.x, Nmap.y, Nmap.z, 0.0f);
-                w.Total[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                w.misc[i] = make_float4(0.001f, 0.0f, 0.0f, 0.0f);
+                // TotalColor = 0 and (AveragedHitDistance, TotalMeaningfulHits, EmissivityMask, ComputedShadow) = (0.001, 0, 0, 0) are not stored:
+                // the first sample's shading starts from these constants instead of loading them (`first` in shade_a / shade_b / final)
                 w.cnt[i] = make_int4(0, 0, SPP, 0);
             }
         }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
 
 // LPVGI: ApproximateGILPV for hits whose reprojection failed (a.lpv_gi); a template flag so the default path compiles without it
 template <bool LPVGI>
-__global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+__global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
     const bool inside = px < a.col1 && py < a.row1;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
         const float T = w.hitT[i];
         const unsigned info = w.hitInfo[i];
         int4 cnt = w.cnt[i];
-        float4 misc = w.misc[i];
-        float4 Total = w.Total[i];
+        float4 misc = first ? make_float4(0.001f, 0.0f, 0.0f, 0.0f) : w.misc[i];
+        float4 Total = first ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : w.Total[i];
         const int SPP = cnt.z;
         if (T > 0.0f) {
             const f3 Normal = unpack_normal(info);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
 
 // shade_b of one path: the sample's sun-shadow term once the shadow ray is back; leaves the updated totals in Total / misc (written back
 // only when `store`)
-VXD bool rf_shade_b_path(const RfWf& w, int i, float4& Total, float4& misc, bool store) {
+VXD bool rf_shade_b_path(const RfWf& w, int i, float4& Total, float4& misc, bool store, bool first) {
     const float4 amb = w.Amb[i];
     if (amb.w == 0.0f) return false;
     const float4 res = w.Res[i];
@@ -322,7 +322,7 @@ VXD bool rf_shade_b_path(const RfWf& w, int i, float4& Total, float4& misc, bool
         const float Shadow = gmin(misc.w, 1.0f);
         Direct = Direct + F3(res.x, res.y, res.z) * gclamp(1.0f - Shadow, 0.0f, 1.0f);
     }
-    Total = w.Total[i];
+    Total = first ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : w.Total[i];   // a path that hit something has not stored its total yet (shade_a only stores sky samples)
     Total = make_float4(Total.x + Direct.x, Total.y + Direct.y, Total.z + Direct.z, Total.w + 1.0f);
     if (store) w.Total[i] = Total;
     return true;
@@ -340,13 +340,13 @@ VXD void rf_resolve_pixel(const ReflArgs& a, int px, int py, const int4 cnt, flo
     a.emissive[pi] = float_to_unorm8(gclamp(misc.z, 0.0f, 1.0f));
 }
 
-__global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+__global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
     if (px >= a.col1 || py >= a.row1) return;
     const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     float4 Total, misc;
-    rf_shade_b_path(w, i, Total, misc, true);
+    rf_shade_b_path(w, i, Total, misc, true, first != 0);
 }
 
 __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constan
 // the LAST sample's shade_b fused with resolve (set_option "gi_fuse_final" governs both wavefronts): the totals of a path whose sample was still
 // waiting for its shadow ray go from registers into the attachments instead of through Total / misc and back; one launch less.  Same
 // arithmetic in the same order, bit-identical.
-__global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
+__global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
     if (px >= a.col1 || py >= a.row1) return;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant_
     const int4 cnt = w.cnt[i];
     if (cnt.w < 0) return;
     float4 Total, misc;
-    if (!rf_shade_b_path(w, i, Total, misc, false)) { Total = w.Total[i]; misc = w.misc[i]; }
+    if (!rf_shade_b_path(w, i, Total, misc, false, first != 0)) { Total = w.Total[i]; misc = w.misc[i]; }
     rf_resolve_pixel(a, px, py, cnt, Total, misc);
 }
 
@@ -423,8 +423,8 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         // the shading reads the GI attachments: on lane 1 of the pass-level concurrency this is where the pass meets the GI (ctx.h)
         if (sample == 0 && c->refl_gi_event) VX_CUDA(cudaStreamWaitEvent(s, c->refl_gi_event, 0));
-        if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w);
-        else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w);
+        if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
         if (c->trace_caps | c->trace_spill) {
             const ReflShadowRays pol = {w, strong};
             const int rc = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);
@@ -432,8 +432,8 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
             c->launches -= 1;
         } else if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         else rf_wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
-        if (sample + 1 < max_spp || !c->gi_fuse_final) rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w);
-        else rf_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w);   // the last sample's shade_b + resolve in one pass
+        if (sample + 1 < max_spp || !c->gi_fuse_final) rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        else rf_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w, sample == 0);   // the last sample's shade_b + resolve in one pass
         c->launches += 5;
     }
     if (!c->gi_fuse_final) {
