@@ -316,11 +316,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_shade_kernel(const __
                     w.rayD[i] = make_float4(NewDirection.x, NewDirection.y, NewDirection.z, 1.0f);
                     push_bounce = true;
                     const float dao = 2.0f;
-                    if (T < dao && T > 0.0f) {  // AO from the first bounce (:637-650)
-                        float4 oa = w.odirAo[i];
-                        oa.w = gmax(T / dao, 0.0f);
-                        w.odirAo[i] = oa;
-                    }
+                    if (T < dao && T > 0.0f)   // AO from the first bounce (:637-650): only the scalar is rewritten
+                        reinterpret_cast<float*>(w.odirAo + i)[3] = gmax(T / dao, 0.0f);
                 }
                 still_alive = true;
             } else {

@@ -70,6 +70,16 @@ VXD float normal_id(f3 n) {
     return 0.0f;
 }
 
+// register allocation of the two per-pixel trace kernels: like the queue trace kernels (trace_queue.cuh VX_TRACE_OCC) a bare
+// __launch_bounds__(256) makes ptxas stop at 40 - 44 registers and reload the grid dimensions from the constant bank inside the loop
+#ifndef VX_PRIMARY_OCC
+#define VX_PRIMARY_OCC 4   // 44 / 48 registers: primary pass 0.103 -> 0.099 ms, sun shadow unchanged (profiles/r2_x_tocc_sweep.txt, pocc4)
+#endif
+#if VX_PRIMARY_OCC > 0
+#define VX_PRIMARY_BOUNDS __launch_bounds__(256, VX_PRIMARY_OCC)
+#else
+#define VX_PRIMARY_BOUNDS __launch_bounds__(256)
+#endif
 // pixel of this thread: CTA = 32x8 pixels, warp = 8x4 tile
 VXD void pixel_of_thread(int& px, int& py, int row0, int col0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,7 +88,7 @@ VXD void pixel_of_thread(int& px, int& py, int row0, int col0) {
 }
 
 template <bool STATS, bool ALPHA>
-__global__ void __launch_bounds__(256) initial_trace_kernel(GridView g, const __grid_constant__ PrimaryArgs a,
+__global__ void VX_PRIMARY_BOUNDS initial_trace_kernel(GridView g, const __grid_constant__ PrimaryArgs a,
                                                             TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
     pixel_of_thread(px, py, a.row0, a.col0);
@@ -156,7 +166,7 @@ VXD f3 sample_cone(f2 Xi, float CosThetaMax) {
 }
 
 template <bool STATS, bool ALPHA>
-__global__ void __launch_bounds__(256) shadow_trace_kernel(GridView g, const __grid_constant__ ShadowArgs a,
+__global__ void VX_PRIMARY_BOUNDS shadow_trace_kernel(GridView g, const __grid_constant__ ShadowArgs a,
                                                            TraceStatsDev* stats, const __grid_constant__ AlphaCtx alpha) {
     int px, py;
     pixel_of_thread(px, py, a.row0, a.col0);
