@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __gr
     tile_pixel(px, py, a.row0, a.col0);
     if (px >= a.col1 || py >= a.row1) return;
     const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
+    // sample 0 keeps what it has just computed in registers; the pixel's position is only stored when it takes further samples
+    float4 p4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int bl = 0;
     if (sample == 0) {
         const size_t pi = (size_t)py * a.width + px;
         const f2 vtc = pixel_uv(px, py, a.width, a.height);
@@ -164,17 +167,18 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) gi_wf_gen_kernel(const __gr
         }
         SPP = iclamp(SPP, 1, 32);
         if (!a.sun_stronger) SPP *= 2;
-        w.pixP[i] = make_float4(P.x, P.y, P.z, (float)cvt_round(nid * 10.0f));
-        w.bl[i] = 0;
+        p4 = make_float4(P.x, P.y, P.z, (float)cvt_round(nid * 10.0f));
+        if (SPP > 1) w.pixP[i] = p4;
         w.spp[i] = SPP;
         // the accumulators are not cleared here: the first sample's finish_sample writes 0 + x instead of reading them
+    } else {
+        bl = w.bl[i];
+        if (bl < 0 || sample >= w.spp[i]) {
+            w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            return;
+        }
+        p4 = w.pixP[i];
     }
-    const int bl = w.bl[i];
-    if (bl < 0 || sample >= w.spp[i]) {
-        w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
-    }
-    const float4 p4 = w.pixP[i];
     const int face = (int)p4.w;
     const f3 Normal = face > 5 ? F3(0.5f) : face_normal(face);
     GiState st;

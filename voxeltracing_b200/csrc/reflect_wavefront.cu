@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
     tile_pixel(px, py, a.row0, a.col0);
     if (px >= a.col1 || py >= a.row1) return;
     const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
+    // sample 0 keeps what it has just computed in registers; the incident direction and the normal are only stored for a pixel that takes
+    // further samples, its metal flag travels in rayD.w (2 instead of 1)
+    float4 p4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), i4 = p4, n4 = p4;
+    int4 cnt = make_int4(0, 0, 0, 0);
     if (sample == 0) {
         const size_t pi = (size_t)py * a.width + px;
         const f2 vtc = pixel_uv(px, py, a.width, a.height);
@@ -139,12 +143,14 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
                 oColor = F4(r.x, r.y, r.z, 0.0f); oHit = 0.5f; oMask = 0.0f;
                 done = true;
             } else {
-                w.P[i] = make_float4(P.x, P.y, P.z, PBRMap.x);
-                w.I[i] = make_float4(I.x, I.y, I.z, (PBRMap.y > 0.05f) ? 1.0f : 0.0f);
-                w.Nmap[i] = make_float4(Nmap.x, Nmap.y, Nmap.z, 0.0f);
+                p4 = make_float4(P.x, P.y, P.z, PBRMap.x);
+                i4 = make_float4(I.x, I.y, I.z, (PBRMap.y > 0.05f) ? 1.0f : 0.0f);
+                n4 = make_float4(Nmap.x, Nmap.y, Nmap.z, 0.0f);
+                w.P[i] = p4;
+                if (SPP > 1) { w.I[i] = i4; w.Nmap[i] = n4; }
                 // TotalColor = 0 and (AveragedHitDistance, TotalMeaningfulHits, EmissivityMask, ComputedShadow) = (0.001, 0, 0, 0) are not stored:
                 // the first sample's shading starts from these constants instead of loading them (`first` in shade_a / shade_b / final)
-                w.cnt[i] = make_int4(0, 0, SPP, 0);
+                cnt = make_int4(0, 0, SPP, 0);
             }
         }
         if (done) {
@@ -156,12 +162,14 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
             return;
         }
     }
-    int4 cnt = w.cnt[i];
-    if (cnt.w < 0 || sample >= cnt.z) {
-        w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
+    if (sample != 0) {
+        cnt = w.cnt[i];
+        if (cnt.w < 0 || sample >= cnt.z) {
+            w.rayD[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            return;
+        }
+        p4 = w.P[i]; i4 = w.I[i]; n4 = w.Nmap[i];
     }
-    const float4 p4 = w.P[i], i4 = w.I[i], n4 = w.Nmap[i];
     const f3 Nmap = F3(n4.x, n4.y, n4.z);
     RfState st;
     st.px = px; st.py = py; st.CurrentBLSample = cnt.w;
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
     const f3 R = reflect(F3(i4.x, i4.y, i4.z), ReflectionNormal);
     cnt.w = st.CurrentBLSample;
     w.cnt[i] = cnt;
-    w.rayD[i] = make_float4(R.x, R.y, R.z, 1.0f);
+    w.rayD[i] = make_float4(R.x, R.y, R.z, i4.w != 0.0f ? 2.0f : 1.0f);
 }
 
 // LPVGI: ApproximateGILPV for hits whose reprojection failed (a.lpv_gi); a template flag so the default path compiles without it
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
             misc.y += 1.0f;
         } else {
             const f3 Atmos = texcube_sample(a.sky, normalize(R));
-            const f3 am = Atmos * gmix(1.0f, 1.175f, w.I[i].w);
+            const f3 am = Atmos * gmix(1.0f, 1.175f, d4.w == 2.0f ? 1.0f : 0.0f);   // the metal flag (PBRMap.y > 0.05) rides in rayD.w
             Total = make_float4(Total.x + am.x, Total.y + am.y, Total.z + am.z, Total.w + 1.0f);
             w.Amb[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             w.Total[i] = Total;
