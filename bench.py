@@ -71,6 +71,8 @@ def parse_args():
                     help="what is gathered to rank 0 / read back in the end-to-end leg: 'final' = G-buffer, shadow, GI, reflection and direct "
                          "attachments (44 B/px); 'all' adds the material G-buffer intermediates only later passes on the device consume (61 B/px)")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="vxrt_cuda_set_option(NAME, VALUE) on the bench's context after its own options (A / B runs: lane2_direct, refl_defer_gi, copy_lanes ...)")
     return ap.parse_args()
 
 
@@ -705,6 +707,9 @@ def main():
     # wavefront; FrameRenderer.submit joins the lanes at the end of the frame, so the step events below bracket all of it
     ctx.set_option("pass_overlap", 0 if args.no_pass_overlap else 1)
     ctx.set_option("wf_bands", args.wf_bands)
+    for kv in args.opt:
+        k_, v_ = kv.split("=", 1)
+        ctx.set_option(k_, int(v_, 0))
     total_rays = int(sum(rays_per_step))
     total_iters = int(sum(v["iterations"] for v in pass_stats.values()))
 

@@ -106,3 +106,59 @@ def test_pass_overlap_does_not_change_a_bit(workload, reproject, inputs512):
     finally:
         ctx.set_option("pass_overlap", 0); ctx.set_option("wf_bands", 1)
         ctx.close()
+
+
+@pytest.mark.parametrize("refl_spp", [1, 2])
+def test_lane2_direct_deferred_reflection_gi_and_lane_copies_do_not_change_a_bit(refl_spp, inputs512):
+    """The last additions to the pass-level concurrency, each behind its option (all on by default): the direct term on lane 2 beside a pending
+    reflection pass ("lane2_direct"), the reflection pass meeting the GI only where a sample is accumulated ("refl_defer_gi": Albedo and the AO
+    factor travel instead of the ambient product, formed later from the same operands in the same order), and read-backs of a lane-1 / lane-2
+    attachment that wait for that lane alone on a second copy stream ("copy_lanes").  Every output attachment equals the single-stream frame with
+    all three off, bit for bit: read synchronously after the frame, and through asynchronous copies queued right behind each pass (the bench's
+    end-to-end leg) over three consecutive frames into two alternating sets of page-locked buffers."""
+    import dataclasses
+    import torch
+    from voxeltracing_b200.pipeline import PASS_OUTPUTS
+    wl, blocks, inputs, ctx, fr = _setup("config4_1080p_gi", inputs512)
+    try:
+        fr.cfg = dataclasses.replace(fr.cfg, refl_spp=refl_spp)
+        frames = (3, 4, 5)
+
+        def run(overlap, lane2, defer, copy_lanes, async_copies):
+            ctx.set_option("pass_overlap", overlap); ctx.set_option("lane2_direct", lane2)
+            ctx.set_option("refl_defer_gi", defer); ctx.set_option("copy_lanes", copy_lanes)
+            out = []
+            host = [{}, {}]
+            for k, f in enumerate(frames):
+                def hook(name, where, k=k):
+                    if async_copies and where == "end":
+                        for a in PASS_OUTPUTS[name]:
+                            _, w, h, bpp = ctx.attachment_info(a)
+                            t = host[k & 1].get(a)
+                            if t is None:
+                                t = host[k & 1][a] = torch.empty(w * h * bpp, dtype=torch.uint8).pin_memory()
+                            ctx.copy_attachment_rect_async(a, t.data_ptr(), (0, 0))
+                fr.render(bench.camera_for(wl, f), f, hook=hook)
+                if async_copies:
+                    if k == 0:   # frame 0 is read out before its buffers are reused; frames 1 and 2 stay in flight: frame 2's passes rewrite the
+                        ctx.wait_reads()   # attachments frame 1's copies are still reading, ordered only by the device-side waits
+                        out.append({a: host[0][a].numpy().copy() for a in fr.outputs})
+                else:
+                    out.append({a: ctx.read_attachment(a).copy().view(np.uint8).ravel() for a in fr.outputs})
+            if async_copies:
+                ctx.wait_reads()
+                out.append({a: host[1][a].numpy().copy() for a in fr.outputs})
+                out.append({a: host[0][a].numpy().copy() for a in fr.outputs})
+            return out
+        want = run(0, 0, 0, 0, False)
+        for overlap, lane2, defer, copy_lanes, async_copies in ((0, 0, 1, 0, False), (1, 0, 0, 0, False), (1, 1, 0, 0, False), (1, 1, 1, 1, False),
+                                                                (1, 1, 1, 1, True), (1, 1, 1, 0, True), (1, 0, 1, 1, True)):
+            ctx.set_option("wf_bands", 2 if lane2 else 1)
+            got = run(overlap, lane2, defer, copy_lanes, async_copies)
+            for fw, fg in zip(want, got):
+                for a in fr.outputs:
+                    assert np.array_equal(fw[a], fg[a]), (refl_spp, overlap, lane2, defer, copy_lanes, async_copies, a)
+    finally:
+        for k_, v_ in (("pass_overlap", 0), ("wf_bands", 1), ("lane2_direct", 1), ("refl_defer_gi", 1), ("copy_lanes", 1)):
+            ctx.set_option(k_, v_)
+        ctx.close()

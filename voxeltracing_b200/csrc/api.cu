@@ -45,6 +45,11 @@ static int vxrt_join_lane1(vxrt_ctx* c, bool keep_fork) {
         VX_CUDA(cudaStreamWaitEvent(c->stream, c->lane1_tail, 0));
         c->lane1_pending = false; c->lane1_reads_gi = false;
     }
+    if (c->lane2_pending) {
+        VX_CUDA(cudaStreamWaitEvent(c->stream, c->lane2_tail, 0));
+        c->lane2_pending = false;
+    }
+    c->lane1_pre_refl_valid = false;
     if (!keep_fork) c->gi_fork_valid = false;
     return VXRT_OK;
 }
@@ -57,31 +62,44 @@ static int vxrt_join_lane1(vxrt_ctx* c, bool keep_fork) {
     DeviceGuard _device_guard((c)->device)
 #define REQUIRE_CTX(c)                                                          \
     REQUIRE_CTX_LANES(c);                                                       \
-    if ((c)->lane1_pending || (c)->gi_fork_valid) { if (int _jrc = vxrt_join_lane1(c, false)) return _jrc; }
+    if ((c)->lane1_pending || (c)->lane2_pending || (c)->gi_fork_valid) { if (int _jrc = vxrt_join_lane1(c, false)) return _jrc; }
 #define REQUIRE_CTX_READER(c)                                                   \
     REQUIRE_CTX_LANES(c);                                                       \
-    if ((c)->lane1_pending) { if (int _jrc = vxrt_join_lane1(c, true)) return _jrc; }
+    if ((c)->lane1_pending || (c)->lane2_pending) { if (int _jrc = vxrt_join_lane1(c, true)) return _jrc; }
 
 static bool lanes_on(const vxrt_ctx* c) { return c->pass_overlap && !c->probe_on && !(c->trace_caps | c->trace_spill); }
 static int ensure_lanes(vxrt_ctx* c) {
     if (c->lane1) return VXRT_OK;
-    VX_CUDA(cudaStreamCreateWithFlags(&c->lane1, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&c->gi_fork, &c->gi_done, &c->lane0_mark, &c->lane1_tail}) VX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&c->gi_fork, &c->gi_done, &c->lane0_mark, &c->lane1_tail, &c->lane1_pre_refl, &c->lane2_tail})
+        VX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    VX_CUDA(cudaStreamCreateWithFlags(&c->lane2, cudaStreamNonBlocking));
+    VX_CUDA(cudaStreamCreateWithFlags(&c->lane1, cudaStreamNonBlocking));   // last: c->lane1 != nullptr means all of the above exist
     return VXRT_OK;
 }
 // a lane-1 pass (sun-shadow trace, direct term): waits for what lane 0 had queued before the frame's diffuse_trace (or for everything, if there
 // was none), runs with c->stream swapped, leaves its tail event behind
 struct Lane1Pass {
-    vxrt_ctx* c; cudaStream_t saved; void* wf; size_t wf_cap; bool on, arena;
+    vxrt_ctx* c; cudaStream_t saved; void* wf; size_t wf_cap; bool on, arena, to2 = false;
     explicit Lane1Pass(vxrt_ctx* c_, bool own_arena = false) : c(c_), saved(c_->stream), wf(c_->d_wf), wf_cap(c_->wf_cap), on(lanes_on(c_)), arena(own_arena) {}
     // reads_gi: the pass reads the GI attachments; gi_first: from its first kernel on (otherwise from the point where the launcher waits for
-    // c->refl_gi_event)
-    int begin(bool reads_gi = false, bool gi_first = false) {
+    // c->refl_gi_event).  gi_free: the pass reads neither the GI nor the reflections (the direct term), so it may overtake a pending
+    // reflection pass on lane 2 (ctx.h).
+    int begin(bool reads_gi = false, bool gi_first = false, bool gi_free = false) {
         if (!on) return VXRT_OK;
         if (int rc = ensure_lanes(c)) return rc;
+        if (gi_free && c->lane2_direct && c->gi_fork_valid && c->lane1_pending && c->lane1_reads_gi && c->lane1_pre_refl_valid) {
+            VX_CUDA(cudaStreamWaitEvent(c->lane2, c->gi_fork, 0));
+            VX_CUDA(cudaStreamWaitEvent(c->lane2, c->lane1_pre_refl, 0));
+            to2 = true;
+            c->stream = c->lane2;
+            return VXRT_OK;
+        }
+        if (c->lane2_pending) VX_CUDA(cudaStreamWaitEvent(c->lane1, c->lane2_tail, 0));   // lane 2 may still read what this pass rewrites
         if (c->gi_fork_valid) {
             VX_CUDA(cudaStreamWaitEvent(c->lane1, c->gi_fork, 0));
             if (reads_gi) {
+                VX_CUDA(cudaEventRecord(c->lane1_pre_refl, c->lane1));   // everything lane 1 holds before this pass (and before its wait for the GI)
+                c->lane1_pre_refl_valid = true;
                 if (gi_first) VX_CUDA(cudaStreamWaitEvent(c->lane1, c->gi_done, 0));
                 else c->refl_gi_event = c->gi_done;
             }
@@ -95,6 +113,13 @@ struct Lane1Pass {
         return VXRT_OK;
     }
     int end(int rc) {
+        if (on && to2 && c->stream == c->lane2) {
+            c->stream = saved;
+            const cudaError_t e = cudaEventRecord(c->lane2_tail, c->lane2);
+            c->lane2_pending = true;
+            if (rc == VXRT_OK && e != cudaSuccess) return vxrt_check_cuda(e, "cudaEventRecord(lane2_tail)");
+            return rc;
+        }
         if (!on || c->stream != c->lane1) return rc;
         if (arena) { c->d_wf1 = c->d_wf; c->wf1_cap = c->wf_cap; c->d_wf = wf; c->wf_cap = wf_cap; }
         c->refl_gi_event = nullptr;
@@ -108,6 +133,44 @@ struct Lane1Pass {
 #define REQUIRE_PTR(p) \
     if (!(p)) return vxrt_fail(VXRT_E_INVALID, "%s: %s is NULL", __func__, #p)
 
+static int sync_copy_streams(vxrt_ctx* c) {
+    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (cudaStream_t cs : c->copy_stream_lane) if (cs) VX_CUDA(cudaStreamSynchronize(cs));
+    return VXRT_OK;
+}
+// Orders a copy of attachment `id` behind the pass that produced it and returns the copy stream to use.  With copy_lanes an attachment that a
+// pending lane-1 / lane-2 pass wrote waits for that lane alone and goes to that lane's own copy stream; an attachment of lane 0 waits for lane 0
+// alone.  Without it the lanes are joined into `stream` first (keeping the frame's fork point), as every reader does.
+static int begin_copy(vxrt_ctx* c, int id, cudaStream_t* cs_out) {
+    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->att_ready[id]) {
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
+        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
+    }
+    cudaStream_t prod = c->stream, cs = c->copy_stream;
+    int lane = 0;
+    if (c->copy_lanes) {
+        if (c->att_lane[id] == 1 && c->lane1_pending) { prod = c->lane1; lane = 1; }
+        else if (c->att_lane[id] == 2 && c->lane2_pending) { prod = c->lane2; lane = 2; }
+    } else if (c->lane1_pending || c->lane2_pending) {
+        if (int jrc = vxrt_join_lane1(c, true)) return jrc;
+    }
+    if (lane) {
+        cudaStream_t& ls = c->copy_stream_lane[lane - 1];
+        if (!ls) VX_CUDA(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
+        cs = ls;
+    }
+    if (c->att_read_pending[id]) VX_CUDA(cudaStreamWaitEvent(cs, c->att_read_done[id], 0));   // an earlier copy of it may be on the other copy stream
+    VX_CUDA(cudaEventRecord(c->att_ready[id], prod));               // everything issued there so far has produced the attachment
+    VX_CUDA(cudaStreamWaitEvent(cs, c->att_ready[id], 0));
+    *cs_out = cs;
+    return VXRT_OK;
+}
+static int end_copy(vxrt_ctx* c, int id, cudaStream_t cs) {
+    VX_CUDA(cudaEventRecord(c->att_read_done[id], cs));
+    c->att_read_pending[id] = true;
+    return VXRT_OK;
+}
 int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return vxrt_fail(VXRT_E_INVALID, "bad attachment size %dx%d", w, h);
@@ -119,8 +182,9 @@ int vxrt_ensure_attachment(vxrt_ctx* c, int id, int w, int h, int bpp) {
     }
     if (need > a.capacity && a.external)
         return vxrt_fail(VXRT_E_INVALID, "attachment %d: bound storage holds %zu bytes, the pass needs %zu", id, a.capacity, need);
+    c->att_lane[id] = (c->lane1 && c->stream == c->lane1) ? 1 : (c->lane2 && c->stream == c->lane2) ? 2 : 0;
     if (need > a.capacity) {
-        if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+        if (int src = sync_copy_streams(c)) return src;
         if (a.ptr) VX_CUDA(cudaFree(a.ptr));
         a.ptr = nullptr;
         a.capacity = 0;
@@ -244,10 +308,10 @@ int vxrt_cuda_destroy(vxrt_ctx* c) {
     for (int i = 0; i < VXRT_ATT_COUNT; ++i)
         if (!c->att[i].external) cudaFree(c->att[i].ptr);
     for (cudaEvent_t e : c->probe_ev) cudaEventDestroy(e);
-    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (cudaStream_t cs : {c->copy_stream, c->copy_stream_lane[0], c->copy_stream_lane[1]}) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
-    if (c->lane1) { cudaStreamSynchronize(c->lane1); cudaStreamDestroy(c->lane1); }
-    for (cudaEvent_t e : {c->gi_fork, c->gi_done, c->lane0_mark, c->lane1_tail}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t ls : {c->lane1, c->lane2}) if (ls) { cudaStreamSynchronize(ls); cudaStreamDestroy(ls); }
+    for (cudaEvent_t e : {c->gi_fork, c->gi_done, c->lane0_mark, c->lane1_tail, c->lane1_pre_refl, c->lane2_tail}) if (e) cudaEventDestroy(e);
     cudaFree(c->d_wf1);
     for (int l = 0; l < 2; ++l) {
         for (auto& b : c->band[l]) {
@@ -297,6 +361,9 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "gi_fuse_final")) { c->gi_fuse_final = value != 0; return VXRT_OK; }
     if (!strcmp(name, "gi_overlap")) { c->gi_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "pass_overlap")) { c->pass_overlap = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "lane2_direct")) { c->lane2_direct = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "refl_defer_gi")) { c->refl_defer_gi = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "copy_lanes")) { c->copy_lanes = value != 0; return VXRT_OK; }
     if (!strcmp(name, "wf_bands")) { if (value < 1 || value > 4) return vxrt_fail(VXRT_E_INVALID, "wf_bands: 1..4"); c->wf_bands = value; return VXRT_OK; }
     if (!strcmp(name, "trace_caps")) { c->trace_caps = value & 0xffffff; return VXRT_OK; }
     if (!strcmp(name, "trace_spill")) { c->trace_spill = value & 0xffffff; return VXRT_OK; }
@@ -493,46 +560,32 @@ int vxrt_cuda_write_attachment(vxrt_ctx* c, int32_t id, int32_t width, int32_t h
     return VXRT_OK;
 }
 int vxrt_cuda_read_attachment_async(vxrt_ctx* c, int32_t id, void* dst, size_t bytes) {
-    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
     size_t have = (size_t)a.width * a.height * a.bpp;
     if (bytes != have) return vxrt_fail(VXRT_E_INVALID, "attachment %d holds %zu bytes, caller asked for %zu", id, have, bytes);
-    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    if (!c->att_ready[id]) {
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
-    }
-    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));               // everything issued so far has produced the attachment
-    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
-    VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, c->copy_stream));
-    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
-    c->att_read_pending[id] = true;
-    return VXRT_OK;
+    cudaStream_t cs;
+    if (int rc = begin_copy(c, id, &cs)) return rc;
+    VX_CUDA(cudaMemcpyAsync(dst, a.ptr, have, cudaMemcpyDeviceToHost, cs));
+    return end_copy(c, id, cs);
 }
 int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, void* dst) {
-    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(dst);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
     if (rows == 0) { row0 = 0; rows = a.height; }
     if (row0 < 0 || rows < 0 || row0 + rows > a.height) return vxrt_fail(VXRT_E_INVALID, "copy_attachment_rows: rows [%d,+%d) of %d", row0, rows, a.height);
-    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    if (!c->att_ready[id]) {
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
-    }
     const size_t row_bytes = (size_t)a.width * a.bpp;
-    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));
-    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
-    VX_CUDA(cudaMemcpyAsync(dst, (const uint8_t*)a.ptr + (size_t)row0 * row_bytes, (size_t)rows * row_bytes, cudaMemcpyDefault, c->copy_stream));
-    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
-    c->att_read_pending[id] = true;
-    return VXRT_OK;
+    cudaStream_t cs;
+    if (int rc = begin_copy(c, id, &cs)) return rc;
+    VX_CUDA(cudaMemcpyAsync(dst, (const uint8_t*)a.ptr + (size_t)row0 * row_bytes, (size_t)rows * row_bytes, cudaMemcpyDefault, cs));
+    return end_copy(c, id, cs);
 }
 int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* c, int32_t id, int32_t row0, int32_t rows, int32_t col0, int32_t cols, void* dst_image) {
-    REQUIRE_CTX_READER(c); REQUIRE_PTR(dst_image);
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(dst_image);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     const Attachment& a = c->att[id];
     if (!a.ptr) return vxrt_fail(VXRT_E_STATE, "attachment %d has not been rendered", id);
@@ -540,19 +593,14 @@ int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* c, int32_t id, int32_t row0, 
     if (cols == 0) { col0 = 0; cols = a.width; }
     if (row0 < 0 || rows < 0 || row0 + rows > a.height || col0 < 0 || cols < 0 || col0 + cols > a.width)
         return vxrt_fail(VXRT_E_INVALID, "copy_attachment_rect: rows [%d,+%d) x columns [%d,+%d) of %dx%d", row0, rows, col0, cols, a.width, a.height);
-    if (!c->copy_stream) VX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    if (!c->att_ready[id]) {
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_ready[id], cudaEventDisableTiming));
-        VX_CUDA(cudaEventCreateWithFlags(&c->att_read_done[id], cudaEventDisableTiming));
-    }
     const size_t pitch = (size_t)a.width * a.bpp, off = (size_t)row0 * pitch + (size_t)col0 * a.bpp;
-    VX_CUDA(cudaEventRecord(c->att_ready[id], c->stream));
-    VX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->att_ready[id], 0));
-    if (rows > 0 && cols > 0)
-        VX_CUDA(cudaMemcpy2DAsync((uint8_t*)dst_image + off, pitch, (const uint8_t*)a.ptr + off, pitch, (size_t)cols * a.bpp, (size_t)rows, cudaMemcpyDefault, c->copy_stream));
-    VX_CUDA(cudaEventRecord(c->att_read_done[id], c->copy_stream));
-    c->att_read_pending[id] = true;
-    return VXRT_OK;
+    cudaStream_t cs;
+    if (int rc = begin_copy(c, id, &cs)) return rc;
+    if (rows > 0 && cols == a.width)   // whole rows are one contiguous block: a linear copy instead of `rows` strided ones
+        VX_CUDA(cudaMemcpyAsync((uint8_t*)dst_image + off, (const uint8_t*)a.ptr + off, (size_t)rows * pitch, cudaMemcpyDefault, cs));
+    else if (rows > 0 && cols > 0)
+        VX_CUDA(cudaMemcpy2DAsync((uint8_t*)dst_image + off, pitch, (const uint8_t*)a.ptr + off, pitch, (size_t)cols * a.bpp, (size_t)rows, cudaMemcpyDefault, cs));
+    return end_copy(c, id, cs);
 }
 int vxrt_cuda_shared_alloc(vxrt_ctx* c, size_t bytes, void** dev_ptr, uint8_t handle[64]) {
     REQUIRE_CTX(c); REQUIRE_PTR(dev_ptr); REQUIRE_PTR(handle);
@@ -569,7 +617,7 @@ int vxrt_cuda_shared_alloc(vxrt_ctx* c, size_t bytes, void** dev_ptr, uint8_t ha
 }
 int vxrt_cuda_shared_free(vxrt_ctx* c, void* dev_ptr) {
     REQUIRE_CTX(c);
-    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (int src = sync_copy_streams(c)) return src;
     VX_CUDA(cudaFree(dev_ptr));
     return VXRT_OK;
 }
@@ -582,7 +630,7 @@ int vxrt_cuda_shared_open(vxrt_ctx* c, const uint8_t handle[64], void** dev_ptr)
 }
 int vxrt_cuda_shared_close(vxrt_ctx* c, void* dev_ptr) {
     REQUIRE_CTX(c);
-    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (int src = sync_copy_streams(c)) return src;
     VX_CUDA(cudaIpcCloseMemHandle(dev_ptr));
     return VXRT_OK;
 }
@@ -590,20 +638,22 @@ int vxrt_cuda_join_reads(vxrt_ctx* c) {
     REQUIRE_CTX_READER(c);
     if (!c->copy_stream) return VXRT_OK;
     if (!c->copies_joined) VX_CUDA(cudaEventCreateWithFlags(&c->copies_joined, cudaEventDisableTiming));
-    VX_CUDA(cudaEventRecord(c->copies_joined, c->copy_stream));
-    VX_CUDA(cudaStreamWaitEvent(c->stream, c->copies_joined, 0));
+    for (cudaStream_t cs : {c->copy_stream, c->copy_stream_lane[0], c->copy_stream_lane[1]}) {   // a wait captures the event's state at the call, so one event serves both
+        if (!cs) continue;
+        VX_CUDA(cudaEventRecord(c->copies_joined, cs));
+        VX_CUDA(cudaStreamWaitEvent(c->stream, c->copies_joined, 0));
+    }
     return VXRT_OK;
 }
 int vxrt_cuda_wait_reads(vxrt_ctx* c) {
     REQUIRE_CTX_READER(c);
-    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
-    return VXRT_OK;
+    return sync_copy_streams(c);
 }
 int vxrt_cuda_bind_attachment(vxrt_ctx* c, int32_t id, void* dev_ptr, size_t capacity) {
     REQUIRE_CTX(c);
     if (id < 0 || id >= VXRT_ATT_COUNT) return vxrt_fail(VXRT_E_INVALID, "bad attachment id %d", id);
     if (dev_ptr && capacity == 0) return vxrt_fail(VXRT_E_INVALID, "bind_attachment: capacity is 0");  // before anything is released
-    if (c->copy_stream) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (int src = sync_copy_streams(c)) return src;
     c->att_read_pending[id] = false;
     Attachment& a = c->att[id];
     if (a.ptr && !a.external) {
@@ -762,7 +812,7 @@ int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
     if ((rc = require_att(c, __func__, VXRT_ATT_GBUF_ALBEDO, "vxrt_cuda_generate_gbuffer"))) return rc;
     if ((rc = require_att(c, __func__, c->shadow_source, c->shadow_source == VXRT_ATT_SHADOW ? "vxrt_cuda_shadow_trace" : "the shadow denoiser"))) return rc;
     Lane1Pass lane(c);
-    if ((rc = lane.begin())) return rc;
+    if ((rc = lane.begin(false, false, true))) return rc;
     return lane.end(vxrt_launch_shade_direct(c, *p));
 }
 int vxrt_cuda_diffuse_trace(vxrt_ctx* c, const vxrt_gi_params* p) {

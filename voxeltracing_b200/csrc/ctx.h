@@ -104,6 +104,19 @@ struct vxrt_ctx {
     cudaEvent_t refl_gi_event = nullptr;
     void* d_wf1 = nullptr;
     size_t wf1_cap = 0;
+    // Lane 2 (set_option "lane2_direct", on by default): the direct term reads the primary / material G-buffer and the sun shadow, never the
+    // GI or the reflections.  Queued on lane 1 behind a reflection pass it would sit behind that pass's wait for the GI; when such a pass is
+    // pending it goes to a stream of its own that waits for the frame's fork point and for what lane 1 held BEFORE the reflection pass
+    // (lane1_pre_refl, recorded by the reflection pass's begin).  Every later lane pass and every join wait for lane 2 as well.
+    bool lane2_direct = true;
+    cudaStream_t lane2 = nullptr;
+    cudaEvent_t lane1_pre_refl = nullptr, lane2_tail = nullptr;
+    bool lane1_pre_refl_valid = false, lane2_pending = false;
+    // The reflection pass without screen-space reprojection and without the LPV term reads the GI only as the per-PIXEL ambient base
+    // (BaseIndirectDiffuse), which enters a hit's colour as ((base * 1) * clamp(AO)) * albedo.  With set_option "refl_defer_gi" (default on)
+    // shade_a leaves albedo and the AO factor in the path state and the product is formed where the sample is accumulated (shade_b / final):
+    // same operands, same order, bit-identical - and the pass meets the GI only at its last kernel instead of at its first shading kernel.
+    bool refl_defer_gi = true;
     // Band pipelining of the wavefront passes (set_option "wf_bands", default 1 = off): the tile of a GI / reflection pass is cut into row
     // bands, each band's whole kernel sequence is queued on its own stream with its own path-state arena, so while one band is in a shading
     // kernel (waiting on memory, issue slots 58 % busy) another is in a trace kernel (issue bound) and the two fill each other's gaps and tails.
@@ -149,6 +162,12 @@ struct vxrt_ctx {
     // asynchronous read-back (vxrt_cuda_read_attachment_async): copies run on their own stream, ordered against
     // the passes by one event pair per attachment
     cudaStream_t copy_stream = nullptr;
+    // set_option "copy_lanes" (default on): a copy of an attachment that a pending lane-1 / lane-2 pass produced waits for THAT lane (not for
+    // a join of the lanes into `stream`, which would put it behind the whole GI) and runs on that lane's own copy stream, so it does not
+    // queue behind the copies of another lane's attachments either
+    cudaStream_t copy_stream_lane[2] = {nullptr, nullptr};
+    bool copy_lanes = true;
+    uint8_t att_lane[VXRT_ATT_COUNT] = {};           // lane whose pass last (re)wrote the attachment (vxrt_ensure_attachment)
     cudaEvent_t att_ready[VXRT_ATT_COUNT] = {};      // recorded on `stream` when a read is requested
     cudaEvent_t att_read_done[VXRT_ATT_COUNT] = {};  // recorded on `copy_stream` after the copy
     bool att_read_pending[VXRT_ATT_COUNT] = {};

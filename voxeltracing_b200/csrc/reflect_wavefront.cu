@@ -31,8 +31,10 @@ struct RfWf {
     float4* rayD;     // reflection direction (xyz), active flag (w)
     float* hitT;
     unsigned* hitInfo;
-    float4* Amb;      // Ambient (xyz); w: 0 = sample already accumulated, 1 = waits for shadeB
+    float4* Amb;      // Ambient (xyz); w: 0 = sample already accumulated, 1 = waits for shadeB, 2 = emissive override (no sun term)
+                      // DEFER (ctx.h refl_defer_gi), w == 1: xyz = Albedo, the ambient product is formed in shadeB
     float4* Res;      // max(Result, 0) of CalculateDirectionalLight (xyz); w: 1 = take ComputedShadow from shadowRes
+                      // DEFER: |w| = clamp(AO, 0.1, 1), w < 0 = take ComputedShadow from shadowRes
     float* shadowRes;
     float4* qShadowO; // compacted shadow rays
     int* counters;
@@ -181,8 +183,21 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_gen_kernel(const __gr
     w.rayD[i] = make_float4(R.x, R.y, R.z, i4.w != 0.0f ? 2.0f : 1.0f);
 }
 
-// LPVGI: ApproximateGILPV for hits whose reprojection failed (a.lpv_gi); a template flag so the default path compiles without it
-template <bool LPVGI>
+// BaseIndirectDiffuse = SHToIrridiance(texture(u_DiffuseSHy, v_TexCoords), texture(u_DiffuseCoCg, v_TexCoords)) of main(): a function of the
+// PIXEL, not of the hit
+VXD f3 rf_base_indirect_diffuse(const ReflArgs& a, int px, int py) {
+    float bsh[4], bcc[2];
+    const f2 vtc = pixel_uv(px, py, a.width, a.height);
+    att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, bsh);
+    att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, bcc);
+    return sh_to_irradiance_a(F4(bsh[0], bsh[1], bsh[2], bsh[3]), F2(bcc[0], bcc[1]));
+}
+
+// LPVGI: ApproximateGILPV for hits whose reprojection failed (a.lpv_gi); a template flag so the default path compiles without it.
+// DEFER (only without a.reproject / a.lpv_gi, where the ambient term of a hit is ((BaseIndirectDiffuse * 1) * clamp(AO)) * Albedo): the kernel
+// does not read the GI attachments at all; it leaves Albedo and the AO factor in Amb / Res and shade_b forms the product from the same
+// operands in the same order.
+template <bool LPVGI, bool DEFER>
 __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
@@ -213,14 +228,9 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
             const int reference_id = iclamp((int)(info & 0xffu), 0, 127);
             bool ReprojectionSuccessful = false;
             f2 SS = F2(-1.0f, -1.0f);
-            // BaseIndirectDiffuse = SHToIrridiance(texture(u_DiffuseSHy, v_TexCoords), texture(u_DiffuseCoCg, v_TexCoords)) of main()
-            float bsh[4], bcc[2];
-            const f2 vtc = pixel_uv(px, py, a.width, a.height);
-            att_half_bilinear<4>(a.gi_sh, a.iw, a.ih, vtc, bsh);
-            att_half_bilinear<2>(a.gi_cocg, a.iw, a.ih, vtc, bcc);
-            const f3 b4 = sh_to_irradiance_a(F4(bsh[0], bsh[1], bsh[2], bsh[3]), F2(bcc[0], bcc[1]));
+            const f3 b4 = DEFER ? F3(0.0f) : rf_base_indirect_diffuse(a, px, py);
             f3 Ambient = b4;
-            if (a.reproject) {
+            if (!DEFER && a.reproject) {
                 f4 pp = mat4_mul(a.proj_view, F4(HitPosition.x, HitPosition.y, HitPosition.z, 1.0f));
                 f3 q = F3(pp.x / pp.w, pp.y / pp.w, pp.z / pp.w);
                 SS = F2(q.x * 0.5f + 0.5f, q.y * 0.5f + 0.5f);
@@ -273,7 +283,8 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
                 }
                 cnt.x = cnt.x + 1;
             }
-            Ambient = (Ambient * 1.0f * gclamp(AO, 0.1f, 1.0f)) * Albedo;
+            const float AOFactor = gclamp(AO, 0.1f, 1.0f);
+            if (!DEFER) Ambient = (Ambient * 1.0f * AOFactor) * Albedo;
             const f3 nm = xyz(texarray_sample(a.tex[VXRT_TEX_NORMAL], UV.x, UV.y, ids.y, 3.0f)) * 2.0f - F3(1.0f);
             const f3 NormalMapped = mat3_mul(Tangent, Bitangent, Normal, nm);
             // CalculateDirectionalLight = max(Result, 0) * clamp(1 - min(shadow, 1), 0, 1): evaluate the first factor now
@@ -290,8 +301,14 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
                     misc.z = 1.0f;
                 }
             }
-            w.Amb[i] = make_float4(Ambient.x, Ambient.y, Ambient.z, 1.0f + override_flag);
-            w.Res[i] = make_float4(Res.x, Res.y, Res.z, from_ray);
+            if (DEFER) {
+                const f3 av = override_flag != 0.0f ? Ambient : Albedo;
+                w.Amb[i] = make_float4(av.x, av.y, av.z, 1.0f + override_flag);
+                w.Res[i] = make_float4(Res.x, Res.y, Res.z, from_ray != 0.0f ? -AOFactor : AOFactor);
+            } else {
+                w.Amb[i] = make_float4(Ambient.x, Ambient.y, Ambient.z, 1.0f + override_flag);
+                w.Res[i] = make_float4(Res.x, Res.y, Res.z, from_ray);
+            }
             misc.x += T;
             misc.y += 1.0f;
         } else {
@@ -319,14 +336,21 @@ __global__ void __launch_bounds__(256, VX_SHADE_OCC) rf_wf_shade_a_kernel(const 
 
 // shade_b of one path: the sample's sun-shadow term once the shadow ray is back; leaves the updated totals in Total / misc (written back
 // only when `store`)
-VXD bool rf_shade_b_path(const RfWf& w, int i, float4& Total, float4& misc, bool store, bool first) {
+template <bool DEFER>
+VXD bool rf_shade_b_path(const ReflArgs& a, const RfWf& w, int px, int py, int i, float4& Total, float4& misc, bool store, bool first) {
     const float4 amb = w.Amb[i];
     if (amb.w == 0.0f) return false;
     const float4 res = w.Res[i];
     misc = w.misc[i];
-    if (res.w != 0.0f) { misc.w = w.shadowRes[i]; if (store) w.misc[i] = misc; }   // ComputedShadow = GetShadowAt(...)
+    if (DEFER ? res.w < 0.0f : res.w != 0.0f) { misc.w = w.shadowRes[i]; if (store) w.misc[i] = misc; }   // ComputedShadow = GetShadowAt(...)
     f3 Direct = F3(amb.x, amb.y, amb.z);
     if (amb.w < 2.0f) {
+        if (DEFER) {   // shade_a's `Ambient = (Ambient * 1.0f * clamp(AO, 0.1, 1)) * Albedo` with Ambient = BaseIndirectDiffuse
+            const f3 Albedo = Direct;
+            f3 Ambient = rf_base_indirect_diffuse(a, px, py);
+            Ambient = (Ambient * 1.0f * fabsf(res.w)) * Albedo;
+            Direct = Ambient;
+        }
         const float Shadow = gmin(misc.w, 1.0f);
         Direct = Direct + F3(res.x, res.y, res.z) * gclamp(1.0f - Shadow, 0.0f, 1.0f);
     }
@@ -348,13 +372,14 @@ VXD void rf_resolve_pixel(const ReflArgs& a, int px, int py, const int4 cnt, flo
     a.emissive[pi] = float_to_unorm8(gclamp(misc.z, 0.0f, 1.0f));
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(256) rf_wf_shade_b_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
     if (px >= a.col1 || py >= a.row1) return;
     const int i = (py - a.row0) * (a.col1 - a.col0) + (px - a.col0);
     float4 Total, misc;
-    rf_shade_b_path(w, i, Total, misc, true, first != 0);
+    rf_shade_b_path<DEFER>(a, w, px, py, i, Total, misc, true, first != 0);
 }
 
 __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constant__ ReflArgs a, RfWf w) {
@@ -370,6 +395,7 @@ __global__ void __launch_bounds__(256) rf_wf_resolve_kernel(const __grid_constan
 // the LAST sample's shade_b fused with resolve (set_option "gi_fuse_final" governs both wavefronts): the totals of a path whose sample was still
 // waiting for its shadow ray go from registers into the attachments instead of through Total / misc and back; one launch less.  Same
 // arithmetic in the same order, bit-identical.
+template <bool DEFER>
 __global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant__ ReflArgs a, RfWf w, int first) {
     int px, py;
     tile_pixel(px, py, a.row0, a.col0);
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(256) rf_wf_final_kernel(const __grid_constant_
     const int4 cnt = w.cnt[i];
     if (cnt.w < 0) return;
     float4 Total, misc;
-    if (!rf_shade_b_path(w, i, Total, misc, false, first != 0)) { Total = w.Total[i]; misc = w.misc[i]; }
+    if (!rf_shade_b_path<DEFER>(a, w, px, py, i, Total, misc, false, first != 0)) { Total = w.Total[i]; misc = w.misc[i]; }
     rf_resolve_pixel(a, px, py, cnt, Total, misc);
 }
 
@@ -419,6 +445,8 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
     int max_spp = a.spp < 1 ? 1 : (a.spp > 16 ? 16 : a.spp);
     const bool st = c->stats_on;
     cudaStream_t s = c->stream;
+    // without reprojection and without the LPV term the GI enters a sample only where it is accumulated (shade_b / final): see ctx.h refl_defer_gi
+    const bool defer = c->refl_defer_gi && !a.reproject && !a.lpv_gi;
     for (int sample = 0; sample < max_spp; ++sample) {
         VX_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), s));
         rf_wf_gen_kernel<<<pgrid, 256, 0, s>>>(a, w, sample);
@@ -430,9 +458,10 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
         } else if (st) rf_wf_trace_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         else rf_wf_trace_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, (int)n, a.trace_length, c->d_stats);
         // the shading reads the GI attachments: on lane 1 of the pass-level concurrency this is where the pass meets the GI (ctx.h)
-        if (sample == 0 && c->refl_gi_event) VX_CUDA(cudaStreamWaitEvent(s, c->refl_gi_event, 0));
-        if (a.lpv_gi) rf_wf_shade_a_kernel<true><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
-        else rf_wf_shade_a_kernel<false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        if (sample == 0 && c->refl_gi_event && !defer) VX_CUDA(cudaStreamWaitEvent(s, c->refl_gi_event, 0));
+        if (defer) rf_wf_shade_a_kernel<false, true><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        else if (a.lpv_gi) rf_wf_shade_a_kernel<true, false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        else rf_wf_shade_a_kernel<false, false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
         if (c->trace_caps | c->trace_spill) {
             const ReflShadowRays pol = {w, strong};
             const int rc = launch_trace_capped(c, g, pol, w.counters + 0, n, a.shadow_trace_length, c->d_stats);
@@ -440,8 +469,14 @@ int vxrt_launch_reflection_trace_wavefront(vxrt_ctx* c, const void* args_blob) {
             c->launches -= 1;
         } else if (st) rf_wf_trace_shadow_kernel<true><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
         else rf_wf_trace_shadow_kernel<false><<<lgrid, VX_TRACE_CTA, 0, s>>>(g, w, strong, a.shadow_trace_length, c->d_stats);
-        if (sample + 1 < max_spp || !c->gi_fuse_final) rf_wf_shade_b_kernel<<<pgrid, 256, 0, s>>>(a, w, sample == 0);
-        else rf_wf_final_kernel<<<pgrid, 256, 0, s>>>(a, w, sample == 0);   // the last sample's shade_b + resolve in one pass
+        if (sample == 0 && c->refl_gi_event && defer) VX_CUDA(cudaStreamWaitEvent(s, c->refl_gi_event, 0));   // ... and with `defer` here
+        if (sample + 1 < max_spp || !c->gi_fuse_final) {
+            if (defer) rf_wf_shade_b_kernel<true><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+            else rf_wf_shade_b_kernel<false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        } else {   // the last sample's shade_b + resolve in one pass
+            if (defer) rf_wf_final_kernel<true><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+            else rf_wf_final_kernel<false><<<pgrid, 256, 0, s>>>(a, w, sample == 0);
+        }
         c->launches += 5;
     }
     if (!c->gi_fuse_final) {
