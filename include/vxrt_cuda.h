@@ -192,7 +192,8 @@ int vxrt_cuda_shared_close(vxrt_ctx* ctx, void* dev_ptr);
  * destination image: device memory of this GPU, of a peer (vxrt_cuda_shared_open) or page-locked host memory. */
 int vxrt_cuda_copy_attachment_rows_async(vxrt_ctx* ctx, int32_t id, int32_t row0, int32_t rows, void* dst);
 /* the same for a rectangle (rows == 0: every row, cols == 0: every column): `dst_image` is the address of pixel (0, 0) of the
- * destination image, which has the attachment's geometry; one strided copy (cudaMemcpy2DAsync) on the copy engines. */
+ * destination image, which has the attachment's geometry; one copy on the copy engines (strided - cudaMemcpy2DAsync - for a column range,
+ * linear for whole rows). */
 int vxrt_cuda_copy_attachment_rect_async(vxrt_ctx* ctx, int32_t id, int32_t row0, int32_t rows, int32_t col0, int32_t cols, void* dst_image);
 /* makes the context's stream wait (on the device) for every copy queued so far: an event recorded on the stream afterwards
  * marks the moment the frame has left the GPU (device-side timing of the export; the host does not block). */
@@ -202,7 +203,14 @@ int vxrt_cuda_join_reads(vxrt_ctx* ctx);
  * the GI wavefront like independent draw calls do on the reference's GL queue; the reflection pass meets the GI where it first reads its SH
  * attachments (its shading; at once with derive_from_diffuse_sh).  Every other entry point first makes the context's stream wait for that
  * work, so results never depend on the option; a caller that orders its OWN work after a frame on the context's stream (an event, a kernel)
- * calls vxrt_cuda_join_passes first. */
+ * calls vxrt_cuda_join_passes first.  Refinements, each its own option, on by default, none changes a bit of any attachment:
+ *   "lane2_direct"   the direct term (reads the G-buffers and the sun shadow only) does not queue behind a pending reflection pass: it runs on
+ *                    a third stream that waits for the frame's fork point and for what the second stream held before that pass;
+ *   "refl_defer_gi"  without reproject_to_screen_space and lpv_gi the reflection pass reads the GI only as the per-pixel ambient base, which
+ *                    is then applied where a sample is accumulated (its last shading kernel), so the pass meets the GI there;
+ *   "copy_lanes"     the asynchronous copies (read_attachment_async, copy_attachment_rows / rect_async) of an attachment written by a pass
+ *                    still pending on the second / third stream wait for that stream alone, on a copy stream of its own, instead of
+ *                    joining the streams first. */
 int vxrt_cuda_join_passes(vxrt_ctx* ctx);
 /* device pointer + geometry of an attachment (valid until the pass that owns it is re-run at a
  * different size).  Used by the host side for NCCL tile gathers.                              */

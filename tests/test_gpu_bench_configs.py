@@ -111,7 +111,7 @@ def test_pass_overlap_does_not_change_a_bit(workload, reproject, inputs512):
 @pytest.mark.parametrize("refl_spp", [1, 2])
 def test_lane2_direct_deferred_reflection_gi_and_lane_copies_do_not_change_a_bit(refl_spp, inputs512):
     """The last additions to the pass-level concurrency, each behind its option (all on by default): the direct term on lane 2 beside a pending
-    reflection pass ("lane2_direct"), the reflection pass meeting the GI only where a sample is accumulated ("refl_defer_gi": Albedo and the AO
+    reflection pass ("lane2_direct"), the material G-buffer on lane 1 beside the GI's first kernels ("lane1_gbuffer"), the reflection pass meeting the GI only where a sample is accumulated ("refl_defer_gi": Albedo and the AO
     factor travel instead of the ambient product, formed later from the same operands in the same order), and read-backs of a lane-1 / lane-2
     attachment that wait for that lane alone on a second copy stream ("copy_lanes").  Every output attachment equals the single-stream frame with
     all three off, bit for bit: read synchronously after the frame, and through asynchronous copies queued right behind each pass (the bench's
@@ -125,7 +125,7 @@ def test_lane2_direct_deferred_reflection_gi_and_lane_copies_do_not_change_a_bit
         frames = (3, 4, 5)
 
         def run(overlap, lane2, defer, copy_lanes, async_copies):
-            ctx.set_option("pass_overlap", overlap); ctx.set_option("lane2_direct", lane2)
+            ctx.set_option("pass_overlap", overlap); ctx.set_option("lane2_direct", lane2 & 1); ctx.set_option("lane1_gbuffer", lane2 >> 1)
             ctx.set_option("refl_defer_gi", defer); ctx.set_option("copy_lanes", copy_lanes)
             out = []
             host = [{}, {}]
@@ -151,14 +151,16 @@ def test_lane2_direct_deferred_reflection_gi_and_lane_copies_do_not_change_a_bit
                 out.append({a: host[0][a].numpy().copy() for a in fr.outputs})
             return out
         want = run(0, 0, 0, 0, False)
-        for overlap, lane2, defer, copy_lanes, async_copies in ((0, 0, 1, 0, False), (1, 0, 0, 0, False), (1, 1, 0, 0, False), (1, 1, 1, 1, False),
-                                                                (1, 1, 1, 1, True), (1, 1, 1, 0, True), (1, 0, 1, 1, True)):
+        # lane2: bit 0 = lane2_direct, bit 1 = lane1_gbuffer
+        for overlap, lane2, defer, copy_lanes, async_copies in ((0, 0, 1, 0, False), (1, 0, 0, 0, False), (1, 1, 0, 0, False), (1, 2, 0, 0, False),
+                                                                (1, 3, 1, 1, False), (1, 3, 1, 1, True), (1, 3, 1, 0, True), (1, 2, 1, 1, True),
+                                                                (1, 1, 1, 1, True)):
             ctx.set_option("wf_bands", 2 if lane2 else 1)
             got = run(overlap, lane2, defer, copy_lanes, async_copies)
             for fw, fg in zip(want, got):
                 for a in fr.outputs:
                     assert np.array_equal(fw[a], fg[a]), (refl_spp, overlap, lane2, defer, copy_lanes, async_copies, a)
     finally:
-        for k_, v_ in (("pass_overlap", 0), ("wf_bands", 1), ("lane2_direct", 1), ("refl_defer_gi", 1), ("copy_lanes", 1)):
+        for k_, v_ in (("pass_overlap", 0), ("wf_bands", 1), ("lane2_direct", 1), ("lane1_gbuffer", 0), ("refl_defer_gi", 1), ("copy_lanes", 1)):
             ctx.set_option(k_, v_)
         ctx.close()

@@ -362,6 +362,7 @@ int vxrt_cuda_set_option(vxrt_ctx* c, const char* name, int32_t value) {
     if (!strcmp(name, "gi_overlap")) { c->gi_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "pass_overlap")) { c->pass_overlap = value != 0; return VXRT_OK; }
     if (!strcmp(name, "lane2_direct")) { c->lane2_direct = value != 0; return VXRT_OK; }
+    if (!strcmp(name, "lane1_gbuffer")) { c->lane1_gbuffer = value != 0; return VXRT_OK; }
     if (!strcmp(name, "refl_defer_gi")) { c->refl_defer_gi = value != 0; return VXRT_OK; }
     if (!strcmp(name, "copy_lanes")) { c->copy_lanes = value != 0; return VXRT_OK; }
     if (!strcmp(name, "wf_bands")) { if (value < 1 || value > 4) return vxrt_fail(VXRT_E_INVALID, "wf_bands: 1..4"); c->wf_bands = value; return VXRT_OK; }
@@ -797,12 +798,20 @@ static int require_textures(vxrt_ctx* c, const char* fn, bool need_normal) {
 }
 
 int vxrt_cuda_generate_gbuffer(vxrt_ctx* c, const vxrt_gbuffer_params* p) {
-    REQUIRE_CTX(c); REQUIRE_PTR(p);
+    // With the lanes on, lane 1 (ctx.h lane1_gbuffer): the material G-buffer is read by the reflection pass, the direct term and the filters,
+    // never by the GI, so the frame's diffuse_trace - issued next on lane 0 - need not wait for it.  Lane 1 waits for what lane 0 has
+    // queued so far (the primary pass); its later passes follow in stream order, lane 2 waits for lane 1's state before the reflection pass.
+    REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);
+    const bool on_lane1 = c->lane1_gbuffer && lanes_on(c);
+    if (!on_lane1 && (c->lane1_pending || c->lane2_pending || c->gi_fork_valid)) { if (int jrc = vxrt_join_lane1(c, false)) return jrc; }
     int rc = check_frame(__func__, p->width, p->height, p->tile);
     if (rc) return rc;
     if ((rc = require_att(c, __func__, VXRT_ATT_INITIAL_INVT, "vxrt_cuda_initial_trace"))) return rc;
     if ((rc = require_textures(c, __func__, true))) return rc;
-    return vxrt_launch_generate_gbuffer(c, *p);
+    if (!on_lane1) return vxrt_launch_generate_gbuffer(c, *p);
+    Lane1Pass lane(c);
+    if ((rc = lane.begin())) return rc;
+    return lane.end(vxrt_launch_generate_gbuffer(c, *p));
 }
 int vxrt_cuda_shade_direct(vxrt_ctx* c, const vxrt_direct_params* p) {
     REQUIRE_CTX_LANES(c); REQUIRE_PTR(p);

@@ -109,6 +109,11 @@ struct vxrt_ctx {
     // pending it goes to a stream of its own that waits for the frame's fork point and for what lane 1 held BEFORE the reflection pass
     // (lane1_pre_refl, recorded by the reflection pass's begin).  Every later lane pass and every join wait for lane 2 as well.
     bool lane2_direct = true;
+    // set_option "lane1_gbuffer" (off by default): GenerateGBuffer on lane 1.  Nothing on lane 0 reads the material G-buffer between the primary
+    // pass and the end of the GI, so the GI can start right behind the primary pass with the material fetch beside its first kernels.
+    // Bit-identical, and measured to change nothing (1.7092 vs 1.7098 ms per 1080p frame, profiles/r2_zo_ab_lanes.txt): with the lanes the
+    // frame is bound by the issue slots its instructions need, not by its dependency chain any more.
+    bool lane1_gbuffer = false;
     cudaStream_t lane2 = nullptr;
     cudaEvent_t lane1_pre_refl = nullptr, lane2_tail = nullptr;
     bool lane1_pre_refl_valid = false, lane2_pending = false;
